@@ -1,0 +1,168 @@
+/*
+ * mlg_b200.h -- C ABI of libmlg_b200.so: hand-written sm_100a kernels for the message-passing and
+ * cross-level pooling hot path of Y-Claw/Multilevel-GNN.
+ *
+ * The reference has no FFI / plugin table of its own (pure Python on torch_geometric /
+ * torch_scatter / ATen): every entry point below replaces a chain of third-party
+ * kernels reached from the cited reference call site, and is what a maintainer would bind (ctypes,
+ * see INTEGRATION.md) from the reference's own nn.Module methods.
+ *
+ * Conventions
+ *   - all pointers are DEVICE pointers on the current CUDA device unless stated otherwise;
+ *     the caller allocates every output and workspace; nothing is allocated or freed inside;
+ *   - float = fp32, row-major, contiguous; node/edge ids inside kernels are int32;
+ *   - `stream` is a cudaStream_t passed as void*; calls only enqueue work (no host sync),
+ *     are re-entrant across streams/devices and safe under CUDA-graph capture
+ *     (except where a function says it synchronises);
+ *   - return value 0 = ok, negative = error (MLG_ERR_*); mlg_last_error() gives a thread-local text.
+ */
+#ifndef MLG_B200_H
+#define MLG_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MLG_ABI_VERSION 1
+
+/* aggregation modes of GenMessagePassing.aggregate (models/gcn_lib/sparse/torch_message.py:44-85) */
+#define MLG_AGGR_SOFTMAX 0 /* softmax, softmax_sg (learn_t=0), softmax_sum (y_dev != NULL) */
+#define MLG_AGGR_POWER 1   /* power, power_sum (y_dev != NULL) */
+#define MLG_AGGR_ADD 2
+#define MLG_AGGR_MEAN 3
+#define MLG_AGGR_MAX 4
+
+/* epilogues of GENConv.forward (models/gcn_lib/sparse/torch_vertex.py:86-89) */
+#define MLG_EPI_NONE 0     /* only the aggregated message m */
+#define MLG_EPI_RESIDUAL 1 /* h = x + m */
+#define MLG_EPI_MSGNORM 2  /* h = x + msg_scale * ||x||_2 * m / max(||m||_2, 1e-12) (torch_message.py:175-179) */
+
+int mlg_abi_version(void);
+const char* mlg_last_error(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * CSR construction.  Replaces per-forward remove_self_loops/add_self_loops
+ * (torch_vertex.py:272-273) and the implicit index broadcast inside torch_scatter.
+ *
+ * edge_index: int64 [2, E] (row 0 = source j, row 1 = target i).  Builds the target-sorted CSR
+ *   rowptr int32 [n_rows+1], col int32 [cap] (source of each entry), eid int32 [cap]
+ *   (index of the entry's original edge, -1 for an added self loop), cap = E + (add_self ? n_rows : 0).
+ * Entries of a row keep original edge order (stable), added self loops come last.
+ * With by_source != 0 the roles of the two rows are swapped (CSR of the reversed graph: rows =
+ * sources, col = targets) -- that is the structure the backward passes traverse.
+ * drop_self removes i==j edges; the number of valid entries is rowptr[n_rows] (stays on device).
+ * workspace: at least mlg_csr_build_workspace_bytes(E, n_rows, add_self) bytes.
+ */
+int64_t mlg_csr_build_workspace_bytes(int64_t n_edges, int64_t n_rows, int add_self);
+int mlg_csr_build(const int64_t* edge_index, int64_t n_edges, int64_t n_rows, int by_source,
+                  int drop_self, int add_self, int32_t* rowptr, int32_t* col, int32_t* eid,
+                  void* workspace, int64_t workspace_bytes, void* stream);
+
+/* val[q] = eid[q] >= 0 ? edge_attr[eid[q]] : fill   for q < rowptr[n_rows] (edge weights in CSR order;
+ * add_self_loops fills new loops with 1.0). */
+int mlg_edge_values(const float* edge_attr, const int32_t* eid, const int32_t* rowptr, int64_t n_rows,
+                    int64_t cap, float fill, float* val, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * GENConv message + aggregation + MsgNorm/residual epilogue, forward.
+ * Replaces GENConv.message (torch_vertex.py:94-101), GenMessagePassing.aggregate
+ * (torch_message.py:44-85), MsgNorm.forward (torch_message.py:175-179) and `h = x + m`
+ * (torch_vertex.py:89):
+ *     msg_e = relu(x[col] + e[eid]) + eps            (e may be NULL)
+ *     msg_e = e[eid]                                 when x == NULL: messages given directly, the
+ *                                                    GenMessagePassing.aggregate(inputs, index) drop-in
+ *     m_i   = AGGR_{e -> i} msg_e                    per channel, one pass, online softmax
+ *     h_i   = epilogue(x_i, m_i)
+ * x [n, H]; e [E, H] indexed by eid[q] (or by q when eid == NULL); t/p/y: device scalars when the
+ * *_dev pointer is non-NULL (learnable Parameters), else the host value; y_dev != NULL multiplies
+ * the result by deg^sigmoid(y) (softmax_sum / power_sum).
+ * Outputs: m [n,H]; aux [n,H] (may be NULL for inference: softmax -> log2-sum-exp of t*msg*log2(e),
+ * power -> the un-clamped mean); h [n,H] (NULL iff epilogue == MLG_EPI_NONE).
+ */
+int mlg_gen_aggr_fwd(const float* x, const float* e, const int32_t* rowptr, const int32_t* col,
+                     const int32_t* eid, int64_t n, int64_t H, int mode, float t, const float* t_dev,
+                     float p, const float* p_dev, const float* y_dev, float eps, int epilogue,
+                     const float* msg_scale_dev, float* m, float* aux, float* h, void* stream);
+
+/* number of float4 partial-sum rows mlg_gen_aggr_bwd writes (one per thread block) */
+int64_t mlg_gen_aggr_bwd_partial_rows(int64_t n, int64_t H);
+
+/* Backward of the above (autograd of the same reference lines; closed forms in SURVEY.md App. B).
+ * g [n,H]: gradient w.r.t. h (or w.r.t. m when epilogue == MLG_EPI_NONE).
+ * Writes g_edge[eid[q]] (or [q]) = d/d(pre-activation of edge q) for every entry  -- this IS the
+ * gradient of e, and the rows the source-side pass (mlg_gather_sum over the by-source CSR) sums into
+ * g_x; writes g_x [n,H] = the direct (residual / MsgNorm) term, zeros for MLG_EPI_NONE;
+ * partials [rows,4] per block: (dL/dt or dL/dp, dL/dy_raw, dL/dmsg_scale, 0).
+ * learn != 0: gradients flow through the softmax weights (learn_t) / to p (learn_p).
+ */
+int mlg_gen_aggr_bwd(const float* g, const float* x, const float* e, const int32_t* rowptr,
+                     const int32_t* col, const int32_t* eid, int64_t n, int64_t H, int mode, int learn,
+                     float t, const float* t_dev, float p, const float* p_dev, const float* y_dev,
+                     float eps, int epilogue, const float* msg_scale_dev, const float* m,
+                     const float* aux, float* g_edge, float* g_x, float* partials, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Weighted segment gather-sum (CSR SpMM with feature rows):
+ *     out_i = post_i * ( sum_{q in row i} val[q] * pre[idx[q]] * src[idx[q] % src_mod] )  (+ out_i if accumulate)
+ *     relative != 0:  out_i -= src_i * (post_mode==mean ? 1 : cnt_i)      (RSAGE x_j*w - x_i)
+ * val NULL = 1, pre NULL = 1, src_mod 0 = no modulo; post_mode 0: post_i = 1, 1: post_i = 1/cnt_i
+ * (cnt_i = row length, PyG mean aggregation incl. the self loop), 2: post_i = post[i].
+ * Forward use: SAGEConv mean aggregation of w_ij * x_j (torch_vertex.py:279-286 + PyG mean), done
+ * BEFORE the lin_r GEMM (algebraically identical).  Backward use: the same call on
+ * the by-source CSR.  Also the source-side pass of mlg_gen_aggr_bwd.
+ */
+int mlg_gather_sum(const float* src, const int32_t* rowptr, const int32_t* idx, const float* val,
+                   const float* pre, const float* post, int64_t n_rows, int64_t C, int64_t src_mod,
+                   int post_mode, int relative, int accumulate, float* out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * MultilevelGNN prologue: x0[b*N+n, :] = xs[b*N+n] * emb[n, :]   (models/multilevel_gnn.py:150-151)
+ * and its backward g_emb[n,:] = sum_b xs[b,n] * g_x0[b,n,:].
+ */
+int mlg_embed_scale_fwd(const float* xs, const float* emb, int64_t B, int64_t N, int64_t C, float* out,
+                        void* stream);
+int mlg_embed_scale_bwd(const float* xs, const float* g_out, int64_t B, int64_t N, int64_t C,
+                        float* g_emb, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Gene -> pathway pool (models/multilevel_gnn.py:205-239): value mask, gather by gene_pca_match,
+ * missing-gene mask, per-gene projection, segment sum -- without materialising [B,C,G,P].
+ *     out[b,c,s,p] = sum_{g in seg(b,s)} vm[node] * x[node, c] * w[g,p],  node = b*N + match[b,g] (skipped if < 0)
+ * seg_rowptr int32 [B*S+1], seg_slot int32 [B*G] : CSR of slots (b*G+g) grouped by (b*S + raw_indice[b,g])
+ *   (built with mlg_csr_build on edge_index = [slot; segment]).
+ * x [B*N, C]; vm [B*N] or NULL (value_att_mask multiplier, batch.x); match int64 [B,G];
+ * w [G,P] = learnable_pca_params * info_mask (caller multiplies, G*P elements);
+ * out [B, C, S, P] (== reference's [B, C, 146, 3P] after its reshape).
+ * wrap_negative != 0 reproduces python negative indexing when pca_match_mask is False.
+ */
+int mlg_pool_fwd(const float* x, const float* vm, const int64_t* match, const float* w,
+                 const int32_t* seg_rowptr, const int32_t* seg_slot, int64_t B, int64_t N, int64_t C,
+                 int64_t G, int64_t S, int64_t P, int wrap_negative, float* out, void* stream);
+
+/* Backward: g_x [B*N, C] via the node-side CSR (node_rowptr [B*N+1], node_slot [B*G]: slots grouped by
+ * node id, built with mlg_csr_build on [slot; node]); seg_of_slot int32 [B*G] = b*S + raw_indice[b,g];
+ * g_w [G,P] (gradient w.r.t. the masked product w; caller multiplies by info_mask).
+ * g_out_cl is the gradient of `out` permuted to channel-last [B, S, P, C] (coalesced reads over c). */
+int mlg_pool_bwd_x(const float* g_out_cl, const float* vm, const float* w, const int32_t* node_rowptr,
+                   const int32_t* node_slot, const int32_t* seg_of_slot, int64_t B, int64_t N, int64_t C,
+                   int64_t G, int64_t S, int64_t P, float* g_x, void* stream);
+int mlg_pool_bwd_w(const float* g_out_cl, const float* x, const float* vm, const int64_t* match,
+                   const int64_t* raw_indice, int64_t B, int64_t N, int64_t C, int64_t G, int64_t S,
+                   int64_t P, int wrap_negative, float* g_w, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Dilated kNN graph (models/gcn_lib/sparse/torch_edge.py:53-104, dense/torch_edge.py:32-58):
+ * fp32 distance d_ij = (|x_i|^2 + (-2 x_i.x_j)) + |x_j|^2, k*dilation nearest per point (self
+ * included), ascending distance, ties by lowest index; every dilation-th rank is kept.
+ * x [B, N, D]; out_nbr / out_ctr int64 [B*N*k] with per-graph node offsets (sparse layout, offset != 0)
+ * or without (dense layout).  out_dist [B*N*k] optional (NULL ok).  workspace: >= B*N*4 bytes (squared norms).
+ */
+int mlg_knn_graph(const float* x, int64_t B, int64_t N, int64_t D, int64_t k, int64_t dilation,
+                  int add_offset, int64_t* out_nbr, int64_t* out_ctr, float* out_dist, void* workspace,
+                  int64_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MLG_B200_H */

@@ -1,0 +1,111 @@
+"""ctypes binding of libmlg_b200.so (include/mlg_b200.h).
+
+This is the only place the product touches native code.  There is NO CPU fallback: if the library
+is missing, cannot be loaded, or a tensor is not a contiguous CUDA tensor of the expected dtype, the
+call raises.  Every wrapper only enqueues work on ``torch.cuda.current_stream()``.
+"""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libmlg_b200.so")
+
+_c_i64, _c_int, _c_f32, _c_vp = ctypes.c_int64, ctypes.c_int, ctypes.c_float, ctypes.c_void_p
+
+# name -> (restype, argtypes); mirrors include/mlg_b200.h one to one
+_SIGNATURES = {
+    "mlg_abi_version": (_c_int, []),
+    "mlg_last_error": (ctypes.c_char_p, []),
+    "mlg_csr_build_workspace_bytes": (_c_i64, [_c_i64, _c_i64, _c_int]),
+    "mlg_csr_build": (_c_int, [_c_vp, _c_i64, _c_i64, _c_int, _c_int, _c_int, _c_vp, _c_vp, _c_vp, _c_vp,
+                               _c_i64, _c_vp]),
+    "mlg_edge_values": (_c_int, [_c_vp, _c_vp, _c_vp, _c_i64, _c_i64, _c_f32, _c_vp, _c_vp]),
+    "mlg_gen_aggr_fwd": (_c_int, [_c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_i64, _c_i64, _c_int, _c_f32, _c_vp,
+                                  _c_f32, _c_vp, _c_vp, _c_f32, _c_int, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp]),
+    "mlg_gen_aggr_bwd_partial_rows": (_c_i64, [_c_i64, _c_i64]),
+    "mlg_gen_aggr_bwd": (_c_int, [_c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_i64, _c_i64, _c_int, _c_int,
+                                  _c_f32, _c_vp, _c_f32, _c_vp, _c_vp, _c_f32, _c_int, _c_vp, _c_vp, _c_vp,
+                                  _c_vp, _c_vp, _c_vp, _c_vp]),
+    "mlg_gather_sum": (_c_int, [_c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_i64, _c_i64, _c_i64, _c_int,
+                                _c_int, _c_int, _c_vp, _c_vp]),
+    "mlg_embed_scale_fwd": (_c_int, [_c_vp, _c_vp, _c_i64, _c_i64, _c_i64, _c_vp, _c_vp]),
+    "mlg_embed_scale_bwd": (_c_int, [_c_vp, _c_vp, _c_i64, _c_i64, _c_i64, _c_vp, _c_vp]),
+    "mlg_pool_fwd": (_c_int, [_c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_i64, _c_i64, _c_i64, _c_i64, _c_i64,
+                              _c_i64, _c_int, _c_vp, _c_vp]),
+    "mlg_pool_bwd_x": (_c_int, [_c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_i64, _c_i64, _c_i64, _c_i64,
+                                _c_i64, _c_i64, _c_vp, _c_vp]),
+    "mlg_pool_bwd_w": (_c_int, [_c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_i64, _c_i64, _c_i64, _c_i64, _c_i64,
+                                _c_i64, _c_int, _c_vp, _c_vp]),
+    "mlg_knn_graph": (_c_int, [_c_vp, _c_i64, _c_i64, _c_i64, _c_i64, _c_i64, _c_int, _c_vp, _c_vp, _c_vp, _c_vp,
+                               _c_i64, _c_vp]),
+}
+
+_lib = None
+
+
+class NativeLibraryError(RuntimeError):
+    pass
+
+
+def exported_symbols():
+    return sorted(_SIGNATURES)
+
+
+def lib():
+    """Loads libmlg_b200.so once; raises NativeLibraryError when it is absent (no fallback)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise NativeLibraryError(
+                "%s not found: build it with `python multilevel-gnn_b200/build.py` "
+                "(or __graft_entry__.build()); there is no CPU fallback" % LIB_PATH)
+        handle = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(handle, name)
+            fn.restype, fn.argtypes = res, args
+        if handle.mlg_abi_version() != 1:
+            raise NativeLibraryError("libmlg_b200.so ABI version mismatch")
+        _lib = handle
+    return _lib
+
+
+def last_error():
+    return lib().mlg_last_error().decode()
+
+
+def check(rc, who):
+    if rc != 0:
+        raise RuntimeError("%s failed (%d): %s" % (who, rc, last_error()))
+
+
+def stream_ptr():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def ptr(t, dtype=None, allow_none=False):
+    """Device pointer of a contiguous CUDA tensor (or NULL)."""
+    if t is None:
+        if allow_none:
+            return None
+        raise ValueError("required tensor is None")
+    if not t.is_cuda:
+        raise NativeLibraryError("multilevel-gnn_b200 kernels need CUDA tensors (got %s); no CPU fallback" % t.device)
+    if dtype is not None and t.dtype != dtype:
+        raise TypeError("expected %s, got %s" % (dtype, t.dtype))
+    if not t.is_contiguous():
+        raise ValueError("tensor must be contiguous")
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def fptr(t, allow_none=False):
+    return ptr(t, torch.float32, allow_none)
+
+
+def iptr(t, allow_none=False):
+    return ptr(t, torch.int32, allow_none)
+
+
+def lptr(t, allow_none=False):
+    return ptr(t, torch.int64, allow_none)

@@ -1,0 +1,207 @@
+// Gene -> pathway cross-level pool of MultilevelGNN, forward and backward (sm_100a).
+//
+// Replaces models/multilevel_gnn.py:205-239: value mask (x * batch.x), gather by gene_pca_match,
+// missing-gene mask, repeat(P) * (learnable_pca_params * info_mask), permute and
+// scatter_reduce(sum) over raw_indice.  The reference materialises [B,C,G,P] fp32 plus an int64 index of
+// the same shape (205 MB + 410 MB at the gbm shape) and scatters with atomics; here one warp owns one
+// (graph, segment) output row and walks its gene slots, so nothing is materialised and the sum order
+// is fixed.  HBM-bound: algorithmic bytes = 4*C*B*N + 4*B*N + 12*G + 4*B*C*S*P  (SURVEY.md section 8d).
+#include "common.cuh"
+#include "../../include/mlg_b200.h"
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kMaxP = 8;
+
+// out[b, c, s, p] = sum_{slot in seg row (b,s)} vm[node] * x[node, c] * w[g, p]
+template <int P_>
+__global__ void __launch_bounds__(kThreads)
+pool_fwd_kernel(const float* __restrict__ x, const float* __restrict__ vm, const long long* __restrict__ match,
+                const float* __restrict__ w, const int* __restrict__ rowptr, const int* __restrict__ slots,
+                int B, int N, int C, int G, int S, int wrap, float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  if (row >= (long long)B * S) return;
+  const int b = (int)(row / S), s = (int)(row % S);
+  const int beg = __ldg(rowptr + row), end = __ldg(rowptr + row + 1);
+  const long long BN = (long long)B * N;
+  for (int c0 = 0; c0 < C; c0 += 32) {
+    const int c = c0 + lane;
+    const bool cok = c < C;
+    float acc[P_];
+#pragma unroll
+    for (int p = 0; p < P_; ++p) acc[p] = 0.f;
+    for (int base = beg; base < end; base += 32) {
+      const int q = min(base + lane, end - 1);
+      const int slot = __ldg(slots + q);
+      const int g = slot % G;
+      long long node = __ldg(match + slot);
+      float scale = 1.f;
+      if (node < 0) {
+        if (wrap) node = ((long long)(slot / G) * N + node + BN) % BN;  // python negative index
+        else { node = 0; scale = 0.f; }
+      } else {
+        node += (long long)(slot / G) * N;
+      }
+      if (vm) scale *= __ldg(vm + node);
+      float wl[P_];
+#pragma unroll
+      for (int p = 0; p < P_; ++p) wl[p] = scale * __ldg(w + (size_t)g * P_ + p);
+      const int cnt = min(32, end - base);
+      for (int j = 0; j < cnt; ++j) {
+        const long long nj = __shfl_sync(0xffffffffu, node, j);
+        const float xv = cok ? __ldg(x + (size_t)nj * C + c) : 0.f;
+#pragma unroll
+        for (int p = 0; p < P_; ++p) acc[p] = fmaf(xv, __shfl_sync(0xffffffffu, wl[p], j), acc[p]);
+      }
+    }
+    if (cok) {
+      float* o = out + (((size_t)b * C + c) * S + s) * P_;
+#pragma unroll
+      for (int p = 0; p < P_; ++p) o[p] = acc[p];
+    }
+  }
+}
+
+// g_x[node, c] = vm[node] * sum_{slot -> node} sum_p w[g,p] * g_cl[b, seg, p, c]
+template <int P_>
+__global__ void __launch_bounds__(kThreads)
+pool_bwd_x_kernel(const float* __restrict__ g_cl, const float* __restrict__ vm, const float* __restrict__ w,
+                  const int* __restrict__ rowptr, const int* __restrict__ slots,
+                  const int* __restrict__ seg_of_slot, long long BN, int C, int G, float* __restrict__ g_x) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  if (row >= BN) return;
+  const int beg = __ldg(rowptr + row), end = __ldg(rowptr + row + 1);
+  const float scale = vm ? __ldg(vm + row) : 1.f;
+  for (int c0 = 0; c0 < C; c0 += 32) {
+    const int c = c0 + lane;
+    const bool cok = c < C;
+    float acc = 0.f;
+    for (int base = beg; base < end; base += 32) {
+      const int q = min(base + lane, end - 1);
+      const int slot = __ldg(slots + q);
+      const int g = slot % G;
+      const int seg = __ldg(seg_of_slot + slot);  // b*S + s
+      float wl[P_];
+#pragma unroll
+      for (int p = 0; p < P_; ++p) wl[p] = __ldg(w + (size_t)g * P_ + p);
+      const int cnt = min(32, end - base);
+      for (int j = 0; j < cnt; ++j) {
+        const int sj = __shfl_sync(0xffffffffu, seg, j);
+        const float* gp = g_cl + (size_t)sj * P_ * C + c;
+#pragma unroll
+        for (int p = 0; p < P_; ++p) {
+          const float gv = cok ? __ldg(gp + (size_t)p * C) : 0.f;
+          acc = fmaf(gv, __shfl_sync(0xffffffffu, wl[p], j), acc);
+        }
+      }
+    }
+    if (cok) g_x[(size_t)row * C + c] = acc * scale;
+  }
+}
+
+// g_w[g, p] = sum_b sum_c vm[node] * x[node, c] * g_cl[b, seg(b,g), p, c]
+template <int P_>
+__global__ void __launch_bounds__(kThreads)
+pool_bwd_w_kernel(const float* __restrict__ g_cl, const float* __restrict__ x, const float* __restrict__ vm,
+                  const long long* __restrict__ match, const long long* __restrict__ raw_indice, int B, int N,
+                  int C, int G, int S, int wrap, float* __restrict__ g_w) {
+  const int lane = threadIdx.x & 31;
+  const long long g = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  if (g >= G) return;
+  const long long BN = (long long)B * N;
+  float acc[P_];
+#pragma unroll
+  for (int p = 0; p < P_; ++p) acc[p] = 0.f;
+  for (int b = 0; b < B; ++b) {
+    long long node = __ldg(match + (size_t)b * G + g);
+    float scale = 1.f;
+    if (node < 0) {
+      if (!wrap) continue;
+      node = ((long long)b * N + node + BN) % BN;
+    } else {
+      node += (long long)b * N;
+    }
+    if (vm) scale = __ldg(vm + node);
+    const long long seg = (long long)b * S + __ldg(raw_indice + (size_t)b * G + g);
+    for (int c = lane; c < C; c += 32) {
+      const float xv = scale * __ldg(x + (size_t)node * C + c);
+#pragma unroll
+      for (int p = 0; p < P_; ++p) acc[p] = fmaf(xv, __ldg(g_cl + ((size_t)seg * P_ + p) * C + c), acc[p]);
+    }
+  }
+#pragma unroll
+  for (int p = 0; p < P_; ++p) acc[p] = warp_sum(acc[p]);
+  if (lane == 0) {
+#pragma unroll
+    for (int p = 0; p < P_; ++p) g_w[(size_t)g * P_ + p] = acc[p];
+  }
+}
+
+#define MLG_P_SWITCH(P, CALL)                                           \
+  switch (P) {                                                          \
+    case 1: { constexpr int P_ = 1; CALL; } break;                      \
+    case 2: { constexpr int P_ = 2; CALL; } break;                      \
+    case 3: { constexpr int P_ = 3; CALL; } break;                      \
+    case 4: { constexpr int P_ = 4; CALL; } break;                      \
+    case 5: { constexpr int P_ = 5; CALL; } break;                      \
+    case 6: { constexpr int P_ = 6; CALL; } break;                      \
+    case 7: { constexpr int P_ = 7; CALL; } break;                      \
+    case 8: { constexpr int P_ = 8; CALL; } break;                      \
+    default: break;                                                     \
+  }
+
+int check_dims(const char* who, int64_t B, int64_t N, int64_t C, int64_t G, int64_t S, int64_t P) {
+  MLG_CHECK_ARG(B > 0 && N > 0 && C > 0 && G > 0 && S > 0, "%s: non-positive size", who);
+  MLG_CHECK_ARG(P >= 1 && P <= kMaxP, "%s: pca_dim P=%lld outside [1,%d]", who, (long long)P, kMaxP);
+  MLG_CHECK_ARG(B * N < (1ll << 31) && B * G < (1ll << 31) && B * S < (1ll << 31), "%s: sizes exceed int32", who);
+  return MLG_OK;
+}
+
+}  // namespace
+
+extern "C" int mlg_pool_fwd(const float* x, const float* vm, const int64_t* match, const float* w,
+                            const int32_t* seg_rowptr, const int32_t* seg_slot, int64_t B, int64_t N,
+                            int64_t C, int64_t G, int64_t S, int64_t P, int wrap_negative, float* out,
+                            void* stream) {
+  MLG_CHECK_ARG(x && match && w && seg_rowptr && seg_slot && out, "mlg_pool_fwd: null pointer");
+  int rc = check_dims("mlg_pool_fwd", B, N, C, G, S, P);
+  if (rc) return rc;
+  const int grid = mlg_ceil_div(B * S, kThreads / 32);
+  MLG_P_SWITCH(P, (pool_fwd_kernel<P_><<<grid, kThreads, 0, (cudaStream_t)stream>>>(
+                      x, vm, (const long long*)match, w, seg_rowptr, seg_slot, (int)B, (int)N, (int)C, (int)G,
+                      (int)S, wrap_negative, out)));
+  MLG_CHECK_LAUNCH("mlg_pool_fwd");
+  return MLG_OK;
+}
+
+extern "C" int mlg_pool_bwd_x(const float* g_out_cl, const float* vm, const float* w,
+                              const int32_t* node_rowptr, const int32_t* node_slot,
+                              const int32_t* seg_of_slot, int64_t B, int64_t N, int64_t C, int64_t G,
+                              int64_t S, int64_t P, float* g_x, void* stream) {
+  MLG_CHECK_ARG(g_out_cl && w && node_rowptr && node_slot && seg_of_slot && g_x, "mlg_pool_bwd_x: null pointer");
+  int rc = check_dims("mlg_pool_bwd_x", B, N, C, G, S, P);
+  if (rc) return rc;
+  const int grid = mlg_ceil_div(B * N, kThreads / 32);
+  MLG_P_SWITCH(P, (pool_bwd_x_kernel<P_><<<grid, kThreads, 0, (cudaStream_t)stream>>>(
+                      g_out_cl, vm, w, node_rowptr, node_slot, seg_of_slot, (long long)(B * N), (int)C, (int)G,
+                      g_x)));
+  MLG_CHECK_LAUNCH("mlg_pool_bwd_x");
+  return MLG_OK;
+}
+
+extern "C" int mlg_pool_bwd_w(const float* g_out_cl, const float* x, const float* vm, const int64_t* match,
+                              const int64_t* raw_indice, int64_t B, int64_t N, int64_t C, int64_t G,
+                              int64_t S, int64_t P, int wrap_negative, float* g_w, void* stream) {
+  MLG_CHECK_ARG(g_out_cl && x && match && raw_indice && g_w, "mlg_pool_bwd_w: null pointer");
+  int rc = check_dims("mlg_pool_bwd_w", B, N, C, G, S, P);
+  if (rc) return rc;
+  const int grid = mlg_ceil_div(G, kThreads / 32);
+  MLG_P_SWITCH(P, (pool_bwd_w_kernel<P_><<<grid, kThreads, 0, (cudaStream_t)stream>>>(
+                      g_out_cl, x, vm, (const long long*)match, (const long long*)raw_indice, (int)B, (int)N,
+                      (int)C, (int)G, (int)S, wrap_negative, g_w)));
+  MLG_CHECK_LAUNCH("mlg_pool_bwd_w");
+  return MLG_OK;
+}

@@ -1,0 +1,230 @@
+"""torch.autograd Functions over the C ABI (forward AND backward are hand-written kernels).
+
+Each Function cites the reference lines whose autograd graph it replaces.  Tensors are allocated by
+torch, the kernels only fill them (include/mlg_b200.h conventions).
+"""
+import torch
+
+from . import _cabi
+
+AGGR_CODE = {"softmax": 0, "softmax_sg": 0, "softmax_sum": 0, "power": 1, "power_sum": 1,
+             "add": 2, "sum": 2, "mean": 3, "max": 4}
+EPI_NONE, EPI_RESIDUAL, EPI_MSGNORM = 0, 1, 2
+
+
+def _f32c(t):
+    return t.contiguous() if t.dtype == torch.float32 else t.float().contiguous()
+
+
+def _scalar_args(v):
+    """(host float, device pointer or None) for a python float or a 1-element Parameter."""
+    if torch.is_tensor(v):
+        return 0.0, _cabi.fptr(v.detach().reshape(1))
+    return float(v), None
+
+
+def gather_sum(src, rowptr, idx, n_rows, val=None, pre=None, post=None, src_mod=0, post_mode=0,
+               relative=False, out=None, accumulate=False):
+    """Raw (non-differentiable) call of mlg_gather_sum."""
+    L = _cabi.lib()
+    C = src.shape[1]
+    if out is None:
+        out = torch.empty(n_rows, C, dtype=torch.float32, device=src.device)
+    with torch.cuda.device(src.device):
+        _cabi.check(L.mlg_gather_sum(_cabi.fptr(src), _cabi.iptr(rowptr), _cabi.iptr(idx),
+                                     _cabi.fptr(val, True), _cabi.fptr(pre, True), _cabi.fptr(post, True),
+                                     n_rows, C, src_mod, post_mode, int(relative), int(accumulate),
+                                     _cabi.fptr(out), _cabi.stream_ptr()), "mlg_gather_sum")
+    return out
+
+
+class GenAggregate(torch.autograd.Function):
+    """GENConv.message + GenMessagePassing.aggregate + MsgNorm + residual
+    (models/gcn_lib/sparse/torch_vertex.py:82-89,94-101; torch_message.py:44-85,175-179).
+
+    forward(x, e, t, p, y, msg_scale, topo, aggr, eps, epilogue, learn) -> h (or m for EPI_NONE)
+      x [N,H] (None = raw messages in e), e [E,H] or None, t/p: float or Parameter[1],
+      y / msg_scale: Parameter[1] or None, topo: graph.Topology without self-loop rewrite.
+    """
+
+    @staticmethod
+    def forward(ctx, x, e, t, p, y, msg_scale, topo, aggr, eps, epilogue, learn):
+        L = _cabi.lib()
+        ref = x if x is not None else e
+        n, H = topo.n, ref.shape[1]
+        xd = None if x is None else _f32c(x.detach())
+        ed = None if e is None else _f32c(e.detach())
+        csr = topo.fwd
+        mode = AGGR_CODE[aggr]
+        t_h, t_d = _scalar_args(t)
+        p_h, p_d = _scalar_args(p)
+        y_d = None if y is None else _cabi.fptr(y.detach().reshape(1))
+        s_d = None if msg_scale is None else _cabi.fptr(msg_scale.detach().reshape(1))
+        need_grad = any(torch.is_tensor(v) and v.requires_grad for v in (x, e, t, p, y, msg_scale))
+        m = torch.empty(n, H, dtype=torch.float32, device=ref.device)
+        aux = torch.empty_like(m) if (need_grad and mode in (0, 1)) else None
+        h = torch.empty_like(m) if epilogue != EPI_NONE else None
+        with torch.cuda.device(ref.device):
+            _cabi.check(L.mlg_gen_aggr_fwd(
+                _cabi.fptr(xd, True), _cabi.fptr(ed, True), _cabi.iptr(csr.rowptr), _cabi.iptr(csr.col),
+                _cabi.iptr(csr.eid), n, H, mode, t_h, t_d, p_h, p_d, y_d, float(eps), epilogue, s_d,
+                _cabi.fptr(m), _cabi.fptr(aux, True), _cabi.fptr(h, True), _cabi.stream_ptr()),
+                "mlg_gen_aggr_fwd")
+        ctx.topo, ctx.mode, ctx.eps, ctx.epilogue, ctx.learn = topo, mode, float(eps), epilogue, bool(learn)
+        ctx.t, ctx.p, ctx.y, ctx.scale = t, p, y, msg_scale
+        ctx.has_x, ctx.has_e = x is not None, e is not None
+        ctx.e_shape = None if e is None else e.shape
+        ctx.save_for_backward(*[v for v in (xd, ed, m, aux) if v is not None])
+        ctx.saved_flags = (xd is not None, ed is not None, aux is not None)
+        return h if h is not None else m
+
+    @staticmethod
+    def backward(ctx, g):
+        L = _cabi.lib()
+        saved = list(ctx.saved_tensors)
+        fx, fe, fa = ctx.saved_flags
+        xd = saved.pop(0) if fx else None
+        ed = saved.pop(0) if fe else None
+        m = saved.pop(0)
+        aux = saved.pop(0) if fa else None
+        topo = ctx.topo
+        n, H = m.shape
+        g = _f32c(g)
+        dev = m.device
+        csr = topo.fwd
+        n_edges = topo.edge_index.shape[1]
+        t_h, t_d = _scalar_args(ctx.t)
+        p_h, p_d = _scalar_args(ctx.p)
+        y_d = None if ctx.y is None else _cabi.fptr(ctx.y.detach().reshape(1))
+        s_d = None if ctx.scale is None else _cabi.fptr(ctx.scale.detach().reshape(1))
+        g_edge = torch.empty(max(n_edges, 1), H, dtype=torch.float32, device=dev)
+        g_x = torch.empty(n, H, dtype=torch.float32, device=dev)
+        rows = L.mlg_gen_aggr_bwd_partial_rows(n, H)
+        partials = torch.empty(rows, 4, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            _cabi.check(L.mlg_gen_aggr_bwd(
+                _cabi.fptr(g), _cabi.fptr(xd, True), _cabi.fptr(ed, True), _cabi.iptr(csr.rowptr),
+                _cabi.iptr(csr.col), _cabi.iptr(csr.eid), n, H, ctx.mode, int(ctx.learn), t_h, t_d, p_h, p_d,
+                y_d, ctx.eps, ctx.epilogue, s_d, _cabi.fptr(m), _cabi.fptr(aux, True), _cabi.fptr(g_edge),
+                _cabi.fptr(g_x), _cabi.fptr(partials), _cabi.stream_ptr()), "mlg_gen_aggr_bwd")
+        needs = ctx.needs_input_grad
+        gx = None
+        if ctx.has_x and needs[0]:
+            bw = topo.bwd      # rows = sources; eid = edge ids whose g_edge rows are summed
+            gx = gather_sum(g_edge, bw.rowptr, bw.eid, n, out=g_x, accumulate=True)
+        ge = g_edge[:n_edges].reshape(ctx.e_shape) if (ctx.has_e and needs[1]) else None
+        sums = None
+
+        def part(i):
+            nonlocal sums
+            if sums is None:
+                sums = partials.sum(dim=0)
+            return sums[i].reshape(1)
+
+        gt = part(0).reshape(ctx.t.shape) if (torch.is_tensor(ctx.t) and needs[2] and ctx.mode == 0 and ctx.learn) else None
+        gp = part(0).reshape(ctx.p.shape) if (torch.is_tensor(ctx.p) and needs[3] and ctx.mode == 1 and ctx.learn) else None
+        gy = part(1).reshape(ctx.y.shape) if (ctx.y is not None and needs[4]) else None
+        gs = part(2).reshape(ctx.scale.shape) if (ctx.scale is not None and needs[5] and ctx.epilogue == EPI_MSGNORM) else None
+        return gx, ge, gt, gp, gy, gs, None, None, None, None, None
+
+
+class SageAggregate(torch.autograd.Function):
+    """Weighted mean over in-neighbours incl. the rewritten self loop, BEFORE the lin_r transform:
+    agg_i = (sum_{j->i, j!=i} w_ij x_j + x_i) / (deg_i + 1)   [- x_i for RSAGE]
+    (SAGEConv.forward/message + PyG mean aggregation, models/gcn_lib/sparse/torch_vertex.py:269-286)."""
+
+    @staticmethod
+    def forward(ctx, x, topo, relative):
+        xd = _f32c(x.detach())
+        csr = topo.fwd
+        out = gather_sum(xd, csr.rowptr, csr.col, topo.n, val=topo.fwd_val, post_mode=1, relative=relative)
+        ctx.topo, ctx.relative = topo, bool(relative)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        topo = ctx.topo
+        g = _f32c(g)
+        bw = topo.bwd
+        # g_x[j] = sum_{i: j->i} w_ij * g[i] / cnt_i   (entries of the by-source CSR: col = target i)
+        gx = gather_sum(g, bw.rowptr, bw.col, topo.n, val=topo.bwd_val, pre=topo.inv_cnt)
+        if ctx.relative:
+            gx = gx - g
+        return gx, None, None
+
+
+class EmbedScale(torch.autograd.Function):
+    """x0[b*N+n,:] = x[b*N+n] * node_embedding[n,:]   (models/multilevel_gnn.py:150-151)."""
+
+    @staticmethod
+    def forward(ctx, xs, emb):
+        L = _cabi.lib()
+        N, C = emb.shape
+        xs_d = _f32c(xs.detach().reshape(-1))
+        emb_d = _f32c(emb.detach())
+        B = xs_d.numel() // N
+        out = torch.empty(B * N, C, dtype=torch.float32, device=emb.device)
+        with torch.cuda.device(emb.device):
+            _cabi.check(L.mlg_embed_scale_fwd(_cabi.fptr(xs_d), _cabi.fptr(emb_d), B, N, C, _cabi.fptr(out),
+                                              _cabi.stream_ptr()), "mlg_embed_scale_fwd")
+        ctx.save_for_backward(xs_d)
+        ctx.dims = (B, N, C)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        L = _cabi.lib()
+        (xs_d,) = ctx.saved_tensors
+        B, N, C = ctx.dims
+        g = _f32c(g)
+        g_emb = torch.empty(N, C, dtype=torch.float32, device=g.device)
+        with torch.cuda.device(g.device):
+            _cabi.check(L.mlg_embed_scale_bwd(_cabi.fptr(xs_d), _cabi.fptr(g), B, N, C, _cabi.fptr(g_emb),
+                                              _cabi.stream_ptr()), "mlg_embed_scale_bwd")
+        return None, g_emb
+
+
+class PathwayPool(torch.autograd.Function):
+    """Gene -> pathway pool (models/multilevel_gnn.py:205-239).
+    forward(x [B*N,C], w [G,P] (already * info_mask), vm [B*N] or None, layout) -> [B,C,S,P]."""
+
+    @staticmethod
+    def forward(ctx, x, w, vm, layout):
+        L = _cabi.lib()
+        xd, wd = _f32c(x.detach()), _f32c(w.detach())
+        B, N, G, S = layout.B, layout.N, layout.G, layout.S
+        C, P = xd.shape[1], wd.shape[1]
+        out = torch.empty(B, C, S, P, dtype=torch.float32, device=xd.device)
+        with torch.cuda.device(xd.device):
+            _cabi.check(L.mlg_pool_fwd(_cabi.fptr(xd), _cabi.fptr(vm, True), _cabi.lptr(layout.match),
+                                       _cabi.fptr(wd), _cabi.iptr(layout.seg.rowptr), _cabi.iptr(layout.seg.col),
+                                       B, N, C, G, S, P, int(layout.wrap_negative), _cabi.fptr(out),
+                                       _cabi.stream_ptr()), "mlg_pool_fwd")
+        ctx.save_for_backward(xd, wd)
+        ctx.vm, ctx.layout = vm, layout
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        L = _cabi.lib()
+        xd, wd = ctx.saved_tensors
+        lay, vm = ctx.layout, ctx.vm
+        B, N, G, S = lay.B, lay.N, lay.G, lay.S
+        C, P = xd.shape[1], wd.shape[1]
+        g_cl = _f32c(g).permute(0, 2, 3, 1).contiguous()      # [B,S,P,C]: channel-last for coalesced reads
+        gx = gw = None
+        with torch.cuda.device(xd.device):
+            if ctx.needs_input_grad[0]:
+                gx = torch.empty_like(xd)
+                node = lay.node_csr
+                _cabi.check(L.mlg_pool_bwd_x(_cabi.fptr(g_cl), _cabi.fptr(vm, True), _cabi.fptr(wd),
+                                             _cabi.iptr(node.rowptr), _cabi.iptr(node.col),
+                                             _cabi.iptr(lay.seg_of_slot), B, N, C, G, S, P, _cabi.fptr(gx),
+                                             _cabi.stream_ptr()), "mlg_pool_bwd_x")
+            if ctx.needs_input_grad[1]:
+                gw = torch.empty_like(wd)
+                _cabi.check(L.mlg_pool_bwd_w(_cabi.fptr(g_cl), _cabi.fptr(xd), _cabi.fptr(vm, True),
+                                             _cabi.lptr(lay.match), _cabi.lptr(lay.raw_indice), B, N, C, G, S, P,
+                                             int(lay.wrap_negative), _cabi.fptr(gw), _cabi.stream_ptr()),
+                            "mlg_pool_bwd_w")
+        return gx, gw, None, None

@@ -1,0 +1,166 @@
+"""CSR topologies for the kernels, built on the GPU by ``mlg_csr_build`` and cached per edge list.
+
+The reference re-derives its edge structure on every forward (``remove_self_loops`` +
+``add_self_loops`` at models/gcn_lib/sparse/torch_vertex.py:272-273, index broadcasting inside
+torch_scatter).  In ``train.py`` the edge list is constant for a whole fold
+(dataloader/multiloader.py:687-698), so the structure is built once and re-used by every layer of
+every step; the cache key is the identity + version counter of the ``edge_index`` tensor.
+"""
+import collections
+
+import torch
+
+from . import _cabi
+
+
+class CSR:
+    """rowptr int32 [n_rows+1]; col int32 [cap]; eid int32 [cap] (edge id, -1 = added self loop)."""
+    __slots__ = ("rowptr", "col", "eid", "n_rows", "cap")
+
+    def __init__(self, rowptr, col, eid, n_rows, cap):
+        self.rowptr, self.col, self.eid, self.n_rows, self.cap = rowptr, col, eid, n_rows, cap
+
+
+def build_csr(edge_index, n_rows, by_source=False, drop_self=False, add_self=False):
+    """edge_index: int64 CUDA tensor [2, E] (row 0 = source, row 1 = target)."""
+    if edge_index.dtype != torch.int64 or edge_index.dim() != 2 or edge_index.shape[0] != 2:
+        raise TypeError("edge_index must be int64 [2, E]")
+    edge_index = edge_index.contiguous()
+    L = _cabi.lib()
+    dev = edge_index.device
+    E = edge_index.shape[1]
+    cap = E + (n_rows if add_self else 0)
+    rowptr = torch.empty(n_rows + 1, dtype=torch.int32, device=dev)
+    col = torch.empty(max(cap, 1), dtype=torch.int32, device=dev)
+    eid = torch.empty(max(cap, 1), dtype=torch.int32, device=dev)
+    ws_bytes = L.mlg_csr_build_workspace_bytes(E, n_rows, int(add_self))
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        _cabi.check(L.mlg_csr_build(_cabi.lptr(edge_index), E, n_rows, int(by_source), int(drop_self),
+                                    int(add_self), _cabi.iptr(rowptr), _cabi.iptr(col), _cabi.iptr(eid),
+                                    _cabi.ptr(ws), ws_bytes, _cabi.stream_ptr()), "mlg_csr_build")
+    return CSR(rowptr, col, eid, n_rows, cap)
+
+
+def edge_values(edge_attr, csr, fill=1.0):
+    """Edge weights permuted into CSR order (self loops get ``fill``), float32 [cap]."""
+    L = _cabi.lib()
+    ea = edge_attr.reshape(-1).contiguous().float()
+    val = torch.empty(max(csr.cap, 1), dtype=torch.float32, device=csr.rowptr.device)
+    with torch.cuda.device(val.device):
+        _cabi.check(L.mlg_edge_values(_cabi.fptr(ea), _cabi.iptr(csr.eid), _cabi.iptr(csr.rowptr), csr.n_rows,
+                                      csr.cap, float(fill), _cabi.fptr(val), _cabi.stream_ptr()), "mlg_edge_values")
+    return val
+
+
+class Topology:
+    """Target-sorted CSR (forward traversal) + source-sorted CSR (backward traversal) of one edge
+    list, optionally with the SAGE self-loop rewrite and edge weights folded in."""
+
+    def __init__(self, edge_index, n_nodes, self_loops=False, edge_weight=None):
+        self.n = n_nodes
+        self.self_loops = self_loops
+        self.edge_index = edge_index
+        self.fwd = build_csr(edge_index, n_nodes, by_source=False, drop_self=self_loops, add_self=self_loops)
+        self._bwd = None
+        self._edge_weight = edge_weight
+        self.fwd_val = edge_values(edge_weight, self.fwd) if edge_weight is not None else None
+        self._bwd_val = None
+        self._inv_cnt = None
+
+    @property
+    def bwd(self):
+        if self._bwd is None:
+            self._bwd = build_csr(self.edge_index, self.n, by_source=True, drop_self=self.self_loops,
+                                  add_self=self.self_loops)
+        return self._bwd
+
+    @property
+    def bwd_val(self):
+        if self._bwd_val is None and self._edge_weight is not None:
+            self._bwd_val = edge_values(self._edge_weight, self.bwd)
+        return self._bwd_val
+
+    @property
+    def inv_cnt(self):
+        """1 / (number of entries per target row) -- PyG mean aggregation's divisor, float32 [n]."""
+        if self._inv_cnt is None:
+            cnt = (self.fwd.rowptr[1:] - self.fwd.rowptr[:-1]).float()
+            self._inv_cnt = torch.where(cnt > 0, 1.0 / cnt.clamp(min=1), torch.zeros_like(cnt))
+        return self._inv_cnt
+
+
+_CACHE = collections.OrderedDict()
+_CACHE_MAX = 16
+
+
+def _key(t):
+    return None if t is None else (t.data_ptr(), tuple(t.shape), t._version, str(t.device))
+
+
+def topology(edge_index, n_nodes, self_loops=False, edge_weight=None):
+    """Cached Topology for this (edge_index, edge_weight) pair."""
+    key = (_key(edge_index), n_nodes, self_loops, _key(edge_weight))
+    hit = _CACHE.get(key)
+    if hit is not None:
+        _CACHE.move_to_end(key)
+        return hit[0]
+    topo = Topology(edge_index, n_nodes, self_loops, edge_weight)
+    _CACHE[key] = (topo, edge_index, edge_weight)   # keep the tensors alive so the pointers stay unique
+    if len(_CACHE) > _CACHE_MAX:
+        _CACHE.popitem(last=False)
+    return topo
+
+
+def clear_cache():
+    _CACHE.clear()
+    _POOL_CACHE.clear()
+
+
+class PoolLayout:
+    """Index structures of the gene -> pathway pool (models/multilevel_gnn.py:212-239):
+    ``seg``      CSR over (graph, segment) rows listing gene slots  -> forward traversal
+    ``node_csr`` CSR over nodes listing the slots that read them    -> backward traversal
+    built once per (gene_pca_match, raw_indice) pair (constant for a fold, multiloader.py:697)."""
+
+    def __init__(self, gene_pca_match, raw_indice, nodes_per_graph, n_segments, wrap_negative=False):
+        B, G = gene_pca_match.shape
+        dev = gene_pca_match.device
+        self.B, self.G, self.N, self.S = B, G, nodes_per_graph, n_segments
+        self.wrap_negative = wrap_negative
+        self.match = gene_pca_match.contiguous()
+        self.raw_indice = raw_indice.contiguous()
+        slot = torch.arange(B * G, device=dev, dtype=torch.int64)
+        boff = torch.arange(B, device=dev, dtype=torch.int64).view(B, 1)
+        seg = (self.raw_indice + boff * n_segments).reshape(-1)
+        self.seg_of_slot = seg.to(torch.int32)
+        self.seg = build_csr(torch.stack([slot, seg]), B * n_segments)
+        node = self.match + boff * nodes_per_graph
+        if wrap_negative:
+            node = torch.where(self.match < 0, node % (B * nodes_per_graph), node)
+        else:
+            node = torch.where(self.match < 0, torch.full_like(node, -1), node)
+        self._node_edges = torch.stack([slot, node.reshape(-1)])
+        self._node_csr = None
+
+    @property
+    def node_csr(self):
+        if self._node_csr is None:
+            self._node_csr = build_csr(self._node_edges, self.B * self.N)
+        return self._node_csr
+
+
+_POOL_CACHE = collections.OrderedDict()
+
+
+def pool_layout(gene_pca_match, raw_indice, nodes_per_graph, n_segments, wrap_negative=False):
+    key = (_key(gene_pca_match), _key(raw_indice), nodes_per_graph, n_segments, wrap_negative)
+    hit = _POOL_CACHE.get(key)
+    if hit is not None:
+        _POOL_CACHE.move_to_end(key)
+        return hit[0]
+    lay = PoolLayout(gene_pca_match, raw_indice, nodes_per_graph, n_segments, wrap_negative)
+    _POOL_CACHE[key] = (lay, gene_pca_match, raw_indice)
+    if len(_POOL_CACHE) > _CACHE_MAX:
+        _POOL_CACHE.popitem(last=False)
+    return lay

@@ -1,0 +1,9 @@
+"""Model registry with the reference's names (models/__init__.py:11-23) for the in-scope families."""
+from .multilevel_gnn import MultilevelGNN
+from .deepergcn import DeeperGCN
+
+MODELS = {'deepergcn': DeeperGCN, 'multilevel_gnn': MultilevelGNN}
+
+
+def get_model(model_name):
+    return MODELS[model_name]

@@ -1,0 +1,232 @@
+"""MultilevelGNN drop-in (models/multilevel_gnn.py:13-395 of the reference).
+
+Same constructor (``args`` namespace, opt.py flags), same ``forward(input_batch, ...) -> (pred,
+pca_feature)``, same setters and state_dict keys (node_embedding, learnable_pca_params, info_mask,
+gnn_model.{i}.gconv.*, conv_model.{0,2}.*, head.{0,3}.*).  The level-1 message passing (GraphConv
+'sage'/'rsage' stack), the embed-scale prologue and the gene->pathway pool run in the sm_100a
+kernels; the 1x1-conv / MLP head stays in torch ("next").
+"""
+import torch
+import torch.nn as nn
+
+from .. import functional as Fn
+from .. import graph
+from ..gcn_lib.sparse.torch_vertex import GraphConv
+
+
+class MultilevelGNN(nn.Module):
+    GENES = 5135      # reference hard-codes node_num (multilevel_gnn.py:34)
+    SLOTS = 25015     # and the gene-slot count (multilevel_gnn.py:74)
+
+    def __init__(self, args, pca_params=None, pathway_indexs=None):
+        super().__init__()
+        self.args = args
+        self.pca_compare = args.pca_compare
+        self.pca_prelinear = args.pca_prelinear
+        self.learnable_pca = args.learnable_pca
+        self.pca_loss = args.pca_loss
+        self.pca_indep_loss = args.pca_indep_loss
+        self.pca_dim = args.pca_dim
+        self.pathway_pool_dim = args.pathway_pool_dim
+        self.pca_pool_dim = args.pca_pool_dim
+        self.pathway_indexs = None
+        self.reorder_idxs = None
+        self.mutual_info_mask = args.mutual_info_mask
+        self.mutual_info_threshold = args.mutual_info_threshold
+        self.pca_loss_coef = args.pca_loss_coef
+        self.node_select_threshold = args.node_select_threshold
+        self.mutual_neighbors = args.mutual_neighbors
+        self.node_num = self.GENES
+        self.mutual_info_mask_cache = {}
+        self.head_dim = args.head_dim
+        self.epoch = None
+        self.step = None
+        self.used_omics = args.used_omics
+        if self.pca_compare or self.pca_prelinear:
+            raise NotImplementedError("pca_compare / pca_prelinear heads are not selected by any shipped config")
+        if args.reduction_method != "linear_projection":
+            raise NotImplementedError("reduction_method=%s (torch.svd / pca_lowrank) is out of scope, SURVEY.md section 2 row 16"
+                                      % args.reduction_method)
+        if len(self.used_omics) != 3:
+            raise NotImplementedError("used_omics subsets are not selected by any shipped config")
+
+        self.input_drop = nn.Dropout(p=args.input_drop) if args.input_drop is not None else None
+        self.input_emb_drop = nn.Dropout(p=args.input_emb_drop) if args.input_emb_drop is not None else None
+
+        if args.node_embedding:
+            self.node_embedding = nn.Parameter(torch.rand([self.node_num * 3, args.node_embedding_dim]),
+                                               requires_grad=not args.freeze_node_embedding)
+            init = args.embedding_init_type
+            if init == "xavier":
+                nn.init.xavier_uniform_(self.node_embedding)
+            elif init == "ones":
+                nn.init.constant_(self.node_embedding, 1)
+            elif init == "constant":
+                nn.init.constant_(self.node_embedding, args.emb_val)
+            elif init == "uniform":
+                nn.init.uniform_(self.node_embedding)
+            self.node_embedding_dim = args.node_embedding_dim
+        else:
+            self.node_embedding = None
+            self.node_embedding_dim = 1
+
+        conv_kw = dict(act=args.gnn_act, conv=args.gnn_name, mlp_norm=args.gnn_mlp_norm, drop=args.gnn_dropout)
+        blocks = [GraphConv(self.node_embedding_dim, args.hidden_channels, **conv_kw)]
+        for _ in range(args.num_layers - 2):
+            blocks.append(GraphConv(args.hidden_channels, args.hidden_channels, **conv_kw))
+        blocks.append(GraphConv(args.hidden_channels, args.final_channels, heads=args.final_head,
+                                norm=args.gnn_last_norm, **conv_kw))
+        self.gnn_model = nn.ModuleList(blocks)
+
+        self.learnable_pca_params = nn.Parameter(torch.rand([self.SLOTS, self.pca_dim]),
+                                                 requires_grad=not args.freeze_pca_weight)
+        if pca_params is None:
+            if args.pca_init_type is None:
+                nn.init.xavier_uniform_(self.learnable_pca_params.data)
+            elif args.pca_init_type == "orthogonal":
+                nn.init.orthogonal_(self.learnable_pca_params.data)
+        else:
+            self.learnable_pca_params.data = pca_params
+
+        # NOTE: like the reference, the constructor rewrites args.final_channels in these two modes
+        if args.edge_type == 'merge':
+            args.final_channels *= 2
+        if args.dense_gnn:
+            args.final_channels = (args.num_layers - 1) * args.hidden_channels + args.final_channels
+
+        convs, cin = [], args.final_channels
+        for cout, ks in zip(args.conv_channel_list, args.conv_kernel_list):
+            convs += [nn.Conv2d(cin, cout, ks, padding=ks // 2), nn.ReLU()]
+            cin = cout
+        self.conv_model = nn.ModuleList(convs)
+        self.pooling = nn.MaxPool2d((self.pathway_pool_dim, self.pca_pool_dim))
+        self.drop1 = nn.Dropout(0.25 if args.feature_drop else 0)
+        head_in = (args.conv_channel_list[-1] * (146 // self.pathway_pool_dim)
+                   * ((len(self.used_omics) * self.pca_dim) // self.pca_pool_dim) + (1 if args.use_age else 0))
+        self.head = nn.Sequential(nn.Linear(head_in, self.head_dim), nn.ReLU(), nn.Dropout(0.5),
+                                  nn.Linear(self.head_dim, 2), nn.Softmax(dim=1))
+        self.init_weight()
+
+    # ------------------------------------------------------------------------------------------
+    def forward(self, input_batch, x=None, gene_pca_match=None, raw_indice=None, age=None, require_grad=True):
+        args = self.args
+        with torch.enable_grad() if require_grad else torch.no_grad():
+            if x is not None:
+                mask_x = x
+            else:
+                mask_x = input_batch.x
+                gene_pca_match = input_batch.gene_pca_match
+                raw_indice = input_batch.raw_indice
+                age = input_batch.age
+            x = mask_x.reshape(-1, 1)
+            if self.input_drop is not None:
+                x = self.input_drop(x)
+            n3 = self.node_num * 3
+            if args.node_embedding:
+                x = Fn.EmbedScale.apply(x, self.node_embedding)          # [B*N, emb_dim], K13
+            if self.input_emb_drop is not None:
+                x = self.input_emb_drop(x)
+
+            edge_index, edge_attr = input_batch.edge_index, input_batch.edge_attr
+            if isinstance(edge_index, list):
+                raise NotImplementedError("list-valued edge_index (edge_type='merge') is not selected by any shipped config")
+            if args.device_num != 1:
+                n_edge = edge_index.shape[-1] // args.device_num
+                edge_index, edge_attr = edge_index[:, :n_edge].contiguous(), edge_attr[:n_edge]
+            edge_index = edge_index.to(x.device)
+            edge_attr = edge_attr.to(x.device) if args.weighted_edge else None
+
+            feats = []
+            mask_col = mask_x.reshape(-1, 1)
+            n_layers = len(self.gnn_model)
+            for i, layer in enumerate(self.gnn_model):
+                y = layer(x, edge_index, edge_attr)
+                if args.dense_gnn:
+                    x = y
+                    feats.append(x)
+                elif args.resgnn:
+                    x = y + x
+                else:
+                    x = y
+                if i + 1 != n_layers and args.repeat_mask and (i + 1) % args.repeat_cyclic == 0:
+                    if args.repeat_norm:
+                        x = x / (x ** 2).sum(1).sqrt()[:, None]
+                    x = x * mask_col
+            if args.dense_gnn:
+                x = torch.cat(feats, dim=-1)
+
+            vm = None
+            if args.value_att_mask:
+                if args.merge_mode == 'mult':
+                    vm = mask_x.reshape(-1).detach().float().contiguous()   # folded into the pool kernel
+                else:
+                    x = args.add_coef1 * x + args.add_coef2 * mask_col
+
+            layout = graph.pool_layout(gene_pca_match, raw_indice, n3, 146 * 3,
+                                       wrap_negative=not args.pca_match_mask)
+            w = self.learnable_pca_params * self.info_mask                   # [G, P]
+            x = Fn.PathwayPool.apply(x, w, vm, layout)                       # [B, C, 438, P]
+            x = x.reshape(x.shape[0], x.shape[1], 146, self.pca_dim * 3)
+            if args.reorder_pathway and self.reorder_idxs is not None:
+                x = x[:, :, self.reorder_idxs.to(x.device), :]
+
+        pca_feature = x
+        for layer in self.conv_model:
+            x = layer(x)
+        x = self.pooling(x)
+        x = self.drop1(x)
+        x = torch.flatten(x, start_dim=1)
+        if args.use_age:
+            x = torch.cat([x, age[:, None]], dim=-1)
+        return self.head(x), pca_feature
+
+    # ------------------------------------------------------------------------------------------
+    def init_weight(self):
+        for m in self.modules():
+            if isinstance(m, (nn.Conv2d, nn.Linear)):
+                nn.init.xavier_uniform_(m.weight.data)
+
+    def set_pca_params(self, pca_params, mutual_info_mask):
+        keep = [i for i in range(len(mutual_info_mask)) if mutual_info_mask[i] > 0]
+        self.learnable_pca_params = nn.Parameter(torch.zeros([len(mutual_info_mask), self.pca_dim]),
+                                                 requires_grad=not self.args.freeze_pca_weight)
+        self.learnable_pca_params.data[keep] = pca_params[:, :self.pca_dim].to(torch.float32)
+
+    def set_pathway_indexs(self, pathway_indexs):
+        self.pathway_indexs = pathway_indexs
+
+    def set_info_mask(self, info_mask):
+        self.info_mask = nn.Parameter(data=info_mask, requires_grad=False)
+
+    def set_reorder_idxs(self, reorder_idx):
+        self.reorder_idxs = torch.tensor(reorder_idx)
+
+    def get_feature_loss(self, pca_feature):
+        """-log mean std of pooled features (pca_loss) and the pathway-wise |cos| between projection
+        columns (pca_indep_loss, no grad: the reference reads ``.data``), multilevel_gnn.py:329-348 --
+        including its loop structure: only the last (i, j) pair of each i is accumulated."""
+        loss = 0
+        if self.pca_loss:
+            flat = pca_feature.reshape(pca_feature.shape[0], -1)
+            loss = loss - self.pca_loss_coef * torch.log(torch.mean(torch.std(flat, dim=0)))
+        if self.pca_indep_loss:
+            w = (self.learnable_pca_params * self.info_mask).data
+            idx = self.pathway_indexs.to(w.device)
+            nseg = int(self.pathway_indexs.max()) + 1 if not hasattr(self, "_nseg") else self._nseg
+            self._nseg = nseg
+
+            def seg(v):
+                return torch.zeros(nseg, device=w.device, dtype=w.dtype).index_add_(0, idx, v)
+
+            indep, count = 0, 0
+            for i in range(self.pca_dim - 1):
+                for j in range(i + 1, self.pca_dim):
+                    count += 1
+                    mul = seg(w[:, i] * w[:, j])
+                    ln = torch.sqrt(seg(w[:, i] ** 2) * seg(w[:, j] ** 2))
+                indep = indep + torch.mean(torch.abs(mul / (ln + 1e-7)))
+            loss = loss + indep / count
+        return loss
+
+    def generate_mutual_mask(self, *a, **k):
+        raise NotImplementedError("sklearn mutual-information data prep is out of scope (SURVEY.md section 2 row 7)")
