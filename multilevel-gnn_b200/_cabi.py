@@ -84,6 +84,14 @@ def stream_ptr():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+def require_cuda(*tensors):
+    """The product has no CPU path: refuse anything that is not a CUDA tensor."""
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise NativeLibraryError(
+                "multilevel-gnn_b200 kernels need CUDA tensors (got %s); there is no CPU fallback" % t.device)
+
+
 def ptr(t, dtype=None, allow_none=False):
     """Device pointer of a contiguous CUDA tensor (or NULL)."""
     if t is None:

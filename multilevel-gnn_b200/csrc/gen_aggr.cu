@@ -211,10 +211,12 @@ __global__ void __launch_bounds__(kThreads) gen_fwd_kernel(GenP P) {
         for (int k = 0; k < VEC; ++k) hv.v[k] = xr.v[k] + o.v[k];
         store_vec<VEC>(P.h + (size_t)row * H + c, hv, cok, false);
       } else {
+        if (cok) {  // lanes past H hold eps-valued garbage: keep them out of the norms
 #pragma unroll
-        for (int k = 0; k < VEC; ++k) {
-          sx2 = fmaf(xr.v[k], xr.v[k], sx2);
-          sm2 = fmaf(o.v[k], o.v[k], sm2);
+          for (int k = 0; k < VEC; ++k) {
+            sx2 = fmaf(xr.v[k], xr.v[k], sx2);
+            sm2 = fmaf(o.v[k], o.v[k], sm2);
+          }
         }
         out = o;
         xi = xr;

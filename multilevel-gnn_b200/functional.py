@@ -50,6 +50,7 @@ class GenAggregate(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, e, t, p, y, msg_scale, topo, aggr, eps, epilogue, learn):
         L = _cabi.lib()
+        _cabi.require_cuda(x, e)
         ref = x if x is not None else e
         n, H = topo.n, ref.shape[1]
         xd = None if x is None else _f32c(x.detach())
@@ -135,6 +136,7 @@ class SageAggregate(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, topo, relative):
+        _cabi.require_cuda(x)
         xd = _f32c(x.detach())
         csr = topo.fwd
         out = gather_sum(xd, csr.rowptr, csr.col, topo.n, val=topo.fwd_val, post_mode=1, relative=relative)
@@ -159,6 +161,7 @@ class EmbedScale(torch.autograd.Function):
     @staticmethod
     def forward(ctx, xs, emb):
         L = _cabi.lib()
+        _cabi.require_cuda(xs, emb)
         N, C = emb.shape
         xs_d = _f32c(xs.detach().reshape(-1))
         emb_d = _f32c(emb.detach())
@@ -191,6 +194,7 @@ class PathwayPool(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, w, vm, layout):
         L = _cabi.lib()
+        _cabi.require_cuda(x, w)
         xd, wd = _f32c(x.detach()), _f32c(w.detach())
         B, N, G, S = layout.B, layout.N, layout.G, layout.S
         C, P = xd.shape[1], wd.shape[1]

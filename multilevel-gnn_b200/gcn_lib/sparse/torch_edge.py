@@ -12,6 +12,7 @@ from ... import _cabi
 def _knn_call(xb, k, dilation, add_offset):
     """xb [B,N,D] fp32 CUDA -> (nbr, ctr) int64 [B*N*k]; k = neighbours kept after dilation."""
     L = _cabi.lib()
+    _cabi.require_cuda(xb)
     xb = xb.detach().contiguous().float()
     B, N, D = xb.shape
     nbr = torch.empty(B * N * k, dtype=torch.int64, device=xb.device)

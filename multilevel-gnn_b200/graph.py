@@ -25,6 +25,7 @@ def build_csr(edge_index, n_rows, by_source=False, drop_self=False, add_self=Fal
     """edge_index: int64 CUDA tensor [2, E] (row 0 = source, row 1 = target)."""
     if edge_index.dtype != torch.int64 or edge_index.dim() != 2 or edge_index.shape[0] != 2:
         raise TypeError("edge_index must be int64 [2, E]")
+    _cabi.require_cuda(edge_index)
     edge_index = edge_index.contiguous()
     L = _cabi.lib()
     dev = edge_index.device
@@ -45,6 +46,7 @@ def build_csr(edge_index, n_rows, by_source=False, drop_self=False, add_self=Fal
 def edge_values(edge_attr, csr, fill=1.0):
     """Edge weights permuted into CSR order (self loops get ``fill``), float32 [cap]."""
     L = _cabi.lib()
+    _cabi.require_cuda(edge_attr)
     ea = edge_attr.reshape(-1).contiguous().float()
     val = torch.empty(max(csr.cap, 1), dtype=torch.float32, device=csr.rowptr.device)
     with torch.cuda.device(val.device):

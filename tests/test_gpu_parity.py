@@ -1,0 +1,357 @@
+"""Parity of the sm_100a kernels (through the C ABI and the drop-in modules) against
+ (a) the committed golden vectors produced by the reference's own files, and
+ (b) the CPU oracle (oracle/restated.py) on seeded inputs, at sizes the oracle finishes in seconds.
+Tolerance: fp32 rtol 1e-4 (BASELINE.json north_star); kNN indices exact outside fp32 tie classes.
+"""
+import pytest
+import torch
+
+from conftest import as_batch, assert_close, load_golden
+from oracle import restated as R
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+@pytest.fixture(scope="module")
+def mlg():
+    import multilevel_gnn_b200 as m
+    m._cabi.lib()      # fail loudly if the native library is missing
+    return m
+
+
+def _load(module, sd):
+    module.load_state_dict(sd, strict=True)
+    return module.to(DEV)
+
+
+# ------------------------------------------------------------------------------------------------
+# GENConv (all aggregation modes) vs golden
+# ------------------------------------------------------------------------------------------------
+GEN = load_golden("genconv")
+
+
+@pytest.mark.parametrize("name", sorted(GEN))
+def test_genconv_golden(mlg, name):
+    c = GEN[name]
+    H = c["H"]
+    conv = _load(mlg.GENConv(H, H, encode_edge=True, edge_feat_dim=H, **c["kw"]), c["state_dict"])
+    conv.train()
+    x = c["x"].to(DEV).requires_grad_()
+    ea = c["edge_attr"].to(DEV).requires_grad_()
+    ei = c["edge_index"].to(DEV)
+    y = conv(x, ei, ea)
+    assert_close(y, c["y"], what=name + ".y")
+    names = list(c["g_params"])
+    params = dict(conv.named_parameters())
+    gs = torch.autograd.grad((y * c["R"].to(DEV)).sum(), [x, ea] + [params[k] for k in names], allow_unused=True)
+    assert_close(gs[0], c["g_x"], what=name + ".g_x")
+    assert_close(gs[1], c["g_edge_attr"], what=name + ".g_edge_attr")
+    for k, g in zip(names, gs[2:]):
+        assert_close(g, c["g_params"][k], rtol=2e-4, what=name + ".g_" + k)
+
+
+@pytest.mark.parametrize("name", sorted(GEN))
+def test_gen_aggregate_golden(mlg, name):
+    """GenMessagePassing.aggregate(inputs, index, dim_size) on explicit messages."""
+    c = GEN[name]
+    H = c["H"]
+    conv = _load(mlg.GENConv(H, H, encode_edge=True, edge_feat_dim=H, **c["kw"]), c["state_dict"])
+    msg = c["msg"].to(DEV).requires_grad_()
+    agg = conv.aggregate(msg * 1.0, c["edge_index"][1].to(DEV), dim_size=c["x"].shape[0])
+    assert_close(agg, c["agg"], what=name + ".agg")
+    g = torch.autograd.grad((agg * c["R"].to(DEV)).sum(), msg)[0]
+    assert_close(g, c["g_msg"], what=name + ".g_msg")
+
+
+# ------------------------------------------------------------------------------------------------
+# SAGE / RSAGE vs golden
+# ------------------------------------------------------------------------------------------------
+SAGE = load_golden("sage")
+
+
+@pytest.mark.parametrize("name", sorted(SAGE))
+def test_sage_golden(mlg, name):
+    c = SAGE[name]
+    conv = _load(mlg.GraphConv(c["cin"], c["cout"], conv=c["conv"], act="leakyrelu", norm=None, mlp_norm="none"),
+                 c["state_dict"])
+    x = c["x"].to(DEV).requires_grad_()
+    y = conv(x, c["edge_index"].to(DEV), c["edge_attr"].to(DEV))
+    assert_close(y, c["y"], what=name + ".y")
+    names = [k for k, g in c["g_params"].items() if g is not None]
+    params = dict(conv.named_parameters())
+    gs = torch.autograd.grad((y * c["R"].to(DEV)).sum(), [x] + [params[k] for k in names])
+    assert_close(gs[0], c["g_x"], what=name + ".g_x")
+    for k, g in zip(names, gs[1:]):
+        assert_close(g, c["g_params"][k], what=name + ".g_" + k)
+    assert c["g_params"]["gconv.lin_l.weight"] is None and params["gconv.lin_l.weight"].grad is None
+
+
+# ------------------------------------------------------------------------------------------------
+# kNN vs golden: identical indices wherever the fp64 distances separate the ranks
+# ------------------------------------------------------------------------------------------------
+KNN = load_golden("knn")
+
+
+def _check_knn(x, batch, k, got, ref, name):
+    """got/ref: [2, B*N*k].  Centres must match exactly; neighbour ids must match wherever the
+    neighbour's distance is separated from the adjacent ranks by more than the fp32 evaluation error;
+    inside a near-tie class any permutation is accepted but the distances must agree."""
+    assert torch.equal(got[1].cpu(), ref[1]), name + ": centre ids"
+    vals, _, d = R.knn_distance_gap(x, k, batch)          # fp64
+    bsz = 1 if batch is None else int(batch[-1]) + 1
+    n = x.shape[0] // bsz
+    g, r = got[0].cpu().view(bsz, n, k), ref[0].view(bsz, n, k)
+    offs = (torch.arange(bsz) * n).view(bsz, 1, 1)
+    dg = torch.gather(d, 2, g - offs)
+    dr = torch.gather(d, 2, r - offs)
+    scale = d.abs().max()
+    assert float((dg - dr).abs().max()) <= 1e-5 * float(scale), name + ": neighbour distances differ"
+    gap_next = (vals[..., 1:k + 1] - vals[..., :k]) if vals.shape[-1] > k else None
+    sep = torch.ones_like(dg, dtype=torch.bool)
+    tol = 4e-6 * float(scale)
+    sep[..., 1:] &= (vals[..., 1:k] - vals[..., :k - 1]) > tol
+    if gap_next is not None:
+        sep &= gap_next > tol
+    assert torch.equal(g[sep], r[sep]), name + ": ids differ outside tie classes"
+    # every row: k distinct neighbours
+    assert int((torch.sort(g, -1).values.diff(dim=-1) == 0).sum()) == 0
+
+
+@pytest.mark.parametrize("name", sorted(KNN))
+def test_knn_golden(mlg, name):
+    c = KNN[name]
+    x, batch = c["x"].to(DEV), c["batch"].to(DEV)
+    kk = c["k"] * c["dil"]
+    full = mlg.knn_graph_matrix(x, kk, batch if c["b"] > 1 else None)
+    _check_knn(c["x"], c["batch"] if c["b"] > 1 else None, kk, full, c["edge_index_full"], name)
+    if name == "grid_ties":
+        # canonical order inside exact ties: ascending distance, then ascending index
+        d = R.pairwise_distance(c["x"].view(1, -1, 2))[0]
+        g = full[0].cpu().view(-1, kk)
+        dsel = torch.gather(d, 1, g)
+        assert bool((dsel.diff(dim=1) >= 0).all())
+        same = dsel.diff(dim=1) == 0
+        assert bool((g.diff(dim=1)[same] > 0).all())
+        return
+    dil = mlg.DilatedKnnGraph(c["k"], c["dil"]).eval()(x, batch)
+    assert torch.equal(dil.cpu(), full.cpu().view(2, -1, kk)[:, :, ::c["dil"]].reshape(2, -1))
+    xd = c["x"].view(c["b"], c["n"], c["d"]).transpose(1, 2).unsqueeze(-1).contiguous().to(DEV)
+    dense = mlg.dense_knn_matrix(xd, kk)
+    assert dense.shape == c["dense_full"].shape
+    offs = (torch.arange(c["b"]) * c["n"]).view(1, c["b"], 1, 1)
+    assert torch.equal((dense.cpu() + offs).reshape(2, -1), full.cpu())
+    dd = mlg.DenseDilatedKnnGraph(c["k"], c["dil"])(xd)
+    assert torch.equal(dd.cpu(), dense.cpu()[:, :, :, ::c["dil"]])
+
+
+def test_knn_vs_oracle_larger(mlg):
+    g = torch.Generator().manual_seed(7)
+    x = torch.randn(3 * 700, 24, generator=g)
+    batch = torch.arange(3).repeat_interleave(700)
+    ref = R.knn_graph_matrix(x, 16, batch)
+    got = mlg.knn_graph_matrix(x.to(DEV), 16, batch.to(DEV))
+    _check_knn(x, batch, 16, got, ref, "n700")
+
+
+# ------------------------------------------------------------------------------------------------
+# MultilevelGNN (small re-sized instance) vs golden: pred, pooled features, per-layer activations,
+# loss, every gradient
+# ------------------------------------------------------------------------------------------------
+ML = load_golden("multilevel")
+
+
+def _build_multilevel(mlg, c):
+    args = mlg.configs.make_args(c["config"], **c["overrides"])
+    model = mlg.MultilevelGNN(args)
+    model.node_num = c["genes"]
+    sd = c["state_dict"]
+    model.node_embedding = torch.nn.Parameter(sd["node_embedding"].clone())
+    model.learnable_pca_params = torch.nn.Parameter(sd["learnable_pca_params"].clone())
+    model.set_info_mask(sd["info_mask"].clone())
+    model.load_state_dict(sd, strict=True)
+    model.set_pathway_indexs(c["batch"]["raw_indice"][0].clone())
+    return model.to(DEV), args
+
+
+@pytest.mark.parametrize("name", sorted(ML))
+def test_multilevel_golden(mlg, name):
+    c = ML[name]
+    model, args = _build_multilevel(mlg, c)
+    model.eval()
+    acts = {}
+    hooks = [layer.register_forward_hook(lambda m, a, o, j=j: acts.__setitem__("gnn%d" % j, o.detach()))
+             for j, layer in enumerate(model.gnn_model)]
+    batch = as_batch(c["batch"], DEV)
+    pred, feat = model(batch)
+    for h in hooks:
+        h.remove()
+    assert_close(pred, c["pred"], what=name + ".pred")
+    assert_close(feat, c["pca_feature"], what=name + ".pca_feature")
+    for k, v in c["acts"].items():
+        assert_close(acts[k], v, what=name + "." + k)
+    fl = model.get_feature_loss(feat)
+    assert_close(torch.as_tensor(fl), c["feature_loss"], what=name + ".feature_loss")
+    loss = torch.nn.BCELoss(weight=c["weight"].to(DEV))(pred.float(), batch.y.reshape(-1, 2)) + fl
+    assert_close(loss, c["loss"], what=name + ".loss")
+    loss.backward()
+    for k, p in model.named_parameters():
+        if not p.requires_grad:
+            continue
+        if c["grads"][k] is None:
+            assert p.grad is None, k
+        else:
+            assert_close(p.grad, c["grads"][k], rtol=2e-4, what=name + ".g_" + k)
+
+
+# ------------------------------------------------------------------------------------------------
+# DeeperGCN vs golden
+# ------------------------------------------------------------------------------------------------
+DG = load_golden("deepergcn")
+
+
+@pytest.mark.parametrize("name", sorted(DG))
+def test_deepergcn_golden(mlg, name):
+    c = DG[name]
+    args = mlg.configs.make_args(None, **c["overrides"])
+    model = _load(mlg.DeeperGCN(args), c["state_dict"])
+    model.train()
+    batch = as_batch(c["batch"], DEV)
+    batch.node_size = c["batch"]["node_size"]          # host tensor: no device sync needed
+    pred = model(batch)
+    assert_close(pred, c["pred"], what=name + ".pred")
+    (pred * c["R"].to(DEV)).sum().backward()
+    for k, p in model.named_parameters():
+        if c["grads"].get(k) is None:
+            continue
+        assert_close(p.grad, c["grads"][k], rtol=5e-4, atol=2e-5, what=name + ".g_" + k)
+
+
+# ------------------------------------------------------------------------------------------------
+# seeded larger cases vs the CPU oracle + size-independent properties
+# ------------------------------------------------------------------------------------------------
+def _rand_graph(n, e, seed):
+    g = torch.Generator().manual_seed(seed)
+    return torch.stack([torch.randint(0, n, (e,), generator=g), torch.randint(0, n - 5, (e,), generator=g)]), g
+
+
+@pytest.mark.parametrize("aggr,H", [("softmax", 128), ("softmax", 64), ("softmax", 256), ("power", 32), ("softmax_sum", 96)])
+def test_gen_aggr_vs_oracle(mlg, aggr, H):
+    n, e = 3000, 40000
+    ei, g = _rand_graph(n, e, 11)
+    x = torch.randn(n, H, generator=g)
+    ea = torch.randn(e, H, generator=g)
+    kw = dict(aggr=aggr, t=0.9, learn_t=True, p=2.0, learn_p=True, y=0.1, learn_y=True, msg_norm=True, norm="layer",
+              mlp_layers=1)
+    torch.manual_seed(1)
+    conv = mlg.GENConv(H, H, encode_edge=False, **kw).to(DEV).train()
+    sd = {k: v.detach().cpu().clone().requires_grad_() for k, v in conv.state_dict().items()}
+    xr, er = x.clone().requires_grad_(), ea.clone().requires_grad_()
+    yr = R.genconv_forward(sd, xr, ei, er, aggr=aggr, t=0.9, learn_t=True, p=2.0, learn_p=True, msg_norm_on=True,
+                           encode_edge=False, norm="layer")
+    Rm = torch.randn(n, H, generator=g)
+    gr = torch.autograd.grad((yr * Rm).sum(), [xr, er])
+    xg, eg = x.to(DEV).requires_grad_(), ea.to(DEV).requires_grad_()
+    yg = conv(xg, ei.to(DEV), eg)
+    assert_close(yg, yr, what="y")
+    gg = torch.autograd.grad((yg * Rm.to(DEV)).sum(), [xg, eg])
+    assert_close(gg[0], gr[0], rtol=2e-4, what="g_x")
+    assert_close(gg[1], gr[1], rtol=2e-4, what="g_e")
+
+
+def test_gen_aggr_properties(mlg):
+    """zero in-degree rows -> 0 (softmax) ; permutation of the edge list leaves the result unchanged
+    up to fp32 summation order; softmax weights sum to one (aggregating a constant returns it)."""
+    n, e, H = 500, 6000, 128
+    ei, g = _rand_graph(n, e, 5)
+    conv = mlg.GenMessagePassing(aggr="softmax", t=1.0).to(DEV)
+    msg = torch.rand(e, H, generator=g).to(DEV)
+    out = conv.aggregate(msg, ei[1].to(DEV), dim_size=n)
+    assert float(out[n - 5:].abs().max()) == 0.0
+    perm = torch.randperm(e, generator=g)
+    out_p = conv.aggregate(msg[perm.to(DEV)], ei[1][perm].to(DEV), dim_size=n)
+    assert_close(out_p, out.cpu(), what="permutation invariance")
+    const = torch.full((e, H), 0.37, device=DEV)
+    outc = conv.aggregate(const, ei[1].to(DEV), dim_size=n)
+    deg = torch.bincount(ei[1], minlength=n)
+    assert_close(outc[deg > 0], torch.full((int((deg > 0).sum()), H), 0.37), what="weights sum to one")
+    pw = mlg.GenMessagePassing(aggr="power", p=2.0).to(DEV)
+    outp = pw.aggregate(msg, ei[1].to(DEV), dim_size=n)
+    assert_close(outp[n - 5:], torch.full((5, H), (1e-7) ** 0.5), what="power-mean of empty rows (SURVEY B.2)")
+
+
+def test_sage_vs_oracle_gbm_like(mlg):
+    from multilevel_gnn_b200 import synth
+    genes, bsz = 400, 3
+    b = synth.multilevel_batch(batch_size=bsz, genes=genes, slots=900, intra_edges=6000, seed=2)
+    n = 3 * genes * bsz
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(n, 64, generator=g)
+    torch.manual_seed(2)
+    conv = mlg.GraphConv(64, 32, conv="sage", act="leakyrelu", mlp_norm="none").to(DEV)
+    sd = {k: v.detach().cpu().clone().requires_grad_() for k, v in conv.state_dict().items()}
+    xr = x.clone().requires_grad_()
+    yr = R.sage_forward(sd, xr, b.edge_index, b.edge_attr)
+    Rm = torch.randn(n, 32, generator=g)
+    gr = torch.autograd.grad((yr * Rm).sum(), [xr, sd["gconv.lin_r.weight"], sd["gconv.nn.0.weight"]])
+    xg = x.to(DEV).requires_grad_()
+    yg = conv(xg, b.edge_index.to(DEV), b.edge_attr.to(DEV))
+    assert_close(yg, yr, what="y")
+    (yg * Rm.to(DEV)).sum().backward()
+    assert_close(xg.grad, gr[0], rtol=2e-4, what="g_x")
+    assert_close(conv.gconv.lin_r.weight.grad, gr[1], rtol=2e-4, what="g_lin_r")
+    assert_close(conv.gconv.nn[0].weight.grad, gr[2], rtol=2e-4, what="g_nn")
+
+
+def test_pool_linearity_and_oracle(mlg):
+    """pool(a*x1 + b*x2) == a*pool(x1) + b*pool(x2); and equality with the oracle incl. -1 slots."""
+    from multilevel_gnn_b200 import functional as Fn, graph, synth
+    genes, bsz, slots, C, P = 300, 4, 2000, 32, 3
+    b = synth.multilevel_batch(batch_size=bsz, genes=genes, slots=slots, intra_edges=100, seed=9)
+    n = 3 * genes
+    g = torch.Generator().manual_seed(4)
+    x1, x2 = torch.randn(bsz * n, C, generator=g), torch.randn(bsz * n, C, generator=g)
+    w = torch.randn(slots, P, generator=g)
+    mask = (torch.rand(slots, 1, generator=g) < 0.5).float()
+    lay = graph.pool_layout(b.gene_pca_match.to(DEV), b.raw_indice.to(DEV), n, 438)
+    wm = (w * mask).to(DEV)
+    f = lambda t: Fn.PathwayPool.apply(t.to(DEV), wm, None, lay)
+    assert_close(f(2.0 * x1 - 0.5 * x2), (2.0 * f(x1) - 0.5 * f(x2)).cpu(), what="linearity")
+    ref = R.multilevel_pool(x1, b.gene_pca_match, b.raw_indice, w, mask, n, 438)
+    assert_close(f(x1).reshape(ref.shape), ref, what="pool vs oracle")
+    # wrap_negative (pca_match_mask False): python negative indexing of the reference
+    lay_w = graph.pool_layout(b.gene_pca_match.to(DEV).clone(), b.raw_indice.to(DEV), n, 438, wrap_negative=True)
+    ref_w = R.multilevel_pool(x1, b.gene_pca_match, b.raw_indice, w, mask, n, 438, match_mask=False)
+    got_w = Fn.PathwayPool.apply(x1.to(DEV), wm, None, lay_w)
+    assert_close(got_w.reshape(ref_w.shape), ref_w, what="pool wrap_negative")
+
+
+def test_csr_build_matches_sort(mlg):
+    from multilevel_gnn_b200 import graph
+    n, e = 1000, 20000
+    ei, g = _rand_graph(n, e, 21)
+    ei[:, :50] = ei[0, :50]
+    csr = graph.build_csr(ei.to(DEV), n, drop_self=True, add_self=True)
+    rp, col, eid = csr.rowptr.cpu().long(), csr.col.cpu().long(), csr.eid.cpu().long()
+    keep = ei[0] != ei[1]
+    src = torch.cat([ei[0][keep], torch.arange(n)])
+    dst = torch.cat([ei[1][keep], torch.arange(n)])
+    ids = torch.cat([torch.arange(e)[keep], torch.full((n,), -1)])
+    order = torch.sort(dst, stable=True).indices
+    nnz = int(rp[-1])
+    assert nnz == src.numel()
+    assert torch.equal(rp, torch.cat([torch.zeros(1, dtype=torch.long), torch.cumsum(torch.bincount(dst, minlength=n), 0)]))
+    assert torch.equal(col[:nnz], src[order])
+    assert torch.equal(eid[:nnz], ids[order])
+    empty = graph.build_csr(torch.zeros(2, 0, dtype=torch.long, device=DEV), 7)
+    assert torch.equal(empty.rowptr.cpu(), torch.zeros(8, dtype=torch.int32))
+
+
+def test_errors_are_loud(mlg):
+    from multilevel_gnn_b200 import _cabi
+    conv = mlg.GraphConv(8, 8, conv="sage", act="leakyrelu", mlp_norm="none")
+    with pytest.raises(_cabi.NativeLibraryError):
+        conv(torch.randn(4, 8), torch.zeros(2, 3, dtype=torch.long), torch.ones(3, 1))     # CPU tensors: no fallback
+    L = _cabi.lib()
+    assert L.mlg_gather_sum(None, None, None, None, None, None, 4, 8, 0, 0, 0, 0, None, None) < 0
+    assert "null" in _cabi.last_error()
