@@ -1,0 +1,300 @@
+#!/usr/bin/env python
+"""bench.py -- train graphs/sec on the gbm.yaml shape (BASELINE.json metric), 1..8 B200.
+
+    python bench.py --gpus 1 --steps 20 --warmup 5
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference --steps 2 --warmup 1      # CPU port of the reference path
+
+One step = one pass of the hot path over one batch of 32 synthetic patient graphs per GPU
+(MultilevelGNN forward, BCE + feature loss, backward, gradient all-reduce, Adam), SURVEY.md section 8(d)
+cfg1/cfg5.  `value` times it with the batch resident in HBM; `e2e` re-uploads the batch from pinned
+host memory every step and reads the loss back, as train.py:42,62 do.  Prints ONE JSON line.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", default="gbm", choices=["gbm", "kirc", "lgg"])
+    ap.add_argument("--batch", type=int, default=None, help="graphs per GPU per step (default: the config's batch_size)")
+    ap.add_argument("--cpu-batch", type=int, default=8, help="graphs per CPU-baseline step (bounded sample)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-genconv", action="store_true", help="skip the GENConv aggregation roofline microbench")
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------------------------------
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                                      stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.f.read().splitlines():
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        self.f.close()
+        os.unlink(self.f.name)
+        if sm:
+            out = {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        return out
+
+
+def max_over_ranks(ms, world, dev):
+    if world == 1:
+        return ms
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def barrier(world):
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+
+
+# ----------------------------------------------------------------------------------------------------
+def cpu_reference_run(cfg, cpu_batch, steps, warmup):
+    """Times the CPU port of the reference train step (oracle/) on the host cores."""
+    import multilevel_gnn_b200 as m
+    from oracle.train_port import CpuTrainer
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    args = m.configs.make_args(cfg)
+    torch.manual_seed(0)
+    model = m.MultilevelGNN(args)
+    m.synth.multilevel_params(model)
+    batch = m.synth.multilevel_batch(batch_size=cpu_batch, seed=0)
+    weight = torch.tensor([[0.8, 1.3]]).repeat(cpu_batch, 1)
+    tr = CpuTrainer(model.state_dict(), args, weight, model.pathway_indexs)
+    for _ in range(warmup):
+        tr.step(batch)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        tr.step(batch)
+    dt = time.perf_counter() - t0
+    return cpu_batch * steps / dt, dt / steps * 1e3, cores
+
+
+def genconv_microbench(dev, hbm_peak):
+    """GENConv softmax aggregation (fwd, fused MsgNorm epilogue) at cfg4: N=100k, k=16, H=128."""
+    import multilevel_gnn_b200 as m
+    from multilevel_gnn_b200 import _cabi, functional as Fn, graph
+    n, k, H = 100000, 16, 128
+    g = torch.Generator().manual_seed(0)
+    src = torch.randint(0, n, (n * k,), generator=g)
+    dst = torch.arange(n).repeat_interleave(k)
+    ei = torch.stack([src, dst]).to(dev)
+    x = torch.randn(n, H, generator=g).to(dev)
+    e = torch.randn(n * k, H, generator=g).to(dev)
+    topo = graph.topology(ei, n)
+    scale = torch.ones(1, device=dev)
+    t = torch.ones(1, device=dev)
+
+    def run():
+        return Fn.GenAggregate.apply(x, e, t, 1.0, None, scale, topo, "softmax", 1e-7, Fn.EPI_MSGNORM, True)
+
+    for _ in range(3):
+        run()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 20
+    torch.cuda.synchronize()
+    a.record()
+    for _ in range(reps):
+        run()
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / reps
+    nbytes = 4 * H * (n * k + 2 * n) + 4 * n * k + 4 * (n + 1)
+    gbs = nbytes / ms / 1e6
+    return {"kernel": "gen_fwd_kernel<32,4,softmax> (N=100k,k=16,H=128, fused MsgNorm)", "bound": "hbm",
+            "achieved": round(gbs, 1), "peak": hbm_peak, "unit": "GB/s", "frac": round(gbs / hbm_peak, 4),
+            "ms": round(ms, 4), "bytes": nbytes, "note": "inputs 0.93 GB > L2; 20 back-to-back launches"}
+
+
+# ----------------------------------------------------------------------------------------------------
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    v, ms, cores = cpu_reference_run(a.config, a.cpu_batch, a.steps, a.warmup)
+    sample = "%d train steps of %d synthetic %s-shaped graphs (N=15405, E=92430/graph), %d warm-up" % (
+        a.steps, a.cpu_batch, a.config, a.warmup)
+    print(json.dumps({
+        "impl": "reference", "metric": "train graphs/sec (%s.yaml shape)" % a.config, "value": round(v, 3),
+        "unit": "graphs/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": round(ms, 2),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "%s.yaml multilevel GNN train step, CPU port of the reference path" % a.config,
+                   "graphs_per_step": a.cpu_batch},
+        "cpu_baseline": {"value": round(v, 3), "unit": "graphs/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": round(v, 3), "unit": "graphs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def run_b200(a):
+    import multilevel_gnn_b200 as m
+    from multilevel_gnn_b200 import _cabi
+    from multilevel_gnn_b200.train import Trainer
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU path")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    _cabi.lib()
+    args = m.configs.make_args(a.config)
+    B = a.batch or args.batch_size
+    torch.manual_seed(0)
+    model = m.MultilevelGNN(args)
+    m.synth.multilevel_params(model)
+    model.to(dev)
+    model.pathway_indexs = model.pathway_indexs.to(dev)
+    host = m.synth.multilevel_batch(batch_size=B, seed=100 + rank).pin_memory()
+    host.topology_key = "fold0"
+    weight = torch.tensor([[0.8, 1.3]]).repeat(B, 1).to(dev)
+    tr = Trainer(model, args, weight, world_size=world)
+    resident = host.to(dev)
+    resident.topology_key = "fold0"
+    hbm_peak, peak_src = peaks()
+
+    # ---- resident leg: `value` ----
+    for _ in range(max(a.warmup, 3)):
+        tr.step(resident)
+    timer = _cabi.KernelTimer()
+    barrier(world)
+    sampler = ClockSampler(local) if rank == 0 else None
+    _cabi.TIMER = timer
+    l0 = _cabi.LAUNCH_COUNT
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(a.steps):
+        loss = tr.step(resident)
+    e1.record()
+    barrier(world)
+    _cabi.TIMER = None
+    launches = _cabi.LAUNCH_COUNT - l0
+    ms_total = max_over_ranks(e0.elapsed_time(e1), world, dev)
+    clocks = sampler.stop() if sampler else None
+    ksum = timer.summary()
+
+    # ---- end-to-end leg: pinned host batch -> device every step, loss read back ----
+    for _ in range(2):
+        float(tr.step(host.to(dev, non_blocking=True)).item())
+    barrier(world)
+    h2d = host.nbytes()
+    e0.record()
+    for _ in range(a.steps):
+        float(tr.step(host.to(dev, non_blocking=True)).item())
+    e1.record()
+    barrier(world)
+    ms_e2e = max_over_ranks(e0.elapsed_time(e1), world, dev)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    ms_step = ms_total / a.steps
+    value = B * world * a.steps / (ms_total / 1e3)
+    top = max(ksum.items(), key=lambda kv: kv[1]["ms"]) if ksum else None
+    roof = None
+    if top:
+        tag, d = top
+        gbs = d["bytes"] / d["ms"] / 1e6
+        roof = {"kernel": tag, "bound": "hbm", "achieved": round(gbs, 1), "peak": hbm_peak, "unit": "GB/s",
+                "frac": round(gbs / hbm_peak, 4), "traffic": None, "peak_source": peak_src,
+                "launches": d["launches"], "avg_us": round(d["ms"] / d["launches"] * 1e3, 2),
+                "share_of_step": round(d["ms"] / ms_total, 4),
+                "all_kernels": {k: {"ms_per_step": round(v["ms"] / a.steps, 4),
+                                    "GBps": round(v["bytes"] / v["ms"] / 1e6, 1) if v["ms"] > 0 and v["bytes"] else None}
+                                for k, v in sorted(ksum.items())}}
+    line = {
+        "metric": "train graphs/sec (%s.yaml shape)" % a.config, "value": round(value, 2), "unit": "graphs/s",
+        "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": round(ms_step, 4),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "config/%s.yaml MultilevelGNN train step (fwd+bwd+allreduce+Adam), %d graphs/GPU, "
+                               "N=15405 nodes, E=92430 edges/graph, G=25015, P=%d" % (a.config, B, args.pca_dim),
+                   "graphs_per_gpu": B, "parallelism": "dp%d" % world,
+                   "l2": "no flush: per-step working set (~2 GB of activations) exceeds the 126 MB L2"},
+        "e2e": {"value": round(B * world * a.steps / (ms_e2e / 1e3), 2), "unit": "graphs/s",
+                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "ms_per_step": round(ms_e2e / a.steps, 4)},
+        "gpu_launches": launches, "clocks": clocks, "roofline": roof, "loss": float(loss.item()),
+    }
+    if world == 1 and not a.no_genconv:
+        line["genconv_agg"] = genconv_microbench(dev, hbm_peak)
+    if world == 1 and not a.no_cpu_baseline:
+        v, ms, cores = cpu_reference_run(a.config, a.cpu_batch, 2, 1)
+        line["cpu_baseline"] = {"value": round(v, 3), "unit": "graphs/s", "cores": cores, "kind": "port",
+                                "sample": "2 train steps of %d graphs (same shape), 1 warm-up, torch CPU threads=%d"
+                                          % (a.cpu_batch, cores)}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_b200(a)

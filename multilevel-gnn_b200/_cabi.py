@@ -10,7 +10,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libmlg_b200.so")
+LIB_PATH = os.environ.get("MLG_B200_LIB") or os.path.join(_HERE, "lib", "libmlg_b200.so")   # override: kernel A/B tuning
 
 _c_i64, _c_int, _c_f32, _c_vp = ctypes.c_int64, ctypes.c_int, ctypes.c_float, ctypes.c_void_p
 
@@ -75,9 +75,67 @@ def last_error():
     return lib().mlg_last_error().decode()
 
 
+# kernels launched per C call (own kernels only; CUB's sort passes inside mlg_csr_build are not counted)
+_LAUNCHES_PER_CALL = {"mlg_csr_build": 2, "mlg_knn_graph": 2}
+LAUNCH_COUNT = 0
+TIMER = None        # a KernelTimer while bench.py measures per-kernel device time
+
+
 def check(rc, who):
+    global LAUNCH_COUNT
     if rc != 0:
         raise RuntimeError("%s failed (%d): %s" % (who, rc, last_error()))
+    LAUNCH_COUNT += _LAUNCHES_PER_CALL.get(who, 1)
+
+
+class KernelTimer:
+    """CUDA-event spans around tagged kernel launches, on the launching stream (bench.py's roofline leg)."""
+
+    def __init__(self):
+        self.spans = []          # (tag, start_event, end_event, algorithmic_bytes)
+
+    def span(self, tag, nbytes):
+        return _Span(self, tag, nbytes)
+
+    def summary(self):
+        torch.cuda.synchronize()
+        out = {}
+        for tag, a, b, nbytes in self.spans:
+            d = out.setdefault(tag, {"launches": 0, "ms": 0.0, "bytes": 0})
+            d["launches"] += 1
+            d["ms"] += a.elapsed_time(b)
+            d["bytes"] += nbytes
+        return out
+
+
+class _Span:
+    def __init__(self, timer, tag, nbytes):
+        self.timer, self.tag, self.nbytes = timer, tag, nbytes
+
+    def __enter__(self):
+        self.a = torch.cuda.Event(enable_timing=True)
+        self.b = torch.cuda.Event(enable_timing=True)
+        self.a.record()
+
+    def __exit__(self, *exc):
+        self.b.record()
+        self.timer.spans.append((self.tag, self.a, self.b, self.nbytes))
+
+
+class _NoSpan:
+    def __enter__(self):
+        return None
+
+    def __exit__(self, *exc):
+        return False
+
+
+_NOSPAN = _NoSpan()
+
+
+def span(tag, nbytes=0):
+    """with _cabi.span("gather_sum", bytes): ...  -- no-op unless a KernelTimer is installed."""
+    return TIMER.span(tag, nbytes) if TIMER is not None else _NOSPAN
 
 
 def stream_ptr():

@@ -66,6 +66,13 @@ __device__ __forceinline__ void st_stream4(float* p, float4 v) {
                : "memory");
 }
 
+// single-MUFU 2^x (ex2.approx.ftz: rel. error 2^-22, flushes denormal results to 0)
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 template <int W>
 __device__ __forceinline__ float group_sum(float v, unsigned mask) {
 #pragma unroll

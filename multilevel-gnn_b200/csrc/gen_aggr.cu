@@ -9,11 +9,21 @@
 // Mapping: a group of LANES lanes (8/16/32) owns one target row; every lane owns VEC=4 consecutive
 // channels (128-bit loads), so one group covers a chunk of 4*LANES channels and loops over chunks
 // for wider rows.  Column / edge ids of a row are fetched coalesced by the group and broadcast with
-// shuffles; UN=4 edges' source rows and edge-feature rows are requested before any is consumed.
-// Softmax is evaluated online (running max / sum / weighted sum, one exp2 per element).
+// shuffles; UN edges' source rows and edge-feature rows are requested before any is consumed.
+// Softmax is evaluated online with a LAZY running max (refreshed only when an element exceeds it by
+// 2^24), so the common path per element is  add, max, add, fma, ex2, add, fma.
 // HBM-bound: algorithmic bytes fwd = 4H(E + 2N) + 4E + 4(N+1)   (SURVEY.md section 8d).
+#include <type_traits>
+
 #include "common.cuh"
 #include "../../include/mlg_b200.h"
+
+#ifndef MLG_GEN_FWD_MIN_BLOCKS
+#define MLG_GEN_FWD_MIN_BLOCKS 3
+#endif
+#ifndef MLG_GEN_UN
+#define MLG_GEN_UN 4
+#endif
 
 namespace {
 
@@ -24,8 +34,8 @@ struct GenP {
   const int* col;
   const int* eid;
   int n;
-  int H;
-  int mode, learn, epi, raw;
+  unsigned H;
+  int mode, learn, epi;
   float t, p, eps;
   const float* t_dev;
   const float* p_dev;
@@ -44,39 +54,45 @@ struct GenP {
 };
 
 constexpr int kThreads = 256;
-constexpr int UN = 4;
+constexpr int UN = MLG_GEN_UN;
 constexpr float kLo = 1e-7f, kHi = 1e1f;
+constexpr float kLazy = 24.f;  // log2 head-room before the running max is refreshed
+
+// kernel families
+constexpr int K_SOFTMAX = 0, K_POWER = 1, K_SIMPLE = 2;  // SIMPLE: add / mean / max chosen at run time
+// message sources
+constexpr int S_XE = 0, S_X = 1, S_RAW = 2;  // relu(x_j + e) + eps | relu(x_j) + eps | e (given messages)
 
 template <int VEC>
 struct Vec {
   float v[VEC];
 };
 
-template <int VEC>
-__device__ __forceinline__ Vec<VEC> load_gather(const float* p, bool ok) {
+template <int VEC, bool FULL>
+__device__ __forceinline__ Vec<VEC> ld_g(const float* p, bool ok) {
   Vec<VEC> r;
   if (VEC == 4) {
-    float4 t = ok ? ld_gather4(p) : make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 t = (FULL || ok) ? ld_gather4(p) : make_float4(0.f, 0.f, 0.f, 0.f);
     r.v[0] = t.x; r.v[1 % VEC] = t.y; r.v[2 % VEC] = t.z; r.v[3 % VEC] = t.w;
   } else {
-    r.v[0] = ok ? __ldg(p) : 0.f;
+    r.v[0] = (FULL || ok) ? __ldg(p) : 0.f;
   }
   return r;
 }
-template <int VEC>
-__device__ __forceinline__ Vec<VEC> load_stream(const float* p, bool ok) {
+template <int VEC, bool FULL>
+__device__ __forceinline__ Vec<VEC> ld_s(const float* p, bool ok) {
   Vec<VEC> r;
   if (VEC == 4) {
-    float4 t = ok ? ld_stream4(p) : make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 t = (FULL || ok) ? ld_stream4(p) : make_float4(0.f, 0.f, 0.f, 0.f);
     r.v[0] = t.x; r.v[1 % VEC] = t.y; r.v[2 % VEC] = t.z; r.v[3 % VEC] = t.w;
   } else {
-    r.v[0] = ok ? __ldg(p) : 0.f;
+    r.v[0] = (FULL || ok) ? __ldg(p) : 0.f;
   }
   return r;
 }
-template <int VEC>
-__device__ __forceinline__ void store_vec(float* p, const Vec<VEC>& r, bool ok, bool stream) {
-  if (!ok) return;
+template <int VEC, bool FULL>
+__device__ __forceinline__ void st_v(float* p, const Vec<VEC>& r, bool ok, bool stream) {
+  if (!FULL && !ok) return;
   if (VEC == 4) {
     float4 t = make_float4(r.v[0], r.v[1 % VEC], r.v[2 % VEC], r.v[3 % VEC]);
     if (stream) st_stream4(p, t); else st4(p, t);
@@ -86,14 +102,20 @@ __device__ __forceinline__ void store_vec(float* p, const Vec<VEC>& r, bool ok, 
 }
 
 __device__ __forceinline__ float sigmoidf_(float y) { return 1.f / (1.f + expf(-y)); }
+// row r of a row-major [*, H] fp32 matrix: one IMAD.WIDE.U32 + 64-bit add
+__device__ __forceinline__ const float* row_ptr(const float* base, unsigned r, unsigned H) {
+  return base + (size_t)r * H;
+}
+__device__ __forceinline__ float* row_ptr(float* base, unsigned r, unsigned H) { return base + (size_t)r * H; }
 
 // ------------------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------------------
-template <int LANES, int VEC, int MODE, bool HAS_E>
-__global__ void __launch_bounds__(kThreads) gen_fwd_kernel(GenP P) {
+template <int LANES, int VEC, int KIND, int SRC, bool FULL>
+__global__ void __launch_bounds__(kThreads, MLG_GEN_FWD_MIN_BLOCKS) gen_fwd_kernel(const GenP P) {
   constexpr int RPW = 32 / LANES;
   constexpr int CW = LANES * VEC;  // channels per chunk
+  constexpr bool HAS_X = SRC != S_RAW, HAS_E = SRC != S_X, RAW = SRC == S_RAW;
   const int lane = threadIdx.x & 31;
   const int sub = lane / LANES, sl = lane % LANES;
   const unsigned gmask = (LANES == 32) ? 0xffffffffu : (((1u << LANES) - 1u) << (sub * LANES));
@@ -101,8 +123,8 @@ __global__ void __launch_bounds__(kThreads) gen_fwd_kernel(GenP P) {
   const long long row = warp * RPW + sub;
   if (row >= P.n) return;  // group-uniform exit; no block-level sync in this kernel
 
-  const int H = P.H;
-  const bool raw = P.raw != 0;  // messages given directly in e (GenMessagePassing.aggregate drop-in)
+  const unsigned H = P.H;
+  const int mode = P.mode;
   const int beg = __ldg(P.rowptr + row), end = __ldg(P.rowptr + row + 1);
   const int deg = end - beg;
   const float t = P.t_dev ? __ldg(P.t_dev) : P.t;
@@ -112,8 +134,9 @@ __global__ void __launch_bounds__(kThreads) gen_fwd_kernel(GenP P) {
   float degpow = 1.f;
   if (P.y_dev) degpow = powf((float)deg, sigmoidf_(__ldg(P.y_dev)));
   const int nchunks = (H + CW - 1) / CW;
-  const float* xrow = P.x + (size_t)row * H;
-  float* mrow = P.m + (size_t)row * H;
+  const float* xrow = HAS_X ? row_ptr(P.x, (unsigned)row, H) : nullptr;
+  float* mrow = row_ptr(P.m, (unsigned)row, H);
+  const bool has_eid = HAS_E && P.eid != nullptr;
 
   float sx2 = 0.f, sm2 = 0.f;
   Vec<VEC> out, xi;
@@ -121,78 +144,108 @@ __global__ void __launch_bounds__(kThreads) gen_fwd_kernel(GenP P) {
   for (int k = 0; k < VEC; ++k) out.v[k] = xi.v[k] = 0.f;
 
   for (int ch = 0; ch < nchunks; ++ch) {
-    const int c = ch * CW + sl * VEC;
-    const bool cok = c < H;
+    const unsigned c = ch * CW + sl * VEC;
+    const bool cok = FULL || c < H;
+    const float* xc = HAS_X ? P.x + c : nullptr;
+    const float* ec = HAS_E ? P.e + c : nullptr;
     float a0[VEC], a1[VEC], a2[VEC];
 #pragma unroll
     for (int k = 0; k < VEC; ++k) {
-      a0[k] = (MODE == MLG_AGGR_SOFTMAX || MODE == MLG_AGGR_MAX) ? -INFINITY : 0.f;
+      a0[k] = (KIND == K_SOFTMAX || (KIND == K_SIMPLE && mode == MLG_AGGR_MAX)) ? -INFINITY : 0.f;
       a1[k] = 0.f;
       a2[k] = 0.f;
     }
     for (int base = beg; base < end; base += LANES) {
       const int q = min(base + sl, end - 1);
-      const int my_col = __ldg(P.col + q);
-      const int my_e = HAS_E ? (P.eid ? __ldg(P.eid + q) : q) : 0;
+      const unsigned my_col = HAS_X ? (unsigned)__ldg(P.col + q) : 0u;
+      const unsigned my_e = has_eid ? (unsigned)__ldg(P.eid + q) : (unsigned)q;  // identity if pre-sorted
       const int cnt = min(LANES, end - base);
-      for (int j = 0; j < cnt; j += UN) {
-        Vec<VEC> xv[UN], ev[UN];
+      // NE edges per step: all 2*NE row loads are issued before any is consumed
+      auto step = [&](auto ne_tag, int j) {
+        constexpr int NE = decltype(ne_tag)::value;
+        Vec<VEC> xv[NE], ev[NE];
 #pragma unroll
-        for (int u = 0; u < UN; ++u) {
-          const int jj = min(j + u, cnt - 1);
-          const int s = __shfl_sync(gmask, my_col, jj, LANES);
-          xv[u] = load_gather<VEC>(P.x + (size_t)s * H + c, cok && !raw);
+        for (int u = 0; u < NE; ++u) {
+          if (HAS_X) {
+            const unsigned s = __shfl_sync(gmask, my_col, j + u, LANES);
+            xv[u] = ld_g<VEC, FULL>(row_ptr(xc, s, H), cok);
+          }
           if (HAS_E) {
-            const int ee = __shfl_sync(gmask, my_e, jj, LANES);
-            ev[u] = load_stream<VEC>(P.e + (size_t)ee * H + c, cok);
+            const unsigned ee = __shfl_sync(gmask, my_e, j + u, LANES);
+            ev[u] = ld_s<VEC, FULL>(row_ptr(ec, ee, H), cok);
           }
         }
 #pragma unroll
-        for (int u = 0; u < UN; ++u) {
-          if (j + u < cnt) {
+        for (int u = 0; u < NE; ++u) {
+          float v[VEC];
 #pragma unroll
-            for (int k = 0; k < VEC; ++k) {
+          for (int k = 0; k < VEC; ++k) {
+            if (RAW) {
+              v[k] = ev[u].v[k];
+            } else {
               const float pre = HAS_E ? xv[u].v[k] + ev[u].v[k] : xv[u].v[k];
-              const float v = raw ? pre : fmaxf(pre, 0.f) + eps;
-              if (MODE == MLG_AGGR_SOFTMAX) {
-                const float z = v * tl2;
-                const float d = z - a0[k];
-                const float ex = exp2f(-fabsf(d));
-                const bool up = d > 0.f;
-                a1[k] = up ? fmaf(a1[k], ex, 1.f) : a1[k] + ex;
-                a2[k] = up ? fmaf(a2[k], ex, v) : fmaf(v, ex, a2[k]);
-                a0[k] = up ? z : a0[k];
-              } else if (MODE == MLG_AGGR_POWER) {
-                const float vc = fminf(fmaxf(v, kLo), kHi);
-                a0[k] += (pw == 1.f) ? vc : powf(vc, pw);
-              } else if (MODE == MLG_AGGR_MAX) {
-                a0[k] = fmaxf(a0[k], v);
-              } else {
-                a0[k] += v;
-              }
+              v[k] = fmaxf(pre, 0.f) + eps;
             }
           }
+          if (KIND == K_SOFTMAX) {
+            float d[VEC];
+            float dm = -INFINITY;
+#pragma unroll
+            for (int k = 0; k < VEC; ++k) {
+              d[k] = fmaf(v[k], tl2, -a0[k]);
+              dm = fmaxf(dm, d[k]);
+            }
+            if (dm > kLazy) {  // rare (always on a row's first edge, where a0 = -inf)
+#pragma unroll
+              for (int k = 0; k < VEC; ++k) {
+                const bool up = d[k] > 0.f;
+                const float sc = ex2_approx(up ? -d[k] : 0.f);  // 2^(old_max - new_max); 0 on the first edge
+                a1[k] *= sc;
+                a2[k] *= sc;
+                a0[k] = up ? v[k] * tl2 : a0[k];
+                d[k] = up ? 0.f : d[k];
+              }
+            }
+#pragma unroll
+            for (int k = 0; k < VEC; ++k) {
+              const float pz = ex2_approx(d[k]);
+              a1[k] += pz;
+              a2[k] = fmaf(v[k], pz, a2[k]);
+            }
+          } else if (KIND == K_POWER) {
+#pragma unroll
+            for (int k = 0; k < VEC; ++k) {
+              const float vc = fminf(fmaxf(v[k], kLo), kHi);
+              a0[k] += (pw == 1.f) ? vc : powf(vc, pw);
+            }
+          } else {
+#pragma unroll
+            for (int k = 0; k < VEC; ++k) a0[k] = (mode == MLG_AGGR_MAX) ? fmaxf(a0[k], v[k]) : a0[k] + v[k];
+          }
         }
-      }
+      };
+      int j = 0;
+      for (; j + UN <= cnt; j += UN) step(std::integral_constant<int, UN>{}, j);
+      for (; j < cnt; ++j) step(std::integral_constant<int, 1>{}, j);
     }
     // finalise this chunk
     Vec<VEC> o, ax;
 #pragma unroll
     for (int k = 0; k < VEC; ++k) {
       float r = 0.f, au = 0.f;
-      if (MODE == MLG_AGGR_SOFTMAX) {
+      if (KIND == K_SOFTMAX) {
         if (deg > 0) {
           r = a2[k] / a1[k];
           au = a0[k] + log2f(a1[k]);
         }
-      } else if (MODE == MLG_AGGR_POWER) {
+      } else if (KIND == K_POWER) {
         const float mean = a0[k] / (float)max(deg, 1);
         au = mean;
         const float cl = fminf(fmaxf(mean, kLo), kHi);
         r = (pw == 1.f) ? cl : powf(cl, 1.f / pw);
-      } else if (MODE == MLG_AGGR_MAX) {
+      } else if (mode == MLG_AGGR_MAX) {
         r = deg > 0 ? a0[k] : 0.f;
-      } else if (MODE == MLG_AGGR_MEAN) {
+      } else if (mode == MLG_AGGR_MEAN) {
         r = a0[k] / (float)max(deg, 1);
       } else {
         r = a0[k];
@@ -201,15 +254,15 @@ __global__ void __launch_bounds__(kThreads) gen_fwd_kernel(GenP P) {
       o.v[k] = r;
       ax.v[k] = au;
     }
-    store_vec<VEC>(mrow + c, o, cok, false);
-    if (P.aux) store_vec<VEC>(P.aux + (size_t)row * H + c, ax, cok, true);
+    st_v<VEC, FULL>(mrow + c, o, cok, false);
+    if (P.aux) st_v<VEC, FULL>(row_ptr(P.aux, (unsigned)row, H) + c, ax, cok, true);
     if (P.epi != MLG_EPI_NONE) {
-      Vec<VEC> xr = load_gather<VEC>(xrow + c, cok);
+      Vec<VEC> xr = ld_g<VEC, FULL>(xrow + c, cok);
       if (P.epi == MLG_EPI_RESIDUAL) {
         Vec<VEC> hv;
 #pragma unroll
         for (int k = 0; k < VEC; ++k) hv.v[k] = xr.v[k] + o.v[k];
-        store_vec<VEC>(P.h + (size_t)row * H + c, hv, cok, false);
+        st_v<VEC, FULL>(row_ptr(P.h, (unsigned)row, H) + c, hv, cok, false);
       } else {
         if (cok) {  // lanes past H hold eps-valued garbage: keep them out of the norms
 #pragma unroll
@@ -230,26 +283,24 @@ __global__ void __launch_bounds__(kThreads) gen_fwd_kernel(GenP P) {
     const float r = sqrtf(sx2);
     const float nm = fmaxf(sqrtf(sm2), 1e-12f);
     const float f = __ldg(P.scale_dev) * r / nm;
+    float* hrow = row_ptr(P.h, (unsigned)row, H);
     for (int ch = 0; ch < nchunks; ++ch) {
-      const int c = ch * CW + sl * VEC;
-      const bool cok = c < H;
+      const unsigned c = ch * CW + sl * VEC;
+      const bool cok = FULL || c < H;
       Vec<VEC> mo, xr;
       if (nchunks == 1) {
         mo = out;
         xr = xi;
       } else {
         // re-read this lane's own writes of m (same thread wrote them: visible without a fence)
-        mo.v[0] = 0.f;
-        if (cok) {
 #pragma unroll
-          for (int k = 0; k < VEC; ++k) mo.v[k] = mrow[c + k];
-        }
-        xr = load_gather<VEC>(xrow + c, cok);
+        for (int k = 0; k < VEC; ++k) mo.v[k] = cok ? mrow[c + k] : 0.f;
+        xr = ld_g<VEC, FULL>(xrow + c, cok);
       }
       Vec<VEC> hv;
 #pragma unroll
       for (int k = 0; k < VEC; ++k) hv.v[k] = fmaf(f, mo.v[k], xr.v[k]);
-      store_vec<VEC>(P.h + (size_t)row * H + c, hv, cok, false);
+      st_v<VEC, FULL>(hrow + c, hv, cok, false);
     }
   }
 }
@@ -257,10 +308,11 @@ __global__ void __launch_bounds__(kThreads) gen_fwd_kernel(GenP P) {
 // ------------------------------------------------------------------------------------------------
 // backward
 // ------------------------------------------------------------------------------------------------
-template <int LANES, int VEC, int MODE, bool HAS_E>
-__global__ void __launch_bounds__(kThreads) gen_bwd_kernel(GenP P) {
+template <int LANES, int VEC, int KIND, int SRC, bool FULL>
+__global__ void __launch_bounds__(kThreads) gen_bwd_kernel(const GenP P) {
   constexpr int RPW = 32 / LANES;
   constexpr int CW = LANES * VEC;
+  constexpr bool HAS_X = SRC != S_RAW, HAS_E = SRC != S_X, RAW = SRC == S_RAW;
   __shared__ float red[3 * 32];
   const int lane = threadIdx.x & 31;
   const int sub = lane / LANES, sl = lane % LANES;
@@ -272,8 +324,9 @@ __global__ void __launch_bounds__(kThreads) gen_bwd_kernel(GenP P) {
   float acc[3] = {0.f, 0.f, 0.f};  // d/dt (or d/dp), d/dy_raw, d/dmsg_scale
 
   if (active) {
-    const int H = P.H;
-    const bool raw = P.raw != 0;
+    const unsigned H = P.H;
+    const int mode = P.mode;
+    const bool learn = P.learn != 0;
     const int beg = __ldg(P.rowptr + row), end = __ldg(P.rowptr + row + 1);
     const int deg = end - beg;
     const float t = P.t_dev ? __ldg(P.t_dev) : P.t;
@@ -288,19 +341,20 @@ __global__ void __launch_bounds__(kThreads) gen_bwd_kernel(GenP P) {
     }
     const float inv_deg = 1.f / (float)max(deg, 1);
     const int nchunks = (H + CW - 1) / CW;
-    const float* xrow = P.x + (size_t)row * H;
-    const float* mrow = P.m_in + (size_t)row * H;
-    const float* grow = P.g + (size_t)row * H;
+    const float* xrow = HAS_X ? row_ptr(P.x, (unsigned)row, H) : nullptr;
+    const float* mrow = row_ptr(P.m_in, (unsigned)row, H);
+    const float* grow = row_ptr(P.g, (unsigned)row, H);
+    const bool has_eid = P.eid != nullptr;
 
     // --- MsgNorm statistics of this row (one sweep over channels) ---
     float f_gm = 1.f, f_u = 0.f, f_x = 0.f;  // g_m = f_gm * g - f_u * m ; g_x = g + f_x * x
     if (P.epi == MLG_EPI_MSGNORM) {
       float sx2 = 0.f, sm2 = 0.f, sgm = 0.f;
       for (int ch = 0; ch < nchunks; ++ch) {
-        const int c = ch * CW + sl * VEC;
-        const bool cok = c < H;
-        Vec<VEC> xr = load_gather<VEC>(xrow + c, cok), mr = load_gather<VEC>(mrow + c, cok),
-                 gr = load_gather<VEC>(grow + c, cok);
+        const unsigned c = ch * CW + sl * VEC;
+        const bool cok = FULL || c < H;
+        Vec<VEC> xr = ld_g<VEC, FULL>(xrow + c, cok), mr = ld_g<VEC, FULL>(mrow + c, cok),
+                 gr = ld_g<VEC, FULL>(grow + c, cok);
 #pragma unroll
         for (int k = 0; k < VEC; ++k) {
           sx2 = fmaf(xr.v[k], xr.v[k], sx2);
@@ -322,14 +376,17 @@ __global__ void __launch_bounds__(kThreads) gen_bwd_kernel(GenP P) {
     }
 
     for (int ch = 0; ch < nchunks; ++ch) {
-      const int c = ch * CW + sl * VEC;
-      const bool cok = c < H;
-      Vec<VEC> gr = load_gather<VEC>(grow + c, cok);
-      Vec<VEC> mr = load_gather<VEC>(mrow + c, cok);
+      const unsigned c = ch * CW + sl * VEC;
+      const bool cok = FULL || c < H;
+      const float* xc = HAS_X ? P.x + c : nullptr;
+      const float* ec = HAS_E ? P.e + c : nullptr;
+      float* gec = P.g_edge + c;
+      Vec<VEC> gr = ld_g<VEC, FULL>(grow + c, cok);
+      Vec<VEC> mr = ld_g<VEC, FULL>(mrow + c, cok);
       Vec<VEC> au;
-      au.v[0] = 0.f;
-      if (MODE == MLG_AGGR_SOFTMAX || MODE == MLG_AGGR_POWER)
-        au = load_gather<VEC>(P.aux_in + (size_t)row * H + c, cok);
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) au.v[k] = 0.f;
+      if (KIND != K_SIMPLE) au = ld_g<VEC, FULL>(row_ptr(P.aux_in, (unsigned)row, H) + c, cok);
       float gin[VEC], oi[VEC], k1[VEC], k2[VEC];
       bool taken[VEC];
       // direct term into g_x and gradient w.r.t. the aggregated message
@@ -341,11 +398,11 @@ __global__ void __launch_bounds__(kThreads) gen_bwd_kernel(GenP P) {
         } else if (P.epi == MLG_EPI_RESIDUAL) {
           gx = gr;
         } else {
-          Vec<VEC> xr = load_gather<VEC>(xrow + c, cok);
+          Vec<VEC> xr = ld_g<VEC, FULL>(xrow + c, cok);
 #pragma unroll
           for (int k = 0; k < VEC; ++k) gx.v[k] = fmaf(f_x, xr.v[k], gr.v[k]);
         }
-        store_vec<VEC>(P.g_x + (size_t)row * H + c, gx, cok, false);
+        st_v<VEC, FULL>(row_ptr(P.g_x, (unsigned)row, H) + c, gx, cok, false);
       }
 #pragma unroll
       for (int k = 0; k < VEC; ++k) {
@@ -356,76 +413,84 @@ __global__ void __launch_bounds__(kThreads) gen_bwd_kernel(GenP P) {
         k1[k] = 0.f;
         k2[k] = 0.f;
         taken[k] = false;
-        if (MODE == MLG_AGGR_POWER) {
+        if (KIND == K_POWER) {
           const float mean = au.v[k];
           const bool inr = mean >= kLo && mean <= kHi;
           const float cl = fminf(fmaxf(mean, kLo), kHi);
           // d out / d v_e = inr * (oi/cl) * vc^(p-1) / deg
           k1[k] = inr ? gin[k] * oi[k] / cl * inv_deg : 0.f;
-          if (P.learn && cok) {
+          if (learn && cok) {
             acc[0] = fmaf(gin[k] * oi[k], -logf(cl) / (pw * pw), acc[0]);
             k2[k] = inr ? gin[k] * oi[k] / (pw * cl) * inv_deg : 0.f;
           }
-        } else if (MODE == MLG_AGGR_MEAN) {
+        } else if (KIND == K_SIMPLE && mode == MLG_AGGR_MEAN) {
           k1[k] = gin[k] * inv_deg;
         }
       }
 
       for (int base = beg; base < end; base += LANES) {
         const int q = min(base + sl, end - 1);
-        const int my_col = __ldg(P.col + q);
-        const int my_e = P.eid ? __ldg(P.eid + q) : q;
+        const unsigned my_col = HAS_X ? (unsigned)__ldg(P.col + q) : 0u;
+        const unsigned my_e = has_eid ? (unsigned)__ldg(P.eid + q) : (unsigned)q;
         const int cnt = min(LANES, end - base);
-        for (int j = 0; j < cnt; j += UN) {
-          Vec<VEC> xv[UN], ev[UN];
-          int eo[UN];
+        auto step = [&](auto ne_tag, int j) {
+          constexpr int NE = decltype(ne_tag)::value;
+          Vec<VEC> xv[NE], ev[NE];
+          unsigned eo[NE];
 #pragma unroll
-          for (int u = 0; u < UN; ++u) {
-            const int jj = min(j + u, cnt - 1);
-            const int s = __shfl_sync(gmask, my_col, jj, LANES);
-            eo[u] = __shfl_sync(gmask, my_e, jj, LANES);
-            xv[u] = load_gather<VEC>(P.x + (size_t)s * H + c, cok && !raw);
-            if (HAS_E) ev[u] = load_stream<VEC>(P.e + (size_t)eo[u] * H + c, cok);
-          }
-#pragma unroll
-          for (int u = 0; u < UN; ++u) {
-            if (j + u < cnt) {
-              Vec<VEC> ge;
-#pragma unroll
-              for (int k = 0; k < VEC; ++k) {
-                const float pre = HAS_E ? xv[u].v[k] + ev[u].v[k] : xv[u].v[k];
-                const float v = raw ? pre : fmaxf(pre, 0.f) + eps;
-                float gv;
-                if (MODE == MLG_AGGR_SOFTMAX) {
-                  const float w = exp2f(fmaf(v, tl2, -au.v[k]));
-                  const float gw = gin[k] * w;
-                  if (P.learn) {
-                    const float dv = v - oi[k];
-                    gv = gw * fmaf(t, dv, 1.f);
-                    if (cok) acc[0] = fmaf(gw * v, dv, acc[0]);
-                  } else {
-                    gv = gw;
-                  }
-                } else if (MODE == MLG_AGGR_POWER) {
-                  const float vc = fminf(fmaxf(v, kLo), kHi);
-                  const float vp1 = (pw == 1.f) ? 1.f : powf(vc, pw - 1.f);
-                  gv = (v <= kHi) ? k1[k] * vp1 : 0.f;
-                  if (P.learn && cok) acc[0] = fmaf(k2[k] * vp1 * vc, logf(vc), acc[0]);
-                } else if (MODE == MLG_AGGR_MAX) {
-                  const bool hit = (!taken[k]) && (v == oi[k]);
-                  gv = hit ? gin[k] : 0.f;
-                  taken[k] = taken[k] || hit;
-                } else if (MODE == MLG_AGGR_MEAN) {
-                  gv = k1[k];
-                } else {
-                  gv = gin[k];
-                }
-                ge.v[k] = (raw || pre > 0.f) ? gv : 0.f;
-              }
-              store_vec<VEC>(P.g_edge + (size_t)eo[u] * H + c, ge, cok, true);
+          for (int u = 0; u < NE; ++u) {
+            eo[u] = __shfl_sync(gmask, my_e, j + u, LANES);
+            if (HAS_X) {
+              const unsigned s = __shfl_sync(gmask, my_col, j + u, LANES);
+              xv[u] = ld_g<VEC, FULL>(row_ptr(xc, s, H), cok);
             }
+            if (HAS_E) ev[u] = ld_s<VEC, FULL>(row_ptr(ec, eo[u], H), cok);
           }
-        }
+#pragma unroll
+          for (int u = 0; u < NE; ++u) {
+            Vec<VEC> ge;
+#pragma unroll
+            for (int k = 0; k < VEC; ++k) {
+              float pre, v;
+              if (RAW) {
+                pre = v = ev[u].v[k];
+              } else {
+                pre = HAS_E ? xv[u].v[k] + ev[u].v[k] : xv[u].v[k];
+                v = fmaxf(pre, 0.f) + eps;
+              }
+              float gv;
+              if (KIND == K_SOFTMAX) {
+                const float w = ex2_approx(fmaf(v, tl2, -au.v[k]));
+                const float gw = gin[k] * w;
+                if (learn) {
+                  const float dv = v - oi[k];
+                  gv = gw * fmaf(t, dv, 1.f);
+                  if (cok) acc[0] = fmaf(gw * v, dv, acc[0]);
+                } else {
+                  gv = gw;
+                }
+              } else if (KIND == K_POWER) {
+                const float vc = fminf(fmaxf(v, kLo), kHi);
+                const float vp1 = (pw == 1.f) ? 1.f : powf(vc, pw - 1.f);
+                gv = (v <= kHi) ? k1[k] * vp1 : 0.f;
+                if (learn && cok) acc[0] = fmaf(k2[k] * vp1 * vc, logf(vc), acc[0]);
+              } else if (mode == MLG_AGGR_MAX) {
+                const bool hit = (!taken[k]) && (v == oi[k]);
+                gv = hit ? gin[k] : 0.f;
+                taken[k] = taken[k] || hit;
+              } else if (mode == MLG_AGGR_MEAN) {
+                gv = k1[k];
+              } else {
+                gv = gin[k];
+              }
+              ge.v[k] = (RAW || pre > 0.f) ? gv : 0.f;
+            }
+            st_v<VEC, FULL>(row_ptr(gec, eo[u], H), ge, cok, true);
+          }
+        };
+        int j = 0;
+        for (; j + UN <= cnt; j += UN) step(std::integral_constant<int, UN>{}, j);
+        for (; j < cnt; ++j) step(std::integral_constant<int, 1>{}, j);
       }
     }
   }
@@ -442,53 +507,55 @@ __global__ void __launch_bounds__(kThreads) gen_bwd_kernel(GenP P) {
 
 struct Cfg {
   int lanes, vec;
+  bool full;
 };
 inline Cfg pick_cfg(long long H) {
-  if (H % 4 != 0) return {32, 1};
-  if (H <= 32) return {8, 4};
-  if (H <= 64) return {16, 4};
-  return {32, 4};
+  if (H % 4 != 0) return {32, 1, false};
+  if (H <= 32) return {8, 4, H == 32};
+  if (H <= 64) return {16, 4, H == 64};
+  return {32, 4, H % 128 == 0};
 }
 inline long long grid_for(long long n, const Cfg& c) {
   const int rows_per_block = (kThreads / 32) * (32 / c.lanes);
   return (n + rows_per_block - 1) / rows_per_block;
 }
 
-template <int MODE, bool HAS_E>
-void launch_fwd(const GenP& P, const Cfg& c, cudaStream_t st) {
-  const unsigned grid = (unsigned)grid_for(P.n, c);
-  if (c.vec == 1) gen_fwd_kernel<32, 1, MODE, HAS_E><<<grid, kThreads, 0, st>>>(P);
-  else if (c.lanes == 8) gen_fwd_kernel<8, 4, MODE, HAS_E><<<grid, kThreads, 0, st>>>(P);
-  else if (c.lanes == 16) gen_fwd_kernel<16, 4, MODE, HAS_E><<<grid, kThreads, 0, st>>>(P);
-  else gen_fwd_kernel<32, 4, MODE, HAS_E><<<grid, kThreads, 0, st>>>(P);
+template <bool FWD, int LANES, int VEC, int KIND, int SRC, bool FULL>
+void launch(const GenP& P, unsigned grid, cudaStream_t st) {
+  if (FWD) gen_fwd_kernel<LANES, VEC, KIND, SRC, FULL><<<grid, kThreads, 0, st>>>(P);
+  else gen_bwd_kernel<LANES, VEC, KIND, SRC, FULL><<<grid, kThreads, 0, st>>>(P);
 }
-template <int MODE, bool HAS_E>
-void launch_bwd(const GenP& P, const Cfg& c, cudaStream_t st) {
+
+template <bool FWD, int KIND, int SRC>
+void launch_cfg(const GenP& P, const Cfg& c, cudaStream_t st) {
   const unsigned grid = (unsigned)grid_for(P.n, c);
-  if (c.vec == 1) gen_bwd_kernel<32, 1, MODE, HAS_E><<<grid, kThreads, 0, st>>>(P);
-  else if (c.lanes == 8) gen_bwd_kernel<8, 4, MODE, HAS_E><<<grid, kThreads, 0, st>>>(P);
-  else if (c.lanes == 16) gen_bwd_kernel<16, 4, MODE, HAS_E><<<grid, kThreads, 0, st>>>(P);
-  else gen_bwd_kernel<32, 4, MODE, HAS_E><<<grid, kThreads, 0, st>>>(P);
+  if (c.vec == 1) launch<FWD, 32, 1, KIND, SRC, false>(P, grid, st);
+  else if (c.lanes == 8) { if (c.full) launch<FWD, 8, 4, KIND, SRC, true>(P, grid, st); else launch<FWD, 8, 4, KIND, SRC, false>(P, grid, st); }
+  else if (c.lanes == 16) { if (c.full) launch<FWD, 16, 4, KIND, SRC, true>(P, grid, st); else launch<FWD, 16, 4, KIND, SRC, false>(P, grid, st); }
+  else { if (c.full) launch<FWD, 32, 4, KIND, SRC, true>(P, grid, st); else launch<FWD, 32, 4, KIND, SRC, false>(P, grid, st); }
 }
 
 template <bool FWD>
 int dispatch(const GenP& P, cudaStream_t st) {
   const Cfg c = pick_cfg(P.H);
-  const bool he = P.e != nullptr;
-#define MLG_GO(M)                                                        \
-  if (FWD) { if (he) launch_fwd<M, true>(P, c, st); else launch_fwd<M, false>(P, c, st); } \
-  else     { if (he) launch_bwd<M, true>(P, c, st); else launch_bwd<M, false>(P, c, st); }
+  const int src = P.x == nullptr ? S_RAW : (P.e != nullptr ? S_XE : S_X);
+  int kind;
   switch (P.mode) {
-    case MLG_AGGR_SOFTMAX: MLG_GO(MLG_AGGR_SOFTMAX); break;
-    case MLG_AGGR_POWER: MLG_GO(MLG_AGGR_POWER); break;
-    case MLG_AGGR_ADD: MLG_GO(MLG_AGGR_ADD); break;
-    case MLG_AGGR_MEAN: MLG_GO(MLG_AGGR_MEAN); break;
-    case MLG_AGGR_MAX: MLG_GO(MLG_AGGR_MAX); break;
+    case MLG_AGGR_SOFTMAX: kind = K_SOFTMAX; break;
+    case MLG_AGGR_POWER: kind = K_POWER; break;
+    case MLG_AGGR_ADD: case MLG_AGGR_MEAN: case MLG_AGGR_MAX: kind = K_SIMPLE; break;
     default:
       mlg_set_error("mlg_gen_aggr: unknown mode %d", P.mode);
       return MLG_ERR_ARG;
   }
-#undef MLG_GO
+#define MLG_SRC(K)                                                    \
+  if (src == S_XE) launch_cfg<FWD, K, S_XE>(P, c, st);                \
+  else if (src == S_X) launch_cfg<FWD, K, S_X>(P, c, st);             \
+  else launch_cfg<FWD, K, S_RAW>(P, c, st);
+  if (kind == K_SOFTMAX) { MLG_SRC(K_SOFTMAX) }
+  else if (kind == K_POWER) { MLG_SRC(K_POWER) }
+  else { MLG_SRC(K_SIMPLE) }
+#undef MLG_SRC
   return MLG_OK;
 }
 
@@ -519,7 +586,7 @@ extern "C" int mlg_gen_aggr_fwd(const float* x, const float* e, const int32_t* r
   GenP P;
   memset(&P, 0, sizeof(P));
   P.x = x; P.e = e; P.rowptr = rowptr; P.col = col; P.eid = eid;
-  P.n = (int)n; P.H = (int)H; P.mode = mode; P.epi = epilogue; P.raw = x ? 0 : 1;
+  P.n = (int)n; P.H = (unsigned)H; P.mode = mode; P.epi = epilogue;
   P.t = t; P.p = p; P.eps = eps; P.t_dev = t_dev; P.p_dev = p_dev; P.y_dev = y_dev;
   P.scale_dev = msg_scale_dev; P.m = m; P.aux = aux; P.h = h;
   rc = dispatch<true>(P, (cudaStream_t)stream);
@@ -548,7 +615,7 @@ extern "C" int mlg_gen_aggr_bwd(const float* g, const float* x, const float* e, 
   GenP P;
   memset(&P, 0, sizeof(P));
   P.x = x; P.e = e; P.rowptr = rowptr; P.col = col; P.eid = eid;
-  P.n = (int)n; P.H = (int)H; P.mode = mode; P.epi = epilogue; P.learn = learn; P.raw = x ? 0 : 1;
+  P.n = (int)n; P.H = (unsigned)H; P.mode = mode; P.epi = epilogue; P.learn = learn;
   P.t = t; P.p = p; P.eps = eps; P.t_dev = t_dev; P.p_dev = p_dev; P.y_dev = y_dev;
   P.scale_dev = msg_scale_dev; P.g = g; P.m_in = m; P.aux_in = aux;
   P.g_edge = g_edge; P.g_x = g_x; P.partials = partials;

@@ -24,13 +24,15 @@ def _scalar_args(v):
 
 
 def gather_sum(src, rowptr, idx, n_rows, val=None, pre=None, post=None, src_mod=0, post_mode=0,
-               relative=False, out=None, accumulate=False):
+               relative=False, out=None, accumulate=False, tag="gather_sum"):
     """Raw (non-differentiable) call of mlg_gather_sum."""
     L = _cabi.lib()
     C = src.shape[1]
     if out is None:
         out = torch.empty(n_rows, C, dtype=torch.float32, device=src.device)
-    with torch.cuda.device(src.device):
+    # algorithmic bytes (SURVEY.md section 8d): rows read once + rows written once + (idx, val) per entry
+    nbytes = 4 * C * n_rows * 2 + 8 * idx.numel()
+    with torch.cuda.device(src.device), _cabi.span(tag, nbytes):
         _cabi.check(L.mlg_gather_sum(_cabi.fptr(src), _cabi.iptr(rowptr), _cabi.iptr(idx),
                                      _cabi.fptr(val, True), _cabi.fptr(pre, True), _cabi.fptr(post, True),
                                      n_rows, C, src_mod, post_mode, int(relative), int(accumulate),
@@ -65,7 +67,9 @@ class GenAggregate(torch.autograd.Function):
         m = torch.empty(n, H, dtype=torch.float32, device=ref.device)
         aux = torch.empty_like(m) if (need_grad and mode in (0, 1)) else None
         h = torch.empty_like(m) if epilogue != EPI_NONE else None
-        with torch.cuda.device(ref.device):
+        n_entries = csr.col.numel()
+        ctx_bytes = 4 * H * ((n_entries if e is not None else 0) + 2 * n) + 4 * n_entries + 4 * (n + 1)
+        with torch.cuda.device(ref.device), _cabi.span("gen_aggr_fwd", ctx_bytes):
             _cabi.check(L.mlg_gen_aggr_fwd(
                 _cabi.fptr(xd, True), _cabi.fptr(ed, True), _cabi.iptr(csr.rowptr), _cabi.iptr(csr.col),
                 _cabi.iptr(csr.eid), n, H, mode, t_h, t_d, p_h, p_d, y_d, float(eps), epilogue, s_d,
@@ -102,7 +106,8 @@ class GenAggregate(torch.autograd.Function):
         g_x = torch.empty(n, H, dtype=torch.float32, device=dev)
         rows = L.mlg_gen_aggr_bwd_partial_rows(n, H)
         partials = torch.empty(rows, 4, dtype=torch.float32, device=dev)
-        with torch.cuda.device(dev):
+        bwd_bytes = 4 * H * (2 * n_edges + 3 * n) + 8 * n_edges          # SURVEY.md section 8d (no learn_t)
+        with torch.cuda.device(dev), _cabi.span("gen_aggr_bwd", bwd_bytes):
             _cabi.check(L.mlg_gen_aggr_bwd(
                 _cabi.fptr(g), _cabi.fptr(xd, True), _cabi.fptr(ed, True), _cabi.iptr(csr.rowptr),
                 _cabi.iptr(csr.col), _cabi.iptr(csr.eid), n, H, ctx.mode, int(ctx.learn), t_h, t_d, p_h, p_d,
@@ -112,7 +117,7 @@ class GenAggregate(torch.autograd.Function):
         gx = None
         if ctx.has_x and needs[0]:
             bw = topo.bwd      # rows = sources; eid = edge ids whose g_edge rows are summed
-            gx = gather_sum(g_edge, bw.rowptr, bw.eid, n, out=g_x, accumulate=True)
+            gx = gather_sum(g_edge, bw.rowptr, bw.eid, n, out=g_x, accumulate=True, tag="gen_aggr_bwd_src")
         ge = g_edge[:n_edges].reshape(ctx.e_shape) if (ctx.has_e and needs[1]) else None
         sums = None
 
@@ -139,7 +144,8 @@ class SageAggregate(torch.autograd.Function):
         _cabi.require_cuda(x)
         xd = _f32c(x.detach())
         csr = topo.fwd
-        out = gather_sum(xd, csr.rowptr, csr.col, topo.n, val=topo.fwd_val, post_mode=1, relative=relative)
+        out = gather_sum(xd, csr.rowptr, csr.col, topo.n, val=topo.fwd_val, post_mode=1, relative=relative,
+                         tag="sage_aggr_fwd")
         ctx.topo, ctx.relative = topo, bool(relative)
         return out
 
@@ -149,7 +155,7 @@ class SageAggregate(torch.autograd.Function):
         g = _f32c(g)
         bw = topo.bwd
         # g_x[j] = sum_{i: j->i} w_ij * g[i] / cnt_i   (entries of the by-source CSR: col = target i)
-        gx = gather_sum(g, bw.rowptr, bw.col, topo.n, val=topo.bwd_val, pre=topo.inv_cnt)
+        gx = gather_sum(g, bw.rowptr, bw.col, topo.n, val=topo.bwd_val, pre=topo.inv_cnt, tag="sage_aggr_bwd")
         if ctx.relative:
             gx = gx - g
         return gx, None, None
@@ -199,7 +205,8 @@ class PathwayPool(torch.autograd.Function):
         B, N, G, S = layout.B, layout.N, layout.G, layout.S
         C, P = xd.shape[1], wd.shape[1]
         out = torch.empty(B, C, S, P, dtype=torch.float32, device=xd.device)
-        with torch.cuda.device(xd.device):
+        nbytes = 4 * C * B * N + 4 * B * N + 12 * G + 4 * B * C * S * P
+        with torch.cuda.device(xd.device), _cabi.span("pool_fwd", nbytes):
             _cabi.check(L.mlg_pool_fwd(_cabi.fptr(xd), _cabi.fptr(vm, True), _cabi.lptr(layout.match),
                                        _cabi.fptr(wd), _cabi.iptr(layout.seg.rowptr), _cabi.iptr(layout.seg.col),
                                        B, N, C, G, S, P, int(layout.wrap_negative), _cabi.fptr(out),

@@ -100,16 +100,31 @@ def _key(t):
     return None if t is None else (t.data_ptr(), tuple(t.shape), t._version, str(t.device))
 
 
-def topology(edge_index, n_nodes, self_loops=False, edge_weight=None):
-    """Cached Topology for this (edge_index, edge_weight) pair."""
+def topology(edge_index, n_nodes, self_loops=False, edge_weight=None, static_key=None):
+    """Cached Topology for this (edge_index, edge_weight) pair.
+
+    ``static_key`` (any hashable) is the caller's promise that the edge list is the same as on the
+    previous call with that key -- the reference's loader installs ONE edge list for all patients of a
+    fold (dataloader/multiloader.py:687-698), so a training loop that re-uploads the batch every step
+    can still reuse the structure built for the first one."""
     key = (_key(edge_index), n_nodes, self_loops, _key(edge_weight))
     hit = _CACHE.get(key)
     if hit is not None:
         _CACHE.move_to_end(key)
         return hit[0]
-    topo = Topology(edge_index, n_nodes, self_loops, edge_weight)
+    topo = None
+    if static_key is not None:
+        skey = ("static", static_key, tuple(edge_index.shape), n_nodes, self_loops, edge_weight is not None)
+        hit = _CACHE.get(skey)
+        if hit is not None:
+            topo = hit[0]
+        else:
+            topo = Topology(edge_index, n_nodes, self_loops, edge_weight)
+            _CACHE[skey] = (topo, edge_index, edge_weight)
+    if topo is None:
+        topo = Topology(edge_index, n_nodes, self_loops, edge_weight)
     _CACHE[key] = (topo, edge_index, edge_weight)   # keep the tensors alive so the pointers stay unique
-    if len(_CACHE) > _CACHE_MAX:
+    while len(_CACHE) > _CACHE_MAX:
         _CACHE.popitem(last=False)
     return topo
 
@@ -155,14 +170,24 @@ class PoolLayout:
 _POOL_CACHE = collections.OrderedDict()
 
 
-def pool_layout(gene_pca_match, raw_indice, nodes_per_graph, n_segments, wrap_negative=False):
+def pool_layout(gene_pca_match, raw_indice, nodes_per_graph, n_segments, wrap_negative=False, static_key=None):
     key = (_key(gene_pca_match), _key(raw_indice), nodes_per_graph, n_segments, wrap_negative)
     hit = _POOL_CACHE.get(key)
     if hit is not None:
         _POOL_CACHE.move_to_end(key)
         return hit[0]
-    lay = PoolLayout(gene_pca_match, raw_indice, nodes_per_graph, n_segments, wrap_negative)
+    lay = None
+    if static_key is not None:
+        skey = ("static", static_key, tuple(gene_pca_match.shape), nodes_per_graph, n_segments, wrap_negative)
+        hit = _POOL_CACHE.get(skey)
+        if hit is not None:
+            lay = hit[0]
+        else:
+            lay = PoolLayout(gene_pca_match, raw_indice, nodes_per_graph, n_segments, wrap_negative)
+            _POOL_CACHE[skey] = (lay, gene_pca_match, raw_indice)
+    if lay is None:
+        lay = PoolLayout(gene_pca_match, raw_indice, nodes_per_graph, n_segments, wrap_negative)
     _POOL_CACHE[key] = (lay, gene_pca_match, raw_indice)
-    if len(_POOL_CACHE) > _CACHE_MAX:
+    while len(_POOL_CACHE) > _CACHE_MAX:
         _POOL_CACHE.popitem(last=False)
     return lay

@@ -135,6 +135,10 @@ class MultilevelGNN(nn.Module):
                 edge_index, edge_attr = edge_index[:, :n_edge].contiguous(), edge_attr[:n_edge]
             edge_index = edge_index.to(x.device)
             edge_attr = edge_attr.to(x.device) if args.weighted_edge else None
+            static_key = getattr(input_batch, "topology_key", None)
+            if static_key is not None and edge_attr is not None:
+                # fold-constant edge list (multiloader.py:687-698): reuse the CSR built for the first batch
+                graph.topology(edge_index, x.shape[0], self_loops=True, edge_weight=edge_attr, static_key=static_key)
 
             feats = []
             mask_col = mask_x.reshape(-1, 1)
@@ -163,7 +167,7 @@ class MultilevelGNN(nn.Module):
                     x = args.add_coef1 * x + args.add_coef2 * mask_col
 
             layout = graph.pool_layout(gene_pca_match, raw_indice, n3, 146 * 3,
-                                       wrap_negative=not args.pca_match_mask)
+                                       wrap_negative=not args.pca_match_mask, static_key=static_key)
             w = self.learnable_pca_params * self.info_mask                   # [G, P]
             x = Fn.PathwayPool.apply(x, w, vm, layout)                       # [B, C, 438, P]
             x = x.reshape(x.shape[0], x.shape[1], 146, self.pca_dim * 3)

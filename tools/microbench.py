@@ -1,0 +1,100 @@
+#!/usr/bin/env python
+"""Per-kernel microbenchmarks (CUDA events, L2-exceeding inputs) -- used for ncu captures and tuning.
+
+    python tools/microbench.py genconv --H 128 [--bwd]
+    python tools/microbench.py sage | pool | knn --n 10000 --d 64
+"""
+import argparse
+import json
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch  # noqa: E402
+
+import multilevel_gnn_b200 as m  # noqa: E402
+from multilevel_gnn_b200 import functional as Fn, graph  # noqa: E402
+
+DEV = "cuda:0"
+HBM = 6454.0
+
+
+def timeit(fn, reps=20, warm=3):
+    for _ in range(warm):
+        fn()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    a.record()
+    for _ in range(reps):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / reps
+
+
+def genconv(a):
+    n, k, H = a.n, a.k, a.H
+    g = torch.Generator().manual_seed(0)
+    pts = None
+    src = torch.randint(0, n, (n * k,), generator=g)
+    dst = torch.arange(n).repeat_interleave(k)
+    ei = torch.stack([src, dst]).to(DEV)
+    x = torch.randn(n, H, generator=g).to(DEV).requires_grad_()
+    e = torch.randn(n * k, H, generator=g).to(DEV).requires_grad_()
+    topo = graph.topology(ei, n)
+    topo.bwd
+    scale = torch.ones(1, device=DEV, requires_grad=True)
+    t = torch.ones(1, device=DEV, requires_grad=True)
+    fwd = lambda: Fn.GenAggregate.apply(x, e, t, 1.0, None, scale, topo, a.aggr, 1e-7, Fn.EPI_MSGNORM, True)
+    ms = timeit(fwd)
+    nb = 4 * H * (n * k + 2 * n) + 4 * n * k + 4 * (n + 1)
+    out = {"kernel": "gen_aggr_fwd", "ms": ms, "GBps": nb / ms / 1e6, "frac": nb / ms / 1e6 / HBM}
+    if a.bwd:
+        h = fwd()
+        gout = torch.randn_like(h)
+        ms_fb = timeit(lambda: torch.autograd.grad(fwd(), [x, e, t, scale], gout))
+        nbb = 4 * H * (2 * n * k + 3 * n) + 8 * n * k
+        out["fwd+bwd_ms"] = ms_fb
+        out["bwd_ms_est"] = ms_fb - ms
+        out["bwd_GBps_alg"] = nbb / (ms_fb - ms) / 1e6
+    print(json.dumps(out))
+
+
+def sage(a):
+    b = m.synth.multilevel_batch(batch_size=a.B, seed=0).to(DEV)
+    n = b.x.shape[0]
+    C = a.H
+    x = torch.randn(n, C, device=DEV, requires_grad=True)
+    topo = graph.topology(b.edge_index, n, self_loops=True, edge_weight=b.edge_attr)
+    topo.bwd, topo.bwd_val, topo.inv_cnt
+    fwd = lambda: Fn.SageAggregate.apply(x, topo, False)
+    ms = timeit(fwd)
+    nnz = topo.fwd.cap
+    nb = 8 * C * n + 8 * nnz
+    out = {"kernel": "sage_aggr_fwd", "ms": ms, "GBps": nb / ms / 1e6, "frac": nb / ms / 1e6 / HBM}
+    y = fwd()
+    gout = torch.randn_like(y)
+    ms2 = timeit(lambda: torch.autograd.grad(fwd(), [x], gout))
+    out["bwd_ms_est"] = ms2 - ms
+    print(json.dumps(out))
+
+
+def knn(a):
+    x = torch.randn(a.n, a.d, device=DEV)
+    ms = timeit(lambda: m.knn_graph_matrix(x, a.k), reps=3, warm=1)
+    fl = 2.0 * a.n * a.n * a.d
+    print(json.dumps({"kernel": "knn", "n": a.n, "d": a.d, "k": a.k, "ms": ms, "TFLOPs_fp32": fl / ms / 1e9}))
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("what", choices=["genconv", "sage", "knn"])
+    ap.add_argument("--n", type=int, default=100000)
+    ap.add_argument("--k", type=int, default=16)
+    ap.add_argument("--H", type=int, default=128)
+    ap.add_argument("--d", type=int, default=64)
+    ap.add_argument("--B", type=int, default=32)
+    ap.add_argument("--aggr", default="softmax")
+    ap.add_argument("--bwd", action="store_true")
+    a = ap.parse_args()
+    {"genconv": genconv, "sage": sage, "knn": knn}[a.what](a)
