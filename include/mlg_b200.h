@@ -103,18 +103,44 @@ int mlg_gen_aggr_bwd(const float* g, const float* x, const float* e, const int32
                      const float* aux, float* g_edge, float* g_x, float* partials, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
- * Weighted segment gather-sum (CSR SpMM with feature rows):
- *     out_i = post_i * ( sum_{q in row i} val[q] * pre[idx[q]] * src[idx[q] % src_mod] )  (+ out_i if accumulate)
+ * Weighted segment gather-sum (CSR SpMM with feature rows), all matrices row-major with a leading
+ * dimension (floats) so that halves of a concatenated buffer can be read / written in place:
+ *     out_i = addend_i + post_i * ( sum_{q in row i} val[q] * pre[idx[q]] * src[idx[q]] )
  *     relative != 0:  out_i -= src_i * (post_mode==mean ? 1 : cnt_i)      (RSAGE x_j*w - x_i)
- * val NULL = 1, pre NULL = 1, src_mod 0 = no modulo; post_mode 0: post_i = 1, 1: post_i = 1/cnt_i
- * (cnt_i = row length, PyG mean aggregation incl. the self loop), 2: post_i = post[i].
+ *     self_out != NULL: self_out_i = src_i                                 (left half of cat(x, agg))
+ * val NULL = 1, pre NULL = 1, addend NULL = 0; post_mode 0: post_i = 1, 1: post_i = 1/cnt_i (cnt_i = row
+ * length, PyG mean aggregation incl. the self loop), 2: post_i = post[i].
+ * replicas = B > 1: the CSR (n_rows rows, idx in [0, n_rows)) is ONE graph shared by B stacked copies
+ * (train.py batches: dataloader/multiloader.py:687-698); replica b gathers src rows b*rep_rows_src + idx and
+ * writes out / self_out / addend rows b*n_rows + i; post is per single-graph row; pre is shared
+ * (rep_rows_pre == 0) or per replica (pre[b*rep_rows_pre + idx]).  rep_rows_src == 0 is the rank-1 source
+ * of MultilevelGNN's first layer: every replica reads the SAME src rows (node_embedding) scaled by its own
+ * pre (batch.x), so x0 = x * node_embedding (multilevel_gnn.py:150-151) is never materialised; self_out
+ * then receives pre[b*rep_rows_pre + i] * src_i.
+ * order (NULL ok): int32 [n_rows] visiting order of the rows (heavy rows first; load balance only).
  * Forward use: SAGEConv mean aggregation of w_ij * x_j (torch_vertex.py:279-286 + PyG mean), done
  * BEFORE the lin_r GEMM (algebraically identical).  Backward use: the same call on
  * the by-source CSR.  Also the source-side pass of mlg_gen_aggr_bwd.
  */
-int mlg_gather_sum(const float* src, const int32_t* rowptr, const int32_t* idx, const float* val,
-                   const float* pre, const float* post, int64_t n_rows, int64_t C, int64_t src_mod,
-                   int post_mode, int relative, int accumulate, float* out, void* stream);
+int mlg_gather_sum(const float* src, int64_t ld_src, const int32_t* rowptr, const int32_t* idx, const float* val,
+                   const float* pre, const float* post, const int32_t* order, int64_t n_rows, int64_t C,
+                   int64_t replicas, int64_t rep_rows_src, int64_t rep_rows_pre, int post_mode, int relative,
+                   const float* addend, int64_t ld_add, float* out, int64_t ld_out, float* self_out,
+                   int64_t ld_self, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Tall-skinny transposed product: out[M,K] = A[rows,M]^T * X[rows,K], colsum[M] = sum_r A[r,:] (NULL ok).
+ * The weight / bias gradient of the Linear layers on the path (SAGEConv.update's MLP and lin_r,
+ * torch_vertex.py:281-291) where rows = B*N nodes and M, K <= 128.  fp32 FMA, fixed reduction order.
+ * 16-byte aligned operands with M, K, ld_a, ld_x multiples of 4 take the 128-bit path.  workspace >= mlg_xty_workspace_bytes().
+ */
+int64_t mlg_xty_workspace_bytes(int64_t rows, int64_t M, int64_t K);
+int mlg_xty(const float* A, int64_t ld_a, const float* X, int64_t ld_x, int64_t rows, int64_t M, int64_t K,
+            float* out, float* colsum, void* workspace, int64_t workspace_bytes, void* stream);
+
+/* z[r,c] = LeakyReLU_slope(z[r,c] + bias[c]) in place (bias NULL ok; slope 0 = ReLU): the bias + activation
+ * of SAGEConv.update's MLP (torch_vertex.py:288-291) after the update GEMM. */
+int mlg_bias_act(float* z, const float* bias, int64_t rows, int64_t C, float slope, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * MultilevelGNN prologue: x0[b*N+n, :] = xs[b*N+n] * emb[n, :]   (models/multilevel_gnn.py:150-151)
@@ -133,20 +159,23 @@ int mlg_embed_scale_bwd(const float* xs, const float* g_out, int64_t B, int64_t 
  *   (built with mlg_csr_build on edge_index = [slot; segment]).
  * x [B*N, C]; vm [B*N] or NULL (value_att_mask multiplier, batch.x); match int64 [B,G];
  * w [G,P] = learnable_pca_params * info_mask (caller multiplies, G*P elements);
- * out [B, C, S, P] (== reference's [B, C, 146, 3P] after its reshape).
+ * out_cl [B, S, P, C]: CHANNEL-LAST; the reference's [B, C, 146, 3P] tensor is its permute(0,3,1,2) view
+ * (s = pathway*3 + omic, so (omic, p) merge into the reference's last axis without a copy).
  * wrap_negative != 0 reproduces python negative indexing when pca_match_mask is False.
  */
 int mlg_pool_fwd(const float* x, const float* vm, const int64_t* match, const float* w,
                  const int32_t* seg_rowptr, const int32_t* seg_slot, int64_t B, int64_t N, int64_t C,
-                 int64_t G, int64_t S, int64_t P, int wrap_negative, float* out, void* stream);
+                 int64_t G, int64_t S, int64_t P, int wrap_negative, float* out_cl, void* stream);
 
-/* Backward: g_x [B*N, C] via the node-side CSR (node_rowptr [B*N+1], node_slot [B*G]: slots grouped by
- * node id, built with mlg_csr_build on [slot; node]); seg_of_slot int32 [B*G] = b*S + raw_indice[b,g];
- * g_w [G,P] (gradient w.r.t. the masked product w; caller multiplies by info_mask).
- * g_out_cl is the gradient of `out` permuted to channel-last [B, S, P, C] (coalesced reads over c). */
+/* Backward.  g_out_cl [B,S,P,C] = gradient of out_cl (channel-last).
+ * mlg_pool_bwd_x: g_x [B*N, C] via the node-side CSR (slots grouped by the node they read, built with
+ *   mlg_csr_build on [slot; node]).  replicas == 1: node_rowptr [B*N+1], node_slot [B*G], seg_of_slot int32
+ *   [B*G] = b*S + raw_indice[b,g].  replicas == B: gene_pca_match / raw_indice are identical for all graphs
+ *   (multiloader.py:697) and the CSR covers ONE graph: node_rowptr [N+1], node_slot [G], seg_of_slot [G] in [0,S).
+ * mlg_pool_bwd_w: g_w [G,P] (gradient w.r.t. the masked product w; caller multiplies by info_mask). */
 int mlg_pool_bwd_x(const float* g_out_cl, const float* vm, const float* w, const int32_t* node_rowptr,
                    const int32_t* node_slot, const int32_t* seg_of_slot, int64_t B, int64_t N, int64_t C,
-                   int64_t G, int64_t S, int64_t P, float* g_x, void* stream);
+                   int64_t G, int64_t S, int64_t P, int64_t replicas, float* g_x, void* stream);
 int mlg_pool_bwd_w(const float* g_out_cl, const float* x, const float* vm, const int64_t* match,
                    const int64_t* raw_indice, int64_t B, int64_t N, int64_t C, int64_t G, int64_t S,
                    int64_t P, int wrap_negative, float* g_w, void* stream);

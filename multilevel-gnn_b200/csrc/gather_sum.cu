@@ -5,14 +5,21 @@
 // (the per-edge lin_r GEMM is hoisted AFTER the aggregation), its backward
 // (same kernel on the by-source CSR) and the source-side pass of the GENConv backward.
 // Deterministic: a row's entries are summed in CSR order by one lane group, no atomics.
-// HBM-bound: algorithmic bytes = 4*C*n_rows*2 + 8*nnz.
+//
+// Replicated topologies: train.py batches B patients that all share ONE edge list
+// (dataloader/multiloader.py:687-698).  With replicas = B the CSR describes a single graph and the
+// kernel walks it once per row while streaming all B feature rows, so index traffic drops B-fold and
+// every entry issues RB independent row loads (memory-level parallelism even for 1-entry rows).
+//
+// HBM-bound: algorithmic bytes = 4*C*rows*2 + 8*nnz.
 #include "common.cuh"
 #include "../../include/mlg_b200.h"
 
 namespace {
 
 constexpr int kThreads = 256;
-constexpr int UN = 4;
+constexpr int UN = 4;   // entries in flight (single-graph path)
+constexpr int RB = 8;   // replicas in flight (replicated path)
 
 struct GsP {
   const float* src;
@@ -21,20 +28,77 @@ struct GsP {
   const float* val;
   const float* pre;
   const float* post;
-  int n, C, src_mod, post_mode, relative, accumulate;
+  const float* addend;
+  const int* order;      // optional row visiting order (heavy rows first, equal degrees together)
   float* out;
+  float* self_out;
+  unsigned ld_src, ld_out, ld_add, ld_self;
+  int n, C, post_mode, relative;
+  int replicas;
+  unsigned rep_rows_src;   // 0: every replica reads the SAME src rows (rank-1 source, pre is per replica)
+  unsigned rep_rows_pre;   // rows per replica of `pre` (0: shared)
 };
 
+__device__ __forceinline__ const float* rowp(const float* b, unsigned r, unsigned ld) { return b + (size_t)r * ld; }
+__device__ __forceinline__ float* rowp(float* b, unsigned r, unsigned ld) { return b + (size_t)r * ld; }
+
+template <int VEC>
+__device__ __forceinline__ void ldv(float (&d)[VEC], const float* p, bool ok) {
+  if (VEC == 4) {
+    const float4 t = ok ? ld_gather4(p) : make_float4(0.f, 0.f, 0.f, 0.f);
+    d[0] = t.x; d[1 % VEC] = t.y; d[2 % VEC] = t.z; d[3 % VEC] = t.w;
+  } else {
+    d[0] = ok ? __ldg(p) : 0.f;
+  }
+}
+template <int VEC>
+__device__ __forceinline__ void stv(float* p, const float (&d)[VEC], bool ok) {
+  if (!ok) return;
+  if (VEC == 4) st4(p, make_float4(d[0], d[1 % VEC], d[2 % VEC], d[3 % VEC]));
+  else p[0] = d[0];
+}
+
+// finish one output row: post scale, relative term, addend, stores
+template <int VEC>
+__device__ __forceinline__ void finish_row(const GsP& P, float (&acc)[VEC], unsigned out_row, unsigned src_row,
+                                           unsigned c, bool cok, float postf, int cnt_row, float self_scale = 1.f) {
+#pragma unroll
+  for (int k = 0; k < VEC; ++k) acc[k] *= postf;
+  if (P.relative || P.self_out) {
+    float xs[VEC];
+    ldv<VEC>(xs, rowp(P.src, src_row, P.ld_src) + c, cok);
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) xs[k] *= self_scale;
+    if (P.relative) {
+      const float f = (P.post_mode == 1) ? (cnt_row > 0 ? 1.f : 0.f) : (float)cnt_row * postf;
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) acc[k] -= f * xs[k];
+    }
+    if (P.self_out) stv<VEC>(rowp(P.self_out, out_row, P.ld_self) + c, xs, cok);
+  }
+  if (P.addend) {
+    float ad[VEC];
+    ldv<VEC>(ad, rowp(P.addend, out_row, P.ld_add) + c, cok);
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) acc[k] += ad[k];
+  }
+  stv<VEC>(rowp(P.out, out_row, P.ld_out) + c, acc, cok);
+}
+
+// ---------------------------------------------------------------------------------------------
+// single-graph path: one lane group per row, UN entries in flight
+// ---------------------------------------------------------------------------------------------
 template <int LANES, int VEC>
-__global__ void __launch_bounds__(kThreads) gather_sum_kernel(GsP P) {
+__global__ void __launch_bounds__(kThreads) gather_sum_kernel(const GsP P) {
   constexpr int RPW = 32 / LANES;
   constexpr int CW = LANES * VEC;
   const int lane = threadIdx.x & 31;
   const int sub = lane / LANES, sl = lane % LANES;
   const unsigned gmask = (LANES == 32) ? 0xffffffffu : (((1u << LANES) - 1u) << (sub * LANES));
   const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
-  const long long row = warp * RPW + sub;
-  if (row >= P.n) return;
+  const long long slot = warp * RPW + sub;
+  if (slot >= P.n) return;
+  const long long row = P.order ? __ldg(P.order + slot) : slot;
   const int C = P.C;
   const int beg = __ldg(P.rowptr + row), end = __ldg(P.rowptr + row + 1);
   const int cnt_row = end - beg;
@@ -43,60 +107,150 @@ __global__ void __launch_bounds__(kThreads) gather_sum_kernel(GsP P) {
   else if (P.post_mode == 2) postf = __ldg(P.post + row);
   const int nchunks = (C + CW - 1) / CW;
   for (int ch = 0; ch < nchunks; ++ch) {
-    const int c = ch * CW + sl * VEC;
-    const bool cok = c < C;
+    const unsigned c = ch * CW + sl * VEC;
+    const bool cok = c < (unsigned)C;
+    const float* sc = P.src + c;
     float acc[VEC];
 #pragma unroll
     for (int k = 0; k < VEC; ++k) acc[k] = 0.f;
     for (int base = beg; base < end; base += LANES) {
       const int q = min(base + sl, end - 1);
-      const int my_idx = __ldg(P.idx + q);
+      const unsigned my_idx = (unsigned)__ldg(P.idx + q);
       float my_w = P.val ? __ldg(P.val + q) : 1.f;
       if (P.pre) my_w *= __ldg(P.pre + my_idx);
-      const int my_row = P.src_mod ? my_idx % P.src_mod : my_idx;
       const int cnt = min(LANES, end - base);
       for (int j = 0; j < cnt; j += UN) {
-        float4 xv[UN];
+        float xv[UN][VEC];
         float w[UN];
 #pragma unroll
         for (int u = 0; u < UN; ++u) {
           const int jj = min(j + u, cnt - 1);
-          const int s = __shfl_sync(gmask, my_row, jj, LANES);
+          const unsigned s = __shfl_sync(gmask, my_idx, jj, LANES);
           w[u] = __shfl_sync(gmask, my_w, jj, LANES);
           if (j + u >= cnt) w[u] = 0.f;
-          const float* p = P.src + (size_t)s * C + c;
-          if (VEC == 4) xv[u] = cok ? ld_gather4(p) : make_float4(0.f, 0.f, 0.f, 0.f);
-          else xv[u].x = cok ? __ldg(p) : 0.f;
+          ldv<VEC>(xv[u], rowp(sc, s, P.ld_src), cok);
         }
 #pragma unroll
-        for (int u = 0; u < UN; ++u) {
-          if (j + u < cnt) {
-            acc[0] = fmaf(w[u], xv[u].x, acc[0]);
-            if (VEC == 4) {
-              acc[1 % VEC] = fmaf(w[u], xv[u].y, acc[1 % VEC]);
-              acc[2 % VEC] = fmaf(w[u], xv[u].z, acc[2 % VEC]);
-              acc[3 % VEC] = fmaf(w[u], xv[u].w, acc[3 % VEC]);
+        for (int u = 0; u < UN; ++u)
+#pragma unroll
+          for (int k = 0; k < VEC; ++k) acc[k] = fmaf(w[u], xv[u][k], acc[k]);
+      }
+    }
+    finish_row<VEC>(P, acc, (unsigned)row, (unsigned)row, c, cok, postf, cnt_row);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// replicated path: the CSR covers ONE graph (n rows); replica b reads src rows b*rep_rows_src + idx and
+// writes out rows b*n + row.  RB replicas are accumulated at once.
+// RANK1: every replica reads the SAME src rows and differs only by the per-(replica,row) scalar `pre`
+//        (MultilevelGNN layer 0: x0[b,n,:] = x[b,n] * node_embedding[n,:] is never materialised).
+// ---------------------------------------------------------------------------------------------
+template <int LANES, int VEC, bool RANK1>
+__global__ void __launch_bounds__(kThreads) gather_sum_rep_kernel(const GsP P, int gy) {
+  constexpr int RPW = 32 / LANES;
+  constexpr int CW = LANES * VEC;
+  constexpr int JU = RANK1 ? 2 : 1;   // entries per step
+  const int lane = threadIdx.x & 31;
+  const int sub = lane / LANES, sl = lane % LANES;
+  const unsigned gmask = (LANES == 32) ? 0xffffffffu : (((1u << LANES) - 1u) << (sub * LANES));
+  // 1-D grid, replica slice fastest: heavy rows (order[] is sorted by degree) of ALL slices start first
+  const int ychunk = blockIdx.x % gy;
+  const long long rowblock = blockIdx.x / gy;
+  const long long warp = (rowblock * (long long)blockDim.x + threadIdx.x) >> 5;
+  const int rep_per_y = (P.replicas + gy - 1) / gy;
+  const int b_lo = ychunk * rep_per_y, b_hi = min(P.replicas, b_lo + rep_per_y);
+  const long long slot = warp * RPW + sub;
+  if (slot >= P.n || b_lo >= b_hi) return;
+  const unsigned row = P.order ? (unsigned)__ldg(P.order + slot) : (unsigned)slot;
+  const int C = P.C;
+  const int beg = __ldg(P.rowptr + row), end = __ldg(P.rowptr + row + 1);
+  const int cnt_row = end - beg;
+  float postf = 1.f;
+  if (P.post_mode == 1) postf = cnt_row > 0 ? 1.f / (float)cnt_row : 0.f;
+  else if (P.post_mode == 2) postf = __ldg(P.post + row);
+  const bool shared_pre = P.pre != nullptr && P.rep_rows_pre == 0;
+  // first LANES entries of the row live in registers for the whole replica loop
+  unsigned idx0 = 0;
+  float w0 = 0.f;
+  if (cnt_row > 0) {
+    const int q = min(beg + sl, end - 1);
+    idx0 = (unsigned)__ldg(P.idx + q);
+    w0 = P.val ? __ldg(P.val + q) : 1.f;
+    if (shared_pre) w0 *= __ldg(P.pre + idx0);
+  }
+  const int nchunks = (C + CW - 1) / CW;
+  for (int ch = 0; ch < nchunks; ++ch) {
+    const unsigned c = ch * CW + sl * VEC;
+    const bool cok = c < (unsigned)C;
+    const float* sc = P.src + c;
+    for (int b0 = b_lo; b0 < b_hi; b0 += RB) {
+      float acc[RB][VEC];
+#pragma unroll
+      for (int r = 0; r < RB; ++r)
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) acc[r][k] = 0.f;
+      for (int base = beg; base < end; base += LANES) {
+        unsigned my_idx = idx0;
+        float my_w = w0;
+        if (base != beg) {
+          const int q = min(base + sl, end - 1);
+          my_idx = (unsigned)__ldg(P.idx + q);
+          my_w = P.val ? __ldg(P.val + q) : 1.f;
+          if (shared_pre) my_w *= __ldg(P.pre + my_idx);
+        }
+        const int cnt = min(LANES, end - base);
+        for (int j = 0; j < cnt; j += JU) {
+          if (RANK1) {
+            unsigned s[JU];
+            float w[JU], xv[JU][VEC], pw[JU][RB];
+#pragma unroll
+            for (int u = 0; u < JU; ++u) {
+              const int jj = min(j + u, cnt - 1);
+              s[u] = __shfl_sync(gmask, my_idx, jj, LANES);
+              w[u] = __shfl_sync(gmask, my_w, jj, LANES);
+              if (j + u >= cnt) w[u] = 0.f;
+              ldv<VEC>(xv[u], rowp(sc, s[u], P.ld_src), cok);
+#pragma unroll
+              for (int r = 0; r < RB; ++r) {
+                const int b = min(b0 + r, b_hi - 1);
+                pw[u][r] = __ldg(P.pre + (size_t)b * P.rep_rows_pre + s[u]);
+              }
             }
+#pragma unroll
+            for (int u = 0; u < JU; ++u)
+#pragma unroll
+              for (int r = 0; r < RB; ++r) {
+                const float f = w[u] * pw[u][r];
+#pragma unroll
+                for (int k = 0; k < VEC; ++k) acc[r][k] = fmaf(f, xv[u][k], acc[r][k]);
+              }
+          } else {
+            const unsigned s = __shfl_sync(gmask, my_idx, j, LANES);
+            const float w = __shfl_sync(gmask, my_w, j, LANES);
+            float xv[RB][VEC];
+#pragma unroll
+            for (int r = 0; r < RB; ++r) {
+              const int b = min(b0 + r, b_hi - 1);
+              ldv<VEC>(xv[r], rowp(sc, (unsigned)b * P.rep_rows_src + s, P.ld_src), cok);
+            }
+#pragma unroll
+            for (int r = 0; r < RB; ++r)
+#pragma unroll
+              for (int k = 0; k < VEC; ++k) acc[r][k] = fmaf(w, xv[r][k], acc[r][k]);
           }
         }
       }
-    }
-    if (!cok) continue;
 #pragma unroll
-    for (int k = 0; k < VEC; ++k) acc[k] *= postf;
-    float* o = P.out + (size_t)row * C + c;
-    if (P.relative) {
-      const long long srow = P.src_mod ? row % P.src_mod : row;
-      const float f = (P.post_mode == 1) ? (cnt_row > 0 ? 1.f : 0.f) : (float)cnt_row * postf;
-#pragma unroll
-      for (int k = 0; k < VEC; ++k) acc[k] -= f * __ldg(P.src + (size_t)srow * C + c + k);
+      for (int r = 0; r < RB; ++r) {
+        const int b = b0 + r;
+        if (b < b_hi) {
+          const float self_scale = RANK1 ? __ldg(P.pre + (size_t)b * P.rep_rows_pre + row) : 1.f;
+          finish_row<VEC>(P, acc[r], (unsigned)b * (unsigned)P.n + row, (unsigned)b * P.rep_rows_src + row, c, cok,
+                          postf, cnt_row, self_scale);
+        }
+      }
     }
-    if (P.accumulate) {
-#pragma unroll
-      for (int k = 0; k < VEC; ++k) acc[k] += o[k];
-    }
-    if (VEC == 4) st4(o, make_float4(acc[0], acc[1 % VEC], acc[2 % VEC], acc[3 % VEC]));
-    else o[0] = acc[0];
   }
 }
 
@@ -145,26 +299,60 @@ __global__ void embed_scale_bwd_kernel(const float* __restrict__ xs, const float
 
 }  // namespace
 
-extern "C" int mlg_gather_sum(const float* src, const int32_t* rowptr, const int32_t* idx, const float* val,
-                              const float* pre, const float* post, int64_t n_rows, int64_t C,
-                              int64_t src_mod, int post_mode, int relative, int accumulate, float* out,
+extern "C" int mlg_gather_sum(const float* src, int64_t ld_src, const int32_t* rowptr, const int32_t* idx,
+                              const float* val, const float* pre, const float* post, const int32_t* order,
+                              int64_t n_rows, int64_t C, int64_t replicas, int64_t rep_rows_src,
+                              int64_t rep_rows_pre, int post_mode, int relative, const float* addend,
+                              int64_t ld_add, float* out, int64_t ld_out, float* self_out, int64_t ld_self,
                               void* stream) {
   MLG_CHECK_ARG(src && rowptr && idx && out, "mlg_gather_sum: null src/rowptr/idx/out");
   MLG_CHECK_ARG(n_rows >= 0 && n_rows < (1ll << 31) && C > 0 && C < (1ll << 20),
                 "mlg_gather_sum: bad sizes n_rows=%lld C=%lld", (long long)n_rows, (long long)C);
   MLG_CHECK_ARG(post_mode >= 0 && post_mode <= 2 && (post_mode != 2 || post), "mlg_gather_sum: bad post_mode");
+  MLG_CHECK_ARG(replicas >= 1 && replicas * n_rows < (1ll << 31) && replicas * rep_rows_src < (1ll << 31) &&
+                    rep_rows_src >= 0 && rep_rows_pre >= 0,
+                "mlg_gather_sum: bad replicas");
+  MLG_CHECK_ARG(replicas > 1 || (rep_rows_pre == 0), "mlg_gather_sum: per-replica pre needs replicas > 1");
+  MLG_CHECK_ARG(rep_rows_src > 0 || replicas == 1 || (pre && rep_rows_pre > 0),
+                "mlg_gather_sum: rep_rows_src == 0 (rank-1 source) needs a per-replica pre");
+  MLG_CHECK_ARG(ld_src >= C && ld_out >= C && (!addend || ld_add >= C) && (!self_out || ld_self >= C),
+                "mlg_gather_sum: leading dimension smaller than C");
   if (n_rows == 0) return MLG_OK;
-  GsP P{src, rowptr, idx, val, pre, post, (int)n_rows, (int)C, (int)src_mod, post_mode, relative, accumulate, out};
+  const bool vec4 = C % 4 == 0 && ld_src % 4 == 0 && ld_out % 4 == 0 && (!addend || ld_add % 4 == 0) &&
+                    (!self_out || ld_self % 4 == 0) && ((uintptr_t)src % 16 == 0) && ((uintptr_t)out % 16 == 0) &&
+                    (!addend || (uintptr_t)addend % 16 == 0) && (!self_out || (uintptr_t)self_out % 16 == 0);
+  GsP P;
+  P.src = src; P.rowptr = rowptr; P.idx = idx; P.val = val; P.pre = pre; P.post = post; P.addend = addend;
+  P.order = order; P.out = out; P.self_out = self_out;
+  P.ld_src = (unsigned)ld_src; P.ld_out = (unsigned)ld_out; P.ld_add = (unsigned)ld_add; P.ld_self = (unsigned)ld_self;
+  P.n = (int)n_rows; P.C = (int)C; P.post_mode = post_mode; P.relative = relative;
+  P.replicas = (int)replicas; P.rep_rows_src = (unsigned)rep_rows_src; P.rep_rows_pre = (unsigned)rep_rows_pre;
   cudaStream_t st = (cudaStream_t)stream;
   const int wpb = kThreads / 32;
-  if (C % 4 != 0) {
-    gather_sum_kernel<32, 1><<<mlg_ceil_div(n_rows, wpb), kThreads, 0, st>>>(P);
-  } else if (C <= 32) {
-    gather_sum_kernel<8, 4><<<mlg_ceil_div(n_rows, wpb * 4), kThreads, 0, st>>>(P);
-  } else if (C <= 64) {
-    gather_sum_kernel<16, 4><<<mlg_ceil_div(n_rows, wpb * 2), kThreads, 0, st>>>(P);
+  int lanes = 32, rows_per_block = wpb;
+  if (vec4 && C <= 32) { lanes = 8; rows_per_block = wpb * 4; }
+  else if (vec4 && C <= 64) { lanes = 16; rows_per_block = wpb * 2; }
+  const long long gx = mlg_ceil_div(n_rows, rows_per_block);
+  if (replicas > 1) {
+    // enough blocks for >= 2 waves of 148 SMs x 8 resident blocks; each slice keeps >= RB replicas
+    int gy = 1;
+    while (gx * gy < 148 * 16 && (replicas / (gy * 2)) >= RB) gy *= 2;
+    const bool rank1 = rep_rows_src == 0;
+    MLG_CHECK_ARG(rank1 || rep_rows_pre == 0, "mlg_gather_sum: per-replica pre is only supported with rep_rows_src == 0");
+    const unsigned grid = (unsigned)(gx * gy);
+#define MLG_REP(L, V)                                                                        \
+  if (rank1) gather_sum_rep_kernel<L, V, true><<<grid, kThreads, 0, st>>>(P, gy);            \
+  else gather_sum_rep_kernel<L, V, false><<<grid, kThreads, 0, st>>>(P, gy);
+    if (!vec4) { MLG_REP(32, 1) }
+    else if (lanes == 8) { MLG_REP(8, 4) }
+    else if (lanes == 16) { MLG_REP(16, 4) }
+    else { MLG_REP(32, 4) }
+#undef MLG_REP
   } else {
-    gather_sum_kernel<32, 4><<<mlg_ceil_div(n_rows, wpb), kThreads, 0, st>>>(P);
+    if (!vec4) gather_sum_kernel<32, 1><<<(unsigned)gx, kThreads, 0, st>>>(P);
+    else if (lanes == 8) gather_sum_kernel<8, 4><<<(unsigned)gx, kThreads, 0, st>>>(P);
+    else if (lanes == 16) gather_sum_kernel<16, 4><<<(unsigned)gx, kThreads, 0, st>>>(P);
+    else gather_sum_kernel<32, 4><<<(unsigned)gx, kThreads, 0, st>>>(P);
   }
   MLG_CHECK_LAUNCH("mlg_gather_sum");
   return MLG_OK;

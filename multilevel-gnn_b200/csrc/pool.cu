@@ -5,7 +5,10 @@
 // scatter_reduce(sum) over raw_indice.  The reference materialises [B,C,G,P] fp32 plus an int64 index of
 // the same shape (205 MB + 410 MB at the gbm shape) and scatters with atomics; here one warp owns one
 // (graph, segment) output row and walks its gene slots, so nothing is materialised and the sum order
-// is fixed.  HBM-bound: algorithmic bytes = 4*C*B*N + 4*B*N + 12*G + 4*B*C*S*P  (SURVEY.md section 8d).
+// is fixed.  The pooled tensor is produced channel-last, out_cl[b, s, p, c] (lanes run over c: coalesced
+// stores, and the 1x1-conv head consumes it as a plain [B*S*P, C] matrix); the reference's
+// [B, C, 146, 3P] tensor is a permuted VIEW of it.
+// HBM-bound: algorithmic bytes = 4*C*B*N + 4*B*N + 12*G + 4*B*C*S*P  (SURVEY.md section 8d).
 #include "common.cuh"
 #include "../../include/mlg_b200.h"
 
@@ -13,17 +16,17 @@ namespace {
 
 constexpr int kThreads = 256;
 constexpr int kMaxP = 8;
+constexpr int UNP = 8;  // independent row loads in flight per lane
 
-// out[b, c, s, p] = sum_{slot in seg row (b,s)} vm[node] * x[node, c] * w[g, p]
+// out_cl[b, s, p, c] = sum_{slot in seg row (b,s)} vm[node] * x[node, c] * w[g, p]
 template <int P_>
 __global__ void __launch_bounds__(kThreads)
 pool_fwd_kernel(const float* __restrict__ x, const float* __restrict__ vm, const long long* __restrict__ match,
                 const float* __restrict__ w, const int* __restrict__ rowptr, const int* __restrict__ slots,
-                int B, int N, int C, int G, int S, int wrap, float* __restrict__ out) {
+                int B, int N, int C, int G, int S, int wrap, float* __restrict__ out_cl) {
   const int lane = threadIdx.x & 31;
   const long long row = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
   if (row >= (long long)B * S) return;
-  const int b = (int)(row / S), s = (int)(row % S);
   const int beg = __ldg(rowptr + row), end = __ldg(rowptr + row + 1);
   const long long BN = (long long)B * N;
   for (int c0 = 0; c0 < C; c0 += 32) {
@@ -49,65 +52,105 @@ pool_fwd_kernel(const float* __restrict__ x, const float* __restrict__ vm, const
 #pragma unroll
       for (int p = 0; p < P_; ++p) wl[p] = scale * __ldg(w + (size_t)g * P_ + p);
       const int cnt = min(32, end - base);
-      for (int j = 0; j < cnt; ++j) {
-        const long long nj = __shfl_sync(0xffffffffu, node, j);
-        const float xv = cok ? __ldg(x + (size_t)nj * C + c) : 0.f;
+      const int inode = (int)node;
+      for (int j = 0; j < cnt; j += UNP) {
+        float xv[UNP];
 #pragma unroll
-        for (int p = 0; p < P_; ++p) acc[p] = fmaf(xv, __shfl_sync(0xffffffffu, wl[p], j), acc[p]);
+        for (int u = 0; u < UNP; ++u) {
+          const int nj = __shfl_sync(0xffffffffu, inode, min(j + u, cnt - 1));
+          xv[u] = cok ? __ldg(x + (size_t)nj * C + c) : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < UNP; ++u) {
+          const bool on = j + u < cnt;
+#pragma unroll
+          for (int p = 0; p < P_; ++p) {
+            const float wj = __shfl_sync(0xffffffffu, wl[p], min(j + u, cnt - 1));
+            acc[p] = fmaf(xv[u], on ? wj : 0.f, acc[p]);
+          }
+        }
       }
     }
     if (cok) {
-      float* o = out + (((size_t)b * C + c) * S + s) * P_;
+      float* o = out_cl + (size_t)row * P_ * C + c;
 #pragma unroll
-      for (int p = 0; p < P_; ++p) o[p] = acc[p];
+      for (int p = 0; p < P_; ++p) o[(size_t)p * C] = acc[p];
     }
   }
 }
 
-// g_x[node, c] = vm[node] * sum_{slot -> node} sum_p w[g,p] * g_cl[b, seg, p, c]
+// g_x[b*N + n, c] = vm * sum_{slot -> node n} sum_p w[g,p] * g_cl[b*S + seg(g), p, c]
+// The node-side CSR covers `n_rows` nodes; replicas > 1: one graph's CSR shared by all B graphs
+// (gene_pca_match / raw_indice identical for every patient, multiloader.py:697,81-82).
 template <int P_>
 __global__ void __launch_bounds__(kThreads)
 pool_bwd_x_kernel(const float* __restrict__ g_cl, const float* __restrict__ vm, const float* __restrict__ w,
                   const int* __restrict__ rowptr, const int* __restrict__ slots,
-                  const int* __restrict__ seg_of_slot, long long BN, int C, int G, float* __restrict__ g_x) {
+                  const int* __restrict__ seg_of_slot, int n_rows, int replicas, int S, int C, int G,
+                  float* __restrict__ g_x) {
+  constexpr int RB = 8;
   const int lane = threadIdx.x & 31;
-  const long long row = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
-  if (row >= BN) return;
+  const long long wid = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const int chunks = (replicas + RB - 1) / RB;
+  const long long row = wid / chunks;
+  const int b0 = (int)(wid % chunks) * RB;
+  if (row >= n_rows) return;
   const int beg = __ldg(rowptr + row), end = __ldg(rowptr + row + 1);
-  const float scale = vm ? __ldg(vm + row) : 1.f;
+  const size_t rep_g = (size_t)S * P_ * C;  // g_cl elements per replica
   for (int c0 = 0; c0 < C; c0 += 32) {
     const int c = c0 + lane;
     const bool cok = c < C;
-    float acc = 0.f;
+    float acc[RB];
+#pragma unroll
+    for (int r = 0; r < RB; ++r) acc[r] = 0.f;
     for (int base = beg; base < end; base += 32) {
       const int q = min(base + lane, end - 1);
       const int slot = __ldg(slots + q);
       const int g = slot % G;
-      const int seg = __ldg(seg_of_slot + slot);  // b*S + s
+      const int seg = __ldg(seg_of_slot + slot);  // (b*)S + s
       float wl[P_];
 #pragma unroll
       for (int p = 0; p < P_; ++p) wl[p] = __ldg(w + (size_t)g * P_ + p);
       const int cnt = min(32, end - base);
       for (int j = 0; j < cnt; ++j) {
         const int sj = __shfl_sync(0xffffffffu, seg, j);
-        const float* gp = g_cl + (size_t)sj * P_ * C + c;
+        float wj[P_];
 #pragma unroll
-        for (int p = 0; p < P_; ++p) {
-          const float gv = cok ? __ldg(gp + (size_t)p * C) : 0.f;
-          acc = fmaf(gv, __shfl_sync(0xffffffffu, wl[p], j), acc);
+        for (int p = 0; p < P_; ++p) wj[p] = __shfl_sync(0xffffffffu, wl[p], j);
+        float gv[RB][P_];
+#pragma unroll
+        for (int r = 0; r < RB; ++r) {
+          const int b = min(b0 + r, replicas - 1);
+          const float* gp = g_cl + (size_t)b * rep_g + (size_t)sj * P_ * C + c;
+#pragma unroll
+          for (int p = 0; p < P_; ++p) gv[r][p] = cok ? __ldg(gp + (size_t)p * C) : 0.f;
+        }
+#pragma unroll
+        for (int r = 0; r < RB; ++r)
+#pragma unroll
+          for (int p = 0; p < P_; ++p) acc[r] = fmaf(gv[r][p], wj[p], acc[r]);
+      }
+    }
+    if (cok) {
+#pragma unroll
+      for (int r = 0; r < RB; ++r) {
+        const int b = b0 + r;
+        if (b < replicas) {
+          const size_t orow = (size_t)b * n_rows + row;
+          g_x[orow * C + c] = acc[r] * (vm ? __ldg(vm + orow) : 1.f);
         }
       }
     }
-    if (cok) g_x[(size_t)row * C + c] = acc * scale;
   }
 }
 
-// g_w[g, p] = sum_b sum_c vm[node] * x[node, c] * g_cl[b, seg(b,g), p, c]
+// g_w[g, p] = sum_b sum_c vm[node] * x[node, c] * g_cl[b*S + seg(b,g), p, c]
 template <int P_>
 __global__ void __launch_bounds__(kThreads)
 pool_bwd_w_kernel(const float* __restrict__ g_cl, const float* __restrict__ x, const float* __restrict__ vm,
                   const long long* __restrict__ match, const long long* __restrict__ raw_indice, int B, int N,
                   int C, int G, int S, int wrap, float* __restrict__ g_w) {
+  constexpr int UB = 4;  // graphs in flight
   const int lane = threadIdx.x & 31;
   const long long g = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
   if (g >= G) return;
@@ -115,21 +158,42 @@ pool_bwd_w_kernel(const float* __restrict__ g_cl, const float* __restrict__ x, c
   float acc[P_];
 #pragma unroll
   for (int p = 0; p < P_; ++p) acc[p] = 0.f;
-  for (int b = 0; b < B; ++b) {
-    long long node = __ldg(match + (size_t)b * G + g);
-    float scale = 1.f;
-    if (node < 0) {
-      if (!wrap) continue;
-      node = ((long long)b * N + node + BN) % BN;
-    } else {
-      node += (long long)b * N;
-    }
-    if (vm) scale = __ldg(vm + node);
-    const long long seg = (long long)b * S + __ldg(raw_indice + (size_t)b * G + g);
-    for (int c = lane; c < C; c += 32) {
-      const float xv = scale * __ldg(x + (size_t)node * C + c);
+  for (int b0 = 0; b0 < B; b0 += UB) {
+    long long node[UB], seg[UB];
+    float scale[UB];
 #pragma unroll
-      for (int p = 0; p < P_; ++p) acc[p] = fmaf(xv, __ldg(g_cl + ((size_t)seg * P_ + p) * C + c), acc[p]);
+    for (int u = 0; u < UB; ++u) {
+      const int b = min(b0 + u, B - 1);
+      long long nd = __ldg(match + (size_t)b * G + g);
+      float sc = (b0 + u < B) ? 1.f : 0.f;
+      if (nd < 0) {
+        if (wrap) nd = ((long long)b * N + nd + BN) % BN;
+        else { nd = 0; sc = 0.f; }
+      } else {
+        nd += (long long)b * N;
+      }
+      node[u] = nd;
+      seg[u] = (long long)b * S + __ldg(raw_indice + (size_t)b * G + g);
+      scale[u] = sc;
+    }
+    if (vm) {
+#pragma unroll
+      for (int u = 0; u < UB; ++u) scale[u] *= __ldg(vm + node[u]);
+    }
+    for (int c = lane; c < C; c += 32) {
+      float xv[UB], gv[UB][P_];
+#pragma unroll
+      for (int u = 0; u < UB; ++u) {
+        xv[u] = __ldg(x + (size_t)node[u] * C + c);
+#pragma unroll
+        for (int p = 0; p < P_; ++p) gv[u][p] = __ldg(g_cl + ((size_t)seg[u] * P_ + p) * C + c);
+      }
+#pragma unroll
+      for (int u = 0; u < UB; ++u) {
+        const float xs = xv[u] * scale[u];
+#pragma unroll
+        for (int p = 0; p < P_; ++p) acc[p] = fmaf(xs, gv[u][p], acc[p]);
+      }
     }
   }
 #pragma unroll
@@ -164,15 +228,15 @@ int check_dims(const char* who, int64_t B, int64_t N, int64_t C, int64_t G, int6
 
 extern "C" int mlg_pool_fwd(const float* x, const float* vm, const int64_t* match, const float* w,
                             const int32_t* seg_rowptr, const int32_t* seg_slot, int64_t B, int64_t N,
-                            int64_t C, int64_t G, int64_t S, int64_t P, int wrap_negative, float* out,
+                            int64_t C, int64_t G, int64_t S, int64_t P, int wrap_negative, float* out_cl,
                             void* stream) {
-  MLG_CHECK_ARG(x && match && w && seg_rowptr && seg_slot && out, "mlg_pool_fwd: null pointer");
+  MLG_CHECK_ARG(x && match && w && seg_rowptr && seg_slot && out_cl, "mlg_pool_fwd: null pointer");
   int rc = check_dims("mlg_pool_fwd", B, N, C, G, S, P);
   if (rc) return rc;
   const int grid = mlg_ceil_div(B * S, kThreads / 32);
   MLG_P_SWITCH(P, (pool_fwd_kernel<P_><<<grid, kThreads, 0, (cudaStream_t)stream>>>(
                       x, vm, (const long long*)match, w, seg_rowptr, seg_slot, (int)B, (int)N, (int)C, (int)G,
-                      (int)S, wrap_negative, out)));
+                      (int)S, wrap_negative, out_cl)));
   MLG_CHECK_LAUNCH("mlg_pool_fwd");
   return MLG_OK;
 }
@@ -180,14 +244,18 @@ extern "C" int mlg_pool_fwd(const float* x, const float* vm, const int64_t* matc
 extern "C" int mlg_pool_bwd_x(const float* g_out_cl, const float* vm, const float* w,
                               const int32_t* node_rowptr, const int32_t* node_slot,
                               const int32_t* seg_of_slot, int64_t B, int64_t N, int64_t C, int64_t G,
-                              int64_t S, int64_t P, float* g_x, void* stream) {
+                              int64_t S, int64_t P, int64_t replicas, float* g_x, void* stream) {
   MLG_CHECK_ARG(g_out_cl && w && node_rowptr && node_slot && seg_of_slot && g_x, "mlg_pool_bwd_x: null pointer");
   int rc = check_dims("mlg_pool_bwd_x", B, N, C, G, S, P);
   if (rc) return rc;
-  const int grid = mlg_ceil_div(B * N, kThreads / 32);
+  MLG_CHECK_ARG(replicas == 1 || replicas == B, "mlg_pool_bwd_x: replicas must be 1 or B");
+  // replicas == B: the CSR covers one graph (N nodes, G slots, seg ids in [0,S)); else B*N nodes / B*G slots
+  const long long n_rows = replicas > 1 ? N : B * N;
+  const long long warps = n_rows * ((replicas + 7) / 8);
+  const int grid = mlg_ceil_div(warps, kThreads / 32);
   MLG_P_SWITCH(P, (pool_bwd_x_kernel<P_><<<grid, kThreads, 0, (cudaStream_t)stream>>>(
-                      g_out_cl, vm, w, node_rowptr, node_slot, seg_of_slot, (long long)(B * N), (int)C, (int)G,
-                      g_x)));
+                      g_out_cl, vm, w, node_rowptr, node_slot, seg_of_slot, (int)n_rows, (int)replicas, (int)S,
+                      (int)C, (int)G, g_x)));
   MLG_CHECK_LAUNCH("mlg_pool_bwd_x");
   return MLG_OK;
 }

@@ -23,21 +23,54 @@ def _scalar_args(v):
     return float(v), None
 
 
-def gather_sum(src, rowptr, idx, n_rows, val=None, pre=None, post=None, src_mod=0, post_mode=0,
-               relative=False, out=None, accumulate=False, tag="gather_sum"):
-    """Raw (non-differentiable) call of mlg_gather_sum."""
+def _ld(t):
+    """Leading dimension (floats) of a 2-D fp32 view whose rows are contiguous."""
+    if t.dim() != 2 or t.stride(1) != 1 or t.dtype != torch.float32:
+        raise ValueError("expected a 2-D fp32 tensor with unit inner stride")
+    return t.stride(0)
+
+
+def _vptr(t):
+    import ctypes
+    _cabi.require_cuda(t)
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def gather_sum(src, rowptr, idx, n_rows, val=None, pre=None, post=None, post_mode=0, relative=False, out=None,
+               addend=None, self_out=None, replicas=1, order=None, rank1=False, tag="gather_sum"):
+    """Raw (non-differentiable) call of mlg_gather_sum.  src / out / addend / self_out may be column
+    slices of wider row-major buffers (leading dimension = stride(0))."""
     L = _cabi.lib()
     C = src.shape[1]
+    total_rows = n_rows * replicas
     if out is None:
-        out = torch.empty(n_rows, C, dtype=torch.float32, device=src.device)
+        out = torch.empty(total_rows, C, dtype=torch.float32, device=src.device)
     # algorithmic bytes (SURVEY.md section 8d): rows read once + rows written once + (idx, val) per entry
-    nbytes = 4 * C * n_rows * 2 + 8 * idx.numel()
+    nbytes = 4 * C * total_rows * 2 + 8 * idx.numel()
     with torch.cuda.device(src.device), _cabi.span(tag, nbytes):
-        _cabi.check(L.mlg_gather_sum(_cabi.fptr(src), _cabi.iptr(rowptr), _cabi.iptr(idx),
-                                     _cabi.fptr(val, True), _cabi.fptr(pre, True), _cabi.fptr(post, True),
-                                     n_rows, C, src_mod, post_mode, int(relative), int(accumulate),
-                                     _cabi.fptr(out), _cabi.stream_ptr()), "mlg_gather_sum")
+        _cabi.check(L.mlg_gather_sum(
+            _vptr(src), _ld(src), _cabi.iptr(rowptr), _cabi.iptr(idx), _cabi.fptr(val, True), _cabi.fptr(pre, True),
+            _cabi.fptr(post, True), _cabi.iptr(order, True), n_rows, C, replicas, 0 if rank1 else n_rows,
+            n_rows if rank1 else 0, post_mode, int(relative),
+            None if addend is None else _vptr(addend), 0 if addend is None else _ld(addend),
+            _vptr(out), _ld(out), None if self_out is None else _vptr(self_out),
+            0 if self_out is None else _ld(self_out), _cabi.stream_ptr()), "mlg_gather_sum")
     return out
+
+
+def xty(a, x, want_colsum=False, tag="xty"):
+    """out[M,K] = a[rows,M]^T @ x[rows,K] (+ column sums of a) through mlg_xty (fp32, deterministic)."""
+    L = _cabi.lib()
+    rows, M = a.shape
+    K = x.shape[1]
+    out = torch.empty(M, K, dtype=torch.float32, device=a.device)
+    cs = torch.empty(M, dtype=torch.float32, device=a.device) if want_colsum else None
+    ws_bytes = L.mlg_xty_workspace_bytes(rows, M, K)
+    ws = torch.empty(ws_bytes // 4, dtype=torch.float32, device=a.device)
+    with torch.cuda.device(a.device), _cabi.span(tag, 4 * rows * (M + K)):
+        _cabi.check(L.mlg_xty(_vptr(a), _ld(a), _vptr(x), _ld(x), rows, M, K, _cabi.fptr(out), _cabi.fptr(cs, True),
+                              _cabi.fptr(ws), ws_bytes, _cabi.stream_ptr()), "mlg_xty")
+    return out, cs
 
 
 class GenAggregate(torch.autograd.Function):
@@ -72,7 +105,8 @@ class GenAggregate(torch.autograd.Function):
         with torch.cuda.device(ref.device), _cabi.span("gen_aggr_fwd", ctx_bytes):
             _cabi.check(L.mlg_gen_aggr_fwd(
                 _cabi.fptr(xd, True), _cabi.fptr(ed, True), _cabi.iptr(csr.rowptr), _cabi.iptr(csr.col),
-                _cabi.iptr(csr.eid), n, H, mode, t_h, t_d, p_h, p_d, y_d, float(eps), epilogue, s_d,
+                None if topo.fwd_identity else _cabi.iptr(csr.eid), n, H, mode, t_h, t_d, p_h, p_d, y_d,
+                float(eps), epilogue, s_d,
                 _cabi.fptr(m), _cabi.fptr(aux, True), _cabi.fptr(h, True), _cabi.stream_ptr()),
                 "mlg_gen_aggr_fwd")
         ctx.topo, ctx.mode, ctx.eps, ctx.epilogue, ctx.learn = topo, mode, float(eps), epilogue, bool(learn)
@@ -110,14 +144,14 @@ class GenAggregate(torch.autograd.Function):
         with torch.cuda.device(dev), _cabi.span("gen_aggr_bwd", bwd_bytes):
             _cabi.check(L.mlg_gen_aggr_bwd(
                 _cabi.fptr(g), _cabi.fptr(xd, True), _cabi.fptr(ed, True), _cabi.iptr(csr.rowptr),
-                _cabi.iptr(csr.col), _cabi.iptr(csr.eid), n, H, ctx.mode, int(ctx.learn), t_h, t_d, p_h, p_d,
+                _cabi.iptr(csr.col), None if topo.fwd_identity else _cabi.iptr(csr.eid), n, H, ctx.mode, int(ctx.learn), t_h, t_d, p_h, p_d,
                 y_d, ctx.eps, ctx.epilogue, s_d, _cabi.fptr(m), _cabi.fptr(aux, True), _cabi.fptr(g_edge),
                 _cabi.fptr(g_x), _cabi.fptr(partials), _cabi.stream_ptr()), "mlg_gen_aggr_bwd")
         needs = ctx.needs_input_grad
         gx = None
         if ctx.has_x and needs[0]:
             bw = topo.bwd      # rows = sources; eid = edge ids whose g_edge rows are summed
-            gx = gather_sum(g_edge, bw.rowptr, bw.eid, n, out=g_x, accumulate=True, tag="gen_aggr_bwd_src")
+            gx = gather_sum(g_edge, bw.rowptr, bw.eid, n, out=g_x, addend=g_x, tag="gen_aggr_bwd_src")
         ge = g_edge[:n_edges].reshape(ctx.e_shape) if (ctx.has_e and needs[1]) else None
         sums = None
 
@@ -144,8 +178,8 @@ class SageAggregate(torch.autograd.Function):
         _cabi.require_cuda(x)
         xd = _f32c(x.detach())
         csr = topo.fwd
-        out = gather_sum(xd, csr.rowptr, csr.col, topo.n, val=topo.fwd_val, post_mode=1, relative=relative,
-                         tag="sage_aggr_fwd")
+        out = gather_sum(xd, csr.rowptr, csr.col, topo.n_single, val=topo.fwd_val, post_mode=1, relative=relative,
+                         replicas=topo.replicas, order=topo.fwd_order, tag="sage_aggr_fwd")
         ctx.topo, ctx.relative = topo, bool(relative)
         return out
 
@@ -155,10 +189,100 @@ class SageAggregate(torch.autograd.Function):
         g = _f32c(g)
         bw = topo.bwd
         # g_x[j] = sum_{i: j->i} w_ij * g[i] / cnt_i   (entries of the by-source CSR: col = target i)
-        gx = gather_sum(g, bw.rowptr, bw.col, topo.n, val=topo.bwd_val, pre=topo.inv_cnt, tag="sage_aggr_bwd")
+        gx = gather_sum(g, bw.rowptr, bw.col, topo.n_single, val=topo.bwd_val, pre=topo.inv_cnt,
+                        replicas=topo.replicas, order=topo.bwd_order, tag="sage_aggr_bwd")
         if ctx.relative:
             gx = gx - g
         return gx, None, None
+
+
+class SageLayer(torch.autograd.Function):
+    """One whole SAGEConv layer (torch_vertex.py:269-294 with RSAGEConv's Linear+activation MLP):
+        out = act( [x | agg_x] @ [W1 | W2 @ W_r]^T + b ),   nn.0.weight = [W1 | W2], lin_r.weight = W_r
+    i.e. the reference's  nn(cat(x, mean_j(w_ij x_j) @ W_r^T))  with the two chained Linears folded into
+    one GEMM over the concatenated buffer (fp reassociation only).
+    Kernels: mlg_gather_sum writes agg_x and the copy of x straight into the two halves of the [N, 2Cin]
+    buffer (no torch.cat); the GEMMs are cuBLAS fp32; the weight/bias gradient is mlg_xty; the backward
+    aggregation reads the right half of d[x|agg_x] in place and adds the left half."""
+
+    @staticmethod
+    def forward(ctx, x, xs, lin_r_w, nn_w, nn_b, topo, relative, slope):
+        """x [B*N, Cin] node features -- or, with ``xs`` [B*N] given, x = node_embedding [N, Cin] and the layer
+        input is the rank-1 product xs[b,n] * x[n,:] (MultilevelGNN's first layer, never materialised)."""
+        _cabi.require_cuda(x, lin_r_w, nn_w)
+        xd = _f32c(x.detach())
+        rank1 = xs is not None
+        xs_d = _f32c(xs.detach().reshape(-1)) if rank1 else None
+        n = xs_d.numel() if rank1 else xd.shape[0]
+        cin = xd.shape[1]
+        w_r, w_nn = lin_r_w.detach(), nn_w.detach()
+        w1, w2 = w_nn[:, :cin], w_nn[:, cin:]
+        wcat = torch.cat([w1, w2 @ w_r], dim=1)                       # [cout, 2cin]  (tiny)
+        xcat = torch.empty(n, 2 * cin, dtype=torch.float32, device=xd.device)
+        csr = topo.fwd
+        gather_sum(xd, csr.rowptr, csr.col, topo.n_single, val=topo.fwd_val, pre=xs_d, post_mode=1, relative=relative,
+                   out=xcat[:, cin:], self_out=xcat[:, :cin], replicas=topo.replicas, order=topo.fwd_order,
+                   rank1=rank1, tag="sage_aggr_fwd")
+        y = xcat @ wcat.t()                                           # cuBLAS fp32, no epilogue
+        L = _cabi.lib()
+        with torch.cuda.device(y.device), _cabi.span("sage_bias_act", 8 * y.numel()):
+            _cabi.check(L.mlg_bias_act(_cabi.fptr(y), None if nn_b is None else _cabi.fptr(_f32c(nn_b.detach())),
+                                       y.shape[0], y.shape[1], float(slope), _cabi.stream_ptr()), "mlg_bias_act")
+        ctx.save_for_backward(xcat, y, wcat, w_r, w2, xs_d if rank1 else None)
+        ctx.topo, ctx.relative, ctx.slope, ctx.cin, ctx.has_bias = topo, bool(relative), float(slope), cin, nn_b is not None
+        ctx.rank1 = rank1
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        xcat, y, wcat, w_r, w2, xs_d = ctx.saved_tensors
+        topo, cin = ctx.topo, ctx.cin
+        gy = _f32c(gy)
+        gz = torch.ops.aten.leaky_relu_backward(gy, y, ctx.slope, True) if ctx.slope != 0.0 \
+            else torch.ops.aten.threshold_backward(gy, y, 0.0)
+        needs = ctx.needs_input_grad
+        gx = g_wr = g_wnn = g_b = None
+        if needs[2] or needs[3] or needs[4]:
+            g_wcat, g_b = xty(gz, xcat, want_colsum=ctx.has_bias, tag="sage_wgrad")       # [cout, 2cin], [cout]
+            g_weff = g_wcat[:, cin:]
+            g_wnn = torch.cat([g_wcat[:, :cin], g_weff @ w_r.t()], dim=1)
+            g_wr = w2.t() @ g_weff
+        if needs[0]:
+            gxcat = gz @ wcat                                                              # [N, 2cin]
+            bw = topo.bwd
+            gx = gather_sum(gxcat[:, cin:], bw.rowptr, bw.col, topo.n_single, val=topo.bwd_val, pre=topo.inv_cnt,
+                            addend=gxcat[:, :cin], replicas=topo.replicas, order=topo.bwd_order, tag="sage_aggr_bwd")
+            if ctx.relative:
+                gx = gx - gxcat[:, cin:]
+            if ctx.rank1:
+                # gradient of the rank-1 input w.r.t. node_embedding: g_emb[n,:] = sum_b xs[b,n] * g_x0[b,n,:]
+                L = _cabi.lib()
+                n1 = topo.n_single
+                g_emb = torch.empty(n1, cin, dtype=torch.float32, device=gx.device)
+                with torch.cuda.device(gx.device), _cabi.span("embed_scale_bwd", 4 * gx.numel()):
+                    _cabi.check(L.mlg_embed_scale_bwd(_cabi.fptr(xs_d), _cabi.fptr(gx), topo.replicas, n1, cin,
+                                                      _cabi.fptr(g_emb), _cabi.stream_ptr()), "mlg_embed_scale_bwd")
+                gx = g_emb
+        return gx, None, g_wr, g_wnn, (g_b if ctx.has_bias else None), None, None, None
+
+
+class RankOne:
+    """Layer input x0[b*N+n, :] = xs[b*N+n] * emb[n, :] kept in factored form (MultilevelGNN's embed-scale
+    prologue, models/multilevel_gnn.py:150-151) so that the first SAGE layer can consume it without the
+    [B*N, C] tensor ever being written; ``materialize()`` produces it for any consumer that needs it."""
+
+    def __init__(self, xs, emb):
+        self.xs, self.emb = xs, emb
+
+    @property
+    def shape(self):
+        return (self.xs.numel(), self.emb.shape[1])
+
+    def dim(self):
+        return 2
+
+    def materialize(self):
+        return EmbedScale.apply(self.xs, self.emb)
 
 
 class EmbedScale(torch.autograd.Function):
@@ -195,7 +319,8 @@ class EmbedScale(torch.autograd.Function):
 
 class PathwayPool(torch.autograd.Function):
     """Gene -> pathway pool (models/multilevel_gnn.py:205-239).
-    forward(x [B*N,C], w [G,P] (already * info_mask), vm [B*N] or None, layout) -> [B,C,S,P]."""
+    forward(x [B*N,C], w [G,P] (already * info_mask), vm [B*N] or None, layout) -> [B,C,S,P], returned as the
+    permute(0,3,1,2) VIEW of the channel-last buffer [B,S,P,C] the kernel writes."""
 
     @staticmethod
     def forward(ctx, x, w, vm, layout):
@@ -204,16 +329,16 @@ class PathwayPool(torch.autograd.Function):
         xd, wd = _f32c(x.detach()), _f32c(w.detach())
         B, N, G, S = layout.B, layout.N, layout.G, layout.S
         C, P = xd.shape[1], wd.shape[1]
-        out = torch.empty(B, C, S, P, dtype=torch.float32, device=xd.device)
+        out_cl = torch.empty(B, S, P, C, dtype=torch.float32, device=xd.device)
         nbytes = 4 * C * B * N + 4 * B * N + 12 * G + 4 * B * C * S * P
         with torch.cuda.device(xd.device), _cabi.span("pool_fwd", nbytes):
             _cabi.check(L.mlg_pool_fwd(_cabi.fptr(xd), _cabi.fptr(vm, True), _cabi.lptr(layout.match),
                                        _cabi.fptr(wd), _cabi.iptr(layout.seg.rowptr), _cabi.iptr(layout.seg.col),
-                                       B, N, C, G, S, P, int(layout.wrap_negative), _cabi.fptr(out),
+                                       B, N, C, G, S, P, int(layout.wrap_negative), _cabi.fptr(out_cl),
                                        _cabi.stream_ptr()), "mlg_pool_fwd")
         ctx.save_for_backward(xd, wd)
         ctx.vm, ctx.layout = vm, layout
-        return out
+        return out_cl.permute(0, 3, 1, 2)
 
     @staticmethod
     def backward(ctx, g):
@@ -222,20 +347,22 @@ class PathwayPool(torch.autograd.Function):
         lay, vm = ctx.layout, ctx.vm
         B, N, G, S = lay.B, lay.N, lay.G, lay.S
         C, P = xd.shape[1], wd.shape[1]
-        g_cl = _f32c(g).permute(0, 2, 3, 1).contiguous()      # [B,S,P,C]: channel-last for coalesced reads
+        g_cl = g.float().permute(0, 2, 3, 1).contiguous()     # [B,S,P,C]; no copy when g is already channel-last
         gx = gw = None
         with torch.cuda.device(xd.device):
             if ctx.needs_input_grad[0]:
                 gx = torch.empty_like(xd)
                 node = lay.node_csr
-                _cabi.check(L.mlg_pool_bwd_x(_cabi.fptr(g_cl), _cabi.fptr(vm, True), _cabi.fptr(wd),
-                                             _cabi.iptr(node.rowptr), _cabi.iptr(node.col),
-                                             _cabi.iptr(lay.seg_of_slot), B, N, C, G, S, P, _cabi.fptr(gx),
-                                             _cabi.stream_ptr()), "mlg_pool_bwd_x")
+                with _cabi.span("pool_bwd_x", 4 * C * B * N + 4 * B * C * S * P):
+                    _cabi.check(L.mlg_pool_bwd_x(_cabi.fptr(g_cl), _cabi.fptr(vm, True), _cabi.fptr(wd),
+                                                 _cabi.iptr(node.rowptr), _cabi.iptr(node.col),
+                                                 _cabi.iptr(lay.seg_of_slot), B, N, C, G, S, P, lay.replicas,
+                                                 _cabi.fptr(gx), _cabi.stream_ptr()), "mlg_pool_bwd_x")
             if ctx.needs_input_grad[1]:
                 gw = torch.empty_like(wd)
-                _cabi.check(L.mlg_pool_bwd_w(_cabi.fptr(g_cl), _cabi.fptr(xd), _cabi.fptr(vm, True),
-                                             _cabi.lptr(lay.match), _cabi.lptr(lay.raw_indice), B, N, C, G, S, P,
-                                             int(lay.wrap_negative), _cabi.fptr(gw), _cabi.stream_ptr()),
-                            "mlg_pool_bwd_w")
+                with _cabi.span("pool_bwd_w", 4 * C * B * N + 4 * B * C * S * P):
+                    _cabi.check(L.mlg_pool_bwd_w(_cabi.fptr(g_cl), _cabi.fptr(xd), _cabi.fptr(vm, True),
+                                                 _cabi.lptr(lay.match), _cabi.lptr(lay.raw_indice), B, N, C, G, S, P,
+                                                 int(lay.wrap_negative), _cabi.fptr(gw), _cabi.stream_ptr()),
+                                "mlg_pool_bwd_w")
         return gx, gw, None, None

@@ -94,15 +94,38 @@ class SAGEConv(nn.Module):
     def forward(self, x, edge_index, size=None, edge_attr=None):
         if size is not None:
             raise NotImplementedError("bipartite `size` is never used by the reference models")
-        x = x.unsqueeze(-1) if x.dim() == 1 else x
         if edge_attr is None:   # torch_vertex.py:279 dereferences edge_attr.dim()
             raise AttributeError("SAGEConv.forward needs edge_attr (reference: 'NoneType' object has no attribute 'dim')")
         if edge_attr.dim() > 1 and edge_attr.shape[-1] != 1:
             raise NotImplementedError("vector edge weights: only [E] / [E,1] edge_attr is used by the reference")
-        topo = graph.topology(edge_index, x.shape[0], self_loops=True, edge_weight=edge_attr)
+        slope = self._fused_slope()
+        n_total = x.shape[0]
+        topo = graph.topology(edge_index, n_total, self_loops=True, edge_weight=edge_attr)
+        if isinstance(x, Fn.RankOne):
+            # x0 = xs * emb consumed in factored form when the whole layer is fused and the batch is replicated
+            if slope is not None and topo.replicas > 1 and topo.n_single == x.emb.shape[0]:
+                lin = self.nn[0]
+                return Fn.SageLayer.apply(x.emb, x.xs, self.lin_r.weight, lin.weight, lin.bias, topo, self.relative, slope)
+            x = x.materialize()
+        x = x.unsqueeze(-1) if x.dim() == 1 else x
+        if slope is not None:
+            lin = self.nn[0]
+            return Fn.SageLayer.apply(x, None, self.lin_r.weight, lin.weight, lin.bias, topo, self.relative, slope)
         agg_x = Fn.SageAggregate.apply(x, topo, self.relative)
         agg = F.linear(agg_x, self.lin_r.weight)
         return self.update(agg, x)
+
+    def _fused_slope(self):
+        """negative slope when ``nn`` is exactly Linear -> ReLU / LeakyReLU (what RSAGEConv builds with
+        mlp_norm 'none' and drop 0, i.e. every shipped config) and no output normalisation; else None."""
+        if self.normalize or len(self.nn) != 2 or not isinstance(self.nn[0], torch.nn.Linear):
+            return None
+        act = self.nn[1]
+        if isinstance(act, torch.nn.LeakyReLU):
+            return float(act.negative_slope)
+        if isinstance(act, torch.nn.ReLU):
+            return 0.0
+        return None
 
     def update(self, aggr_out, x):
         out = self.nn(torch.cat((x, aggr_out), dim=1))

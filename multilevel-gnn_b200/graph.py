@@ -55,25 +55,62 @@ def edge_values(edge_attr, csr, fill=1.0):
     return val
 
 
+def _detect_replicas(edge_index, n_nodes, period, edge_weight):
+    """B if edge_index is B node-offset copies of one edge list over `period` nodes (and the weights
+    repeat), else 1.  One device reduction + host sync, at build time only."""
+    if not period or n_nodes % period or n_nodes // period < 2:
+        return 1
+    B, E = n_nodes // period, edge_index.shape[1]
+    if E == 0 or E % B:
+        return 1
+    e1 = E // B
+    ei = edge_index.view(2, B, e1)
+    offs = (torch.arange(B, device=edge_index.device, dtype=edge_index.dtype) * period).view(1, B, 1)
+    first = ei[:, :1, :]
+    same = ((ei - offs) == first).all() & (first.max() < period) & (first.min() >= 0)
+    if edge_weight is not None:
+        w = edge_weight.reshape(B, e1, -1)
+        same = same & (w == w[:1]).all()
+    return B if bool(same) else 1
+
+
 class Topology:
     """Target-sorted CSR (forward traversal) + source-sorted CSR (backward traversal) of one edge
-    list, optionally with the SAGE self-loop rewrite and edge weights folded in."""
+    list, optionally with the SAGE self-loop rewrite and edge weights folded in.
 
-    def __init__(self, edge_index, n_nodes, self_loops=False, edge_weight=None):
+    ``period``: nodes per graph of a PyG-style batch.  When the batch turns out to be B offset copies
+    of ONE edge list (what the reference's loader produces, multiloader.py:687-698) only the first
+    graph's CSR is built (``n_single`` rows) and ``replicas = B`` tells the kernels to stream the B
+    stacked feature blocks through it."""
+
+    def __init__(self, edge_index, n_nodes, self_loops=False, edge_weight=None, period=None):
         self.n = n_nodes
         self.self_loops = self_loops
+        self.replicas = _detect_replicas(edge_index, n_nodes, period, edge_weight)
+        self.n_single = n_nodes // self.replicas
+        if self.replicas > 1:
+            e1 = edge_index.shape[1] // self.replicas
+            edge_index = edge_index[:, :e1].contiguous()
+            if edge_weight is not None:
+                edge_weight = edge_weight.reshape(self.replicas, e1, -1)[0].contiguous()
         self.edge_index = edge_index
-        self.fwd = build_csr(edge_index, n_nodes, by_source=False, drop_self=self_loops, add_self=self_loops)
+        self.fwd = build_csr(edge_index, self.n_single, by_source=False, drop_self=self_loops, add_self=self_loops)
         self._bwd = None
         self._edge_weight = edge_weight
         self.fwd_val = edge_values(edge_weight, self.fwd) if edge_weight is not None else None
         self._bwd_val = None
         self._inv_cnt = None
+        self._fwd_order = None
+        self._bwd_order = None
+        # edges already sorted by target (kNN graphs are centre-major): the permutation is the identity
+        self.fwd_identity = False
+        if not self_loops and edge_index.shape[1] > 1:
+            self.fwd_identity = bool((edge_index[1, 1:] >= edge_index[1, :-1]).all())
 
     @property
     def bwd(self):
         if self._bwd is None:
-            self._bwd = build_csr(self.edge_index, self.n, by_source=True, drop_self=self.self_loops,
+            self._bwd = build_csr(self.edge_index, self.n_single, by_source=True, drop_self=self.self_loops,
                                   add_self=self.self_loops)
         return self._bwd
 
@@ -83,9 +120,28 @@ class Topology:
             self._bwd_val = edge_values(self._edge_weight, self.bwd)
         return self._bwd_val
 
+    @staticmethod
+    def _order(csr):
+        """rows sorted by entry count, heaviest first: lane groups of a warp get equal-length rows (no
+        divergence) and the long rows start first (no tail).  int32 [n_rows]."""
+        deg = csr.rowptr[1:] - csr.rowptr[:-1]
+        return torch.sort(deg, descending=True, stable=True).indices.to(torch.int32)
+
+    @property
+    def fwd_order(self):
+        if self._fwd_order is None:
+            self._fwd_order = self._order(self.fwd)
+        return self._fwd_order
+
+    @property
+    def bwd_order(self):
+        if self._bwd_order is None:
+            self._bwd_order = self._order(self.bwd)
+        return self._bwd_order
+
     @property
     def inv_cnt(self):
-        """1 / (number of entries per target row) -- PyG mean aggregation's divisor, float32 [n]."""
+        """1 / (number of entries per target row) -- PyG mean aggregation's divisor, float32 [n_single]."""
         if self._inv_cnt is None:
             cnt = (self.fwd.rowptr[1:] - self.fwd.rowptr[:-1]).float()
             self._inv_cnt = torch.where(cnt > 0, 1.0 / cnt.clamp(min=1), torch.zeros_like(cnt))
@@ -94,13 +150,14 @@ class Topology:
 
 _CACHE = collections.OrderedDict()
 _CACHE_MAX = 16
+_STATIC = {}     # structures registered under a caller-supplied static_key: never evicted
 
 
 def _key(t):
     return None if t is None else (t.data_ptr(), tuple(t.shape), t._version, str(t.device))
 
 
-def topology(edge_index, n_nodes, self_loops=False, edge_weight=None, static_key=None):
+def topology(edge_index, n_nodes, self_loops=False, edge_weight=None, static_key=None, period=None):
     """Cached Topology for this (edge_index, edge_weight) pair.
 
     ``static_key`` (any hashable) is the caller's promise that the edge list is the same as on the
@@ -115,14 +172,14 @@ def topology(edge_index, n_nodes, self_loops=False, edge_weight=None, static_key
     topo = None
     if static_key is not None:
         skey = ("static", static_key, tuple(edge_index.shape), n_nodes, self_loops, edge_weight is not None)
-        hit = _CACHE.get(skey)
+        hit = _STATIC.get(skey)
         if hit is not None:
             topo = hit[0]
         else:
-            topo = Topology(edge_index, n_nodes, self_loops, edge_weight)
-            _CACHE[skey] = (topo, edge_index, edge_weight)
+            topo = Topology(edge_index, n_nodes, self_loops, edge_weight, period)
+            _STATIC[skey] = (topo, edge_index, edge_weight)
     if topo is None:
-        topo = Topology(edge_index, n_nodes, self_loops, edge_weight)
+        topo = Topology(edge_index, n_nodes, self_loops, edge_weight, period)
     _CACHE[key] = (topo, edge_index, edge_weight)   # keep the tensors alive so the pointers stay unique
     while len(_CACHE) > _CACHE_MAX:
         _CACHE.popitem(last=False)
@@ -132,13 +189,16 @@ def topology(edge_index, n_nodes, self_loops=False, edge_weight=None, static_key
 def clear_cache():
     _CACHE.clear()
     _POOL_CACHE.clear()
+    _STATIC.clear()
 
 
 class PoolLayout:
     """Index structures of the gene -> pathway pool (models/multilevel_gnn.py:212-239):
     ``seg``      CSR over (graph, segment) rows listing gene slots  -> forward traversal
     ``node_csr`` CSR over nodes listing the slots that read them    -> backward traversal
-    built once per (gene_pca_match, raw_indice) pair (constant for a fold, multiloader.py:697)."""
+    built once per (gene_pca_match, raw_indice) pair (constant for a fold, multiloader.py:697).
+    When every graph of the batch carries the same match / segment rows (what the loader produces) the
+    node-side CSR is built for ONE graph and ``replicas = B``."""
 
     def __init__(self, gene_pca_match, raw_indice, nodes_per_graph, n_segments, wrap_negative=False):
         B, G = gene_pca_match.shape
@@ -150,20 +210,32 @@ class PoolLayout:
         slot = torch.arange(B * G, device=dev, dtype=torch.int64)
         boff = torch.arange(B, device=dev, dtype=torch.int64).view(B, 1)
         seg = (self.raw_indice + boff * n_segments).reshape(-1)
-        self.seg_of_slot = seg.to(torch.int32)
         self.seg = build_csr(torch.stack([slot, seg]), B * n_segments)
-        node = self.match + boff * nodes_per_graph
-        if wrap_negative:
-            node = torch.where(self.match < 0, node % (B * nodes_per_graph), node)
+        self.replicas = 1
+        if B > 1 and not wrap_negative:
+            same = (self.match == self.match[:1]).all() & (self.raw_indice == self.raw_indice[:1]).all()
+            if bool(same):                      # one host sync, at build time only
+                self.replicas = B
+        if self.replicas > 1:
+            self.seg_of_slot = self.raw_indice[0].to(torch.int32).contiguous()
+            node = torch.where(self.match[0] < 0, torch.full_like(self.match[0], -1), self.match[0])
+            self._node_edges = torch.stack([slot[:G], node])
+            self._node_rows = nodes_per_graph
         else:
-            node = torch.where(self.match < 0, torch.full_like(node, -1), node)
-        self._node_edges = torch.stack([slot, node.reshape(-1)])
+            self.seg_of_slot = seg.to(torch.int32)
+            node = self.match + boff * nodes_per_graph
+            if wrap_negative:
+                node = torch.where(self.match < 0, node % (B * nodes_per_graph), node)
+            else:
+                node = torch.where(self.match < 0, torch.full_like(node, -1), node)
+            self._node_edges = torch.stack([slot, node.reshape(-1)])
+            self._node_rows = B * nodes_per_graph
         self._node_csr = None
 
     @property
     def node_csr(self):
         if self._node_csr is None:
-            self._node_csr = build_csr(self._node_edges, self.B * self.N)
+            self._node_csr = build_csr(self._node_edges, self._node_rows)
         return self._node_csr
 
 
@@ -179,12 +251,12 @@ def pool_layout(gene_pca_match, raw_indice, nodes_per_graph, n_segments, wrap_ne
     lay = None
     if static_key is not None:
         skey = ("static", static_key, tuple(gene_pca_match.shape), nodes_per_graph, n_segments, wrap_negative)
-        hit = _POOL_CACHE.get(skey)
+        hit = _STATIC.get(skey)
         if hit is not None:
             lay = hit[0]
         else:
             lay = PoolLayout(gene_pca_match, raw_indice, nodes_per_graph, n_segments, wrap_negative)
-            _POOL_CACHE[skey] = (lay, gene_pca_match, raw_indice)
+            _STATIC[skey] = (lay, gene_pca_match, raw_indice)
     if lay is None:
         lay = PoolLayout(gene_pca_match, raw_indice, nodes_per_graph, n_segments, wrap_negative)
     _POOL_CACHE[key] = (lay, gene_pca_match, raw_indice)

@@ -1,0 +1,140 @@
+"""DiffPool drop-in (models/diff_pooling.py:11-133 of the reference; PyG 2.2.0 ``DenseSAGEConv`` and
+``dense_diff_pool`` semantics restated from SURVEY.md Appendix A).
+
+Same constructors, ``forward(x, adj, mask=None) -> (x, l_total, e_total)`` and state_dict keys
+(``diffpool_layers.{i}.gnn_pool.layers.0.lin_rel.weight`` ...).  The dense contractions
+(A.X, S^T.X, S^T.A.S, S.S^T) go through ``dense_ops.matmul``: cuBLAS fp32 at the reference's size
+(146 nodes -> 37 -> 10 clusters: launch-bound, tensor cores are irrelevant there) and the hand-written
+tcgen05/TMA bf16 GEMM (``mlg_gemm_bf16``) once the operands are large enough for the tensor pipe
+(``dense_ops.TENSOR_CORE_MIN``), e.g. the synthetic N=10k / K=2.5k / C=1024 shape of SURVEY section 8(d).
+"""
+from math import ceil
+
+import torch
+from torch import nn
+from torch.nn import functional as F
+
+from .. import dense_ops
+
+
+class DenseSAGEConv(nn.Module):
+    """out = lin_rel((A.X) / clamp(rowsum(A), 1)) + lin_root(X), optional L2 normalisation and mask."""
+
+    def __init__(self, in_channels, out_channels, normalize=False, bias=True):
+        super().__init__()
+        self.in_channels, self.out_channels, self.normalize = in_channels, out_channels, normalize
+        self.lin_rel = nn.Linear(in_channels, out_channels, bias=False)
+        self.lin_root = nn.Linear(in_channels, out_channels, bias=bias)
+
+    def forward(self, x, adj, mask=None):
+        x = x.unsqueeze(0) if x.dim() == 2 else x
+        adj = adj.unsqueeze(0) if adj.dim() == 2 else adj
+        out = dense_ops.matmul(adj, x)
+        out = out / adj.sum(dim=-1, keepdim=True).clamp(min=1)
+        out = self.lin_rel(out) + self.lin_root(x)
+        if self.normalize:
+            out = F.normalize(out, p=2.0, dim=-1)
+        if mask is not None:
+            out = out * mask.view(x.size(0), x.size(1), 1).to(x.dtype)
+        return out
+
+
+class DenseGraphConv(nn.Module):
+    def __init__(self, in_channels, out_channels, aggr="add", bias=True):
+        super().__init__()
+        self.lin_rel = nn.Linear(in_channels, out_channels, bias=bias)
+        self.lin_root = nn.Linear(in_channels, out_channels, bias=False)
+
+    def forward(self, x, adj, mask=None):
+        x = x.unsqueeze(0) if x.dim() == 2 else x
+        adj = adj.unsqueeze(0) if adj.dim() == 2 else adj
+        out = self.lin_rel(dense_ops.matmul(adj, x)) + self.lin_root(x)
+        if mask is not None:
+            out = out * mask.view(x.size(0), x.size(1), 1).to(x.dtype)
+        return out
+
+
+def dense_diff_pool(x, adj, s, mask=None, normalize=True):
+    """softmax(S); S^T X; S^T A S; link loss ||A - S S^T||_F / numel(A); entropy mean(sum(-S log(S + 1e-15)))."""
+    x = x.unsqueeze(0) if x.dim() == 2 else x
+    adj = adj.unsqueeze(0) if adj.dim() == 2 else adj
+    s = s.unsqueeze(0) if s.dim() == 2 else s
+    s = torch.softmax(s, dim=-1)
+    if mask is not None:
+        m = mask.view(x.size(0), x.size(1), 1).to(x.dtype)
+        x, s = x * m, s * m
+    st = s.transpose(1, 2)
+    out = dense_ops.matmul(st, x)
+    out_adj = dense_ops.matmul(dense_ops.matmul(st, adj), s)
+    link = torch.norm(adj - dense_ops.matmul(s, st), p=2)
+    if normalize:
+        link = link / adj.numel()
+    ent = (-s * torch.log(s + 1e-15)).sum(dim=-1).mean()
+    return out, out_adj, link, ent
+
+
+class SAGEConvolutions(nn.Module):
+    def __init__(self, num_layers, in_channels, out_channels, residual=True):
+        super().__init__()
+        self.num_layers, self.residual = num_layers, residual
+        self.layers, self.bns = nn.ModuleList(), nn.ModuleList()
+        for i in range(num_layers - 1):
+            self.layers.append(DenseSAGEConv(in_channels if i == 0 else out_channels, out_channels, normalize=True))
+            self.bns.append(nn.BatchNorm1d(out_channels))
+        self.layers.append(DenseSAGEConv(in_channels if num_layers == 1 else out_channels, out_channels, normalize=True))
+
+    def forward(self, x, adj, mask=None):
+        for i in range(self.num_layers - 1):
+            x_new = F.relu(self.layers[i](x, adj, mask))
+            b, n, c = x_new.size()
+            x_new = self.bns[i](x_new.view(-1, c)).view(b, n, c)
+            x = x + x_new if (self.residual and x.shape == x_new.shape) else x_new
+        return self.layers[self.num_layers - 1](x, adj, mask)
+
+
+class DiffPoolLayer(nn.Module):
+    def __init__(self, dim_input, dim_embedding, current_num_clusters, no_new_clusters):
+        super().__init__()
+        self.gnn_pool = SAGEConvolutions(1, dim_input, no_new_clusters)
+        self.gnn_embed = SAGEConvolutions(1, dim_input, dim_embedding)
+
+    def forward(self, x, adj, mask=None):
+        s = self.gnn_pool(x, adj, mask)
+        x = self.gnn_embed(x, adj, mask)
+        return dense_diff_pool(x, adj, s, mask)
+
+
+class DiffPool(nn.Module):
+    def __init__(self, num_features, num_classes, max_num_nodes, num_layers, gnn_hidden_dim, gnn_output_dim, args,
+                 encode_edge=False, pre_sum_aggr=False):
+        super().__init__()
+        self.args = args
+        self.encode_edge = encode_edge
+        self.max_num_nodes = max_num_nodes
+        self.pooling_type = args.pooling_type
+        self.num_pooling_layers = num_layers
+        coarse = 0.1 if num_layers == 1 else 0.25        # the DiffPool paper's coarsening factors
+        if pre_sum_aggr:
+            self.initial_embed = DenseGraphConv(num_features, gnn_output_dim)
+        else:
+            self.initial_embed = SAGEConvolutions(1, num_features, gnn_output_dim)
+        clusters = ceil(coarse * max_num_nodes)
+        current = max_num_nodes
+        pools, afters = [], []
+        for i in range(num_layers):
+            d_in = num_features if i == 0 else gnn_hidden_dim
+            d_out = gnn_output_dim if i == num_layers - 1 else gnn_hidden_dim
+            pools.append(DiffPoolLayer(d_in, d_out, current, clusters))
+            current, clusters = clusters, ceil(clusters * coarse)
+            afters.append(SAGEConvolutions(args.after_pooling_layer, d_out, d_out))
+        self.diffpool_layers = nn.ModuleList(pools)
+        self.after_pool_layers = nn.ModuleList(afters)
+
+    def forward(self, x, adj, mask=None):
+        l_total, e_total = 0, 0
+        for i in range(self.num_pooling_layers):
+            x, adj, l, e = self.diffpool_layers[i](x, adj, mask if i == 0 else None)
+            x = self.after_pool_layers[i](x, adj)
+            l_total = l_total + l
+            e_total = e_total + e
+        return x, l_total, e_total

@@ -353,5 +353,88 @@ def test_errors_are_loud(mlg):
     with pytest.raises(_cabi.NativeLibraryError):
         conv(torch.randn(4, 8), torch.zeros(2, 3, dtype=torch.long), torch.ones(3, 1))     # CPU tensors: no fallback
     L = _cabi.lib()
-    assert L.mlg_gather_sum(None, None, None, None, None, None, 4, 8, 0, 0, 0, 0, None, None) < 0
+    assert L.mlg_gather_sum(None, 8, None, None, None, None, None, None, 4, 8, 1, 4, 0, 0, 0, None, 0, None, 8, None, 0, None) < 0
     assert "null" in _cabi.last_error()
+
+
+def test_xty_matches_matmul(mlg):
+    from multilevel_gnn_b200 import functional as Fn
+    g = torch.Generator().manual_seed(31)
+    for rows, M, K in [(5000, 64, 128), (777, 32, 128), (12345, 64, 64), (33, 8, 4), (1000, 100, 260)]:
+        a = torch.randn(rows, M, generator=g).to(DEV)
+        x = torch.randn(rows, K, generator=g).to(DEV)
+        out, cs = Fn.xty(a, x, want_colsum=True)
+        ref = (a.double().t() @ x.double()).float()
+        assert_close(out, ref, rtol=1e-5, atol=2e-6, what="xty %s" % ((rows, M, K),))
+        assert_close(cs, a.double().sum(0).float(), rtol=1e-5, atol=2e-6, what="colsum")
+    # strided operands (halves of a wider buffer)
+    big = torch.randn(4000, 96, generator=g).to(DEV)
+    out, _ = Fn.xty(big[:, :32], big[:, 32:])
+    assert_close(out, (big[:, :32].double().t() @ big[:, 32:].double()).float(), rtol=1e-5, atol=2e-6, what="xty strided")
+
+
+def test_replicated_topology_equals_generic(mlg):
+    """The B-copies fast path (single-graph CSR streamed over the batch) must agree with the generic CSR."""
+    from multilevel_gnn_b200 import functional as Fn, graph, synth
+    genes, bsz = 250, 5
+    b = synth.multilevel_batch(batch_size=bsz, genes=genes, slots=600, intra_edges=3000, seed=12).to(DEV)
+    n = 3 * genes * bsz
+    x = torch.randn(n, 64, device=DEV, requires_grad=True)
+    rep = graph.Topology(b.edge_index, n, self_loops=True, edge_weight=b.edge_attr, period=3 * genes)
+    gen = graph.Topology(b.edge_index, n, self_loops=True, edge_weight=b.edge_attr)
+    assert rep.replicas == bsz and gen.replicas == 1
+    y1, y2 = Fn.SageAggregate.apply(x, rep, False), Fn.SageAggregate.apply(x, gen, False)
+    assert_close(y1, y2.cpu(), rtol=1e-6, what="replicated fwd")
+    go = torch.randn_like(y1)
+    g1, g2 = torch.autograd.grad(y1, x, go)[0], torch.autograd.grad(y2, x, go)[0]
+    assert_close(g1, g2.cpu(), rtol=1e-5, what="replicated bwd")
+    # a batch whose graphs differ must NOT be detected as replicated
+    ei = b.edge_index.clone()
+    ei[0, -1] = ei[0, -1] - 3 if int(ei[0, -1]) % (3 * genes) >= 3 else ei[0, -1] + 3
+    assert graph.Topology(ei, n, self_loops=True, edge_weight=b.edge_attr, period=3 * genes).replicas == 1
+
+
+def test_trainer_steps_match_cpu_port(mlg):
+    """Two optimizer steps of the B200 Trainer vs the CPU port of train.py:38-68 (loss + updated weights)."""
+    from multilevel_gnn_b200.train import Trainer
+    from oracle.train_port import CpuTrainer
+    c = load_golden("multilevel")["gbm"]
+    model, args = _build_multilevel(mlg, c)
+    args.lr = 1e-2
+    model.drop1.p = 0.0
+    model.head[2].p = 0.0                      # dropout off: the port has none
+    batch = as_batch(c["batch"], DEV)
+    cpu = CpuTrainer({k: v.clone() for k, v in c["state_dict"].items()}, args, c["weight"], c["batch"]["raw_indice"][0])
+    model.pathway_indexs = model.pathway_indexs.to(DEV)
+    tr = Trainer(model, args, c["weight"].to(DEV))
+    for step in range(2):
+        lg = tr.step(batch)
+        lc = cpu.step(as_batch(c["batch"]))
+        assert_close(lg, lc, rtol=2e-4, what="loss step %d" % step)
+    sd = model.state_dict()
+    for k in cpu.train_keys:
+        assert_close(sd[k], cpu.sd[k], rtol=1e-3, atol=2e-5, what="weights after 2 steps: " + k)
+
+
+# ------------------------------------------------------------------------------------------------
+# DiffPool vs golden (reference-sized problems: fp32 library GEMMs, rtol 1e-4)
+# ------------------------------------------------------------------------------------------------
+DPG = load_golden("diffpool")
+
+
+@pytest.mark.parametrize("name", sorted(DPG))
+def test_diffpool_golden(mlg, name):
+    c = DPG[name]
+    args = mlg.configs.make_args("lgg")
+    dp = _load(mlg.DiffPool(c["c"], 2, c["n"], 2, c["hid"], c["outd"], args), c["state_dict"])
+    dp.train()
+    x = c["x"].to(DEV).requires_grad_()
+    out, l, e = dp(x, c["adj"].to(DEV))
+    assert_close(out, c["out"], what=name + ".out")
+    assert_close(l, c["link"], what=name + ".link")
+    assert_close(e, c["ent"], what=name + ".ent")
+    ((out * c["R"].to(DEV)).sum() + 3.0 * l + 0.5 * e).backward()
+    assert_close(x.grad, c["g_x"], rtol=2e-4, what=name + ".g_x")
+    for k, p in dp.named_parameters():
+        if c["g_params"].get(k) is not None:
+            assert_close(p.grad, c["g_params"][k], rtol=2e-4, what=name + ".g_" + k)

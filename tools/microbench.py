@@ -65,7 +65,8 @@ def sage(a):
     n = b.x.shape[0]
     C = a.H
     x = torch.randn(n, C, device=DEV, requires_grad=True)
-    topo = graph.topology(b.edge_index, n, self_loops=True, edge_weight=b.edge_attr)
+    topo = graph.Topology(b.edge_index, n, self_loops=True, edge_weight=b.edge_attr, period=None if a.generic else 15405)
+    print("replicas", topo.replicas)
     topo.bwd, topo.bwd_val, topo.inv_cnt
     fwd = lambda: Fn.SageAggregate.apply(x, topo, False)
     ms = timeit(fwd)
@@ -96,5 +97,6 @@ if __name__ == "__main__":
     ap.add_argument("--B", type=int, default=32)
     ap.add_argument("--aggr", default="softmax")
     ap.add_argument("--bwd", action="store_true")
+    ap.add_argument("--generic", action="store_true")
     a = ap.parse_args()
     {"genconv": genconv, "sage": sage, "knn": knn}[a.what](a)
