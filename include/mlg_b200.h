@@ -191,6 +191,21 @@ int mlg_knn_graph(const float* x, int64_t B, int64_t N, int64_t D, int64_t k, in
                   int add_offset, int64_t* out_nbr, int64_t* out_ctr, float* out_dist, void* workspace,
                   int64_t workspace_bytes, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Dense contractions of DiffPool (models/diff_pooling.py:61-64 -> PyG dense_diff_pool / DenseSAGEConv:
+ * S^T.X, S^T.A.S, A.X, S.S^T) on the tcgen05 tensor cores:
+ *     C[b][M,N] = alpha * A[b][M,K] . B[b][N,K]^T     A, B bf16 K-major (row-major [rows, K]); C fp32 row-major
+ * TMA-fed 128B-swizzled tiles, accumulation in tensor memory (fp32).  lda/ldb multiples of 8 elements, operands
+ * 16-byte aligned; stride_* are per-batch element strides (ignored for batch == 1).
+ * mlg_cast_bf16 produces the K-major bf16 operands from fp32 row-major matrices [rows, cols]
+ * (transpose != 0: dst[b][c][r] = src[b][r][c], i.e. dst is [cols, rows]).
+ */
+int mlg_cast_bf16(const float* src, int64_t ld_src, int64_t rows, int64_t cols, int64_t batch, int transpose,
+                  void* dst_bf16, int64_t ld_dst, void* stream);
+int mlg_gemm_bf16(const void* A, int64_t lda, int64_t stride_a, const void* B, int64_t ldb, int64_t stride_b,
+                  float* C, int64_t ldc, int64_t stride_c, int64_t M, int64_t N, int64_t K, int64_t batch,
+                  float alpha, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

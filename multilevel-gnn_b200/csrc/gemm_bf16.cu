@@ -1,0 +1,320 @@
+// bf16 x bf16 -> fp32 GEMM on the 5th-generation tensor cores (sm_100a): TMA-fed shared-memory tiles,
+// tcgen05.mma issued by one thread, accumulator in tensor memory, tcgen05.ld epilogue.
+//
+//   C[b][M,N] = alpha * A[b][M,K] . B[b][N,K]^T          ("TN": both operands K-major, bf16; C fp32 row-major)
+//
+// This is the contraction engine of DiffPool at sizes where the assignment products really are dense
+// GEMMs (models/diff_pooling.py:61-64 -> PyG dense_diff_pool / DenseSAGEConv):  S^T.X, S^T.A, (S^T.A).S,
+// A.X and S.S^T; dense_ops.py casts / transposes the fp32 operands into K-major bf16 once per product.
+//
+// Structure (one 128 x BN output tile per CTA, BN = 256 or 128):
+//   warp 0   TMA producer: cp.async.bulk.tensor (3-D maps: k, row, batch) into a kStages-deep ring of
+//            128B-swizzled tiles, completion on `full` mbarriers
+//   warp 1   MMA issuer: one elected lane issues BLOCK_K/16 tcgen05.mma (M=128, N=BN, K=16) per stage,
+//            tcgen05.commit releases the stage (`empty`) and finally signals `tmem_full`
+//   warp 2   allocates / frees BN tensor-memory columns
+//   warps 4-7 epilogue: tcgen05.ld 32x32b (lane quarter = warp % 4) -> registers -> 128-bit global stores
+// Tensor-bound: flops = 2*M*N*K per batch entry.
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+#include "../../include/mlg_b200.h"
+
+namespace {
+
+constexpr int BM = 128, BK = 64, UMMA_K = 16;
+constexpr int kThreads = 256;
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "MLG_WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra MLG_DONE_%=;\n"
+      "bra MLG_WAIT_%=;\n"
+      "MLG_DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, unsigned long long* bar, int c0, int c1,
+                                            int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tcgen05_commit(unsigned long long* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+// D[tmem] (+)= A[smem desc] . B[smem desc]
+__device__ __forceinline__ void umma_bf16(unsigned tmem_d, unsigned long long adesc, unsigned long long bdesc,
+                                          unsigned idesc, unsigned accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// shared-memory matrix descriptor: K-major tile, 128-byte swizzle, rows of 64 bf16 (128 B), 8-row groups 1024 B apart
+__device__ __forceinline__ unsigned long long make_smem_desc(const void* tile) {
+  unsigned long long d = 0;
+  d |= (unsigned long long)((smem_u32(tile) & 0x3FFFF) >> 4);   // start address, 16-byte units
+  d |= (unsigned long long)1 << 16;                             // leading byte offset (unused for swizzled K-major)
+  d |= (unsigned long long)(1024 >> 4) << 32;                   // stride byte offset between 8-row groups
+  d |= (unsigned long long)1 << 46;                             // descriptor version (sm_100)
+  d |= (unsigned long long)2 << 61;                             // layout: SWIZZLE_128B
+  return d;
+}
+// instruction descriptor, kind::f16: D=f32, A=B=bf16, both K-major, M=128, N=BN
+__host__ __device__ constexpr unsigned make_idesc(int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((unsigned)(n >> 3) << 17) | ((unsigned)(BM >> 4) << 24);
+}
+
+template <int BN, int kStages>
+struct Smem {
+  alignas(1024) __nv_bfloat16 a[kStages][BM * BK];
+  alignas(1024) __nv_bfloat16 b[kStages][BN * BK];
+  unsigned long long full[kStages], empty[kStages], tmem_full;
+  unsigned tmem_base;
+};
+
+template <int BN, int kStages>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                 float* __restrict__ C, long long ldc, long long stride_c, int M, int N, int K, float alpha) {
+  extern __shared__ unsigned char smem_raw[];
+  Smem<BN, kStages>& S = *reinterpret_cast<Smem<BN, kStages>*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n0 = blockIdx.x * BN, m0 = blockIdx.y * BM, batch = blockIdx.z;
+  const int k_blocks = (K + BK - 1) / BK;
+  constexpr unsigned kStageBytes = (BM + BN) * BK * 2;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&S.full[s], 1);
+      mbar_init(&S.empty[s], 1);
+    }
+    mbar_init(&S.tmem_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {  // tensor-memory allocation: BN fp32 accumulator columns (power of two >= 32)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&S.tmem_base)),
+                 "n"(BN)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const unsigned tmem = S.tmem_base;
+
+  if (warp == 0) {
+    if (lane == 0) {  // ===== TMA producer =====
+      for (int kb = 0; kb < k_blocks; ++kb) {
+        const int s = kb % kStages;
+        const unsigned ph = (kb / kStages) & 1;
+        mbar_wait(&S.empty[s], ph ^ 1);
+        mbar_expect_tx(&S.full[s], kStageBytes);
+        tma_load_3d(S.a[s], &map_a, &S.full[s], kb * BK, m0, batch);
+        tma_load_3d(S.b[s], &map_b, &S.full[s], kb * BK, n0, batch);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {  // ===== MMA issuer =====
+      constexpr unsigned idesc = make_idesc(BN);
+      for (int kb = 0; kb < k_blocks; ++kb) {
+        const int s = kb % kStages;
+        const unsigned ph = (kb / kStages) & 1;
+        mbar_wait(&S.full[s], ph);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const unsigned long long da = make_smem_desc(S.a[s]), db = make_smem_desc(S.b[s]);
+#pragma unroll
+        for (int k = 0; k < BK / UMMA_K; ++k) {
+          // advance 16 bf16 = 32 B along K inside the 128 B swizzle row: +2 in the 16-byte start-address field
+          umma_bf16(tmem, da + (unsigned long long)(k * 2), db + (unsigned long long)(k * 2), idesc,
+                    (kb | k) != 0 ? 1u : 0u);
+        }
+        tcgen05_commit(&S.empty[s]);  // frees the stage once the MMAs above have read it
+      }
+      tcgen05_commit(&S.tmem_full);  // accumulator complete
+    }
+  } else if (warp >= 4) {  // ===== epilogue: TMEM -> registers -> global =====
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    mbar_wait(&S.tmem_full, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const int row = m0 + q * 32 + lane;
+    float* crow = C + (size_t)batch * stride_c + (size_t)row * ldc;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      unsigned r[32];
+      const unsigned taddr = tmem + ((unsigned)(q * 32) << 16) + (unsigned)c0;
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+          "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+          "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+          : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+            "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+            "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+            "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+          : "r"(taddr));
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      if (row < M) {
+        const int col = n0 + c0;
+        if (col + 32 <= N && (ldc % 4) == 0 && ((uintptr_t)(crow + col) % 16) == 0) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            st_stream4(crow + col + j, make_float4(alpha * __uint_as_float(r[j]), alpha * __uint_as_float(r[j + 1]),
+                                                   alpha * __uint_as_float(r[j + 2]), alpha * __uint_as_float(r[j + 3])));
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (col + j < N) crow[col + j] = alpha * __uint_as_float(r[j]);
+        }
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 2) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(BN) : "memory");
+  }
+}
+
+// ---- fp32 -> bf16 cast (optionally transposing) so that any operand becomes K-major ----------------
+__global__ void cast_bf16_kernel(const float* __restrict__ src, long long ld_src, long long rows, long long cols,
+                                 __nv_bfloat16* __restrict__ dst, long long ld_dst) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long b = blockIdx.y;
+  if (i >= rows * cols) return;
+  const long long r = i / cols, c = i % cols;
+  dst[b * rows * ld_dst + r * ld_dst + c] = __float2bfloat16_rn(src[b * rows * ld_src + r * ld_src + c]);
+}
+// dst[b][c][r] = src[b][r][c]; 32x32 shared-memory tiles, both sides coalesced
+__global__ void cast_bf16_transpose_kernel(const float* __restrict__ src, long long ld_src, long long rows,
+                                           long long cols, __nv_bfloat16* __restrict__ dst, long long ld_dst) {
+  __shared__ float tile[32][33];
+  const long long b = blockIdx.z;
+  const long long c0 = (long long)blockIdx.x * 32, r0 = (long long)blockIdx.y * 32;
+  const float* s = src + b * rows * ld_src;
+  __nv_bfloat16* d = dst + b * cols * ld_dst;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const long long r = r0 + j, c = c0 + threadIdx.x;
+    tile[j][threadIdx.x] = (r < rows && c < cols) ? s[r * ld_src + c] : 0.f;
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const long long c = c0 + j, r = r0 + threadIdx.x;
+    if (c < cols && r < rows) d[c * ld_dst + r] = __float2bfloat16_rn(tile[threadIdx.x][j]);
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+// 3-D map over a K-major bf16 operand: dims (K, rows, batch); box (64, box_rows, 1); 128 B swizzle
+int make_map(CUtensorMap* map, const void* base, long long K, long long rows, long long ld, long long batch,
+             long long batch_stride, int box_rows) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) {
+    mlg_set_error("mlg_gemm_bf16: cuTensorMapEncodeTiled entry point not available");
+    return MLG_ERR_CUDA;
+  }
+  cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)rows, (cuuint64_t)batch};
+  cuuint64_t strides[2] = {(cuuint64_t)ld * 2, (cuuint64_t)(batch > 1 ? batch_stride : rows * ld) * 2};
+  cuuint32_t box[3] = {BK, (cuuint32_t)box_rows, 1};
+  cuuint32_t elem[3] = {1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, elem,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    mlg_set_error("mlg_gemm_bf16: cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return MLG_ERR_CUDA;
+  }
+  return MLG_OK;
+}
+
+template <int BN, int kStages>
+int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, float* C, long long ldc, long long stride_c, int M, int N,
+                int K, int batch, float alpha, cudaStream_t st) {
+  const int smem = (int)sizeof(Smem<BN, kStages>) + 1024;
+  static bool done = false;
+  if (!done) {
+    MLG_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<BN, kStages>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    done = true;
+  }
+  dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM, batch);
+  gemm_bf16_kernel<BN, kStages><<<grid, kThreads, smem, st>>>(ma, mb, C, ldc, stride_c, M, N, K, alpha);
+  MLG_CHECK_LAUNCH("mlg_gemm_bf16");
+  return MLG_OK;
+}
+
+}  // namespace
+
+extern "C" int mlg_cast_bf16(const float* src, int64_t ld_src, int64_t rows, int64_t cols, int64_t batch,
+                             int transpose, void* dst_bf16, int64_t ld_dst, void* stream) {
+  MLG_CHECK_ARG(src && dst_bf16 && rows > 0 && cols > 0 && batch > 0, "mlg_cast_bf16: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (transpose) {
+    MLG_CHECK_ARG(batch < 65536 && (rows + 31) / 32 < 65536, "mlg_cast_bf16: grid too large");
+    dim3 grid((unsigned)((cols + 31) / 32), (unsigned)((rows + 31) / 32), (unsigned)batch), block(32, 8);
+    cast_bf16_transpose_kernel<<<grid, block, 0, st>>>(src, ld_src, rows, cols, (__nv_bfloat16*)dst_bf16, ld_dst);
+  } else {
+    MLG_CHECK_ARG(batch < 65536, "mlg_cast_bf16: batch too large");
+    dim3 grid((unsigned)mlg_ceil_div(rows * cols, 256), (unsigned)batch);
+    cast_bf16_kernel<<<grid, 256, 0, st>>>(src, ld_src, rows, cols, (__nv_bfloat16*)dst_bf16, ld_dst);
+  }
+  MLG_CHECK_LAUNCH("mlg_cast_bf16");
+  return MLG_OK;
+}
+
+extern "C" int mlg_gemm_bf16(const void* A, int64_t lda, int64_t stride_a, const void* B, int64_t ldb,
+                             int64_t stride_b, float* C, int64_t ldc, int64_t stride_c, int64_t M, int64_t N,
+                             int64_t K, int64_t batch, float alpha, void* stream) {
+  MLG_CHECK_ARG(A && B && C, "mlg_gemm_bf16: null pointer");
+  MLG_CHECK_ARG(M > 0 && N > 0 && K > 0 && batch > 0 && batch < 65536 && M < (1ll << 31) && N < (1ll << 31) &&
+                    K < (1ll << 31),
+                "mlg_gemm_bf16: bad sizes");
+  MLG_CHECK_ARG(lda % 8 == 0 && ldb % 8 == 0 && (uintptr_t)A % 16 == 0 && (uintptr_t)B % 16 == 0 &&
+                    (batch == 1 || (stride_a % 8 == 0 && stride_b % 8 == 0)),
+                "mlg_gemm_bf16: TMA needs 16-byte aligned operands with leading dimensions that are multiples of 8");
+  MLG_CHECK_ARG(lda >= K && ldb >= K && ldc >= N, "mlg_gemm_bf16: leading dimension too small");
+  CUtensorMap ma, mb;
+  const bool wide = N > 128;
+  int rc = make_map(&ma, A, K, M, lda, batch, stride_a, BM);
+  if (rc) return rc;
+  rc = make_map(&mb, B, K, N, ldb, batch, stride_b, wide ? 256 : 128);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (wide) return launch_gemm<256, 4>(ma, mb, C, ldc, stride_c, (int)M, (int)N, (int)K, (int)batch, alpha, st);
+  return launch_gemm<128, 6>(ma, mb, C, ldc, stride_c, (int)M, (int)N, (int)K, (int)batch, alpha, st);
+}

@@ -187,12 +187,16 @@ extern "C" int mlg_xty(const float* A, int64_t ld_a, const float* X, int64_t ld_
   rpb = ((rpb + TR - 1) / TR) * TR;
   if (rpb < TR) rpb = TR;
   dim3 grid(parts, tiles);
-  if (aligned) {
+  static bool attr_done = false;   // 48 KB is exactly the default limit; set once, outside any stream capture
+  if (!attr_done) {
     MLG_CUDA(cudaFuncSetAttribute(xty_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    MLG_CUDA(cudaFuncSetAttribute(xty_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    attr_done = true;
+  }
+  if (aligned) {
     xty_kernel<true><<<grid, kThreads, kSmemBytes, st>>>(A, (unsigned)ld_a, X, (unsigned)ld_x, rows, (int)M, (int)K,
                                                         (int)rpb, (float*)workspace, colsum ? 1 : 0);
   } else {
-    MLG_CUDA(cudaFuncSetAttribute(xty_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     xty_kernel<false><<<grid, kThreads, kSmemBytes, st>>>(A, (unsigned)ld_a, X, (unsigned)ld_x, rows, (int)M, (int)K,
                                                          (int)rpb, (float*)workspace, colsum ? 1 : 0);
   }

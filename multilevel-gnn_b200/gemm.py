@@ -1,0 +1,97 @@
+"""Tensor-core matmul for DiffPool's dense contractions: fp32 in / fp32 out, bf16 operands, fp32 accumulate.
+
+``matmul_bf16(a, b)`` = a @ b with a [..., M, K], b [..., K, N] (leading dims broadcast like torch.matmul for
+the 2-D x 3-D and 3-D x 3-D cases DiffPool uses).  The kernel wants both operands K-major, so a is cast as is and
+b is cast + transposed (one pass each, ``mlg_cast_bf16``).  Backward: dA = dC @ b^T and dB = a^T @ dC are the same
+kernel (fp32 gradients, bf16 operands)."""
+import ctypes
+
+import torch
+
+from . import _cabi
+
+
+def _pad8(n):
+    return (n + 7) // 8 * 8
+
+
+def _cast(src, transpose):
+    """fp32 [b, R, C] (rows contiguous) -> bf16 K-major [b, R, ld] (or [b, C, ld] when transposed)."""
+    L = _cabi.lib()
+    b, R, C = src.shape
+    rows, cols = (C, R) if transpose else (R, C)
+    ld = _pad8(cols)
+    dst = torch.zeros(b, rows, ld, dtype=torch.bfloat16, device=src.device) if ld != cols else \
+        torch.empty(b, rows, ld, dtype=torch.bfloat16, device=src.device)
+    with torch.cuda.device(src.device):
+        _cabi.check(L.mlg_cast_bf16(_cabi.fptr(src), src.stride(1), R, C, b, int(transpose),
+                                    ctypes.c_void_p(dst.data_ptr()), ld, _cabi.stream_ptr()), "mlg_cast_bf16")
+    return dst, ld
+
+
+def _gemm_tn(a_bf, lda, b_bf, ldb, M, N, K, batch, a_batched, b_batched):
+    """C[b] = A[b] (M x K) . B[b]^T (N x K), operands already bf16 K-major."""
+    L = _cabi.lib()
+    c = torch.empty(batch, M, N, dtype=torch.float32, device=a_bf.device)
+    sa = a_bf.stride(0) if a_batched else 0
+    sb = b_bf.stride(0) if b_batched else 0
+    flops = 2.0 * M * N * K * batch
+    with torch.cuda.device(a_bf.device), _cabi.span("gemm_bf16", flops):
+        if batch > 1 and (not a_batched or not b_batched):
+            # TMA maps carry one batch stride; a shared operand is looped over (rare: only adj is shared)
+            for i in range(batch):
+                ai = a_bf[i] if a_batched else a_bf[0]
+                bi = b_bf[i] if b_batched else b_bf[0]
+                _cabi.check(L.mlg_gemm_bf16(ctypes.c_void_p(ai.data_ptr()), lda, 0, ctypes.c_void_p(bi.data_ptr()), ldb, 0,
+                                            _cabi.fptr(c[i]), N, 0, M, N, K, 1, 1.0, _cabi.stream_ptr()), "mlg_gemm_bf16")
+        else:
+            _cabi.check(L.mlg_gemm_bf16(ctypes.c_void_p(a_bf.data_ptr()), lda, sa, ctypes.c_void_p(b_bf.data_ptr()), ldb, sb,
+                                        _cabi.fptr(c), N, M * N, M, N, K, batch, 1.0, _cabi.stream_ptr()), "mlg_gemm_bf16")
+    return c
+
+
+def _as3(t):
+    return t.unsqueeze(0) if t.dim() == 2 else t.reshape(-1, t.shape[-2], t.shape[-1])
+
+
+def _mm(a, b):
+    """a [ba, M, K] @ b [bb, K, N] -> [max(ba, bb), M, N] (ba, bb in {1, B})."""
+    a3, b3 = _as3(a).float(), _as3(b).float()
+    a3 = a3 if a3.stride(2) == 1 else a3.contiguous()
+    b3 = b3 if b3.stride(2) == 1 else b3.contiguous()
+    batch = max(a3.shape[0], b3.shape[0])
+    M, K, N = a3.shape[1], a3.shape[2], b3.shape[2]
+    a_bf, lda = _cast(a3, False)
+    b_bf, ldb = _cast(b3, True)
+    return _gemm_tn(a_bf, lda, b_bf, ldb, M, N, K, batch, a3.shape[0] > 1, b3.shape[0] > 1)
+
+
+class _MatmulBf16(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a, b):
+        _cabi.require_cuda(a, b)
+        ctx.save_for_backward(a, b)
+        out = _mm(a.detach(), b.detach())
+        ctx.out_dim = max(a.dim(), b.dim())
+        return out if ctx.out_dim == 3 else out[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        a, b = ctx.saved_tensors
+        g3 = _as3(g)
+        ga = gb = None
+        if ctx.needs_input_grad[0]:
+            ga = _mm(g3, _as3(b).transpose(1, 2))                # [B, M, K]
+            ga = ga.sum(0, keepdim=True) if _as3(a).shape[0] == 1 and ga.shape[0] > 1 else ga
+            ga = ga.reshape(a.shape)
+        if ctx.needs_input_grad[1]:
+            gb = _mm(_as3(a).transpose(1, 2), g3)                # [B, K, N]
+            gb = gb.sum(0, keepdim=True) if _as3(b).shape[0] == 1 and gb.shape[0] > 1 else gb
+            gb = gb.reshape(b.shape)
+        return ga, gb
+
+
+def matmul_bf16(a, b):
+    if a.dim() > 3 or b.dim() > 3:
+        raise NotImplementedError("matmul_bf16 handles 2-D / 3-D operands")
+    return _MatmulBf16.apply(a, b)

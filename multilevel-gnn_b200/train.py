@@ -53,6 +53,9 @@ class GradBucket:
 
 
 class Trainer:
+    """One training step of train.py:38-68 on the B200 kernels; ``capture()`` turns the whole step
+    (forward, loss, backward, NCCL all-reduce, fused Adam) into ONE CUDA graph replayed per step."""
+
     def __init__(self, model, args, criterion_weight=None, world_size=1, fused_adam=True):
         self.model, self.args, self.world = model, args, world_size
         self.params = [p for n, p in model.named_parameters() if p.requires_grad and not n.endswith("lin_l.weight")]
@@ -61,19 +64,21 @@ class Trainer:
         self.flat = self.bucket.flat
         kw = dict(lr=args.lr, betas=(args.beta1, args.beta2), weight_decay=args.wd)
         if fused_adam and dev.type == "cuda":
-            kw["fused"] = True
+            kw.update(fused=True, capturable=True)
         self.opt = torch.optim.Adam(self.params, **kw)
         self.weight = criterion_weight
         self.crit = torch.nn.BCELoss(weight=criterion_weight) if args.weight_balance else torch.nn.BCELoss()
+        self.graph = None
+        self.static_batch = None
+        self.static_loss = None
+        self._copy_stream = None
 
     def loss(self, batch):
         pred, feat = self.model(batch)
         loss = self.crit(pred.to(torch.float32), batch.y.reshape(-1, 2).to(torch.float32))
         return loss + self.model.get_feature_loss(feat)
 
-    def step(self, batch):
-        """forward, loss, backward, (all-reduce), Adam.  Returns the loss as a device scalar (the
-        reference's ``loss.item()`` host sync is the caller's choice)."""
+    def _step_eager(self, batch):
         self.model.train()
         self.bucket.zero()                       # == optimizer.zero_grad() with grads kept as bucket views
         loss = self.loss(batch)
@@ -83,3 +88,64 @@ class Trainer:
             torch.nn.utils.clip_grad_norm_(self.params, max_norm=20, norm_type=2)
         self.opt.step()
         return loss.detach()
+
+    def capture(self, batch, warmup=3):
+        """Capture one full step as a CUDA graph over ``batch``'s device tensors (they become the static
+        input buffers).  The CSR / pool layouts are built during the warm-up steps (their one-time host
+        syncs are not capturable); afterwards every step is a single graph launch."""
+        self.static_batch = batch
+        cur = torch.cuda.current_stream()
+        side = torch.cuda.Stream()
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                self._step_eager(batch)
+        cur.wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.static_loss = self._step_eager(batch)
+        return self
+
+    def load_batch(self, host_batch):
+        """Copy a (pinned) host batch into the captured graph's static device buffers (async H2D)."""
+        for k, v in vars(self.static_batch).items():
+            if torch.is_tensor(v):
+                v.copy_(getattr(host_batch, k), non_blocking=True)
+
+    def prefetch(self, host_batch):
+        """Start the H2D copy of the NEXT batch on a side stream into staging buffers while the current step's
+        graph is still running; ``step_prefetched`` then moves it into the static buffers (device-to-device)
+        and replays.  This is the double buffering the reference's synchronous ``batch.to(device)``
+        (train.py:42) lacks."""
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream()
+            self._staging = {k: torch.empty_like(v) for k, v in vars(self.static_batch).items() if torch.is_tensor(v)}
+            self._staged = torch.cuda.Event()
+            self._consumed = torch.cuda.Event()
+            self._consumed.record()
+        self._copy_stream.wait_event(self._consumed)        # staging may not be overwritten before it was consumed
+        with torch.cuda.stream(self._copy_stream):
+            for k, v in self._staging.items():
+                v.copy_(getattr(host_batch, k), non_blocking=True)
+            self._staged.record()
+
+    def step_prefetched(self):
+        cur = torch.cuda.current_stream()
+        cur.wait_event(self._staged)
+        for k, v in self._staging.items():
+            getattr(self.static_batch, k).copy_(v, non_blocking=True)
+        self._consumed.record()
+        self.graph.replay()
+        return self.static_loss
+
+    def step(self, batch=None):
+        """forward, loss, backward, (all-reduce), Adam.  Returns the loss as a device scalar (the
+        reference's ``loss.item()`` host sync is the caller's choice).  With a captured graph, ``batch`` must
+        be the static batch (or None); use ``load_batch`` to feed new data."""
+        if self.graph is not None:
+            if batch is not None and batch is not self.static_batch:
+                self.load_batch(batch)
+            self.graph.replay()
+            return self.static_loss
+        return self._step_eager(batch)

@@ -1,0 +1,79 @@
+"""tcgen05 / TMA bf16 GEMM (mlg_gemm_bf16) and the DiffPool tensor-core path.
+
+Tolerances: operands are rounded to bf16 (8-bit mantissa), accumulation is fp32 in tensor memory.
+ (1) against the SAME bf16-rounded operands multiplied in fp64 the only difference is summation order:
+     rtol 1e-4 / atol 1e-4*scale;
+ (2) against the fp32 product the bf16 rounding of both operands gives a relative error ~2^-8 per term:
+     |err| <= 2^-7 * sqrt(K) * rms(a) * rms(b) * 4 is asserted (a loose statistical bound)."""
+import math
+
+import pytest
+import torch
+
+from conftest import assert_close
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+@pytest.fixture(scope="module")
+def gemm():
+    from multilevel_gnn_b200 import gemm as g
+    return g
+
+
+@pytest.mark.parametrize("shape", [(128, 128, 64), (256, 384, 512), (130, 70, 200), (1000, 37, 146), (2048, 2048, 4096),
+                                   (300, 1024, 1000)])
+def test_gemm_bf16_matches_rounded_reference(gemm, shape):
+    M, N, K = shape
+    g = torch.Generator().manual_seed(M + N + K)
+    a = torch.randn(M, K, generator=g).to(DEV)
+    b = torch.randn(K, N, generator=g).to(DEV)
+    c = gemm.matmul_bf16(a, b)
+    ref = (a.bfloat16().double() @ b.bfloat16().double()).float()
+    assert_close(c, ref, rtol=1e-4, atol=1e-4, what="bf16-rounded reference %s" % (shape,))
+    err = (c - a @ b).abs().max().item()
+    assert err <= 2 ** -7 * math.sqrt(K) * 4, "vs fp32 product: %g" % err
+
+
+def test_gemm_bf16_batched_and_grad(gemm):
+    g = torch.Generator().manual_seed(5)
+    a = torch.randn(3, 200, 320, generator=g).to(DEV).requires_grad_()
+    b = torch.randn(3, 320, 150, generator=g).to(DEV).requires_grad_()
+    c = gemm.matmul_bf16(a, b)
+    ref = torch.matmul(a.detach().bfloat16().double(), b.detach().bfloat16().double()).float()
+    assert_close(c, ref, rtol=1e-4, atol=1e-4, what="batched")
+    go = torch.randn(c.shape, generator=g).to(DEV)
+    ga, gb = torch.autograd.grad(c, [a, b], go)
+    ra = torch.matmul(go.bfloat16().double(), b.detach().bfloat16().double().transpose(1, 2)).float()
+    rb = torch.matmul(a.detach().bfloat16().double().transpose(1, 2), go.bfloat16().double()).float()
+    assert_close(ga, ra, rtol=1e-4, atol=1e-4, what="grad a")
+    assert_close(gb, rb, rtol=1e-4, atol=1e-4, what="grad b")
+    # shared (2-D) left operand broadcast over the batch, as DiffPool's adj
+    adj = torch.randn(200, 200, generator=g).to(DEV)
+    x = torch.randn(3, 200, 96, generator=g).to(DEV)
+    y = gemm.matmul_bf16(adj, x)
+    assert_close(y, torch.matmul(adj.bfloat16().double(), x.bfloat16().double()).float(), rtol=1e-4, atol=1e-4, what="2D x 3D")
+
+
+def test_diffpool_tensor_core_path_close_to_fp32():
+    """DiffPool at a size where dense_ops takes the tcgen05 path (N=1024 nodes): outputs within the bf16
+    tolerance of the fp32 library path on the same weights."""
+    import multilevel_gnn_b200 as m
+    from multilevel_gnn_b200 import dense_ops
+    torch.manual_seed(0)
+    args = m.configs.make_args("lgg")
+    n, c = 4096, 1024
+    dp = m.DiffPool(c, 2, n, 1, 1024, 1024, args).to(DEV)
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(1, n, c, generator=g).to(DEV)
+    a = torch.rand(n, n, generator=g)
+    adj = ((a + a.t()) * 0.5 + torch.eye(n)).to(DEV)
+    dense_ops.FORCE_FP32 = True
+    ref, l0, e0 = dp(x, adj)
+    dense_ops.FORCE_FP32 = False
+    assert dense_ops.use_tensor_cores(adj, x[0])
+    out, l1, e1 = dp(x, adj)
+    assert_close(out, ref, rtol=3e-2, atol=3e-2, what="DiffPool bf16 vs fp32")
+    assert abs(float(l1) - float(l0)) <= 2e-2 * abs(float(l0)) + 1e-6
+    assert abs(float(e1) - float(e0)) <= 2e-2 * abs(float(e0)) + 1e-4

@@ -87,9 +87,29 @@ def knn(a):
     print(json.dumps({"kernel": "knn", "n": a.n, "d": a.d, "k": a.k, "ms": ms, "TFLOPs_fp32": fl / ms / 1e9}))
 
 
+def gemm(a):
+    """tcgen05 bf16 GEMM on pre-cast K-major operands: C[M,N] = A[M,K] . B[N,K]^T."""
+    import ctypes
+    from multilevel_gnn_b200 import _cabi
+    L = _cabi.lib()
+    for (M, N, K, what) in [(2500, 10000, 10000, "S^T.A"), (2500, 1024, 10000, "S^T.X"), (2500, 2500, 10000, "(S^T.A).S"),
+                            (10000, 1024, 10000, "A.X"), (10000, 10000, 2500, "S.S^T"), (8192, 8192, 8192, "square")]:
+        A = torch.randn(M, K, device=DEV).bfloat16()
+        B = torch.randn(N, K, device=DEV).bfloat16()
+        C = torch.empty(M, N, device=DEV)
+        run = lambda: _cabi.check(L.mlg_gemm_bf16(ctypes.c_void_p(A.data_ptr()), K, 0, ctypes.c_void_p(B.data_ptr()), K, 0,
+                                                  _cabi.fptr(C), N, 0, M, N, K, 1, 1.0, _cabi.stream_ptr()), "mlg_gemm_bf16")
+        ms = timeit(run, reps=10, warm=2)
+        ref = timeit(lambda: torch.matmul(A, B.t()), reps=10, warm=2)
+        tf = 2.0 * M * N * K / ms / 1e9
+        print(json.dumps({"kernel": "gemm_bf16", "what": what, "M": M, "N": N, "K": K, "ms": round(ms, 4), "TFLOPs": round(tf, 1),
+                          "frac_of_1650": round(tf / 1650.5, 3), "cublas_bf16_ms": round(ref, 4),
+                          "cublas_TFLOPs": round(2.0 * M * N * K / ref / 1e9, 1)}))
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
-    ap.add_argument("what", choices=["genconv", "sage", "knn"])
+    ap.add_argument("what", choices=["genconv", "sage", "knn", "gemm"])
     ap.add_argument("--n", type=int, default=100000)
     ap.add_argument("--k", type=int, default=16)
     ap.add_argument("--H", type=int, default=128)
@@ -99,4 +119,4 @@ if __name__ == "__main__":
     ap.add_argument("--bwd", action="store_true")
     ap.add_argument("--generic", action="store_true")
     a = ap.parse_args()
-    {"genconv": genconv, "sage": sage, "knn": knn}[a.what](a)
+    {"genconv": genconv, "sage": sage, "knn": knn, "gemm": gemm}[a.what](a)
