@@ -309,7 +309,9 @@ extern "C" int mlg_gemm_bf16(const void* A, int64_t lda, int64_t stride_a, const
                 "mlg_gemm_bf16: TMA needs 16-byte aligned operands with leading dimensions that are multiples of 8");
   MLG_CHECK_ARG(lda >= K && ldb >= K && ldc >= N, "mlg_gemm_bf16: leading dimension too small");
   CUtensorMap ma, mb;
-  const bool wide = N > 128;
+  // 256-wide tiles halve the A re-reads, but only pay when they still fill the 148 SMs
+  const long long tiles256 = ((M + BM - 1) / BM) * ((N + 255) / 256) * batch;
+  const bool wide = N > 128 && tiles256 >= 148;
   int rc = make_map(&ma, A, K, M, lda, batch, stride_a, BM);
   if (rc) return rc;
   rc = make_map(&mb, B, K, N, ldb, batch, stride_b, wide ? 256 : 128);
