@@ -77,7 +77,7 @@ int mlg_edge_values(const float* edge_attr, const int32_t* eid, const int32_t* r
  * x [n, H]; e [E, H] indexed by eid[q] (or by q when eid == NULL); t/p/y: device scalars when the
  * *_dev pointer is non-NULL (learnable Parameters), else the host value; y_dev != NULL multiplies
  * the result by deg^sigmoid(y) (softmax_sum / power_sum).
- * Outputs: m [n,H]; aux [n,H] (may be NULL for inference: softmax -> log2-sum-exp of t*msg*log2(e),
+ * Outputs: m [n,H] (may be NULL for inference when h is produced); aux [n,H] (may be NULL for inference: softmax -> log2-sum-exp of t*msg*log2(e),
  * power -> the un-clamped mean); h [n,H] (NULL iff epilogue == MLG_EPI_NONE).
  */
 int mlg_gen_aggr_fwd(const float* x, const float* e, const int32_t* rowptr, const int32_t* col,

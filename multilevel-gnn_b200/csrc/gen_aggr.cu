@@ -254,7 +254,7 @@ __global__ void __launch_bounds__(kThreads, MLG_GEN_FWD_MIN_BLOCKS) gen_fwd_kern
       o.v[k] = r;
       ax.v[k] = au;
     }
-    st_v<VEC, FULL>(mrow + c, o, cok, false);
+    if (P.m) st_v<VEC, FULL>(mrow + c, o, cok, false);
     if (P.aux) st_v<VEC, FULL>(row_ptr(P.aux, (unsigned)row, H) + c, ax, cok, true);
     if (P.epi != MLG_EPI_NONE) {
       Vec<VEC> xr = ld_g<VEC, FULL>(xrow + c, cok);
@@ -505,6 +505,219 @@ __global__ void __launch_bounds__(kThreads) gen_bwd_kernel(const GenP P) {
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// forward, shared-memory staged variant (softmax family, x + e messages, H = 128 * NV):
+// every warp owns RPW consecutive target rows and walks their edges as ONE flat stream; each edge's
+// source row and edge-feature row are copied global -> shared with 16-byte cp.async (one commit group
+// per edge, kDepth edges in flight per warp, no registers held), each lane reading back exactly the 16
+// bytes it copied (no barrier needed, cp.async.wait_group only).  The edge stream carries an L2
+// evict-first policy so that it does not push the re-used node rows out of L2.
+// ------------------------------------------------------------------------------------------------
+#ifndef MLG_RING_WARPS
+#define MLG_RING_WARPS 4
+#endif
+#ifndef MLG_RING_RPW
+#define MLG_RING_RPW 8
+#endif
+#ifndef MLG_RING_DEPTH
+#define MLG_RING_DEPTH 8
+#endif
+constexpr int kRingWarps = MLG_RING_WARPS;   // warps per block
+constexpr int kRPW = MLG_RING_RPW;           // rows per warp
+constexpr int kDepth = MLG_RING_DEPTH;       // edges in flight per warp (power of two)
+
+__device__ __forceinline__ void cp_async16_pol(unsigned dst, const void* src, unsigned long long pol) {
+  asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "l"(pol)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async16_plain(unsigned dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ float4 lds128(unsigned addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+
+constexpr int kGroup = 4;                       // edges per commit group
+constexpr int kGroups = kDepth / kGroup;        // groups in flight per warp
+
+template <int NV>
+__global__ void __launch_bounds__(kRingWarps * 32) gen_fwd_ring_kernel(const GenP P) {
+  extern __shared__ __align__(16) unsigned char ring_raw[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const long long gw = (long long)blockIdx.x * kRingWarps + wib;
+  const long long r0 = gw * kRPW;
+  if (r0 >= P.n) return;
+  const int r1 = (int)min((long long)P.n, r0 + kRPW);
+  const unsigned H = P.H;
+  constexpr unsigned kSlotBytes = 2 * NV * 512;   // x chunk(s) + e chunk(s) of one edge
+  const unsigned sbase = (unsigned)__cvta_generic_to_shared(ring_raw) + wib * kDepth * kSlotBytes + lane * 16;
+  unsigned long long pol_stream;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_stream));
+
+  // row pointers of this warp's rows: lane j holds rowptr[r0 + j] (j <= RPW)
+  const int rp = __ldg(P.rowptr + min((long long)P.n, r0 + min(lane, kRPW)));
+  const int qb = __shfl_sync(0xffffffffu, rp, 0);
+  const int qe = __shfl_sync(0xffffffffu, rp, r1 - (int)r0);
+  const int* eidp = P.eid;
+  const float t = P.t_dev ? __ldg(P.t_dev) : P.t;
+  const float tl2 = t * MLG_LOG2E;
+  const float eps = P.eps;
+  const float ysig = P.y_dev ? sigmoidf_(__ldg(P.y_dev)) : 0.f;
+  const float scale = (P.epi == MLG_EPI_MSGNORM) ? __ldg(P.scale_dev) : 0.f;
+  const float* xc = P.x + lane * 4;
+  const float* ec = P.e + lane * 4;
+  const int n_groups = (qe - qb + kGroup - 1) / kGroup;
+
+  // ---- issue side: one commit group = kGroup edges; the group's source / edge ids are fetched (uniform,
+  //      L1-broadcast loads) one group ahead of their use so the address chain never stalls the issue ----
+  unsigned nxt_s[kGroup], nxt_e[kGroup];
+  auto fetch_ids = [&](int g) {
+#pragma unroll
+    for (int u = 0; u < kGroup; ++u) {
+      const int p = min(qb + g * kGroup + u, qe - 1);
+      nxt_s[u] = (unsigned)__ldg(P.col + p);
+      nxt_e[u] = eidp ? (unsigned)__ldg(eidp + p) : (unsigned)p;
+    }
+  };
+  auto issue = [&](int g) {   // uses the ids fetched for group g, then fetches those of group g + 1
+    if (g < n_groups) {
+      const unsigned slot0 = sbase + (unsigned)((g % kGroups) * kGroup) * kSlotBytes;
+#pragma unroll
+      for (int u = 0; u < kGroup; ++u) {
+        const unsigned slot = slot0 + u * kSlotBytes;
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+          cp_async16_plain(slot + v * 512, row_ptr(xc, nxt_s[u], H) + v * 128);
+          cp_async16_pol(slot + (NV + v) * 512, row_ptr(ec, nxt_e[u], H) + v * 128, pol_stream);
+        }
+      }
+      if (g + 1 < n_groups) fetch_ids(g + 1);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  if (n_groups > 0) fetch_ids(0);
+#pragma unroll
+  for (int i = 0; i < kGroups - 1; ++i) issue(i);
+
+  // ---- consume side ----
+  int row = (int)r0;
+  int rend = __shfl_sync(0xffffffffu, rp, 1);
+  int rbeg = qb;
+  float a0[NV][4], a1[NV][4], a2[NV][4];
+  float4 xi[NV];
+  auto reset = [&]() {
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { a0[v][k] = -INFINITY; a1[v][k] = 0.f; a2[v][k] = 0.f; }
+      xi[v] = (P.epi != MLG_EPI_NONE) ? ld_gather4(row_ptr(xc, (unsigned)row, H) + v * 128) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  };
+  auto finalize = [&]() {
+    const int deg = rend - rbeg;
+    const float degpow = P.y_dev ? powf((float)deg, ysig) : 1.f;
+    float o[NV][4];
+    float sx2 = 0.f, sm2 = 0.f;
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      float au[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        float r = 0.f;
+        au[k] = 0.f;
+        if (deg > 0) {
+          r = a2[v][k] / a1[v][k];
+          au[k] = a0[v][k] + log2f(a1[v][k]);
+        }
+        o[v][k] = r * degpow;
+        sm2 = fmaf(o[v][k], o[v][k], sm2);
+      }
+      sx2 += xi[v].x * xi[v].x + xi[v].y * xi[v].y + xi[v].z * xi[v].z + xi[v].w * xi[v].w;
+      const unsigned off = lane * 4 + v * 128;
+      if (P.m) st4(row_ptr(P.m, (unsigned)row, H) + off, make_float4(o[v][0], o[v][1], o[v][2], o[v][3]));
+      if (P.aux) st_stream4(row_ptr(P.aux, (unsigned)row, H) + off, make_float4(au[0], au[1], au[2], au[3]));
+    }
+    if (P.epi != MLG_EPI_NONE) {
+      float f = 1.f;
+      if (P.epi == MLG_EPI_MSGNORM) {
+        sx2 = warp_sum(sx2);
+        sm2 = warp_sum(sm2);
+        f = scale * sqrtf(sx2) / fmaxf(sqrtf(sm2), 1e-12f);
+      }
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+        const unsigned off = lane * 4 + v * 128;
+        st4(row_ptr(P.h, (unsigned)row, H) + off,
+            make_float4(fmaf(f, o[v][0], xi[v].x), fmaf(f, o[v][1], xi[v].y), fmaf(f, o[v][2], xi[v].z),
+                        fmaf(f, o[v][3], xi[v].w)));
+      }
+    }
+  };
+  reset();
+  for (int g = 0; g < n_groups; ++g) {
+    issue(g + kGroups - 1);
+    asm volatile("cp.async.wait_group %0;" ::"n"(kGroups - 1) : "memory");
+    const unsigned slot0 = sbase + (unsigned)((g % kGroups) * kGroup) * kSlotBytes;
+    const int q0 = qb + g * kGroup;
+#pragma unroll
+    for (int u = 0; u < kGroup; ++u) {
+      const int q = q0 + u;
+      if (q >= qe) break;
+      while (q >= rend) {  // row finished (also skips empty rows)
+        finalize();
+        ++row;
+        rbeg = rend;
+        rend = __shfl_sync(0xffffffffu, rp, row - (int)r0 + 1);
+        reset();
+      }
+      const unsigned slot = slot0 + u * kSlotBytes;
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+        const float4 xv = lds128(slot + v * 512);
+        const float4 ev = lds128(slot + (NV + v) * 512);
+        const float vv[4] = {fmaxf(xv.x + ev.x, 0.f) + eps, fmaxf(xv.y + ev.y, 0.f) + eps,
+                             fmaxf(xv.z + ev.z, 0.f) + eps, fmaxf(xv.w + ev.w, 0.f) + eps};
+        float d[4];
+        float dm = -INFINITY;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          d[k] = fmaf(vv[k], tl2, -a0[v][k]);
+          dm = fmaxf(dm, d[k]);
+        }
+        if (dm > kLazy) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const bool up = d[k] > 0.f;
+            const float sc = ex2_approx(up ? -d[k] : 0.f);
+            a1[v][k] *= sc;
+            a2[v][k] *= sc;
+            a0[v][k] = up ? vv[k] * tl2 : a0[v][k];
+            d[k] = up ? 0.f : d[k];
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float pz = ex2_approx(d[k]);
+          a1[v][k] += pz;
+          a2[v][k] = fmaf(vv[k], pz, a2[v][k]);
+        }
+      }
+    }
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  while (row < r1) {  // last row with edges + trailing empty rows
+    finalize();
+    ++row;
+    if (row < r1) {
+      rbeg = rend;
+      rend = __shfl_sync(0xffffffffu, rp, row - (int)r0 + 1);
+      reset();
+    }
+  }
+}
+
 struct Cfg {
   int lanes, vec;
   bool full;
@@ -580,8 +793,15 @@ extern "C" int mlg_gen_aggr_fwd(const float* x, const float* e, const int32_t* r
                                 float* h, void* stream) {
   int rc = check_common("mlg_gen_aggr_fwd", x, e, rowptr, col, n, H, epilogue, msg_scale_dev);
   if (rc) return rc;
-  MLG_CHECK_ARG(m, "mlg_gen_aggr_fwd: null m");
   MLG_CHECK_ARG(epilogue == MLG_EPI_NONE || h, "mlg_gen_aggr_fwd: epilogue needs h");
+  {
+    // m may be omitted (inference: only h is wanted) unless the MsgNorm epilogue has to re-read it (rows wider
+    // than one 4*LANES chunk on the register-staged path)
+    const bool single_chunk = (H % 4 == 0) && H <= 128;
+    const bool ring = mode == MLG_AGGR_SOFTMAX && x && e && (H == 128 || H == 256);
+    MLG_CHECK_ARG(m || (epilogue != MLG_EPI_NONE && (ring || single_chunk || epilogue == MLG_EPI_RESIDUAL)),
+                  "mlg_gen_aggr_fwd: m may only be NULL when h is produced without re-reading m");
+  }
   if (n == 0) return MLG_OK;
   GenP P;
   memset(&P, 0, sizeof(P));
@@ -589,6 +809,25 @@ extern "C" int mlg_gen_aggr_fwd(const float* x, const float* e, const int32_t* r
   P.n = (int)n; P.H = (unsigned)H; P.mode = mode; P.epi = epilogue;
   P.t = t; P.p = p; P.eps = eps; P.t_dev = t_dev; P.p_dev = p_dev; P.y_dev = y_dev;
   P.scale_dev = msg_scale_dev; P.m = m; P.aux = aux; P.h = h;
+#ifndef MLG_GEN_NO_RING
+  if (mode == MLG_AGGR_SOFTMAX && x && e && (H == 128 || H == 256) && ((uintptr_t)x % 16 == 0) && ((uintptr_t)e % 16 == 0)) {
+    const int nv = (int)(H / 128);
+    const int smem = kRingWarps * kDepth * 2 * nv * 512;
+    const unsigned grid = (unsigned)mlg_ceil_div(n, kRingWarps * kRPW);
+    static bool attr = false;
+    if (!attr) {
+      MLG_CUDA(cudaFuncSetAttribute(gen_fwd_ring_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    kRingWarps * kDepth * 2 * 1 * 512));
+      MLG_CUDA(cudaFuncSetAttribute(gen_fwd_ring_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    kRingWarps * kDepth * 2 * 2 * 512));
+      attr = true;
+    }
+    if (nv == 1) gen_fwd_ring_kernel<1><<<grid, kRingWarps * 32, smem, (cudaStream_t)stream>>>(P);
+    else gen_fwd_ring_kernel<2><<<grid, kRingWarps * 32, smem, (cudaStream_t)stream>>>(P);
+    MLG_CHECK_LAUNCH("mlg_gen_aggr_fwd(ring)");
+    return MLG_OK;
+  }
+#endif
   rc = dispatch<true>(P, (cudaStream_t)stream);
   if (rc) return rc;
   MLG_CHECK_LAUNCH("mlg_gen_aggr_fwd");

@@ -96,10 +96,14 @@ class GenAggregate(torch.autograd.Function):
         p_h, p_d = _scalar_args(p)
         y_d = None if y is None else _cabi.fptr(y.detach().reshape(1))
         s_d = None if msg_scale is None else _cabi.fptr(msg_scale.detach().reshape(1))
-        need_grad = any(torch.is_tensor(v) and v.requires_grad for v in (x, e, t, p, y, msg_scale))
-        m = torch.empty(n, H, dtype=torch.float32, device=ref.device)
-        aux = torch.empty_like(m) if (need_grad and mode in (0, 1)) else None
-        h = torch.empty_like(m) if epilogue != EPI_NONE else None
+        need_grad = any(ctx.needs_input_grad)      # False under torch.no_grad() as well
+        h = torch.empty(n, H, dtype=torch.float32, device=ref.device) if epilogue != EPI_NONE else None
+        # inference: only h leaves the kernel (m / aux exist for the backward pass); the kernel re-reads m for
+        # the MsgNorm epilogue of rows wider than one chunk on the register-staged path, so keep it there
+        m_optional = h is not None and not need_grad and (H <= 128 or (mode == 0 and x is not None and e is not None
+                                                                        and H == 256) or epilogue == EPI_RESIDUAL)
+        m = None if m_optional else torch.empty(n, H, dtype=torch.float32, device=ref.device)
+        aux = torch.empty(n, H, dtype=torch.float32, device=ref.device) if (need_grad and mode in (0, 1)) else None
         n_entries = csr.col.numel()
         ctx_bytes = 4 * H * ((n_entries if e is not None else 0) + 2 * n) + 4 * n_entries + 4 * (n + 1)
         with torch.cuda.device(ref.device), _cabi.span("gen_aggr_fwd", ctx_bytes):
@@ -107,8 +111,10 @@ class GenAggregate(torch.autograd.Function):
                 _cabi.fptr(xd, True), _cabi.fptr(ed, True), _cabi.iptr(csr.rowptr), _cabi.iptr(csr.col),
                 None if topo.fwd_identity else _cabi.iptr(csr.eid), n, H, mode, t_h, t_d, p_h, p_d, y_d,
                 float(eps), epilogue, s_d,
-                _cabi.fptr(m), _cabi.fptr(aux, True), _cabi.fptr(h, True), _cabi.stream_ptr()),
+                _cabi.fptr(m, True), _cabi.fptr(aux, True), _cabi.fptr(h, True), _cabi.stream_ptr()),
                 "mlg_gen_aggr_fwd")
+        if not need_grad:
+            return h if h is not None else m
         ctx.topo, ctx.mode, ctx.eps, ctx.epilogue, ctx.learn = topo, mode, float(eps), epilogue, bool(learn)
         ctx.t, ctx.p, ctx.y, ctx.scale = t, p, y, msg_scale
         ctx.has_x, ctx.has_e = x is not None, e is not None

@@ -49,6 +49,14 @@ def genconv(a):
     ms = timeit(fwd)
     nb = 4 * H * (n * k + 2 * n) + 4 * n * k + 4 * (n + 1)
     out = {"kernel": "gen_aggr_fwd", "ms": ms, "GBps": nb / ms / 1e6, "frac": nb / ms / 1e6 / HBM}
+    with torch.no_grad():
+        ms_inf = timeit(fwd)
+    out.update({"inference_ms": ms_inf, "inference_GBps": nb / ms_inf / 1e6, "inference_frac": nb / ms_inf / 1e6 / HBM})
+    with torch.no_grad():
+        ms_x = timeit(lambda: Fn.GenAggregate.apply(x, None, t, 1.0, None, scale, topo, a.aggr, 1e-7, Fn.EPI_MSGNORM, True))
+        ms_e = timeit(lambda: Fn.GenAggregate.apply(None, e, t, 1.0, None, None, topo, a.aggr, 0.0, Fn.EPI_NONE, True))
+    out.update({"x_only_ms": ms_x, "x_only_L2_GBps": 4 * H * n * k / ms_x / 1e6, "e_only_ms": ms_e,
+                "e_only_GBps": 4 * H * n * k / ms_e / 1e6})
     if a.bwd:
         h = fwd()
         gout = torch.randn_like(h)
