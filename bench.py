@@ -302,7 +302,8 @@ def run_b200(a):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "config/%s.yaml MultilevelGNN train step (fwd+bwd+allreduce+Adam), %d graphs/GPU, "
                                "N=15405 nodes, E=92430 edges/graph, G=25015, P=%d" % (a.config, B, args.pca_dim),
-                   "graphs_per_gpu": B, "parallelism": "dp%d" % world, "step": "one CUDA graph (fwd+loss+bwd+allreduce+Adam)" if tr.graph is not None else "eager",
+                   "graphs_per_gpu": B, "parallelism": "dp%d" % world, "step": ("eager" if tr.graph is None else "one CUDA graph (fwd+loss+bwd+Adam)" if world == 1 else
+                            "CUDA graph (fwd+loss+bwd) -> NCCL all-reduce -> CUDA graph (Adam)"),
                    "l2": "no flush: per-step working set (~2 GB of activations) exceeds the 126 MB L2"},
         "e2e": {"value": round(B * world * a.steps / (ms_e2e / 1e3), 2), "unit": "graphs/s",
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "ms_per_step": round(ms_e2e / a.steps, 4)},

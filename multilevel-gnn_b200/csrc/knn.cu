@@ -4,8 +4,9 @@
 //   models/gcn_lib/sparse/torch_edge.py:53-104   (knn_matrix / knn_graph_matrix / Dilated)
 //   models/gcn_lib/dense/torch_edge.py:32-58     (dense_knn_matrix / DenseDilated)
 // The reference materialises the [B,N,N] distance matrix (400 MB per graph at N=10k) and runs a full-row
-// radix select; here a 64x64 distance tile lives in registers/shared memory only and each query row keeps
-// a sorted K-entry candidate list in shared memory.
+// radix select; here a 128x128 distance tile lives in registers (8x8 per thread) and passes through shared
+// memory 32 columns at a time for the selection; each query row keeps a sorted K-entry candidate list in
+// shared memory.
 //
 // Arithmetic (exactness contract, SURVEY.md section 7 "hard parts"): fp32 FMA only (no TF32/BF16),
 //   dot_ij = fma-chain over d ascending;  sq_i = the same chain on (x_i, x_i)  => d_ii == 0 exactly;
@@ -18,9 +19,10 @@
 
 namespace {
 
-constexpr int TQ = 64;   // query rows per block
-constexpr int TC = 64;   // candidate columns per tile
+constexpr int TC = 128;  // candidate columns per tile
 constexpr int DK = 16;   // feature chunk
+constexpr int LDT = 128 + 4;  // padded row length of the transposed operand tiles
+constexpr int QW = 32;   // columns per selection pass
 constexpr int kThreads = 256;
 constexpr int kMaxK = 128;
 
@@ -55,14 +57,17 @@ __device__ __forceinline__ void list_insert(float* bd, int* bi, int K, float d, 
   __syncwarp();
 }
 
+// 128 x 128 distance tile per iteration: 16 x 16 threads, 8 x 8 outputs each (rows {ty*4..+3, 64+ty*4..+3},
+// cols {tx*4..+3, 64+tx*4..+3}: every shared-memory operand read is a conflict-free / broadcast LDS.128)
+template <int TQ>   // query rows per block: 128 (8x8 outputs per thread) or 64 (4x8; more blocks for small graphs)
 __global__ void __launch_bounds__(kThreads)
 knn_kernel(const float* __restrict__ x, const float* __restrict__ sq, int N, int D, int K, int dil, int add_offset,
            long long* __restrict__ out_nbr, long long* __restrict__ out_ctr, float* __restrict__ out_dist) {
-  extern __shared__ float smem[];
-  float* As = smem;                        // [DK][TQ+4]
-  float* Bs = As + DK * (TQ + 4);          // [DK][TC+4]
-  float* Ds = Bs + DK * (TC + 4);          // [TQ][TC+1]
-  float* sqc = Ds + TQ * (TC + 1);         // [TC]
+  extern __shared__ __align__(16) float smem[];
+  float* As = smem;                        // [DK][LDT]
+  float* Bs = As + DK * LDT;               // [DK][LDT]
+  float* Ds = Bs + DK * LDT;               // [TQ][QW+1]
+  float* sqc = Ds + TQ * (QW + 1);         // [TC]
   float* bd = sqc + TC;                    // [TQ][K]
   int* bi = reinterpret_cast<int*>(bd + TQ * K);  // [TQ][K]
 
@@ -71,80 +76,90 @@ knn_kernel(const float* __restrict__ x, const float* __restrict__ sq, int N, int
   const float* xb = x + (size_t)b * N * D;
   const float* sqb = sq + (size_t)b * N;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const int ty = tid / 16, tx = tid % 16;  // 16x16 threads, 4x4 outputs each
+  const int ty = tid / 16, tx = tid % 16;
 
   for (int i = tid; i < TQ * K; i += kThreads) { bd[i] = INFINITY; bi[i] = -1; }
-  float sqq[4];
+  constexpr int RT = TQ / 16;   // rows per thread
+  float sqq[RT];
 #pragma unroll
-  for (int r = 0; r < 4; ++r) {
-    const int qi = q0 + ty * 4 + r;
+  for (int r = 0; r < RT; ++r) {
+    const int qi = q0 + (r < 4 ? ty * 4 + r : 64 + ty * 4 + r - 4);
     sqq[r] = qi < N ? __ldg(sqb + qi) : 0.f;
   }
   __syncthreads();
 
   for (int c0 = 0; c0 < N; c0 += TC) {
-    float acc[4][4];
+    float acc[RT][8];
 #pragma unroll
-    for (int r = 0; r < 4; ++r)
+    for (int r = 0; r < RT; ++r)
 #pragma unroll
-      for (int c = 0; c < 4; ++c) acc[r][c] = 0.f;
+      for (int c = 0; c < 8; ++c) acc[r][c] = 0.f;
     if (tid < TC) sqc[tid] = (c0 + tid < N) ? __ldg(sqb + c0 + tid) : 0.f;
 
     for (int d0 = 0; d0 < D; d0 += DK) {
-      // load 64 x 16 query and candidate sub-tiles, transposed into [k][row]
-      for (int i = tid; i < TQ * DK; i += kThreads) {
+      // 128 rows x 16 features of the query block and of the candidate block, transposed into [k][row]
+      for (int i = tid; i < TC * DK; i += kThreads) {
         const int row = i / DK, k = i % DK;
         const int qi = q0 + row, ci = c0 + row, dd = d0 + k;
-        As[k * (TQ + 4) + row] = (qi < N && dd < D) ? __ldg(xb + (size_t)qi * D + dd) : 0.f;
-        Bs[k * (TC + 4) + row] = (ci < N && dd < D) ? __ldg(xb + (size_t)ci * D + dd) : 0.f;
+        if (row < TQ) As[k * LDT + row] = (qi < N && dd < D) ? __ldg(xb + (size_t)qi * D + dd) : 0.f;
+        Bs[k * LDT + row] = (ci < N && dd < D) ? __ldg(xb + (size_t)ci * D + dd) : 0.f;
       }
       __syncthreads();
 #pragma unroll
       for (int k = 0; k < DK; ++k) {
-        const float4 a = *reinterpret_cast<const float4*>(As + k * (TQ + 4) + ty * 4);
-        const float4 bb = *reinterpret_cast<const float4*>(Bs + k * (TC + 4) + tx * 4);
-        const float av[4] = {a.x, a.y, a.z, a.w};
-        const float bv[4] = {bb.x, bb.y, bb.z, bb.w};
+        const float4 a0 = *reinterpret_cast<const float4*>(As + k * LDT + ty * 4);
+        const float4 a1 = (RT == 8) ? *reinterpret_cast<const float4*>(As + k * LDT + 64 + ty * 4) : a0;
+        const float4 b0 = *reinterpret_cast<const float4*>(Bs + k * LDT + tx * 4);
+        const float4 b1 = *reinterpret_cast<const float4*>(Bs + k * LDT + 64 + tx * 4);
+        const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+        const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-        for (int r = 0; r < 4; ++r)
+        for (int r = 0; r < RT; ++r)
 #pragma unroll
-          for (int c = 0; c < 4; ++c) acc[r][c] = fmaf(av[r], bv[c], acc[r][c]);
+          for (int c = 0; c < 8; ++c) acc[r][c] = fmaf(av[r], bv[c], acc[r][c]);
       }
       __syncthreads();
     }
-    // distances of this tile -> shared
+    // selection in four 32-column passes: distances -> shared, then warp w scans rows 16w .. 16w+15
 #pragma unroll
-    for (int r = 0; r < 4; ++r)
+    for (int pass = 0; pass < TC / QW; ++pass) {
+      const int half = pass >> 1;              // 0: columns tx*4.., 1: columns 64 + tx*4..
+      const int txlo = (pass & 1) * 8;         // which 8 tx values own this pass's 32 columns
+      if (tx >= txlo && tx < txlo + 8) {
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const int cj = tx * 4 + c;
-        const float dist = (sqq[r] + (-2.f * acc[r][c])) + sqc[cj];
-        Ds[(ty * 4 + r) * (TC + 1) + cj] = (c0 + cj < N) ? dist : INFINITY;
+        for (int r = 0; r < RT; ++r) {
+          const int row = r < 4 ? ty * 4 + r : 64 + ty * 4 + r - 4;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const int cl = (tx - txlo) * 4 + c;                  // column inside the pass
+            const int cj = half * 64 + tx * 4 + c;               // column inside the tile
+            const float dist = (sqq[r] + (-2.f * acc[r][half * 4 + c])) + sqc[cj];
+            Ds[row * (QW + 1) + cl] = (c0 + cj < N) ? dist : INFINITY;
+          }
+        }
       }
-    __syncthreads();
-    // selection: warp w owns query rows w*8 .. w*8+7
-    for (int rr = 0; rr < TQ / 8; ++rr) {
-      const int row = wid * (TQ / 8) + rr;
-      if (q0 + row >= N) break;
-      float* rbd = bd + row * K;
-      int* rbi = bi + row * K;
-#pragma unroll
-      for (int half = 0; half < TC / 32; ++half) {
-        const float dv = Ds[row * (TC + 1) + half * 32 + lane];
+      __syncthreads();
+      const int colbase = c0 + half * 64 + txlo * 4;
+      for (int rr = 0; rr < TQ / 8; ++rr) {
+        const int row = wid * (TQ / 8) + rr;
+        if (q0 + row >= N) break;
+        float* rbd = bd + row * K;
+        int* rbi = bi + row * K;
+        const float dv = Ds[row * (QW + 1) + lane];
         float thr = rbd[K - 1];
-        unsigned pass = __ballot_sync(0xffffffffu, dv < thr);
-        while (pass) {
-          const int src = __ffs(pass) - 1;
-          pass &= pass - 1;
+        unsigned hit = __ballot_sync(0xffffffffu, dv < thr);
+        while (hit) {
+          const int src = __ffs(hit) - 1;
+          hit &= hit - 1;
           const float dc = __shfl_sync(0xffffffffu, dv, src);
           if (dc < thr) {  // threshold may have tightened since the ballot
-            list_insert(rbd, rbi, K, dc, c0 + half * 32 + src, lane);
+            list_insert(rbd, rbi, K, dc, colbase + src, lane);
             thr = rbd[K - 1];
           }
         }
       }
+      __syncthreads();
     }
-    __syncthreads();
   }
 
   // write every dil-th rank
@@ -178,11 +193,20 @@ extern "C" int mlg_knn_graph(const float* x, int64_t B, int64_t N, int64_t D, in
   float* sq = (float*)workspace;
   sqnorm_kernel<<<mlg_ceil_div(B * N, 256), 256, 0, st>>>(x, B * N, (int)D, sq);
   MLG_CHECK_LAUNCH("mlg_knn_graph(sqnorm)");
-  const size_t smem = sizeof(float) * (DK * (TQ + 4) + DK * (TC + 4) + TQ * (TC + 1) + TC) + (size_t)TQ * K * 8;
-  MLG_CUDA(cudaFuncSetAttribute(knn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  dim3 grid(mlg_ceil_div(N, TQ), (unsigned)B);
-  knn_kernel<<<grid, kThreads, smem, st>>>(x, sq, (int)N, (int)D, (int)K, (int)dilation, add_offset,
-                                          (long long*)out_nbr, (long long*)out_ctr, out_dist);
+  // 128-row query tiles when they still give >= 2 blocks per SM, else 64-row tiles (more, smaller blocks)
+  const bool big = mlg_ceil_div(N, 128) * B >= 2 * 148;
+  const int tq = big ? 128 : 64;
+  const size_t smem = sizeof(float) * (2 * DK * LDT + tq * (QW + 1) + TC) + (size_t)tq * K * 8;
+  dim3 grid(mlg_ceil_div(N, tq), (unsigned)B);
+  if (big) {
+    MLG_CUDA(cudaFuncSetAttribute(knn_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    knn_kernel<128><<<grid, kThreads, smem, st>>>(x, sq, (int)N, (int)D, (int)K, (int)dilation, add_offset,
+                                                 (long long*)out_nbr, (long long*)out_ctr, out_dist);
+  } else {
+    MLG_CUDA(cudaFuncSetAttribute(knn_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    knn_kernel<64><<<grid, kThreads, smem, st>>>(x, sq, (int)N, (int)D, (int)K, (int)dilation, add_offset,
+                                                (long long*)out_nbr, (long long*)out_ctr, out_dist);
+  }
   MLG_CHECK_LAUNCH("mlg_knn_graph");
   return MLG_OK;
 }

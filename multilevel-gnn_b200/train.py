@@ -69,6 +69,7 @@ class Trainer:
         self.weight = criterion_weight
         self.crit = torch.nn.BCELoss(weight=criterion_weight) if args.weight_balance else torch.nn.BCELoss()
         self.graph = None
+        self.graph_update = None
         self.static_batch = None
         self.static_loss = None
         self._copy_stream = None
@@ -78,21 +79,30 @@ class Trainer:
         loss = self.crit(pred.to(torch.float32), batch.y.reshape(-1, 2).to(torch.float32))
         return loss + self.model.get_feature_loss(feat)
 
-    def _step_eager(self, batch):
+    def _fwd_bwd(self, batch):
         self.model.train()
         self.bucket.zero()                       # == optimizer.zero_grad() with grads kept as bucket views
         loss = self.loss(batch)
         loss.backward()
-        self.bucket.all_reduce(self.world)
+        return loss.detach()
+
+    def _update(self):
         if self.args.clip_grad:
             torch.nn.utils.clip_grad_norm_(self.params, max_norm=20, norm_type=2)
         self.opt.step()
-        return loss.detach()
+
+    def _step_eager(self, batch):
+        loss = self._fwd_bwd(batch)
+        self.bucket.all_reduce(self.world)
+        self._update()
+        return loss
 
     def capture(self, batch, warmup=3):
-        """Capture one full step as a CUDA graph over ``batch``'s device tensors (they become the static
-        input buffers).  The CSR / pool layouts are built during the warm-up steps (their one-time host
-        syncs are not capturable); afterwards every step is a single graph launch."""
+        """Capture the step as CUDA graphs over ``batch``'s device tensors (they become the static input
+        buffers).  The CSR / pool layouts are built during the warm-up steps (their one-time host syncs are not
+        capturable).  Single GPU: ONE graph (fwd, loss, bwd, Adam).  Data parallel: graph A (fwd, loss, bwd) ->
+        the NCCL all-reduce issued eagerly on the same stream -> graph B (Adam); the collective stays outside
+        the capture so that NCCL's own stream/event management never interferes with it."""
         self.static_batch = batch
         cur = torch.cuda.current_stream()
         side = torch.cuda.Stream()
@@ -103,9 +113,24 @@ class Trainer:
         cur.wait_stream(side)
         torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
-            self.static_loss = self._step_eager(batch)
+        if self.world > 1:
+            self.graph_update = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self.static_loss = self._fwd_bwd(batch)
+            with torch.cuda.graph(self.graph_update, pool=self.graph.pool()):
+                self._update()
+        else:
+            self.graph_update = None
+            with torch.cuda.graph(self.graph):
+                self.static_loss = self._step_eager(batch)
         return self
+
+    def _replay(self):
+        self.graph.replay()
+        if self.graph_update is not None:
+            self.bucket.all_reduce(self.world)
+            self.graph_update.replay()
+        return self.static_loss
 
     def load_batch(self, host_batch):
         """Copy a (pinned) host batch into the captured graph's static device buffers (async H2D)."""
@@ -136,8 +161,7 @@ class Trainer:
         for k, v in self._staging.items():
             getattr(self.static_batch, k).copy_(v, non_blocking=True)
         self._consumed.record()
-        self.graph.replay()
-        return self.static_loss
+        return self._replay()
 
     def step(self, batch=None):
         """forward, loss, backward, (all-reduce), Adam.  Returns the loss as a device scalar (the
@@ -146,6 +170,5 @@ class Trainer:
         if self.graph is not None:
             if batch is not None and batch is not self.static_batch:
                 self.load_batch(batch)
-            self.graph.replay()
-            return self.static_loss
+            return self._replay()
         return self._step_eager(batch)

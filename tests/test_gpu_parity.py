@@ -438,3 +438,30 @@ def test_diffpool_golden(mlg, name):
     for k, p in dp.named_parameters():
         if c["g_params"].get(k) is not None:
             assert_close(p.grad, c["g_params"][k], rtol=2e-4, what=name + ".g_" + k)
+
+
+def test_cuda_graph_step_equals_eager(mlg):
+    """Trainer.capture(): 3 warm-up steps + 2 graph replays must land on the same weights as 5 eager steps."""
+    from multilevel_gnn_b200.train import Trainer
+    c = load_golden("multilevel")["kirc"]
+    results = []
+    for graphed in (False, True):
+        model, args = _build_multilevel(mlg, c)
+        args.lr = 1e-2
+        model.drop1.p = 0.0
+        model.head[2].p = 0.0
+        model.pathway_indexs = model.pathway_indexs.to(DEV)
+        batch = as_batch(c["batch"], DEV)
+        tr = Trainer(model, args, c["weight"].to(DEV))
+        if graphed:
+            tr.capture(batch, warmup=3)
+            for _ in range(2):
+                loss = tr.step()
+        else:
+            for _ in range(5):
+                loss = tr.step(batch)
+        torch.cuda.synchronize()
+        results.append((float(loss), {k: v.detach().clone() for k, v in model.state_dict().items()}))
+    assert abs(results[0][0] - results[1][0]) <= 1e-5 * max(1.0, abs(results[0][0]))
+    for k in results[0][1]:
+        assert_close(results[1][1][k], results[0][1][k], rtol=1e-5, atol=1e-6, what="graph vs eager: " + k)
