@@ -73,6 +73,38 @@ def xty(a, x, want_colsum=False, tag="xty"):
     return out, cs
 
 
+class TallLinear(torch.autograd.Function):
+    """y = x @ W^T + b for a TALL x (rows >> features): forward and dX are cuBLAS fp32, the weight / bias gradient
+    (a [out, rows] x [rows, in] product with a tiny output, which library GEMMs handle poorly) is mlg_xty.
+    Used for GENConv's per-layer edge encoder on [E, H] edge embeddings (torch_vertex.py:76-77)."""
+
+    MIN_ROWS = 65536
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        ctx.save_for_backward(x, weight)
+        ctx.has_bias = bias is not None
+        return torch.nn.functional.linear(x, weight, bias)
+
+    @staticmethod
+    def backward(ctx, g):
+        x, weight = ctx.saved_tensors
+        g = _f32c(g)
+        gx = gw = gb = None
+        if ctx.needs_input_grad[0]:
+            gx = g @ weight
+        if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
+            gw, gb = xty(g, _f32c(x), want_colsum=ctx.has_bias, tag="linear_wgrad")
+        return gx, gw, (gb if ctx.has_bias else None)
+
+
+def tall_linear(x, lin):
+    """Apply an nn.Linear, routing its weight gradient through mlg_xty when x is a tall CUDA matrix."""
+    if x.is_cuda and x.dim() == 2 and x.shape[0] >= TallLinear.MIN_ROWS and x.dtype == torch.float32:
+        return TallLinear.apply(x, lin.weight, lin.bias)
+    return lin(x)
+
+
 class GenAggregate(torch.autograd.Function):
     """GENConv.message + GenMessagePassing.aggregate + MsgNorm + residual
     (models/gcn_lib/sparse/torch_vertex.py:82-89,94-101; torch_message.py:44-85,175-179).

@@ -43,7 +43,7 @@ class GENConv(GenMessagePassing):
         if self.pca_only:
             return self.feature_encoder(x)
         if self.encode_edge and edge_attr is not None:
-            edge_emb = self.edge_encoder(edge_attr)
+            edge_emb = Fn.tall_linear(edge_attr, self.edge_encoder)
         else:
             edge_emb = edge_attr
         if edge_emb is None:   # the reference dereferences edge_emb unconditionally (torch_vertex.py:81)

@@ -77,3 +77,4 @@ def test_diffpool_tensor_core_path_close_to_fp32():
     assert_close(out, ref, rtol=3e-2, atol=3e-2, what="DiffPool bf16 vs fp32")
     assert abs(float(l1) - float(l0)) <= 2e-2 * abs(float(l0)) + 1e-6
     assert abs(float(e1) - float(e0)) <= 2e-2 * abs(float(e0)) + 1e-4
+
