@@ -361,7 +361,7 @@ extern "C" int mlg_gather_sum(const float* src, int64_t ld_src, const int32_t* r
 extern "C" int mlg_edge_values(const float* edge_attr, const int32_t* eid, const int32_t* rowptr,
                                int64_t n_rows, int64_t cap, float fill, float* val, void* stream) {
   MLG_CHECK_ARG(eid && rowptr && val, "mlg_edge_values: null eid/rowptr/val");
-  MLG_CHECK_ARG(edge_attr || cap == 0, "mlg_edge_values: null edge_attr");
+  // edge_attr may be NULL when the edge list is empty (every entry is then an added self loop, eid = -1)
   if (cap == 0) return MLG_OK;
   edge_values_kernel<<<mlg_ceil_div(cap, 256), 256, 0, (cudaStream_t)stream>>>(edge_attr, eid, rowptr,
                                                                              (int)n_rows, cap, fill, val);

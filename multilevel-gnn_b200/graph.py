@@ -50,7 +50,7 @@ def edge_values(edge_attr, csr, fill=1.0):
     ea = edge_attr.reshape(-1).contiguous().float()
     val = torch.empty(max(csr.cap, 1), dtype=torch.float32, device=csr.rowptr.device)
     with torch.cuda.device(val.device):
-        _cabi.check(L.mlg_edge_values(_cabi.fptr(ea), _cabi.iptr(csr.eid), _cabi.iptr(csr.rowptr), csr.n_rows,
+        _cabi.check(L.mlg_edge_values(_cabi.fptr(ea) if ea.numel() else None, _cabi.iptr(csr.eid), _cabi.iptr(csr.rowptr), csr.n_rows,
                                       csr.cap, float(fill), _cabi.fptr(val), _cabi.stream_ptr()), "mlg_edge_values")
     return val
 

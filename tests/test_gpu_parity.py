@@ -465,3 +465,76 @@ def test_cuda_graph_step_equals_eager(mlg):
     assert abs(results[0][0] - results[1][0]) <= 1e-5 * max(1.0, abs(results[0][0]))
     for k in results[0][1]:
         assert_close(results[1][1][k], results[0][1][k], rtol=1e-5, atol=1e-6, what="graph vs eager: " + k)
+
+
+# ------------------------------------------------------------------------------------------------
+# edge cases: empty / ragged / non-replicated inputs
+# ------------------------------------------------------------------------------------------------
+def test_empty_edge_list(mlg):
+    """A graph without edges: GENConv softmax aggregate -> 0 (so h = x), SAGE -> every node only sees its self loop."""
+    n, H = 70, 32
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn(n, H, generator=g)
+    ei = torch.zeros(2, 0, dtype=torch.long)
+    conv = mlg.GENConv(H, H, aggr="softmax", msg_norm=True, encode_edge=False, norm="layer").to(DEV)
+    sd = {k: v.detach().cpu() for k, v in conv.state_dict().items()}
+    y = conv(x.to(DEV), ei.to(DEV), torch.zeros(0, H, device=DEV))
+    assert_close(y, R.genconv_forward(sd, x, ei, torch.zeros(0, H), aggr="softmax", msg_norm_on=True, norm="layer"), what="GENConv E=0")
+    sage = mlg.GraphConv(H, 16, conv="sage", act="leakyrelu", mlp_norm="none").to(DEV)
+    ssd = {k: v.detach().cpu() for k, v in sage.state_dict().items()}
+    ys = sage(x.to(DEV), ei.to(DEV), torch.zeros(0, 1, device=DEV))
+    assert_close(ys, R.sage_forward(ssd, x, ei, torch.zeros(0, 1)), what="SAGE E=0")
+
+
+def test_ragged_batch_is_not_replicated(mlg):
+    """Graphs of different sizes / different edge lists in one batch: the generic CSR path must be taken and agree
+    with the oracle (the replicated fast path only applies to B offset copies of one edge list)."""
+    from multilevel_gnn_b200 import graph
+    g = torch.Generator().manual_seed(8)
+    sizes = [40, 65, 13]
+    eis, off = [], 0
+    for s in sizes:
+        e = torch.stack([torch.randint(0, s, (5 * s,), generator=g), torch.randint(0, s, (5 * s,), generator=g)]) + off
+        eis.append(e)
+        off += s
+    ei = torch.cat(eis, 1)
+    n = sum(sizes)
+    w = torch.rand(ei.shape[1], 1, generator=g)
+    x = torch.randn(n, 64, generator=g)
+    topo = graph.Topology(ei.to(DEV), n, self_loops=True, edge_weight=w.to(DEV), period=40)
+    assert topo.replicas == 1
+    sage = mlg.GraphConv(64, 32, conv="rsage", act="relu", mlp_norm="none").to(DEV)
+    ssd = {k: v.detach().cpu().clone().requires_grad_() for k, v in sage.state_dict().items()}
+    xr = x.clone().requires_grad_()
+    yr = R.sage_forward(ssd, xr, ei, w, relative=True, act="relu")
+    xg = x.to(DEV).requires_grad_()
+    yg = sage(xg, ei.to(DEV), w.to(DEV))
+    assert_close(yg, yr, what="ragged rsage fwd")
+    yr.sum().backward()
+    yg.sum().backward()
+    assert_close(xg.grad, xr.grad, rtol=2e-4, what="ragged rsage g_x")
+
+
+def test_multilevel_single_graph_batch(mlg):
+    """B = 1: no replication to exploit, rank-1 first layer falls back to the materialised embed-scale."""
+    c = load_golden("multilevel")["gbm"]
+    model, args = _build_multilevel(mlg, c)
+    model.eval()
+    n, G = 3 * c["genes"], c["slots"]
+    E = c["batch"]["edge_index"].shape[1] // 3
+    one = dict(x=c["batch"]["x"][:n], edge_index=c["batch"]["edge_index"][:, :E], edge_attr=c["batch"]["edge_attr"][:E],
+               gene_pca_match=c["batch"]["gene_pca_match"][:1], raw_indice=c["batch"]["raw_indice"][:1],
+               age=c["batch"]["age"][:1], y=c["batch"]["y"][:2])
+    pred, feat = model(as_batch(one, DEV))
+    assert_close(pred, c["pred"][:1], what="B=1 pred")
+    assert_close(feat, c["pca_feature"][:1], what="B=1 pca_feature")
+
+
+def test_knn_ragged_sizes_and_full_k(mlg):
+    g = torch.Generator().manual_seed(4)
+    for n, d, k in [(1, 5, 1), (7, 3, 7), (129, 17, 16), (300, 130, 64)]:
+        x = torch.randn(n, d, generator=g)
+        got = mlg.knn_graph_matrix(x.to(DEV), k)
+        _check_knn(x, None, k, got, R.knn_graph_matrix(x, k), "n%d" % n)
+    with pytest.raises(RuntimeError):
+        mlg.knn_graph_matrix(torch.randn(5, 3, device=DEV), 6)          # k > N: torch.topk raises in the reference too
