@@ -178,7 +178,7 @@ int mlg_pool_bwd_x(const float* g_out_cl, const float* vm, const float* w, const
                    int64_t G, int64_t S, int64_t P, int64_t replicas, float* g_x, void* stream);
 int mlg_pool_bwd_w(const float* g_out_cl, const float* x, const float* vm, const int64_t* match,
                    const int64_t* raw_indice, int64_t B, int64_t N, int64_t C, int64_t G, int64_t S,
-                   int64_t P, int wrap_negative, float* g_w, void* stream);
+                   int64_t P, int wrap_negative, int64_t replicas, float* g_w, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Dilated kNN graph (models/gcn_lib/sparse/torch_edge.py:53-104, dense/torch_edge.py:32-58):

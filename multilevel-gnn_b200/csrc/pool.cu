@@ -145,12 +145,14 @@ pool_bwd_x_kernel(const float* __restrict__ g_cl, const float* __restrict__ vm, 
 }
 
 // g_w[g, p] = sum_b sum_c vm[node] * x[node, c] * g_cl[b*S + seg(b,g), p, c]
+// replicated != 0: every graph carries the same match / segment rows (multiloader.py:697), so the slot's node and
+// segment are read once and UB graphs' rows are in flight per step.
 template <int P_>
 __global__ void __launch_bounds__(kThreads)
 pool_bwd_w_kernel(const float* __restrict__ g_cl, const float* __restrict__ x, const float* __restrict__ vm,
                   const long long* __restrict__ match, const long long* __restrict__ raw_indice, int B, int N,
-                  int C, int G, int S, int wrap, float* __restrict__ g_w) {
-  constexpr int UB = 4;  // graphs in flight
+                  int C, int G, int S, int wrap, int replicated, float* __restrict__ g_w) {
+  constexpr int UB = 8;  // graphs in flight
   const int lane = threadIdx.x & 31;
   const long long g = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
   if (g >= G) return;
@@ -158,13 +160,14 @@ pool_bwd_w_kernel(const float* __restrict__ g_cl, const float* __restrict__ x, c
   float acc[P_];
 #pragma unroll
   for (int p = 0; p < P_; ++p) acc[p] = 0.f;
+  const long long m0 = __ldg(match + g), s0 = __ldg(raw_indice + g);
   for (int b0 = 0; b0 < B; b0 += UB) {
     long long node[UB], seg[UB];
     float scale[UB];
 #pragma unroll
     for (int u = 0; u < UB; ++u) {
       const int b = min(b0 + u, B - 1);
-      long long nd = __ldg(match + (size_t)b * G + g);
+      long long nd = replicated ? m0 : __ldg(match + (size_t)b * G + g);
       float sc = (b0 + u < B) ? 1.f : 0.f;
       if (nd < 0) {
         if (wrap) nd = ((long long)b * N + nd + BN) % BN;
@@ -173,7 +176,7 @@ pool_bwd_w_kernel(const float* __restrict__ g_cl, const float* __restrict__ x, c
         nd += (long long)b * N;
       }
       node[u] = nd;
-      seg[u] = (long long)b * S + __ldg(raw_indice + (size_t)b * G + g);
+      seg[u] = (long long)b * S + (replicated ? s0 : __ldg(raw_indice + (size_t)b * G + g));
       scale[u] = sc;
     }
     if (vm) {
@@ -262,14 +265,15 @@ extern "C" int mlg_pool_bwd_x(const float* g_out_cl, const float* vm, const floa
 
 extern "C" int mlg_pool_bwd_w(const float* g_out_cl, const float* x, const float* vm, const int64_t* match,
                               const int64_t* raw_indice, int64_t B, int64_t N, int64_t C, int64_t G,
-                              int64_t S, int64_t P, int wrap_negative, float* g_w, void* stream) {
+                              int64_t S, int64_t P, int wrap_negative, int64_t replicas, float* g_w, void* stream) {
   MLG_CHECK_ARG(g_out_cl && x && match && raw_indice && g_w, "mlg_pool_bwd_w: null pointer");
+  MLG_CHECK_ARG(replicas == 1 || replicas == B, "mlg_pool_bwd_w: replicas must be 1 or B");
   int rc = check_dims("mlg_pool_bwd_w", B, N, C, G, S, P);
   if (rc) return rc;
   const int grid = mlg_ceil_div(G, kThreads / 32);
   MLG_P_SWITCH(P, (pool_bwd_w_kernel<P_><<<grid, kThreads, 0, (cudaStream_t)stream>>>(
                       g_out_cl, x, vm, (const long long*)match, (const long long*)raw_indice, (int)B, (int)N,
-                      (int)C, (int)G, (int)S, wrap_negative, g_w)));
+                      (int)C, (int)G, (int)S, wrap_negative, replicas > 1 ? 1 : 0, g_w)));
   MLG_CHECK_LAUNCH("mlg_pool_bwd_w");
   return MLG_OK;
 }

@@ -401,6 +401,6 @@ class PathwayPool(torch.autograd.Function):
                 with _cabi.span("pool_bwd_w", 4 * C * B * N + 4 * B * C * S * P):
                     _cabi.check(L.mlg_pool_bwd_w(_cabi.fptr(g_cl), _cabi.fptr(xd), _cabi.fptr(vm, True),
                                                  _cabi.lptr(lay.match), _cabi.lptr(lay.raw_indice), B, N, C, G, S, P,
-                                                 int(lay.wrap_negative), _cabi.fptr(gw), _cabi.stream_ptr()),
+                                                 int(lay.wrap_negative), lay.replicas, _cabi.fptr(gw), _cabi.stream_ptr()),
                                 "mlg_pool_bwd_w")
         return gx, gw, None, None
