@@ -17,6 +17,7 @@
 // Tensor-bound: flops = 2*M*N*K per batch entry.
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "../../include/mlg_b200.h"
@@ -197,6 +198,162 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// cta_group::2 variant: a cluster of two CTAs (one SM pair) computes one 256 x 256 output tile.
+// Each CTA stages its own 128 rows of A and HALF of the B tile (128 of the 256 columns), so the per-SM
+// shared-memory traffic (TMA fill + MMA operand reads) drops from ~190 to ~128 B/clk -- the 1-CTA kernel
+// above is limited by exactly that.  The leader CTA (rank 0) issues tcgen05.mma.cta_group::2 (M=256, N=256,
+// K=16); both CTAs' TMA loads complete on the LEADER's `full` barrier (peer-masked mbarrier address),
+// tcgen05.commit multicasts the `empty` / `tmem_full` arrivals to both CTAs, and each CTA drains its own
+// 128 accumulator rows from its own tensor memory.
+// ------------------------------------------------------------------------------------------------
+template <int kStages>
+struct Smem2 {
+  alignas(1024) __nv_bfloat16 a[kStages][BM * BK];
+  alignas(1024) __nv_bfloat16 b[kStages][128 * BK];
+  unsigned long long full[kStages], empty[kStages], tmem_full;
+  unsigned tmem_base;
+};
+
+__device__ __forceinline__ unsigned cluster_ctarank() {
+  unsigned r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// TMA load whose completion is signalled on the mbarrier at the same offset in the pair's LEADER CTA
+__device__ __forceinline__ void tma_load_3d_2sm(void* dst, const CUtensorMap* map, unsigned long long* bar, int c0, int c1,
+                                                int c2) {
+  const unsigned bar_leader = smem_u32(bar) & 0xFEFFFFFFu;   // clear the CTA-rank bit of the shared::cluster address
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(dst)),
+      "l"(map), "r"(bar_leader), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tcgen05_commit_2sm(unsigned long long* bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+      "h"((unsigned short)3)
+      : "memory");
+}
+__device__ __forceinline__ void umma_bf16_2sm(unsigned tmem_d, unsigned long long adesc, unsigned long long bdesc,
+                                              unsigned idesc, unsigned accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+template <int kStages>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                      float* __restrict__ C, long long ldc, long long stride_c, int M, int N, int K, float alpha) {
+  extern __shared__ unsigned char smem_raw[];
+  Smem2<kStages>& S = *reinterpret_cast<Smem2<kStages>*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const unsigned rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int n0 = blockIdx.y * 256, m0 = (blockIdx.x >> 1) * 256 + (int)rank * 128, batch = blockIdx.z;
+  const int k_blocks = (K + BK - 1) / BK;
+  constexpr unsigned kStageBytes = (BM + 128) * BK * 2;   // per CTA
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&S.full[s], 1);
+      mbar_init(&S.empty[s], 1);
+    }
+    mbar_init(&S.tmem_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {  // one warp of EACH CTA of the pair takes part in the paired allocation
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&S.tmem_base)), "n"(256)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  cluster_sync_all();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const unsigned tmem = S.tmem_base;
+
+  if (warp == 0) {
+    if (lane == 0) {  // ===== TMA producer (both CTAs): own 128 rows of A, own half of the B tile =====
+      for (int kb = 0; kb < k_blocks; ++kb) {
+        const int s = kb % kStages;
+        const unsigned ph = (kb / kStages) & 1;
+        mbar_wait(&S.empty[s], ph ^ 1);
+        if (leader) mbar_expect_tx(&S.full[s], 2 * kStageBytes);   // bytes of both CTAs land on the leader's barrier
+        tma_load_3d_2sm(S.a[s], &map_a, &S.full[s], kb * BK, m0, batch);
+        tma_load_3d_2sm(S.b[s], &map_b, &S.full[s], kb * BK, n0 + (int)rank * 128, batch);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && leader) {  // ===== MMA issuer (leader CTA only) =====
+      constexpr unsigned idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((unsigned)(256 >> 3) << 17) | ((unsigned)(256 >> 4) << 24);
+      for (int kb = 0; kb < k_blocks; ++kb) {
+        const int s = kb % kStages;
+        const unsigned ph = (kb / kStages) & 1;
+        mbar_wait(&S.full[s], ph);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const unsigned long long da = make_smem_desc(S.a[s]), db = make_smem_desc(S.b[s]);
+#pragma unroll
+        for (int k = 0; k < BK / UMMA_K; ++k)
+          umma_bf16_2sm(tmem, da + (unsigned long long)(k * 2), db + (unsigned long long)(k * 2), idesc,
+                        (kb | k) != 0 ? 1u : 0u);
+        tcgen05_commit_2sm(&S.empty[s]);   // frees the stage in BOTH CTAs
+      }
+      tcgen05_commit_2sm(&S.tmem_full);    // accumulators complete in BOTH CTAs
+    }
+  } else if (warp >= 4) {  // ===== epilogue: this CTA's 128 rows =====
+    const int q = warp & 3;
+    mbar_wait(&S.tmem_full, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const int row = m0 + q * 32 + lane;
+    float* crow = C + (size_t)batch * stride_c + (size_t)row * ldc;
+#pragma unroll 1
+    for (int c0 = 0; c0 < 256; c0 += 32) {
+      unsigned r[32];
+      const unsigned taddr = tmem + ((unsigned)(q * 32) << 16) + (unsigned)c0;
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+          "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+          "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+          : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+            "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+            "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+            "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+          : "r"(taddr));
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      if (row < M) {
+        const int col = n0 + c0;
+        if (col + 32 <= N && (ldc % 4) == 0 && ((uintptr_t)(crow + col) % 16) == 0) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            st_stream4(crow + col + j, make_float4(alpha * __uint_as_float(r[j]), alpha * __uint_as_float(r[j + 1]),
+                                                   alpha * __uint_as_float(r[j + 2]), alpha * __uint_as_float(r[j + 3])));
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (col + j < N) crow[col + j] = alpha * __uint_as_float(r[j]);
+        }
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  cluster_sync_all();   // the peer may still be reading operands / tensor memory of this CTA's pair allocation
+  if (warp == 2) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(256) : "memory");
+  }
+}
+
 // ---- fp32 -> bf16 cast (optionally transposing) so that any operand becomes K-major ----------------
 __global__ void cast_bf16_kernel(const float* __restrict__ src, long long ld_src, long long rows, long long cols,
                                  __nv_bfloat16* __restrict__ dst, long long ld_dst) {
@@ -280,6 +437,21 @@ int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, float* C, long lon
 
 }  // namespace
 
+template <int kStages>
+int launch_gemm_2cta(const CUtensorMap& ma, const CUtensorMap& mb, float* C, long long ldc, long long stride_c, int M,
+                     int N, int K, int batch, float alpha, cudaStream_t st) {
+  const int smem = (int)sizeof(Smem2<kStages>) + 1024;
+  static bool done = false;
+  if (!done) {
+    MLG_CUDA(cudaFuncSetAttribute(gemm_bf16_2cta_kernel<kStages>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    done = true;
+  }
+  dim3 grid(2 * ((M + 255) / 256), (N + 255) / 256, batch);   // x: (256-row tile, CTA rank); cluster = 2 along x
+  gemm_bf16_2cta_kernel<kStages><<<grid, kThreads, smem, st>>>(ma, mb, C, ldc, stride_c, M, N, K, alpha);
+  MLG_CHECK_LAUNCH("mlg_gemm_bf16(2cta)");
+  return MLG_OK;
+}
+
 extern "C" int mlg_cast_bf16(const float* src, int64_t ld_src, int64_t rows, int64_t cols, int64_t batch,
                              int transpose, void* dst_bf16, int64_t ld_dst, void* stream) {
   MLG_CHECK_ARG(src && dst_bf16 && rows > 0 && cols > 0 && batch > 0, "mlg_cast_bf16: bad arguments");
@@ -308,7 +480,20 @@ extern "C" int mlg_gemm_bf16(const void* A, int64_t lda, int64_t stride_a, const
                     (batch == 1 || (stride_a % 8 == 0 && stride_b % 8 == 0)),
                 "mlg_gemm_bf16: TMA needs 16-byte aligned operands with leading dimensions that are multiples of 8");
   MLG_CHECK_ARG(lda >= K && ldb >= K && ldc >= N, "mlg_gemm_bf16: leading dimension too small");
+  cudaStream_t st = (cudaStream_t)stream;
   CUtensorMap ma, mb;
+  // SM-pair kernel when the grid of 256 x 256 tiles fills the machine (MLG_GEMM_1CTA=1 forces the single-CTA kernel)
+  {
+    static const bool force_1cta = getenv("MLG_GEMM_1CTA") != nullptr;
+    const long long tiles = ((M + 255) / 256) * ((N + 255) / 256) * batch;
+    if (!force_1cta && M >= 256 && N >= 256 && tiles >= 64) {
+      int rc2 = make_map(&ma, A, K, M, lda, batch, stride_a, BM);
+      if (rc2) return rc2;
+      rc2 = make_map(&mb, B, K, N, ldb, batch, stride_b, 128);
+      if (rc2) return rc2;
+      return launch_gemm_2cta<6>(ma, mb, C, ldc, stride_c, (int)M, (int)N, (int)K, (int)batch, alpha, st);
+    }
+  }
   // 256-wide tiles halve the A re-reads, but only pay when they still fill the 148 SMs
   const long long tiles256 = ((M + BM - 1) / BM) * ((N + 255) / 256) * batch;
   const bool wide = N > 128 && tiles256 >= 64;   // measured: 80 wide tiles (743 TF) beat 160 narrow ones (575 TF)
@@ -316,7 +501,6 @@ extern "C" int mlg_gemm_bf16(const void* A, int64_t lda, int64_t stride_a, const
   if (rc) return rc;
   rc = make_map(&mb, B, K, N, ldb, batch, stride_b, wide ? 256 : 128);
   if (rc) return rc;
-  cudaStream_t st = (cudaStream_t)stream;
   if (wide) return launch_gemm<256, 4>(ma, mb, C, ldc, stride_c, (int)M, (int)N, (int)K, (int)batch, alpha, st);
   return launch_gemm<128, 6>(ma, mb, C, ldc, stride_c, (int)M, (int)N, (int)K, (int)batch, alpha, st);
 }

@@ -101,7 +101,7 @@ def gemm(a):
     from multilevel_gnn_b200 import _cabi
     L = _cabi.lib()
     for (M, N, K, what) in [(2500, 10000, 10000, "S^T.A"), (2500, 1024, 10000, "S^T.X"), (2500, 2500, 10000, "(S^T.A).S"),
-                            (10000, 1024, 10000, "A.X"), (10000, 10000, 2500, "S.S^T"), (8192, 8192, 8192, "square")]:
+                            (10000, 1024, 10000, "A.X"), (10000, 10000, 2504, "S.S^T (K padded to 8)"), (8192, 8192, 8192, "square")]:
         A = torch.randn(M, K, device=DEV).bfloat16()
         B = torch.randn(N, K, device=DEV).bfloat16()
         C = torch.empty(M, N, device=DEV)
