@@ -206,6 +206,19 @@ int mlg_gemm_bf16(const void* A, int64_t lda, int64_t stride_a, const void* B, i
                   float* C, int64_t ldc, int64_t stride_c, int64_t M, int64_t N, int64_t K, int64_t batch,
                   float alpha, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * fp32-accurate tall GEMM on the tensor cores (3xTF32 split, fp32 accumulation in tensor memory):
+ *     C[M,N] = act( A[M,K] . B[N,K]^T + bias ),  act: 0 none, 1 LeakyReLU(slope) (slope 0 = ReLU)
+ * for the Linear layers around the aggregations (SAGEConv.update MLP + lin_r, torch_vertex.py:281-291; GENConv
+ * edge encoder, torch_vertex.py:76-77): M = nodes / edges (huge), 32 <= K <= 256 (K % 32 == 0), 16 <= N <= 256
+ * (N % 16 == 0).  B_hi / B_lo [N,K] are the weight split by mlg_split_tf32 (hi = top 19 bits, lo = w - hi).
+ * Relative error ~2^-20 (passes the fp32 rtol-1e-4 parity bar; plain TF32 would not).
+ */
+int mlg_split_tf32(const float* w, int64_t n, float* hi, float* lo, void* stream);
+int mlg_gemm_tf32x3_supported(int64_t M, int64_t N, int64_t K);
+int mlg_gemm_tf32x3(const float* A, int64_t lda, const float* B_hi, const float* B_lo, const float* bias, float* C,
+                    int64_t ldc, int64_t M, int64_t N, int64_t K, int act, float slope, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

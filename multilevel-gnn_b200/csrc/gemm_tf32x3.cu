@@ -1,0 +1,350 @@
+// fp32-accurate tall GEMM on the tcgen05 tensor cores (sm_100a), 3xTF32 error-compensated:
+//
+//   C[M,N] = act( A[M,K] . B[N,K]^T + bias )        A fp32 row-major, M huge (nodes / edges), K <= 256, N <= 256
+//
+// The Linear layers around the aggregations (SAGEConv.update's MLP + lin_r folded into one weight,
+// models/gcn_lib/sparse/torch_vertex.py:281-291; GENConv's per-layer edge encoder, torch_vertex.py:76-77) are
+// [rows x K] x [K x N] products with rows ~ 5e5..2e6 and K, N <= 128.  In fp32 on the CUDA cores they are
+// FMA-bound (8 GFLOP -> 160-200 us at the gbm shape); plain TF32 would break the rtol-1e-4 parity bar.  Here every
+// fp32 operand is split into hi = top 19 bits and lo = x - hi (exact), and the tensor core computes
+//   hi_A.hi_B + hi_A.lo_B + lo_A.hi_B          (fp32 accumulation in tensor memory, error ~2^-21 relative)
+// so the product becomes HBM-bound.  B (the small weight) is split on the host side once and stays resident in
+// shared memory; A tiles arrive by TMA (128B-swizzled rows of 32 fp32) and a splitter warpgroup rewrites each tile
+// in place as `hi` and writes `lo` to a twin tile (layout-agnostic: same byte offsets), then hands the stage to the
+// single MMA-issuing thread through an mbarrier (with a generic->async proxy fence).  Persistent CTAs (one per SM)
+// walk 128-row tiles; the accumulator is double-buffered in tensor memory so the epilogue (bias + LeakyReLU, 128-bit
+// stores) of tile i overlaps the main loop of tile i+1.
+#include <cuda.h>
+
+#include "common.cuh"
+#include "../../include/mlg_b200.h"
+
+namespace {
+
+constexpr int BM = 128, BKF = 32, UK = 8;          // tile rows, fp32 per 128 B swizzle row, K per tf32 MMA
+constexpr int kThreads = 384;                      // warps: 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4-7 epilogue, 8-11 splitter
+constexpr int kTileBytes = BM * BKF * 4;           // 16 KB
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "MLGX_WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra MLGX_DONE_%=;\n"
+      "bra MLGX_WAIT_%=;\n"
+      "MLGX_DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, unsigned long long* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tcgen05_commit(unsigned long long* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void umma_tf32(unsigned tmem_d, unsigned long long adesc, unsigned long long bdesc,
+                                          unsigned idesc, unsigned accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// K-major tile, 128-byte swizzle, 8-row groups 1024 B apart
+__device__ __forceinline__ unsigned long long make_smem_desc(unsigned addr) {
+  unsigned long long d = 0;
+  d |= (unsigned long long)((addr & 0x3FFFF) >> 4);
+  d |= (unsigned long long)1 << 16;
+  d |= (unsigned long long)(1024 >> 4) << 32;
+  d |= (unsigned long long)1 << 46;
+  d |= (unsigned long long)2 << 61;
+  return d;
+}
+// kind::tf32: D = f32 (1 << 4), A = B = tf32 (format code 2), K-major, M = 128, N
+__host__ __device__ constexpr unsigned make_idesc_tf32(int n) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(n >> 3) << 17) | ((unsigned)(BM >> 4) << 24);
+}
+
+struct Ctl {   // barriers and bookkeeping, placed after the tiles
+  unsigned long long full_raw[4], full_split[4], empty[4], b_full, tmem_full[2], tmem_empty[2];
+  unsigned tmem_base;
+};
+
+// shared memory: [B_hi: kb][N x 128 B] [B_lo: kb][...] [stages][A_hi 16 KB | A_lo 16 KB] Ctl
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_bh,
+                   const __grid_constant__ CUtensorMap map_bl, const float* __restrict__ bias, float* __restrict__ C,
+                   long long ldc, int M, int N, int K, int n_stages, int tmem_cols, int act, float slope) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* base = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const int k_blocks = K / BKF;
+  const unsigned b_tile = (unsigned)N * 128u;                       // bytes of one [N x 32 fp32] tile
+  unsigned char* b_hi = base;
+  unsigned char* b_lo = base + (size_t)k_blocks * b_tile;
+  unsigned char* a_st = base + (size_t)2 * k_blocks * b_tile;       // stage s: a_st + s * 2 * kTileBytes
+  Ctl& S = *reinterpret_cast<Ctl*>(a_st + (size_t)n_stages * 2 * kTileBytes);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_tiles = (M + BM - 1) / BM;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < 4; ++s) {
+      mbar_init(&S.full_raw[s], 1);
+      mbar_init(&S.full_split[s], 128);
+      mbar_init(&S.empty[s], 1);
+    }
+    mbar_init(&S.b_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&S.tmem_full[i], 1);
+      mbar_init(&S.tmem_empty[i], 128);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&S.tmem_base)),
+                 "r"(tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const unsigned tmem = S.tmem_base;
+
+  if (warp == 0) {
+    if (lane == 0) {  // ===== TMA producer: resident weight tiles once, then the A tiles of this CTA's row tiles =====
+      mbar_expect_tx(&S.b_full, 2u * (unsigned)k_blocks * b_tile);
+      for (int kb = 0; kb < k_blocks; ++kb) {
+        tma_load_2d(b_hi + (size_t)kb * b_tile, &map_bh, &S.b_full, kb * BKF, 0);
+        tma_load_2d(b_lo + (size_t)kb * b_tile, &map_bl, &S.b_full, kb * BKF, 0);
+      }
+      int it = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        for (int kb = 0; kb < k_blocks; ++kb, ++it) {
+          const int s = it % n_stages;
+          const unsigned ph = (it / n_stages) & 1;
+          mbar_wait(&S.empty[s], ph ^ 1);
+          mbar_expect_tx(&S.full_raw[s], kTileBytes);
+          tma_load_2d(a_st + (size_t)s * 2 * kTileBytes, &map_a, &S.full_raw[s], kb * BKF, tile * BM);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {  // ===== MMA issuer =====
+      const unsigned idesc = make_idesc_tf32(N);
+      mbar_wait(&S.b_full, 0);
+      int it = 0, tl = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tl) {
+        const int buf = tl & 1;
+        mbar_wait(&S.tmem_empty[buf], ((tl >> 1) & 1) ^ 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const unsigned d_tmem = tmem + (unsigned)(buf * N);
+        for (int kb = 0; kb < k_blocks; ++kb, ++it) {
+          const int s = it % n_stages;
+          const unsigned ph = (it / n_stages) & 1;
+          mbar_wait(&S.full_split[s], ph);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const unsigned a_hi = smem_u32(a_st + (size_t)s * 2 * kTileBytes), a_lo = a_hi + kTileBytes;
+          const unsigned long long dah = make_smem_desc(a_hi), dal = make_smem_desc(a_lo);
+          const unsigned long long dbh = make_smem_desc(smem_u32(b_hi + (size_t)kb * b_tile));
+          const unsigned long long dbl = make_smem_desc(smem_u32(b_lo + (size_t)kb * b_tile));
+#pragma unroll
+          for (int k = 0; k < BKF / UK; ++k) {
+            const unsigned long long o = (unsigned long long)(k * 2);   // 8 fp32 = 32 B along K: +2 (16-byte units)
+            umma_tf32(d_tmem, dal + o, dbh + o, idesc, (kb | k) != 0 ? 1u : 0u);   // small terms first
+            umma_tf32(d_tmem, dah + o, dbl + o, idesc, 1u);
+            umma_tf32(d_tmem, dah + o, dbh + o, idesc, 1u);
+          }
+          tcgen05_commit(&S.empty[s]);
+        }
+        tcgen05_commit(&S.tmem_full[buf]);
+      }
+    }
+  } else if (warp >= 4 && warp < 8) {  // ===== epilogue =====
+    const int q = warp & 3;
+    int tl = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tl) {
+      const int buf = tl & 1;
+      mbar_wait(&S.tmem_full[buf], (tl >> 1) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const int row = tile * BM + q * 32 + lane;
+      float* crow = C + (size_t)row * ldc;
+      for (int c0 = 0; c0 < N; c0 += 16) {
+        unsigned r[16];
+        const unsigned taddr = tmem + ((unsigned)(q * 32) << 16) + (unsigned)(buf * N + c0);
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+              "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+            : "r"(taddr));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (row < M) {
+          float v[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            float t = __uint_as_float(r[j]) + (bias ? __ldg(bias + c0 + j) : 0.f);
+            if (act) t = t > 0.f ? t : t * slope;
+            v[j] = t;
+          }
+#pragma unroll
+          for (int j = 0; j < 16; j += 4) st4(crow + c0 + j, make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      mbar_arrive(&S.tmem_empty[buf]);
+    }
+  } else if (warp >= 8) {  // ===== splitter: raw fp32 tile -> hi (in place) + lo (twin tile) =====
+    const int t = threadIdx.x - 256;   // 0..127
+    int it = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      for (int kb = 0; kb < k_blocks; ++kb, ++it) {
+        const int s = it % n_stages;
+        const unsigned ph = (it / n_stages) & 1;
+        mbar_wait(&S.full_raw[s], ph);
+        float4* hi = reinterpret_cast<float4*>(a_st + (size_t)s * 2 * kTileBytes);
+        float4* lo = reinterpret_cast<float4*>(a_st + (size_t)s * 2 * kTileBytes + kTileBytes);
+#pragma unroll
+        for (int i = 0; i < kTileBytes / 16 / 128; ++i) {
+          const int idx = t + i * 128;
+          const float4 x = hi[idx];
+          float4 h, l;
+          h.x = __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u);
+          h.y = __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u);
+          h.z = __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u);
+          h.w = __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u);
+          l.x = x.x - h.x; l.y = x.y - h.y; l.z = x.z - h.z; l.w = x.w - h.w;
+          hi[idx] = h;
+          lo[idx] = l;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to tcgen05.mma
+        mbar_arrive(&S.full_split[s]);
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 2) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(tmem_cols) : "memory");
+  }
+}
+
+__global__ void split_tf32_kernel(const float* __restrict__ w, long long n, float* __restrict__ hi, float* __restrict__ lo) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float x = w[i];
+  const float h = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
+  hi[i] = h;
+  lo[i] = x - h;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+// 2-D map over a K-major fp32 matrix [rows, K] (leading dimension ld): box (32, box_rows), 128 B swizzle
+int make_map_f32(CUtensorMap* map, const void* basep, long long K, long long rows, long long ld, int box_rows) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) {
+    mlg_set_error("mlg_gemm_tf32x3: cuTensorMapEncodeTiled entry point not available");
+    return MLG_ERR_CUDA;
+  }
+  cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2] = {BKF, (cuuint32_t)box_rows};
+  cuuint32_t elem[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(basep), dims, strides, box, elem,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    mlg_set_error("mlg_gemm_tf32x3: cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return MLG_ERR_CUDA;
+  }
+  return MLG_OK;
+}
+
+}  // namespace
+
+extern "C" int mlg_split_tf32(const float* w, int64_t n, float* hi, float* lo, void* stream) {
+  MLG_CHECK_ARG(w && hi && lo && n >= 0, "mlg_split_tf32: bad arguments");
+  if (n == 0) return MLG_OK;
+  split_tf32_kernel<<<mlg_ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(w, n, hi, lo);
+  MLG_CHECK_LAUNCH("mlg_split_tf32");
+  return MLG_OK;
+}
+
+extern "C" int mlg_gemm_tf32x3_supported(int64_t M, int64_t N, int64_t K) {
+  if (M < 1 || N < 16 || N > 256 || N % 16 || K < 32 || K > 256 || K % 32) return 0;
+  const long long bbytes = 2ll * (K / 32) * N * 128;
+  return (220 * 1024 - bbytes) / (2 * kTileBytes) >= 2 ? 1 : 0;
+}
+
+extern "C" int mlg_gemm_tf32x3(const float* A, int64_t lda, const float* B_hi, const float* B_lo, const float* bias,
+                               float* C, int64_t ldc, int64_t M, int64_t N, int64_t K, int act, float slope,
+                               void* stream) {
+  MLG_CHECK_ARG(A && B_hi && B_lo && C, "mlg_gemm_tf32x3: null pointer");
+  MLG_CHECK_ARG(mlg_gemm_tf32x3_supported(M, N, K), "mlg_gemm_tf32x3: unsupported shape M=%lld N=%lld K=%lld "
+                "(need N%%16==0, 16<=N<=256, K%%32==0, K<=256 and the split weights must fit in shared memory)",
+                (long long)M, (long long)N, (long long)K);
+  MLG_CHECK_ARG(lda % 4 == 0 && lda >= K && ldc % 4 == 0 && ldc >= N && (uintptr_t)A % 16 == 0 && (uintptr_t)C % 16 == 0 &&
+                    (uintptr_t)B_hi % 16 == 0 && (uintptr_t)B_lo % 16 == 0,
+                "mlg_gemm_tf32x3: operands must be 16-byte aligned with leading dimensions that are multiples of 4");
+  MLG_CHECK_ARG(M < (1ll << 31), "mlg_gemm_tf32x3: M too large");
+  CUtensorMap ma, mbh, mbl;
+  int rc = make_map_f32(&ma, A, K, M, lda, BM);
+  if (rc) return rc;
+  rc = make_map_f32(&mbh, B_hi, K, N, K, (int)N);
+  if (rc) return rc;
+  rc = make_map_f32(&mbl, B_lo, K, N, K, (int)N);
+  if (rc) return rc;
+  const long long bbytes = 2ll * (K / 32) * N * 128;
+  int stages = (int)((220 * 1024 - bbytes) / (2 * kTileBytes));
+  if (stages > 4) stages = 4;
+  int tmem_cols = 32;
+  while (tmem_cols < 2 * N) tmem_cols *= 2;
+  const int smem = (int)(bbytes + (long long)stages * 2 * kTileBytes + sizeof(Ctl) + 1024);
+  static int attr_smem = 0;
+  if (smem > attr_smem) {
+    MLG_CUDA(cudaFuncSetAttribute(gemm_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_smem = smem;
+  }
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int n_tiles = (int)((M + BM - 1) / BM);
+  const int grid = n_tiles < sms ? n_tiles : sms;
+  gemm_tf32x3_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(ma, mbh, mbl, bias, C, ldc, (int)M, (int)N, (int)K,
+                                                                    stages, tmem_cols, act, slope);
+  MLG_CHECK_LAUNCH("mlg_gemm_tf32x3");
+  return MLG_OK;
+}

@@ -73,6 +73,36 @@ def xty(a, x, want_colsum=False, tag="xty"):
     return out, cs
 
 
+USE_TF32X3 = True      # tall Linears on the tensor cores with the 3xTF32 split (fp32-accurate); False = cuBLAS fp32
+
+
+def tall_matmul(a, w, bias=None, act=0, slope=0.0, tag="gemm_tf32x3"):
+    """act(a @ w^T + bias) for a tall fp32 matrix a [M, K] and a small weight w [N, K]: mlg_gemm_tf32x3 when the shape
+    is supported, else cuBLAS fp32 (+ mlg_bias_act).  act: 0 none, 1 LeakyReLU(slope)."""
+    L = _cabi.lib()
+    M, K = a.shape
+    N = w.shape[0]
+    if (USE_TF32X3 and a.is_cuda and a.stride(1) == 1 and a.stride(0) % 4 == 0 and a.data_ptr() % 16 == 0
+            and L.mlg_gemm_tf32x3_supported(M, N, K)):
+        wd = _f32c(w)
+        hi, lo = torch.empty_like(wd), torch.empty_like(wd)
+        out = torch.empty(M, N, dtype=torch.float32, device=a.device)
+        with torch.cuda.device(a.device):
+            _cabi.check(L.mlg_split_tf32(_cabi.fptr(wd), wd.numel(), _cabi.fptr(hi), _cabi.fptr(lo), _cabi.stream_ptr()),
+                        "mlg_split_tf32")
+            with _cabi.span(tag, 4 * M * (K + N)):
+                _cabi.check(L.mlg_gemm_tf32x3(_vptr(a), a.stride(0), _cabi.fptr(hi), _cabi.fptr(lo),
+                                              None if bias is None else _cabi.fptr(_f32c(bias)), _cabi.fptr(out), N, M, N, K,
+                                              int(act), float(slope), _cabi.stream_ptr()), "mlg_gemm_tf32x3")
+        return out
+    out = a @ w.t()
+    if bias is not None or act:
+        with torch.cuda.device(out.device):
+            _cabi.check(L.mlg_bias_act(_cabi.fptr(out), None if bias is None else _cabi.fptr(_f32c(bias)), M, N,
+                                       float(slope) if act else 1.0, _cabi.stream_ptr()), "mlg_bias_act")
+    return out
+
+
 class TallLinear(torch.autograd.Function):
     """y = x @ W^T + b for a TALL x (rows >> features): forward and dX are cuBLAS fp32, the weight / bias gradient
     (a [out, rows] x [rows, in] product with a tiny output, which library GEMMs handle poorly) is mlg_xty.
@@ -84,7 +114,7 @@ class TallLinear(torch.autograd.Function):
     def forward(ctx, x, weight, bias):
         ctx.save_for_backward(x, weight)
         ctx.has_bias = bias is not None
-        return torch.nn.functional.linear(x, weight, bias)
+        return tall_matmul(_f32c(x.detach()), weight.detach(), None if bias is None else bias.detach(), tag="linear_fwd")
 
     @staticmethod
     def backward(ctx, g):
@@ -92,7 +122,7 @@ class TallLinear(torch.autograd.Function):
         g = _f32c(g)
         gx = gw = gb = None
         if ctx.needs_input_grad[0]:
-            gx = g @ weight
+            gx = tall_matmul(g, weight.t().contiguous(), tag="linear_dgrad")
         if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
             gw, gb = xty(g, _f32c(x), want_colsum=ctx.has_bias, tag="linear_wgrad")
         return gx, gw, (gb if ctx.has_bias else None)
@@ -261,11 +291,9 @@ class SageLayer(torch.autograd.Function):
         gather_sum(xd, csr.rowptr, csr.col, topo.n_single, val=topo.fwd_val, pre=xs_d, post_mode=1, relative=relative,
                    out=xcat[:, cin:], self_out=xcat[:, :cin], replicas=topo.replicas, order=topo.fwd_order,
                    rank1=rank1, tag="sage_aggr_fwd")
-        y = xcat @ wcat.t()                                           # cuBLAS fp32, no epilogue
-        L = _cabi.lib()
-        with torch.cuda.device(y.device), _cabi.span("sage_bias_act", 8 * y.numel()):
-            _cabi.check(L.mlg_bias_act(_cabi.fptr(y), None if nn_b is None else _cabi.fptr(_f32c(nn_b.detach())),
-                                       y.shape[0], y.shape[1], float(slope), _cabi.stream_ptr()), "mlg_bias_act")
+        # update GEMM + bias + (Leaky)ReLU: 3xTF32 tensor-core kernel with fused epilogue (cuBLAS fp32 + mlg_bias_act
+        # for shapes it does not cover)
+        y = tall_matmul(xcat, wcat, None if nn_b is None else nn_b.detach(), act=1, slope=slope, tag="sage_update_gemm")
         ctx.save_for_backward(xcat, y, wcat, w_r, w2, xs_d if rank1 else None)
         ctx.topo, ctx.relative, ctx.slope, ctx.cin, ctx.has_bias = topo, bool(relative), float(slope), cin, nn_b is not None
         ctx.rank1 = rank1
@@ -286,7 +314,7 @@ class SageLayer(torch.autograd.Function):
             g_wnn = torch.cat([g_wcat[:, :cin], g_weff @ w_r.t()], dim=1)
             g_wr = w2.t() @ g_weff
         if needs[0]:
-            gxcat = gz @ wcat                                                              # [N, 2cin]
+            gxcat = tall_matmul(gz, wcat.t().contiguous(), tag="sage_dgrad_gemm")            # [N, 2cin]
             bw = topo.bwd
             gx = gather_sum(gxcat[:, cin:], bw.rowptr, bw.col, topo.n_single, val=topo.bwd_val, pre=topo.inv_cnt,
                             addend=gxcat[:, :cin], replicas=topo.replicas, order=topo.bwd_order, tag="sage_aggr_bwd")

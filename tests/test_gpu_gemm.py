@@ -78,3 +78,28 @@ def test_diffpool_tensor_core_path_close_to_fp32():
     assert abs(float(l1) - float(l0)) <= 2e-2 * abs(float(l0)) + 1e-6
     assert abs(float(e1) - float(e0)) <= 2e-2 * abs(float(e0)) + 1e-4
 
+
+
+@pytest.mark.parametrize("shape", [(1000, 64, 128), (128, 32, 64), (5000, 128, 64), (12345, 64, 128), (777, 128, 128),
+                                   (300, 16, 32), (70000, 32, 128), (4096, 256, 32)])
+def test_gemm_tf32x3_is_fp32_accurate(shape):
+    """3xTF32 split GEMM (mlg_gemm_tf32x3) vs an fp64 product: relative error far below the rtol-1e-4 parity bar;
+    fused bias + LeakyReLU epilogue."""
+    from multilevel_gnn_b200 import functional as Fn
+    M, N, K = shape
+    g = torch.Generator().manual_seed(M + N)
+    a = (torch.randn(M, K, generator=g) * torch.rand(M, 1, generator=g) * 3).to(DEV)
+    w = torch.randn(N, K, generator=g).to(DEV)
+    b = torch.randn(N, generator=g).to(DEV)
+    assert Fn._cabi.lib().mlg_gemm_tf32x3_supported(M, N, K)
+    out = Fn.tall_matmul(a, w, b, act=1, slope=0.2)
+    ref = torch.nn.functional.leaky_relu(a.double() @ w.double().t() + b.double(), 0.2).float()
+    assert_close(out, ref, rtol=2e-5, atol=2e-6, what="tf32x3 %s" % (shape,))
+    out2 = Fn.tall_matmul(a, w)
+    scale = (a.double().abs() @ w.double().abs().t()).float()       # error bound relative to sum |a||w|
+    err = (out2 - (a.double() @ w.double().t()).float()).abs()
+    assert float((err / scale).max()) < 3e-6
+    # strided A (left half of a wider buffer)
+    big = torch.randn(M, 2 * K, generator=g).to(DEV)
+    out3 = Fn.tall_matmul(big[:, :K], w)
+    assert_close(out3, (big[:, :K].double() @ w.double().t()).float(), rtol=2e-5, atol=2e-5, what="strided A")
