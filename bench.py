@@ -290,7 +290,7 @@ def run_b200(a):
     value = B * world * a.steps / (ms_total / 1e3)
     # the kernels of the step, by what bounds them
     bound_of = {"sage_aggr_fwd": "hbm", "sage_aggr_bwd": "hbm", "pool_fwd": "hbm", "pool_bwd_x": "hbm",
-                "pool_bwd_w": "hbm", "sage_bias_act": "hbm", "embed_scale_bwd": "hbm", "sage_wgrad": "fp32-fma"}
+                "pool_bwd_w": "hbm", "pool_bwd": "hbm", "sage_update_gemm": "hbm (tensor 3xTF32)", "sage_dgrad_gemm": "hbm (tensor 3xTF32)", "sage_bias_act": "hbm", "embed_scale_bwd": "hbm", "sage_wgrad": "fp32-fma"}
     # sage_aggr_fwd / sage_aggr_bwd are the same kernel (gather_sum_rep_kernel) on the CSR / its transpose
     merged = {}
     for tag, d in ksum.items():

@@ -179,6 +179,12 @@ int mlg_pool_bwd_x(const float* g_out_cl, const float* vm, const float* w, const
 int mlg_pool_bwd_w(const float* g_out_cl, const float* x, const float* vm, const int64_t* match,
                    const int64_t* raw_indice, int64_t B, int64_t N, int64_t C, int64_t G, int64_t S,
                    int64_t P, int wrap_negative, int64_t replicas, float* g_w, void* stream);
+/* Both gradients in ONE pass over the node-side CSR (x streamed in node order, every g_out_cl row loaded once):
+ * g_x as above; per-graph partial weight gradients go to workspace [B*G*P] floats and are reduced over the
+ * graphs in a fixed order into g_w.  C <= 128.  Node-side structures as for mlg_pool_bwd_x. */
+int mlg_pool_bwd(const float* g_out_cl, const float* x, const float* vm, const float* w, const int32_t* node_rowptr,
+                 const int32_t* node_slot, const int32_t* seg_of_slot, int64_t B, int64_t N, int64_t C, int64_t G,
+                 int64_t S, int64_t P, int64_t replicas, float* g_x, float* g_w, float* workspace, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Dilated kNN graph (models/gcn_lib/sparse/torch_edge.py:53-104, dense/torch_edge.py:32-58):

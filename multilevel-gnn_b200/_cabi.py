@@ -41,6 +41,8 @@ _SIGNATURES = {
                                 _c_i64, _c_i64, _c_i64, _c_vp, _c_vp]),
     "mlg_pool_bwd_w": (_c_int, [_c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_i64, _c_i64, _c_i64, _c_i64, _c_i64,
                                 _c_i64, _c_int, _c_i64, _c_vp, _c_vp]),
+    "mlg_pool_bwd": (_c_int, [_c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_i64, _c_i64, _c_i64, _c_i64, _c_i64, _c_i64,
+                              _c_i64, _c_vp, _c_vp, _c_vp, _c_vp]),
     "mlg_cast_bf16": (_c_int, [_c_vp, _c_i64, _c_i64, _c_i64, _c_i64, _c_int, _c_vp, _c_i64, _c_vp]),
     "mlg_gemm_bf16": (_c_int, [_c_vp, _c_i64, _c_i64, _c_vp, _c_i64, _c_i64, _c_vp, _c_i64, _c_i64, _c_i64, _c_i64,
                                _c_i64, _c_i64, _c_f32, _c_vp]),
@@ -86,7 +88,7 @@ def last_error():
 
 
 # kernels launched per C call (own kernels only; CUB's sort passes inside mlg_csr_build are not counted)
-_LAUNCHES_PER_CALL = {"mlg_csr_build": 2, "mlg_knn_graph": 2, "mlg_xty": 2}
+_LAUNCHES_PER_CALL = {"mlg_csr_build": 2, "mlg_knn_graph": 2, "mlg_xty": 2, "mlg_pool_bwd": 2}
 LAUNCH_COUNT = 0
 TIMER = None        # a KernelTimer while bench.py measures per-kernel device time
 

@@ -207,6 +207,106 @@ pool_bwd_w_kernel(const float* __restrict__ g_cl, const float* __restrict__ x, c
   }
 }
 
+// Fused backward: ONE pass over the node-side CSR produces g_x AND per-graph partial weight gradients
+//   g_x[b*n + row, c]      = vm * sum_{slot -> row} sum_p w[g,p] * g_cl[b, seg, p, c]
+//   part[b, g, p]          = sum_c vm * x[b*n + row, c] * g_cl[b, seg, p, c]          (g = slot's gene)
+// x is streamed in node order (coalesced) instead of being gathered per gene slot, and the g_cl rows are loaded
+// once for both gradients; g_w = sum_b part[b] is a second, fixed-order pass (deterministic, no atomics).
+template <int P_, int CCH>
+__global__ void __launch_bounds__(kThreads)
+pool_bwd_fused_kernel(const float* __restrict__ g_cl, const float* __restrict__ x, const float* __restrict__ vm,
+                      const float* __restrict__ w, const int* __restrict__ rowptr, const int* __restrict__ slots,
+                      const int* __restrict__ seg_of_slot, int n_rows, int replicas, int S, int C, int G,
+                      float* __restrict__ g_x, float* __restrict__ part) {
+  constexpr int RB = 4;
+  const int lane = threadIdx.x & 31;
+  const long long wid = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const int chunks = (replicas + RB - 1) / RB;
+  const long long row = wid / chunks;
+  const int b0 = (int)(wid % chunks) * RB;
+  if (row >= n_rows) return;
+  const int beg = __ldg(rowptr + row), end = __ldg(rowptr + row + 1);
+  const size_t rep_g = (size_t)S * P_ * C;
+  float accx[RB][CCH], xr[RB][CCH], scale[RB];
+#pragma unroll
+  for (int r = 0; r < RB; ++r) {
+    const int b = min(b0 + r, replicas - 1);
+    const size_t orow = (size_t)b * n_rows + row;
+    scale[r] = vm ? __ldg(vm + orow) : 1.f;
+#pragma unroll
+    for (int cc = 0; cc < CCH; ++cc) {
+      const int c = cc * 32 + lane;
+      accx[r][cc] = 0.f;
+      xr[r][cc] = (c < C && beg < end) ? __ldg(x + orow * C + c) * scale[r] : 0.f;
+    }
+  }
+  for (int base = beg; base < end; base += 32) {
+    const int q = min(base + lane, end - 1);
+    const int slot = __ldg(slots + q);
+    const int g = slot % G;
+    const int seg = __ldg(seg_of_slot + slot);
+    float wl[P_];
+#pragma unroll
+    for (int p = 0; p < P_; ++p) wl[p] = __ldg(w + (size_t)g * P_ + p);
+    const int cnt = min(32, end - base);
+    for (int j = 0; j < cnt; ++j) {
+      const int sj = __shfl_sync(0xffffffffu, seg, j);
+      const int slotj = __shfl_sync(0xffffffffu, slot, j);
+      float wj[P_];
+#pragma unroll
+      for (int p = 0; p < P_; ++p) wj[p] = __shfl_sync(0xffffffffu, wl[p], j);
+      float gv[RB][P_][CCH];
+#pragma unroll
+      for (int r = 0; r < RB; ++r) {
+        const int b = min(b0 + r, replicas - 1);
+        const float* gp = g_cl + (size_t)b * rep_g + (size_t)sj * P_ * C + lane;
+#pragma unroll
+        for (int p = 0; p < P_; ++p)
+#pragma unroll
+          for (int cc = 0; cc < CCH; ++cc) gv[r][p][cc] = (cc * 32 + lane < C) ? __ldg(gp + (size_t)p * C + cc * 32) : 0.f;
+      }
+#pragma unroll
+      for (int r = 0; r < RB; ++r) {
+#pragma unroll
+        for (int p = 0; p < P_; ++p) {
+          float dot = 0.f;
+#pragma unroll
+          for (int cc = 0; cc < CCH; ++cc) {
+            accx[r][cc] = fmaf(gv[r][p][cc], wj[p], accx[r][cc]);
+            dot = fmaf(xr[r][cc], gv[r][p][cc], dot);
+          }
+          dot = warp_sum(dot);
+          const int b = b0 + r;
+          if (lane == 0 && b < replicas) {
+            // replicated layout: slot ids are per graph (part row = b); general layout: slot ids already span b*G + g
+            const size_t prow = (replicas > 1) ? (size_t)b * G + slotj : (size_t)slotj;
+            part[prow * P_ + p] = dot;
+          }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < RB; ++r) {
+    const int b = b0 + r;
+    if (b >= replicas) continue;
+    const size_t orow = (size_t)b * n_rows + row;
+#pragma unroll
+    for (int cc = 0; cc < CCH; ++cc) {
+      const int c = cc * 32 + lane;
+      if (c < C) g_x[orow * C + c] = accx[r][cc] * scale[r];
+    }
+  }
+}
+
+__global__ void pool_wgrad_reduce_kernel(const float* __restrict__ part, int B, long long gp, float* __restrict__ g_w) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= gp) return;
+  float s = 0.f;
+  for (int b = 0; b < B; ++b) s += part[(size_t)b * gp + i];
+  g_w[i] = s;
+}
+
 #define MLG_P_SWITCH(P, CALL)                                           \
   switch (P) {                                                          \
     case 1: { constexpr int P_ = 1; CALL; } break;                      \
@@ -275,5 +375,35 @@ extern "C" int mlg_pool_bwd_w(const float* g_out_cl, const float* x, const float
                       g_out_cl, x, vm, (const long long*)match, (const long long*)raw_indice, (int)B, (int)N,
                       (int)C, (int)G, (int)S, wrap_negative, replicas > 1 ? 1 : 0, g_w)));
   MLG_CHECK_LAUNCH("mlg_pool_bwd_w");
+  return MLG_OK;
+}
+
+extern "C" int mlg_pool_bwd(const float* g_out_cl, const float* x, const float* vm, const float* w,
+                            const int32_t* node_rowptr, const int32_t* node_slot, const int32_t* seg_of_slot,
+                            int64_t B, int64_t N, int64_t C, int64_t G, int64_t S, int64_t P, int64_t replicas,
+                            float* g_x, float* g_w, float* workspace, void* stream) {
+  MLG_CHECK_ARG(g_out_cl && x && w && node_rowptr && node_slot && seg_of_slot && g_x && g_w && workspace,
+                "mlg_pool_bwd: null pointer");
+  int rc = check_dims("mlg_pool_bwd", B, N, C, G, S, P);
+  if (rc) return rc;
+  MLG_CHECK_ARG(replicas == 1 || replicas == B, "mlg_pool_bwd: replicas must be 1 or B");
+  MLG_CHECK_ARG(C <= 128, "mlg_pool_bwd: fused backward supports C <= 128 (use mlg_pool_bwd_x / _w)");
+  cudaStream_t st = (cudaStream_t)stream;
+  MLG_CUDA(cudaMemsetAsync(workspace, 0, (size_t)B * G * P * sizeof(float), st));   // slots without a node stay zero
+  const long long n_rows = replicas > 1 ? N : B * N;
+  const long long warps = n_rows * ((replicas + 3) / 4);
+  const int grid = mlg_ceil_div(warps, kThreads / 32);
+  const int cch = C <= 32 ? 1 : (C <= 64 ? 2 : 4);
+#define MLG_POOL_FUSED(CC)                                                                                          \
+  MLG_P_SWITCH(P, (pool_bwd_fused_kernel<P_, CC><<<grid, kThreads, 0, st>>>(g_out_cl, x, vm, w, node_rowptr, node_slot, \
+                                                                            seg_of_slot, (int)n_rows, (int)replicas,   \
+                                                                            (int)S, (int)C, (int)G, g_x, workspace)))
+  if (cch == 1) { MLG_POOL_FUSED(1); }
+  else if (cch == 2) { MLG_POOL_FUSED(2); }
+  else { MLG_POOL_FUSED(4); }
+#undef MLG_POOL_FUSED
+  MLG_CHECK_LAUNCH("mlg_pool_bwd(fused)");
+  pool_wgrad_reduce_kernel<<<mlg_ceil_div(G * P, 256), 256, 0, st>>>(workspace, (int)B, G * P, g_w);
+  MLG_CHECK_LAUNCH("mlg_pool_bwd(reduce)");
   return MLG_OK;
 }

@@ -415,6 +415,16 @@ class PathwayPool(torch.autograd.Function):
         C, P = xd.shape[1], wd.shape[1]
         g_cl = g.float().permute(0, 2, 3, 1).contiguous()     # [B,S,P,C]; no copy when g is already channel-last
         gx = gw = None
+        if ctx.needs_input_grad[0] and ctx.needs_input_grad[1] and C <= 128 and not lay.wrap_negative:
+            gx, gw = torch.empty_like(xd), torch.empty_like(wd)
+            node = lay.node_csr
+            ws = torch.empty(B * G * P, dtype=torch.float32, device=xd.device)
+            with torch.cuda.device(xd.device), _cabi.span("pool_bwd", 2 * (4 * C * B * N) + 4 * B * C * S * P):
+                _cabi.check(L.mlg_pool_bwd(_cabi.fptr(g_cl), _cabi.fptr(xd), _cabi.fptr(vm, True), _cabi.fptr(wd),
+                                           _cabi.iptr(node.rowptr), _cabi.iptr(node.col), _cabi.iptr(lay.seg_of_slot),
+                                           B, N, C, G, S, P, lay.replicas, _cabi.fptr(gx), _cabi.fptr(gw), _cabi.fptr(ws),
+                                           _cabi.stream_ptr()), "mlg_pool_bwd")
+            return gx, gw, None, None
         with torch.cuda.device(xd.device):
             if ctx.needs_input_grad[0]:
                 gx = torch.empty_like(xd)
