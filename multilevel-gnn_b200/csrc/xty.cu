@@ -176,7 +176,7 @@ extern "C" int mlg_xty(const float* A, int64_t ld_a, const float* X, int64_t ld_
                        int64_t K, float* out, float* colsum, void* workspace, int64_t workspace_bytes,
                        void* stream) {
   MLG_CHECK_ARG(A && X && out && workspace, "mlg_xty: null pointer");
-  MLG_CHECK_ARG(rows >= 0 && M > 0 && K > 0 && M <= 4096 && K <= 4096, "mlg_xty: bad sizes");
+  MLG_CHECK_ARG(rows >= 0 && M > 0 && K > 0 && M <= (1 << 20) && K <= (1 << 20) && M * K < (1ll << 31), "mlg_xty: bad sizes");
   const bool aligned = ld_a % 4 == 0 && ld_x % 4 == 0 && M % 4 == 0 && K % 4 == 0 && (uintptr_t)A % 16 == 0 &&
                        (uintptr_t)X % 16 == 0;
   MLG_CHECK_ARG(workspace_bytes >= mlg_xty_workspace_bytes(rows, M, K), "mlg_xty: workspace too small");

@@ -128,9 +128,11 @@ class TallLinear(torch.autograd.Function):
         return gx, gw, (gb if ctx.has_bias else None)
 
 
-def tall_linear(x, lin):
-    """Apply an nn.Linear, routing its weight gradient through mlg_xty when x is a tall CUDA matrix."""
-    if x.is_cuda and x.dim() == 2 and x.shape[0] >= TallLinear.MIN_ROWS and x.dtype == torch.float32:
+def tall_linear(x, lin, min_rows=None):
+    """Apply an nn.Linear through TallLinear (3xTF32 tensor-core forward / dX where the shape allows, mlg_xty weight
+    and bias gradient) when x is a CUDA matrix with at least ``min_rows`` rows (default TallLinear.MIN_ROWS)."""
+    rows = TallLinear.MIN_ROWS if min_rows is None else min_rows
+    if x.is_cuda and x.dim() == 2 and x.shape[0] >= rows and x.dtype == torch.float32:
         return TallLinear.apply(x, lin.weight, lin.bias)
     return lin(x)
 

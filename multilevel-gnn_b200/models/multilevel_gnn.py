@@ -184,23 +184,32 @@ class MultilevelGNN(nn.Module):
         pca_feature = x
         for layer in self.conv_model:
             x = self._conv(layer, x)
-        x = self.pooling(x)
+        x = self.pooling(x.contiguous())          # NCHW copy (7 MB): the NHWC max-pool kernels are ~7x slower here
         x = self.drop1(x)
         x = torch.flatten(x, start_dim=1)
         if args.use_age:
             x = torch.cat([x, age[:, None]], dim=-1)
-        return self.head(x), pca_feature
+        for mod in self.head:
+            # wide first Linear (6913 / 84096 inputs): weight gradient through mlg_xty (cuBLAS picks a slow large-k kernel)
+            x = Fn.tall_linear(x, mod, min_rows=1) if (isinstance(mod, nn.Linear) and mod.in_features >= 1024) else mod(x)
+        return x, pca_feature
 
     @staticmethod
     def _conv(layer, x):
-        """1x1 convolutions run as a plain fp32 matmul over the channel axis: (a) cuDNN's convolution path
-        defaults to TF32 (torch.backends.cudnn.allow_tf32), which breaks the fp32 rtol-1e-4 parity with the
-        reference; (b) the pooled tensor is channel-last in memory (PathwayPool), so [B,C,H,W] -> [B*H*W, C]
-        is a free view and the conv is one [B*H*W, C] x [C, O] GEMM."""
+        """1x1 convolutions run as a matmul over the channel axis: (a) cuDNN's convolution path defaults to TF32
+        (torch.backends.cudnn.allow_tf32), which breaks the fp32 rtol-1e-4 parity with the reference; (b) the pooled
+        tensor is channel-last in memory (PathwayPool), so [B,C,H,W] -> [B*H*W, C] is a free view and the conv is one
+        tall [B*H*W, C] x [C, O] product (3xTF32 tensor-core kernel; weight/bias gradient through mlg_xty instead of
+        an 18-way split-K library GEMM)."""
         if isinstance(layer, nn.Conv2d) and layer.kernel_size == (1, 1):
-            w = layer.weight.view(layer.out_channels, layer.in_channels)
-            y = torch.nn.functional.linear(x.permute(0, 2, 3, 1), w, layer.bias)     # [B,H,W,O]
-            return y.permute(0, 3, 1, 2)
+            b, c, hh, ww = x.shape
+            x2 = x.permute(0, 2, 3, 1).reshape(-1, c)
+            w = layer.weight.view(layer.out_channels, c)
+            if x2.is_cuda:
+                y2 = Fn.TallLinear.apply(x2, w, layer.bias)
+            else:
+                y2 = torch.nn.functional.linear(x2, w, layer.bias)
+            return y2.view(b, hh, ww, layer.out_channels).permute(0, 3, 1, 2)
         return layer(x)
 
     # ------------------------------------------------------------------------------------------
