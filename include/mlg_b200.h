@@ -225,6 +225,13 @@ int mlg_gemm_tf32x3_supported(int64_t M, int64_t N, int64_t K);
 int mlg_gemm_tf32x3(const float* A, int64_t lda, const float* B_hi, const float* B_lo, const float* bias, float* C,
                     int64_t ldc, int64_t M, int64_t N, int64_t K, int act, float slope, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Adam (torch.optim.Adam semantics, amsgrad off; train.py:112,66) over ONE flat fp32 buffer of parameters, their
+ * gradients (the data-parallel gradient bucket) and the two moment buffers.  step_dev: device float holding the number
+ * of steps taken so far (incremented by the call), so the update can be replayed inside a CUDA graph. */
+int mlg_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, float* step_dev, int64_t n,
+                  float lr, float beta1, float beta2, float eps, float weight_decay, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -52,6 +52,35 @@ class GradBucket:
             self.flat.mul_(1.0 / world)
 
 
+class FlatAdam:
+    """torch.optim.Adam (amsgrad off) as ONE kernel over flat buffers (mlg_adam_step): parameters are re-homed as views
+    of one contiguous fp32 buffer laid out like the gradient bucket; the step counter is a device scalar so the
+    update replays inside a CUDA graph.  lr / betas / eps / weight_decay as in train.py:112."""
+
+    def __init__(self, bucket, lr, betas, eps=1e-8, weight_decay=0.0):
+        self.bucket, self.lr, self.betas, self.eps, self.wd = bucket, lr, betas, eps, weight_decay
+        flat_g = bucket.flat
+        self.flat_p = torch.empty_like(flat_g)
+        off = 0
+        for p in bucket.params:
+            n = p.numel()
+            self.flat_p[off:off + n].copy_(p.data.reshape(-1))
+            p.data = self.flat_p[off:off + n].view_as(p)
+            off += n
+        self.exp_avg = torch.zeros_like(flat_g)
+        self.exp_avg_sq = torch.zeros_like(flat_g)
+        self.step_dev = torch.zeros(1, dtype=torch.float32, device=flat_g.device)
+
+    def step(self):
+        from . import _cabi
+        L = _cabi.lib()
+        with torch.cuda.device(self.flat_p.device):
+            _cabi.check(L.mlg_adam_step(_cabi.fptr(self.flat_p), _cabi.fptr(self.bucket.flat), _cabi.fptr(self.exp_avg),
+                                        _cabi.fptr(self.exp_avg_sq), _cabi.fptr(self.step_dev), self.flat_p.numel(),
+                                        float(self.lr), float(self.betas[0]), float(self.betas[1]), float(self.eps),
+                                        float(self.wd), _cabi.stream_ptr()), "mlg_adam_step")
+
+
 class Trainer:
     """One training step of train.py:38-68 on the B200 kernels; ``capture()`` turns the whole step
     (forward, loss, backward, NCCL all-reduce, fused Adam) into ONE CUDA graph replayed per step."""
@@ -62,10 +91,10 @@ class Trainer:
         dev = self.params[0].device
         self.bucket = GradBucket(self.params)
         self.flat = self.bucket.flat
-        kw = dict(lr=args.lr, betas=(args.beta1, args.beta2), weight_decay=args.wd)
         if fused_adam and dev.type == "cuda":
-            kw.update(fused=True, capturable=True)
-        self.opt = torch.optim.Adam(self.params, **kw)
+            self.opt = FlatAdam(self.bucket, lr=args.lr, betas=(args.beta1, args.beta2), weight_decay=args.wd)
+        else:
+            self.opt = torch.optim.Adam(self.params, lr=args.lr, betas=(args.beta1, args.beta2), weight_decay=args.wd)
         self.weight = criterion_weight
         self.crit = torch.nn.BCELoss(weight=criterion_weight) if args.weight_balance else torch.nn.BCELoss()
         self.graph = None
