@@ -138,6 +138,15 @@ int64_t mlg_xty_workspace_bytes(int64_t rows, int64_t M, int64_t K);
 int mlg_xty(const float* A, int64_t ld_a, const float* X, int64_t ld_x, int64_t rows, int64_t M, int64_t K,
             float* out, float* colsum, void* workspace, int64_t workspace_bytes, void* stream);
 
+/* The same product on the tensor cores (tcgen05, 3xTF32 split: fp32-accurate, relative error ~2^-20) for the shapes
+ * that dominate the training step: K == 128 (X is [x | agg_x] of a 64-wide SAGE layer, or a 128-wide GENConv edge
+ * encoder input), 16 <= M <= 128, M % 16 == 0, 16-byte aligned operands, ld multiples of 4.  Each 32-row chunk is
+ * transposed + split in shared memory; per-CTA partial sums are reduced in a fixed order (deterministic). */
+int mlg_xty_tc_supported(int64_t rows, int64_t M, int64_t K);
+int64_t mlg_xty_tc_workspace_bytes(int64_t M);
+int mlg_xty_tc(const float* A, int64_t ld_a, const float* X, int64_t ld_x, int64_t rows, int64_t M, int64_t K,
+               float* out, float* colsum, void* workspace, int64_t workspace_bytes, void* stream);
+
 /* z[r,c] = LeakyReLU_slope(z[r,c] + bias[c]) in place (bias NULL ok; slope 0 = ReLU): the bias + activation
  * of SAGEConv.update's MLP (torch_vertex.py:288-291) after the update GEMM. */
 int mlg_bias_act(float* z, const float* bias, int64_t rows, int64_t C, float slope, void* stream);

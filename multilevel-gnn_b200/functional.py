@@ -58,18 +58,25 @@ def gather_sum(src, rowptr, idx, n_rows, val=None, pre=None, post=None, post_mod
     return out
 
 
+XTY_TC_MIN_ROWS = 8192   # below this the SIMT kernel's single launch wins
+
+
 def xty(a, x, want_colsum=False, tag="xty"):
-    """out[M,K] = a[rows,M]^T @ x[rows,K] (+ column sums of a) through mlg_xty (fp32, deterministic)."""
+    """out[M,K] = a[rows,M]^T @ x[rows,K] (+ column sums of a), fp32-accurate and deterministic: mlg_xty_tc (tensor
+    cores, 3xTF32) when K == 128 and the shape allows, else mlg_xty (fp32 FMA)."""
     L = _cabi.lib()
     rows, M = a.shape
     K = x.shape[1]
     out = torch.empty(M, K, dtype=torch.float32, device=a.device)
     cs = torch.empty(M, dtype=torch.float32, device=a.device) if want_colsum else None
-    ws_bytes = L.mlg_xty_workspace_bytes(rows, M, K)
+    tc = (USE_TF32X3 and rows >= XTY_TC_MIN_ROWS and L.mlg_xty_tc_supported(rows, M, K) and _ld(a) % 4 == 0
+          and _ld(x) % 4 == 0 and a.data_ptr() % 16 == 0 and x.data_ptr() % 16 == 0)
+    ws_bytes = L.mlg_xty_tc_workspace_bytes(M) if tc else L.mlg_xty_workspace_bytes(rows, M, K)
     ws = torch.empty(ws_bytes // 4, dtype=torch.float32, device=a.device)
-    with torch.cuda.device(a.device), _cabi.span(tag, 4 * rows * (M + K)):
-        _cabi.check(L.mlg_xty(_vptr(a), _ld(a), _vptr(x), _ld(x), rows, M, K, _cabi.fptr(out), _cabi.fptr(cs, True),
-                              _cabi.fptr(ws), ws_bytes, _cabi.stream_ptr()), "mlg_xty")
+    with torch.cuda.device(a.device), _cabi.span(tag + ("_tc" if tc else ""), 4 * rows * (M + K)):
+        fn, name = (L.mlg_xty_tc, "mlg_xty_tc") if tc else (L.mlg_xty, "mlg_xty")
+        _cabi.check(fn(_vptr(a), _ld(a), _vptr(x), _ld(x), rows, M, K, _cabi.fptr(out), _cabi.fptr(cs, True),
+                       _cabi.fptr(ws), ws_bytes, _cabi.stream_ptr()), name)
     return out, cs
 
 

@@ -373,6 +373,37 @@ def test_xty_matches_matmul(mlg):
     assert_close(out, (big[:, :32].double().t() @ big[:, 32:].double()).float(), rtol=1e-5, atol=2e-6, what="xty strided")
 
 
+def test_xty_tensor_core_matches_fp64(mlg):
+    """mlg_xty_tc (transpose + 3xTF32 split in shared memory, tcgen05): fp32-accurate, deterministic, ragged row
+    counts (zero-filled tail chunk), strided operands, every supported M."""
+    from multilevel_gnn_b200 import functional as Fn
+    g = torch.Generator().manual_seed(32)
+    L = mlg._cabi.lib()
+    for rows, M in [(64000, 64), (8192, 16), (100003, 32), (20001, 128), (9000, 48), (300000, 64)]:
+        assert L.mlg_xty_tc_supported(rows, M, 128)
+        a = torch.randn(rows, M, generator=g).to(DEV)
+        x = (torch.randn(rows, 128, generator=g) * 3 + 0.5).to(DEV)
+        out, cs = Fn.xty(a, x, want_colsum=True)
+        ref = (a.double().t() @ x.double())
+        scale = (a.double().abs().t() @ x.double().abs())
+        err = ((out.double() - ref).abs() / scale).max().item()
+        assert err < 4e-6, ("xty_tc rel-to-abs-product error", rows, M, err)
+        assert_close(cs, a.double().sum(0).float(), rtol=1e-5, atol=1e-3, what="colsum_tc")
+        out2, cs2 = Fn.xty(a, x, want_colsum=True)
+        assert torch.equal(out, out2) and torch.equal(cs, cs2), "xty_tc must be deterministic"
+        Fn.USE_TF32X3 = False
+        try:
+            simt, _ = Fn.xty(a, x)
+        finally:
+            Fn.USE_TF32X3 = True
+        assert ((simt.double() - out.double()).abs() / scale).max().item() < 4e-6
+    big = torch.randn(50000, 256, generator=g).to(DEV)      # strided: halves of a wider buffer
+    out, _ = Fn.xty(big[:, :64], big[:, 128:])
+    ref = big[:, :64].double().t() @ big[:, 128:].double()
+    assert ((out.double() - ref).abs().max() / ref.abs().max()).item() < 1e-5
+    assert not L.mlg_xty_tc_supported(1000, 64, 64) and not L.mlg_xty_tc_supported(1000, 20, 128)
+
+
 def test_replicated_topology_equals_generic(mlg):
     """The B-copies fast path (single-graph CSR streamed over the batch) must agree with the generic CSR."""
     from multilevel_gnn_b200 import functional as Fn, graph, synth
