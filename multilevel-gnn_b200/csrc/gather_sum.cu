@@ -12,6 +12,8 @@
 // every entry issues RB independent row loads (memory-level parallelism even for 1-entry rows).
 //
 // HBM-bound: algorithmic bytes = 4*C*rows*2 + 8*nnz.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "../../include/mlg_b200.h"
 
@@ -19,7 +21,18 @@ namespace {
 
 constexpr int kThreads = 256;
 constexpr int UN = 4;   // entries in flight (single-graph path)
-constexpr int RB = 8;   // replicas in flight (replicated path)
+#ifndef MLG_GS_RB
+#define MLG_GS_RB 4
+#endif
+// min resident blocks per SM for the replicated kernel.  With plain __launch_bounds__(256) ptxas minimised registers by
+// re-using ONE pair of float4 registers for all RB row loads of an entry, which serialised them into RB/2 dependent
+// round trips (ncu source page: all stall samples on the first FFMA after each load pair).  RB = 4 with an explicit
+// 3-blocks/SM budget (80 registers) makes it batch the four loads: 139 -> 102 us per SAGE aggregation at the gbm shape
+// (RB = 8 / 2 blocks: 111 us, RB = 16 / 1 block: 129 us, RB = 2: 132 us).
+#ifndef MLG_GS_MINB
+#define MLG_GS_MINB 3
+#endif
+constexpr int RB = MLG_GS_RB;   // replicas in flight (replicated path)
 
 struct GsP {
   const float* src;
@@ -49,6 +62,17 @@ __device__ __forceinline__ void ldv(float (&d)[VEC], const float* p, bool ok) {
     d[0] = t.x; d[1 % VEC] = t.y; d[2 % VEC] = t.z; d[3 % VEC] = t.w;
   } else {
     d[0] = ok ? __ldg(p) : 0.f;
+  }
+}
+// unconditional load that cannot be sunk below later arithmetic
+template <int VEC>
+__device__ __forceinline__ void ldv_now(float (&d)[VEC], const float* p) {
+  if (VEC == 4) {
+    asm volatile("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(d[0]), "=f"(d[1 % VEC]), "=f"(d[2 % VEC]), "=f"(d[3 % VEC])
+                 : "l"(p));
+  } else {
+    asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(d[0]) : "l"(p));
   }
 }
 template <int VEC>
@@ -147,7 +171,7 @@ __global__ void __launch_bounds__(kThreads) gather_sum_kernel(const GsP P) {
 //        (MultilevelGNN layer 0: x0[b,n,:] = x[b,n] * node_embedding[n,:] is never materialised).
 // ---------------------------------------------------------------------------------------------
 template <int LANES, int VEC, bool RANK1>
-__global__ void __launch_bounds__(kThreads) gather_sum_rep_kernel(const GsP P, int gy) {
+__global__ void __launch_bounds__(kThreads, MLG_GS_MINB) gather_sum_rep_kernel(const GsP P, int gy) {
   constexpr int RPW = 32 / LANES;
   constexpr int CW = LANES * VEC;
   constexpr int JU = RANK1 ? 2 : 1;   // entries per step
@@ -155,6 +179,7 @@ __global__ void __launch_bounds__(kThreads) gather_sum_rep_kernel(const GsP P, i
   const int sub = lane / LANES, sl = lane % LANES;
   const unsigned gmask = (LANES == 32) ? 0xffffffffu : (((1u << LANES) - 1u) << (sub * LANES));
   // 1-D grid, replica slice fastest: heavy rows (order[] is sorted by degree) of ALL slices start first
+  // (slice-slowest, i.e. a 4x smaller live working set in L2, measured SLOWER: 161 vs 139 us at the gbm shape)
   const int ychunk = blockIdx.x % gy;
   const long long rowblock = blockIdx.x / gy;
   const long long warp = (rowblock * (long long)blockDim.x + threadIdx.x) >> 5;
@@ -183,8 +208,10 @@ __global__ void __launch_bounds__(kThreads) gather_sum_rep_kernel(const GsP P, i
   for (int ch = 0; ch < nchunks; ++ch) {
     const unsigned c = ch * CW + sl * VEC;
     const bool cok = c < (unsigned)C;
-    const float* sc = P.src + c;
+    const float* sc = P.src + (cok ? c : 0u);   // lanes past C read (and discard) the row start: no predicated loads
+    const size_t rep_stride = (size_t)P.rep_rows_src * P.ld_src;
     for (int b0 = b_lo; b0 < b_hi; b0 += RB) {
+      const int nb = min(RB, b_hi - b0);
       float acc[RB][VEC];
 #pragma unroll
       for (int r = 0; r < RB; ++r)
@@ -229,11 +256,11 @@ __global__ void __launch_bounds__(kThreads) gather_sum_rep_kernel(const GsP P, i
             const unsigned s = __shfl_sync(gmask, my_idx, j, LANES);
             const float w = __shfl_sync(gmask, my_w, j, LANES);
             float xv[RB][VEC];
+            // all RB row loads are issued before the first FMA (volatile asm keeps ptxas from re-using one pair of
+            // registers for the loads, which serialised them into RB/2 round trips: ncu source page, r01)
+            const float* p0 = rowp(sc, (unsigned)b0 * P.rep_rows_src + s, P.ld_src);
 #pragma unroll
-            for (int r = 0; r < RB; ++r) {
-              const int b = min(b0 + r, b_hi - 1);
-              ldv<VEC>(xv[r], rowp(sc, (unsigned)b * P.rep_rows_src + s, P.ld_src), cok);
-            }
+            for (int r = 0; r < RB; ++r) ldv_now<VEC>(xv[r], p0 + (size_t)min(r, nb - 1) * rep_stride);
 #pragma unroll
             for (int r = 0; r < RB; ++r)
 #pragma unroll
@@ -253,6 +280,12 @@ __global__ void __launch_bounds__(kThreads) gather_sum_rep_kernel(const GsP P, i
     }
   }
 }
+
+// Negative result kept for the record (r01): a shared-memory staged variant of the replicated path (16-byte cp.async
+// per lane into a per-warp ring, 12-16 entries in flight, the layout gen_aggr.cu's ring kernel uses) ran at
+// 221-293 us against 134 us for the register-staged kernel above on the gbm shape: cp.async gathers top out near
+// 4-4.5 TB/s on this part, below what plain LDG.128 gathers served from L2 reach (6.5-8.6 TB/s).  What did help was
+// getting ptxas to issue all RB row loads before the first FMA (see MLG_GS_MINB).
 
 __global__ void edge_values_kernel(const float* __restrict__ ea, const int* __restrict__ eid,
                                    const int* __restrict__ rowptr, int n_rows, long long cap, float fill,
@@ -336,7 +369,8 @@ extern "C" int mlg_gather_sum(const float* src, int64_t ld_src, const int32_t* r
   if (replicas > 1) {
     // enough blocks for >= 2 waves of 148 SMs x 8 resident blocks; each slice keeps >= RB replicas
     int gy = 1;
-    while (gx * gy < 148 * 16 && (replicas / (gy * 2)) >= RB) gy *= 2;
+    static const int cta_target = getenv("MLG_GS_CTAS") ? atoi(getenv("MLG_GS_CTAS")) : 148 * 16;
+    while (gx * gy < cta_target && (replicas / (gy * 2)) >= RB) gy *= 2;
     const bool rank1 = rep_rows_src == 0;
     MLG_CHECK_ARG(rank1 || rep_rows_pre == 0, "mlg_gather_sum: per-replica pre is only supported with rep_rows_src == 0");
     const unsigned grid = (unsigned)(gx * gy);
