@@ -147,6 +147,15 @@ int64_t mlg_xty_tc_workspace_bytes(int64_t M);
 int mlg_xty_tc(const float* A, int64_t ld_a, const float* X, int64_t ld_x, int64_t rows, int64_t M, int64_t K,
                float* out, float* colsum, void* workspace, int64_t workspace_bytes, void* stream);
 
+/* Skinny Linear forward: out[rows,N] = act(x[rows,K] * W[N,K]^T + bias), rows <= 32, any K (long reduction).
+ * MultilevelGNN's head Linear(6913 -> 256) on a batch of <= 32 graphs (models/multilevel_gnn.py:104-110): a batched
+ * GEMV bound by the one pass over W.  act: 0 none, 1 LeakyReLU(slope) (slope 0 = ReLU).  fp32 FMA, fixed summation
+ * order.  workspace >= mlg_skinny_linear_workspace_bytes(N, K). */
+int64_t mlg_skinny_linear_workspace_bytes(int64_t N, int64_t K);
+int mlg_skinny_linear(const float* x, int64_t ld_x, const float* W, int64_t ld_w, const float* bias, int64_t rows,
+                      int64_t N, int64_t K, int act, float slope, float* out, int64_t ld_out, void* workspace,
+                      int64_t workspace_bytes, void* stream);
+
 /* z[r,c] = LeakyReLU_slope(z[r,c] + bias[c]) in place (bias NULL ok; slope 0 = ReLU): the bias + activation
  * of SAGEConv.update's MLP (torch_vertex.py:288-291) after the update GEMM. */
 int mlg_bias_act(float* z, const float* bias, int64_t rows, int64_t C, float slope, void* stream);

@@ -31,7 +31,8 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 template <bool ALIGNED>
 __global__ void __launch_bounds__(kThreads, 2)
 xty_kernel(const float* __restrict__ A, unsigned ld_a, const float* __restrict__ X, unsigned ld_x, long long rows,
-           int M, int K, int rows_per_block, float* __restrict__ partial, int want_colsum) {
+           int M, int K, int rows_per_block, float* __restrict__ partial, int want_colsum,
+           float* __restrict__ colsum_direct) {
   extern __shared__ __align__(16) float smem[];
   float* As = smem;                          // [kStages][TR][TM]
   float* Xs = smem + kStages * TR * TM;      // [kStages][TR][TK]
@@ -123,6 +124,7 @@ xty_kernel(const float* __restrict__ A, unsigned ld_a, const float* __restrict__
     __syncthreads();
   }
   // partial[blockIdx.x][m][k] (+ a trailing [M] block of column sums per row-chunk)
+  // (with a single row chunk the host passes `out` as partial and `colsum` as colsum_direct: no reduce pass)
   const size_t stride = (size_t)M * K + (want_colsum ? M : 0);
   float* pb = partial + (size_t)blockIdx.x * stride;
 #pragma unroll
@@ -137,7 +139,7 @@ xty_kernel(const float* __restrict__ A, unsigned ld_a, const float* __restrict__
         if (k < K) pb[(size_t)m * K + k] = acc[i][h * 4 + j];
       }
     }
-    if (want_colsum && tk == 0 && k0 == 0) pb[(size_t)M * K + m] = cs[i];
+    if (want_colsum && tk == 0 && k0 == 0) (colsum_direct ? colsum_direct : pb + (size_t)M * K)[m] = cs[i];
   }
 }
 
@@ -187,6 +189,8 @@ extern "C" int mlg_xty(const float* A, int64_t ld_a, const float* X, int64_t ld_
   rpb = ((rpb + TR - 1) / TR) * TR;
   if (rpb < TR) rpb = TR;
   dim3 grid(parts, tiles);
+  float* dst = parts == 1 ? out : (float*)workspace;
+  float* cs_direct = parts == 1 ? colsum : nullptr;
   static bool attr_done = false;   // 48 KB is exactly the default limit; set once, outside any stream capture
   if (!attr_done) {
     MLG_CUDA(cudaFuncSetAttribute(xty_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
@@ -195,13 +199,14 @@ extern "C" int mlg_xty(const float* A, int64_t ld_a, const float* X, int64_t ld_
   }
   if (aligned) {
     xty_kernel<true><<<grid, kThreads, kSmemBytes, st>>>(A, (unsigned)ld_a, X, (unsigned)ld_x, rows, (int)M, (int)K,
-                                                        (int)rpb, (float*)workspace, colsum ? 1 : 0);
+                                                        (int)rpb, dst, colsum ? 1 : 0, cs_direct);
   } else {
     xty_kernel<false><<<grid, kThreads, kSmemBytes, st>>>(A, (unsigned)ld_a, X, (unsigned)ld_x, rows, (int)M, (int)K,
-                                                         (int)rpb, (float*)workspace, colsum ? 1 : 0);
+                                                         (int)rpb, dst, colsum ? 1 : 0, cs_direct);
   }
   MLG_CHECK_LAUNCH("mlg_xty");
   const long long stride = M * K + (colsum ? M : 0);
+  if (parts == 1) return MLG_OK;   // the kernel wrote out / colsum directly
   xty_reduce_kernel<<<mlg_ceil_div(stride * 8, 256), 256, 0, st>>>((const float*)workspace, parts, stride, M * K, (int)M,
                                                               out, colsum);
   MLG_CHECK_LAUNCH("mlg_xty(reduce)");

@@ -102,6 +102,17 @@ def tall_matmul(a, w, bias=None, act=0, slope=0.0, tag="gemm_tf32x3"):
                                               None if bias is None else _cabi.fptr(_f32c(bias)), _cabi.fptr(out), N, M, N, K,
                                               int(act), float(slope), _cabi.stream_ptr()), "mlg_gemm_tf32x3")
         return out
+    if a.is_cuda and M <= 32 and K >= 1024 and a.stride(1) == 1 and w.stride(1) == 1:
+        # a handful of rows against a wide weight (the head's Linear(6913 -> 256)): one pass over W, bias + act fused
+        out = torch.empty(M, N, dtype=torch.float32, device=a.device)
+        ws_bytes = L.mlg_skinny_linear_workspace_bytes(N, K)
+        ws = torch.empty(ws_bytes // 4, dtype=torch.float32, device=a.device)
+        with torch.cuda.device(a.device), _cabi.span(tag, 4 * (N * K + M * K + M * N)):
+            _cabi.check(L.mlg_skinny_linear(_vptr(a), a.stride(0), _vptr(w), w.stride(0),
+                                            None if bias is None else _cabi.fptr(_f32c(bias)), M, N, K, int(act),
+                                            float(slope), _cabi.fptr(out), N, _cabi.fptr(ws), ws_bytes,
+                                            _cabi.stream_ptr()), "mlg_skinny_linear")
+        return out
     out = a @ w.t()
     if bias is not None or act:
         with torch.cuda.device(out.device):

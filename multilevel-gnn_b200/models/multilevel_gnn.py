@@ -247,16 +247,18 @@ class MultilevelGNN(nn.Module):
             nseg = int(self.pathway_indexs.max()) + 1 if not hasattr(self, "_nseg") else self._nseg
             self._nseg = nseg
 
-            def seg(v):
-                return torch.zeros(nseg, device=w.device, dtype=w.dtype).index_add_(0, idx, v)
-
-            indep, count = 0, 0
-            for i in range(self.pca_dim - 1):
-                for j in range(i + 1, self.pca_dim):
-                    count += 1
-                    mul = seg(w[:, i] * w[:, j])
-                    ln = torch.sqrt(seg(w[:, i] ** 2) * seg(w[:, j] ** 2))
-                indep = indep + torch.mean(torch.abs(mul / (ln + 1e-7)))
+            # only the LAST j of every i survives the reference's loop (j = pca_dim - 1): all pairs (i, P-1) at once,
+            # one segment sum over [w_i * w_last | w_i^2 | w_last^2] instead of three index_adds per pair
+            P = self.pca_dim
+            if P > 1:
+                a, b = w[:, :P - 1], w[:, P - 1:P]
+                seg = torch.zeros(nseg, 2 * (P - 1) + 1, device=w.device, dtype=w.dtype).index_add_(
+                    0, idx, torch.cat([a * b, a * a, b * b], dim=1))
+                mul, ln = seg[:, :P - 1], torch.sqrt(seg[:, P - 1:2 * (P - 1)] * seg[:, 2 * (P - 1):])
+                indep = torch.abs(mul / (ln + 1e-7)).mean(dim=0).sum()
+                count = P * (P - 1) // 2
+            else:
+                indep, count = 0, 1
             loss = loss + indep / count
         return loss
 

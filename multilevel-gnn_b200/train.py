@@ -42,6 +42,20 @@ class GradBucket:
     def zero(self):
         self.flat.zero_()
 
+    def store(self, grads):
+        """Write a list of gradients (one per bucket parameter, None = no gradient) into the bucket with one
+        multi-tensor copy.  Replaces zero() + AccumulateGrad's per-parameter in-place add (one tiny kernel per
+        parameter: ~20 launches per step on the gbm model)."""
+        if any(g is None for g in grads):
+            if not hasattr(self, "_has_none"):
+                self._has_none = True
+            for p, g in zip(self.params, grads):
+                if g is None:
+                    p.grad.zero_()
+        dst = [p.grad for p, g in zip(self.params, grads) if g is not None]
+        src = [g for g in grads if g is not None]
+        torch._foreach_copy_(dst, src)
+
     def all_reduce(self, world):
         if world <= 1:
             return
@@ -110,9 +124,9 @@ class Trainer:
 
     def _fwd_bwd(self, batch):
         self.model.train()
-        self.bucket.zero()                       # == optimizer.zero_grad() with grads kept as bucket views
         loss = self.loss(batch)
-        loss.backward()
+        # == optimizer.zero_grad(); loss.backward() with the gradients landing in the bucket views (p.grad)
+        self.bucket.store(torch.autograd.grad(loss, self.params, allow_unused=True))
         return loss.detach()
 
     def _update(self):

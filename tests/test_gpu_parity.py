@@ -404,6 +404,37 @@ def test_xty_tensor_core_matches_fp64(mlg):
     assert not L.mlg_xty_tc_supported(1000, 64, 64) and not L.mlg_xty_tc_supported(1000, 20, 128)
 
 
+def test_skinny_linear_and_head_wgrad(mlg):
+    """Head Linear(6913 -> 256) on <= 32 rows: mlg_skinny_linear forward (bias + act fused) and the single-part
+    mlg_xty weight gradient (direct write, no reduce pass) against fp64."""
+    from multilevel_gnn_b200 import functional as Fn
+    g = torch.Generator().manual_seed(33)
+    for rows, N, K in [(32, 256, 6913), (4, 256, 6913), (17, 100, 1025), (1, 8, 5000), (32, 2, 84096)]:
+        x = torch.randn(rows, K, generator=g).to(DEV)
+        w = (torch.randn(N, K, generator=g) / K ** 0.5).to(DEV)
+        b = torch.randn(N, generator=g).to(DEV)
+        for act, slope in [(0, 0.0), (1, 0.0), (1, 0.2)]:
+            out = Fn.tall_matmul(x, w, b, act=act, slope=slope)
+            ref = x.double() @ w.double().t() + b.double()
+            if act:
+                ref = torch.where(ref > 0, ref, ref * slope)
+            assert_close(out, ref.float(), rtol=1e-5, atol=1e-5, what="skinny %s act=%d" % ((rows, N, K), act))
+        assert torch.equal(Fn.tall_matmul(x, w, b), Fn.tall_matmul(x, w, b))
+        gy = torch.randn(rows, N, generator=g).to(DEV)
+        gw, gb = Fn.xty(gy, x, want_colsum=True)
+        assert_close(gw, (gy.double().t() @ x.double()).float(), rtol=1e-5, atol=1e-5, what="head wgrad")
+        assert_close(gb, gy.double().sum(0).float(), rtol=1e-5, atol=1e-5, what="head bgrad")
+    lin = torch.nn.Linear(6913, 256).to(DEV)
+    x = torch.randn(32, 6913, device=DEV, requires_grad=True)
+    y = Fn.tall_linear(x, lin, min_rows=1)
+    y.square().sum().backward()
+    gx, gw = x.grad.clone(), lin.weight.grad.clone()
+    x.grad = None; lin.weight.grad = None
+    torch.nn.functional.linear(x, lin.weight, lin.bias).square().sum().backward()
+    assert_close(gx, x.grad, rtol=1e-4, atol=1e-5, what="head dgrad")
+    assert_close(gw, lin.weight.grad, rtol=1e-4, atol=1e-5, what="head wgrad (autograd)")
+
+
 def test_replicated_topology_equals_generic(mlg):
     """The B-copies fast path (single-graph CSR streamed over the batch) must agree with the generic CSR."""
     from multilevel_gnn_b200 import functional as Fn, graph, synth
