@@ -212,6 +212,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
       // stores wrote 32 half-filled sectors per instruction and kept these warps 100 % busy (ncu r01).
       const unsigned st0 = smem_u32(out_st) + (unsigned)q * 8192u;
       const unsigned my_row = (unsigned)lane * 128u, swz = (unsigned)(lane & 7);
+      const unsigned bias_u32 = smem_u32(&S.bias_s[0]);
       int ob = 0;
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tl) {
         const int buf = tl & 1;
@@ -236,7 +237,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
           const unsigned sb = st0 + (unsigned)ob * 4096u + my_row;
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            const float4 bv = *reinterpret_cast<const float4*>(&S.bias_s[c0 + j * 4]);
+            const float4 bv = lds128(bias_u32 + (unsigned)((c0 + j * 4) * 4));
             float4 v = make_float4(__uint_as_float(r[4 * j]) + bv.x, __uint_as_float(r[4 * j + 1]) + bv.y,
                                    __uint_as_float(r[4 * j + 2]) + bv.z, __uint_as_float(r[4 * j + 3]) + bv.w);
             if (act) {

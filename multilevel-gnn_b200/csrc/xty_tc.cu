@@ -79,6 +79,14 @@ __device__ __forceinline__ unsigned long long make_smem_desc(unsigned addr) {
   return d;
 }
 // kind::tf32: D = f32 (1 << 4), A = B = tf32 (format code 2), K-major, M = 128, N
+__device__ __forceinline__ float lds32(unsigned addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts128(unsigned addr, float4 v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
 __host__ __device__ constexpr unsigned make_idesc_tf32_xty(int n) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(n >> 3) << 17) | ((unsigned)(KX >> 4) << 24);
 }
@@ -198,18 +206,19 @@ xty_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
     for (int i = wg; i < my_chunks; i += 2) {
       const int s = i % n_raw, q = i % kSplit;
       mbar_wait(&S.full_raw[s], (i / n_raw) & 1);
-      const unsigned char* st = base + (size_t)s * raw_bytes;
-      const float* xr = reinterpret_cast<const float*>(st);                 // [32][128]
-      const float* gr = reinterpret_cast<const float*>(st + off_graw);      // [32][N]
+      // explicit shared-space accesses (generic pointers made these LD.E / ST.E)
+      const unsigned st = smem_u32(base + (size_t)s * raw_bytes);
+      const unsigned xr = st + (unsigned)t * 4u;                 // [32][128] fp32, column t
+      const unsigned gr = st + off_graw + (unsigned)t * 4u;      // [32][N]  fp32, column t
       float xv[CH], gv[CH];
 #pragma unroll
-      for (int r = 0; r < CH; ++r) xv[r] = xr[r * KX + t];
+      for (int r = 0; r < CH; ++r) xv[r] = lds32(xr + (unsigned)(r * KX * 4));
       if (t < N) {
 #pragma unroll
-        for (int r = 0; r < CH; ++r) gv[r] = gr[r * N + t];
+        for (int r = 0; r < CH; ++r) gv[r] = lds32(gr + (unsigned)(r * N * 4));
       }
       mbar_wait(&S.empty_split[q], ((i / kSplit) & 1) ^ 1);
-      unsigned char* sp = split_base + (size_t)q * split_bytes;
+      const unsigned sp = smem_u32(split_base + (size_t)q * split_bytes);
 #pragma unroll
       for (int j = 0; j < CH / 4; ++j) {   // 4 consecutive rows (= K elements) -> one 16-byte chunk of K-major row t
         float4 h, l;
@@ -218,8 +227,8 @@ xty_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
         h.z = __uint_as_float(__float_as_uint(xv[4 * j + 2]) & 0xFFFFE000u); l.z = xv[4 * j + 2] - h.z;
         h.w = __uint_as_float(__float_as_uint(xv[4 * j + 3]) & 0xFFFFE000u); l.w = xv[4 * j + 3] - h.w;
         const unsigned o = (unsigned)t * 128u + (((unsigned)j ^ swz) << 4);
-        *reinterpret_cast<float4*>(sp + o) = h;
-        *reinterpret_cast<float4*>(sp + off_xlo + o) = l;
+        sts128(sp + o, h);
+        sts128(sp + off_xlo + o, l);
       }
       if (t < N) {
 #pragma unroll
@@ -231,8 +240,8 @@ xty_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
           h.z = __uint_as_float(__float_as_uint(gv[4 * j + 2]) & 0xFFFFE000u); l.z = gv[4 * j + 2] - h.z;
           h.w = __uint_as_float(__float_as_uint(gv[4 * j + 3]) & 0xFFFFE000u); l.w = gv[4 * j + 3] - h.w;
           const unsigned o = (unsigned)t * 128u + (((unsigned)j ^ swz) << 4);
-          *reinterpret_cast<float4*>(sp + off_ghi + o) = h;
-          *reinterpret_cast<float4*>(sp + off_glo + o) = l;
+          sts128(sp + off_ghi + o, h);
+          sts128(sp + off_glo + o, l);
         }
       }
       mbar_arrive(&S.empty_raw[s]);     // raw values are in registers: the slot can be refilled
