@@ -9,6 +9,8 @@
 // stores, and the 1x1-conv head consumes it as a plain [B*S*P, C] matrix); the reference's
 // [B, C, 146, 3P] tensor is a permuted VIEW of it.
 // HBM-bound: algorithmic bytes = 4*C*B*N + 4*B*N + 12*G + 4*B*C*S*P  (SURVEY.md section 8d).
+#include <cstdlib>
+
 #include "common.cuh"
 #include "../../include/mlg_b200.h"
 
@@ -299,6 +301,152 @@ pool_bwd_fused_kernel(const float* __restrict__ g_cl, const float* __restrict__ 
   }
 }
 
+// Second-generation fused backward (C == 32 * VEC, vector lanes, RB2 replicas per warp):
+//   * every lane owns VEC consecutive channels (64- / 128-bit loads), the RB2 x-rows of a warp are all requested before
+//     anything depends on them, and the g_cl rows of a slot are requested as one batch (min-blocks launch bound so that
+//     ptxas keeps them in distinct registers);
+//   * the RB2 * P dot products of a slot are reduced across the warp TOGETHER with the packed butterfly (halve the
+//     value set at every exchange: K-1+log2(32/K) shuffles for K values instead of 5 per value).
+// v1 above spent its time in 40 shuffles + 16 scalar loads per slot (150 us at the gbm shape; HBM floor ~45 us).
+template <int K>
+__device__ __forceinline__ float reduce_packed(float (&v)[K], int lane) {
+  static_assert(K >= 1 && K <= 32 && (K & (K - 1)) == 0, "K must be a power of two <= 32");
+  int off = 16;
+#pragma unroll
+  for (int n = K; n > 1; n >>= 1, off >>= 1) {
+    const bool up = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < n / 2; ++i) {
+      const float send = up ? v[i] : v[i + n / 2];
+      const float keep = up ? v[i + n / 2] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+#pragma unroll
+  for (; off >= 1; off >>= 1) v[0] += __shfl_xor_sync(0xffffffffu, v[0], off);
+  return v[0];   // total of value index (lane >> (5 - log2 K)), replicated over the lanes sharing that index
+}
+
+template <int VEC> struct VecT;
+template <> struct VecT<1> { typedef float T; };
+template <> struct VecT<2> { typedef float2 T; };
+template <> struct VecT<4> { typedef float4 T; };
+
+template <int VEC>
+__device__ __forceinline__ void ldvec(float (&d)[VEC], const float* p) {
+  typedef typename VecT<VEC>::T T;
+  const T t = __ldg(reinterpret_cast<const T*>(p));
+  const float* f = reinterpret_cast<const float*>(&t);
+#pragma unroll
+  for (int k = 0; k < VEC; ++k) d[k] = f[k];
+}
+template <int VEC>
+__device__ __forceinline__ void stvec(float* p, const float (&d)[VEC]) {
+  typedef typename VecT<VEC>::T T;
+  T t;
+  float* f = reinterpret_cast<float*>(&t);
+#pragma unroll
+  for (int k = 0; k < VEC; ++k) f[k] = d[k];
+  *reinterpret_cast<T*>(p) = t;
+}
+
+template <int P_, int VEC, int RB2>
+__global__ void __launch_bounds__(kThreads, 2)
+pool_bwd_fused2_kernel(const float* __restrict__ g_cl, const float* __restrict__ x, const float* __restrict__ vm,
+                       const float* __restrict__ w, const int* __restrict__ rowptr, const int* __restrict__ slots,
+                       const int* __restrict__ seg_of_slot, int n_rows, int replicas, int S, int G,
+                       float* __restrict__ g_x, float* __restrict__ part) {
+  constexpr int C = 32 * VEC;
+  constexpr int P2 = P_ <= 1 ? 1 : (P_ <= 2 ? 2 : (P_ <= 4 ? 4 : 8));
+  constexpr int K = RB2 * P2;
+  constexpr int KSHIFT = K == 1 ? 5 : (K == 2 ? 4 : (K == 4 ? 3 : (K == 8 ? 2 : (K == 16 ? 1 : 0))));
+  const int lane = threadIdx.x & 31;
+  const long long wid = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const int chunks = (replicas + RB2 - 1) / RB2;
+  const long long row = wid / chunks;
+  const int b0 = (int)(wid % chunks) * RB2;
+  if (row >= n_rows) return;
+  const int nb = min(RB2, replicas - b0);
+  const int beg = __ldg(rowptr + row), end = __ldg(rowptr + row + 1);
+  const size_t rep_g = (size_t)S * P_ * C;
+  const size_t rep_x = (size_t)n_rows * C;
+  const unsigned c = lane * VEC;
+  float* gx0 = g_x + ((size_t)b0 * n_rows + row) * C + c;
+  if (beg == end) {   // node without a gene slot: zero gradient, nothing to read
+    float z[VEC];
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) z[k] = 0.f;
+#pragma unroll
+    for (int r = 0; r < RB2; ++r)
+      if (r < nb) stvec<VEC>(gx0 + (size_t)r * rep_x, z);
+    return;
+  }
+  float xr[RB2][VEC], accx[RB2][VEC], scale[RB2];
+  const float* x0 = x + ((size_t)b0 * n_rows + row) * C + c;
+#pragma unroll
+  for (int r = 0; r < RB2; ++r) ldvec<VEC>(xr[r], x0 + (size_t)min(r, nb - 1) * rep_x);
+#pragma unroll
+  for (int r = 0; r < RB2; ++r) {
+    scale[r] = vm ? __ldg(vm + (size_t)(b0 + min(r, nb - 1)) * n_rows + row) : 1.f;
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) accx[r][k] = 0.f;
+  }
+  for (int base = beg; base < end; base += 32) {
+    const int q = min(base + lane, end - 1);
+    const int slot = __ldg(slots + q);
+    const int g = slot % G;
+    const int seg = __ldg(seg_of_slot + slot);
+    float wl[P_];
+#pragma unroll
+    for (int p = 0; p < P_; ++p) wl[p] = __ldg(w + (size_t)g * P_ + p);
+    const int cnt = min(32, end - base);
+    for (int j = 0; j < cnt; ++j) {
+      const int sj = __shfl_sync(0xffffffffu, seg, j);
+      const int slotj = __shfl_sync(0xffffffffu, slot, j);
+      float wj[P_];
+#pragma unroll
+      for (int p = 0; p < P_; ++p) wj[p] = __shfl_sync(0xffffffffu, wl[p], j);
+      float gv[RB2][P_][VEC];
+      const float* gp = g_cl + (size_t)b0 * rep_g + (size_t)sj * P_ * C + c;
+#pragma unroll
+      for (int r = 0; r < RB2; ++r)
+#pragma unroll
+        for (int p = 0; p < P_; ++p) ldvec<VEC>(gv[r][p], gp + (size_t)min(r, nb - 1) * rep_g + (size_t)p * C);
+      float d[K];
+#pragma unroll
+      for (int r = 0; r < RB2; ++r)
+#pragma unroll
+        for (int p = 0; p < P2; ++p) {
+          float dot = 0.f;
+          if (p < P_) {
+#pragma unroll
+            for (int k = 0; k < VEC; ++k) {
+              accx[r][k] = fmaf(gv[r][p < P_ ? p : 0][k], wj[p < P_ ? p : 0], accx[r][k]);
+              dot = fmaf(xr[r][k], gv[r][p < P_ ? p : 0][k], dot);
+            }
+          }
+          d[r * P2 + p] = dot * scale[r];
+        }
+      const float tot = reduce_packed<K>(d, lane);
+      const int vi = lane >> KSHIFT;
+      const int r = vi / P2, p = vi % P2;
+      if ((lane & ((1 << KSHIFT) - 1)) == 0 && p < P_ && r < nb) {
+        // replicated layout: slot ids are per graph (part row = b); general layout: slot ids already span b*G + g
+        const size_t prow = (replicas > 1) ? (size_t)(b0 + r) * G + slotj : (size_t)slotj;
+        part[prow * P_ + p] = tot;
+      }
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < RB2; ++r) {
+    if (r < nb) {
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) accx[r][k] *= scale[r];
+      stvec<VEC>(gx0 + (size_t)r * rep_x, accx[r]);
+    }
+  }
+}
+
 __global__ void pool_wgrad_reduce_kernel(const float* __restrict__ part, int B, long long gp, float* __restrict__ g_w) {
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (i >= gp) return;
@@ -391,6 +539,26 @@ extern "C" int mlg_pool_bwd(const float* g_out_cl, const float* x, const float* 
   cudaStream_t st = (cudaStream_t)stream;
   MLG_CUDA(cudaMemsetAsync(workspace, 0, (size_t)B * G * P * sizeof(float), st));   // slots without a node stay zero
   const long long n_rows = replicas > 1 ? N : B * N;
+  static const bool v1_only = getenv("MLG_POOL_BWD_V1") != nullptr;
+  if (!v1_only && replicas > 1 && (C == 32 || C == 64 || C == 128) && (uintptr_t)g_out_cl % 16 == 0 && (uintptr_t)x % 16 == 0 &&
+      (uintptr_t)g_x % 16 == 0) {
+    // vector-lane kernel; replicas per warp chosen so that RB2 * pow2(P) <= 32 packed dot products
+    const int rb2 = P <= 2 ? 8 : (P <= 4 ? 8 : 4);
+    const long long warps2 = n_rows * ((replicas + rb2 - 1) / rb2);
+    const int grid2 = mlg_ceil_div(warps2, kThreads / 32);
+#define MLG_POOL_F2(VV, RR)                                                                                           \
+  MLG_P_SWITCH(P, (pool_bwd_fused2_kernel<P_, VV, (P_ <= 4 ? 8 : 4)><<<grid2, kThreads, 0, st>>>(                      \
+                      g_out_cl, x, vm, w, node_rowptr, node_slot, seg_of_slot, (int)n_rows, (int)replicas, (int)S,     \
+                      (int)G, g_x, workspace)))
+    if (C == 32) { MLG_POOL_F2(1, 0); }
+    else if (C == 64) { MLG_POOL_F2(2, 0); }
+    else { MLG_POOL_F2(4, 0); }
+#undef MLG_POOL_F2
+    MLG_CHECK_LAUNCH("mlg_pool_bwd(fused2)");
+    pool_wgrad_reduce_kernel<<<mlg_ceil_div(G * P, 256), 256, 0, st>>>(workspace, (int)B, G * P, g_w);
+    MLG_CHECK_LAUNCH("mlg_pool_bwd(reduce)");
+    return MLG_OK;
+  }
   const long long warps = n_rows * ((replicas + 3) / 4);
   const int grid = mlg_ceil_div(warps, kThreads / 32);
   const int cch = C <= 32 ? 1 : (C <= 64 ? 2 : 4);
