@@ -175,11 +175,27 @@ class Trainer:
             self.graph_update.replay()
         return self.static_loss
 
+    # fields that are dataset constants when a batch carries a ``topology_key``: the key promises that the edge list,
+    # edge weights, node->graph vector and pooling layout are identical for every batch with that key (one gene network
+    # shared by all patients, dataloader/multiloader.py:687-698) -- exactly what MultilevelGNN.forward already assumes
+    # when it caches the CSR / pool layout under that key.  They are uploaded once, not per step.
+    STATIC_TOPOLOGY_FIELDS = ("edge_index", "edge_attr", "batch", "gene_pca_match", "raw_indice")
+
+    def _step_fields(self, host_batch):
+        key = getattr(self.static_batch, "topology_key", None)
+        same = key is not None and getattr(host_batch, "topology_key", None) == key
+        return [k for k, v in vars(self.static_batch).items()
+                if torch.is_tensor(v) and not (same and k in self.STATIC_TOPOLOGY_FIELDS)]
+
+    def h2d_bytes(self, host_batch):
+        """Bytes ``load_batch`` / ``prefetch`` copy host -> device for this batch."""
+        return sum(getattr(host_batch, k).numel() * getattr(host_batch, k).element_size()
+                   for k in self._step_fields(host_batch))
+
     def load_batch(self, host_batch):
         """Copy a (pinned) host batch into the captured graph's static device buffers (async H2D)."""
-        for k, v in vars(self.static_batch).items():
-            if torch.is_tensor(v):
-                v.copy_(getattr(host_batch, k), non_blocking=True)
+        for k in self._step_fields(host_batch):
+            getattr(self.static_batch, k).copy_(getattr(host_batch, k), non_blocking=True)
 
     def prefetch(self, host_batch):
         """Start the H2D copy of the NEXT batch on a side stream into staging buffers while the current step's
@@ -188,12 +204,15 @@ class Trainer:
         (train.py:42) lacks."""
         if self._copy_stream is None:
             self._copy_stream = torch.cuda.Stream()
-            self._staging = {k: torch.empty_like(v) for k, v in vars(self.static_batch).items() if torch.is_tensor(v)}
+            self._staging = {k: torch.empty_like(getattr(self.static_batch, k)) for k in self._step_fields(host_batch)}
             self._staged = torch.cuda.Event()
             self._consumed = torch.cuda.Event()
             self._consumed.record()
         self._copy_stream.wait_event(self._consumed)        # staging may not be overwritten before it was consumed
         with torch.cuda.stream(self._copy_stream):
+            if set(self._staging) != set(self._step_fields(host_batch)):
+                raise ValueError("prefetch: this batch's topology_key differs from the one the staging buffers were "
+                                 "sized for; use step(batch) for a batch with a different topology")
             for k, v in self._staging.items():
                 v.copy_(getattr(host_batch, k), non_blocking=True)
             self._staged.record()
