@@ -147,6 +147,15 @@ int64_t mlg_xty_tc_workspace_bytes(int64_t M);
 int mlg_xty_tc(const float* A, int64_t ld_a, const float* X, int64_t ld_x, int64_t rows, int64_t M, int64_t K,
                float* out, float* colsum, void* workspace, int64_t workspace_bytes, void* stream);
 
+/* Weight folding of the fused SAGE layer (SAGEConv, torch_vertex.py:279-291: nn(cat[x, mean_j lin_r(x_j)]) with lin_r
+ * commuted past the mean).  nn_w = nn.weight [cout, cin + r], lin_r_w = lin_r.weight [r, cin].
+ * fwd: wcat = [W1 | W2 * W_r] [cout, 2cin], its 3xTF32 hi/lo split, and the hi/lo split of wcat^T [2cin, cout].
+ * bwd: g_nn_w = [g_wcat[:, :cin] | g_wcat[:, cin:] * W_r^T],  g_lin_r_w = W2^T * g_wcat[:, cin:]. */
+int mlg_sage_fold_fwd(const float* nn_w, const float* lin_r_w, int64_t cout, int64_t cin, int64_t r, float* wcat, float* wcat_hi,
+                      float* wcat_lo, float* wcat_t_hi, float* wcat_t_lo, void* stream);
+int mlg_sage_fold_bwd(const float* g_wcat, const float* nn_w, const float* lin_r_w, int64_t cout, int64_t cin, int64_t r,
+                      float* g_nn_w, float* g_lin_r_w, void* stream);
+
 /* Skinny Linear forward: out[rows,N] = act(x[rows,K] * W[N,K]^T + bias), rows <= 32, any K (long reduction).
  * MultilevelGNN's head Linear(6913 -> 256) on a batch of <= 32 graphs (models/multilevel_gnn.py:104-110): a batched
  * GEMV bound by the one pass over W.  act: 0 none, 1 LeakyReLU(slope) (slope 0 = ReLU).  fp32 FMA, fixed summation

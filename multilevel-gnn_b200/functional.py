@@ -83,7 +83,7 @@ def xty(a, x, want_colsum=False, tag="xty"):
 USE_TF32X3 = True      # tall Linears on the tensor cores with the 3xTF32 split (fp32-accurate); False = cuBLAS fp32
 
 
-def tall_matmul(a, w, bias=None, act=0, slope=0.0, tag="gemm_tf32x3"):
+def tall_matmul(a, w, bias=None, act=0, slope=0.0, tag="gemm_tf32x3", w_split=None):
     """act(a @ w^T + bias) for a tall fp32 matrix a [M, K] and a small weight w [N, K]: mlg_gemm_tf32x3 when the shape
     is supported, else cuBLAS fp32 (+ mlg_bias_act).  act: 0 none, 1 LeakyReLU(slope)."""
     L = _cabi.lib()
@@ -91,12 +91,15 @@ def tall_matmul(a, w, bias=None, act=0, slope=0.0, tag="gemm_tf32x3"):
     N = w.shape[0]
     if (USE_TF32X3 and a.is_cuda and a.stride(1) == 1 and a.stride(0) % 4 == 0 and a.data_ptr() % 16 == 0
             and L.mlg_gemm_tf32x3_supported(M, N, K)):
-        wd = _f32c(w)
-        hi, lo = torch.empty_like(wd), torch.empty_like(wd)
         out = torch.empty(M, N, dtype=torch.float32, device=a.device)
         with torch.cuda.device(a.device):
-            _cabi.check(L.mlg_split_tf32(_cabi.fptr(wd), wd.numel(), _cabi.fptr(hi), _cabi.fptr(lo), _cabi.stream_ptr()),
-                        "mlg_split_tf32")
+            if w_split is not None:
+                hi, lo = w_split          # [N, K] hi / lo parts prepared by the caller (mlg_sage_fold_fwd)
+            else:
+                wd = _f32c(w)
+                hi, lo = torch.empty_like(wd), torch.empty_like(wd)
+                _cabi.check(L.mlg_split_tf32(_cabi.fptr(wd), wd.numel(), _cabi.fptr(hi), _cabi.fptr(lo),
+                                             _cabi.stream_ptr()), "mlg_split_tf32")
             with _cabi.span(tag, 4 * M * (K + N)):
                 _cabi.check(L.mlg_gemm_tf32x3(_vptr(a), a.stride(0), _cabi.fptr(hi), _cabi.fptr(lo),
                                               None if bias is None else _cabi.fptr(_f32c(bias)), _cabi.fptr(out), N, M, N, K,
@@ -304,8 +307,16 @@ class SageLayer(torch.autograd.Function):
         n = xs_d.numel() if rank1 else xd.shape[0]
         cin = xd.shape[1]
         w_r, w_nn = lin_r_w.detach(), nn_w.detach()
-        w1, w2 = w_nn[:, :cin], w_nn[:, cin:]
-        wcat = torch.cat([w1, w2 @ w_r], dim=1)                       # [cout, 2cin]  (tiny)
+        w_r, w_nn = _f32c(w_r), _f32c(w_nn)
+        cout = w_nn.shape[0]
+        wbuf = torch.empty(5, cout * 2 * cin, dtype=torch.float32, device=xd.device)
+        with torch.cuda.device(xd.device):   # Wcat = [W1 | W2 . W_r], its tf32 hi/lo split, and the split of Wcat^T
+            _cabi.check(_cabi.lib().mlg_sage_fold_fwd(_cabi.fptr(w_nn), _cabi.fptr(w_r), cout, cin, w_r.shape[0],
+                                                      _cabi.fptr(wbuf[0]),
+                                                      _cabi.fptr(wbuf[1]), _cabi.fptr(wbuf[2]), _cabi.fptr(wbuf[3]),
+                                                      _cabi.fptr(wbuf[4]), _cabi.stream_ptr()), "mlg_sage_fold_fwd")
+        wcat = wbuf[0].view(cout, 2 * cin)
+        wsplit = (wbuf[1].view(cout, 2 * cin), wbuf[2].view(cout, 2 * cin))
         xcat = torch.empty(n, 2 * cin, dtype=torch.float32, device=xd.device)
         csr = topo.fwd
         gather_sum(xd, csr.rowptr, csr.col, topo.n_single, val=topo.fwd_val, pre=xs_d, post_mode=1, relative=relative,
@@ -313,16 +324,18 @@ class SageLayer(torch.autograd.Function):
                    rank1=rank1, tag="sage_aggr_fwd")
         # update GEMM + bias + (Leaky)ReLU: 3xTF32 tensor-core kernel with fused epilogue (cuBLAS fp32 + mlg_bias_act
         # for shapes it does not cover)
-        y = tall_matmul(xcat, wcat, None if nn_b is None else nn_b.detach(), act=1, slope=slope, tag="sage_update_gemm")
-        ctx.save_for_backward(xcat, y, wcat, w_r, w2, xs_d if rank1 else None)
+        y = tall_matmul(xcat, wcat, None if nn_b is None else nn_b.detach(), act=1, slope=slope, tag="sage_update_gemm",
+                        w_split=wsplit)
+        ctx.save_for_backward(xcat, y, wbuf, w_r, w_nn, xs_d if rank1 else None)
         ctx.topo, ctx.relative, ctx.slope, ctx.cin, ctx.has_bias = topo, bool(relative), float(slope), cin, nn_b is not None
         ctx.rank1 = rank1
         return y
 
     @staticmethod
     def backward(ctx, gy):
-        xcat, y, wcat, w_r, w2, xs_d = ctx.saved_tensors
+        xcat, y, wbuf, w_r, w_nn, xs_d = ctx.saved_tensors
         topo, cin = ctx.topo, ctx.cin
+        cout = w_nn.shape[0]
         gy = _f32c(gy)
         gz = torch.ops.aten.leaky_relu_backward(gy, y, ctx.slope, True) if ctx.slope != 0.0 \
             else torch.ops.aten.threshold_backward(gy, y, 0.0)
@@ -330,11 +343,15 @@ class SageLayer(torch.autograd.Function):
         gx = g_wr = g_wnn = g_b = None
         if needs[2] or needs[3] or needs[4]:
             g_wcat, g_b = xty(gz, xcat, want_colsum=ctx.has_bias, tag="sage_wgrad")       # [cout, 2cin], [cout]
-            g_weff = g_wcat[:, cin:]
-            g_wnn = torch.cat([g_wcat[:, :cin], g_weff @ w_r.t()], dim=1)
-            g_wr = w2.t() @ g_weff
+            g_wnn, g_wr = torch.empty_like(w_nn), torch.empty_like(w_r)
+            with torch.cuda.device(gz.device):
+                _cabi.check(_cabi.lib().mlg_sage_fold_bwd(_cabi.fptr(g_wcat), _cabi.fptr(w_nn), _cabi.fptr(w_r), cout, cin,
+                                                          w_r.shape[0], _cabi.fptr(g_wnn), _cabi.fptr(g_wr),
+                                                          _cabi.stream_ptr()), "mlg_sage_fold_bwd")
         if needs[0]:
-            gxcat = tall_matmul(gz, wcat.t().contiguous(), tag="sage_dgrad_gemm")            # [N, 2cin]
+            wcat_t = wbuf[0].view(cout, 2 * cin).t()
+            gxcat = tall_matmul(gz, wcat_t, tag="sage_dgrad_gemm",
+                                w_split=(wbuf[3].view(2 * cin, cout), wbuf[4].view(2 * cin, cout)))   # [N, 2cin]
             bw = topo.bwd
             gx = gather_sum(gxcat[:, cin:], bw.rowptr, bw.col, topo.n_single, val=topo.bwd_val, pre=topo.inv_cnt,
                             addend=gxcat[:, :cin], replicas=topo.replicas, order=topo.bwd_order, tag="sage_aggr_bwd")
