@@ -108,6 +108,8 @@ int mlg_gen_aggr_bwd(const float* g, const float* x, const float* e, const int32
  *     out_i = addend_i + post_i * ( sum_{q in row i} val[q] * pre[idx[q]] * src[idx[q]] )
  *     relative != 0:  out_i -= src_i * (post_mode==mean ? 1 : cnt_i)      (RSAGE x_j*w - x_i)
  *     self_out != NULL: self_out_i = src_i                                 (left half of cat(x, agg))
+ *     mask != NULL:     out_i *= (mask_i > 0 ? 1 : mask_slope) elementwise  (backward only: the derivative of the
+ *                       (Leaky)ReLU that produced this layer's input, so the previous layer gets dL/dz directly)
  * val NULL = 1, pre NULL = 1, addend NULL = 0; post_mode 0: post_i = 1, 1: post_i = 1/cnt_i (cnt_i = row
  * length, PyG mean aggregation incl. the self loop), 2: post_i = post[i].
  * replicas = B > 1: the CSR (n_rows rows, idx in [0, n_rows)) is ONE graph shared by B stacked copies
@@ -126,7 +128,7 @@ int mlg_gather_sum(const float* src, int64_t ld_src, const int32_t* rowptr, cons
                    const float* pre, const float* post, const int32_t* order, int64_t n_rows, int64_t C,
                    int64_t replicas, int64_t rep_rows_src, int64_t rep_rows_pre, int post_mode, int relative,
                    const float* addend, int64_t ld_add, float* out, int64_t ld_out, float* self_out,
-                   int64_t ld_self, void* stream);
+                   int64_t ld_self, const float* mask, int64_t ld_mask, float mask_slope, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Tall-skinny transposed product: out[M,K] = A[rows,M]^T * X[rows,K], colsum[M] = sum_r A[r,:] (NULL ok).
@@ -208,10 +210,13 @@ int mlg_pool_bwd_w(const float* g_out_cl, const float* x, const float* vm, const
                    int64_t P, int wrap_negative, int64_t replicas, float* g_w, void* stream);
 /* Both gradients in ONE pass over the node-side CSR (x streamed in node order, every g_out_cl row loaded once):
  * g_x as above; per-graph partial weight gradients go to workspace [B*G*P] floats and are reduced over the
- * graphs in a fixed order into g_w.  C <= 128.  Node-side structures as for mlg_pool_bwd_x. */
+ * graphs in a fixed order into g_w.  C <= 128.  Node-side structures as for mlg_pool_bwd_x.
+ * mask_input != 0: g_x *= (x > 0 ? 1 : mask_slope), the derivative of the (Leaky)ReLU that produced x (the last GNN
+ * layer's output), so that layer receives dL/dz directly and skips its own activation-backward pass. */
 int mlg_pool_bwd(const float* g_out_cl, const float* x, const float* vm, const float* w, const int32_t* node_rowptr,
                  const int32_t* node_slot, const int32_t* seg_of_slot, int64_t B, int64_t N, int64_t C, int64_t G,
-                 int64_t S, int64_t P, int64_t replicas, float* g_x, float* g_w, float* workspace, void* stream);
+                 int64_t S, int64_t P, int64_t replicas, float* g_x, float* g_w, float* workspace, int mask_input,
+                 float mask_slope, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Dilated kNN graph (models/gcn_lib/sparse/torch_edge.py:53-104, dense/torch_edge.py:32-58):

@@ -29,7 +29,8 @@ _SIGNATURES = {
                                   _c_f32, _c_vp, _c_f32, _c_vp, _c_vp, _c_f32, _c_int, _c_vp, _c_vp, _c_vp,
                                   _c_vp, _c_vp, _c_vp, _c_vp]),
     "mlg_gather_sum": (_c_int, [_c_vp, _c_i64, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_i64, _c_i64, _c_i64,
-                                _c_i64, _c_i64, _c_int, _c_int, _c_vp, _c_i64, _c_vp, _c_i64, _c_vp, _c_i64, _c_vp]),
+                                _c_i64, _c_i64, _c_int, _c_int, _c_vp, _c_i64, _c_vp, _c_i64, _c_vp, _c_i64, _c_vp, _c_i64,
+                                _c_f32, _c_vp]),
     "mlg_xty_workspace_bytes": (_c_i64, [_c_i64, _c_i64, _c_i64]),
     "mlg_xty_tc_supported": (_c_int, [_c_i64, _c_i64, _c_i64]),
     "mlg_xty_tc_workspace_bytes": (_c_i64, [_c_i64]),
@@ -50,7 +51,7 @@ _SIGNATURES = {
     "mlg_pool_bwd_w": (_c_int, [_c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_i64, _c_i64, _c_i64, _c_i64, _c_i64,
                                 _c_i64, _c_int, _c_i64, _c_vp, _c_vp]),
     "mlg_pool_bwd": (_c_int, [_c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_i64, _c_i64, _c_i64, _c_i64, _c_i64, _c_i64,
-                              _c_i64, _c_vp, _c_vp, _c_vp, _c_vp]),
+                              _c_i64, _c_vp, _c_vp, _c_vp, _c_int, _c_f32, _c_vp]),
     "mlg_cast_bf16": (_c_int, [_c_vp, _c_i64, _c_i64, _c_i64, _c_i64, _c_int, _c_vp, _c_i64, _c_vp]),
     "mlg_gemm_bf16": (_c_int, [_c_vp, _c_i64, _c_i64, _c_vp, _c_i64, _c_i64, _c_vp, _c_i64, _c_i64, _c_i64, _c_i64,
                                _c_i64, _c_i64, _c_f32, _c_vp]),

@@ -42,10 +42,12 @@ struct GsP {
   const float* pre;
   const float* post;
   const float* addend;
+  const float* mask;     // optional: out *= (mask[row, c] > 0 ? 1 : mask_slope)  (activation derivative of the consumer's input)
   const int* order;      // optional row visiting order (heavy rows first, equal degrees together)
   float* out;
   float* self_out;
-  unsigned ld_src, ld_out, ld_add, ld_self;
+  unsigned ld_src, ld_out, ld_add, ld_self, ld_mask;
+  float mask_slope;
   int n, C, post_mode, relative;
   int replicas;
   unsigned rep_rows_src;   // 0: every replica reads the SAME src rows (rank-1 source, pre is per replica)
@@ -105,6 +107,12 @@ __device__ __forceinline__ void finish_row(const GsP& P, float (&acc)[VEC], unsi
     ldv<VEC>(ad, rowp(P.addend, out_row, P.ld_add) + c, cok);
 #pragma unroll
     for (int k = 0; k < VEC; ++k) acc[k] += ad[k];
+  }
+  if (P.mask) {
+    float mk[VEC];
+    ldv<VEC>(mk, rowp(P.mask, out_row, P.ld_mask) + c, cok);
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) acc[k] *= mk[k] > 0.f ? 1.f : P.mask_slope;
   }
   stv<VEC>(rowp(P.out, out_row, P.ld_out) + c, acc, cok);
 }
@@ -337,7 +345,7 @@ extern "C" int mlg_gather_sum(const float* src, int64_t ld_src, const int32_t* r
                               int64_t n_rows, int64_t C, int64_t replicas, int64_t rep_rows_src,
                               int64_t rep_rows_pre, int post_mode, int relative, const float* addend,
                               int64_t ld_add, float* out, int64_t ld_out, float* self_out, int64_t ld_self,
-                              void* stream) {
+                              const float* mask, int64_t ld_mask, float mask_slope, void* stream) {
   MLG_CHECK_ARG(src && rowptr && idx && out, "mlg_gather_sum: null src/rowptr/idx/out");
   MLG_CHECK_ARG(n_rows >= 0 && n_rows < (1ll << 31) && C > 0 && C < (1ll << 20),
                 "mlg_gather_sum: bad sizes n_rows=%lld C=%lld", (long long)n_rows, (long long)C);
@@ -348,15 +356,17 @@ extern "C" int mlg_gather_sum(const float* src, int64_t ld_src, const int32_t* r
   MLG_CHECK_ARG(replicas > 1 || (rep_rows_pre == 0), "mlg_gather_sum: per-replica pre needs replicas > 1");
   MLG_CHECK_ARG(rep_rows_src > 0 || replicas == 1 || (pre && rep_rows_pre > 0),
                 "mlg_gather_sum: rep_rows_src == 0 (rank-1 source) needs a per-replica pre");
-  MLG_CHECK_ARG(ld_src >= C && ld_out >= C && (!addend || ld_add >= C) && (!self_out || ld_self >= C),
+  MLG_CHECK_ARG(ld_src >= C && ld_out >= C && (!addend || ld_add >= C) && (!self_out || ld_self >= C) &&
+                    (!mask || ld_mask >= C),
                 "mlg_gather_sum: leading dimension smaller than C");
   if (n_rows == 0) return MLG_OK;
   const bool vec4 = C % 4 == 0 && ld_src % 4 == 0 && ld_out % 4 == 0 && (!addend || ld_add % 4 == 0) &&
                     (!self_out || ld_self % 4 == 0) && ((uintptr_t)src % 16 == 0) && ((uintptr_t)out % 16 == 0) &&
-                    (!addend || (uintptr_t)addend % 16 == 0) && (!self_out || (uintptr_t)self_out % 16 == 0);
+                    (!addend || (uintptr_t)addend % 16 == 0) && (!self_out || (uintptr_t)self_out % 16 == 0) &&
+                    (!mask || (ld_mask % 4 == 0 && (uintptr_t)mask % 16 == 0));
   GsP P;
   P.src = src; P.rowptr = rowptr; P.idx = idx; P.val = val; P.pre = pre; P.post = post; P.addend = addend;
-  P.order = order; P.out = out; P.self_out = self_out;
+  P.order = order; P.out = out; P.self_out = self_out; P.mask = mask; P.ld_mask = (unsigned)ld_mask; P.mask_slope = mask_slope;
   P.ld_src = (unsigned)ld_src; P.ld_out = (unsigned)ld_out; P.ld_add = (unsigned)ld_add; P.ld_self = (unsigned)ld_self;
   P.n = (int)n_rows; P.C = (int)C; P.post_mode = post_mode; P.relative = relative;
   P.replicas = (int)replicas; P.rep_rows_src = (unsigned)rep_rows_src; P.rep_rows_pre = (unsigned)rep_rows_pre;

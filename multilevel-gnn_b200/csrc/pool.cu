@@ -219,7 +219,7 @@ __global__ void __launch_bounds__(kThreads)
 pool_bwd_fused_kernel(const float* __restrict__ g_cl, const float* __restrict__ x, const float* __restrict__ vm,
                       const float* __restrict__ w, const int* __restrict__ rowptr, const int* __restrict__ slots,
                       const int* __restrict__ seg_of_slot, int n_rows, int replicas, int S, int C, int G,
-                      float* __restrict__ g_x, float* __restrict__ part) {
+                      float* __restrict__ g_x, float* __restrict__ part, int mask_input, float mask_slope) {
   constexpr int RB = 4;
   const int lane = threadIdx.x & 31;
   const long long wid = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
@@ -229,7 +229,7 @@ pool_bwd_fused_kernel(const float* __restrict__ g_cl, const float* __restrict__ 
   if (row >= n_rows) return;
   const int beg = __ldg(rowptr + row), end = __ldg(rowptr + row + 1);
   const size_t rep_g = (size_t)S * P_ * C;
-  float accx[RB][CCH], xr[RB][CCH], scale[RB];
+  float accx[RB][CCH], xr[RB][CCH], scale[RB], dmask[RB][CCH];
 #pragma unroll
   for (int r = 0; r < RB; ++r) {
     const int b = min(b0 + r, replicas - 1);
@@ -239,7 +239,9 @@ pool_bwd_fused_kernel(const float* __restrict__ g_cl, const float* __restrict__ 
     for (int cc = 0; cc < CCH; ++cc) {
       const int c = cc * 32 + lane;
       accx[r][cc] = 0.f;
-      xr[r][cc] = (c < C && beg < end) ? __ldg(x + orow * C + c) * scale[r] : 0.f;
+      const float raw = (c < C && beg < end) ? __ldg(x + orow * C + c) : 0.f;
+      dmask[r][cc] = (mask_input && !(raw > 0.f)) ? mask_slope : 1.f;
+      xr[r][cc] = raw * scale[r];
     }
   }
   for (int base = beg; base < end; base += 32) {
@@ -296,7 +298,7 @@ pool_bwd_fused_kernel(const float* __restrict__ g_cl, const float* __restrict__ 
 #pragma unroll
     for (int cc = 0; cc < CCH; ++cc) {
       const int c = cc * 32 + lane;
-      if (c < C) g_x[orow * C + c] = accx[r][cc] * scale[r];
+      if (c < C) g_x[orow * C + c] = accx[r][cc] * scale[r] * dmask[r][cc];
     }
   }
 }
@@ -355,7 +357,7 @@ __global__ void __launch_bounds__(kThreads, 2)
 pool_bwd_fused2_kernel(const float* __restrict__ g_cl, const float* __restrict__ x, const float* __restrict__ vm,
                        const float* __restrict__ w, const int* __restrict__ rowptr, const int* __restrict__ slots,
                        const int* __restrict__ seg_of_slot, int n_rows, int replicas, int S, int G,
-                       float* __restrict__ g_x, float* __restrict__ part) {
+                       float* __restrict__ g_x, float* __restrict__ part, int mask_input, float mask_slope) {
   constexpr int C = 32 * VEC;
   constexpr int P2 = P_ <= 1 ? 1 : (P_ <= 2 ? 2 : (P_ <= 4 ? 4 : 8));
   constexpr int K = RB2 * P2;
@@ -441,7 +443,7 @@ pool_bwd_fused2_kernel(const float* __restrict__ g_cl, const float* __restrict__
   for (int r = 0; r < RB2; ++r) {
     if (r < nb) {
 #pragma unroll
-      for (int k = 0; k < VEC; ++k) accx[r][k] *= scale[r];
+      for (int k = 0; k < VEC; ++k) accx[r][k] *= (mask_input && !(xr[r][k] > 0.f)) ? scale[r] * mask_slope : scale[r];
       stvec<VEC>(gx0 + (size_t)r * rep_x, accx[r]);
     }
   }
@@ -529,7 +531,7 @@ extern "C" int mlg_pool_bwd_w(const float* g_out_cl, const float* x, const float
 extern "C" int mlg_pool_bwd(const float* g_out_cl, const float* x, const float* vm, const float* w,
                             const int32_t* node_rowptr, const int32_t* node_slot, const int32_t* seg_of_slot,
                             int64_t B, int64_t N, int64_t C, int64_t G, int64_t S, int64_t P, int64_t replicas,
-                            float* g_x, float* g_w, float* workspace, void* stream) {
+                            float* g_x, float* g_w, float* workspace, int mask_input, float mask_slope, void* stream) {
   MLG_CHECK_ARG(g_out_cl && x && w && node_rowptr && node_slot && seg_of_slot && g_x && g_w && workspace,
                 "mlg_pool_bwd: null pointer");
   int rc = check_dims("mlg_pool_bwd", B, N, C, G, S, P);
@@ -549,7 +551,7 @@ extern "C" int mlg_pool_bwd(const float* g_out_cl, const float* x, const float* 
 #define MLG_POOL_F2(VV, RR)                                                                                           \
   MLG_P_SWITCH(P, (pool_bwd_fused2_kernel<P_, VV, (P_ <= 4 ? 8 : 4)><<<grid2, kThreads, 0, st>>>(                      \
                       g_out_cl, x, vm, w, node_rowptr, node_slot, seg_of_slot, (int)n_rows, (int)replicas, (int)S,     \
-                      (int)G, g_x, workspace)))
+                      (int)G, g_x, workspace, mask_input, mask_slope)))
     if (C == 32) { MLG_POOL_F2(1, 0); }
     else if (C == 64) { MLG_POOL_F2(2, 0); }
     else { MLG_POOL_F2(4, 0); }
@@ -565,7 +567,8 @@ extern "C" int mlg_pool_bwd(const float* g_out_cl, const float* x, const float* 
 #define MLG_POOL_FUSED(CC)                                                                                          \
   MLG_P_SWITCH(P, (pool_bwd_fused_kernel<P_, CC><<<grid, kThreads, 0, st>>>(g_out_cl, x, vm, w, node_rowptr, node_slot, \
                                                                             seg_of_slot, (int)n_rows, (int)replicas,   \
-                                                                            (int)S, (int)C, (int)G, g_x, workspace)))
+                                                                            (int)S, (int)C, (int)G, g_x, workspace,   \
+                                                                            mask_input, mask_slope)))
   if (cch == 1) { MLG_POOL_FUSED(1); }
   else if (cch == 2) { MLG_POOL_FUSED(2); }
   else { MLG_POOL_FUSED(4); }

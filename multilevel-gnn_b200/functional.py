@@ -37,7 +37,8 @@ def _vptr(t):
 
 
 def gather_sum(src, rowptr, idx, n_rows, val=None, pre=None, post=None, post_mode=0, relative=False, out=None,
-               addend=None, self_out=None, replicas=1, order=None, rank1=False, tag="gather_sum"):
+               addend=None, self_out=None, replicas=1, order=None, rank1=False, tag="gather_sum", mask=None,
+               mask_slope=0.0):
     """Raw (non-differentiable) call of mlg_gather_sum.  src / out / addend / self_out may be column
     slices of wider row-major buffers (leading dimension = stride(0))."""
     L = _cabi.lib()
@@ -54,7 +55,8 @@ def gather_sum(src, rowptr, idx, n_rows, val=None, pre=None, post=None, post_mod
             n_rows if rank1 else 0, post_mode, int(relative),
             None if addend is None else _vptr(addend), 0 if addend is None else _ld(addend),
             _vptr(out), _ld(out), None if self_out is None else _vptr(self_out),
-            0 if self_out is None else _ld(self_out), _cabi.stream_ptr()), "mlg_gather_sum")
+            0 if self_out is None else _ld(self_out), None if mask is None else _vptr(mask),
+            0 if mask is None else _ld(mask), float(mask_slope), _cabi.stream_ptr()), "mlg_gather_sum")
     return out
 
 
@@ -297,9 +299,13 @@ class SageLayer(torch.autograd.Function):
     aggregation reads the right half of d[x|agg_x] in place and adds the left half."""
 
     @staticmethod
-    def forward(ctx, x, xs, lin_r_w, nn_w, nn_b, topo, relative, slope):
+    def forward(ctx, x, xs, lin_r_w, nn_w, nn_b, topo, relative, slope, in_slope=None, out_premasked=False):
         """x [B*N, Cin] node features -- or, with ``xs`` [B*N] given, x = node_embedding [N, Cin] and the layer
-        input is the rank-1 product xs[b,n] * x[n,:] (MultilevelGNN's first layer, never materialised)."""
+        input is the rank-1 product xs[b,n] * x[n,:] (MultilevelGNN's first layer, never materialised).
+        Activation-backward fusion across layers (set by the model, which knows the layer chain):
+        ``in_slope`` -- x is the output of a (Leaky)ReLU with that slope whose producer expects dL/dz: the returned
+        gradient is multiplied by the activation derivative inside the backward aggregation's epilogue;
+        ``out_premasked`` -- the consumer of y does the same for this layer, so backward takes gy as dL/dz."""
         _cabi.require_cuda(x, lin_r_w, nn_w)
         xd = _f32c(x.detach())
         rank1 = xs is not None
@@ -329,6 +335,10 @@ class SageLayer(torch.autograd.Function):
         ctx.save_for_backward(xcat, y, wbuf, w_r, w_nn, xs_d if rank1 else None)
         ctx.topo, ctx.relative, ctx.slope, ctx.cin, ctx.has_bias = topo, bool(relative), float(slope), cin, nn_b is not None
         ctx.rank1 = rank1
+        ctx.in_slope = None if (in_slope is None or relative or rank1) else float(in_slope)
+        if in_slope is not None and ctx.in_slope is None:
+            raise ValueError("SageLayer: in_slope needs a plain (non-relative, materialised) input")
+        ctx.out_premasked = bool(out_premasked)
         return y
 
     @staticmethod
@@ -337,8 +347,11 @@ class SageLayer(torch.autograd.Function):
         topo, cin = ctx.topo, ctx.cin
         cout = w_nn.shape[0]
         gy = _f32c(gy)
-        gz = torch.ops.aten.leaky_relu_backward(gy, y, ctx.slope, True) if ctx.slope != 0.0 \
-            else torch.ops.aten.threshold_backward(gy, y, 0.0)
+        if ctx.out_premasked:
+            gz = gy          # the consumer already applied this layer's activation derivative
+        else:
+            gz = torch.ops.aten.leaky_relu_backward(gy, y, ctx.slope, True) if ctx.slope != 0.0 \
+                else torch.ops.aten.threshold_backward(gy, y, 0.0)
         needs = ctx.needs_input_grad
         gx = g_wr = g_wnn = g_b = None
         if needs[2] or needs[3] or needs[4]:
@@ -354,7 +367,9 @@ class SageLayer(torch.autograd.Function):
                                 w_split=(wbuf[3].view(2 * cin, cout), wbuf[4].view(2 * cin, cout)))   # [N, 2cin]
             bw = topo.bwd
             gx = gather_sum(gxcat[:, cin:], bw.rowptr, bw.col, topo.n_single, val=topo.bwd_val, pre=topo.inv_cnt,
-                            addend=gxcat[:, :cin], replicas=topo.replicas, order=topo.bwd_order, tag="sage_aggr_bwd")
+                            addend=gxcat[:, :cin], replicas=topo.replicas, order=topo.bwd_order, tag="sage_aggr_bwd",
+                            mask=None if ctx.in_slope is None else xcat[:, :cin],
+                            mask_slope=0.0 if ctx.in_slope is None else ctx.in_slope)
             if ctx.relative:
                 gx = gx - gxcat[:, cin:]
             if ctx.rank1:
@@ -366,7 +381,7 @@ class SageLayer(torch.autograd.Function):
                     _cabi.check(L.mlg_embed_scale_bwd(_cabi.fptr(xs_d), _cabi.fptr(gx), topo.replicas, n1, cin,
                                                       _cabi.fptr(g_emb), _cabi.stream_ptr()), "mlg_embed_scale_bwd")
                 gx = g_emb
-        return gx, None, g_wr, g_wnn, (g_b if ctx.has_bias else None), None, None, None
+        return gx, None, g_wr, g_wnn, (g_b if ctx.has_bias else None), None, None, None, None, None
 
 
 class RankOne:
@@ -426,7 +441,8 @@ class PathwayPool(torch.autograd.Function):
     permute(0,3,1,2) VIEW of the channel-last buffer [B,S,P,C] the kernel writes."""
 
     @staticmethod
-    def forward(ctx, x, w, vm, layout):
+    def forward(ctx, x, w, vm, layout, in_slope=None):
+        """``in_slope``: x is the output of a (Leaky)ReLU with that slope whose producer expects dL/dz (see SageLayer)."""
         L = _cabi.lib()
         _cabi.require_cuda(x, w)
         xd, wd = _f32c(x.detach()), _f32c(w.detach())
@@ -441,6 +457,7 @@ class PathwayPool(torch.autograd.Function):
                                        _cabi.stream_ptr()), "mlg_pool_fwd")
         ctx.save_for_backward(xd, wd)
         ctx.vm, ctx.layout = vm, layout
+        ctx.in_slope = None if in_slope is None else float(in_slope)
         return out_cl.permute(0, 3, 1, 2)
 
     @staticmethod
@@ -460,8 +477,9 @@ class PathwayPool(torch.autograd.Function):
                 _cabi.check(L.mlg_pool_bwd(_cabi.fptr(g_cl), _cabi.fptr(xd), _cabi.fptr(vm, True), _cabi.fptr(wd),
                                            _cabi.iptr(node.rowptr), _cabi.iptr(node.col), _cabi.iptr(lay.seg_of_slot),
                                            B, N, C, G, S, P, lay.replicas, _cabi.fptr(gx), _cabi.fptr(gw), _cabi.fptr(ws),
+                                           0 if ctx.in_slope is None else 1, 0.0 if ctx.in_slope is None else ctx.in_slope,
                                            _cabi.stream_ptr()), "mlg_pool_bwd")
-            return gx, gw, None, None
+            return gx, gw, None, None, None
         with torch.cuda.device(xd.device):
             if ctx.needs_input_grad[0]:
                 gx = torch.empty_like(xd)
@@ -478,4 +496,6 @@ class PathwayPool(torch.autograd.Function):
                                                  _cabi.lptr(lay.match), _cabi.lptr(lay.raw_indice), B, N, C, G, S, P,
                                                  int(lay.wrap_negative), lay.replicas, _cabi.fptr(gw), _cabi.stream_ptr()),
                                 "mlg_pool_bwd_w")
-        return gx, gw, None, None
+        if gx is not None and ctx.in_slope is not None:      # unfused fallback of the activation-derivative mask
+            gx = torch.where(xd > 0, gx, gx * ctx.in_slope)
+        return gx, gw, None, None, None

@@ -99,21 +99,31 @@ class SAGEConv(nn.Module):
         if edge_attr.dim() > 1 and edge_attr.shape[-1] != 1:
             raise NotImplementedError("vector edge weights: only [E] / [E,1] edge_attr is used by the reference")
         slope = self._fused_slope()
+        # cross-layer activation-backward fusion requested by the model for THIS call (see Fn.SageLayer.forward)
+        in_slope, out_premasked = getattr(self, "_mlg_fuse", (None, False))
+        self._mlg_fuse = (None, False)
         n_total = x.shape[0]
         topo = graph.topology(edge_index, n_total, self_loops=True, edge_weight=edge_attr)
         if isinstance(x, Fn.RankOne):
             # x0 = xs * emb consumed in factored form when the whole layer is fused and the batch is replicated
             if slope is not None and topo.replicas > 1 and topo.n_single == x.emb.shape[0]:
                 lin = self.nn[0]
-                return Fn.SageLayer.apply(x.emb, x.xs, self.lin_r.weight, lin.weight, lin.bias, topo, self.relative, slope)
+                return Fn.SageLayer.apply(x.emb, x.xs, self.lin_r.weight, lin.weight, lin.bias, topo, self.relative, slope,
+                                          None, out_premasked)
             x = x.materialize()
         x = x.unsqueeze(-1) if x.dim() == 1 else x
         if slope is not None:
             lin = self.nn[0]
-            return Fn.SageLayer.apply(x, None, self.lin_r.weight, lin.weight, lin.bias, topo, self.relative, slope)
+            return Fn.SageLayer.apply(x, None, self.lin_r.weight, lin.weight, lin.bias, topo, self.relative, slope,
+                                      in_slope, out_premasked)
         agg_x = Fn.SageAggregate.apply(x, topo, self.relative)
         agg = F.linear(agg_x, self.lin_r.weight)
         return self.update(agg, x)
+
+    def grad_fusion_slope(self):
+        """Slope of this layer's output activation if the layer runs as the fused Fn.SageLayer (so that it can take a
+        pre-masked output gradient, and -- when not ``relative`` -- mask its own input gradient); else None."""
+        return self._fused_slope()
 
     def _fused_slope(self):
         """negative slope when ``nn`` is exactly Linear -> ReLU / LeakyReLU (what RSAGEConv builds with
@@ -160,7 +170,17 @@ class GraphConv(nn.Module):
             raise NotImplementedError('conv {} is not implemented'.format(conv))
 
     def forward(self, x, edge_index, edge_attr=None):
+        fuse = self.__dict__.pop("_mlg_fuse", None)     # per-call request from the model, handed to the wrapped conv
+        if fuse is not None:
+            self.gconv._mlg_fuse = fuse
         return self.gconv(x, edge_index, edge_attr=edge_attr)
+
+    def grad_fusion_slope(self):
+        return self.gconv.grad_fusion_slope()
+
+    @property
+    def relative(self):
+        return self.gconv.relative
 
 
 class DynConv(GraphConv):

@@ -17,6 +17,7 @@ from ..gcn_lib.sparse.torch_vertex import GraphConv
 class MultilevelGNN(nn.Module):
     GENES = 5135      # reference hard-codes node_num (multilevel_gnn.py:34)
     SLOTS = 25015     # and the gene-slot count (multilevel_gnn.py:74)
+    FUSE_ACT_BACKWARD = True     # cross-layer activation-backward fusion (see forward); False = one pass per layer
 
     def __init__(self, args, pca_params=None, pathway_indexs=None):
         super().__init__()
@@ -150,7 +151,19 @@ class MultilevelGNN(nn.Module):
                     x = Fn.EmbedScale.apply(xs, self.node_embedding)     # [B*N, emb_dim]
                     if self.input_emb_drop is not None:
                         x = self.input_emb_drop(x)
+            # Activation-backward fusion along a plain layer chain (x_{i+1} = y_i, nothing else reads y_i): the consumer
+            # of y_i multiplies its input gradient by LeakyReLU'(y_i) inside its own backward kernel (it has y_i in
+            # hand), and layer i takes that gradient as dL/dz -- one 3-tensor elementwise pass per layer saved.
+            plain = self.FUSE_ACT_BACKWARD and xs.is_cuda and not args.dense_gnn and not args.resgnn \
+                and not args.repeat_mask and torch.is_grad_enabled()
+            slopes = [getattr(l, "grad_fusion_slope", lambda: None)() if plain else None for l in self.gnn_model]
+            pool_masks = plain and slopes[-1] is not None and (not args.value_att_mask or args.merge_mode == 'mult')
             for i, layer in enumerate(self.gnn_model):
+                if plain and slopes[i] is not None:
+                    consumer_masks = pool_masks if i + 1 == n_layers else \
+                        (slopes[i + 1] is not None and not getattr(self.gnn_model[i + 1], "relative", True))
+                    producer_masked = i > 0 and slopes[i - 1] is not None and not getattr(layer, "relative", True)
+                    layer._mlg_fuse = (slopes[i - 1] if producer_masked else None, bool(consumer_masks))
                 y = layer(x, edge_index, edge_attr)
                 if args.dense_gnn:
                     x = y
@@ -176,7 +189,7 @@ class MultilevelGNN(nn.Module):
             layout = graph.pool_layout(gene_pca_match, raw_indice, n3, 146 * 3,
                                        wrap_negative=not args.pca_match_mask, static_key=static_key)
             w = self.learnable_pca_params * self.info_mask                   # [G, P]
-            x = Fn.PathwayPool.apply(x, w, vm, layout)                       # [B, C, 438, P]
+            x = Fn.PathwayPool.apply(x, w, vm, layout, slopes[-1] if pool_masks else None)   # [B, C, 438, P]
             x = x.reshape(x.shape[0], x.shape[1], 146, self.pca_dim * 3)
             if args.reorder_pathway and self.reorder_idxs is not None:
                 x = x[:, :, self.reorder_idxs.to(x.device), :]

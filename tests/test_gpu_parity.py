@@ -353,7 +353,8 @@ def test_errors_are_loud(mlg):
     with pytest.raises(_cabi.NativeLibraryError):
         conv(torch.randn(4, 8), torch.zeros(2, 3, dtype=torch.long), torch.ones(3, 1))     # CPU tensors: no fallback
     L = _cabi.lib()
-    assert L.mlg_gather_sum(None, 8, None, None, None, None, None, None, 4, 8, 1, 4, 0, 0, 0, None, 0, None, 8, None, 0, None) < 0
+    assert L.mlg_gather_sum(None, 8, None, None, None, None, None, None, 4, 8, 1, 4, 0, 0, 0, None, 0, None, 8, None, 0, None, 0,
+                            0.0, None) < 0
     assert "null" in _cabi.last_error()
 
 
@@ -433,6 +434,42 @@ def test_skinny_linear_and_head_wgrad(mlg):
     torch.nn.functional.linear(x, lin.weight, lin.bias).square().sum().backward()
     assert_close(gx, x.grad, rtol=1e-4, atol=1e-5, what="head dgrad")
     assert_close(gw, lin.weight.grad, rtol=1e-4, atol=1e-5, what="head wgrad (autograd)")
+
+
+def test_activation_backward_fusion_is_equivalent(mlg):
+    """The cross-layer fusion (consumer kernels apply LeakyReLU' of their input; producers take dL/dz) must give the
+    gradients of the unfused chain, and must actually remove the per-layer activation-backward pass."""
+    from multilevel_gnn_b200 import configs, synth
+    args = configs.make_args("gbm")
+    torch.manual_seed(3)
+    model = mlg.MultilevelGNN(args)
+    synth.multilevel_params(model)
+    model.to(DEV).train()
+    model.pathway_indexs = model.pathway_indexs.to(DEV)
+    b = synth.multilevel_batch(batch_size=3, seed=5).to(DEV)
+    params = [p for n, p in model.named_parameters() if p.requires_grad and not n.endswith("lin_l.weight")]
+
+    def grads(fuse):
+        type(model).FUSE_ACT_BACKWARD = fuse
+        torch.manual_seed(11)                     # same dropout masks
+        try:
+            pred, feat = model(b)
+            loss = (pred * torch.arange(pred.numel(), device=DEV).reshape(pred.shape)).sum() + feat.square().mean()
+            with torch.profiler.profile(activities=[torch.profiler.ProfilerActivity.CPU]) as prof:
+                g = torch.autograd.grad(loss, params, allow_unused=True)
+            seen = [e.key for e in prof.key_averages() if "leaky_relu_backward" in e.key]
+        finally:
+            type(model).FUSE_ACT_BACKWARD = True
+        return g, seen
+
+    g1, seen1 = grads(True)
+    g0, seen0 = grads(False)
+    for a, c in zip(g1, g0):
+        if a is None or c is None:
+            assert a is None and c is None
+            continue
+        assert_close(a, c, rtol=1e-5, atol=1e-7, what="fused vs unfused grad")
+    assert len(seen0) >= 1 and len(seen1) == 0, (seen0, seen1)
 
 
 def test_replicated_topology_equals_generic(mlg):
