@@ -27,6 +27,7 @@ __global__ void sage_fold_fwd_kernel(const float* __restrict__ nn_w, const float
   } else {
     v = 0.f;
     const float* w2 = nn_w + (size_t)o * kin + cin;
+#pragma unroll 8
     for (int m = 0; m < r; ++m) v = fmaf(__ldg(w2 + m), __ldg(w_r + (size_t)m * cin + (k - cin)), v);
   }
   const float h = tf32_hi(v);
@@ -52,6 +53,7 @@ __global__ void sage_fold_bwd_kernel(const float* __restrict__ g_wcat, const flo
       v = 0.f;
       const float* ge = g_wcat + (size_t)o * k2 + cin;
       const float* wr = w_r + (size_t)(k - cin) * cin;
+#pragma unroll 8
       for (int j = 0; j < cin; ++j) v = fmaf(__ldg(ge + j), __ldg(wr + j), v);
     }
     g_nn[i] = v;
@@ -59,6 +61,7 @@ __global__ void sage_fold_bwd_kernel(const float* __restrict__ g_wcat, const flo
     const int j = i - n_nn;
     const int m = j / cin, k = j % cin;
     float v = 0.f;
+#pragma unroll 8
     for (int o = 0; o < cout; ++o)
       v = fmaf(__ldg(nn_w + (size_t)o * kin + cin + m), __ldg(g_wcat + (size_t)o * k2 + cin + k), v);
     g_wr[j] = v;
