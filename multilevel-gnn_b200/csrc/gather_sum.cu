@@ -308,6 +308,27 @@ __global__ void __launch_bounds__(kThreads, MLG_GS_MINB) gather_sum_rep_kernel(c
 #pragma unroll
         for (int r = 0; r < RB; ++r)
           if (b0 + r < b_hi) stv<VEC>(rowp(P.out, (unsigned)(b0 + r) * (unsigned)P.n + row, P.ld_out) + c, acc[r], cok);
+      } else if (RANK1 && !P.relative && !P.addend && !P.mask && P.self_out) {
+        // first-layer epilogue: the self row (one embedding row for ALL replicas) and the RB per-replica scalars are
+        // requested together; then 2*RB stores
+        float es[VEC], sc[RB];
+        ldv<VEC>(es, rowp(P.src, row, P.ld_src) + c, cok);
+#pragma unroll
+        for (int r = 0; r < RB; ++r) sc[r] = __ldg(P.pre + (size_t)min(b0 + r, b_hi - 1) * P.rep_rows_pre + row);
+#pragma unroll
+        for (int r = 0; r < RB; ++r) {
+          if (b0 + r < b_hi) {
+            const unsigned orow = (unsigned)(b0 + r) * (unsigned)P.n + row;
+            float xs[VEC];
+#pragma unroll
+            for (int k = 0; k < VEC; ++k) {
+              xs[k] = es[k] * sc[r];
+              acc[r][k] *= postf;
+            }
+            stv<VEC>(rowp(P.self_out, orow, P.ld_self) + c, xs, cok);
+            stv<VEC>(rowp(P.out, orow, P.ld_out) + c, acc[r], cok);
+          }
+        }
       } else {
 #pragma unroll
         for (int r = 0; r < RB; ++r) {
