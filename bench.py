@@ -176,6 +176,45 @@ def genconv_microbench(dev, hbm_peak):
                     "log-sum-exp for backward); traffic = ncu dram bytes per launch (profiles/r01_ncu_full_summaries.md)"}
 
 
+def dominant_kernel_alone(batch, hbm_peak, reps=20):
+    """The dominant kernel (SAGE mean aggregation over the replicated CSR, C=64) timed alone: `reps` back-to-back
+    launches on the bench's own topology, CUDA events on the launching stream.  Besides the HBM fraction it reports the
+    L2 -> SM side, which is what actually bounds a gather over ~7-entry rows: every source row is re-read once per
+    entry, and those reads are served by L2 (full-chip L2 throughput cap measured at ~6300 B/clk,
+    /opt/skills/guides/B300_MICROARCH.md 'LTS throughput cap')."""
+    import multilevel_gnn_b200 as m
+    from multilevel_gnn_b200 import functional as Fn, graph
+    n = batch.x.shape[0]
+    C = 64
+    topo = graph.topology(batch.edge_index, n, self_loops=True, edge_weight=batch.edge_attr,
+                          static_key=getattr(batch, "topology_key", None), period=3 * m.MultilevelGNN.GENES)
+    x = torch.randn(n, C, device=batch.x.device)
+    out = torch.empty_like(x)
+    csr = topo.fwd
+    run = lambda: Fn.gather_sum(x, csr.rowptr, csr.col, topo.n_single, val=topo.fwd_val, post_mode=1, out=out,
+                                replicas=topo.replicas, order=topo.fwd_order, tag="sage_aggr_alone")
+    for _ in range(3):
+        run()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        run()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    nnz = int(csr.col.numel())
+    alg = 8 * C * n + 8 * nnz
+    gathered = 4 * C * nnz * topo.replicas + 4 * C * n          # source rows re-read per entry + rows written
+    sm_mhz = 1965.0
+    l2_cap = 6300.0 * sm_mhz / 1e3                               # GB/s
+    return {"ms": round(ms, 4), "achieved": round(alg / ms / 1e6, 1), "frac": round(alg / ms / 1e6 / hbm_peak, 4),
+            "l2_bytes": gathered, "l2_GBps": round(gathered / ms / 1e6, 1), "l2_cap_GBps": round(l2_cap, 0),
+            "l2_frac": round(gathered / ms / 1e6 / l2_cap, 4),
+            "note": "%d launches back to back, x [%d,%d] fp32 (126 MB) + output, nnz=%d per graph x %d replicas; l2_cap = "
+                    "6300 B/clk x 1965 MHz (guide-measured full-chip LTS cap)" % (reps, n, C, nnz, topo.replicas)}
+
+
 # ----------------------------------------------------------------------------------------------------
 def run_reference(a):
     rank = int(os.environ.get("RANK", "0"))
@@ -314,6 +353,7 @@ def run_b200(a):
                                      "54 % L2 hits), not by DRAM; traffic = ncu dram bytes of one launch at this shape",
                 "timed": "CUDA events around each launch in an eager pass of the same %d steps (the timed region itself "
                          "is a CUDA-graph replay)" % a.steps,
+                "back_to_back": dominant_kernel_alone(resident, hbm_peak),
                 "all_kernels": {k: {"bound": v["bound"], "ms_per_step": round(v["ms"] / a.steps, 4),
                                     "share_of_step": round(v["ms"] / ms_total, 4),
                                     "GBps": round(v["bytes"] / v["ms"] / 1e6, 1) if v["ms"] > 0 and v["bytes"] else None}
