@@ -128,7 +128,14 @@ int mlg_gather_sum(const float* src, int64_t ld_src, const int32_t* rowptr, cons
                    const float* pre, const float* post, const int32_t* order, int64_t n_rows, int64_t C,
                    int64_t replicas, int64_t rep_rows_src, int64_t rep_rows_pre, int post_mode, int relative,
                    const float* addend, int64_t ld_add, float* out, int64_t ld_out, float* self_out,
-                   int64_t ld_self, const float* mask, int64_t ld_mask, float mask_slope, void* stream);
+                   int64_t ld_self, const float* mask, int64_t ld_mask, float mask_slope, const float* reduce_scale,
+                   void* stream);
+/* reduce_scale != NULL (replicated path only): instead of one output row per (replica, row) the kernel writes, per row,
+ * the weighted sum over the replicas of each replica SLICE:  out[s*n_rows + i] = sum_{b in slice s} reduce_scale[b*n_rows + i]
+ * * out_i(b); out must hold mlg_gather_sum_slices(n_rows, C, replicas) * n_rows rows and the caller adds the slices.
+ * This is the gradient of MultilevelGNN's embed-scale prologue (x0 = x * node_embedding, multilevel_gnn.py:150-151)
+ * folded into the first layer's backward aggregation: g_emb[n,:] = sum_b x[b,n] * g_x0[b,n,:]. */
+int64_t mlg_gather_sum_slices(int64_t n_rows, int64_t C, int64_t replicas);
 
 /* ---------------------------------------------------------------------------------------------
  * Tall-skinny transposed product: out[M,K] = A[rows,M]^T * X[rows,K], colsum[M] = sum_r A[r,:] (NULL ok).

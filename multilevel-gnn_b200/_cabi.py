@@ -30,7 +30,8 @@ _SIGNATURES = {
                                   _c_vp, _c_vp, _c_vp, _c_vp]),
     "mlg_gather_sum": (_c_int, [_c_vp, _c_i64, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_i64, _c_i64, _c_i64,
                                 _c_i64, _c_i64, _c_int, _c_int, _c_vp, _c_i64, _c_vp, _c_i64, _c_vp, _c_i64, _c_vp, _c_i64,
-                                _c_f32, _c_vp]),
+                                _c_f32, _c_vp, _c_vp]),
+    "mlg_gather_sum_slices": (_c_i64, [_c_i64, _c_i64, _c_i64]),
     "mlg_xty_workspace_bytes": (_c_i64, [_c_i64, _c_i64, _c_i64]),
     "mlg_xty_tc_supported": (_c_int, [_c_i64, _c_i64, _c_i64]),
     "mlg_xty_tc_workspace_bytes": (_c_i64, [_c_i64]),

@@ -42,6 +42,7 @@ struct GsP {
   const float* pre;
   const float* post;
   const float* addend;
+  const float* red_scale;   // optional [replicas*n]: out[slice*n + row] = sum_{b in slice} red_scale[b*n+row] * result_b (replicated path)
   const float* mask;     // optional: out *= (mask[row, c] > 0 ? 1 : mask_slope)  (activation derivative of the consumer's input)
   const int* order;      // optional row visiting order (heavy rows first, equal degrees together)
   float* out;
@@ -178,7 +179,7 @@ __global__ void __launch_bounds__(kThreads) gather_sum_kernel(const GsP P) {
 // RANK1: every replica reads the SAME src rows and differs only by the per-(replica,row) scalar `pre`
 //        (MultilevelGNN layer 0: x0[b,n,:] = x[b,n] * node_embedding[n,:] is never materialised).
 // ---------------------------------------------------------------------------------------------
-template <int LANES, int VEC, bool RANK1>
+template <int LANES, int VEC, bool RANK1, bool RED = false>
 __global__ void __launch_bounds__(kThreads, MLG_GS_MINB) gather_sum_rep_kernel(const GsP P, int gy) {
   constexpr int RPW = 32 / LANES;
   constexpr int CW = LANES * VEC;
@@ -218,6 +219,9 @@ __global__ void __launch_bounds__(kThreads, MLG_GS_MINB) gather_sum_rep_kernel(c
     const bool cok = c < (unsigned)C;
     const float* sc = P.src + (cok ? c : 0u);   // lanes past C read (and discard) the row start: no predicated loads
     const size_t rep_stride = (size_t)P.rep_rows_src * P.ld_src;
+    float red[VEC];
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) red[k] = 0.f;
     for (int b0 = b_lo; b0 < b_hi; b0 += RB) {
       const int nb = min(RB, b_hi - b0);
       float acc[RB][VEC];
@@ -305,9 +309,18 @@ __global__ void __launch_bounds__(kThreads, MLG_GS_MINB) gather_sum_rep_kernel(c
 #pragma unroll
             for (int k = 0; k < VEC; ++k) acc[r][k] *= t[r][k] > 0.f ? 1.f : P.mask_slope;
         }
+        if (RED) {   // weighted reduction over the replicas instead of one output row per replica
 #pragma unroll
-        for (int r = 0; r < RB; ++r)
-          if (b0 + r < b_hi) stv<VEC>(rowp(P.out, (unsigned)(b0 + r) * (unsigned)P.n + row, P.ld_out) + c, acc[r], cok);
+          for (int r = 0; r < RB; ++r) {
+            const float w = (b0 + r < b_hi) ? __ldg(P.red_scale + (size_t)(b0 + r) * P.n + row) : 0.f;
+#pragma unroll
+            for (int k = 0; k < VEC; ++k) red[k] = fmaf(w, acc[r][k], red[k]);
+          }
+        } else {
+#pragma unroll
+          for (int r = 0; r < RB; ++r)
+            if (b0 + r < b_hi) stv<VEC>(rowp(P.out, (unsigned)(b0 + r) * (unsigned)P.n + row, P.ld_out) + c, acc[r], cok);
+        }
       } else if (RANK1 && !P.relative && !P.addend && !P.mask && P.self_out) {
         // first-layer epilogue: the self row (one embedding row for ALL replicas) and the RB per-replica scalars are
         // requested together; then 2*RB stores
@@ -341,6 +354,7 @@ __global__ void __launch_bounds__(kThreads, MLG_GS_MINB) gather_sum_rep_kernel(c
         }
       }
     }
+    if (RED) stv<VEC>(rowp(P.out, (unsigned)ychunk * (unsigned)P.n + row, P.ld_out) + c, red, cok);
   }
 }
 
@@ -393,14 +407,39 @@ __global__ void embed_scale_bwd_kernel(const float* __restrict__ xs, const float
   g_emb[i] = a;
 }
 
+// replica slices of the replicated path (grid = row blocks x slices; also the number of partial rows per node that
+// the reduce_scale mode writes)
+inline int rep_slices(long long gx, long long replicas) {
+  int gy = 1;
+  static const int cta_target = getenv("MLG_GS_CTAS") ? atoi(getenv("MLG_GS_CTAS")) : 148 * 16;
+  while (gx * gy < cta_target && (replicas / (gy * 2)) >= RB) gy *= 2;
+  return gy;
+}
+
+inline void rep_geometry(int64_t C, bool vec4, int* lanes, int* rows_per_block) {
+  const int wpb = kThreads / 32;
+  *lanes = 32;
+  *rows_per_block = wpb;
+  if (vec4 && C <= 32) { *lanes = 8; *rows_per_block = wpb * 4; }
+  else if (vec4 && C <= 64) { *lanes = 16; *rows_per_block = wpb * 2; }
+}
+
 }  // namespace
+
+extern "C" int64_t mlg_gather_sum_slices(int64_t n_rows, int64_t C, int64_t replicas) {
+  if (replicas <= 1 || n_rows <= 0) return 1;
+  int lanes, rpb;
+  rep_geometry(C, C % 4 == 0, &lanes, &rpb);
+  return rep_slices(mlg_ceil_div(n_rows, rpb), replicas);
+}
 
 extern "C" int mlg_gather_sum(const float* src, int64_t ld_src, const int32_t* rowptr, const int32_t* idx,
                               const float* val, const float* pre, const float* post, const int32_t* order,
                               int64_t n_rows, int64_t C, int64_t replicas, int64_t rep_rows_src,
                               int64_t rep_rows_pre, int post_mode, int relative, const float* addend,
                               int64_t ld_add, float* out, int64_t ld_out, float* self_out, int64_t ld_self,
-                              const float* mask, int64_t ld_mask, float mask_slope, void* stream) {
+                              const float* mask, int64_t ld_mask, float mask_slope, const float* reduce_scale,
+                              void* stream) {
   MLG_CHECK_ARG(src && rowptr && idx && out, "mlg_gather_sum: null src/rowptr/idx/out");
   MLG_CHECK_ARG(n_rows >= 0 && n_rows < (1ll << 31) && C > 0 && C < (1ll << 20),
                 "mlg_gather_sum: bad sizes n_rows=%lld C=%lld", (long long)n_rows, (long long)C);
@@ -421,7 +460,7 @@ extern "C" int mlg_gather_sum(const float* src, int64_t ld_src, const int32_t* r
                     (!mask || (ld_mask % 4 == 0 && (uintptr_t)mask % 16 == 0));
   GsP P;
   P.src = src; P.rowptr = rowptr; P.idx = idx; P.val = val; P.pre = pre; P.post = post; P.addend = addend;
-  P.order = order; P.out = out; P.self_out = self_out; P.mask = mask; P.ld_mask = (unsigned)ld_mask; P.mask_slope = mask_slope;
+  P.order = order; P.out = out; P.self_out = self_out; P.mask = mask; P.ld_mask = (unsigned)ld_mask; P.mask_slope = mask_slope; P.red_scale = reduce_scale;
   P.ld_src = (unsigned)ld_src; P.ld_out = (unsigned)ld_out; P.ld_add = (unsigned)ld_add; P.ld_self = (unsigned)ld_self;
   P.n = (int)n_rows; P.C = (int)C; P.post_mode = post_mode; P.relative = relative;
   P.replicas = (int)replicas; P.rep_rows_src = (unsigned)rep_rows_src; P.rep_rows_pre = (unsigned)rep_rows_pre;
@@ -431,16 +470,18 @@ extern "C" int mlg_gather_sum(const float* src, int64_t ld_src, const int32_t* r
   if (vec4 && C <= 32) { lanes = 8; rows_per_block = wpb * 4; }
   else if (vec4 && C <= 64) { lanes = 16; rows_per_block = wpb * 2; }
   const long long gx = mlg_ceil_div(n_rows, rows_per_block);
+  MLG_CHECK_ARG(!reduce_scale || (replicas > 1 && rep_rows_src > 0 && !relative && !self_out && vec4),
+                "mlg_gather_sum: reduce_scale needs the replicated path (replicas > 1, per-replica src), no relative / "
+                "self_out, and 16-byte aligned operands with C %% 4 == 0");
   if (replicas > 1) {
     // enough blocks for >= 2 waves of 148 SMs x 8 resident blocks; each slice keeps >= RB replicas
-    int gy = 1;
-    static const int cta_target = getenv("MLG_GS_CTAS") ? atoi(getenv("MLG_GS_CTAS")) : 148 * 16;
-    while (gx * gy < cta_target && (replicas / (gy * 2)) >= RB) gy *= 2;
+    const int gy = rep_slices(gx, replicas);
     const bool rank1 = rep_rows_src == 0;
     MLG_CHECK_ARG(rank1 || rep_rows_pre == 0, "mlg_gather_sum: per-replica pre is only supported with rep_rows_src == 0");
     const unsigned grid = (unsigned)(gx * gy);
 #define MLG_REP(L, V)                                                                        \
   if (rank1) gather_sum_rep_kernel<L, V, true><<<grid, kThreads, 0, st>>>(P, gy);            \
+  else if (reduce_scale) gather_sum_rep_kernel<L, V, false, true><<<grid, kThreads, 0, st>>>(P, gy); \
   else gather_sum_rep_kernel<L, V, false><<<grid, kThreads, 0, st>>>(P, gy);
     if (!vec4) { MLG_REP(32, 1) }
     else if (lanes == 8) { MLG_REP(8, 4) }

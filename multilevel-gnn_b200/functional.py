@@ -38,12 +38,15 @@ def _vptr(t):
 
 def gather_sum(src, rowptr, idx, n_rows, val=None, pre=None, post=None, post_mode=0, relative=False, out=None,
                addend=None, self_out=None, replicas=1, order=None, rank1=False, tag="gather_sum", mask=None,
-               mask_slope=0.0):
+               mask_slope=0.0, reduce_scale=None):
     """Raw (non-differentiable) call of mlg_gather_sum.  src / out / addend / self_out may be column
     slices of wider row-major buffers (leading dimension = stride(0))."""
     L = _cabi.lib()
     C = src.shape[1]
     total_rows = n_rows * replicas
+    if reduce_scale is not None:     # per-slice weighted sums over the replicas: [slices * n_rows, C]; caller adds the slices
+        slices = L.mlg_gather_sum_slices(n_rows, C, replicas)
+        out = torch.empty(slices * n_rows, C, dtype=torch.float32, device=src.device)
     if out is None:
         out = torch.empty(total_rows, C, dtype=torch.float32, device=src.device)
     # algorithmic bytes (SURVEY.md section 8d): rows read once + rows written once + (idx, val) per entry
@@ -56,7 +59,8 @@ def gather_sum(src, rowptr, idx, n_rows, val=None, pre=None, post=None, post_mod
             None if addend is None else _vptr(addend), 0 if addend is None else _ld(addend),
             _vptr(out), _ld(out), None if self_out is None else _vptr(self_out),
             0 if self_out is None else _ld(self_out), None if mask is None else _vptr(mask),
-            0 if mask is None else _ld(mask), float(mask_slope), _cabi.stream_ptr()), "mlg_gather_sum")
+            0 if mask is None else _ld(mask), float(mask_slope), _cabi.fptr(reduce_scale, True), _cabi.stream_ptr()),
+            "mlg_gather_sum")
     return out
 
 
@@ -366,6 +370,15 @@ class SageLayer(torch.autograd.Function):
             gxcat = tall_matmul(gz, wcat_t, tag="sage_dgrad_gemm",
                                 w_split=(wbuf[3].view(2 * cin, cout), wbuf[4].view(2 * cin, cout)))   # [N, 2cin]
             bw = topo.bwd
+            if ctx.rank1 and not ctx.relative and topo.replicas > 1 and cin % 4 == 0:
+                # first layer: only g_emb[n,:] = sum_b xs[b,n] * g_x0[b,n,:] is needed, so the backward aggregation reduces
+                # over the replicas in its epilogue (per replica slice; slices added here) and g_x0 is never written
+                n1 = topo.n_single
+                part = gather_sum(gxcat[:, cin:], bw.rowptr, bw.col, n1, val=topo.bwd_val, pre=topo.inv_cnt,
+                                  addend=gxcat[:, :cin], replicas=topo.replicas, order=topo.bwd_order,
+                                  tag="sage_aggr_bwd", reduce_scale=xs_d)
+                g_emb = part.view(-1, n1, cin).sum(0) if part.shape[0] > n1 else part
+                return g_emb, None, g_wr, g_wnn, (g_b if ctx.has_bias else None), None, None, None, None, None
             gx = gather_sum(gxcat[:, cin:], bw.rowptr, bw.col, topo.n_single, val=topo.bwd_val, pre=topo.inv_cnt,
                             addend=gxcat[:, :cin], replicas=topo.replicas, order=topo.bwd_order, tag="sage_aggr_bwd",
                             mask=None if ctx.in_slope is None else xcat[:, :cin],

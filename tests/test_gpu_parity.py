@@ -354,7 +354,7 @@ def test_errors_are_loud(mlg):
         conv(torch.randn(4, 8), torch.zeros(2, 3, dtype=torch.long), torch.ones(3, 1))     # CPU tensors: no fallback
     L = _cabi.lib()
     assert L.mlg_gather_sum(None, 8, None, None, None, None, None, None, 4, 8, 1, 4, 0, 0, 0, None, 0, None, 8, None, 0, None, 0,
-                            0.0, None) < 0
+                            0.0, None, None) < 0
     assert "null" in _cabi.last_error()
 
 
