@@ -64,16 +64,33 @@ def gather_sum(src, rowptr, idx, n_rows, val=None, pre=None, post=None, post_mod
     return out
 
 
+GRAD_SLOTS_ENABLED = False   # set by train.Trainer around its own autograd.grad call only (loss.backward() would add
+                             # the in-place result to .grad a second time)
+
+
+def grad_slot(param, shape):
+    """A preallocated gradient destination for ``param`` if the trainer registered one (train.GradBucket marks its
+    views with ``_mlg_grad_slot``): backward kernels then write the gradient straight into the flat bucket and the
+    bucket's multi-tensor copy skips it.  Each slot is handed out once per backward (a parameter used twice falls back
+    to a fresh buffer and autograd adds the two)."""
+    slot = getattr(param, "_mlg_grad_slot", None) if GRAD_SLOTS_ENABLED else None
+    if slot is None or slot["claimed"] or tuple(slot["view"].shape) != tuple(shape) or not slot["view"].is_contiguous():
+        return None
+    slot["claimed"] = True
+    return slot["view"]
+
+
 XTY_TC_MIN_ROWS = 8192   # below this the SIMT kernel's single launch wins
 
 
-def xty(a, x, want_colsum=False, tag="xty"):
+def xty(a, x, want_colsum=False, tag="xty", out=None):
     """out[M,K] = a[rows,M]^T @ x[rows,K] (+ column sums of a), fp32-accurate and deterministic: mlg_xty_tc (tensor
     cores, 3xTF32) when K == 128 and the shape allows, else mlg_xty (fp32 FMA)."""
     L = _cabi.lib()
     rows, M = a.shape
     K = x.shape[1]
-    out = torch.empty(M, K, dtype=torch.float32, device=a.device)
+    if out is None:
+        out = torch.empty(M, K, dtype=torch.float32, device=a.device)
     cs = torch.empty(M, dtype=torch.float32, device=a.device) if want_colsum else None
     tc = (USE_TF32X3 and rows >= XTY_TC_MIN_ROWS and L.mlg_xty_tc_supported(rows, M, K) and _ld(a) % 4 == 0
           and _ld(x) % 4 == 0 and a.data_ptr() % 16 == 0 and x.data_ptr() % 16 == 0)
@@ -151,7 +168,7 @@ class TallLinear(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             gx = tall_matmul(g, weight.t().contiguous(), tag="linear_dgrad")
         if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
-            gw, gb = xty(g, _f32c(x), want_colsum=ctx.has_bias, tag="linear_wgrad")
+            gw, gb = xty(g, _f32c(x), want_colsum=ctx.has_bias, tag="linear_wgrad", out=grad_slot(weight, weight.shape))
         return gx, gw, (gb if ctx.has_bias else None)
 
 
@@ -339,6 +356,7 @@ class SageLayer(torch.autograd.Function):
         ctx.save_for_backward(xcat, y, wbuf, w_r, w_nn, xs_d if rank1 else None)
         ctx.topo, ctx.relative, ctx.slope, ctx.cin, ctx.has_bias = topo, bool(relative), float(slope), cin, nn_b is not None
         ctx.rank1 = rank1
+        ctx.emb_param = x if (rank1 and isinstance(x, torch.nn.Parameter)) else None
         ctx.in_slope = None if (in_slope is None or relative or rank1) else float(in_slope)
         if in_slope is not None and ctx.in_slope is None:
             raise ValueError("SageLayer: in_slope needs a plain (non-relative, materialised) input")
@@ -377,7 +395,11 @@ class SageLayer(torch.autograd.Function):
                 part = gather_sum(gxcat[:, cin:], bw.rowptr, bw.col, n1, val=topo.bwd_val, pre=topo.inv_cnt,
                                   addend=gxcat[:, :cin], replicas=topo.replicas, order=topo.bwd_order,
                                   tag="sage_aggr_bwd", reduce_scale=xs_d)
-                g_emb = part.view(-1, n1, cin).sum(0) if part.shape[0] > n1 else part
+                slot = grad_slot(ctx.emb_param, (n1, cin)) if ctx.emb_param is not None else None
+                if part.shape[0] > n1:
+                    g_emb = torch.sum(part.view(-1, n1, cin), 0, out=slot) if slot is not None else part.view(-1, n1, cin).sum(0)
+                else:
+                    g_emb = part
                 return g_emb, None, g_wr, g_wnn, (g_b if ctx.has_bias else None), None, None, None, None, None
             gx = gather_sum(gxcat[:, cin:], bw.rowptr, bw.col, topo.n_single, val=topo.bwd_val, pre=topo.inv_cnt,
                             addend=gxcat[:, :cin], replicas=topo.replicas, order=topo.bwd_order, tag="sage_aggr_bwd",

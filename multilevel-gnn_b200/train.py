@@ -37,6 +37,8 @@ class GradBucket:
         off = 0
         for p in self.params:
             p.grad = self.flat[off:off + p.numel()].view_as(p)
+            # backward kernels that produce a whole parameter gradient may write it here directly (functional.grad_slot)
+            p._mlg_grad_slot = {"view": p.grad, "claimed": False}
             off += p.numel()
 
     def zero(self):
@@ -52,9 +54,14 @@ class GradBucket:
             for p, g in zip(self.params, grads):
                 if g is None:
                     p.grad.zero_()
-        dst = [p.grad for p, g in zip(self.params, grads) if g is not None]
-        src = [g for g in grads if g is not None]
-        torch._foreach_copy_(dst, src)
+        dst, src = [], []
+        for p, g in zip(self.params, grads):
+            p._mlg_grad_slot["claimed"] = False
+            if g is not None and g.data_ptr() != p.grad.data_ptr():    # same pointer: written in place by its kernel
+                dst.append(p.grad)
+                src.append(g)
+        if dst:
+            torch._foreach_copy_(dst, src)
 
     def all_reduce(self, world):
         if world <= 1:
@@ -126,7 +133,13 @@ class Trainer:
         self.model.train()
         loss = self.loss(batch)
         # == optimizer.zero_grad(); loss.backward() with the gradients landing in the bucket views (p.grad)
-        self.bucket.store(torch.autograd.grad(loss, self.params, allow_unused=True))
+        from . import functional as Fn
+        Fn.GRAD_SLOTS_ENABLED = loss.is_cuda
+        try:
+            grads = torch.autograd.grad(loss, self.params, allow_unused=True)
+        finally:
+            Fn.GRAD_SLOTS_ENABLED = False
+        self.bucket.store(grads)
         return loss.detach()
 
     def _update(self):
