@@ -81,6 +81,82 @@ pool_fwd_kernel(const float* __restrict__ x, const float* __restrict__ vm, const
   }
 }
 
+// Vector-lane forward for C == 32 * VEC (the shipped widths 32 / 64 / 128): one pass over a segment's slots with
+// 64- / 128-bit row loads, UNP rows in flight per lane (v1 above walks the slot list once per 32-channel chunk with
+// scalar loads).  VecT / ldvec / stvec are defined with the backward kernels below.
+template <int VEC> struct VecF;
+template <> struct VecF<1> { typedef float T; };
+template <> struct VecF<2> { typedef float2 T; };
+template <> struct VecF<4> { typedef float4 T; };
+
+template <int P_, int VEC>
+__global__ void __launch_bounds__(kThreads)
+pool_fwd_vec_kernel(const float* __restrict__ x, const float* __restrict__ vm, const long long* __restrict__ match,
+                    const float* __restrict__ w, const int* __restrict__ rowptr, const int* __restrict__ slots,
+                    int B, int N, int G, int S, int wrap, float* __restrict__ out_cl) {
+  typedef typename VecF<VEC>::T T;
+  constexpr int C = 32 * VEC;
+  const int lane = threadIdx.x & 31;
+  const long long row = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  if (row >= (long long)B * S) return;
+  const int beg = __ldg(rowptr + row), end = __ldg(rowptr + row + 1);
+  const long long BN = (long long)B * N;
+  const float* xc = x + lane * VEC;
+  float acc[P_][VEC];
+#pragma unroll
+  for (int p = 0; p < P_; ++p)
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) acc[p][k] = 0.f;
+  for (int base = beg; base < end; base += 32) {
+    const int q = min(base + lane, end - 1);
+    const int slot = __ldg(slots + q);
+    const int g = slot % G;
+    long long node = __ldg(match + slot);
+    float scale = 1.f;
+    if (node < 0) {
+      if (wrap) node = ((long long)(slot / G) * N + node + BN) % BN;  // python negative index
+      else { node = 0; scale = 0.f; }
+    } else {
+      node += (long long)(slot / G) * N;
+    }
+    if (vm) scale *= __ldg(vm + node);
+    float wl[P_];
+#pragma unroll
+    for (int p = 0; p < P_; ++p) wl[p] = scale * __ldg(w + (size_t)g * P_ + p);
+    const int cnt = min(32, end - base);
+    const int inode = (int)node;
+    for (int j = 0; j < cnt; j += UNP) {
+      T xv[UNP];
+#pragma unroll
+      for (int u = 0; u < UNP; ++u) {
+        const int nj = __shfl_sync(0xffffffffu, inode, min(j + u, cnt - 1));
+        xv[u] = __ldg(reinterpret_cast<const T*>(xc + (size_t)nj * C));
+      }
+#pragma unroll
+      for (int u = 0; u < UNP; ++u) {
+        const bool on = j + u < cnt;
+        const float* xf = reinterpret_cast<const float*>(&xv[u]);
+#pragma unroll
+        for (int p = 0; p < P_; ++p) {
+          float wj = __shfl_sync(0xffffffffu, wl[p], min(j + u, cnt - 1));
+          wj = on ? wj : 0.f;
+#pragma unroll
+          for (int k = 0; k < VEC; ++k) acc[p][k] = fmaf(xf[k], wj, acc[p][k]);
+        }
+      }
+    }
+  }
+  float* o = out_cl + (size_t)row * P_ * C + lane * VEC;
+#pragma unroll
+  for (int p = 0; p < P_; ++p) {
+    T t;
+    float* tf = reinterpret_cast<float*>(&t);
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) tf[k] = acc[p][k];
+    *reinterpret_cast<T*>(o + (size_t)p * C) = t;
+  }
+}
+
 // g_x[b*N + n, c] = vm * sum_{slot -> node n} sum_p w[g,p] * g_cl[b*S + seg(g), p, c]
 // The node-side CSR covers `n_rows` nodes; replicas > 1: one graph's CSR shared by all B graphs
 // (gene_pca_match / raw_indice identical for every patient, multiloader.py:697,81-82).
@@ -487,9 +563,20 @@ extern "C" int mlg_pool_fwd(const float* x, const float* vm, const int64_t* matc
   int rc = check_dims("mlg_pool_fwd", B, N, C, G, S, P);
   if (rc) return rc;
   const int grid = mlg_ceil_div(B * S, kThreads / 32);
-  MLG_P_SWITCH(P, (pool_fwd_kernel<P_><<<grid, kThreads, 0, (cudaStream_t)stream>>>(
-                      x, vm, (const long long*)match, w, seg_rowptr, seg_slot, (int)B, (int)N, (int)C, (int)G,
-                      (int)S, wrap_negative, out_cl)));
+  const bool vec_ok = (C == 32 || C == 64 || C == 128) && (uintptr_t)x % 16 == 0 && (uintptr_t)out_cl % 16 == 0;
+#define MLG_POOL_FV(VV)                                                                                        \
+  MLG_P_SWITCH(P, (pool_fwd_vec_kernel<P_, VV><<<grid, kThreads, 0, (cudaStream_t)stream>>>(                    \
+                      x, vm, (const long long*)match, w, seg_rowptr, seg_slot, (int)B, (int)N, (int)G, (int)S,  \
+                      wrap_negative, out_cl)))
+  if (vec_ok && C == 32) { MLG_POOL_FV(1); }
+  else if (vec_ok && C == 64) { MLG_POOL_FV(2); }
+  else if (vec_ok) { MLG_POOL_FV(4); }
+  else {
+    MLG_P_SWITCH(P, (pool_fwd_kernel<P_><<<grid, kThreads, 0, (cudaStream_t)stream>>>(
+                        x, vm, (const long long*)match, w, seg_rowptr, seg_slot, (int)B, (int)N, (int)C, (int)G,
+                        (int)S, wrap_negative, out_cl)));
+  }
+#undef MLG_POOL_FV
   MLG_CHECK_LAUNCH("mlg_pool_fwd");
   return MLG_OK;
 }
