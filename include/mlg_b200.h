@@ -165,6 +165,15 @@ int mlg_sage_fold_fwd(const float* nn_w, const float* lin_r_w, int64_t cout, int
 int mlg_sage_fold_bwd(const float* g_wcat, const float* nn_w, const float* lin_r_w, int64_t cout, int64_t cin, int64_t r,
                       float* g_nn_w, float* g_lin_r_w, void* stream);
 
+/* Head max-pool over a channel-LAST activation (nn.MaxPool2d((kh, kw)), stride = kernel, floor mode, of
+ * multilevel_gnn.py:286): x_cl [B, H, W, C] in memory -> out_nchw [B, C, H/kh, W/kw] (the order flatten() expects) and the
+ * window position of each maximum (first maximum in row-major scan order, ATen's tie rule).  Backward scatters g_out to
+ * those positions and zero-fills the rest of g_x_cl [B, H, W, C]. */
+int mlg_maxpool_cl_fwd(const float* x_cl, int64_t B, int64_t H, int64_t W, int64_t C, int64_t kh, int64_t kw,
+                       float* out_nchw, uint8_t* argmax, void* stream);
+int mlg_maxpool_cl_bwd(const float* g_out_nchw, const uint8_t* argmax, int64_t B, int64_t H, int64_t W, int64_t C,
+                       int64_t kh, int64_t kw, float* g_x_cl, void* stream);
+
 /* Skinny Linear forward: out[rows,N] = act(x[rows,K] * W[N,K]^T + bias), rows <= 32, any K (long reduction).
  * MultilevelGNN's head Linear(6913 -> 256) on a batch of <= 32 graphs (models/multilevel_gnn.py:104-110): a batched
  * GEMV bound by the one pass over W.  act: 0 none, 1 LeakyReLU(slope) (slope 0 = ReLU).  fp32 FMA, fixed summation

@@ -470,6 +470,46 @@ class EmbedScale(torch.autograd.Function):
         return None, g_emb
 
 
+class MaxPoolCL(torch.autograd.Function):
+    """nn.MaxPool2d((kh, kw)) (stride = kernel, floor mode; multilevel_gnn.py:286) of a [B, C, H, W] tensor whose MEMORY is
+    channel-last (the permuted view the pooled features / 1x1 convs produce): one kernel, NCHW-contiguous output, no
+    layout copy either way (mlg_maxpool_cl_fwd / _bwd)."""
+
+    @staticmethod
+    def forward(ctx, x, kh, kw):
+        L = _cabi.lib()
+        _cabi.require_cuda(x)
+        B, C, H, W = x.shape
+        x_cl = x.detach().permute(0, 2, 3, 1)
+        if not x_cl.is_contiguous() or x.dtype != torch.float32:
+            raise ValueError("MaxPoolCL needs a float32 tensor that is contiguous in channel-last memory order")
+        out = torch.empty(B, C, H // kh, W // kw, dtype=torch.float32, device=x.device)
+        arg = torch.empty(out.shape, dtype=torch.uint8, device=x.device)
+        with torch.cuda.device(x.device):
+            _cabi.check(L.mlg_maxpool_cl_fwd(_cabi.fptr(x_cl), B, H, W, C, kh, kw, _cabi.fptr(out),
+                                             ctypes_ptr(arg), _cabi.stream_ptr()), "mlg_maxpool_cl_fwd")
+        ctx.save_for_backward(arg)
+        ctx.dims = (B, C, H, W, kh, kw)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        L = _cabi.lib()
+        (arg,) = ctx.saved_tensors
+        B, C, H, W, kh, kw = ctx.dims
+        g = _f32c(g)
+        gx_cl = torch.empty(B, H, W, C, dtype=torch.float32, device=g.device)
+        with torch.cuda.device(g.device):
+            _cabi.check(L.mlg_maxpool_cl_bwd(_cabi.fptr(g), ctypes_ptr(arg), B, H, W, C, kh, kw, _cabi.fptr(gx_cl),
+                                             _cabi.stream_ptr()), "mlg_maxpool_cl_bwd")
+        return gx_cl.permute(0, 3, 1, 2), None, None
+
+
+def ctypes_ptr(t):
+    import ctypes
+    return ctypes.c_void_p(t.data_ptr())
+
+
 class PathwayPool(torch.autograd.Function):
     """Gene -> pathway pool (models/multilevel_gnn.py:205-239).
     forward(x [B*N,C], w [G,P] (already * info_mask), vm [B*N] or None, layout) -> [B,C,S,P], returned as the

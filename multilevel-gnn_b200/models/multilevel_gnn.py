@@ -197,7 +197,14 @@ class MultilevelGNN(nn.Module):
         pca_feature = x
         for layer in self.conv_model:
             x = self._conv(layer, x)
-        x = self.pooling(x.contiguous())          # NCHW copy (7 MB): the NHWC max-pool kernels are ~7x slower here
+        pool = self.pooling
+        ks = pool.kernel_size if isinstance(pool.kernel_size, tuple) else (pool.kernel_size,) * 2
+        if (x.is_cuda and x.dtype == torch.float32 and x.permute(0, 2, 3, 1).is_contiguous()
+                and pool.stride in (ks, pool.kernel_size) and pool.padding in (0, (0, 0)) and pool.dilation in (1, (1, 1))
+                and not pool.ceil_mode and not pool.return_indices):
+            x = Fn.MaxPoolCL.apply(x, int(ks[0]), int(ks[1]))     # channel-last in, NCHW out, no layout copies
+        else:
+            x = pool(x.contiguous())          # NCHW copy: the library's NHWC max-pool kernels are ~7x slower here
         x = self.drop1(x)
         x = torch.flatten(x, start_dim=1)
         if args.use_age:

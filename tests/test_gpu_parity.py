@@ -472,6 +472,27 @@ def test_activation_backward_fusion_is_equivalent(mlg):
     assert len(seen0) >= 1 and len(seen1) == 0, (seen0, seen1)
 
 
+def test_maxpool_channel_last_matches_torch(mlg):
+    """mlg_maxpool_cl_fwd/bwd vs nn.MaxPool2d on the head's shape and on ragged ones (floor mode drops the tail rows /
+    columns); ties (quantised values) must route the gradient to the first maximum like ATen."""
+    from multilevel_gnn_b200 import functional as Fn
+    g = torch.Generator().manual_seed(41)
+    for (B, C, H, W, kh, kw), quant in [((32, 64, 146, 6, 4, 2), False), ((3, 32, 146, 6, 4, 2), True),
+                                        ((2, 5, 7, 9, 3, 2), True), ((1, 64, 8, 8, 1, 1), False), ((2, 16, 5, 4, 5, 4), False)]:
+        base = torch.randn(B, H, W, C, generator=g)
+        if quant:
+            base = (base * 2).round() / 2          # many exact ties inside a window
+        x = base.to(DEV).permute(0, 3, 1, 2).requires_grad_(True)          # NCHW view of channel-last memory
+        xr = base.permute(0, 3, 1, 2).contiguous().to(DEV).requires_grad_(True)
+        y = Fn.MaxPoolCL.apply(x, kh, kw)
+        yr = torch.nn.functional.max_pool2d(xr, (kh, kw))
+        assert y.is_contiguous() and torch.equal(y, yr)
+        go = torch.randn(yr.shape, generator=g).to(DEV)
+        (gx,) = torch.autograd.grad(y, x, go)
+        (gr,) = torch.autograd.grad(yr, xr, go)
+        assert torch.equal(gx, gr), (B, C, H, W, kh, kw)
+
+
 def test_replicated_topology_equals_generic(mlg):
     """The B-copies fast path (single-graph CSR streamed over the batch) must agree with the generic CSR."""
     from multilevel_gnn_b200 import functional as Fn, graph, synth
