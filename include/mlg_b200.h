@@ -154,7 +154,9 @@ int mlg_xty(const float* A, int64_t ld_a, const float* X, int64_t ld_x, int64_t 
 int mlg_xty_tc_supported(int64_t rows, int64_t M, int64_t K);
 int64_t mlg_xty_tc_workspace_bytes(int64_t M);
 int mlg_xty_tc(const float* A, int64_t ld_a, const float* X, int64_t ld_x, int64_t rows, int64_t M, int64_t K,
-               float* out, float* colsum, void* workspace, int64_t workspace_bytes, void* stream);
+               float* out, float* colsum, float* colsum_x, void* workspace, int64_t workspace_bytes, void* stream);
+/* (colsum_x [128]: column sums of X, NULL ok -- the bias gradient when the roles of A and X are swapped for a 128-wide
+ *  output, e.g. the weight gradient of Linear(256 -> 128)) */
 
 /* Weight folding of the fused SAGE layer (SAGEConv, torch_vertex.py:279-291: nn(cat[x, mean_j lin_r(x_j)]) with lin_r
  * commuted past the mean).  nn_w = nn.weight [cout, cin + r], lin_r_w = lin_r.weight [r, cin].
@@ -173,6 +175,19 @@ int mlg_maxpool_cl_fwd(const float* x_cl, int64_t B, int64_t H, int64_t W, int64
                        float* out_nchw, uint8_t* argmax, void* stream);
 int mlg_maxpool_cl_bwd(const float* g_out_nchw, const uint8_t* argmax, int64_t B, int64_t H, int64_t W, int64_t C,
                        int64_t kh, int64_t kw, float* g_x_cl, void* stream);
+
+/* LayerNorm over the channel axis of a tall [rows, C] fp32 activation (nn.LayerNorm(C), biased variance): DeeperGCN's
+ * res+ block norm (models/deepergcn.py:262-275) and the norm inside GENConv's MLP (gcn_lib/sparse/torch_nn.py:55-73).
+ * C in {128, 256, 384, 512}; gamma / beta may be NULL (= 1 / 0).  fwd also writes the per-row mean and 1/std that bwd
+ * reads; bwd writes the input gradient and (fixed summation order) the gamma / beta gradients (either may be NULL).
+ * workspace >= mlg_layernorm_bwd_workspace_bytes(rows, C). */
+int mlg_layernorm_supported(int64_t C);
+int64_t mlg_layernorm_bwd_workspace_bytes(int64_t rows, int64_t C);
+int mlg_layernorm_fwd(const float* x, const float* gamma, const float* beta, int64_t rows, int64_t C, float eps, float* y,
+                      float* mean, float* rstd, void* stream);
+int mlg_layernorm_bwd(const float* x, const float* g, const float* gamma, const float* mean, const float* rstd,
+                      int64_t rows, int64_t C, float* gx, float* dgamma, float* dbeta, void* workspace,
+                      int64_t workspace_bytes, void* stream);
 
 /* Skinny Linear forward: out[rows,N] = act(x[rows,K] * W[N,K]^T + bias), rows <= 32, any K (long reduction).
  * MultilevelGNN's head Linear(6913 -> 256) on a batch of <= 32 graphs (models/multilevel_gnn.py:104-110): a batched

@@ -35,7 +35,7 @@ _SIGNATURES = {
     "mlg_xty_workspace_bytes": (_c_i64, [_c_i64, _c_i64, _c_i64]),
     "mlg_xty_tc_supported": (_c_int, [_c_i64, _c_i64, _c_i64]),
     "mlg_xty_tc_workspace_bytes": (_c_i64, [_c_i64]),
-    "mlg_xty_tc": (_c_int, [_c_vp, _c_i64, _c_vp, _c_i64, _c_i64, _c_i64, _c_i64, _c_vp, _c_vp, _c_vp, _c_i64, _c_vp]),
+    "mlg_xty_tc": (_c_int, [_c_vp, _c_i64, _c_vp, _c_i64, _c_i64, _c_i64, _c_i64, _c_vp, _c_vp, _c_vp, _c_vp, _c_i64, _c_vp]),
     "mlg_skinny_linear_workspace_bytes": (_c_i64, [_c_i64, _c_i64]),
     "mlg_skinny_linear": (_c_int, [_c_vp, _c_i64, _c_vp, _c_i64, _c_vp, _c_i64, _c_i64, _c_i64, _c_int, _c_f32, _c_vp,
                                    _c_i64, _c_vp, _c_i64, _c_vp]),
@@ -43,6 +43,11 @@ _SIGNATURES = {
     "mlg_sage_fold_bwd": (_c_int, [_c_vp, _c_vp, _c_vp, _c_i64, _c_i64, _c_i64, _c_vp, _c_vp, _c_vp]),
     "mlg_maxpool_cl_fwd": (_c_int, [_c_vp, _c_i64, _c_i64, _c_i64, _c_i64, _c_i64, _c_i64, _c_vp, _c_vp, _c_vp]),
     "mlg_maxpool_cl_bwd": (_c_int, [_c_vp, _c_vp, _c_i64, _c_i64, _c_i64, _c_i64, _c_i64, _c_i64, _c_vp, _c_vp]),
+    "mlg_layernorm_supported": (_c_int, [_c_i64]),
+    "mlg_layernorm_bwd_workspace_bytes": (_c_i64, [_c_i64, _c_i64]),
+    "mlg_layernorm_fwd": (_c_int, [_c_vp, _c_vp, _c_vp, _c_i64, _c_i64, _c_f32, _c_vp, _c_vp, _c_vp, _c_vp]),
+    "mlg_layernorm_bwd": (_c_int, [_c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_i64, _c_i64, _c_vp, _c_vp, _c_vp, _c_vp, _c_i64,
+                                   _c_vp]),
     "mlg_xty": (_c_int, [_c_vp, _c_i64, _c_vp, _c_i64, _c_i64, _c_i64, _c_i64, _c_vp, _c_vp, _c_vp, _c_i64, _c_vp]),
     "mlg_bias_act": (_c_int, [_c_vp, _c_vp, _c_i64, _c_i64, _c_f32, _c_vp]),
     "mlg_embed_scale_fwd": (_c_int, [_c_vp, _c_vp, _c_i64, _c_i64, _c_i64, _c_vp, _c_vp]),
@@ -101,7 +106,7 @@ def last_error():
 
 
 # kernels launched per C call (own kernels only; CUB's sort passes inside mlg_csr_build are not counted)
-_LAUNCHES_PER_CALL = {"mlg_csr_build": 2, "mlg_knn_graph": 2, "mlg_xty": 2, "mlg_xty_tc": 2, "mlg_skinny_linear": 2, "mlg_pool_bwd": 2, "mlg_adam_step": 2}
+_LAUNCHES_PER_CALL = {"mlg_csr_build": 2, "mlg_knn_graph": 2, "mlg_xty": 2, "mlg_xty_tc": 2, "mlg_skinny_linear": 2, "mlg_layernorm_bwd": 2, "mlg_pool_bwd": 2, "mlg_adam_step": 2}
 LAUNCH_COUNT = 0
 TIMER = None        # a KernelTimer while bench.py measures per-kernel device time
 

@@ -20,7 +20,10 @@
 namespace {
 
 constexpr int kThreads = 256;
-constexpr int UN = 4;   // entries in flight (single-graph path)
+#ifndef MLG_GS_UN
+#define MLG_GS_UN 4
+#endif
+constexpr int UN = MLG_GS_UN;   // entries in flight (single-graph path)
 #ifndef MLG_GS_RB
 #define MLG_GS_RB 4
 #endif

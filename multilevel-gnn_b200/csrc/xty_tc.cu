@@ -97,6 +97,7 @@ struct CtlX {
   unsigned long long full_raw[kMaxRaw], empty_raw[kMaxRaw], full_split[kSplit], empty_split[kSplit], tmem_full;
   unsigned tmem_base;
   float csum[2][KX];
+  float csum_x[2][KX];
 };
 
 // shared memory: raw ring   n_raw x [X chunk 32 x 128 fp32 = 16 KB][G chunk 32 x N fp32]      (TMA -> splitter)
@@ -137,6 +138,7 @@ xty_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const unsigned tmem = S.tmem_base;
+  const size_t stride_p = (size_t)KX * N + N + KX;   // per-CTA partial: D [128 x N], colsum(A) [N], colsum(X) [128]
   const int my_chunks = blockIdx.x < n_chunks ? (n_chunks - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
 
   if (warp == 0) {
@@ -176,7 +178,7 @@ xty_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
     }
   } else if (warp >= 4 && warp < 8) {  // ===== epilogue: this CTA's partial D -> workspace =====
     const int q = warp & 3;
-    float* prow = partial + (size_t)blockIdx.x * (KX * N + N) + (size_t)(q * 32 + lane) * N;
+    float* prow = partial + (size_t)blockIdx.x * stride_p + (size_t)(q * 32 + lane) * N;
     if (my_chunks > 0) {
       mbar_wait(&S.tmem_full, 0);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -202,7 +204,7 @@ xty_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
     const int wg = (warp - 8) >> 2;
     const int t = (threadIdx.x - 256) & 127;   // column of X; column of G when t < N
     const unsigned swz = (unsigned)(t & 7);
-    float csum = 0.f;
+    float csum = 0.f, csum_x = 0.f;
     for (int i = wg; i < my_chunks; i += 2) {
       const int s = i % n_raw, q = i % kSplit;
       mbar_wait(&S.full_raw[s], (i / n_raw) & 1);
@@ -213,6 +215,10 @@ xty_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
       float xv[CH], gv[CH];
 #pragma unroll
       for (int r = 0; r < CH; ++r) xv[r] = lds32(xr + (unsigned)(r * KX * 4));
+      if (want_colsum & 2) {
+#pragma unroll
+        for (int r = 0; r < CH; r += 4) csum_x += (xv[r] + xv[r + 1]) + (xv[r + 2] + xv[r + 3]);
+      }
       if (t < N) {
 #pragma unroll
         for (int r = 0; r < CH; ++r) gv[r] = lds32(gr + (unsigned)(r * N * 4));
@@ -249,25 +255,30 @@ xty_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
       mbar_arrive(&S.full_split[q]);
     }
     S.csum[wg][t] = csum;
+    S.csum_x[wg][t] = csum_x;
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (want_colsum && (int)threadIdx.x < N)
-    partial[(size_t)blockIdx.x * (KX * N + N) + (size_t)KX * N + threadIdx.x] = S.csum[0][threadIdx.x] + S.csum[1][threadIdx.x];
+  if ((want_colsum & 1) && (int)threadIdx.x < N)
+    partial[(size_t)blockIdx.x * stride_p + (size_t)KX * N + threadIdx.x] = S.csum[0][threadIdx.x] + S.csum[1][threadIdx.x];
+  if ((want_colsum & 2) && (int)threadIdx.x >= 128 && (int)threadIdx.x < 128 + KX)
+    partial[(size_t)blockIdx.x * stride_p + (size_t)KX * N + N + (threadIdx.x - 128)] =
+        S.csum_x[0][threadIdx.x - 128] + S.csum_x[1][threadIdx.x - 128];
   if (warp == 2) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(tmem_cols) : "memory");
   }
 }
 
-// out[n][m] = sum_c partial[c][m*N + n]  (transposing), colsum[n] = sum_c partial[c][128*N + n]; 8 lanes per element
+// out[n][m] = sum_c partial[c][m*N + n]  (transposing), colsum[n] = sum_c partial[c][128*N + n],
+// colsum_x[m] = sum_c partial[c][128*N + N + m]; 8 lanes per element
 __global__ void xty_tc_reduce_kernel(const float* __restrict__ partial, int n_part, int N, float* __restrict__ out,
-                                     float* __restrict__ colsum) {
+                                     float* __restrict__ colsum, float* __restrict__ colsum_x) {
   const long long tix = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   const long long i = tix >> 3;
   const int sub = (int)(tix & 7);
-  const long long total = (long long)KX * N + (colsum ? N : 0);
-  const long long stride = (long long)KX * N + N;
+  const long long total = (long long)KX * N + N + KX;
+  const long long stride = total;
   float s = 0.f;
   long long src = 0;
   if (i < total) {
@@ -277,14 +288,17 @@ __global__ void xty_tc_reduce_kernel(const float* __restrict__ partial, int n_pa
     } else {
       src = i;
     }
-    for (int g = sub; g < n_part; g += 8) s += partial[(size_t)g * stride + src];
+    const bool wanted = i < (long long)KX * N || (i < (long long)KX * N + N ? colsum != nullptr : colsum_x != nullptr);
+    if (wanted)
+      for (int g = sub; g < n_part; g += 8) s += partial[(size_t)g * stride + src];
   }
   s += __shfl_down_sync(0xffffffffu, s, 4, 8);
   s += __shfl_down_sync(0xffffffffu, s, 2, 8);
   s += __shfl_down_sync(0xffffffffu, s, 1, 8);
   if (sub != 0 || i >= total) return;
   if (i < (long long)KX * N) out[i] = s;
-  else colsum[i - (long long)KX * N] = s;
+  else if (i < (long long)KX * N + N) { if (colsum) colsum[i - (long long)KX * N] = s; }
+  else if (colsum_x) colsum_x[i - (long long)KX * N - N] = s;
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -338,11 +352,12 @@ extern "C" int mlg_xty_tc_supported(int64_t rows, int64_t M, int64_t K) {
   return rows >= 1 && K == KX && M >= 16 && M <= 128 && M % 16 == 0 && plan((int)M, &nr, &rb, &sb);
 }
 
-extern "C" int64_t mlg_xty_tc_workspace_bytes(int64_t M) { return (int64_t)148 * 2 * (KX * M + M) * 4; }
+extern "C" int64_t mlg_xty_tc_workspace_bytes(int64_t M) { return (int64_t)148 * 2 * (KX * M + M + KX) * 4; }
 
-// out[M, 128] = A[rows, M]^T . X[rows, 128], colsum[M] = column sums of A (NULL ok)
+// out[M, 128] = A[rows, M]^T . X[rows, 128], colsum[M] = column sums of A, colsum_x[128] = column sums of X (NULL ok)
 extern "C" int mlg_xty_tc(const float* A, int64_t ld_a, const float* X, int64_t ld_x, int64_t rows, int64_t M, int64_t K,
-                          float* out, float* colsum, void* workspace, int64_t workspace_bytes, void* stream) {
+                          float* out, float* colsum, float* colsum_x, void* workspace, int64_t workspace_bytes,
+                          void* stream) {
   MLG_CHECK_ARG(A && X && out && workspace, "mlg_xty_tc: null pointer");
   MLG_CHECK_ARG(mlg_xty_tc_supported(rows, M, K), "mlg_xty_tc: unsupported shape (need K == 128, 16 <= M <= 128, M %% 16 == 0)");
   MLG_CHECK_ARG(ld_a % 4 == 0 && ld_x % 4 == 0 && (uintptr_t)A % 16 == 0 && (uintptr_t)X % 16 == 0 && rows < (1ll << 31),
@@ -352,7 +367,7 @@ extern "C" int mlg_xty_tc(const float* A, int64_t ld_a, const float* X, int64_t 
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int n_chunks = (int)((rows + CH - 1) / CH);
   const int grid = n_chunks < sms ? n_chunks : sms;
-  MLG_CHECK_ARG(workspace_bytes >= (int64_t)grid * (KX * M + M) * 4, "mlg_xty_tc: workspace too small");
+  MLG_CHECK_ARG(workspace_bytes >= (int64_t)grid * (KX * M + M + KX) * 4, "mlg_xty_tc: workspace too small");
   CUtensorMap mx, mg;
   int rc = make_map_rowmajor(&mx, X, KX, rows, ld_x);
   if (rc) return rc;
@@ -370,10 +385,11 @@ extern "C" int mlg_xty_tc(const float* A, int64_t ld_a, const float* X, int64_t 
   }
   cudaStream_t st = (cudaStream_t)stream;
   xty_tc_kernel<<<grid, kThreads, smem, st>>>(mx, mg, rows, (int)M, n_raw, raw_bytes, split_bytes, tmem_cols, (float*)workspace,
-                                             colsum ? 1 : 0);
+                                             (colsum ? 1 : 0) | (colsum_x ? 2 : 0));
   MLG_CHECK_LAUNCH("mlg_xty_tc");
-  const long long total = (long long)KX * M + (colsum ? M : 0);
-  xty_tc_reduce_kernel<<<mlg_ceil_div(total * 8, 256), 256, 0, st>>>((const float*)workspace, grid, (int)M, out, colsum);
+  const long long total = (long long)KX * M + M + KX;
+  xty_tc_reduce_kernel<<<mlg_ceil_div(total * 8, 256), 256, 0, st>>>((const float*)workspace, grid, (int)M, out, colsum,
+                                                                     colsum_x);
   MLG_CHECK_LAUNCH("mlg_xty_tc(reduce)");
   return MLG_OK;
 }

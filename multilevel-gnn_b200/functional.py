@@ -83,23 +83,51 @@ def grad_slot(param, shape):
 XTY_TC_MIN_ROWS = 8192   # below this the SIMT kernel's single launch wins
 
 
+def _xty_tc_call(L, a, x, out, cs, cs_x, tag):
+    rows, M = a.shape
+    ws_bytes = L.mlg_xty_tc_workspace_bytes(M)
+    ws = torch.empty(ws_bytes // 4, dtype=torch.float32, device=a.device)
+    with torch.cuda.device(a.device), _cabi.span(tag + "_tc", 4 * rows * (M + 128)):
+        _cabi.check(L.mlg_xty_tc(_vptr(a), _ld(a), _vptr(x), _ld(x), rows, M, 128, _cabi.fptr(out), _cabi.fptr(cs, True),
+                                 _cabi.fptr(cs_x, True), _cabi.fptr(ws), ws_bytes, _cabi.stream_ptr()), "mlg_xty_tc")
+
+
 def xty(a, x, want_colsum=False, tag="xty", out=None):
-    """out[M,K] = a[rows,M]^T @ x[rows,K] (+ column sums of a), fp32-accurate and deterministic: mlg_xty_tc (tensor
-    cores, 3xTF32) when K == 128 and the shape allows, else mlg_xty (fp32 FMA)."""
+    """out[M,K] = a[rows,M]^T @ x[rows,K] (+ column sums of a), fp32-accurate and deterministic.  Tensor cores
+    (mlg_xty_tc, 3xTF32) when one side is 128 wide: K == 128 directly (M in chunks of <= 128 columns), or M == 128 with
+    K a multiple of 128 by computing the transpose (roles swapped, the bias gradient then comes from the kernel's
+    X-column sums); else mlg_xty (fp32 FMA)."""
     L = _cabi.lib()
     rows, M = a.shape
     K = x.shape[1]
+    aligned = (_ld(a) % 4 == 0 and _ld(x) % 4 == 0 and a.data_ptr() % 16 == 0 and x.data_ptr() % 16 == 0)
+    if USE_TF32X3 and rows >= XTY_TC_MIN_ROWS and aligned:
+        if K == 128 and M % 16 == 0 and (M <= 128 or M % 128 == 0):
+            if out is None:
+                out = torch.empty(M, K, dtype=torch.float32, device=a.device)
+            cs = torch.empty(M, dtype=torch.float32, device=a.device) if want_colsum else None
+            step = min(M, 128)
+            for m0 in range(0, M, step):
+                _xty_tc_call(L, a[:, m0:m0 + step], x, out[m0:m0 + step], None if cs is None else cs[m0:m0 + step], None, tag)
+            return out, cs
+        if M == 128 and K % 128 == 0 and K > 128:
+            out_t = torch.empty(K, M, dtype=torch.float32, device=a.device)       # (x^T a) = out^T
+            cs = torch.empty(M, dtype=torch.float32, device=a.device) if want_colsum else None
+            for k0 in range(0, K, 128):
+                _xty_tc_call(L, x[:, k0:k0 + 128], a, out_t[k0:k0 + 128], None, cs if k0 == 0 else None, tag)
+            res = out_t.t()
+            if out is not None:
+                out.copy_(res)
+                return out, cs
+            return res.contiguous(), cs
     if out is None:
         out = torch.empty(M, K, dtype=torch.float32, device=a.device)
     cs = torch.empty(M, dtype=torch.float32, device=a.device) if want_colsum else None
-    tc = (USE_TF32X3 and rows >= XTY_TC_MIN_ROWS and L.mlg_xty_tc_supported(rows, M, K) and _ld(a) % 4 == 0
-          and _ld(x) % 4 == 0 and a.data_ptr() % 16 == 0 and x.data_ptr() % 16 == 0)
-    ws_bytes = L.mlg_xty_tc_workspace_bytes(M) if tc else L.mlg_xty_workspace_bytes(rows, M, K)
+    ws_bytes = L.mlg_xty_workspace_bytes(rows, M, K)
     ws = torch.empty(ws_bytes // 4, dtype=torch.float32, device=a.device)
-    with torch.cuda.device(a.device), _cabi.span(tag + ("_tc" if tc else ""), 4 * rows * (M + K)):
-        fn, name = (L.mlg_xty_tc, "mlg_xty_tc") if tc else (L.mlg_xty, "mlg_xty")
-        _cabi.check(fn(_vptr(a), _ld(a), _vptr(x), _ld(x), rows, M, K, _cabi.fptr(out), _cabi.fptr(cs, True),
-                       _cabi.fptr(ws), ws_bytes, _cabi.stream_ptr()), name)
+    with torch.cuda.device(a.device), _cabi.span(tag, 4 * rows * (M + K)):
+        _cabi.check(L.mlg_xty(_vptr(a), _ld(a), _vptr(x), _ld(x), rows, M, K, _cabi.fptr(out), _cabi.fptr(cs, True),
+                              _cabi.fptr(ws), ws_bytes, _cabi.stream_ptr()), "mlg_xty")
     return out, cs
 
 
@@ -112,8 +140,26 @@ def tall_matmul(a, w, bias=None, act=0, slope=0.0, tag="gemm_tf32x3", w_split=No
     L = _cabi.lib()
     M, K = a.shape
     N = w.shape[0]
-    if (USE_TF32X3 and a.is_cuda and a.stride(1) == 1 and a.stride(0) % 4 == 0 and a.data_ptr() % 16 == 0
-            and L.mlg_gemm_tf32x3_supported(M, N, K)):
+    tc_ok = USE_TF32X3 and a.is_cuda and a.stride(1) == 1 and a.stride(0) % 4 == 0 and a.data_ptr() % 16 == 0
+    if (tc_ok and w_split is None and not L.mlg_gemm_tf32x3_supported(M, N, K) and N > 128 and N % 128 == 0
+            and L.mlg_gemm_tf32x3_supported(M, 128, K)):
+        # the split weight of a 128-column slice fits in shared memory, the full width does not (e.g. 128 -> 256):
+        # one launch per 128 output columns, each writing its column slice of the output in place
+        out = torch.empty(M, N, dtype=torch.float32, device=a.device)
+        wd = _f32c(w)
+        hi, lo = torch.empty_like(wd), torch.empty_like(wd)
+        bd = None if bias is None else _f32c(bias)
+        with torch.cuda.device(a.device):
+            _cabi.check(L.mlg_split_tf32(_cabi.fptr(wd), wd.numel(), _cabi.fptr(hi), _cabi.fptr(lo), _cabi.stream_ptr()),
+                        "mlg_split_tf32")
+            for n0 in range(0, N, 128):
+                with _cabi.span(tag, 4 * M * (K + 128)):
+                    _cabi.check(L.mlg_gemm_tf32x3(_vptr(a), a.stride(0), _cabi.fptr(hi[n0:n0 + 128]), _cabi.fptr(lo[n0:n0 + 128]),
+                                                  None if bd is None else _cabi.fptr(bd[n0:n0 + 128]),
+                                                  _vptr(out[:, n0:n0 + 128]), N, M, 128, K, int(act), float(slope),
+                                                  _cabi.stream_ptr()), "mlg_gemm_tf32x3")
+        return out
+    if (tc_ok and L.mlg_gemm_tf32x3_supported(M, N, K)):
         out = torch.empty(M, N, dtype=torch.float32, device=a.device)
         with torch.cuda.device(a.device):
             if w_split is not None:
@@ -468,6 +514,57 @@ class EmbedScale(torch.autograd.Function):
             _cabi.check(L.mlg_embed_scale_bwd(_cabi.fptr(xs_d), _cabi.fptr(g), B, N, C, _cabi.fptr(g_emb),
                                               _cabi.stream_ptr()), "mlg_embed_scale_bwd")
         return None, g_emb
+
+
+class LayerNormFn(torch.autograd.Function):
+    """nn.LayerNorm over the last axis of a tall [rows, C] fp32 tensor (mlg_layernorm_fwd / _bwd): one warp per row,
+    input gradient and gamma / beta gradients in one backward pass."""
+
+    MIN_ROWS = 4096
+
+    @staticmethod
+    def supported(x, normalized_shape):
+        return (x.is_cuda and x.dtype == torch.float32 and x.dim() == 2 and len(normalized_shape) == 1
+                and x.shape[1] == normalized_shape[0] and x.shape[0] >= LayerNormFn.MIN_ROWS
+                and bool(_cabi.lib().mlg_layernorm_supported(x.shape[1])))
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, eps):
+        L = _cabi.lib()
+        xd = _f32c(x.detach())
+        rows, C = xd.shape
+        y = torch.empty_like(xd)
+        mean = torch.empty(rows, dtype=torch.float32, device=xd.device)
+        rstd = torch.empty(rows, dtype=torch.float32, device=xd.device)
+        wd = None if weight is None else _f32c(weight.detach())
+        bd = None if bias is None else _f32c(bias.detach())
+        with torch.cuda.device(xd.device), _cabi.span("layernorm_fwd", 8 * rows * C):
+            _cabi.check(L.mlg_layernorm_fwd(_cabi.fptr(xd), _cabi.fptr(wd, True), _cabi.fptr(bd, True), rows, C, float(eps),
+                                            _cabi.fptr(y), _cabi.fptr(mean), _cabi.fptr(rstd), _cabi.stream_ptr()),
+                        "mlg_layernorm_fwd")
+        ctx.save_for_backward(xd, wd, mean, rstd)
+        ctx.has_w, ctx.has_b = weight is not None, bias is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        L = _cabi.lib()
+        xd, wd, mean, rstd = ctx.saved_tensors
+        rows, C = xd.shape
+        g = _f32c(g)
+        gx = torch.empty_like(xd)
+        need_w = ctx.has_w and ctx.needs_input_grad[1]
+        need_b = ctx.has_b and ctx.needs_input_grad[2]
+        dgam = torch.empty(C, dtype=torch.float32, device=xd.device) if need_w else None
+        dbet = torch.empty(C, dtype=torch.float32, device=xd.device) if need_b else None
+        ws_bytes = L.mlg_layernorm_bwd_workspace_bytes(rows, C)
+        ws = torch.empty(ws_bytes // 4, dtype=torch.float32, device=xd.device)
+        with torch.cuda.device(xd.device), _cabi.span("layernorm_bwd", 12 * rows * C):
+            _cabi.check(L.mlg_layernorm_bwd(_cabi.fptr(xd), _cabi.fptr(g), _cabi.fptr(wd, True), _cabi.fptr(mean),
+                                            _cabi.fptr(rstd), rows, C, _cabi.fptr(gx), _cabi.fptr(dgam, True),
+                                            _cabi.fptr(dbet, True), _cabi.fptr(ws), ws_bytes, _cabi.stream_ptr()),
+                        "mlg_layernorm_bwd")
+        return gx, dgam, dbet, None
 
 
 class MaxPoolCL(torch.autograd.Function):

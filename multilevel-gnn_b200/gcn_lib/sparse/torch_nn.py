@@ -2,6 +2,7 @@
 (models/gcn_lib/sparse/torch_nn.py:9-75), so state_dict keys such as ``gconv.nn.0.weight`` and
 ``feature_encoder.{0,1,3}.*`` are unchanged.  These stay torch modules (cuBLAS / ATen): SURVEY.md
 section 2 row 4 keeps them as "next" epilogue-fusion candidates."""
+import torch
 from torch import nn
 
 _ACTS = {
@@ -20,12 +21,23 @@ def act_layer(act_type, inplace=False, neg_slope=0.2, n_prelu=1):
     return _ACTS[key](neg_slope, n_prelu)
 
 
+class LayerNorm(nn.LayerNorm):
+    """nn.LayerNorm (same parameters / state_dict keys); tall fp32 CUDA inputs go through mlg_layernorm_fwd / _bwd
+    (functional.LayerNormFn), anything else through the library."""
+
+    def forward(self, x):
+        from ... import functional as Fn
+        if Fn.LayerNormFn.supported(x, self.normalized_shape):
+            return Fn.LayerNormFn.apply(x, self.weight, self.bias, self.eps)
+        return super().forward(x)
+
+
 def norm_layer(norm_type, nc):
     key = norm_type.lower()
     if key == 'batch':
         return nn.BatchNorm1d(nc, affine=True)
     if key == 'layer':
-        return nn.LayerNorm(nc, elementwise_affine=True)
+        return LayerNorm(nc, elementwise_affine=True)
     if key == 'instance':
         return nn.InstanceNorm1d(nc, affine=False)
     raise NotImplementedError('normalization layer [%s] is not found' % key)
@@ -49,3 +61,15 @@ class MLP(nn.Sequential):
                 layers.append(nn.Dropout2d(drop))
         self.m = layers
         super().__init__(*layers)
+
+    def forward(self, x):
+        """Same chain as nn.Sequential; the Linears of a TALL CUDA input (node / edge rows) go through
+        functional.tall_linear: 3xTF32 tensor-core forward and dX where the shape allows, tensor-core / fp32-FMA weight and
+        bias gradient instead of the library's split-K SIMT GEMM + separate bias reductions."""
+        from ... import functional as Fn
+        for mod in self:
+            if isinstance(mod, nn.Linear) and torch.is_tensor(x) and x.is_cuda and x.dim() == 2:
+                x = Fn.tall_linear(x, mod)
+            else:
+                x = mod(x)
+        return x

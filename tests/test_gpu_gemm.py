@@ -103,3 +103,22 @@ def test_gemm_tf32x3_is_fp32_accurate(shape):
     big = torch.randn(M, 2 * K, generator=g).to(DEV)
     out3 = Fn.tall_matmul(big[:, :K], w)
     assert_close(out3, (big[:, :K].double() @ w.double().t()).float(), rtol=2e-5, atol=2e-5, what="strided A")
+
+
+@pytest.mark.gpu
+def test_tall_matmul_splits_wide_outputs():
+    """N = 256 with K = 128 does not fit the resident split weight: two 128-column launches writing column slices."""
+    from multilevel_gnn_b200 import functional as Fn, _cabi
+    g = torch.Generator().manual_seed(77)
+    M, K, N = 100146, 128, 256
+    a = torch.randn(M, K, generator=g).to(DEV)
+    w = torch.randn(N, K, generator=g).to(DEV)
+    b = torch.randn(N, generator=g).to(DEV)
+    assert not _cabi.lib().mlg_gemm_tf32x3_supported(M, N, K) and _cabi.lib().mlg_gemm_tf32x3_supported(M, 128, K)
+    _cabi.TIMER = _cabi.KernelTimer()
+    out = Fn.tall_matmul(a, w, b, act=1, slope=0.0, tag="wide")
+    launches = _cabi.TIMER.summary()["wide"]["launches"]
+    _cabi.TIMER = None
+    assert launches == 2
+    ref = torch.relu(a.double() @ w.double().t() + b.double()).float()
+    assert_close(out, ref, rtol=2e-5, atol=2e-5, what="wide tall_matmul")

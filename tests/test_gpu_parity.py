@@ -403,6 +403,21 @@ def test_xty_tensor_core_matches_fp64(mlg):
     ref = big[:, :64].double().t() @ big[:, 128:].double()
     assert ((out.double() - ref).abs().max() / ref.abs().max()).item() < 1e-5
     assert not L.mlg_xty_tc_supported(1000, 64, 64) and not L.mlg_xty_tc_supported(1000, 20, 128)
+    # wider problems through the same kernel: M in 128-column chunks, and K > 128 with the roles swapped (the bias
+    # gradient then comes from the kernel's X-column sums) -- the node-side MLP Linears 128 -> 256 and 256 -> 128
+    for rows, M, K in [(100146, 256, 128), (100146, 128, 256), (9000, 128, 384)]:
+        a = torch.randn(rows, M, generator=g).to(DEV)
+        x = torch.randn(rows, K, generator=g).to(DEV)
+        Fn._cabi.TIMER = Fn._cabi.KernelTimer()
+        out, cs = Fn.xty(a, x, want_colsum=True)
+        tags = set(Fn._cabi.TIMER.summary())
+        Fn._cabi.TIMER = None
+        assert all(t.endswith("_tc") for t in tags), tags
+        ref = a.double().t() @ x.double()
+        scale = a.double().abs().t() @ x.double().abs()
+        assert out.shape == (M, K) and out.is_contiguous()
+        assert ((out.double() - ref).abs() / scale).max().item() < 4e-6, (rows, M, K)
+        assert_close(cs, a.double().sum(0).float(), rtol=1e-5, atol=2e-3, what="colsum wide")
 
 
 def test_skinny_linear_and_head_wgrad(mlg):
@@ -491,6 +506,38 @@ def test_maxpool_channel_last_matches_torch(mlg):
         (gx,) = torch.autograd.grad(y, x, go)
         (gr,) = torch.autograd.grad(yr, xr, go)
         assert torch.equal(gx, gr), (B, C, H, W, kh, kw)
+
+
+def test_layernorm_matches_torch(mlg):
+    """mlg_layernorm_fwd/bwd (functional.LayerNormFn) vs torch layer_norm in fp64: output, input gradient, gamma / beta
+    gradients; ragged row counts; deterministic; module wrapper falls back for unsupported widths."""
+    from multilevel_gnn_b200 import functional as Fn
+    from multilevel_gnn_b200.gcn_lib.sparse.torch_nn import norm_layer
+    g = torch.Generator().manual_seed(51)
+    for rows, C in [(100146, 128), (100146, 256), (4097, 384), (5000, 512)]:
+        x = (torch.randn(rows, C, generator=g) * 2 + 0.7).to(DEV).requires_grad_(True)
+        w = (torch.rand(C, generator=g) + 0.5).to(DEV).requires_grad_(True)
+        b = torch.randn(C, generator=g).to(DEV).requires_grad_(True)
+        go = torch.randn(rows, C, generator=g).to(DEV)
+        y = Fn.LayerNormFn.apply(x, w, b, 1e-5)
+        gx, gw, gb = torch.autograd.grad(y, [x, w, b], go)
+        xd, wd, bd = x.detach().double().requires_grad_(True), w.detach().double().requires_grad_(True), b.detach().double().requires_grad_(True)
+        yr = torch.nn.functional.layer_norm(xd, (C,), wd, bd, 1e-5)
+        rx, rw, rb = torch.autograd.grad(yr, [xd, wd, bd], go.double())
+        assert_close(y, yr.float(), rtol=1e-5, atol=1e-5, what="ln y")
+        assert_close(gx, rx.float(), rtol=1e-4, atol=1e-5, what="ln gx")
+        assert_close(gw, rw.float(), rtol=1e-4, atol=2e-3, what="ln dgamma")
+        assert_close(gb, rb.float(), rtol=1e-4, atol=2e-3, what="ln dbeta")
+        y2 = Fn.LayerNormFn.apply(x, w, b, 1e-5)
+        g2 = torch.autograd.grad(y2, [x, w, b], go)
+        assert torch.equal(y, y2) and all(torch.equal(a, c) for a, c in zip((gx, gw, gb), g2))
+    ln = norm_layer("layer", 256).to(DEV)
+    assert type(ln).__mro__[1] is torch.nn.LayerNorm and set(ln.state_dict()) == {"weight", "bias"}
+    xs = torch.randn(10, 256, device=DEV)                     # too few rows: library path
+    assert_close(ln(xs), torch.nn.functional.layer_norm(xs, (256,), ln.weight, ln.bias, ln.eps), what="ln small")
+    ln96 = norm_layer("layer", 96).to(DEV)                    # unsupported width: library path
+    xw = torch.randn(5000, 96, device=DEV)
+    assert_close(ln96(xw), torch.nn.functional.layer_norm(xw, (96,), ln96.weight, ln96.bias, ln96.eps), what="ln 96")
 
 
 def test_replicated_topology_equals_generic(mlg):
