@@ -114,15 +114,35 @@ ln_bwd_kernel(const float* __restrict__ x, const float* __restrict__ g, const fl
   }
 }
 
-__global__ void ln_param_reduce_kernel(const float* __restrict__ partial, int n_part, int C2, float* __restrict__ dgamma,
-                                       float* __restrict__ dbeta) {
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= C2) return;
-  float s = 0.f;
-  for (int p = 0; p < n_part; ++p) s += partial[(size_t)p * C2 + j];
-  const int C = C2 / 2;
-  if (j < C) { if (dgamma) dgamma[j] = s; }
-  else if (dbeta) dbeta[j - C] = s;
+// one block per 32 columns of the [2C] partial rows: lane = column, the 8 warps split the partials (coalesced 128-byte
+// reads, 4 in flight), then a warp-ordered sum through shared memory (fixed order: deterministic)
+__global__ void __launch_bounds__(256)
+ln_param_reduce_kernel(const float* __restrict__ partial, int n_part, int C2, float* __restrict__ dgamma,
+                       float* __restrict__ dbeta) {
+  __shared__ float sm[8][32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int j = blockIdx.x * 32 + lane;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  if (j < C2) {
+    int p = w;
+    for (; p + 24 < n_part; p += 32) {
+      s0 += partial[(size_t)p * C2 + j];
+      s1 += partial[(size_t)(p + 8) * C2 + j];
+      s2 += partial[(size_t)(p + 16) * C2 + j];
+      s3 += partial[(size_t)(p + 24) * C2 + j];
+    }
+    for (; p < n_part; p += 8) s0 += partial[(size_t)p * C2 + j];
+  }
+  sm[w][lane] = (s0 + s1) + (s2 + s3);
+  __syncthreads();
+  if (w == 0 && j < C2) {
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += sm[k][lane];
+    const int C = C2 / 2;
+    if (j < C) { if (dgamma) dgamma[j] = s; }
+    else if (dbeta) dbeta[j - C] = s;
+  }
 }
 
 inline int bwd_blocks(long long rows) {
@@ -183,7 +203,7 @@ extern "C" int mlg_layernorm_bwd(const float* x, const float* g, const float* ga
   }
   MLG_CHECK_LAUNCH("mlg_layernorm_bwd");
   if (dgamma || dbeta) {
-    ln_param_reduce_kernel<<<(unsigned)mlg_ceil_div(2 * C, 256), 256, 0, st>>>(part, grid, (int)(2 * C), dgamma, dbeta);
+    ln_param_reduce_kernel<<<(unsigned)mlg_ceil_div(2 * C, 32), 256, 0, st>>>(part, grid, (int)(2 * C), dgamma, dbeta);
     MLG_CHECK_LAUNCH("mlg_layernorm_bwd(reduce)");
   }
   return MLG_OK;

@@ -141,10 +141,15 @@ def tall_matmul(a, w, bias=None, act=0, slope=0.0, tag="gemm_tf32x3", w_split=No
     M, K = a.shape
     N = w.shape[0]
     tc_ok = USE_TF32X3 and a.is_cuda and a.stride(1) == 1 and a.stride(0) % 4 == 0 and a.data_ptr() % 16 == 0
-    if (tc_ok and w_split is None and not L.mlg_gemm_tf32x3_supported(M, N, K) and N > 128 and N % 128 == 0
-            and L.mlg_gemm_tf32x3_supported(M, 128, K)):
-        # the split weight of a 128-column slice fits in shared memory, the full width does not (e.g. 128 -> 256):
-        # one launch per 128 output columns, each writing its column slice of the output in place
+    chunk = 0
+    if tc_ok and w_split is None and not L.mlg_gemm_tf32x3_supported(M, N, K):
+        for c in (128, 64):
+            if N > c and N % c == 0 and L.mlg_gemm_tf32x3_supported(M, c, K):
+                chunk = c
+                break
+    if chunk:
+        # the split weight of a column slice fits in shared memory, the full width does not (128 -> 256 in two 128-column
+        # launches, 256 -> 128 in two 64-column launches): each launch writes its column slice of the output in place
         out = torch.empty(M, N, dtype=torch.float32, device=a.device)
         wd = _f32c(w)
         hi, lo = torch.empty_like(wd), torch.empty_like(wd)
@@ -152,11 +157,12 @@ def tall_matmul(a, w, bias=None, act=0, slope=0.0, tag="gemm_tf32x3", w_split=No
         with torch.cuda.device(a.device):
             _cabi.check(L.mlg_split_tf32(_cabi.fptr(wd), wd.numel(), _cabi.fptr(hi), _cabi.fptr(lo), _cabi.stream_ptr()),
                         "mlg_split_tf32")
-            for n0 in range(0, N, 128):
-                with _cabi.span(tag, 4 * M * (K + 128)):
-                    _cabi.check(L.mlg_gemm_tf32x3(_vptr(a), a.stride(0), _cabi.fptr(hi[n0:n0 + 128]), _cabi.fptr(lo[n0:n0 + 128]),
-                                                  None if bd is None else _cabi.fptr(bd[n0:n0 + 128]),
-                                                  _vptr(out[:, n0:n0 + 128]), N, M, 128, K, int(act), float(slope),
+            for n0 in range(0, N, chunk):
+                with _cabi.span(tag, 4 * M * (K + chunk)):
+                    _cabi.check(L.mlg_gemm_tf32x3(_vptr(a), a.stride(0), _cabi.fptr(hi[n0:n0 + chunk]),
+                                                  _cabi.fptr(lo[n0:n0 + chunk]),
+                                                  None if bd is None else _cabi.fptr(bd[n0:n0 + chunk]),
+                                                  _vptr(out[:, n0:n0 + chunk]), N, M, chunk, K, int(act), float(slope),
                                                   _cabi.stream_ptr()), "mlg_gemm_tf32x3")
         return out
     if (tc_ok and L.mlg_gemm_tf32x3_supported(M, N, K)):

@@ -122,3 +122,9 @@ def test_tall_matmul_splits_wide_outputs():
     assert launches == 2
     ref = torch.relu(a.double() @ w.double().t() + b.double()).float()
     assert_close(out, ref, rtol=2e-5, atol=2e-5, what="wide tall_matmul")
+    # K = 256 -> N = 128: two 64-column launches
+    a2 = torch.randn(M, 256, generator=g).to(DEV)
+    w2 = torch.randn(128, 256, generator=g).to(DEV)
+    assert not _cabi.lib().mlg_gemm_tf32x3_supported(M, 128, 256) and _cabi.lib().mlg_gemm_tf32x3_supported(M, 64, 256)
+    out2 = Fn.tall_matmul(a2, w2, b[:128])
+    assert_close(out2, (a2.double() @ w2.double().t() + b[:128].double()).float(), rtol=2e-5, atol=4e-5, what="K=256 tall_matmul")
