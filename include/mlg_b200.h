@@ -189,6 +189,28 @@ int mlg_layernorm_bwd(const float* x, const float* g, const float* gamma, const 
                       int64_t rows, int64_t C, float* gx, float* dgamma, float* dbeta, void* workspace,
                       int64_t workspace_bytes, void* stream);
 
+/* GENConv aggregation with a rank-1 AFFINE edge term: message_ij = relu(x_j + a_e * p + q) + eps, a_e = edge_scalar[e]
+ * (one number per edge), p = edge_p, q = edge_q ([H]).  Same semantics, epilogues and outputs as mlg_gen_aggr_fwd / _bwd
+ * with e_ij = a_e * p + q, but the [E, H] edge embedding is never read or written: this is DeeperGCN's edge path when
+ * the raw edge attribute is a scalar weight -- Linear(1 -> H) (models/deepergcn.py:209) followed by each GENConv's own
+ * Linear(H -> H) edge encoder (gcn_lib/sparse/torch_vertex.py:76-77) is affine in a_e.  g_edge [E, H] (gradient w.r.t.
+ * the edge term, original edge order) is still produced: the source-side pass (mlg_gather_sum over the by-source CSR)
+ * and mlg_wcolsum (g_p = sum_e a_e g_edge[e], g_q = sum_e g_edge[e]) consume it. */
+int mlg_gen_aggr_fwd_affine(const float* x, const float* edge_scalar, const float* edge_p, const float* edge_q,
+                            const int32_t* rowptr, const int32_t* col, const int32_t* eid, int64_t n, int64_t H, int mode,
+                            float t, const float* t_dev, float p, const float* p_dev, const float* y_dev, float eps,
+                            int epilogue, const float* msg_scale_dev, float* m, float* aux, float* h, void* stream);
+int mlg_gen_aggr_bwd_affine(const float* g, const float* x, const float* edge_scalar, const float* edge_p,
+                            const float* edge_q, const int32_t* rowptr, const int32_t* col, const int32_t* eid, int64_t n,
+                            int64_t H, int mode, int learn, float t, const float* t_dev, float p, const float* p_dev,
+                            const float* y_dev, float eps, int epilogue, const float* msg_scale_dev, const float* m,
+                            const float* aux, float* g_edge, float* g_x, float* partials, void* stream);
+/* Weighted column sums of a tall matrix: u[c] = sum_r a[r] * G[r,c] (u NULL ok), v[c] = sum_r G[r,c] (v NULL ok); one
+ * streaming pass, fixed summation order.  C % 4 == 0, C <= 1024.  workspace >= mlg_wcolsum_workspace_bytes(rows, C). */
+int64_t mlg_wcolsum_workspace_bytes(int64_t rows, int64_t C);
+int mlg_wcolsum(const float* G, int64_t ld, const float* a, int64_t rows, int64_t C, float* u, float* v, void* workspace,
+                int64_t workspace_bytes, void* stream);
+
 /* Skinny Linear forward: out[rows,N] = act(x[rows,K] * W[N,K]^T + bias), rows <= 32, any K (long reduction).
  * MultilevelGNN's head Linear(6913 -> 256) on a batch of <= 32 graphs (models/multilevel_gnn.py:104-110): a batched
  * GEMV bound by the one pass over W.  act: 0 none, 1 LeakyReLU(slope) (slope 0 = ReLU).  fp32 FMA, fixed summation

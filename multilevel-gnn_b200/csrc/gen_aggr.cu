@@ -30,6 +30,9 @@ namespace {
 struct GenP {
   const float* x;
   const float* e;
+  const float* ea;   // S_XA: per-edge scalar a_e [E] ...
+  const float* ep;   // ... and the vectors p, q [H]: edge term e_ij = a_e * p + q (never materialised)
+  const float* eq;
   const int* rowptr;
   const int* col;
   const int* eid;
@@ -61,7 +64,8 @@ constexpr float kLazy = 24.f;  // log2 head-room before the running max is refre
 // kernel families
 constexpr int K_SOFTMAX = 0, K_POWER = 1, K_SIMPLE = 2;  // SIMPLE: add / mean / max chosen at run time
 // message sources
-constexpr int S_XE = 0, S_X = 1, S_RAW = 2;  // relu(x_j + e) + eps | relu(x_j) + eps | e (given messages)
+constexpr int S_XE = 0, S_X = 1, S_RAW = 2, S_XA = 3;  // relu(x_j + e) + eps | relu(x_j) + eps | e (given messages) |
+                                                        // relu(x_j + a_e * p + q) + eps (rank-1 affine edge term)
 
 template <int VEC>
 struct Vec {
@@ -115,7 +119,7 @@ template <int LANES, int VEC, int KIND, int SRC, bool FULL>
 __global__ void __launch_bounds__(kThreads, MLG_GEN_FWD_MIN_BLOCKS) gen_fwd_kernel(const GenP P) {
   constexpr int RPW = 32 / LANES;
   constexpr int CW = LANES * VEC;  // channels per chunk
-  constexpr bool HAS_X = SRC != S_RAW, HAS_E = SRC != S_X, RAW = SRC == S_RAW;
+  constexpr bool HAS_X = SRC != S_RAW, HAS_E = (SRC == S_XE || SRC == S_RAW), RAW = SRC == S_RAW, AFF = SRC == S_XA;
   const int lane = threadIdx.x & 31;
   const int sub = lane / LANES, sl = lane % LANES;
   const unsigned gmask = (LANES == 32) ? 0xffffffffu : (((1u << LANES) - 1u) << (sub * LANES));
@@ -136,7 +140,7 @@ __global__ void __launch_bounds__(kThreads, MLG_GEN_FWD_MIN_BLOCKS) gen_fwd_kern
   const int nchunks = (H + CW - 1) / CW;
   const float* xrow = HAS_X ? row_ptr(P.x, (unsigned)row, H) : nullptr;
   float* mrow = row_ptr(P.m, (unsigned)row, H);
-  const bool has_eid = HAS_E && P.eid != nullptr;
+  const bool has_eid = (HAS_E || AFF) && P.eid != nullptr;
 
   float sx2 = 0.f, sm2 = 0.f;
   Vec<VEC> out, xi;
@@ -148,6 +152,11 @@ __global__ void __launch_bounds__(kThreads, MLG_GEN_FWD_MIN_BLOCKS) gen_fwd_kern
     const bool cok = FULL || c < H;
     const float* xc = HAS_X ? P.x + c : nullptr;
     const float* ec = HAS_E ? P.e + c : nullptr;
+    Vec<VEC> pv, qv;
+    if (AFF) {
+      pv = ld_g<VEC, FULL>(P.ep + c, cok);
+      qv = ld_g<VEC, FULL>(P.eq + c, cok);
+    }
     float a0[VEC], a1[VEC], a2[VEC];
 #pragma unroll
     for (int k = 0; k < VEC; ++k) {
@@ -159,6 +168,7 @@ __global__ void __launch_bounds__(kThreads, MLG_GEN_FWD_MIN_BLOCKS) gen_fwd_kern
       const int q = min(base + sl, end - 1);
       const unsigned my_col = HAS_X ? (unsigned)__ldg(P.col + q) : 0u;
       const unsigned my_e = has_eid ? (unsigned)__ldg(P.eid + q) : (unsigned)q;  // identity if pre-sorted
+      const float my_a = AFF ? __ldg(P.ea + my_e) : 0.f;
       const int cnt = min(LANES, end - base);
       // NE edges per step: all 2*NE row loads are issued before any is consumed
       auto step = [&](auto ne_tag, int j) {
@@ -169,6 +179,11 @@ __global__ void __launch_bounds__(kThreads, MLG_GEN_FWD_MIN_BLOCKS) gen_fwd_kern
           if (HAS_X) {
             const unsigned s = __shfl_sync(gmask, my_col, j + u, LANES);
             xv[u] = ld_g<VEC, FULL>(row_ptr(xc, s, H), cok);
+          }
+          if (AFF) {
+            const float a = __shfl_sync(gmask, my_a, j + u, LANES);
+#pragma unroll
+            for (int k = 0; k < VEC; ++k) ev[u].v[k] = fmaf(a, pv.v[k], qv.v[k]);
           }
           if (HAS_E) {
             const unsigned ee = __shfl_sync(gmask, my_e, j + u, LANES);
@@ -183,7 +198,7 @@ __global__ void __launch_bounds__(kThreads, MLG_GEN_FWD_MIN_BLOCKS) gen_fwd_kern
             if (RAW) {
               v[k] = ev[u].v[k];
             } else {
-              const float pre = HAS_E ? xv[u].v[k] + ev[u].v[k] : xv[u].v[k];
+              const float pre = (HAS_E || AFF) ? xv[u].v[k] + ev[u].v[k] : xv[u].v[k];
               v[k] = fmaxf(pre, 0.f) + eps;
             }
           }
@@ -312,7 +327,7 @@ template <int LANES, int VEC, int KIND, int SRC, bool FULL>
 __global__ void __launch_bounds__(kThreads) gen_bwd_kernel(const GenP P) {
   constexpr int RPW = 32 / LANES;
   constexpr int CW = LANES * VEC;
-  constexpr bool HAS_X = SRC != S_RAW, HAS_E = SRC != S_X, RAW = SRC == S_RAW;
+  constexpr bool HAS_X = SRC != S_RAW, HAS_E = (SRC == S_XE || SRC == S_RAW), RAW = SRC == S_RAW, AFF = SRC == S_XA;
   __shared__ float red[3 * 32];
   const int lane = threadIdx.x & 31;
   const int sub = lane / LANES, sl = lane % LANES;
@@ -380,6 +395,11 @@ __global__ void __launch_bounds__(kThreads) gen_bwd_kernel(const GenP P) {
       const bool cok = FULL || c < H;
       const float* xc = HAS_X ? P.x + c : nullptr;
       const float* ec = HAS_E ? P.e + c : nullptr;
+      Vec<VEC> pv, qv;
+      if (AFF) {
+        pv = ld_g<VEC, FULL>(P.ep + c, cok);
+        qv = ld_g<VEC, FULL>(P.eq + c, cok);
+      }
       float* gec = P.g_edge + c;
       Vec<VEC> gr = ld_g<VEC, FULL>(grow + c, cok);
       Vec<VEC> mr = ld_g<VEC, FULL>(mrow + c, cok);
@@ -432,6 +452,7 @@ __global__ void __launch_bounds__(kThreads) gen_bwd_kernel(const GenP P) {
         const int q = min(base + sl, end - 1);
         const unsigned my_col = HAS_X ? (unsigned)__ldg(P.col + q) : 0u;
         const unsigned my_e = has_eid ? (unsigned)__ldg(P.eid + q) : (unsigned)q;
+        const float my_a = AFF ? __ldg(P.ea + my_e) : 0.f;
         const int cnt = min(LANES, end - base);
         auto step = [&](auto ne_tag, int j) {
           constexpr int NE = decltype(ne_tag)::value;
@@ -440,6 +461,11 @@ __global__ void __launch_bounds__(kThreads) gen_bwd_kernel(const GenP P) {
 #pragma unroll
           for (int u = 0; u < NE; ++u) {
             eo[u] = __shfl_sync(gmask, my_e, j + u, LANES);
+            if (AFF) {
+              const float a = __shfl_sync(gmask, my_a, j + u, LANES);
+#pragma unroll
+              for (int k = 0; k < VEC; ++k) ev[u].v[k] = fmaf(a, pv.v[k], qv.v[k]);
+            }
             if (HAS_X) {
               const unsigned s = __shfl_sync(gmask, my_col, j + u, LANES);
               xv[u] = ld_g<VEC, FULL>(row_ptr(xc, s, H), cok);
@@ -455,7 +481,7 @@ __global__ void __launch_bounds__(kThreads) gen_bwd_kernel(const GenP P) {
               if (RAW) {
                 pre = v = ev[u].v[k];
               } else {
-                pre = HAS_E ? xv[u].v[k] + ev[u].v[k] : xv[u].v[k];
+                pre = (HAS_E || AFF) ? xv[u].v[k] + ev[u].v[k] : xv[u].v[k];
                 v = fmaxf(pre, 0.f) + eps;
               }
               float gv;
@@ -751,7 +777,7 @@ void launch_cfg(const GenP& P, const Cfg& c, cudaStream_t st) {
 template <bool FWD>
 int dispatch(const GenP& P, cudaStream_t st) {
   const Cfg c = pick_cfg(P.H);
-  const int src = P.x == nullptr ? S_RAW : (P.e != nullptr ? S_XE : S_X);
+  const int src = P.x == nullptr ? S_RAW : (P.e != nullptr ? S_XE : (P.ea != nullptr ? S_XA : S_X));
   int kind;
   switch (P.mode) {
     case MLG_AGGR_SOFTMAX: kind = K_SOFTMAX; break;
@@ -764,6 +790,7 @@ int dispatch(const GenP& P, cudaStream_t st) {
 #define MLG_SRC(K)                                                    \
   if (src == S_XE) launch_cfg<FWD, K, S_XE>(P, c, st);                \
   else if (src == S_X) launch_cfg<FWD, K, S_X>(P, c, st);             \
+  else if (src == S_XA) launch_cfg<FWD, K, S_XA>(P, c, st);           \
   else launch_cfg<FWD, K, S_RAW>(P, c, st);
   if (kind == K_SOFTMAX) { MLG_SRC(K_SOFTMAX) }
   else if (kind == K_POWER) { MLG_SRC(K_POWER) }
@@ -861,5 +888,63 @@ extern "C" int mlg_gen_aggr_bwd(const float* g, const float* x, const float* e, 
   rc = dispatch<false>(P, (cudaStream_t)stream);
   if (rc) return rc;
   MLG_CHECK_LAUNCH("mlg_gen_aggr_bwd");
+  return MLG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Rank-1 affine edge term: e_ij = a_e * p + q with a per-edge SCALAR a_e and two H-vectors.  This is what DeeperGCN's
+// edge path produces when the raw edge attribute is one number per edge (the reference's weighted gene graph,
+// dataloader/multiloader.py): edge_encoder = Linear(1 -> H) followed by every GENConv's own Linear(H -> H)
+// (models/deepergcn.py:209, gcn_lib/sparse/torch_vertex.py:76-77) is affine in a_e, so the [E, H] edge embedding -- and
+// its per-layer GEMM, its gradient GEMMs and the [E, H] gradient accumulation across layers -- never have to exist.
+// Forward reads x rows only; backward writes g_edge (= d loss / d e_ij, the source-side pass needs it) and the caller
+// reduces it to g_p = sum_e a_e * g_edge[e], g_q = sum_e g_edge[e].
+// ------------------------------------------------------------------------------------------------
+extern "C" int mlg_gen_aggr_fwd_affine(const float* x, const float* edge_scalar, const float* edge_p, const float* edge_q,
+                                       const int32_t* rowptr, const int32_t* col, const int32_t* eid, int64_t n, int64_t H,
+                                       int mode, float t, const float* t_dev, float p, const float* p_dev,
+                                       const float* y_dev, float eps, int epilogue, const float* msg_scale_dev, float* m,
+                                       float* aux, float* h, void* stream) {
+  MLG_CHECK_ARG(x && edge_scalar && edge_p && edge_q, "mlg_gen_aggr_fwd_affine: null x / edge_scalar / edge_p / edge_q");
+  int rc = check_common("mlg_gen_aggr_fwd_affine", x, nullptr, rowptr, col, n, H, epilogue, msg_scale_dev);
+  if (rc) return rc;
+  MLG_CHECK_ARG(epilogue == MLG_EPI_NONE || h, "mlg_gen_aggr_fwd_affine: epilogue needs h");
+  MLG_CHECK_ARG(m, "mlg_gen_aggr_fwd_affine: m is required");
+  if (n == 0) return MLG_OK;
+  GenP P;
+  memset(&P, 0, sizeof(P));
+  P.x = x; P.ea = edge_scalar; P.ep = edge_p; P.eq = edge_q; P.rowptr = rowptr; P.col = col; P.eid = eid;
+  P.n = (int)n; P.H = (unsigned)H; P.mode = mode; P.epi = epilogue;
+  P.t = t; P.p = p; P.eps = eps; P.t_dev = t_dev; P.p_dev = p_dev; P.y_dev = y_dev;
+  P.scale_dev = msg_scale_dev; P.m = m; P.aux = aux; P.h = h;
+  rc = dispatch<true>(P, (cudaStream_t)stream);
+  if (rc) return rc;
+  MLG_CHECK_LAUNCH("mlg_gen_aggr_fwd_affine");
+  return MLG_OK;
+}
+
+extern "C" int mlg_gen_aggr_bwd_affine(const float* g, const float* x, const float* edge_scalar, const float* edge_p,
+                                       const float* edge_q, const int32_t* rowptr, const int32_t* col, const int32_t* eid,
+                                       int64_t n, int64_t H, int mode, int learn, float t, const float* t_dev, float p,
+                                       const float* p_dev, const float* y_dev, float eps, int epilogue,
+                                       const float* msg_scale_dev, const float* m, const float* aux, float* g_edge,
+                                       float* g_x, float* partials, void* stream) {
+  MLG_CHECK_ARG(x && edge_scalar && edge_p && edge_q, "mlg_gen_aggr_bwd_affine: null x / edge_scalar / edge_p / edge_q");
+  int rc = check_common("mlg_gen_aggr_bwd_affine", x, nullptr, rowptr, col, n, H, epilogue, msg_scale_dev);
+  if (rc) return rc;
+  MLG_CHECK_ARG(g && m && g_edge && g_x && partials, "mlg_gen_aggr_bwd_affine: null g/m/g_edge/g_x/partials");
+  MLG_CHECK_ARG(aux || (mode != MLG_AGGR_SOFTMAX && mode != MLG_AGGR_POWER),
+                "mlg_gen_aggr_bwd_affine: softmax/power backward needs aux from the forward");
+  if (n == 0) return MLG_OK;
+  GenP P;
+  memset(&P, 0, sizeof(P));
+  P.x = x; P.ea = edge_scalar; P.ep = edge_p; P.eq = edge_q; P.rowptr = rowptr; P.col = col; P.eid = eid;
+  P.n = (int)n; P.H = (unsigned)H; P.mode = mode; P.epi = epilogue; P.learn = learn;
+  P.t = t; P.p = p; P.eps = eps; P.t_dev = t_dev; P.p_dev = p_dev; P.y_dev = y_dev;
+  P.scale_dev = msg_scale_dev; P.g = g; P.m_in = m; P.aux_in = aux;
+  P.g_edge = g_edge; P.g_x = g_x; P.partials = partials;
+  rc = dispatch<false>(P, (cudaStream_t)stream);
+  if (rc) return rc;
+  MLG_CHECK_LAUNCH("mlg_gen_aggr_bwd_affine");
   return MLG_OK;
 }

@@ -1,0 +1,108 @@
+// Weighted column sums of a tall matrix:  u[c] = sum_r a[r] * G[r, c],  v[c] = sum_r G[r, c]   (sm_100a).
+//
+// Backward of the rank-1 affine edge term e_ij = a_e * p + q of mlg_gen_aggr_*_affine: with G = d loss / d e ([E, H]) the
+// gradients of the two H-vectors are g_p = u and g_q = v.  One streaming pass over G (HBM-bound, 4*E*H bytes): a warp owns
+// a row at a time (lanes over the columns, float4), per-lane partial sums, block partials through shared memory, and a
+// fixed-order reduction over the blocks (deterministic).  C % 4 == 0, C <= 1024.
+#include "common.cuh"
+#include "../../include/mlg_b200.h"
+
+namespace {
+
+constexpr int kWarps = 8;
+constexpr int kMaxV = 8;   // float4 per lane: C <= 1024
+
+__global__ void __launch_bounds__(kWarps * 32)
+wcolsum_kernel(const float* __restrict__ G, unsigned ld, const float* __restrict__ a, long long rows, int C,
+               float* __restrict__ partial /* [gridDim.x][2][C] */) {
+  extern __shared__ float stage[];   // [kWarps][2][C]
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int nv = (C + 127) / 128;
+  float4 su[kMaxV], sv[kMaxV];
+#pragma unroll
+  for (int i = 0; i < kMaxV; ++i) su[i] = sv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  const long long stride = (long long)gridDim.x * kWarps;
+  for (long long r = (long long)blockIdx.x * kWarps + wib; r < rows; r += stride) {
+    const float w = a ? __ldg(a + r) : 0.f;
+    const float* row = G + (size_t)r * ld + lane * 4;
+#pragma unroll
+    for (int i = 0; i < kMaxV; ++i) {
+      if (i < nv && i * 128 + lane * 4 < C) {
+        const float4 g = ld_stream4(row + i * 128);
+        su[i].x = fmaf(w, g.x, su[i].x); su[i].y = fmaf(w, g.y, su[i].y);
+        su[i].z = fmaf(w, g.z, su[i].z); su[i].w = fmaf(w, g.w, su[i].w);
+        sv[i].x += g.x; sv[i].y += g.y; sv[i].z += g.z; sv[i].w += g.w;
+      }
+    }
+  }
+  float* mine = stage + (size_t)wib * 2 * C;
+#pragma unroll
+  for (int i = 0; i < kMaxV; ++i) {
+    const int c = i * 128 + lane * 4;
+    if (i < nv && c < C) {
+      *reinterpret_cast<float4*>(mine + c) = su[i];
+      *reinterpret_cast<float4*>(mine + C + c) = sv[i];
+    }
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < 2 * C; j += kWarps * 32) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) s += stage[(size_t)w * 2 * C + j];
+    partial[(size_t)blockIdx.x * 2 * C + j] = s;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+wcolsum_reduce_kernel(const float* __restrict__ partial, int n_part, int C2, float* __restrict__ u, float* __restrict__ v) {
+  __shared__ float sm[8][32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int j = blockIdx.x * 32 + lane;
+  float s0 = 0.f, s1 = 0.f;
+  if (j < C2) {
+    int p = w;
+    for (; p + 8 < n_part; p += 16) {
+      s0 += partial[(size_t)p * C2 + j];
+      s1 += partial[(size_t)(p + 8) * C2 + j];
+    }
+    for (; p < n_part; p += 8) s0 += partial[(size_t)p * C2 + j];
+  }
+  sm[w][lane] = s0 + s1;
+  __syncthreads();
+  if (w == 0 && j < C2) {
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += sm[k][lane];
+    const int C = C2 / 2;
+    if (j < C) { if (u) u[j] = s; }
+    else if (v) v[j - C] = s;
+  }
+}
+
+inline int wc_blocks(long long rows) {
+  long long b = (rows + kWarps - 1) / kWarps;
+  const long long cap = 148 * 4;
+  return (int)(b < cap ? (b < 1 ? 1 : b) : cap);
+}
+
+}  // namespace
+
+extern "C" int64_t mlg_wcolsum_workspace_bytes(int64_t rows, int64_t C) { return (int64_t)wc_blocks(rows) * 2 * C * 4; }
+
+extern "C" int mlg_wcolsum(const float* G, int64_t ld, const float* a, int64_t rows, int64_t C, float* u, float* v,
+                           void* workspace, int64_t workspace_bytes, void* stream) {
+  MLG_CHECK_ARG(G && workspace && (u || v), "mlg_wcolsum: null pointer");
+  MLG_CHECK_ARG(rows >= 0 && C >= 4 && C % 4 == 0 && C <= 128 * kMaxV && ld >= C && ld % 4 == 0 && (uintptr_t)G % 16 == 0,
+                "mlg_wcolsum: need C %% 4 == 0, C <= 1024, 16-byte aligned rows");
+  MLG_CHECK_ARG(!u || a, "mlg_wcolsum: the weighted sum u needs the weights a");
+  MLG_CHECK_ARG(workspace_bytes >= mlg_wcolsum_workspace_bytes(rows, C), "mlg_wcolsum: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int grid = wc_blocks(rows);
+  const size_t smem = (size_t)kWarps * 2 * C * 4;
+  if (smem > 48 * 1024) cudaFuncSetAttribute(wcolsum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  wcolsum_kernel<<<grid, kWarps * 32, smem, st>>>(G, (unsigned)ld, a, rows, (int)C, (float*)workspace);
+  MLG_CHECK_LAUNCH("mlg_wcolsum");
+  wcolsum_reduce_kernel<<<(unsigned)mlg_ceil_div(2 * C, 32), 256, 0, st>>>((const float*)workspace, grid, (int)(2 * C), u, v);
+  MLG_CHECK_LAUNCH("mlg_wcolsum(reduce)");
+  return MLG_OK;
+}

@@ -334,6 +334,122 @@ class GenAggregate(torch.autograd.Function):
         return gx, ge, gt, gp, gy, gs, None, None, None, None, None
 
 
+class AffineEdge:
+    """Edge embedding kept in factored form: e_ij = a_e * p + q with a per-edge scalar ``a`` [E] and H-vectors ``p``, ``q``
+    (differentiable tensors).  DeeperGCN builds it from a scalar edge attribute and its Linear(1 -> H) edge encoder; a
+    GENConv whose own edge encoder is a Linear composes the two analytically (``compose``) and aggregates through
+    GenAggregateAffine, so no [E, H] edge tensor is ever written; ``materialize()`` serves any other consumer."""
+
+    def __init__(self, a, p, q):
+        self.a, self.p, self.q = a, p, q
+
+    @property
+    def shape(self):
+        return (self.a.numel(), self.p.numel())
+
+    def compose(self, lin):
+        """The same edge term after an nn.Linear: W (a p + q) + b = a (W p) + (W q + b)."""
+        q = lin.weight @ self.q
+        return AffineEdge(self.a, lin.weight @ self.p, q if lin.bias is None else q + lin.bias)
+
+    def materialize(self):
+        return self.a.reshape(-1, 1) * self.p.reshape(1, -1) + self.q.reshape(1, -1)
+
+
+class GenAggregateAffine(torch.autograd.Function):
+    """GenAggregate with the edge term in AffineEdge form (mlg_gen_aggr_fwd_affine / _bwd_affine + mlg_wcolsum).
+
+    forward(x [N,H], a [E], p [H], q [H], t, pw, y, msg_scale, topo, aggr, eps, epilogue, learn) -> h (or m)."""
+
+    @staticmethod
+    def forward(ctx, x, a, p, q, t, pw, y, msg_scale, topo, aggr, eps, epilogue, learn):
+        L = _cabi.lib()
+        _cabi.require_cuda(x, a, p, q)
+        xd, ad, pd, qd = _f32c(x.detach()), _f32c(a.detach().reshape(-1)), _f32c(p.detach()), _f32c(q.detach())
+        n, H = xd.shape
+        csr = topo.fwd
+        mode = AGGR_CODE[aggr]
+        t_h, t_d = _scalar_args(t)
+        p_h, p_d = _scalar_args(pw)
+        y_d = None if y is None else _cabi.fptr(y.detach().reshape(1))
+        s_d = None if msg_scale is None else _cabi.fptr(msg_scale.detach().reshape(1))
+        need_grad = any(ctx.needs_input_grad)
+        h = torch.empty(n, H, dtype=torch.float32, device=xd.device) if epilogue != EPI_NONE else None
+        m = torch.empty(n, H, dtype=torch.float32, device=xd.device)
+        aux = torch.empty(n, H, dtype=torch.float32, device=xd.device) if (need_grad and mode in (0, 1)) else None
+        n_entries = csr.col.numel()
+        with torch.cuda.device(xd.device), _cabi.span("gen_aggr_fwd_affine", 4 * H * 3 * n + 8 * n_entries + 4 * (n + 1)):
+            _cabi.check(L.mlg_gen_aggr_fwd_affine(
+                _cabi.fptr(xd), _cabi.fptr(ad), _cabi.fptr(pd), _cabi.fptr(qd), _cabi.iptr(csr.rowptr), _cabi.iptr(csr.col),
+                None if topo.fwd_identity else _cabi.iptr(csr.eid), n, H, mode, t_h, t_d, p_h, p_d, y_d, float(eps),
+                epilogue, s_d, _cabi.fptr(m), _cabi.fptr(aux, True), _cabi.fptr(h, True), _cabi.stream_ptr()),
+                "mlg_gen_aggr_fwd_affine")
+        if not need_grad:
+            return h if h is not None else m
+        ctx.topo, ctx.mode, ctx.eps, ctx.epilogue, ctx.learn = topo, mode, float(eps), epilogue, bool(learn)
+        ctx.t, ctx.p, ctx.y, ctx.scale = t, pw, y, msg_scale
+        ctx.has_aux, ctx.a_shape = aux is not None, a.shape
+        ctx.save_for_backward(*[v for v in (xd, ad, pd, qd, m, aux) if v is not None])
+        return h if h is not None else m
+
+    @staticmethod
+    def backward(ctx, g):
+        L = _cabi.lib()
+        saved = list(ctx.saved_tensors)
+        xd, ad, pd, qd, m = saved[:5]
+        aux = saved[5] if ctx.has_aux else None
+        topo = ctx.topo
+        n, H = m.shape
+        g = _f32c(g)
+        dev = m.device
+        csr = topo.fwd
+        n_edges = topo.edge_index.shape[1]
+        t_h, t_d = _scalar_args(ctx.t)
+        p_h, p_d = _scalar_args(ctx.p)
+        y_d = None if ctx.y is None else _cabi.fptr(ctx.y.detach().reshape(1))
+        s_d = None if ctx.scale is None else _cabi.fptr(ctx.scale.detach().reshape(1))
+        g_edge = torch.empty(max(n_edges, 1), H, dtype=torch.float32, device=dev)
+        g_x = torch.empty(n, H, dtype=torch.float32, device=dev)
+        rows = L.mlg_gen_aggr_bwd_partial_rows(n, H)
+        partials = torch.empty(rows, 4, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev), _cabi.span("gen_aggr_bwd_affine", 4 * H * (n_edges + 4 * n) + 12 * n_edges):
+            _cabi.check(L.mlg_gen_aggr_bwd_affine(
+                _cabi.fptr(g), _cabi.fptr(xd), _cabi.fptr(ad), _cabi.fptr(pd), _cabi.fptr(qd), _cabi.iptr(csr.rowptr),
+                _cabi.iptr(csr.col), None if topo.fwd_identity else _cabi.iptr(csr.eid), n, H, ctx.mode, int(ctx.learn),
+                t_h, t_d, p_h, p_d, y_d, ctx.eps, ctx.epilogue, s_d, _cabi.fptr(m), _cabi.fptr(aux, True),
+                _cabi.fptr(g_edge), _cabi.fptr(g_x), _cabi.fptr(partials), _cabi.stream_ptr()), "mlg_gen_aggr_bwd_affine")
+        needs = ctx.needs_input_grad
+        gx = None
+        if needs[0]:
+            bw = topo.bwd
+            gx = gather_sum(g_edge, bw.rowptr, bw.eid, n, out=g_x, addend=g_x, tag="gen_aggr_bwd_src")
+        ga = gp = gq = None
+        if (needs[2] or needs[3]) and n_edges > 0:
+            gp, gq = torch.empty_like(pd), torch.empty_like(qd)
+            ws_bytes = L.mlg_wcolsum_workspace_bytes(n_edges, H)
+            ws = torch.empty(ws_bytes // 4, dtype=torch.float32, device=dev)
+            with torch.cuda.device(dev), _cabi.span("gen_edge_pq_grad", 4 * H * n_edges):
+                _cabi.check(L.mlg_wcolsum(_cabi.fptr(g_edge), H, _cabi.fptr(ad), n_edges, H, _cabi.fptr(gp), _cabi.fptr(gq),
+                                          _cabi.fptr(ws), ws_bytes, _cabi.stream_ptr()), "mlg_wcolsum")
+        elif needs[2] or needs[3]:
+            gp, gq = torch.zeros_like(pd), torch.zeros_like(qd)
+        if needs[1]:      # gradient w.r.t. the scalar edge attribute itself (not needed by the reference's data path)
+            ga = (g_edge[:n_edges] @ pd).reshape(ctx.a_shape)
+        sums = None
+
+        def part(i):
+            nonlocal sums
+            if sums is None:
+                sums = partials.sum(dim=0)
+            return sums[i].reshape(1)
+
+        gt = part(0).reshape(ctx.t.shape) if (torch.is_tensor(ctx.t) and needs[4] and ctx.mode == 0 and ctx.learn) else None
+        gpw = part(0).reshape(ctx.p.shape) if (torch.is_tensor(ctx.p) and needs[5] and ctx.mode == 1 and ctx.learn) else None
+        gy = part(1).reshape(ctx.y.shape) if (ctx.y is not None and needs[6]) else None
+        gs = part(2).reshape(ctx.scale.shape) if (ctx.scale is not None and needs[7] and ctx.epilogue == EPI_MSGNORM) else None
+        return gx, ga, gp, gq, gt, gpw, gy, gs, None, None, None, None, None
+
+
 class SageAggregate(torch.autograd.Function):
     """Weighted mean over in-neighbours incl. the rewritten self loop, BEFORE the lin_r transform:
     agg_i = (sum_{j->i, j!=i} w_ij x_j + x_i) / (deg_i + 1)   [- x_i for RSAGE]

@@ -42,6 +42,19 @@ class GENConv(GenMessagePassing):
     def forward(self, x, edge_index, edge_attr=None):
         if self.pca_only:
             return self.feature_encoder(x)
+        if isinstance(edge_attr, Fn.AffineEdge):
+            # factored edge term a_e * p + q (DeeperGCN with a scalar edge attribute): this layer's Linear edge encoder is
+            # composed analytically and the aggregation kernel rebuilds e_ij in registers -- no [E, H] tensor, no edge GEMM
+            ae = edge_attr.compose(self.edge_encoder) if self.encode_edge else edge_attr
+            tx = x.flatten(1)
+            topo = graph.topology(edge_index, tx.shape[0])
+            aggr, t, p, y, learn = self._kernel_args()
+            scale = self.msg_norm.msg_scale if self.msg_norm is not None else None
+            h = Fn.GenAggregateAffine.apply(tx, ae.a, ae.p, ae.q, t, p, y, scale, topo, aggr, self.eps,
+                                            Fn.EPI_MSGNORM if scale is not None else Fn.EPI_RESIDUAL, learn)
+            if aggr in ('softmax_sum', 'power_sum'):
+                self.sigmoid_y = torch.sigmoid(self.y)
+            return self.feature_encoder(h.reshape(x.shape))
         if self.encode_edge and edge_attr is not None:
             edge_emb = Fn.tall_linear(edge_attr, self.edge_encoder)
         else:

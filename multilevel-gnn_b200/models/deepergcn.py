@@ -12,11 +12,16 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from ..functional import AffineEdge
 from ..gcn_lib.sparse.torch_nn import norm_layer
 from ..gcn_lib.sparse.torch_vertex import GENConv
 
 
 class DeeperGCN(nn.Module):
+    # carry a scalar edge attribute's embedding in factored form (functional.AffineEdge) instead of an [E, H] tensor;
+    # False = the literal per-layer edge GEMM path (kept for the equivalence test)
+    AFFINE_EDGE = True
+
     def __init__(self, args):
         super().__init__()
         self.num_layers = args.num_layers
@@ -121,7 +126,13 @@ class DeeperGCN(nn.Module):
                 x = torch.cat([x[:, :-1], self.node_embedding_encoder(x[:, -1].to(torch.long))], dim=-1)
             h = self.node_features_encoder(x)
             if self.use_edge_attr:
-                edge_emb = self.edge_encoder(edge_attr)
+                if (self.AFFINE_EDGE and isinstance(self.edge_encoder, nn.Linear) and self.edge_encoder.in_features == 1
+                        and edge_attr.is_cuda and edge_attr.numel() == edge_index.shape[1]
+                        and self.edge_encoder.out_features % 4 == 0 and not self.gcns[0].bond_encoder):
+                    # scalar edge attribute: Linear(1 -> H) is a_e * w + b; carried in factored form through every GENConv
+                    edge_emb = AffineEdge(edge_attr.reshape(-1), self.edge_encoder.weight[:, 0], self.edge_encoder.bias)
+                else:
+                    edge_emb = self.edge_encoder(edge_attr)
         rows = None
         if self.pathway_global_node:
             pemb = self.pathway_features_encoder(input_batch.pathway_node_attr)

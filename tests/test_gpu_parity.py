@@ -210,11 +210,15 @@ def test_multilevel_golden(mlg, name):
 DG = load_golden("deepergcn")
 
 
+@pytest.mark.parametrize("affine", [True, False], ids=["affine_edge", "edge_gemm"])
 @pytest.mark.parametrize("name", sorted(DG))
-def test_deepergcn_golden(mlg, name):
+def test_deepergcn_golden(mlg, name, affine):
+    """Both edge paths against the reference's outputs: the factored scalar-edge term (functional.AffineEdge, no [E, H]
+    tensor) and the literal per-layer edge GEMM."""
     c = DG[name]
     args = mlg.configs.make_args(None, **c["overrides"])
     model = _load(mlg.DeeperGCN(args), c["state_dict"])
+    model.AFFINE_EDGE = affine
     model.train()
     batch = as_batch(c["batch"], DEV)
     batch.node_size = c["batch"]["node_size"]          # host tensor: no device sync needed
@@ -225,6 +229,60 @@ def test_deepergcn_golden(mlg, name):
         if c["grads"].get(k) is None:
             continue
         assert_close(p.grad, c["grads"][k], rtol=5e-4, atol=2e-5, what=name + ".g_" + k)
+
+
+@pytest.mark.parametrize("aggr,H,epi", [("softmax", 128, "msgnorm"), ("softmax", 256, "residual"), ("softmax_sg", 64, "msgnorm"),
+                                        ("power", 32, "msgnorm"), ("softmax_sum", 96, "residual"), ("power_sum", 128, "msgnorm"),
+                                        ("add", 128, "residual"), ("mean", 48, "msgnorm"), ("max", 128, "residual")])
+def test_gen_aggregate_affine_vs_materialized(mlg, aggr, H, epi):
+    """mlg_gen_aggr_{fwd,bwd}_affine + mlg_wcolsum (edge term a_e * p + q rebuilt in registers) against the [E, H] path on
+    the same numbers: output, g_x, g_p, g_q, g_a and the learnable scalars."""
+    Fn = mlg.functional
+    n, e = 2500, 30000
+    ei, g = _rand_graph(n, e, 23)
+    topo = mlg.graph.topology(ei.to(DEV), n)
+    x0 = torch.randn(n, H, generator=g).to(DEV)
+    a0 = torch.rand(e, generator=g).to(DEV)
+    p0, q0 = torch.randn(H, generator=g).to(DEV), (0.3 * torch.randn(H, generator=g)).to(DEV)
+    Rm = torch.randn(n, H, generator=g).to(DEV)
+    learn = True
+    outs = []
+    for affine in (True, False):
+        x, a, p, q = (v.clone().requires_grad_() for v in (x0, a0, p0, q0))
+        t = torch.tensor([0.9], device=DEV, requires_grad=True)
+        pw = torch.tensor([2.0], device=DEV, requires_grad=True)
+        y = torch.tensor([0.1], device=DEV, requires_grad=True) if aggr.endswith("_sum") else None
+        sc = torch.tensor([1.3], device=DEV, requires_grad=True) if epi == "msgnorm" else None
+        code = Fn.EPI_MSGNORM if epi == "msgnorm" else Fn.EPI_RESIDUAL
+        if affine:
+            h = Fn.GenAggregateAffine.apply(x, a, p, q, t, pw, y, sc, topo, aggr, 1e-7, code, learn)
+        else:
+            h = Fn.GenAggregate.apply(x, Fn.AffineEdge(a, p, q).materialize(), t, pw, y, sc, topo, aggr, 1e-7, code, learn)
+        leaves = [x, a, p, q] + [v for v in (t, pw, y, sc) if v is not None]
+        gs = torch.autograd.grad((h * Rm).sum(), leaves, allow_unused=True)
+        outs.append((h, gs))
+    (ha, ga), (hm, gm) = outs
+    assert_close(ha, hm, what="h")
+    for i, (u, v) in enumerate(zip(ga, gm)):
+        assert (u is None) == (v is None), i
+        if u is not None:
+            assert_close(u, v, rtol=2e-4, atol=1e-5 * max(1.0, float(v.abs().max())), what="grad[%d]" % i)
+
+
+def test_wcolsum(mlg):
+    L, cabi = mlg._cabi.lib(), mlg._cabi
+    for rows, C in ((1, 4), (777, 128), (50001, 64), (4099, 1024)):
+        g = torch.Generator().manual_seed(rows)
+        G = torch.randn(rows, C, generator=g).to(DEV)
+        a = torch.rand(rows, generator=g).to(DEV)
+        u, v = torch.empty(C, device=DEV), torch.empty(C, device=DEV)
+        nb = L.mlg_wcolsum_workspace_bytes(rows, C)
+        ws = torch.empty(nb // 4, device=DEV)
+        cabi.check(L.mlg_wcolsum(cabi.fptr(G), C, cabi.fptr(a), rows, C, cabi.fptr(u), cabi.fptr(v), cabi.fptr(ws), nb,
+                                 cabi.stream_ptr()), "mlg_wcolsum")
+        Gd = G.double()
+        assert_close(u, (a.double() @ Gd).float(), rtol=1e-4, atol=1e-4, what="u")
+        assert_close(v, Gd.sum(0).float(), rtol=1e-4, atol=1e-4, what="v")
 
 
 # ------------------------------------------------------------------------------------------------

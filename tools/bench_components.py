@@ -186,10 +186,13 @@ def deepergcn(quick):
         model.zero_grad(set_to_none=True)
         out = model(bd)
         out[:, 0].sum().backward()
-    ms = gpu_ms(fb, reps=2, warm=1)
-    emit(row="a5 DeeperGCN train step (res+, softmax, learn_t, msg_norm, per-layer edge encoder)",
-         shape="N=100k(+146) k=16 H=128 L=%d" % layers, fwd_bwd_ms=round(ms, 2),
-         note="aggregation kernels: see a1-a4/a14; the per-layer [E,H]x[H,H] edge-encoder GEMMs (cuBLAS fp32) dominate")
+    for affine in (True, False):
+        model.AFFINE_EDGE = affine
+        ms = gpu_ms(fb, reps=2, warm=1)
+        emit(row="a5 DeeperGCN train step (res+, softmax, learn_t, msg_norm, per-layer edge encoder), edge term %s"
+             % ("factored a_e*p+q (no [E,H] tensor)" if affine else "materialised [E,H] + per-layer edge GEMM"),
+             shape="N=100k(+146) k=16 H=128 L=%d" % layers, fwd_bwd_ms=round(ms, 2))
+        torch.cuda.empty_cache()
 
 
 if __name__ == "__main__":
