@@ -18,6 +18,7 @@ import statistics
 import subprocess
 import sys
 import tempfile
+import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -53,10 +54,32 @@ def peaks():
 
 
 class ClockSampler:
+    """SM clock + throttle reasons of one GPU sampled DURING the timed region: an NVML polling thread (1 ms period; the
+    timed region of a 20-step run is ~30 ms, shorter than `nvidia-smi`'s start-up), `nvidia-smi -lms` as the fallback."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    BITS = {"sw_power_cap": 0x4, "hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
 
     def __init__(self, index=0):
+        self.p = self.f = self.thread = None
+        self.sm, self.reason_bits, self.mx = [], 0, None
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            try:
+                uuid = str(torch.cuda.get_device_properties(index).uuid)
+                h = nv.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
+            except Exception:
+                h = nv.nvmlDeviceGetHandleByIndex(index)
+            self.mx = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            reasons_fn = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+            self.nv, self.h, self.reasons_fn = nv, h, reasons_fn
+            self._stop = threading.Event()
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.thread = None
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
@@ -65,8 +88,29 @@ class ClockSampler:
         except OSError:
             self.p = None
 
+    def _sample(self):
+        try:
+            self.sm.append(float(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM)))
+            self.reason_bits |= int(self.reasons_fn(self.h))
+        except Exception:
+            pass
+
+    def _poll(self):
+        while not self._stop.is_set():
+            self._sample()
+            time.sleep(0.001)
+
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.thread is not None:
+            self._sample()          # at least one sample with the last steps still in flight
+            self._stop.set()
+            self.thread.join(timeout=2)
+            if self.sm:
+                out = {"sm_mhz": statistics.median(self.sm), "sm_max_mhz": self.mx,
+                       "reasons": sorted(k for k, b in self.BITS.items() if self.reason_bits & b), "samples": len(self.sm),
+                       "source": "nvml"}
+            return out
         if self.p is None:
             return out
         self.p.terminate()
@@ -93,7 +137,8 @@ class ClockSampler:
         self.f.close()
         os.unlink(self.f.name)
         if sm:
-            out = {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+            out = {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm),
+                   "source": "nvidia-smi"}
         return out
 
 

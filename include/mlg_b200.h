@@ -195,16 +195,21 @@ int mlg_layernorm_bwd(const float* x, const float* g, const float* gamma, const 
  * the raw edge attribute is a scalar weight -- Linear(1 -> H) (models/deepergcn.py:209) followed by each GENConv's own
  * Linear(H -> H) edge encoder (gcn_lib/sparse/torch_vertex.py:76-77) is affine in a_e.  g_edge [E, H] (gradient w.r.t.
  * the edge term, original edge order) is still produced: the source-side pass (mlg_gather_sum over the by-source CSR)
- * and mlg_wcolsum (g_p = sum_e a_e g_edge[e], g_q = sum_e g_edge[e]) consume it. */
+ * consumes it. */
 int mlg_gen_aggr_fwd_affine(const float* x, const float* edge_scalar, const float* edge_p, const float* edge_q,
                             const int32_t* rowptr, const int32_t* col, const int32_t* eid, int64_t n, int64_t H, int mode,
                             float t, const float* t_dev, float p, const float* p_dev, const float* y_dev, float eps,
                             int epilogue, const float* msg_scale_dev, float* m, float* aux, float* h, void* stream);
+/* g_p / g_q (both NULL ok): gradients of edge_p / edge_q, g_p = sum_e a_e * g_edge[e], g_q = sum_e g_edge[e], accumulated
+ * inside the backward kernel (per-block partials in `workspace`, fixed-order two-level reduction) -- no second pass over
+ * g_edge.  n_edges = rows of edge_scalar / g_edge.  workspace >= mlg_gen_aggr_bwd_affine_workspace_bytes(n, n_edges, H). */
+int64_t mlg_gen_aggr_bwd_affine_workspace_bytes(int64_t n, int64_t n_edges, int64_t H);
 int mlg_gen_aggr_bwd_affine(const float* g, const float* x, const float* edge_scalar, const float* edge_p,
                             const float* edge_q, const int32_t* rowptr, const int32_t* col, const int32_t* eid, int64_t n,
-                            int64_t H, int mode, int learn, float t, const float* t_dev, float p, const float* p_dev,
-                            const float* y_dev, float eps, int epilogue, const float* msg_scale_dev, const float* m,
-                            const float* aux, float* g_edge, float* g_x, float* partials, void* stream);
+                            int64_t n_edges, int64_t H, int mode, int learn, float t, const float* t_dev, float p,
+                            const float* p_dev, const float* y_dev, float eps, int epilogue, const float* msg_scale_dev,
+                            const float* m, const float* aux, float* g_edge, float* g_x, float* partials, float* g_p,
+                            float* g_q, void* workspace, int64_t workspace_bytes, void* stream);
 /* Weighted column sums of a tall matrix: u[c] = sum_r a[r] * G[r,c] (u NULL ok), v[c] = sum_r G[r,c] (v NULL ok); one
  * streaming pass, fixed summation order.  C % 4 == 0, C <= 1024.  workspace >= mlg_wcolsum_workspace_bytes(rows, C). */
 int64_t mlg_wcolsum_workspace_bytes(int64_t rows, int64_t C);

@@ -124,55 +124,110 @@ __device__ __forceinline__ void finish_row(const GsP& P, float (&acc)[VEC], unsi
 // ---------------------------------------------------------------------------------------------
 // single-graph path: one lane group per row, UN entries in flight
 // ---------------------------------------------------------------------------------------------
+// Rows longer than kHeavy entries (hubs: the by-source CSR of a kNN graph has out-degrees in the thousands while the
+// mean is k) are NOT walked by their one lane group -- a single group with UN loads in flight would be the kernel's
+// tail (measured: 610 us for an 820 MB gather at N=100k, k=16, H=128, max out-degree 1502).  The group only records the
+// row; after the block's light rows are done ALL lane groups of the block walk each recorded row together (group g takes
+// entry blocks g, g+G, ...), partial sums meet in shared memory and are added in group order: still a fixed summation
+// order, no atomics on the data.
+constexpr int kHeavy = 96;
+
+template <int LANES, int VEC>
+__device__ __forceinline__ void gs_accumulate(const GsP& P, const float* sc, bool cok, unsigned gmask, int sl, int first,
+                                              int end, int stride, float (&acc)[VEC]) {
+  for (int base = first; base < end; base += stride) {
+    const int q = min(base + sl, end - 1);
+    const unsigned my_idx = (unsigned)__ldg(P.idx + q);
+    float my_w = P.val ? __ldg(P.val + q) : 1.f;
+    if (P.pre) my_w *= __ldg(P.pre + my_idx);
+    const int cnt = min(LANES, end - base);
+    for (int j = 0; j < cnt; j += UN) {
+      float xv[UN][VEC];
+      float w[UN];
+#pragma unroll
+      for (int u = 0; u < UN; ++u) {
+        const int jj = min(j + u, cnt - 1);
+        const unsigned s = __shfl_sync(gmask, my_idx, jj, LANES);
+        w[u] = __shfl_sync(gmask, my_w, jj, LANES);
+        if (j + u >= cnt) w[u] = 0.f;
+        ldv<VEC>(xv[u], rowp(sc, s, P.ld_src), cok);
+      }
+#pragma unroll
+      for (int u = 0; u < UN; ++u)
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) acc[k] = fmaf(w[u], xv[u][k], acc[k]);
+    }
+  }
+}
+
 template <int LANES, int VEC>
 __global__ void __launch_bounds__(kThreads) gather_sum_kernel(const GsP P) {
   constexpr int RPW = 32 / LANES;
   constexpr int CW = LANES * VEC;
+  constexpr int G = kThreads / LANES;          // lane groups per block
+  __shared__ int heavy_rows[G];
+  __shared__ int n_heavy;
+  __shared__ float part[G * CW];
   const int lane = threadIdx.x & 31;
   const int sub = lane / LANES, sl = lane % LANES;
   const unsigned gmask = (LANES == 32) ? 0xffffffffu : (((1u << LANES) - 1u) << (sub * LANES));
   const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
   const long long slot = warp * RPW + sub;
-  if (slot >= P.n) return;
-  const long long row = P.order ? __ldg(P.order + slot) : slot;
   const int C = P.C;
-  const int beg = __ldg(P.rowptr + row), end = __ldg(P.rowptr + row + 1);
-  const int cnt_row = end - beg;
-  float postf = 1.f;
-  if (P.post_mode == 1) postf = cnt_row > 0 ? 1.f / (float)cnt_row : 0.f;
-  else if (P.post_mode == 2) postf = __ldg(P.post + row);
   const int nchunks = (C + CW - 1) / CW;
-  for (int ch = 0; ch < nchunks; ++ch) {
-    const unsigned c = ch * CW + sl * VEC;
-    const bool cok = c < (unsigned)C;
-    const float* sc = P.src + c;
-    float acc[VEC];
+  if (threadIdx.x == 0) n_heavy = 0;
+  __syncthreads();
+  if (slot < P.n) {
+    const long long row = P.order ? __ldg(P.order + slot) : slot;
+    const int beg = __ldg(P.rowptr + row), end = __ldg(P.rowptr + row + 1);
+    const int cnt_row = end - beg;
+    if (cnt_row > kHeavy) {
+      if (sl == 0) heavy_rows[atomicAdd(&n_heavy, 1)] = (int)row;   // list order is irrelevant: rows are independent
+    } else {
+      float postf = 1.f;
+      if (P.post_mode == 1) postf = cnt_row > 0 ? 1.f / (float)cnt_row : 0.f;
+      else if (P.post_mode == 2) postf = __ldg(P.post + row);
+      for (int ch = 0; ch < nchunks; ++ch) {
+        const unsigned c = ch * CW + sl * VEC;
+        const bool cok = c < (unsigned)C;
+        float acc[VEC];
 #pragma unroll
-    for (int k = 0; k < VEC; ++k) acc[k] = 0.f;
-    for (int base = beg; base < end; base += LANES) {
-      const int q = min(base + sl, end - 1);
-      const unsigned my_idx = (unsigned)__ldg(P.idx + q);
-      float my_w = P.val ? __ldg(P.val + q) : 1.f;
-      if (P.pre) my_w *= __ldg(P.pre + my_idx);
-      const int cnt = min(LANES, end - base);
-      for (int j = 0; j < cnt; j += UN) {
-        float xv[UN][VEC];
-        float w[UN];
-#pragma unroll
-        for (int u = 0; u < UN; ++u) {
-          const int jj = min(j + u, cnt - 1);
-          const unsigned s = __shfl_sync(gmask, my_idx, jj, LANES);
-          w[u] = __shfl_sync(gmask, my_w, jj, LANES);
-          if (j + u >= cnt) w[u] = 0.f;
-          ldv<VEC>(xv[u], rowp(sc, s, P.ld_src), cok);
-        }
-#pragma unroll
-        for (int u = 0; u < UN; ++u)
-#pragma unroll
-          for (int k = 0; k < VEC; ++k) acc[k] = fmaf(w[u], xv[u][k], acc[k]);
+        for (int k = 0; k < VEC; ++k) acc[k] = 0.f;
+        gs_accumulate<LANES, VEC>(P, P.src + c, cok, gmask, sl, beg, end, LANES, acc);
+        finish_row<VEC>(P, acc, (unsigned)row, (unsigned)row, c, cok, postf, cnt_row);
       }
     }
-    finish_row<VEC>(P, acc, (unsigned)row, (unsigned)row, c, cok, postf, cnt_row);
+  }
+  __syncthreads();
+  const int nh = n_heavy;
+  if (nh == 0) return;
+  const int g = threadIdx.x / LANES;
+  for (int h = 0; h < nh; ++h) {
+    const int row = heavy_rows[h];
+    const int beg = __ldg(P.rowptr + row), end = __ldg(P.rowptr + row + 1);
+    const int cnt_row = end - beg;
+    float postf = 1.f;
+    if (P.post_mode == 1) postf = 1.f / (float)cnt_row;
+    else if (P.post_mode == 2) postf = __ldg(P.post + row);
+    for (int ch = 0; ch < nchunks; ++ch) {
+      const unsigned c = ch * CW + sl * VEC;
+      const bool cok = c < (unsigned)C;
+      float acc[VEC];
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) acc[k] = 0.f;
+      gs_accumulate<LANES, VEC>(P, P.src + c, cok, gmask, sl, beg + g * LANES, end, G * LANES, acc);
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) part[g * CW + sl * VEC + k] = acc[k];
+      __syncthreads();
+      if (g == 0) {
+#pragma unroll 4
+        for (int gg = 1; gg < G; ++gg)
+#pragma unroll
+          for (int k = 0; k < VEC; ++k) acc[k] += part[gg * CW + sl * VEC + k];
+        finish_row<VEC>(P, acc, (unsigned)row, (unsigned)row, c, cok, postf, cnt_row);
+      }
+      __syncthreads();
+    }
   }
 }
 

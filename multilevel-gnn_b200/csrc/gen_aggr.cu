@@ -33,6 +33,7 @@ struct GenP {
   const float* ea;   // S_XA: per-edge scalar a_e [E] ...
   const float* ep;   // ... and the vectors p, q [H]: edge term e_ij = a_e * p + q (never materialised)
   const float* eq;
+  float* pq_part;    // S_XA backward, optional: per-block partial sums [grid][2][H] of (a_e * g_edge, g_edge) over the edges
   const int* rowptr;
   const int* col;
   const int* eid;
@@ -329,12 +330,20 @@ __global__ void __launch_bounds__(kThreads) gen_bwd_kernel(const GenP P) {
   constexpr int CW = LANES * VEC;
   constexpr bool HAS_X = SRC != S_RAW, HAS_E = (SRC == S_XE || SRC == S_RAW), RAW = SRC == S_RAW, AFF = SRC == S_XA;
   __shared__ float red[3 * 32];
+  extern __shared__ __align__(16) float pq_stage[];   // AFF && pq_part: [lane groups][2][H] per-row edge-gradient sums
   const int lane = threadIdx.x & 31;
   const int sub = lane / LANES, sl = lane % LANES;
   const unsigned gmask = (LANES == 32) ? 0xffffffffu : (((1u << LANES) - 1u) << (sub * LANES));
   const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
   const long long row = warp * RPW + sub;
   const bool active = row < P.n;
+  const bool pq_on = AFF && P.pq_part != nullptr;
+  constexpr int G = kThreads / LANES;
+  if (pq_on) {
+    for (unsigned j = threadIdx.x; j < G * 2 * P.H; j += kThreads) pq_stage[j] = 0.f;
+    __syncthreads();
+  }
+  float* my_stage = pq_stage + (size_t)(threadIdx.x / LANES) * 2 * P.H;
 
   float acc[3] = {0.f, 0.f, 0.f};  // d/dt (or d/dp), d/dy_raw, d/dmsg_scale
 
@@ -448,6 +457,9 @@ __global__ void __launch_bounds__(kThreads) gen_bwd_kernel(const GenP P) {
         }
       }
 
+      float su[VEC], sv[VEC];   // AFF: sum over this row's edges of a_e * g_edge and g_edge (this lane's channels)
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) su[k] = sv[k] = 0.f;
       for (int base = beg; base < end; base += LANES) {
         const int q = min(base + sl, end - 1);
         const unsigned my_col = HAS_X ? (unsigned)__ldg(P.col + q) : 0u;
@@ -458,11 +470,14 @@ __global__ void __launch_bounds__(kThreads) gen_bwd_kernel(const GenP P) {
           constexpr int NE = decltype(ne_tag)::value;
           Vec<VEC> xv[NE], ev[NE];
           unsigned eo[NE];
+          float av[NE];
 #pragma unroll
           for (int u = 0; u < NE; ++u) {
             eo[u] = __shfl_sync(gmask, my_e, j + u, LANES);
+            av[u] = 0.f;
             if (AFF) {
               const float a = __shfl_sync(gmask, my_a, j + u, LANES);
+              av[u] = a;
 #pragma unroll
               for (int k = 0; k < VEC; ++k) ev[u].v[k] = fmaf(a, pv.v[k], qv.v[k]);
             }
@@ -510,6 +525,10 @@ __global__ void __launch_bounds__(kThreads) gen_bwd_kernel(const GenP P) {
                 gv = gin[k];
               }
               ge.v[k] = (RAW || pre > 0.f) ? gv : 0.f;
+              if (AFF) {
+                su[k] = fmaf(av[u], ge.v[k], su[k]);
+                sv[k] += ge.v[k];
+              }
             }
             st_v<VEC, FULL>(row_ptr(gec, eo[u], H), ge, cok, true);
           }
@@ -518,6 +537,24 @@ __global__ void __launch_bounds__(kThreads) gen_bwd_kernel(const GenP P) {
         for (; j + UN <= cnt; j += UN) step(std::integral_constant<int, UN>{}, j);
         for (; j < cnt; ++j) step(std::integral_constant<int, 1>{}, j);
       }
+      if (pq_on && cok) {
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) {
+          my_stage[c + k] = su[k];
+          my_stage[H + c + k] = sv[k];
+        }
+      }
+    }
+  }
+
+  if (pq_on) {   // this block's rows, added in lane-group order
+    __syncthreads();
+    const unsigned H2 = 2 * P.H;
+    for (unsigned j = threadIdx.x; j < H2; j += kThreads) {
+      float sum = 0.f;
+#pragma unroll 4
+      for (int gi = 0; gi < G; ++gi) sum += pq_stage[(size_t)gi * H2 + j];
+      P.pq_part[(size_t)blockIdx.x * H2 + j] = sum;
     }
   }
 
@@ -762,7 +799,15 @@ inline long long grid_for(long long n, const Cfg& c) {
 template <bool FWD, int LANES, int VEC, int KIND, int SRC, bool FULL>
 void launch(const GenP& P, unsigned grid, cudaStream_t st) {
   if (FWD) gen_fwd_kernel<LANES, VEC, KIND, SRC, FULL><<<grid, kThreads, 0, st>>>(P);
-  else gen_bwd_kernel<LANES, VEC, KIND, SRC, FULL><<<grid, kThreads, 0, st>>>(P);
+  else {
+    size_t smem = 0;
+    if (SRC == S_XA && P.pq_part) {
+      smem = (size_t)(kThreads / LANES) * 2 * P.H * sizeof(float);
+      if (smem > 48 * 1024)
+        cudaFuncSetAttribute(gen_bwd_kernel<LANES, VEC, KIND, SRC, FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    }
+    gen_bwd_kernel<LANES, VEC, KIND, SRC, FULL><<<grid, kThreads, smem, st>>>(P);
+  }
 }
 
 template <bool FWD, int KIND, int SRC>
@@ -923,12 +968,36 @@ extern "C" int mlg_gen_aggr_fwd_affine(const float* x, const float* edge_scalar,
   return MLG_OK;
 }
 
+// wcolsum.cu
+int mlg_detail_colsum_partials(const float* partial, long long n_part, long long C, float* u, float* v, float* scratch,
+                               cudaStream_t st);
+long long mlg_detail_colsum_partials_scratch_floats(long long C);
+
+namespace {
+constexpr long long kPqSmemMax = 200 * 1024;   // [lane groups][2][H] staging of the fused edge-term gradient
+inline bool pq_fused(long long H) { return (long long)(kThreads / pick_cfg(H).lanes) * 2 * H * 4 <= kPqSmemMax; }
+}  // namespace
+
+extern "C" int64_t mlg_gen_aggr_bwd_affine_workspace_bytes(int64_t n, int64_t n_edges, int64_t H) {
+  if (n <= 0 || H <= 0) return 16;
+  if (pq_fused(H)) return 4 * (grid_for(n, pick_cfg(H)) * 2 * H + mlg_detail_colsum_partials_scratch_floats(H));
+  return mlg_wcolsum_workspace_bytes(n_edges, H);
+}
+
 extern "C" int mlg_gen_aggr_bwd_affine(const float* g, const float* x, const float* edge_scalar, const float* edge_p,
                                        const float* edge_q, const int32_t* rowptr, const int32_t* col, const int32_t* eid,
-                                       int64_t n, int64_t H, int mode, int learn, float t, const float* t_dev, float p,
-                                       const float* p_dev, const float* y_dev, float eps, int epilogue,
-                                       const float* msg_scale_dev, const float* m, const float* aux, float* g_edge,
-                                       float* g_x, float* partials, void* stream) {
+                                       int64_t n, int64_t n_edges, int64_t H, int mode, int learn, float t,
+                                       const float* t_dev, float p, const float* p_dev, const float* y_dev, float eps,
+                                       int epilogue, const float* msg_scale_dev, const float* m, const float* aux,
+                                       float* g_edge, float* g_x, float* partials, float* g_p, float* g_q, void* workspace,
+                                       int64_t workspace_bytes, void* stream) {
+  const bool want_pq = g_p != nullptr || g_q != nullptr;
+  MLG_CHECK_ARG(!want_pq || (workspace && workspace_bytes >= mlg_gen_aggr_bwd_affine_workspace_bytes(n, n_edges, H)),
+                "mlg_gen_aggr_bwd_affine: g_p / g_q need a workspace of mlg_gen_aggr_bwd_affine_workspace_bytes()");
+  if (want_pq && n == 0) {
+    if (g_p) cudaMemsetAsync(g_p, 0, (size_t)H * 4, (cudaStream_t)stream);
+    if (g_q) cudaMemsetAsync(g_q, 0, (size_t)H * 4, (cudaStream_t)stream);
+  }
   MLG_CHECK_ARG(x && edge_scalar && edge_p && edge_q, "mlg_gen_aggr_bwd_affine: null x / edge_scalar / edge_p / edge_q");
   int rc = check_common("mlg_gen_aggr_bwd_affine", x, nullptr, rowptr, col, n, H, epilogue, msg_scale_dev);
   if (rc) return rc;
@@ -943,8 +1012,17 @@ extern "C" int mlg_gen_aggr_bwd_affine(const float* g, const float* x, const flo
   P.t = t; P.p = p; P.eps = eps; P.t_dev = t_dev; P.p_dev = p_dev; P.y_dev = y_dev;
   P.scale_dev = msg_scale_dev; P.g = g; P.m_in = m; P.aux_in = aux;
   P.g_edge = g_edge; P.g_x = g_x; P.partials = partials;
+  const bool fused = want_pq && pq_fused(H);
+  if (fused) P.pq_part = (float*)workspace;
   rc = dispatch<false>(P, (cudaStream_t)stream);
   if (rc) return rc;
   MLG_CHECK_LAUNCH("mlg_gen_aggr_bwd_affine");
+  if (fused) {
+    const long long parts = grid_for(n, pick_cfg(H));
+    return mlg_detail_colsum_partials((const float*)workspace, parts, H, g_p, g_q, (float*)workspace + parts * 2 * H,
+                                      (cudaStream_t)stream);
+  }
+  if (want_pq)   // very wide rows: one extra streaming pass over g_edge
+    return mlg_wcolsum(g_edge, H, edge_scalar, n_edges, H, g_p, g_q, workspace, workspace_bytes, stream);
   return MLG_OK;
 }

@@ -79,6 +79,34 @@ wcolsum_reduce_kernel(const float* __restrict__ partial, int n_part, int C2, flo
   }
 }
 
+// first level of a two-level reduction over many per-block partials: slice y adds partial rows [y*per, (y+1)*per)
+__global__ void __launch_bounds__(256)
+colsum_slices_kernel(const float* __restrict__ partial, int n_part, int per, int C2, float* __restrict__ out /* [slices][C2] */) {
+  __shared__ float sm[8][32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int j = blockIdx.x * 32 + lane;
+  const int p0 = blockIdx.y * per, p1 = min(n_part, p0 + per);
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  if (j < C2) {
+    int p = p0 + w;
+    for (; p + 24 < p1; p += 32) {
+      s0 += partial[(size_t)p * C2 + j];
+      s1 += partial[(size_t)(p + 8) * C2 + j];
+      s2 += partial[(size_t)(p + 16) * C2 + j];
+      s3 += partial[(size_t)(p + 24) * C2 + j];
+    }
+    for (; p < p1; p += 8) s0 += partial[(size_t)p * C2 + j];
+  }
+  sm[w][lane] = (s0 + s1) + (s2 + s3);
+  __syncthreads();
+  if (w == 0 && j < C2) {
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += sm[k][lane];
+    out[(size_t)blockIdx.y * C2 + j] = s;
+  }
+}
+
 inline int wc_blocks(long long rows) {
   long long b = (rows + kWarps - 1) / kWarps;
   const long long cap = 148 * 4;
@@ -86,6 +114,27 @@ inline int wc_blocks(long long rows) {
 }
 
 }  // namespace
+
+// u[c] = sum_p partial[p][c], v[c] = sum_p partial[p][C + c] for per-block partials [n_part][2C] (the fused edge-term
+// gradient of gen_bwd_kernel); scratch holds kPartSlices * 2C floats.  Fixed summation order.
+constexpr int kPartSlices = 64;
+int mlg_detail_colsum_partials(const float* partial, long long n_part, long long C, float* u, float* v, float* scratch,
+                               cudaStream_t st) {
+  const int C2 = (int)(2 * C);
+  const unsigned gx = (unsigned)mlg_ceil_div(C2, 32);
+  if (n_part > 4 * kPartSlices) {
+    const int per = (int)mlg_ceil_div(n_part, kPartSlices);
+    const int slices = (int)mlg_ceil_div(n_part, per);
+    colsum_slices_kernel<<<dim3(gx, slices), 256, 0, st>>>(partial, (int)n_part, per, C2, scratch);
+    MLG_CHECK_LAUNCH("colsum_slices");
+    wcolsum_reduce_kernel<<<gx, 256, 0, st>>>(scratch, slices, C2, u, v);
+  } else {
+    wcolsum_reduce_kernel<<<gx, 256, 0, st>>>(partial, (int)n_part, C2, u, v);
+  }
+  MLG_CHECK_LAUNCH("colsum_partials");
+  return MLG_OK;
+}
+long long mlg_detail_colsum_partials_scratch_floats(long long C) { return (long long)kPartSlices * 2 * C; }
 
 extern "C" int64_t mlg_wcolsum_workspace_bytes(int64_t rows, int64_t C) { return (int64_t)wc_blocks(rows) * 2 * C * 4; }
 

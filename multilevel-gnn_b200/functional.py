@@ -412,27 +412,26 @@ class GenAggregateAffine(torch.autograd.Function):
         g_x = torch.empty(n, H, dtype=torch.float32, device=dev)
         rows = L.mlg_gen_aggr_bwd_partial_rows(n, H)
         partials = torch.empty(rows, 4, dtype=torch.float32, device=dev)
+        needs = ctx.needs_input_grad
+        want_pq = needs[2] or needs[3]
+        gp = gq = ws = None
+        ws_bytes = 0
+        if want_pq:
+            gp, gq = torch.empty_like(pd), torch.empty_like(qd)
+            ws_bytes = L.mlg_gen_aggr_bwd_affine_workspace_bytes(n, n_edges, H)
+            ws = torch.empty((ws_bytes + 3) // 4, dtype=torch.float32, device=dev)
         with torch.cuda.device(dev), _cabi.span("gen_aggr_bwd_affine", 4 * H * (n_edges + 4 * n) + 12 * n_edges):
             _cabi.check(L.mlg_gen_aggr_bwd_affine(
                 _cabi.fptr(g), _cabi.fptr(xd), _cabi.fptr(ad), _cabi.fptr(pd), _cabi.fptr(qd), _cabi.iptr(csr.rowptr),
-                _cabi.iptr(csr.col), None if topo.fwd_identity else _cabi.iptr(csr.eid), n, H, ctx.mode, int(ctx.learn),
-                t_h, t_d, p_h, p_d, y_d, ctx.eps, ctx.epilogue, s_d, _cabi.fptr(m), _cabi.fptr(aux, True),
-                _cabi.fptr(g_edge), _cabi.fptr(g_x), _cabi.fptr(partials), _cabi.stream_ptr()), "mlg_gen_aggr_bwd_affine")
-        needs = ctx.needs_input_grad
+                _cabi.iptr(csr.col), None if topo.fwd_identity else _cabi.iptr(csr.eid), n, n_edges, H, ctx.mode,
+                int(ctx.learn), t_h, t_d, p_h, p_d, y_d, ctx.eps, ctx.epilogue, s_d, _cabi.fptr(m), _cabi.fptr(aux, True),
+                _cabi.fptr(g_edge), _cabi.fptr(g_x), _cabi.fptr(partials), _cabi.fptr(gp, True), _cabi.fptr(gq, True),
+                _cabi.fptr(ws, True), ws_bytes, _cabi.stream_ptr()), "mlg_gen_aggr_bwd_affine")
         gx = None
         if needs[0]:
             bw = topo.bwd
             gx = gather_sum(g_edge, bw.rowptr, bw.eid, n, out=g_x, addend=g_x, tag="gen_aggr_bwd_src")
-        ga = gp = gq = None
-        if (needs[2] or needs[3]) and n_edges > 0:
-            gp, gq = torch.empty_like(pd), torch.empty_like(qd)
-            ws_bytes = L.mlg_wcolsum_workspace_bytes(n_edges, H)
-            ws = torch.empty(ws_bytes // 4, dtype=torch.float32, device=dev)
-            with torch.cuda.device(dev), _cabi.span("gen_edge_pq_grad", 4 * H * n_edges):
-                _cabi.check(L.mlg_wcolsum(_cabi.fptr(g_edge), H, _cabi.fptr(ad), n_edges, H, _cabi.fptr(gp), _cabi.fptr(gq),
-                                          _cabi.fptr(ws), ws_bytes, _cabi.stream_ptr()), "mlg_wcolsum")
-        elif needs[2] or needs[3]:
-            gp, gq = torch.zeros_like(pd), torch.zeros_like(qd)
+        ga = None
         if needs[1]:      # gradient w.r.t. the scalar edge attribute itself (not needed by the reference's data path)
             ga = (g_edge[:n_edges] @ pd).reshape(ctx.a_shape)
         sums = None

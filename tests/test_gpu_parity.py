@@ -269,6 +269,33 @@ def test_gen_aggregate_affine_vs_materialized(mlg, aggr, H, epi):
             assert_close(u, v, rtol=2e-4, atol=1e-5 * max(1.0, float(v.abs().max())), what="grad[%d]" % i)
 
 
+@pytest.mark.parametrize("C", [128, 64, 32, 20, 256])
+def test_gather_sum_hub_rows(mlg, C):
+    """Rows far longer than the mean (hubs of a by-source kNN CSR) are walked by the whole block: same sums as a
+    float64 index_add, with weights / mean post-scale / addend, for every lane-group width."""
+    Fn = mlg.functional
+    g = torch.Generator().manual_seed(5 + C)
+    n, n_src = 700, 5000
+    deg = torch.randint(0, 12, (n,), generator=g)
+    deg[[3, 77, 78, 300, 699]] = torch.tensor([1502, 97, 96, 640, 2049])
+    rowptr = torch.zeros(n + 1, dtype=torch.int64)
+    rowptr[1:] = deg.cumsum(0)
+    nnz = int(rowptr[-1])
+    idx = torch.randint(0, n_src, (nnz,), generator=g)
+    val = torch.rand(nnz, generator=g)
+    src = torch.randn(n_src, C, generator=g)
+    add = torch.randn(n, C, generator=g)
+    rows = torch.arange(n).repeat_interleave(deg)
+    ref = torch.zeros(n, C, dtype=torch.float64).index_add_(0, rows, src[idx].double() * val.double()[:, None])
+    ref = ref / deg.clamp(min=1).double()[:, None] + add.double()
+    out = Fn.gather_sum(src.to(DEV), rowptr.to(torch.int32).to(DEV), idx.to(torch.int32).to(DEV), n, val=val.to(DEV),
+                        post_mode=1, addend=add.to(DEV))
+    assert_close(out, ref.float(), rtol=1e-4, atol=1e-5, what="hub gather_sum C=%d" % C)
+    out2 = Fn.gather_sum(src.to(DEV), rowptr.to(torch.int32).to(DEV), idx.to(torch.int32).to(DEV), n, val=val.to(DEV),
+                         post_mode=1, addend=add.to(DEV))
+    assert torch.equal(out, out2), "hub rows must be summed in a fixed order"
+
+
 def test_wcolsum(mlg):
     L, cabi = mlg._cabi.lib(), mlg._cabi
     for rows, C in ((1, 4), (777, 128), (50001, 64), (4099, 1024)):
