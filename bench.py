@@ -40,6 +40,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-genconv", action="store_true", help="skip the GENConv aggregation roofline microbench")
     ap.add_argument("--no-graph", action="store_true", help="do not capture the step as a CUDA graph")
+    ap.add_argument("--nccl-update", action="store_true",
+                    help="N>1: NCCL all-reduce + replicated Adam instead of the fused NVLink peer-memory update kernel")
     return ap.parse_args()
 
 
@@ -306,7 +308,7 @@ def run_b200(a):
     host = m.synth.multilevel_batch(batch_size=B, seed=100 + rank).pin_memory()
     host.topology_key = "fold0"
     weight = torch.tensor([[0.8, 1.3]]).repeat(B, 1).to(dev)
-    tr = Trainer(model, args, weight, world_size=world)
+    tr = Trainer(model, args, weight, world_size=world, peer_update=False if a.nccl_update else None)
     resident = host.to(dev)
     resident.topology_key = "fold0"
     hbm_peak, peak_src = peaks()
@@ -410,6 +412,9 @@ def run_b200(a):
         "config": {"workload": "config/%s.yaml MultilevelGNN train step (fwd+bwd+allreduce+Adam), %d graphs/GPU, "
                                "N=15405 nodes, E=92430 edges/graph, G=25015, P=%d" % (a.config, B, args.pca_dim),
                    "graphs_per_gpu": B, "parallelism": "dp%d" % world, "step": ("eager" if tr.graph is None else "one CUDA graph (fwd+loss+bwd+Adam)" if world == 1 else
+                            "one CUDA graph per rank (fwd+loss+bwd + ONE fused kernel: gradient reduce-scatter -> Adam on the "
+                            "owned shard -> parameter all-gather over NVLink peer memory; no NCCL call in the step)"
+                            if tr.peer is not None else
                             "CUDA graph (fwd+loss+bwd) -> NCCL all-reduce -> CUDA graph (Adam)"),
                    "l2": "no flush: per-step working set (~2 GB of activations) exceeds the 126 MB L2",
                    "e2e_h2d": "per-step node features, labels, age from pinned memory; the edge list / pooling layout "
@@ -418,6 +423,9 @@ def run_b200(a):
         "e2e": {"value": round(B * world * a.steps / (ms_e2e / 1e3), 2), "unit": "graphs/s",
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "ms_per_step": round(ms_e2e / a.steps, 4)},
         "gpu_launches": launches, "clocks": clocks, "roofline": roof, "loss": loss_value,
+        "dp_update": (None if world == 1 else "nccl all-reduce + replicated Adam" if tr.peer is None else
+                      {"kernel": "peer_adam_kernel (reduce-scatter -> Adam shard -> all-gather over NVLink peer memory)",
+                       "status": tr.peer.status()}),
         "cuda_graph": tr.graph is not None,
     }
     if world == 1 and not a.no_genconv:

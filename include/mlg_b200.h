@@ -322,6 +322,29 @@ int mlg_gemm_tf32x3(const float* A, int64_t lda, const float* B_hi, const float*
 int mlg_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, float* step_dev, int64_t n,
                   float lr, float beta1, float beta2, float eps, float weight_decay, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Data-parallel optimizer step over NVLink / NVSwitch peer memory: reduce-scatter(gradients) -> Adam on the owned
+ * 1/world shard -> all-gather(parameters) as ONE kernel per rank, replacing "NCCL all-reduce + replicated Adam" of the
+ * data-parallel wrapper around train.py:62-66 (the reference itself is single-device).  Every rank keeps its flat
+ * gradient bucket, flat parameter buffer and a flag block (mlg_peer_flag_bytes(), zero-initialised) in device memory
+ * from mlg_peer_alloc (cudaMalloc, zeroed) that the other ranks of the box map with mlg_peer_export / mlg_peer_open
+ * (CUDA IPC, 64-byte handle).  peer_grads / peer_params / peer_flags are HOST arrays of `world` device pointers indexed
+ * by rank (entry `rank` = this rank's own buffers).  n_padded: elements per buffer, a multiple of 4*world; rank r owns
+ * [r, r+1) * n_padded/world, and exp_avg / exp_avg_sq hold only that shard.  Gradients are summed in rank order and
+ * scaled by 1/world, so every rank ends with bitwise identical parameters.  step_dev as in mlg_adam_step.  The kernel
+ * synchronises the ranks itself (system-scope flags): every rank must issue the same sequence of calls; a wait longer
+ * than timeout_s (<= 0: 5 s) gives up and sets the status word read by mlg_peer_status (0 = ok).  Graph-capturable. */
+int64_t mlg_peer_flag_bytes(void);
+void* mlg_peer_alloc(int64_t bytes);
+int mlg_peer_free(void* ptr);
+int mlg_peer_export(void* ptr, void* handle64);
+void* mlg_peer_open(const void* handle64);
+int mlg_peer_close(void* ptr);
+int mlg_peer_adam_step(const float* const* peer_grads, float* const* peer_params, void* const* peer_flags, int world,
+                       int rank, int64_t n_padded, float* exp_avg, float* exp_avg_sq, float* step_dev, float lr,
+                       float beta1, float beta2, float eps, float weight_decay, double timeout_s, void* stream);
+int mlg_peer_status(const void* flags, int* status_out);
+
 #ifdef __cplusplus
 }
 #endif

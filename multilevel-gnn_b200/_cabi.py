@@ -78,6 +78,15 @@ _SIGNATURES = {
     "mlg_gemm_tf32x3_supported": (_c_int, [_c_i64, _c_i64, _c_i64]),
     "mlg_gemm_tf32x3": (_c_int, [_c_vp, _c_i64, _c_vp, _c_vp, _c_vp, _c_vp, _c_i64, _c_i64, _c_i64, _c_i64, _c_int, _c_f32,
                                  _c_vp]),
+    "mlg_peer_flag_bytes": (_c_i64, []),
+    "mlg_peer_alloc": (_c_vp, [_c_i64]),
+    "mlg_peer_free": (_c_int, [_c_vp]),
+    "mlg_peer_export": (_c_int, [_c_vp, _c_vp]),
+    "mlg_peer_open": (_c_vp, [_c_vp]),
+    "mlg_peer_close": (_c_int, [_c_vp]),
+    "mlg_peer_adam_step": (_c_int, [_c_vp, _c_vp, _c_vp, _c_int, _c_int, _c_i64, _c_vp, _c_vp, _c_vp, _c_f32, _c_f32, _c_f32,
+                                    _c_f32, _c_f32, ctypes.c_double, _c_vp]),
+    "mlg_peer_status": (_c_int, [_c_vp, _c_vp]),
     "mlg_adam_step": (_c_int, [_c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_i64, _c_f32, _c_f32, _c_f32, _c_f32, _c_f32, _c_vp]),
     "mlg_knn_graph": (_c_int, [_c_vp, _c_i64, _c_i64, _c_i64, _c_i64, _c_i64, _c_int, _c_vp, _c_vp, _c_vp, _c_vp,
                                _c_i64, _c_vp]),

@@ -30,10 +30,13 @@ class GradBucket:
     synchronisation is ONE all-reduce with no packing/unpacking (NCCL: op=AVG folds the 1/world scale in;
     gloo has no AVG, so SUM + scale).  Parameters that never get a gradient are not in the bucket."""
 
-    def __init__(self, params):
+    def __init__(self, params, flat=None):
         self.params = list(params)
         dev = self.params[0].device
-        self.flat = torch.zeros(sum(p.numel() for p in self.params), dtype=torch.float32, device=dev)
+        n = sum(p.numel() for p in self.params)
+        # ``flat``: caller-provided storage (PeerArena: peer-mapped device memory, padded past n)
+        self.flat = torch.zeros(n, dtype=torch.float32, device=dev) if flat is None else flat
+        assert self.flat.numel() >= n and self.flat.is_contiguous()
         off = 0
         for p in self.params:
             p.grad = self.flat[off:off + p.numel()].view_as(p)
@@ -102,17 +105,159 @@ class FlatAdam:
                                         float(self.wd), _cabi.stream_ptr()), "mlg_adam_step")
 
 
+class _DeviceSpan:
+    """A raw device allocation exposed through __cuda_array_interface__ so that torch can alias it (no copy)."""
+
+    def __init__(self, ptr, n_floats):
+        self.__cuda_array_interface__ = {"shape": (n_floats,), "typestr": "<f4", "data": (ptr, False), "version": 3,
+                                         "strides": None}
+
+
+class PeerArena:
+    """This rank's peer-visible device memory [gradient bucket | parameters | flag block] (mlg_peer_alloc) and the
+    mappings of every other rank's arena (CUDA IPC handles exchanged once through torch.distributed).  ``group_arenas``
+    lets several arenas of ONE process stand in for the ranks (single-GPU protocol test)."""
+
+    def __init__(self, n, world, rank, device, exchange=True):
+        from . import _cabi
+        L = _cabi.lib()
+        self.world, self.rank, self.device = world, rank, device
+        self.n_padded = -(-n // (4 * world)) * (4 * world)
+        self.flag_bytes = int(L.mlg_peer_flag_bytes())
+        self.bytes = 2 * 4 * self.n_padded + self.flag_bytes
+        with torch.cuda.device(device):
+            self.base = L.mlg_peer_alloc(self.bytes)
+        if not self.base:
+            raise RuntimeError("mlg_peer_alloc failed: %s" % _cabi.last_error())
+        self._opened = []
+        self._hold = (_DeviceSpan(self.base, self.n_padded), _DeviceSpan(self.base + 4 * self.n_padded, self.n_padded))
+        self.grad = torch.as_tensor(self._hold[0], device=device)
+        self.param = torch.as_tensor(self._hold[1], device=device)
+        self.peer_base = [None] * world
+        self.peer_base[rank] = self.base
+        if exchange and world > 1:
+            self._exchange()
+
+    def _exchange(self):
+        import ctypes
+        from . import _cabi
+        L = _cabi.lib()
+        handle = ctypes.create_string_buffer(64)
+        _cabi.check(L.mlg_peer_export(self.base, handle), "mlg_peer_export")
+        handles = [None] * self.world
+        dist.all_gather_object(handles, bytes(handle.raw))
+        with torch.cuda.device(self.device):
+            for r, h in enumerate(handles):
+                if r == self.rank:
+                    continue
+                buf = ctypes.create_string_buffer(h, 64)
+                ptr = L.mlg_peer_open(buf)
+                if not ptr:
+                    raise RuntimeError("mlg_peer_open(rank %d) failed: %s" % (r, _cabi.last_error()))
+                self._opened.append(ptr)
+                self.peer_base[r] = ptr
+
+    def pointer_tables(self):
+        """(grads, params, flags): ctypes arrays of ``world`` device pointers, indexed by rank."""
+        import ctypes
+        arr = ctypes.c_void_p * self.world
+        g = arr(*[b for b in self.peer_base])
+        p = arr(*[b + 4 * self.n_padded for b in self.peer_base])
+        f = arr(*[b + 8 * self.n_padded for b in self.peer_base])
+        return g, p, f
+
+    def status(self):
+        import ctypes
+        from . import _cabi
+        out = ctypes.c_int(0)
+        _cabi.check(_cabi.lib().mlg_peer_status(self.base + 8 * self.n_padded, ctypes.byref(out)), "mlg_peer_status")
+        return out.value
+
+    def close(self):
+        from . import _cabi
+        L = _cabi.lib()
+        for ptr in self._opened:
+            L.mlg_peer_close(ptr)
+        self._opened = []
+        # the arena itself stays allocated for the life of the process: parameters and gradients alias it
+
+
+class PeerAdam:
+    """Data-parallel optimizer step as ONE kernel over NVLink peer memory (mlg_peer_adam_step): reduce-scatter of the
+    gradient buckets, torch.optim.Adam on the owned 1/world shard (ZeRO-1: the moment buffers exist once per box),
+    all-gather of the updated parameters -- no NCCL call, no second graph, every rank bitwise in step.  Parameters are
+    re-homed as views of the arena's parameter buffer (like FlatAdam)."""
+
+    def __init__(self, bucket, arena, lr, betas, eps=1e-8, weight_decay=0.0, timeout_s=5.0):
+        self.bucket, self.arena = bucket, arena
+        self.lr, self.betas, self.eps, self.wd, self.timeout_s = lr, betas, eps, weight_decay, timeout_s
+        self.flat_p = arena.param
+        off = 0
+        for p in bucket.params:
+            n = p.numel()
+            self.flat_p[off:off + n].copy_(p.data.reshape(-1))
+            p.data = self.flat_p[off:off + n].view_as(p)
+            off += n
+        shard = arena.n_padded // arena.world
+        self.exp_avg = torch.zeros(shard, dtype=torch.float32, device=arena.device)
+        self.exp_avg_sq = torch.zeros(shard, dtype=torch.float32, device=arena.device)
+        self.step_dev = torch.zeros(1, dtype=torch.float32, device=arena.device)
+        self._tables = arena.pointer_tables()
+
+    def step(self):
+        from . import _cabi
+        L = _cabi.lib()
+        a = self.arena
+        g, p, f = self._tables
+        with torch.cuda.device(a.device):
+            _cabi.check(L.mlg_peer_adam_step(g, p, f, a.world, a.rank, a.n_padded, _cabi.fptr(self.exp_avg),
+                                             _cabi.fptr(self.exp_avg_sq), _cabi.fptr(self.step_dev), float(self.lr),
+                                             float(self.betas[0]), float(self.betas[1]), float(self.eps), float(self.wd),
+                                             float(self.timeout_s), _cabi.stream_ptr()), "mlg_peer_adam_step")
+
+
+def peer_update_available(world, device):
+    """True when every rank of the job sits on one box with CUDA peer access to every other rank's GPU (NVLink /
+    NVSwitch) -- the precondition of PeerAdam.  Collective: every rank must call it."""
+    if world <= 1 or device.type != "cuda" or not dist.is_initialized() or dist.get_backend() != "nccl" or world > 8:
+        return False
+    ids = [None] * world
+    dist.all_gather_object(ids, (torch.cuda.current_device(), __import__("socket").gethostname()))
+    mine = torch.cuda.current_device()
+    ok = len({h for _, h in ids}) == 1 and len({d for d, _ in ids}) == world
+    ok = ok and all(d == mine or torch.cuda.can_device_access_peer(mine, d) for d, _ in ids)
+    flag = torch.tensor([1 if ok else 0], device=device)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    return bool(flag.item())
+
+
 class Trainer:
     """One training step of train.py:38-68 on the B200 kernels; ``capture()`` turns the whole step
     (forward, loss, backward, NCCL all-reduce, fused Adam) into ONE CUDA graph replayed per step."""
 
-    def __init__(self, model, args, criterion_weight=None, world_size=1, fused_adam=True):
+    def __init__(self, model, args, criterion_weight=None, world_size=1, fused_adam=True, peer_update=None):
+        """peer_update: None = use the fused NVLink peer-memory update (PeerAdam) whenever the job allows it (one box,
+        NCCL process group, peer access between all ranks, no gradient clipping -- clipping needs the averaged gradient
+        on every rank before the update); False = NCCL all-reduce + replicated FlatAdam; True = require PeerAdam."""
         self.model, self.args, self.world = model, args, world_size
         self.params = [p for n, p in model.named_parameters() if p.requires_grad and not n.endswith("lin_l.weight")]
         dev = self.params[0].device
-        self.bucket = GradBucket(self.params)
+        self.peer = None
+        want_peer = (peer_update is not False and fused_adam and world_size > 1 and dev.type == "cuda"
+                     and not args.clip_grad)
+        if want_peer and not peer_update_available(world_size, dev):
+            if peer_update:
+                raise RuntimeError("peer_update=True but the ranks do not all have CUDA peer access on one box")
+            want_peer = False
+        if want_peer:
+            self.peer = PeerArena(sum(p.numel() for p in self.params), world_size, dist.get_rank(), dev)
+            self.bucket = GradBucket(self.params, flat=self.peer.grad)
+        else:
+            self.bucket = GradBucket(self.params)
         self.flat = self.bucket.flat
-        if fused_adam and dev.type == "cuda":
+        if self.peer is not None:
+            self.opt = PeerAdam(self.bucket, self.peer, lr=args.lr, betas=(args.beta1, args.beta2), weight_decay=args.wd)
+        elif fused_adam and dev.type == "cuda":
             self.opt = FlatAdam(self.bucket, lr=args.lr, betas=(args.beta1, args.beta2), weight_decay=args.wd)
         else:
             self.opt = torch.optim.Adam(self.params, lr=args.lr, betas=(args.beta1, args.beta2), weight_decay=args.wd)
@@ -149,16 +294,18 @@ class Trainer:
 
     def _step_eager(self, batch):
         loss = self._fwd_bwd(batch)
-        self.bucket.all_reduce(self.world)
-        self._update()
+        if self.peer is None:
+            self.bucket.all_reduce(self.world)
+        self._update()         # PeerAdam: the update kernel reduces the gradients over NVLink itself
         return loss
 
     def capture(self, batch, warmup=3):
         """Capture the step as CUDA graphs over ``batch``'s device tensors (they become the static input
         buffers).  The CSR / pool layouts are built during the warm-up steps (their one-time host syncs are not
-        capturable).  Single GPU: ONE graph (fwd, loss, bwd, Adam).  Data parallel: graph A (fwd, loss, bwd) ->
-        the NCCL all-reduce issued eagerly on the same stream -> graph B (Adam); the collective stays outside
-        the capture so that NCCL's own stream/event management never interferes with it."""
+        capturable).  Single GPU: ONE graph (fwd, loss, bwd, Adam).  Data parallel with PeerAdam: also ONE graph
+        (fwd, loss, bwd, the fused reduce-scatter/Adam/all-gather kernel).  Data parallel over NCCL: graph A (fwd,
+        loss, bwd) -> the NCCL all-reduce issued eagerly on the same stream -> graph B (Adam); the collective stays
+        outside the capture so that NCCL's own stream/event management never interferes with it."""
         self.static_batch = batch
         cur = torch.cuda.current_stream()
         side = torch.cuda.Stream()
@@ -169,7 +316,7 @@ class Trainer:
         cur.wait_stream(side)
         torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
-        if self.world > 1:
+        if self.world > 1 and self.peer is None:
             self.graph_update = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.graph):
                 self.static_loss = self._fwd_bwd(batch)
