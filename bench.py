@@ -78,17 +78,26 @@ class ClockSampler:
             self.nv, self.h, self.reasons_fn = nv, h, reasons_fn
             self._stop = threading.Event()
             self.thread = threading.Thread(target=self._poll, daemon=True)
-            self.thread.start()
-            return
+            self._sample()
+            self.sm, self.reason_bits = [], 0
         except Exception:
             self.thread = None
+        self.index = index
+
+    def start(self):
+        """Begin polling.  Set-up (NVML import/init: milliseconds) happens in __init__, BEFORE the barrier that opens the
+        timed region -- done inside it, rank 0 would enter the region late and every other rank would wait for it."""
+        if self.thread is not None:
+            self.thread.start()
+            return self
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         try:
-            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
                                        "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
                                       stderr=subprocess.DEVNULL)
         except OSError:
             self.p = None
+        return self
 
     def _sample(self):
         try:
@@ -325,9 +334,11 @@ def run_b200(a):
             tr.step()
 
     # ---- resident leg: `value` ----
-    barrier(world)
     sampler = ClockSampler(local) if rank == 0 else None
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier(world)
+    if sampler:
+        sampler.start()
     e0.record()
     for _ in range(a.steps):
         loss = tr.step(resident)
