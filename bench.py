@@ -351,24 +351,37 @@ def run_b200(a):
 
     # ---- end-to-end leg: pinned host batch -> device EVERY step (train.py:42), loss read back (train.py:62) ----
     # graph mode: the next batch's H2D runs on a copy stream while the current step's graph executes
+    # the loss of EVERY step reaches the host inside the timed region; in graph mode step i's value is awaited while step
+    # i+1 is already running (Trainer.loss_to_host) instead of idling the GPU on a per-step .item()
+    pending = []
+
     def e2e_step(first=False):
         if tr.graph is None:
             return float(tr.step(host.to(dev, non_blocking=True)).item())
         if first:
             tr.prefetch(host)
-        out = tr.step_prefetched()
+        handle = tr.loss_to_host(tr.step_prefetched())
         tr.prefetch(host)                     # H2D of the following step's batch, overlapped with this replay
-        return float(out.item())
+        pending.append(handle)
+        return pending.pop(0).get() if len(pending) > 1 else None
+
+    def e2e_drain():
+        return [h.get() for h in pending[:]], pending.clear()
 
     e2e_step(first=True)
     e2e_step()
+    e2e_drain()
     barrier(world)
     h2d = tr.h2d_bytes(host) if tr.graph is not None else host.nbytes()
+    e2e_losses = []
     e0.record()
     for _ in range(a.steps):
-        e2e_step()
+        e2e_losses.append(e2e_step())
+    e2e_losses += e2e_drain()[0]
     e1.record()
     barrier(world)
+    e2e_losses = [x for x in e2e_losses if x is not None]
+    assert len(e2e_losses) == a.steps and all(x == x for x in e2e_losses), "every step's loss must reach the host"
     ms_e2e = max_over_ranks(e0.elapsed_time(e1), world, dev)
 
     # ---- per-kernel device time (CUDA events around every launch of the same step, eager) ----
@@ -432,7 +445,9 @@ def run_b200(a):
                               "are dataset constants (one gene network for all patients) uploaded once under the "
                               "batch's topology_key"},
         "e2e": {"value": round(B * world * a.steps / (ms_e2e / 1e3), 2), "unit": "graphs/s",
-                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "ms_per_step": round(ms_e2e / a.steps, 4)},
+                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "ms_per_step": round(ms_e2e / a.steps, 4),
+                "loss_readback": "every step's loss is copied to pinned host memory and read by the host inside the timed "
+                                 "region; step i's value is awaited while step i+1 runs"},
         "gpu_launches": launches, "clocks": clocks, "roofline": roof, "loss": loss_value,
         "dp_update": (None if world == 1 else "nccl all-reduce + replicated Adam" if tr.peer is None else
                       {"kernel": "peer_adam_kernel (reduce-scatter -> Adam shard -> all-gather over NVLink peer memory)",

@@ -231,6 +231,17 @@ def peer_update_available(world, device):
     return bool(flag.item())
 
 
+class _PendingLoss:
+    """A loss value on its way to pinned host memory (Trainer.loss_to_host)."""
+
+    def __init__(self, slot, event):
+        self.slot, self.event = slot, event
+
+    def get(self):
+        self.event.synchronize()
+        return float(self.slot[0])
+
+
 class Trainer:
     """One training step of train.py:38-68 on the B200 kernels; ``capture()`` turns the whole step
     (forward, loss, backward, NCCL all-reduce, fused Adam) into ONE CUDA graph replayed per step."""
@@ -384,6 +395,20 @@ class Trainer:
             getattr(self.static_batch, k).copy_(v, non_blocking=True)
         self._consumed.record()
         return self._replay()
+
+    def loss_to_host(self, loss):
+        """Start the device->host copy of a step's loss into a pinned slot and return a handle whose ``get()`` waits for
+        THAT copy only.  train.py:62 reads ``loss.item()`` right after the step, which idles the GPU for a launch latency
+        every step; reading step i's loss while step i+1 runs gives the host the same number one step later."""
+        if getattr(self, "_loss_ring", None) is None:
+            self._loss_ring = [torch.empty(1, dtype=torch.float32).pin_memory() for _ in range(4)]
+            self._loss_events = [torch.cuda.Event() for _ in range(4)]
+            self._loss_slot = 0
+        i = self._loss_slot
+        self._loss_slot = (i + 1) % len(self._loss_ring)
+        self._loss_ring[i].copy_(loss.reshape(1), non_blocking=True)
+        self._loss_events[i].record()
+        return _PendingLoss(self._loss_ring[i], self._loss_events[i])
 
     def step(self, batch=None):
         """forward, loss, backward, (all-reduce), Adam.  Returns the loss as a device scalar (the
