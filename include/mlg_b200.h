@@ -137,6 +137,29 @@ int mlg_gather_sum(const float* src, int64_t ld_src, const int32_t* rowptr, cons
  * folded into the first layer's backward aggregation: g_emb[n,:] = sum_b x[b,n] * g_x0[b,n,:]. */
 int64_t mlg_gather_sum_slices(int64_t n_rows, int64_t C, int64_t replicas);
 
+/* Fully factored first SAGE layer of MultilevelGNN (models/multilevel_gnn.py:150-151 feeding SAGEConv,
+ * gcn_lib/sparse/torch_vertex.py:269-294).  The layer input x0[b,n,:] = x[b,n] * node_embedding[n,:] is rank-1 per node,
+ * so both halves of the update  z = [x0 | mean_j(w_ij x0_j)] [W1 | W2 W_r]^T + bias  factor through two per-gene tables
+ * E_self = emb W1^T and E_nbr = emb (W2 W_r)^T ([n_rows, C], C = Cout):
+ *     out[b*n_rows+i,:] = LeakyReLU_slope( xs[b*n_rows+i] * e_self[i,:]
+ *                                          + (1/cnt_i) * sum_{q in row i} val[q] * xs[b*n_rows+idx[q]] * e_nbr[idx[q],:] + bias )
+ * (cnt_i = row length incl. the added self loop: PyG mean aggregation; bias NULL ok; slope 0 = ReLU).
+ * Neither x0, the [x0 | agg] buffer nor the (replicas*n_rows)-row update GEMM are ever formed.  replicas >= 2, C % 4 == 0,
+ * 16-byte aligned tables / out with leading dimensions that are multiples of 4; CSR / order as in mlg_gather_sum. */
+int mlg_sage_rank1_fwd(const float* xs, const float* e_self, int64_t ld_self, const float* e_nbr, int64_t ld_nbr,
+                       const int32_t* rowptr, const int32_t* idx, const float* val, const int32_t* order, int64_t n_rows,
+                       int64_t C, int64_t replicas, const float* bias, float slope, float* out, int64_t ld_out,
+                       void* stream);
+/* Its backward w.r.t. the tables and the bias from gz = dL/dz [replicas*n_rows, C], one pass over the by-source CSR
+ * (rowptr_t / idx_t / val_t / order_t; inv_cnt[i] = 1/cnt_i of the forward rows, NULL = 1):
+ *     g_e12_parts[s*n_rows+j, 0:C]  = sum_{b in slice s} xs[b,j] * gz[b,j,:]                                       -> g_E_self
+ *     g_e12_parts[s*n_rows+j, C:2C] = sum_{b in slice s} xs[b,j] * sum_{i: j in row i} val_ij * inv_cnt[i] * gz[b,i,:] -> g_E_nbr
+ *     g_bias_parts[s*n_rows+j, :]   = sum_{b in slice s} gz[b,j,:]
+ * for s < mlg_gather_sum_slices(n_rows, C, replicas); the caller adds the slices (fixed order: deterministic). */
+int mlg_sage_rank1_bwd(const float* gz, int64_t ld_g, const float* xs, const int32_t* rowptr_t, const int32_t* idx_t,
+                       const float* val_t, const float* inv_cnt, const int32_t* order_t, int64_t n_rows, int64_t C,
+                       int64_t replicas, float* g_e12_parts, float* g_bias_parts, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Tall-skinny transposed product: out[M,K] = A[rows,M]^T * X[rows,K], colsum[M] = sum_r A[r,:] (NULL ok).
  * The weight / bias gradient of the Linear layers on the path (SAGEConv.update's MLP and lin_r,

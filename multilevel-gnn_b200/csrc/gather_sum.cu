@@ -56,6 +56,13 @@ struct GsP {
   int replicas;
   unsigned rep_rows_src;   // 0: every replica reads the SAME src rows (rank-1 source, pre is per replica)
   unsigned rep_rows_pre;   // rows per replica of `pre` (0: shared)
+  // fully factored rank-1 SAGE layer (mlg_sage_rank1_fwd / _bwd below)
+  const float* e_self;     // fwd: out = act(pre[b,row] * e_self[row] + post * sum + bias)
+  const float* bias;
+  float act_slope;
+  float* aux1;             // bwd (RED): aux1[slice*n + row] = sum_b red_scale[b,row] * addend[b,row]   (NOT added to out)
+  float* auxb;             //            auxb[slice*n + row] = sum_b addend[b,row]
+  unsigned ld_aux1, ld_auxb;
 };
 
 __device__ __forceinline__ const float* rowp(const float* b, unsigned r, unsigned ld) { return b + (size_t)r * ld; }
@@ -237,7 +244,7 @@ __global__ void __launch_bounds__(kThreads) gather_sum_kernel(const GsP P) {
 // RANK1: every replica reads the SAME src rows and differs only by the per-(replica,row) scalar `pre`
 //        (MultilevelGNN layer 0: x0[b,n,:] = x[b,n] * node_embedding[n,:] is never materialised).
 // ---------------------------------------------------------------------------------------------
-template <int LANES, int VEC, bool RANK1, bool RED = false>
+template <int LANES, int VEC, bool RANK1, bool RED = false, bool AUX = false>
 __global__ void __launch_bounds__(kThreads, MLG_GS_MINB) gather_sum_rep_kernel(const GsP P, int gy) {
   constexpr int RPW = 32 / LANES;
   constexpr int CW = LANES * VEC;
@@ -277,9 +284,11 @@ __global__ void __launch_bounds__(kThreads, MLG_GS_MINB) gather_sum_rep_kernel(c
     const bool cok = c < (unsigned)C;
     const float* sc = P.src + (cok ? c : 0u);   // lanes past C read (and discard) the row start: no predicated loads
     const size_t rep_stride = (size_t)P.rep_rows_src * P.ld_src;
-    float red[VEC];
+    float red[VEC], red1[AUX ? VEC : 1], redb[AUX ? VEC : 1];
 #pragma unroll
     for (int k = 0; k < VEC; ++k) red[k] = 0.f;
+#pragma unroll
+    for (int k = 0; k < (AUX ? VEC : 1); ++k) red1[k] = redb[k] = 0.f;
     for (int b0 = b_lo; b0 < b_hi; b0 += RB) {
       const int nb = min(RB, b_hi - b0);
       float acc[RB][VEC];
@@ -344,7 +353,27 @@ __global__ void __launch_bounds__(kThreads, MLG_GS_MINB) gather_sum_rep_kernel(c
         // ran 180 us against 138 us unmasked with the row-by-row epilogue)
         // (two phases -- addend rows, then mask rows -- so that only RB rows are live next to the accumulators)
         float t[RB][VEC];
-        if (P.addend) {
+        if (AUX) {
+          // factored first layer: the row's own gradient rows feed two SEPARATE replica reductions (weighted -> aux1,
+          // plain -> auxb) instead of being added to the gathered sum
+          float w[RB];
+#pragma unroll
+          for (int r = 0; r < RB; ++r) {
+            const unsigned brow = (unsigned)min(b0 + r, b_hi - 1) * (unsigned)P.n + row;
+            ldv<VEC>(t[r], rowp(P.addend, brow, P.ld_add) + c, cok);
+            w[r] = __ldg(P.red_scale + brow);
+          }
+#pragma unroll
+          for (int r = 0; r < RB; ++r) {
+            const bool live = b0 + r < b_hi;
+#pragma unroll
+            for (int k = 0; k < (AUX ? VEC : 1); ++k) {
+              red1[k] = fmaf(live ? w[r] : 0.f, t[r][k], red1[k]);
+              redb[k] += live ? t[r][k] : 0.f;
+              red[k] = fmaf(live ? w[r] * postf : 0.f, acc[r][k], red[k]);
+            }
+          }
+        } else if (P.addend) {
 #pragma unroll
           for (int r = 0; r < RB; ++r)
             ldv<VEC>(t[r], rowp(P.addend, (unsigned)min(b0 + r, b_hi - 1) * (unsigned)P.n + row, P.ld_add) + c, cok);
@@ -367,7 +396,9 @@ __global__ void __launch_bounds__(kThreads, MLG_GS_MINB) gather_sum_rep_kernel(c
 #pragma unroll
             for (int k = 0; k < VEC; ++k) acc[r][k] *= t[r][k] > 0.f ? 1.f : P.mask_slope;
         }
-        if (RED) {   // weighted reduction over the replicas instead of one output row per replica
+        if (AUX) {
+          // reductions done above
+        } else if (RED) {   // weighted reduction over the replicas instead of one output row per replica
 #pragma unroll
           for (int r = 0; r < RB; ++r) {
             const float w = (b0 + r < b_hi) ? __ldg(P.red_scale + (size_t)(b0 + r) * P.n + row) : 0.f;
@@ -378,6 +409,26 @@ __global__ void __launch_bounds__(kThreads, MLG_GS_MINB) gather_sum_rep_kernel(c
 #pragma unroll
           for (int r = 0; r < RB; ++r)
             if (b0 + r < b_hi) stv<VEC>(rowp(P.out, (unsigned)(b0 + r) * (unsigned)P.n + row, P.ld_out) + c, acc[r], cok);
+        }
+      } else if (RANK1 && P.e_self) {
+        // fully factored first layer: y = act(x[b,row] * E_self[row] + mean_j(w_ij x[b,j] E_nbr[j]) + bias), one store
+        float es[VEC], bs[VEC], sc[RB];
+        ldv<VEC>(es, rowp(P.e_self, row, P.ld_self) + c, cok);
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) bs[k] = (cok && P.bias) ? __ldg(P.bias + c + k) : 0.f;   // parameter view: 4-byte aligned only
+#pragma unroll
+        for (int r = 0; r < RB; ++r) sc[r] = __ldg(P.pre + (size_t)min(b0 + r, b_hi - 1) * P.rep_rows_pre + row);
+#pragma unroll
+        for (int r = 0; r < RB; ++r) {
+          if (b0 + r < b_hi) {
+            float y[VEC];
+#pragma unroll
+            for (int k = 0; k < VEC; ++k) {
+              const float z = fmaf(es[k], sc[r], fmaf(acc[r][k], postf, bs[k]));
+              y[k] = z > 0.f ? z : z * P.act_slope;
+            }
+            stv<VEC>(rowp(P.out, (unsigned)(b0 + r) * (unsigned)P.n + row, P.ld_out) + c, y, cok);
+          }
         }
       } else if (RANK1 && !P.relative && !P.addend && !P.mask && P.self_out) {
         // first-layer epilogue: the self row (one embedding row for ALL replicas) and the RB per-replica scalars are
@@ -413,6 +464,16 @@ __global__ void __launch_bounds__(kThreads, MLG_GS_MINB) gather_sum_rep_kernel(c
       }
     }
     if (RED) stv<VEC>(rowp(P.out, (unsigned)ychunk * (unsigned)P.n + row, P.ld_out) + c, red, cok);
+    if (AUX) {
+      float a1[VEC], ab[VEC];
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) {
+        a1[k] = red1[AUX ? k : 0];
+        ab[k] = redb[AUX ? k : 0];
+      }
+      stv<VEC>(rowp(P.aux1, (unsigned)ychunk * (unsigned)P.n + row, P.ld_aux1) + c, a1, cok);
+      stv<VEC>(rowp(P.auxb, (unsigned)ychunk * (unsigned)P.n + row, P.ld_auxb) + c, ab, cok);
+    }
   }
 }
 
@@ -522,6 +583,7 @@ extern "C" int mlg_gather_sum(const float* src, int64_t ld_src, const int32_t* r
   P.ld_src = (unsigned)ld_src; P.ld_out = (unsigned)ld_out; P.ld_add = (unsigned)ld_add; P.ld_self = (unsigned)ld_self;
   P.n = (int)n_rows; P.C = (int)C; P.post_mode = post_mode; P.relative = relative;
   P.replicas = (int)replicas; P.rep_rows_src = (unsigned)rep_rows_src; P.rep_rows_pre = (unsigned)rep_rows_pre;
+  P.e_self = nullptr; P.bias = nullptr; P.act_slope = 0.f; P.aux1 = nullptr; P.auxb = nullptr; P.ld_aux1 = P.ld_auxb = 0;
   cudaStream_t st = (cudaStream_t)stream;
   const int wpb = kThreads / 32;
   int lanes = 32, rows_per_block = wpb;
@@ -553,6 +615,83 @@ extern "C" int mlg_gather_sum(const float* src, int64_t ld_src, const int32_t* r
     else gather_sum_kernel<32, 4><<<(unsigned)gx, kThreads, 0, st>>>(P);
   }
   MLG_CHECK_LAUNCH("mlg_gather_sum");
+  return MLG_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Fully factored first SAGE layer of MultilevelGNN (multilevel_gnn.py:150-151 + torch_vertex.py:269-294).  The layer
+// input x0[b,n,:] = x[b,n] * node_embedding[n,:] is rank-1 per node, so BOTH halves of the update
+//     z = [x0 | mean_j(w_ij x0_j)] * [W1 | W2 W_r]^T + bias
+// factor through two small per-gene tables  E_self = emb W1^T,  E_nbr = emb (W2 W_r)^T  ([N, Cout], a 15 405-row GEMM):
+//     z[b,i,:] = x[b,i] E_self[i,:] + (1/cnt_i) sum_q val_q x[b,idx_q] E_nbr[idx_q,:] + bias.
+// Neither x0, the [x0 | agg] buffer (252 MB at the gbm shape) nor the 492 960-row update GEMM exist any more; the kernel
+// reads the two tables (L2-resident) and x, and writes the activation once.
+// ---------------------------------------------------------------------------------------------
+extern "C" int mlg_sage_rank1_fwd(const float* xs, const float* e_self, int64_t ld_self, const float* e_nbr,
+                                  int64_t ld_nbr, const int32_t* rowptr, const int32_t* idx, const float* val,
+                                  const int32_t* order, int64_t n_rows, int64_t C, int64_t replicas, const float* bias,
+                                  float slope, float* out, int64_t ld_out, void* stream) {
+  MLG_CHECK_ARG(xs && e_self && e_nbr && rowptr && idx && out, "mlg_sage_rank1_fwd: null pointer");
+  MLG_CHECK_ARG(n_rows >= 0 && replicas >= 2 && replicas * n_rows < (1ll << 31) && C > 0 && C % 4 == 0 && C < (1ll << 20),
+                "mlg_sage_rank1_fwd: bad sizes (needs replicas >= 2, C %% 4 == 0)");
+  MLG_CHECK_ARG(ld_self >= C && ld_nbr >= C && ld_out >= C && ld_self % 4 == 0 && ld_nbr % 4 == 0 && ld_out % 4 == 0,
+                "mlg_sage_rank1_fwd: leading dimensions must be >= C and multiples of 4");
+  MLG_CHECK_ARG(((uintptr_t)e_self | (uintptr_t)e_nbr | (uintptr_t)out) % 16 == 0,
+                "mlg_sage_rank1_fwd: 16-byte alignment");
+  if (n_rows == 0) return MLG_OK;
+  GsP P;
+  memset(&P, 0, sizeof(P));
+  P.src = e_nbr; P.ld_src = (unsigned)ld_nbr; P.rowptr = rowptr; P.idx = idx; P.val = val; P.pre = xs; P.order = order;
+  P.out = out; P.ld_out = (unsigned)ld_out; P.e_self = e_self; P.ld_self = (unsigned)ld_self; P.bias = bias;
+  P.act_slope = slope; P.n = (int)n_rows; P.C = (int)C; P.post_mode = 1; P.replicas = (int)replicas;
+  P.rep_rows_src = 0; P.rep_rows_pre = (unsigned)n_rows;
+  int lanes, rpb;
+  rep_geometry(C, true, &lanes, &rpb);
+  const long long gx = mlg_ceil_div(n_rows, rpb);
+  const int gy = rep_slices(gx, replicas);
+  const unsigned grid = (unsigned)(gx * gy);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (lanes == 8) gather_sum_rep_kernel<8, 4, true><<<grid, kThreads, 0, st>>>(P, gy);
+  else if (lanes == 16) gather_sum_rep_kernel<16, 4, true><<<grid, kThreads, 0, st>>>(P, gy);
+  else gather_sum_rep_kernel<32, 4, true><<<grid, kThreads, 0, st>>>(P, gy);
+  MLG_CHECK_LAUNCH("mlg_sage_rank1_fwd");
+  return MLG_OK;
+}
+
+// Backward of the above w.r.t. the two tables and the bias, from gz = dL/dz [replicas*n_rows, C] (one pass, by-source CSR):
+//   g_e12_parts[s*n + j, 0:C]  = sum_{b in slice s} x[b,j] gz[b,j,:]                                  (-> g_E_self)
+//   g_e12_parts[s*n + j, C:2C] = sum_{b in slice s} x[b,j] sum_{i: j in row i} val_ij/cnt_i gz[b,i,:]  (-> g_E_nbr)
+//   g_bias_parts[s*n + j, :]   = sum_{b in slice s} gz[b,j,:]
+// The caller adds the mlg_gather_sum_slices(n_rows, C, replicas) slices (fixed order: deterministic).
+extern "C" int mlg_sage_rank1_bwd(const float* gz, int64_t ld_g, const float* xs, const int32_t* rowptr_t,
+                                  const int32_t* idx_t, const float* val_t, const float* inv_cnt, const int32_t* order_t,
+                                  int64_t n_rows, int64_t C, int64_t replicas, float* g_e12_parts, float* g_bias_parts,
+                                  void* stream) {
+  MLG_CHECK_ARG(gz && xs && rowptr_t && idx_t && g_e12_parts && g_bias_parts, "mlg_sage_rank1_bwd: null pointer");
+  MLG_CHECK_ARG(n_rows >= 0 && replicas >= 2 && replicas * n_rows < (1ll << 31) && C > 0 && C % 4 == 0 && C < (1ll << 20),
+                "mlg_sage_rank1_bwd: bad sizes (needs replicas >= 2, C %% 4 == 0)");
+  MLG_CHECK_ARG(ld_g >= C && ld_g % 4 == 0, "mlg_sage_rank1_bwd: ld_g must be >= C and a multiple of 4");
+  MLG_CHECK_ARG(((uintptr_t)gz | (uintptr_t)g_e12_parts | (uintptr_t)g_bias_parts) % 16 == 0,
+                "mlg_sage_rank1_bwd: 16-byte alignment");
+  if (n_rows == 0) return MLG_OK;
+  GsP P;
+  memset(&P, 0, sizeof(P));
+  P.src = gz; P.ld_src = (unsigned)ld_g; P.rowptr = rowptr_t; P.idx = idx_t; P.val = val_t; P.pre = inv_cnt;
+  P.order = order_t; P.addend = gz; P.ld_add = (unsigned)ld_g; P.red_scale = xs;
+  P.out = g_e12_parts + C; P.ld_out = (unsigned)(2 * C); P.aux1 = g_e12_parts; P.ld_aux1 = (unsigned)(2 * C);
+  P.auxb = g_bias_parts; P.ld_auxb = (unsigned)C;
+  P.n = (int)n_rows; P.C = (int)C; P.post_mode = 0; P.replicas = (int)replicas;
+  P.rep_rows_src = (unsigned)n_rows; P.rep_rows_pre = 0;
+  int lanes, rpb;
+  rep_geometry(C, true, &lanes, &rpb);
+  const long long gx = mlg_ceil_div(n_rows, rpb);
+  const int gy = rep_slices(gx, replicas);
+  const unsigned grid = (unsigned)(gx * gy);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (lanes == 8) gather_sum_rep_kernel<8, 4, false, true, true><<<grid, kThreads, 0, st>>>(P, gy);
+  else if (lanes == 16) gather_sum_rep_kernel<16, 4, false, true, true><<<grid, kThreads, 0, st>>>(P, gy);
+  else gather_sum_rep_kernel<32, 4, false, true, true><<<grid, kThreads, 0, st>>>(P, gy);
+  MLG_CHECK_LAUNCH("mlg_sage_rank1_bwd");
   return MLG_OK;
 }
 

@@ -477,6 +477,9 @@ class SageAggregate(torch.autograd.Function):
         return gx, None, None
 
 
+FACTORED_RANK1 = True    # first layer of MultilevelGNN through mlg_sage_rank1_fwd/_bwd (False: [x0 | agg] buffer + GEMMs)
+
+
 class SageLayer(torch.autograd.Function):
     """One whole SAGEConv layer (torch_vertex.py:269-294 with RSAGEConv's Linear+activation MLP):
         out = act( [x | agg_x] @ [W1 | W2 @ W_r]^T + b ),   nn.0.weight = [W1 | W2], lin_r.weight = W_r
@@ -510,6 +513,33 @@ class SageLayer(torch.autograd.Function):
                                                       _cabi.fptr(wbuf[1]), _cabi.fptr(wbuf[2]), _cabi.fptr(wbuf[3]),
                                                       _cabi.fptr(wbuf[4]), _cabi.stream_ptr()), "mlg_sage_fold_fwd")
         wcat = wbuf[0].view(cout, 2 * cin)
+        ctx.factored = False
+        if (FACTORED_RANK1 and rank1 and not relative and topo.replicas > 1 and cout % 4 == 0
+                and xd.shape[0] == topo.n_single and n == topo.n_single * topo.replicas):
+            # Fully factored first layer: x0 = xs * emb is rank-1 per node, so z = xs[b,i] E_self[i] + mean_j(w_ij xs[b,j]
+            # E_nbr[j]) + b with the per-gene tables [E_self | E_nbr] = emb [W1 ; W2 W_r]^T (an n_single-row GEMM).  Neither
+            # x0, the [x0 | agg] buffer nor the B*N-row update / dgrad / weight-gradient GEMMs exist on this path.
+            L = _cabi.lib()
+            n1 = topo.n_single
+            wst = wcat.view(cout, 2, cin).permute(1, 0, 2).reshape(2 * cout, cin)      # [W1 ; W2 W_r]   [2cout, cin]
+            e12 = torch.mm(xd, wst.t())                                               # [n1, 2cout]
+            y = torch.empty(n, cout, dtype=torch.float32, device=xd.device)
+            csr = topo.fwd
+            bias = None if nn_b is None else _f32c(nn_b.detach())
+            nbytes = 4 * cout * n + 4 * n + 8 * csr.col.numel() + 8 * cout * n1
+            with torch.cuda.device(xd.device), _cabi.span("sage_rank1_fwd", nbytes):
+                _cabi.check(L.mlg_sage_rank1_fwd(
+                    _cabi.fptr(xs_d), _vptr(e12), 2 * cout, _vptr(e12[:, cout:]), 2 * cout, _cabi.iptr(csr.rowptr),
+                    _cabi.iptr(csr.col), _cabi.fptr(topo.fwd_val, True), _cabi.iptr(topo.fwd_order, True), n1, cout,
+                    topo.replicas, _cabi.fptr(bias, True), float(slope), _cabi.fptr(y), cout, _cabi.stream_ptr()),
+                    "mlg_sage_rank1_fwd")
+            ctx.save_for_backward(xd, y, wst, w_r, w_nn, xs_d)
+            ctx.topo, ctx.relative, ctx.slope, ctx.cin, ctx.has_bias = topo, False, float(slope), cin, nn_b is not None
+            ctx.rank1, ctx.factored = True, True
+            ctx.emb_param = x if isinstance(x, torch.nn.Parameter) else None
+            ctx.in_slope = None
+            ctx.out_premasked = bool(out_premasked)
+            return y
         wsplit = (wbuf[1].view(cout, 2 * cin), wbuf[2].view(cout, 2 * cin))
         xcat = torch.empty(n, 2 * cin, dtype=torch.float32, device=xd.device)
         csr = topo.fwd
@@ -531,7 +561,46 @@ class SageLayer(torch.autograd.Function):
         return y
 
     @staticmethod
+    def _backward_factored(ctx, gy):
+        emb, y, wst, w_r, w_nn, xs_d = ctx.saved_tensors
+        topo, cin = ctx.topo, ctx.cin
+        cout = w_nn.shape[0]
+        gy = _f32c(gy)
+        if ctx.out_premasked:
+            gz = gy
+        else:
+            gz = torch.ops.aten.leaky_relu_backward(gy, y, ctx.slope, True) if ctx.slope != 0.0 \
+                else torch.ops.aten.threshold_backward(gy, y, 0.0)
+        L = _cabi.lib()
+        n1, B = topo.n_single, topo.replicas
+        slices = L.mlg_gather_sum_slices(n1, cout, B)
+        parts = torch.empty(slices * n1 * 3 * cout, dtype=torch.float32, device=gz.device)
+        p12 = parts[:slices * n1 * 2 * cout].view(slices, n1, 2 * cout)
+        pb = parts[slices * n1 * 2 * cout:].view(slices * n1, cout)
+        bw = topo.bwd
+        nbytes = 4 * cout * gz.shape[0] + 4 * gz.shape[0] + 8 * bw.col.numel() + 4 * parts.numel()
+        with torch.cuda.device(gz.device), _cabi.span("sage_rank1_bwd", nbytes):
+            _cabi.check(L.mlg_sage_rank1_bwd(
+                _cabi.fptr(gz), cout, _cabi.fptr(xs_d), _cabi.iptr(bw.rowptr), _cabi.iptr(bw.col),
+                _cabi.fptr(topo.bwd_val, True), _cabi.fptr(topo.inv_cnt, True), _cabi.iptr(topo.bwd_order, True), n1, cout, B,
+                _cabi.fptr(p12), _cabi.fptr(pb), _cabi.stream_ptr()), "mlg_sage_rank1_bwd")
+        g12 = p12.sum(0) if slices > 1 else p12[0]                 # [n1, 2cout] = [g_E_self | g_E_nbr]
+        g_b = pb.sum(0) if ctx.has_bias else None
+        slot = grad_slot(ctx.emb_param, (n1, cin)) if ctx.emb_param is not None else None
+        g_emb = torch.mm(g12, wst, out=slot) if slot is not None else torch.mm(g12, wst)
+        g_wst = torch.mm(g12.t(), emb)                             # [2cout, cin] = [g_W1 ; g_(W2 W_r)]
+        g_wcat = g_wst.view(2, cout, cin).permute(1, 0, 2).reshape(cout, 2 * cin)
+        g_wnn, g_wr = torch.empty_like(w_nn), torch.empty_like(w_r)
+        with torch.cuda.device(gz.device):
+            _cabi.check(L.mlg_sage_fold_bwd(_cabi.fptr(g_wcat), _cabi.fptr(w_nn), _cabi.fptr(w_r), cout, cin,
+                                            w_r.shape[0], _cabi.fptr(g_wnn), _cabi.fptr(g_wr), _cabi.stream_ptr()),
+                        "mlg_sage_fold_bwd")
+        return g_emb, None, g_wr, g_wnn, g_b, None, None, None, None, None
+
+    @staticmethod
     def backward(ctx, gy):
+        if ctx.factored:
+            return SageLayer._backward_factored(ctx, gy)
         xcat, y, wbuf, w_r, w_nn, xs_d = ctx.saved_tensors
         topo, cin = ctx.topo, ctx.cin
         cout = w_nn.shape[0]

@@ -572,6 +572,51 @@ def test_activation_backward_fusion_is_equivalent(mlg):
     assert len(seen0) >= 1 and len(seen1) == 0, (seen0, seen1)
 
 
+def test_factored_first_layer_is_equivalent(mlg):
+    """mlg_sage_rank1_fwd/_bwd (first SAGE layer factored through the per-gene tables E_self / E_nbr) against the
+    [x0 | agg] buffer + GEMM path it replaces: prediction, pooled features and every parameter gradient, on the plain
+    and on the activation-unfused chain; and the factored path must be the one that ran."""
+    from multilevel_gnn_b200 import _cabi, configs, functional as Fn, synth
+    for cfg, fuse in (("gbm", True), ("gbm", False), ("kirc", True)):
+        args = configs.make_args(cfg)
+        torch.manual_seed(3)
+        model = mlg.MultilevelGNN(args)
+        synth.multilevel_params(model)
+        model.to(DEV).train()
+        model.pathway_indexs = model.pathway_indexs.to(DEV)
+        b = synth.multilevel_batch(batch_size=5, seed=6).to(DEV)
+        params = [p for n, p in model.named_parameters() if p.requires_grad and not n.endswith("lin_l.weight")]
+
+        def run(factored):
+            Fn.FACTORED_RANK1 = factored
+            type(model).FUSE_ACT_BACKWARD = fuse
+            torch.manual_seed(11)                     # same dropout masks
+            timer = _cabi.KernelTimer()
+            _cabi.TIMER = timer
+            try:
+                pred, feat = model(b)
+                loss = (pred * torch.arange(pred.numel(), device=DEV).reshape(pred.shape)).sum() + feat.square().mean()
+                g = torch.autograd.grad(loss, params, allow_unused=True)
+                torch.cuda.synchronize()
+            finally:
+                _cabi.TIMER = None
+                Fn.FACTORED_RANK1 = True
+                type(model).FUSE_ACT_BACKWARD = True
+            return pred.detach(), feat.detach(), g, set(timer.summary())
+
+        p1, f1, g1, tags1 = run(True)
+        p0, f0, g0, tags0 = run(False)
+        assert {"sage_rank1_fwd", "sage_rank1_bwd"} <= tags1 and not ({"sage_rank1_fwd", "sage_rank1_bwd"} & tags0), (tags1, tags0)
+        assert_close(p1, p0, rtol=1e-5, atol=1e-6, what="factored vs buffered pred")
+        assert_close(f1, f0, rtol=1e-4, atol=1e-6, what="factored vs buffered pooled features")
+        for (n, _), a, c in zip([(n, p) for n, p in model.named_parameters() if p.requires_grad and not n.endswith("lin_l.weight")], g1, g0):
+            if a is None or c is None:
+                assert a is None and c is None
+                continue
+            sc = float(c.abs().max().clamp_min(1e-30))          # compare at unit scale: atol is then relative to the largest entry
+            assert_close(a / sc, c / sc, rtol=1e-4, atol=2e-6, what="factored vs buffered grad " + n)
+
+
 def test_maxpool_channel_last_matches_torch(mlg):
     """mlg_maxpool_cl_fwd/bwd vs nn.MaxPool2d on the head's shape and on ragged ones (floor mode drops the tail rows /
     columns); ties (quantised values) must route the gradient to the first maximum like ATen."""
