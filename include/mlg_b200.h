@@ -160,6 +160,16 @@ int mlg_sage_rank1_bwd(const float* gz, int64_t ld_g, const float* xs, const int
                        const float* val_t, const float* inv_cnt, const int32_t* order_t, int64_t n_rows, int64_t C,
                        int64_t replicas, float* g_e12_parts, float* g_bias_parts, void* stream);
 
+/* The same gradients organised by TARGET row so that gz is read exactly once (C == 32 or 64; forward CSR rowptr / idx /
+ * val / order): per entry q of row i (source j = idx[q])  h[q,:] = (val[q] / cnt_i) * sum_b xs[b,j] * gz[b,i,:], and per row
+ * g_self[i,:] = sum_b xs[b,i] * gz[b,i,:] (-> g_E_self, leading dimension ld_self), g_bias_rows[i,:] = sum_b gz[b,i,:].
+ * g_E_nbr[j,:] = sum_{q: idx[q] == j} h[q,:] is a segment sum the caller runs over the by-source CSR with mlg_gather_sum
+ * (single graph, idx = by-source position -> forward position).  h must hold rowptr[n_rows] rows of C floats. */
+int mlg_sage_rank1_bwd_rows_supported(int64_t C);
+int mlg_sage_rank1_bwd_rows(const float* gz, int64_t ld_g, const float* xs, const int32_t* rowptr, const int32_t* idx,
+                            const float* val, const int32_t* order, int64_t n_rows, int64_t C, int64_t replicas, float* h,
+                            float* g_self, int64_t ld_self, float* g_bias_rows, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Tall-skinny transposed product: out[M,K] = A[rows,M]^T * X[rows,K], colsum[M] = sum_r A[r,:] (NULL ok).
  * The weight / bias gradient of the Linear layers on the path (SAGEConv.update's MLP and lin_r,

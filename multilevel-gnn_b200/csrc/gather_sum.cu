@@ -410,26 +410,6 @@ __global__ void __launch_bounds__(kThreads, MLG_GS_MINB) gather_sum_rep_kernel(c
           for (int r = 0; r < RB; ++r)
             if (b0 + r < b_hi) stv<VEC>(rowp(P.out, (unsigned)(b0 + r) * (unsigned)P.n + row, P.ld_out) + c, acc[r], cok);
         }
-      } else if (RANK1 && P.e_self) {
-        // fully factored first layer: y = act(x[b,row] * E_self[row] + mean_j(w_ij x[b,j] E_nbr[j]) + bias), one store
-        float es[VEC], bs[VEC], sc[RB];
-        ldv<VEC>(es, rowp(P.e_self, row, P.ld_self) + c, cok);
-#pragma unroll
-        for (int k = 0; k < VEC; ++k) bs[k] = (cok && P.bias) ? __ldg(P.bias + c + k) : 0.f;   // parameter view: 4-byte aligned only
-#pragma unroll
-        for (int r = 0; r < RB; ++r) sc[r] = __ldg(P.pre + (size_t)min(b0 + r, b_hi - 1) * P.rep_rows_pre + row);
-#pragma unroll
-        for (int r = 0; r < RB; ++r) {
-          if (b0 + r < b_hi) {
-            float y[VEC];
-#pragma unroll
-            for (int k = 0; k < VEC; ++k) {
-              const float z = fmaf(es[k], sc[r], fmaf(acc[r][k], postf, bs[k]));
-              y[k] = z > 0.f ? z : z * P.act_slope;
-            }
-            stv<VEC>(rowp(P.out, (unsigned)(b0 + r) * (unsigned)P.n + row, P.ld_out) + c, y, cok);
-          }
-        }
       } else if (RANK1 && !P.relative && !P.addend && !P.mask && P.self_out) {
         // first-layer epilogue: the self row (one embedding row for ALL replicas) and the RB per-replica scalars are
         // requested together; then 2*RB stores
@@ -473,6 +453,216 @@ __global__ void __launch_bounds__(kThreads, MLG_GS_MINB) gather_sum_rep_kernel(c
       }
       stv<VEC>(rowp(P.aux1, (unsigned)ychunk * (unsigned)P.n + row, P.ld_aux1) + c, a1, cok);
       stv<VEC>(rowp(P.auxb, (unsigned)ychunk * (unsigned)P.n + row, P.ld_auxb) + c, ab, cok);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Fully factored first SAGE layer, forward (mlg_sage_rank1_fwd):
+//     out[b,i,:] = act( x[b,i] E_self[i,:] + (1/cnt_i) sum_q val_q x[b,idx_q] E_nbr[idx_q,:] + bias )
+// Same row / lane-group / replica-slice geometry as gather_sum_rep_kernel<.., RANK1>, but that kernel (2 entries and 4
+// replicas per step under an 80-register budget) measured latency bound here: 8 dependent load round trips per row and
+// slice, 110 us for a 126 MB output.  This one keeps F_JU = 4 entries x F_RB = 8 replicas in flight (table rows + the
+// per-replica scalars of all four entries are requested before the first FMA), 2 blocks/SM.
+// ---------------------------------------------------------------------------------------------
+constexpr int F_RB = 8, F_JU = 4;
+
+template <int LANES>
+__global__ void __launch_bounds__(kThreads, 2) sage_rank1_fwd_kernel(const GsP P, int gy) {
+  constexpr int VEC = 4;
+  constexpr int RPW = 32 / LANES;
+  constexpr int CW = LANES * VEC;
+  const int lane = threadIdx.x & 31;
+  const int sub = lane / LANES, sl = lane % LANES;
+  const unsigned gmask = (LANES == 32) ? 0xffffffffu : (((1u << LANES) - 1u) << (sub * LANES));
+  const int ychunk = blockIdx.x % gy;
+  const long long rowblock = blockIdx.x / gy;
+  const long long warp = (rowblock * (long long)blockDim.x + threadIdx.x) >> 5;
+  const int rep_per_y = (P.replicas + gy - 1) / gy;
+  const int b_lo = ychunk * rep_per_y, b_hi = min(P.replicas, b_lo + rep_per_y);
+  const long long slot = warp * RPW + sub;
+  if (slot >= P.n || b_lo >= b_hi) return;
+  const unsigned row = P.order ? (unsigned)__ldg(P.order + slot) : (unsigned)slot;
+  const int beg = __ldg(P.rowptr + row), end = __ldg(P.rowptr + row + 1);
+  const int cnt_row = end - beg;
+  const float postf = cnt_row > 0 ? 1.f / (float)cnt_row : 0.f;
+  unsigned idx0 = 0;
+  float w0 = 0.f;
+  if (cnt_row > 0) {
+    const int q = min(beg + sl, end - 1);
+    idx0 = (unsigned)__ldg(P.idx + q);
+    w0 = P.val ? __ldg(P.val + q) : 1.f;
+  }
+  const int nchunks = (P.C + CW - 1) / CW;
+  for (int ch = 0; ch < nchunks; ++ch) {
+    const unsigned c = ch * CW + sl * VEC;
+    const bool cok = c < (unsigned)P.C;
+    const float* sc = P.src + (cok ? c : 0u);
+    for (int b0 = b_lo; b0 < b_hi; b0 += F_RB) {
+      float acc[F_RB][VEC];
+#pragma unroll
+      for (int r = 0; r < F_RB; ++r)
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) acc[r][k] = 0.f;
+      const float* pre0 = P.pre + (size_t)b0 * P.rep_rows_pre;
+      const int nb = min(F_RB, b_hi - b0);
+      for (int base = beg; base < end; base += LANES) {
+        unsigned my_idx = idx0;
+        float my_w = w0;
+        if (base != beg) {
+          const int q = min(base + sl, end - 1);
+          my_idx = (unsigned)__ldg(P.idx + q);
+          my_w = P.val ? __ldg(P.val + q) : 1.f;
+        }
+        const int cnt = min(LANES, end - base);
+        for (int j = 0; j < cnt; j += F_JU) {
+          unsigned s[F_JU];
+          float w[F_JU], xv[F_JU][VEC], pw[F_JU][F_RB];
+#pragma unroll
+          for (int u = 0; u < F_JU; ++u) {
+            const int jj = min(j + u, cnt - 1);
+            s[u] = __shfl_sync(gmask, my_idx, jj, LANES);
+            w[u] = __shfl_sync(gmask, my_w, jj, LANES);
+            if (j + u >= cnt) w[u] = 0.f;
+            ldv<VEC>(xv[u], rowp(sc, s[u], P.ld_src), true);
+#pragma unroll
+            for (int r = 0; r < F_RB; ++r)
+              pw[u][r] = __ldg(pre0 + (size_t)min(r, nb - 1) * P.rep_rows_pre + s[u]);
+          }
+#pragma unroll
+          for (int u = 0; u < F_JU; ++u)
+#pragma unroll
+            for (int r = 0; r < F_RB; ++r) {
+              const float f = w[u] * pw[u][r];
+#pragma unroll
+              for (int k = 0; k < VEC; ++k) acc[r][k] = fmaf(f, xv[u][k], acc[r][k]);
+            }
+        }
+      }
+      // epilogue operands requested together (one exposed latency): self table row, bias, the row's own scalars
+      float es[VEC], bs[VEC], xself[F_RB];
+      ldv<VEC>(es, rowp(P.e_self, row, P.ld_self) + c, cok);
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) bs[k] = (cok && P.bias) ? __ldg(P.bias + c + k) : 0.f;   // parameter view: 4-byte aligned only
+#pragma unroll
+      for (int r = 0; r < F_RB; ++r) xself[r] = __ldg(pre0 + (size_t)min(r, nb - 1) * P.rep_rows_pre + row);
+#pragma unroll
+      for (int r = 0; r < F_RB; ++r) {
+        if (r < nb) {
+          float y[VEC];
+#pragma unroll
+          for (int k = 0; k < VEC; ++k) {
+            const float z = fmaf(es[k], xself[r], fmaf(acc[r][k], postf, bs[k]));
+            y[k] = z > 0.f ? z : z * P.act_slope;
+          }
+          stv<VEC>(rowp(P.out, (unsigned)(b0 + r) * (unsigned)P.n + row, P.ld_out) + c, y, cok);
+        }
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Fully factored first SAGE layer, backward w.r.t. the tables (mlg_sage_rank1_bwd_rows), organised by TARGET row so
+// that gz is read exactly once (the by-source gather of mlg_sage_rank1_bwd re-reads every gz row once per edge):
+// one warp per row i; lane l owns channels l, l+32, ... and keeps gz[b,i,channel] of 32 replicas in registers
+// (coalesced 128-byte loads, all in flight together); then for every entry q of the row (source j)
+//     h[q,:] = (val_q / cnt_i) * sum_b x[b,j] gz[b,i,:]
+// -- a 32-term dot per channel with x[.,j] broadcast by shuffles -- plus the two per-row reductions
+//     g_self[i,:] = sum_b x[b,i] gz[b,i,:]        g_bias_rows[i,:] = sum_b gz[b,i,:].
+// g_E_nbr[j,:] = sum_{q: idx_q = j} h[q,:] is then a segment sum over the by-source CSR (mlg_gather_sum, single graph):
+// fixed order, no atomics.  More than 32 replicas: further passes accumulate into the same outputs.
+// ---------------------------------------------------------------------------------------------
+struct R1B {
+  const float* gz;
+  const float* xs;
+  const int* rowptr;
+  const int* idx;
+  const float* val;
+  const int* order;
+  float* h;
+  float* g_self;
+  float* g_bias_rows;
+  unsigned ld_g, ld_self;
+  int n, B;
+};
+
+template <int CPL>
+__global__ void __launch_bounds__(kThreads, 2) sage_rank1_bwd_rows_kernel(const R1B P) {
+  constexpr int C = 32 * CPL;
+  constexpr int EU = 4;   // entries whose x loads are in flight together
+  const int lane = threadIdx.x & 31;
+  const long long slot = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (slot >= P.n) return;
+  const unsigned row = P.order ? (unsigned)__ldg(P.order + slot) : (unsigned)slot;
+  const int beg = __ldg(P.rowptr + row), end = __ldg(P.rowptr + row + 1);
+  const float inv = end > beg ? 1.f / (float)(end - beg) : 0.f;
+  for (int rb0 = 0; rb0 < P.B; rb0 += 32) {
+    const int nb = min(32, P.B - rb0);
+    const bool first = rb0 == 0;
+    float g[CPL][32];
+    const float* gp = P.gz + ((size_t)rb0 * P.n + row) * P.ld_g + lane;
+#pragma unroll
+    for (int b = 0; b < 32; ++b)
+#pragma unroll
+      for (int k = 0; k < CPL; ++k) g[k][b] = b < nb ? __ldg(gp + (size_t)b * P.n * P.ld_g + 32 * k) : 0.f;
+    const float* xp = P.xs + (size_t)(rb0 + min(lane, nb - 1)) * P.n;   // lane b reads replica rb0+b (clamped; masked below)
+    const float lane_live = lane < nb ? 1.f : 0.f;
+    {
+      const float xv = __ldg(xp + row) * lane_live;
+      float e1[CPL], gb[CPL];
+#pragma unroll
+      for (int k = 0; k < CPL; ++k) e1[k] = gb[k] = 0.f;
+#pragma unroll
+      for (int b = 0; b < 32; ++b) {
+        const float xb = __shfl_sync(0xffffffffu, xv, b);
+#pragma unroll
+        for (int k = 0; k < CPL; ++k) {
+          e1[k] = fmaf(xb, g[k][b], e1[k]);
+          gb[k] += g[k][b];
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < CPL; ++k) {
+        float* ps = P.g_self + (size_t)row * P.ld_self + lane + 32 * k;
+        float* pb = P.g_bias_rows + (size_t)row * C + lane + 32 * k;
+        *ps = first ? e1[k] : *ps + e1[k];
+        *pb = first ? gb[k] : *pb + gb[k];
+      }
+    }
+    for (int base = beg; base < end; base += 32) {
+      const int q = min(base + lane, end - 1);
+      const unsigned my_idx = (unsigned)__ldg(P.idx + q);
+      const float my_w = (P.val ? __ldg(P.val + q) : 1.f) * inv;
+      const int cnt = min(32, end - base);
+      for (int j = 0; j < cnt; j += EU) {
+        float xv[EU];
+#pragma unroll
+        for (int u = 0; u < EU; ++u) {
+          const unsigned s = __shfl_sync(0xffffffffu, my_idx, min(j + u, cnt - 1));
+          xv[u] = __ldg(xp + s) * lane_live;
+        }
+#pragma unroll
+        for (int u = 0; u < EU; ++u) {
+          if (j + u < cnt) {   // warp-uniform
+            const float w = __shfl_sync(0xffffffffu, my_w, j + u);
+            float hk[CPL];
+#pragma unroll
+            for (int k = 0; k < CPL; ++k) hk[k] = 0.f;
+#pragma unroll
+            for (int b = 0; b < 32; ++b) {
+              const float xb = __shfl_sync(0xffffffffu, xv[u], b);
+#pragma unroll
+              for (int k = 0; k < CPL; ++k) hk[k] = fmaf(xb, g[k][b], hk[k]);
+            }
+#pragma unroll
+            for (int k = 0; k < CPL; ++k) {
+              float* ph = P.h + (size_t)(base + j + u) * C + lane + 32 * k;
+              *ph = first ? w * hk[k] : fmaf(w, hk[k], *ph);
+            }
+          }
+        }
+      }
     }
   }
 }
@@ -651,9 +841,9 @@ extern "C" int mlg_sage_rank1_fwd(const float* xs, const float* e_self, int64_t 
   const int gy = rep_slices(gx, replicas);
   const unsigned grid = (unsigned)(gx * gy);
   cudaStream_t st = (cudaStream_t)stream;
-  if (lanes == 8) gather_sum_rep_kernel<8, 4, true><<<grid, kThreads, 0, st>>>(P, gy);
-  else if (lanes == 16) gather_sum_rep_kernel<16, 4, true><<<grid, kThreads, 0, st>>>(P, gy);
-  else gather_sum_rep_kernel<32, 4, true><<<grid, kThreads, 0, st>>>(P, gy);
+  if (lanes == 8) sage_rank1_fwd_kernel<8><<<grid, kThreads, 0, st>>>(P, gy);
+  else if (lanes == 16) sage_rank1_fwd_kernel<16><<<grid, kThreads, 0, st>>>(P, gy);
+  else sage_rank1_fwd_kernel<32><<<grid, kThreads, 0, st>>>(P, gy);
   MLG_CHECK_LAUNCH("mlg_sage_rank1_fwd");
   return MLG_OK;
 }
@@ -692,6 +882,28 @@ extern "C" int mlg_sage_rank1_bwd(const float* gz, int64_t ld_g, const float* xs
   else if (lanes == 16) gather_sum_rep_kernel<16, 4, false, true, true><<<grid, kThreads, 0, st>>>(P, gy);
   else gather_sum_rep_kernel<32, 4, false, true, true><<<grid, kThreads, 0, st>>>(P, gy);
   MLG_CHECK_LAUNCH("mlg_sage_rank1_bwd");
+  return MLG_OK;
+}
+
+extern "C" int mlg_sage_rank1_bwd_rows_supported(int64_t C) { return C == 32 || C == 64; }
+
+extern "C" int mlg_sage_rank1_bwd_rows(const float* gz, int64_t ld_g, const float* xs, const int32_t* rowptr,
+                                       const int32_t* idx, const float* val, const int32_t* order, int64_t n_rows,
+                                       int64_t C, int64_t replicas, float* h, float* g_self, int64_t ld_self,
+                                       float* g_bias_rows, void* stream) {
+  MLG_CHECK_ARG(gz && xs && rowptr && idx && h && g_self && g_bias_rows, "mlg_sage_rank1_bwd_rows: null pointer");
+  MLG_CHECK_ARG(mlg_sage_rank1_bwd_rows_supported(C), "mlg_sage_rank1_bwd_rows: C=%lld (needs 32 or 64)", (long long)C);
+  MLG_CHECK_ARG(n_rows >= 0 && replicas >= 1 && replicas * n_rows < (1ll << 31) && ld_g >= C && ld_self >= C,
+                "mlg_sage_rank1_bwd_rows: bad sizes");
+  if (n_rows == 0) return MLG_OK;
+  R1B P;
+  P.gz = gz; P.xs = xs; P.rowptr = rowptr; P.idx = idx; P.val = val; P.order = order; P.h = h; P.g_self = g_self;
+  P.g_bias_rows = g_bias_rows; P.ld_g = (unsigned)ld_g; P.ld_self = (unsigned)ld_self; P.n = (int)n_rows; P.B = (int)replicas;
+  const unsigned grid = (unsigned)mlg_ceil_div(n_rows, kThreads / 32);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (C == 64) sage_rank1_bwd_rows_kernel<2><<<grid, kThreads, 0, st>>>(P);
+  else sage_rank1_bwd_rows_kernel<1><<<grid, kThreads, 0, st>>>(P);
+  MLG_CHECK_LAUNCH("mlg_sage_rank1_bwd_rows");
   return MLG_OK;
 }
 

@@ -477,7 +477,9 @@ class SageAggregate(torch.autograd.Function):
         return gx, None, None
 
 
-FACTORED_RANK1 = True    # first layer of MultilevelGNN through mlg_sage_rank1_fwd/_bwd (False: [x0 | agg] buffer + GEMMs)
+# first layer of MultilevelGNN through mlg_sage_rank1_fwd / mlg_sage_rank1_bwd_rows; "gather": backward through the
+# by-source gather mlg_sage_rank1_bwd (any width); False: [x0 | agg] buffer + GEMMs
+FACTORED_RANK1 = True
 
 
 class SageLayer(torch.autograd.Function):
@@ -573,22 +575,45 @@ class SageLayer(torch.autograd.Function):
                 else torch.ops.aten.threshold_backward(gy, y, 0.0)
         L = _cabi.lib()
         n1, B = topo.n_single, topo.replicas
-        slices = L.mlg_gather_sum_slices(n1, cout, B)
-        parts = torch.empty(slices * n1 * 3 * cout, dtype=torch.float32, device=gz.device)
-        p12 = parts[:slices * n1 * 2 * cout].view(slices, n1, 2 * cout)
-        pb = parts[slices * n1 * 2 * cout:].view(slices * n1, cout)
-        bw = topo.bwd
-        nbytes = 4 * cout * gz.shape[0] + 4 * gz.shape[0] + 8 * bw.col.numel() + 4 * parts.numel()
-        with torch.cuda.device(gz.device), _cabi.span("sage_rank1_bwd", nbytes):
-            _cabi.check(L.mlg_sage_rank1_bwd(
-                _cabi.fptr(gz), cout, _cabi.fptr(xs_d), _cabi.iptr(bw.rowptr), _cabi.iptr(bw.col),
-                _cabi.fptr(topo.bwd_val, True), _cabi.fptr(topo.inv_cnt, True), _cabi.iptr(topo.bwd_order, True), n1, cout, B,
-                _cabi.fptr(p12), _cabi.fptr(pb), _cabi.stream_ptr()), "mlg_sage_rank1_bwd")
-        g12 = p12.sum(0) if slices > 1 else p12[0]                 # [n1, 2cout] = [g_E_self | g_E_nbr]
-        g_b = pb.sum(0) if ctx.has_bias else None
+        if FACTORED_RANK1 != "gather" and L.mlg_sage_rank1_bwd_rows_supported(cout):
+            # by target row: gz read once -> per-entry rows h (+ the self / bias reductions), then a segment sum by source
+            fw, bw = topo.fwd, topo.bwd
+            g12 = torch.empty(n1, 2 * cout, dtype=torch.float32, device=gz.device)      # [g_E_self | g_E_nbr]
+            gbr = torch.empty(n1, cout, dtype=torch.float32, device=gz.device)
+            h = torch.empty(fw.cap, cout, dtype=torch.float32, device=gz.device)
+            nbytes = 4 * cout * gz.shape[0] + 4 * gz.shape[0] + 8 * fw.col.numel() + 4 * (h.numel() + 2 * gbr.numel())
+            with torch.cuda.device(gz.device), _cabi.span("sage_rank1_bwd", nbytes):
+                _cabi.check(L.mlg_sage_rank1_bwd_rows(
+                    _cabi.fptr(gz), cout, _cabi.fptr(xs_d), _cabi.iptr(fw.rowptr), _cabi.iptr(fw.col),
+                    _cabi.fptr(topo.fwd_val, True), _cabi.iptr(topo.fwd_order, True), n1, cout, B, _cabi.fptr(h),
+                    _cabi.fptr(g12), 2 * cout, _cabi.fptr(gbr), _cabi.stream_ptr()), "mlg_sage_rank1_bwd_rows")
+            gather_sum(h, bw.rowptr, topo.bwd2fwd, n1, out=g12[:, cout:], order=topo.bwd_order, tag="sage_rank1_bwd_seg")
+            g_b = None
+            if ctx.has_bias:       # column sums of the per-row partials: one streaming pass, fixed order (mlg_wcolsum)
+                g_b = torch.empty(cout, dtype=torch.float32, device=gz.device)
+                ws_bytes = L.mlg_wcolsum_workspace_bytes(n1, cout)
+                ws = torch.empty(ws_bytes // 4, dtype=torch.float32, device=gz.device)
+                with torch.cuda.device(gz.device):
+                    _cabi.check(L.mlg_wcolsum(_cabi.fptr(gbr), cout, None, n1, cout, None, _cabi.fptr(g_b), _cabi.fptr(ws),
+                                              ws_bytes, _cabi.stream_ptr()), "mlg_wcolsum")
+        else:
+            slices = L.mlg_gather_sum_slices(n1, cout, B)
+            parts = torch.empty(slices * n1 * 3 * cout, dtype=torch.float32, device=gz.device)
+            p12 = parts[:slices * n1 * 2 * cout].view(slices, n1, 2 * cout)
+            pb = parts[slices * n1 * 2 * cout:].view(slices * n1, cout)
+            bw = topo.bwd
+            nbytes = 4 * cout * gz.shape[0] + 4 * gz.shape[0] + 8 * bw.col.numel() + 4 * parts.numel()
+            with torch.cuda.device(gz.device), _cabi.span("sage_rank1_bwd", nbytes):
+                _cabi.check(L.mlg_sage_rank1_bwd(
+                    _cabi.fptr(gz), cout, _cabi.fptr(xs_d), _cabi.iptr(bw.rowptr), _cabi.iptr(bw.col),
+                    _cabi.fptr(topo.bwd_val, True), _cabi.fptr(topo.inv_cnt, True), _cabi.iptr(topo.bwd_order, True), n1, cout, B,
+                    _cabi.fptr(p12), _cabi.fptr(pb), _cabi.stream_ptr()), "mlg_sage_rank1_bwd")
+            g12 = p12.sum(0) if slices > 1 else p12[0]                 # [n1, 2cout] = [g_E_self | g_E_nbr]
+            g_b = pb.sum(0) if ctx.has_bias else None
         slot = grad_slot(ctx.emb_param, (n1, cin)) if ctx.emb_param is not None else None
         g_emb = torch.mm(g12, wst, out=slot) if slot is not None else torch.mm(g12, wst)
-        g_wst = torch.mm(g12.t(), emb)                             # [2cout, cin] = [g_W1 ; g_(W2 W_r)]
+        # [2cout, cin] = [g_W1 ; g_(W2 W_r)] = g12^T emb: a 15 405-deep reduction (cuBLAS picks a one-wave SIMT kernel: 48 us)
+        g_wst, _ = xty(g12, emb, tag="sage_rank1_wgrad")
         g_wcat = g_wst.view(2, cout, cin).permute(1, 0, 2).reshape(cout, 2 * cin)
         g_wnn, g_wr = torch.empty_like(w_nn), torch.empty_like(w_r)
         with torch.cuda.device(gz.device):

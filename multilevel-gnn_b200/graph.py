@@ -102,6 +102,7 @@ class Topology:
         self._inv_cnt = None
         self._fwd_order = None
         self._bwd_order = None
+        self._bwd2fwd = None
         # edges already sorted by target (kNN graphs are centre-major): the permutation is the identity
         self.fwd_identity = False
         if not self_loops and edge_index.shape[1] > 1:
@@ -138,6 +139,33 @@ class Topology:
         if self._bwd_order is None:
             self._bwd_order = self._order(self.bwd)
         return self._bwd_order
+
+    @property
+    def bwd2fwd(self):
+        """int32 [nnz]: position in the forward (target-sorted) CSR of the entry at each position of the by-source CSR --
+        the same edge seen from its other end (matched through the original edge id; added self loops through their
+        node).  Lets a per-forward-entry result be segment-summed by source.  Built once (host sync at build time)."""
+        if self._bwd2fwd is None:
+            f, b = self.fwd, self.bwd
+            nnz = int(f.rowptr[-1])
+            if nnz != int(b.rowptr[-1]):
+                raise RuntimeError("forward and by-source CSR disagree on the entry count")
+            dev = f.rowptr.device
+            fe, be = f.eid[:nnz].long(), b.eid[:nnz].long()
+            ar = torch.arange(nnz, device=dev)
+            n_edges = int(max(int(fe.max()) if nnz else -1, int(be.max()) if nnz else -1)) + 1
+            pos_f = torch.full((max(n_edges, 1),), -1, dtype=torch.long, device=dev)
+            mf, mb = fe >= 0, be >= 0
+            pos_f[fe[mf]] = ar[mf]
+            out = torch.full((nnz,), -1, dtype=torch.long, device=dev)
+            out[mb] = pos_f[be[mb]]
+            selfpos = torch.full((self.n_single,), -1, dtype=torch.long, device=dev)
+            selfpos[f.col[:nnz].long()[~mf]] = ar[~mf]
+            out[~mb] = selfpos[b.col[:nnz].long()[~mb]]
+            if nnz and int(out.min()) < 0:
+                raise RuntimeError("by-source CSR entry without a forward counterpart")
+            self._bwd2fwd = out.to(torch.int32)
+        return self._bwd2fwd
 
     @property
     def inv_cnt(self):

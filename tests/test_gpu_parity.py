@@ -604,17 +604,22 @@ def test_factored_first_layer_is_equivalent(mlg):
                 type(model).FUSE_ACT_BACKWARD = True
             return pred.detach(), feat.detach(), g, set(timer.summary())
 
-        p1, f1, g1, tags1 = run(True)
         p0, f0, g0, tags0 = run(False)
-        assert {"sage_rank1_fwd", "sage_rank1_bwd"} <= tags1 and not ({"sage_rank1_fwd", "sage_rank1_bwd"} & tags0), (tags1, tags0)
-        assert_close(p1, p0, rtol=1e-5, atol=1e-6, what="factored vs buffered pred")
-        assert_close(f1, f0, rtol=1e-4, atol=1e-6, what="factored vs buffered pooled features")
-        for (n, _), a, c in zip([(n, p) for n, p in model.named_parameters() if p.requires_grad and not n.endswith("lin_l.weight")], g1, g0):
-            if a is None or c is None:
-                assert a is None and c is None
-                continue
-            sc = float(c.abs().max().clamp_min(1e-30))          # compare at unit scale: atol is then relative to the largest entry
-            assert_close(a / sc, c / sc, rtol=1e-4, atol=2e-6, what="factored vs buffered grad " + n)
+        assert not ({"sage_rank1_fwd", "sage_rank1_bwd"} & tags0), tags0
+        names = [n for n, p in model.named_parameters() if p.requires_grad and not n.endswith("lin_l.weight")]
+        # True: backward by target row (mlg_sage_rank1_bwd_rows + segment sum); "gather": by-source gather (mlg_sage_rank1_bwd)
+        for mode in (True, "gather"):
+            p1, f1, g1, tags1 = run(mode)
+            assert {"sage_rank1_fwd", "sage_rank1_bwd"} <= tags1, tags1
+            assert ("sage_rank1_bwd_seg" in tags1) == (mode is True), (mode, tags1)
+            assert_close(p1, p0, rtol=1e-5, atol=1e-6, what="factored vs buffered pred")
+            assert_close(f1, f0, rtol=1e-4, atol=1e-6, what="factored vs buffered pooled features")
+            for n, a, c in zip(names, g1, g0):
+                if a is None or c is None:
+                    assert a is None and c is None
+                    continue
+                sc = float(c.abs().max().clamp_min(1e-30))      # compare at unit scale: atol is then relative to the largest entry
+                assert_close(a / sc, c / sc, rtol=1e-4, atol=2e-6, what="factored (%s) vs buffered grad %s" % (mode, n))
 
 
 def test_maxpool_channel_last_matches_torch(mlg):
