@@ -51,6 +51,7 @@ _SIGNATURES = {
                                    _c_i64, _c_vp, _c_i64, _c_vp]),
     "mlg_sage_fold_fwd": (_c_int, [_c_vp, _c_vp, _c_i64, _c_i64, _c_i64, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp]),
     "mlg_sage_fold_bwd": (_c_int, [_c_vp, _c_vp, _c_vp, _c_i64, _c_i64, _c_i64, _c_vp, _c_vp, _c_vp]),
+    "mlg_pca_indep_loss": (_c_int, [_c_vp, _c_vp, _c_vp, _c_i64, _c_i64, _c_vp, _c_vp]),
     "mlg_maxpool_cl_fwd": (_c_int, [_c_vp, _c_i64, _c_i64, _c_i64, _c_i64, _c_i64, _c_i64, _c_vp, _c_vp, _c_vp]),
     "mlg_maxpool_cl_bwd": (_c_int, [_c_vp, _c_vp, _c_i64, _c_i64, _c_i64, _c_i64, _c_i64, _c_i64, _c_vp, _c_vp]),
     "mlg_layernorm_supported": (_c_int, [_c_i64]),

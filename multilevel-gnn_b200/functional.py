@@ -207,21 +207,28 @@ class TallLinear(torch.autograd.Function):
     MIN_ROWS = 65536
 
     @staticmethod
-    def forward(ctx, x, weight, bias):
-        ctx.save_for_backward(x, weight)
+    def forward(ctx, x, weight, bias, relu=False):
+        """relu: the ReLU that follows the Linear (nn.Conv2d(1x1) + nn.ReLU in MultilevelGNN's head) applied in the GEMM
+        epilogue; backward then starts from the activation's derivative."""
         ctx.has_bias = bias is not None
-        return tall_matmul(_f32c(x.detach()), weight.detach(), None if bias is None else bias.detach(), tag="linear_fwd")
+        ctx.relu = bool(relu)
+        y = tall_matmul(_f32c(x.detach()), weight.detach(), None if bias is None else bias.detach(), tag="linear_fwd",
+                        act=1 if relu else 0, slope=0.0)
+        ctx.save_for_backward(x, weight, y if relu else None)
+        return y
 
     @staticmethod
     def backward(ctx, g):
-        x, weight = ctx.saved_tensors
+        x, weight, y = ctx.saved_tensors
         g = _f32c(g)
+        if ctx.relu:
+            g = torch.ops.aten.threshold_backward(g, y, 0.0)
         gx = gw = gb = None
         if ctx.needs_input_grad[0]:
             gx = tall_matmul(g, weight.t().contiguous(), tag="linear_dgrad")
         if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
             gw, gb = xty(g, _f32c(x), want_colsum=ctx.has_bias, tag="linear_wgrad", out=grad_slot(weight, weight.shape))
-        return gx, gw, (gb if ctx.has_bias else None)
+        return gx, gw, (gb if ctx.has_bias else None), None
 
 
 def tall_linear(x, lin, min_rows=None):
@@ -229,7 +236,7 @@ def tall_linear(x, lin, min_rows=None):
     and bias gradient) when x is a CUDA matrix with at least ``min_rows`` rows (default TallLinear.MIN_ROWS)."""
     rows = TallLinear.MIN_ROWS if min_rows is None else min_rows
     if x.is_cuda and x.dim() == 2 and x.shape[0] >= rows and x.dtype == torch.float32:
-        return TallLinear.apply(x, lin.weight, lin.bias)
+        return TallLinear.apply(x, lin.weight, lin.bias, False)
     return lin(x)
 
 

@@ -195,8 +195,13 @@ class MultilevelGNN(nn.Module):
                 x = x[:, :, self.reorder_idxs.to(x.device), :]
 
         pca_feature = x
-        for layer in self.conv_model:
-            x = self._conv(layer, x)
+        layers, i = list(self.conv_model), 0
+        while i < len(layers):
+            # Conv2d(1x1) + ReLU pairs: the ReLU runs in the GEMM epilogue (forward hooks on either module: unfused)
+            fuse = (x.is_cuda and i + 1 < len(layers) and isinstance(layers[i], nn.Conv2d) and layers[i].kernel_size == (1, 1)
+                    and type(layers[i + 1]) is nn.ReLU and not layers[i]._forward_hooks and not layers[i + 1]._forward_hooks)
+            x = self._conv(layers[i], x, relu=fuse)
+            i += 2 if fuse else 1
         pool = self.pooling
         ks = pool.kernel_size if isinstance(pool.kernel_size, tuple) else (pool.kernel_size,) * 2
         if (x.is_cuda and x.dtype == torch.float32 and x.permute(0, 2, 3, 1).is_contiguous()
@@ -215,7 +220,7 @@ class MultilevelGNN(nn.Module):
         return x, pca_feature
 
     @staticmethod
-    def _conv(layer, x):
+    def _conv(layer, x, relu=False):
         """1x1 convolutions run as a matmul over the channel axis: (a) cuDNN's convolution path defaults to TF32
         (torch.backends.cudnn.allow_tf32), which breaks the fp32 rtol-1e-4 parity with the reference; (b) the pooled
         tensor is channel-last in memory (PathwayPool), so [B,C,H,W] -> [B*H*W, C] is a free view and the conv is one
@@ -226,7 +231,7 @@ class MultilevelGNN(nn.Module):
             x2 = x.permute(0, 2, 3, 1).reshape(-1, c)
             w = layer.weight.view(layer.out_channels, c)
             if x2.is_cuda:
-                y2 = Fn.TallLinear.apply(x2, w, layer.bias)
+                y2 = Fn.TallLinear.apply(x2, w, layer.bias, relu)
             else:
                 y2 = torch.nn.functional.linear(x2, w, layer.bias)
             return y2.view(b, hh, ww, layer.out_channels).permute(0, 3, 1, 2)
@@ -270,6 +275,19 @@ class MultilevelGNN(nn.Module):
             # only the LAST j of every i survives the reference's loop (j = pca_dim - 1): all pairs (i, P-1) at once,
             # one segment sum over [w_i * w_last | w_i^2 | w_last^2] instead of three index_adds per pair
             P = self.pca_dim
+            segptr = self._segment_pointers(idx, nseg) if (w.is_cuda and 2 <= P <= 8) else None
+            if segptr is not None:
+                # genes sorted by pathway: the whole term is ONE launch (mlg_pca_indep_loss) instead of ~14 tiny ones
+                from .. import _cabi
+                out = torch.empty(1, dtype=torch.float32, device=w.device)
+                wr = self.learnable_pca_params.data
+                mk = self.info_mask.data.reshape(-1)
+                wr = wr if (wr.dtype == torch.float32 and wr.is_contiguous()) else wr.float().contiguous()
+                mk = mk if (mk.dtype == torch.float32 and mk.is_contiguous()) else mk.float().contiguous()
+                with torch.cuda.device(w.device):
+                    _cabi.check(_cabi.lib().mlg_pca_indep_loss(_cabi.fptr(wr), _cabi.fptr(mk), _cabi.iptr(segptr), nseg, P,
+                                                              _cabi.fptr(out), _cabi.stream_ptr()), "mlg_pca_indep_loss")
+                return loss + out[0]
             if P > 1:
                 a, b = w[:, :P - 1], w[:, P - 1:P]
                 seg = torch.zeros(nseg, 2 * (P - 1) + 1, device=w.device, dtype=w.dtype).index_add_(
@@ -281,6 +299,19 @@ class MultilevelGNN(nn.Module):
                 indep, count = 0, 1
             loss = loss + indep / count
         return loss
+
+    def _segment_pointers(self, idx, nseg):
+        """int32 [nseg+1] segment boundaries when ``pathway_indexs`` is sorted (it is for the reference's loaders), else
+        None; checked once per index tensor (one host sync, before any graph capture)."""
+        key = (idx.data_ptr(), idx._version, tuple(idx.shape), nseg)
+        cache = getattr(self, "_segptr_cache", None)
+        if cache is None or cache[0] != key:
+            ok = idx.numel() > 0 and bool((idx[1:] >= idx[:-1]).all()) and int(idx.min()) >= 0
+            ptr = None
+            if ok:
+                ptr = torch.searchsorted(idx.contiguous(), torch.arange(nseg + 1, device=idx.device, dtype=idx.dtype)).to(torch.int32)
+            self._segptr_cache = cache = (key, ptr)
+        return cache[1]
 
     def generate_mutual_mask(self, *a, **k):
         raise NotImplementedError("sklearn mutual-information data prep is out of scope (SURVEY.md section 2 row 7)")
