@@ -154,7 +154,7 @@ class ClockSampler:
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from `ncu --set full` captures (profiles/), or None
-NCU_TRAFFIC = {"gather_sum_rep": 302514176, "gen_fwd": 1084807680}   # profiles/r01_ncu_full_summaries.md
+NCU_TRAFFIC = {"gather_sum_rep": 302514176, "gather_sum_rep_c32": None, "gen_fwd": 1084807680}   # profiles/r01_ncu_full_summaries.md
 
 
 def max_over_ranks(ms, world, dev):
@@ -233,22 +233,24 @@ def genconv_microbench(dev, hbm_peak):
 
 
 def dominant_kernel_alone(batch, hbm_peak, reps=20):
-    """The dominant kernel (SAGE mean aggregation over the replicated CSR, C=64) timed alone: `reps` back-to-back
-    launches on the bench's own topology, CUDA events on the launching stream.  Besides the HBM fraction it reports the
-    L2 -> SM side, which is what actually bounds a gather over ~7-entry rows: every source row is re-read once per
-    entry, and those reads are served by L2 (full-chip L2 throughput cap measured at ~6300 B/clk,
+    """The dominant kernel (SAGE mean aggregation over the replicated CSR as the step's second layer launches it:
+    transform-first, so 32-wide rows V gathered from the right half of the [U | V] buffer, U added, LeakyReLU fused) timed
+    alone: `reps` back-to-back launches on the bench's own topology, CUDA events on the launching stream.  Besides the HBM
+    fraction it reports the L2 -> SM side, which is what actually bounds a gather over ~7-entry rows: every source row is
+    re-read once per entry, and those reads are served by L2 (full-chip L2 throughput cap measured at ~6300 B/clk,
     /opt/skills/guides/B300_MICROARCH.md 'LTS throughput cap')."""
     import multilevel_gnn_b200 as m
     from multilevel_gnn_b200 import functional as Fn, graph
     n = batch.x.shape[0]
-    C = 64
+    C = 32
     topo = graph.topology(batch.edge_index, n, self_loops=True, edge_weight=batch.edge_attr,
                           static_key=getattr(batch, "topology_key", None), period=3 * m.MultilevelGNN.GENES)
-    x = torch.randn(n, C, device=batch.x.device)
-    out = torch.empty_like(x)
+    uv = torch.randn(n, 2 * C, device=batch.x.device)
+    out = torch.empty(n, C, device=batch.x.device)
     csr = topo.fwd
-    run = lambda: Fn.gather_sum(x, csr.rowptr, csr.col, topo.n_single, val=topo.fwd_val, post_mode=1, out=out,
-                                replicas=topo.replicas, order=topo.fwd_order, tag="sage_aggr_alone")
+    run = lambda: Fn.gather_sum(uv[:, C:], csr.rowptr, csr.col, topo.n_single, val=topo.fwd_val, post_mode=1, out=out,
+                                addend=uv[:, :C], replicas=topo.replicas, order=topo.fwd_order, tag="sage_aggr_alone",
+                                act_slope=0.2)
     for _ in range(3):
         run()
     torch.cuda.synchronize()
@@ -260,15 +262,16 @@ def dominant_kernel_alone(batch, hbm_peak, reps=20):
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / reps
     nnz = int(csr.col.numel())
-    alg = 8 * C * n + 8 * nnz
-    gathered = 4 * C * nnz * topo.replicas + 4 * C * n          # source rows re-read per entry + rows written
+    alg = 12 * C * n + 8 * nnz                                   # U and V read once, output written once, idx + val
+    gathered = 4 * C * nnz * topo.replicas + 8 * C * n           # V rows re-read per entry + U rows read + rows written
     sm_mhz = 1965.0
     l2_cap = 6300.0 * sm_mhz / 1e3                               # GB/s
     return {"ms": round(ms, 4), "achieved": round(alg / ms / 1e6, 1), "frac": round(alg / ms / 1e6 / hbm_peak, 4),
             "l2_bytes": gathered, "l2_GBps": round(gathered / ms / 1e6, 1), "l2_cap_GBps": round(l2_cap, 0),
             "l2_frac": round(gathered / ms / 1e6 / l2_cap, 4),
-            "note": "%d launches back to back, x [%d,%d] fp32 (126 MB) + output, nnz=%d per graph x %d replicas; l2_cap = "
-                    "6300 B/clk x 1965 MHz (guide-measured full-chip LTS cap)" % (reps, n, C, nnz, topo.replicas)}
+            "note": "%d launches back to back, [U | V] [%d,%d] fp32 (126 MB) -> out [%d,%d], nnz=%d per graph x %d replicas; "
+                    "l2_cap = 6300 B/clk x 1965 MHz (guide-measured full-chip LTS cap)"
+                    % (reps, n, 2 * C, n, C, nnz, topo.replicas)}
 
 
 # ----------------------------------------------------------------------------------------------------
@@ -416,12 +419,14 @@ def run_b200(a):
         tag, d = max(hbm_kernels.items(), key=lambda kv: kv[1]["ms"])
         gbs = d["bytes"] / d["ms"] / 1e6
         roof = {"kernel": tag, "bound": "hbm", "achieved": round(gbs, 1), "peak": hbm_peak, "unit": "GB/s",
-                "frac": round(gbs / hbm_peak, 4), "traffic": NCU_TRAFFIC.get("gather_sum_rep"), "peak_source": peak_src,
+                "frac": round(gbs / hbm_peak, 4), "traffic": NCU_TRAFFIC.get("gather_sum_rep_c32"), "peak_source": peak_src,
                 "launches": d["launches"], "avg_us": round(d["ms"] / d["launches"] * 1e3, 2),
                 "share_of_step": round(d["ms"] / ms_total, 4),
-                "algorithmic_bytes": "8*C*B*N + 8*nnz per launch (rows read once + written once + idx/val per entry); the "
-                                     "kernel is limited by L2 row gathers (7 entries/row on average: 878 MB of L1 misses per launch, "
-                                     "54 % L2 hits), not by DRAM; traffic = ncu dram bytes of one launch at this shape",
+                "algorithmic_bytes": "8*C*B*N + 8*nnz per launch (rows read once + written once + idx/val per entry), C = 32: the "
+                                     "second SAGE layer (64 -> 32) runs transform-first, so its forward and backward aggregations "
+                                     "gather 32-wide rows; the kernel is limited by L2 row gathers (7 entries/row on average), not "
+                                     "by DRAM; traffic = ncu dram bytes of one launch at this shape (null: not captured at C = 32; "
+                                     "the C = 64 capture in profiles/r01_ncu_full_summaries.md read 1.2x its algorithmic bytes)",
                 "timed": "CUDA events around each launch in an eager pass of the same %d steps (the timed region itself "
                          "is a CUDA-graph replay)" % a.steps,
                 "back_to_back": dominant_kernel_alone(resident, hbm_peak),

@@ -130,6 +130,16 @@ int mlg_gather_sum(const float* src, int64_t ld_src, const int32_t* rowptr, cons
                    const float* addend, int64_t ld_add, float* out, int64_t ld_out, float* self_out,
                    int64_t ld_self, const float* mask, int64_t ld_mask, float mask_slope, const float* reduce_scale,
                    void* stream);
+/* mlg_gather_sum with a fused output activation (replicated path, no relative / reduce_scale): act != 0 applies
+ * out = LeakyReLU_act_slope(out) after the addend / mask steps.  Forward of a SAGE layer evaluated transform-first
+ * (out_channels < in_channels: z = U + mean_j(w_ij V_j) with [U | V] = x [W1 ; W2 W_r]^T + [b | 0], so the gather runs on
+ * the narrower rows). */
+int mlg_gather_sum_act(const float* src, int64_t ld_src, const int32_t* rowptr, const int32_t* idx, const float* val,
+                       const float* pre, const float* post, const int32_t* order, int64_t n_rows, int64_t C,
+                       int64_t replicas, int64_t rep_rows_src, int64_t rep_rows_pre, int post_mode, int relative,
+                       const float* addend, int64_t ld_add, float* out, int64_t ld_out, float* self_out,
+                       int64_t ld_self, const float* mask, int64_t ld_mask, float mask_slope, const float* reduce_scale,
+                       int act, float act_slope, void* stream);
 /* reduce_scale != NULL (replicated path only): instead of one output row per (replica, row) the kernel writes, per row,
  * the weighted sum over the replicas of each replica SLICE:  out[s*n_rows + i] = sum_{b in slice s} reduce_scale[b*n_rows + i]
  * * out_i(b); out must hold mlg_gather_sum_slices(n_rows, C, replicas) * n_rows rows and the caller adds the slices.
@@ -149,7 +159,9 @@ int64_t mlg_gather_sum_slices(int64_t n_rows, int64_t C, int64_t replicas);
 int mlg_sage_rank1_fwd(const float* xs, const float* e_self, int64_t ld_self, const float* e_nbr, int64_t ld_nbr,
                        const int32_t* rowptr, const int32_t* idx, const float* val, const int32_t* order, int64_t n_rows,
                        int64_t C, int64_t replicas, const float* bias, float slope, float* out, int64_t ld_out,
-                       void* stream);
+                       uint64_t* mask_bits, void* stream);
+/* mask_bits (NULL ok; C == 64 only): [n_rows][replicas] 64-bit words, bit 16*(c % 4) + c / 4 = (out[b,i,c] > 0): lets the
+ * backward pass apply LeakyReLU' from 8 bytes per (row, replica) instead of re-reading the activation. */
 /* Its backward w.r.t. the tables and the bias from gz = dL/dz [replicas*n_rows, C], one pass over the by-source CSR
  * (rowptr_t / idx_t / val_t / order_t; inv_cnt[i] = 1/cnt_i of the forward rows, NULL = 1):
  *     g_e12_parts[s*n_rows+j, 0:C]  = sum_{b in slice s} xs[b,j] * gz[b,j,:]                                       -> g_E_self
@@ -164,9 +176,12 @@ int mlg_sage_rank1_bwd(const float* gz, int64_t ld_g, const float* xs, const int
  * val / order): per entry q of row i (source j = idx[q])  h[q,:] = (val[q] / cnt_i) * sum_b xs[b,j] * gz[b,i,:], and per row
  * g_self[i,:] = sum_b xs[b,i] * gz[b,i,:] (-> g_E_self, leading dimension ld_self), g_bias_rows[i,:] = sum_b gz[b,i,:].
  * g_E_nbr[j,:] = sum_{q: idx[q] == j} h[q,:] is a segment sum the caller runs over the by-source CSR with mlg_gather_sum
- * (single graph, idx = by-source position -> forward position).  h must hold rowptr[n_rows] rows of C floats. */
+ * (single graph, idx = by-source position -> forward position).  h must hold rowptr[n_rows] rows of C floats.
+ * y != NULL: gz is dL/dy of the layer's LeakyReLU(slope) output y (same layout as gz) and the kernel multiplies by the
+ * activation derivative while loading (no separate activation-backward pass); mask_bits != NULL (C == 64): the same
+ * from the sign bits mlg_sage_rank1_fwd wrote (y is then not read). */
 int mlg_sage_rank1_bwd_rows_supported(int64_t C);
-int mlg_sage_rank1_bwd_rows(const float* gz, int64_t ld_g, const float* xs, const int32_t* rowptr, const int32_t* idx,
+int mlg_sage_rank1_bwd_rows(const float* gz, int64_t ld_g, const float* y, const uint64_t* mask_bits, float slope, const float* xs, const int32_t* rowptr, const int32_t* idx,
                             const float* val, const int32_t* order, int64_t n_rows, int64_t C, int64_t replicas, float* h,
                             float* g_self, int64_t ld_self, float* g_bias_rows, void* stream);
 

@@ -31,17 +31,20 @@ _SIGNATURES = {
     "mlg_gather_sum": (_c_int, [_c_vp, _c_i64, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_i64, _c_i64, _c_i64,
                                 _c_i64, _c_i64, _c_int, _c_int, _c_vp, _c_i64, _c_vp, _c_i64, _c_vp, _c_i64, _c_vp, _c_i64,
                                 _c_f32, _c_vp, _c_vp]),
+    "mlg_gather_sum_act": (_c_int, [_c_vp, _c_i64, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_i64, _c_i64, _c_i64,
+                                    _c_i64, _c_i64, _c_int, _c_int, _c_vp, _c_i64, _c_vp, _c_i64, _c_vp, _c_i64, _c_vp, _c_i64,
+                                    _c_f32, _c_vp, _c_int, _c_f32, _c_vp]),
     "mlg_gather_sum_slices": (_c_i64, [_c_i64, _c_i64, _c_i64]),
-    # (xs, e_self, ld_self, e_nbr, ld_nbr, rowptr, idx, val, order, n_rows, C, replicas, bias, slope, out, ld_out, stream)
+    # (xs, e_self, ld_self, e_nbr, ld_nbr, rowptr, idx, val, order, n_rows, C, replicas, bias, slope, out, ld_out, mask_bits, stream)
     "mlg_sage_rank1_fwd": (_c_int, [_c_vp, _c_vp, _c_i64, _c_vp, _c_i64, _c_vp, _c_vp, _c_vp, _c_vp, _c_i64, _c_i64, _c_i64,
-                                    _c_vp, _c_f32, _c_vp, _c_i64, _c_vp]),
+                                    _c_vp, _c_f32, _c_vp, _c_i64, _c_vp, _c_vp]),
     # (gz, ld_g, xs, rowptr_t, idx_t, val_t, inv_cnt, order_t, n_rows, C, replicas, g_e12_parts, g_bias_parts, stream)
     "mlg_sage_rank1_bwd": (_c_int, [_c_vp, _c_i64, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_i64, _c_i64, _c_i64, _c_vp,
                                     _c_vp, _c_vp]),
     "mlg_sage_rank1_bwd_rows_supported": (_c_int, [_c_i64]),
-    # (gz, ld_g, xs, rowptr, idx, val, order, n_rows, C, replicas, h, g_self, ld_self, g_bias_rows, stream)
-    "mlg_sage_rank1_bwd_rows": (_c_int, [_c_vp, _c_i64, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_i64, _c_i64, _c_i64, _c_vp,
-                                         _c_vp, _c_i64, _c_vp, _c_vp]),
+    # (gz, ld_g, y, mask_bits, slope, xs, rowptr, idx, val, order, n_rows, C, replicas, h, g_self, ld_self, g_bias_rows, stream)
+    "mlg_sage_rank1_bwd_rows": (_c_int, [_c_vp, _c_i64, _c_vp, _c_vp, _c_f32, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_i64, _c_i64, _c_i64,
+                                         _c_vp, _c_vp, _c_i64, _c_vp, _c_vp]),
     "mlg_xty_workspace_bytes": (_c_i64, [_c_i64, _c_i64, _c_i64]),
     "mlg_xty_tc_supported": (_c_int, [_c_i64, _c_i64, _c_i64]),
     "mlg_xty_tc_workspace_bytes": (_c_i64, [_c_i64]),

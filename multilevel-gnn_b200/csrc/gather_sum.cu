@@ -60,6 +60,8 @@ struct GsP {
   const float* e_self;     // fwd: out = act(pre[b,row] * e_self[row] + post * sum + bias)
   const float* bias;
   float act_slope;
+  unsigned long long* mbits;   // sage_rank1_fwd_kernel<16> (C == 64): sign bits of the output, [n][replicas] x 64 bits
+  int act;                 // fast replicated epilogue: out = LeakyReLU_act_slope(out) after addend / mask
   float* aux1;             // bwd (RED): aux1[slice*n + row] = sum_b red_scale[b,row] * addend[b,row]   (NOT added to out)
   float* auxb;             //            auxb[slice*n + row] = sum_b addend[b,row]
   unsigned ld_aux1, ld_auxb;
@@ -347,12 +349,20 @@ __global__ void __launch_bounds__(kThreads, MLG_GS_MINB) gather_sum_rep_kernel(c
           }
         }
       }
-      if (!RANK1 && !P.relative && !P.self_out) {
+      if (!RANK1 && !P.relative) {
         // backward-style epilogue (addend / activation mask): request ALL replicas' addend and mask rows first, then
         // finish -- one exposed load latency per thread instead of RB sequential ones (the masked backward aggregation
         // ran 180 us against 138 us unmasked with the row-by-row epilogue)
         // (two phases -- addend rows, then mask rows -- so that only RB rows are live next to the accumulators)
         float t[RB][VEC];
+        if (P.self_out) {   // left half of cat(x, agg): the row's own src rows, copied with batched loads
+#pragma unroll
+          for (int r = 0; r < RB; ++r)
+            ldv<VEC>(t[r], rowp(P.src, (unsigned)min(b0 + r, b_hi - 1) * P.rep_rows_src + row, P.ld_src) + c, cok);
+#pragma unroll
+          for (int r = 0; r < RB; ++r)
+            if (b0 + r < b_hi) stv<VEC>(rowp(P.self_out, (unsigned)(b0 + r) * (unsigned)P.n + row, P.ld_self) + c, t[r], cok);
+        }
         if (AUX) {
           // factored first layer: the row's own gradient rows feed two SEPARATE replica reductions (weighted -> aux1,
           // plain -> auxb) instead of being added to the gathered sum
@@ -395,6 +405,12 @@ __global__ void __launch_bounds__(kThreads, MLG_GS_MINB) gather_sum_rep_kernel(c
           for (int r = 0; r < RB; ++r)
 #pragma unroll
             for (int k = 0; k < VEC; ++k) acc[r][k] *= t[r][k] > 0.f ? 1.f : P.mask_slope;
+        }
+        if (P.act) {
+#pragma unroll
+          for (int r = 0; r < RB; ++r)
+#pragma unroll
+            for (int k = 0; k < VEC; ++k) acc[r][k] = acc[r][k] > 0.f ? acc[r][k] : acc[r][k] * P.act_slope;
         }
         if (AUX) {
           // reductions done above
@@ -556,6 +572,16 @@ __global__ void __launch_bounds__(kThreads, 2) sage_rank1_fwd_kernel(const GsP P
             y[k] = z > 0.f ? z : z * P.act_slope;
           }
           stv<VEC>(rowp(P.out, (unsigned)(b0 + r) * (unsigned)P.n + row, P.ld_out) + c, y, cok);
+          if (LANES == 16 && P.mbits) {
+            // sign bits of this (replica, row): 64 channels -> bit 16*(c % 4) + c / 4; the backward pass reads 8 bytes
+            // per (row, replica) instead of the 256-byte activation row to apply LeakyReLU'
+            unsigned f[VEC];
+#pragma unroll
+            for (int k = 0; k < VEC; ++k) f[k] = (__ballot_sync(gmask, y[k] > 0.f) >> (sub * LANES)) & 0xffffu;
+            if (sl == 0)
+              P.mbits[(size_t)row * P.replicas + (b0 + r)] =
+                  (unsigned long long)(f[0] | (f[1] << 16)) | ((unsigned long long)(f[2] | (f[3] << 16)) << 32);
+          }
         }
       }
     }
@@ -575,6 +601,9 @@ __global__ void __launch_bounds__(kThreads, 2) sage_rank1_fwd_kernel(const GsP P
 // ---------------------------------------------------------------------------------------------
 struct R1B {
   const float* gz;
+  const unsigned long long* mbits;   // optional (C == 64): sign bits of y written by sage_rank1_fwd_kernel, [n][B]
+  const float* y;      // optional: gz is dL/dy of this layer's LeakyReLU output y; the kernel applies the derivative
+  float slope;
   const float* xs;
   const int* rowptr;
   const int* idx;
@@ -587,8 +616,15 @@ struct R1B {
   int n, B;
 };
 
+#ifndef MLG_R1B_MINB
+#define MLG_R1B_MINB 2     // resident blocks per SM (register budget 128; 1 -> 255)
+#endif
+#ifndef MLG_R1B_YB
+#define MLG_R1B_YB 8       // replicas whose y values (self-masking) are requested together
+#endif
+
 template <int CPL>
-__global__ void __launch_bounds__(kThreads, 2) sage_rank1_bwd_rows_kernel(const R1B P) {
+__global__ void __launch_bounds__(kThreads, MLG_R1B_MINB) sage_rank1_bwd_rows_kernel(const R1B P) {
   constexpr int C = 32 * CPL;
   constexpr int EU = 4;   // entries whose x loads are in flight together
   const int lane = threadIdx.x & 31;
@@ -606,6 +642,32 @@ __global__ void __launch_bounds__(kThreads, 2) sage_rank1_bwd_rows_kernel(const 
     for (int b = 0; b < 32; ++b)
 #pragma unroll
       for (int k = 0; k < CPL; ++k) g[k][b] = b < nb ? __ldg(gp + (size_t)b * P.n * P.ld_g + 32 * k) : 0.f;
+    if (P.mbits) {   // gz arrived as dL/dy: LeakyReLU'(y) from the forward kernel's sign bits (one 8-byte word per replica)
+      const unsigned long long wd = lane < nb ? __ldg(P.mbits + (size_t)row * P.B + rb0 + lane) : ~0ull;
+      const unsigned lo = (unsigned)wd, hi = (unsigned)(wd >> 32);
+      const int pos = (lane & 3) * 16 + (lane >> 2);    // channel `lane`; channel lane + 32 sits 8 bits higher
+#pragma unroll
+      for (int b = 0; b < 32; ++b) {
+        const unsigned long long w =
+            ((unsigned long long)__shfl_sync(0xffffffffu, hi, b) << 32) | __shfl_sync(0xffffffffu, lo, b);
+        g[0][b] *= ((w >> pos) & 1ull) ? 1.f : P.slope;
+        if (CPL == 2) g[CPL - 1][b] *= ((w >> (pos + 8)) & 1ull) ? 1.f : P.slope;
+      }
+    } else if (P.y) {   // gz arrived as dL/dy: multiply by LeakyReLU'(y) (y has the layout of gz); 8 replicas' y values at a time
+      const float* yp = P.y + ((size_t)rb0 * P.n + row) * P.ld_g + lane;
+#pragma unroll
+      for (int b8 = 0; b8 < 32; b8 += MLG_R1B_YB) {
+        float yv[CPL][MLG_R1B_YB];
+#pragma unroll
+        for (int b = 0; b < MLG_R1B_YB; ++b)
+#pragma unroll
+          for (int k = 0; k < CPL; ++k) yv[k][b] = b8 + b < nb ? __ldg(yp + (size_t)(b8 + b) * P.n * P.ld_g + 32 * k) : 1.f;
+#pragma unroll
+        for (int b = 0; b < MLG_R1B_YB; ++b)
+#pragma unroll
+          for (int k = 0; k < CPL; ++k) g[k][b8 + b] *= yv[k][b] > 0.f ? 1.f : P.slope;
+      }
+    }
     const float* xp = P.xs + (size_t)(rb0 + min(lane, nb - 1)) * P.n;   // lane b reads replica rb0+b (clamped; masked below)
     const float lane_live = lane < nb ? 1.f : 0.f;
     {
@@ -749,6 +811,18 @@ extern "C" int mlg_gather_sum(const float* src, int64_t ld_src, const int32_t* r
                               int64_t ld_add, float* out, int64_t ld_out, float* self_out, int64_t ld_self,
                               const float* mask, int64_t ld_mask, float mask_slope, const float* reduce_scale,
                               void* stream) {
+  return mlg_gather_sum_act(src, ld_src, rowptr, idx, val, pre, post, order, n_rows, C, replicas, rep_rows_src, rep_rows_pre,
+                            post_mode, relative, addend, ld_add, out, ld_out, self_out, ld_self, mask, ld_mask, mask_slope,
+                            reduce_scale, 0, 0.f, stream);
+}
+
+extern "C" int mlg_gather_sum_act(const float* src, int64_t ld_src, const int32_t* rowptr, const int32_t* idx,
+                                  const float* val, const float* pre, const float* post, const int32_t* order,
+                                  int64_t n_rows, int64_t C, int64_t replicas, int64_t rep_rows_src,
+                                  int64_t rep_rows_pre, int post_mode, int relative, const float* addend,
+                                  int64_t ld_add, float* out, int64_t ld_out, float* self_out, int64_t ld_self,
+                                  const float* mask, int64_t ld_mask, float mask_slope, const float* reduce_scale,
+                                  int act, float act_slope, void* stream) {
   MLG_CHECK_ARG(src && rowptr && idx && out, "mlg_gather_sum: null src/rowptr/idx/out");
   MLG_CHECK_ARG(n_rows >= 0 && n_rows < (1ll << 31) && C > 0 && C < (1ll << 20),
                 "mlg_gather_sum: bad sizes n_rows=%lld C=%lld", (long long)n_rows, (long long)C);
@@ -773,7 +847,10 @@ extern "C" int mlg_gather_sum(const float* src, int64_t ld_src, const int32_t* r
   P.ld_src = (unsigned)ld_src; P.ld_out = (unsigned)ld_out; P.ld_add = (unsigned)ld_add; P.ld_self = (unsigned)ld_self;
   P.n = (int)n_rows; P.C = (int)C; P.post_mode = post_mode; P.relative = relative;
   P.replicas = (int)replicas; P.rep_rows_src = (unsigned)rep_rows_src; P.rep_rows_pre = (unsigned)rep_rows_pre;
-  P.e_self = nullptr; P.bias = nullptr; P.act_slope = 0.f; P.aux1 = nullptr; P.auxb = nullptr; P.ld_aux1 = P.ld_auxb = 0;
+  P.e_self = nullptr; P.bias = nullptr; P.act_slope = act_slope; P.act = act; P.aux1 = nullptr; P.auxb = nullptr; P.ld_aux1 = P.ld_auxb = 0;
+  MLG_CHECK_ARG(!act || (replicas > 1 && rep_rows_src > 0 && !relative && !reduce_scale),
+                "mlg_gather_sum_act: the fused activation needs the replicated path (replicas > 1, per-replica src), no "
+                "relative / reduce_scale");
   cudaStream_t st = (cudaStream_t)stream;
   const int wpb = kThreads / 32;
   int lanes = 32, rows_per_block = wpb;
@@ -820,7 +897,7 @@ extern "C" int mlg_gather_sum(const float* src, int64_t ld_src, const int32_t* r
 extern "C" int mlg_sage_rank1_fwd(const float* xs, const float* e_self, int64_t ld_self, const float* e_nbr,
                                   int64_t ld_nbr, const int32_t* rowptr, const int32_t* idx, const float* val,
                                   const int32_t* order, int64_t n_rows, int64_t C, int64_t replicas, const float* bias,
-                                  float slope, float* out, int64_t ld_out, void* stream) {
+                                  float slope, float* out, int64_t ld_out, uint64_t* mask_bits, void* stream) {
   MLG_CHECK_ARG(xs && e_self && e_nbr && rowptr && idx && out, "mlg_sage_rank1_fwd: null pointer");
   MLG_CHECK_ARG(n_rows >= 0 && replicas >= 2 && replicas * n_rows < (1ll << 31) && C > 0 && C % 4 == 0 && C < (1ll << 20),
                 "mlg_sage_rank1_fwd: bad sizes (needs replicas >= 2, C %% 4 == 0)");
@@ -835,6 +912,8 @@ extern "C" int mlg_sage_rank1_fwd(const float* xs, const float* e_self, int64_t 
   P.out = out; P.ld_out = (unsigned)ld_out; P.e_self = e_self; P.ld_self = (unsigned)ld_self; P.bias = bias;
   P.act_slope = slope; P.n = (int)n_rows; P.C = (int)C; P.post_mode = 1; P.replicas = (int)replicas;
   P.rep_rows_src = 0; P.rep_rows_pre = (unsigned)n_rows;
+  MLG_CHECK_ARG(!mask_bits || C == 64, "mlg_sage_rank1_fwd: mask_bits needs C == 64");
+  P.mbits = reinterpret_cast<unsigned long long*>(mask_bits);
   int lanes, rpb;
   rep_geometry(C, true, &lanes, &rpb);
   const long long gx = mlg_ceil_div(n_rows, rpb);
@@ -887,7 +966,7 @@ extern "C" int mlg_sage_rank1_bwd(const float* gz, int64_t ld_g, const float* xs
 
 extern "C" int mlg_sage_rank1_bwd_rows_supported(int64_t C) { return C == 32 || C == 64; }
 
-extern "C" int mlg_sage_rank1_bwd_rows(const float* gz, int64_t ld_g, const float* xs, const int32_t* rowptr,
+extern "C" int mlg_sage_rank1_bwd_rows(const float* gz, int64_t ld_g, const float* y, const uint64_t* mask_bits, float slope, const float* xs, const int32_t* rowptr,
                                        const int32_t* idx, const float* val, const int32_t* order, int64_t n_rows,
                                        int64_t C, int64_t replicas, float* h, float* g_self, int64_t ld_self,
                                        float* g_bias_rows, void* stream) {
@@ -897,7 +976,9 @@ extern "C" int mlg_sage_rank1_bwd_rows(const float* gz, int64_t ld_g, const floa
                 "mlg_sage_rank1_bwd_rows: bad sizes");
   if (n_rows == 0) return MLG_OK;
   R1B P;
-  P.gz = gz; P.xs = xs; P.rowptr = rowptr; P.idx = idx; P.val = val; P.order = order; P.h = h; P.g_self = g_self;
+  MLG_CHECK_ARG(!mask_bits || C == 64, "mlg_sage_rank1_bwd_rows: mask_bits needs C == 64");
+  P.mbits = reinterpret_cast<const unsigned long long*>(mask_bits);
+  P.gz = gz; P.y = y; P.slope = slope; P.xs = xs; P.rowptr = rowptr; P.idx = idx; P.val = val; P.order = order; P.h = h; P.g_self = g_self;
   P.g_bias_rows = g_bias_rows; P.ld_g = (unsigned)ld_g; P.ld_self = (unsigned)ld_self; P.n = (int)n_rows; P.B = (int)replicas;
   const unsigned grid = (unsigned)mlg_ceil_div(n_rows, kThreads / 32);
   cudaStream_t st = (cudaStream_t)stream;

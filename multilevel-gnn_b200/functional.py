@@ -38,7 +38,7 @@ def _vptr(t):
 
 def gather_sum(src, rowptr, idx, n_rows, val=None, pre=None, post=None, post_mode=0, relative=False, out=None,
                addend=None, self_out=None, replicas=1, order=None, rank1=False, tag="gather_sum", mask=None,
-               mask_slope=0.0, reduce_scale=None):
+               mask_slope=0.0, reduce_scale=None, act_slope=None):
     """Raw (non-differentiable) call of mlg_gather_sum.  src / out / addend / self_out may be column
     slices of wider row-major buffers (leading dimension = stride(0))."""
     L = _cabi.lib()
@@ -51,16 +51,18 @@ def gather_sum(src, rowptr, idx, n_rows, val=None, pre=None, post=None, post_mod
         out = torch.empty(total_rows, C, dtype=torch.float32, device=src.device)
     # algorithmic bytes: rows read once + rows written once + (idx, val) per entry
     nbytes = 4 * C * total_rows * 2 + 8 * idx.numel()
-    with torch.cuda.device(src.device), _cabi.span(tag, nbytes):
-        _cabi.check(L.mlg_gather_sum(
-            _vptr(src), _ld(src), _cabi.iptr(rowptr), _cabi.iptr(idx), _cabi.fptr(val, True), _cabi.fptr(pre, True),
+    args = (_vptr(src), _ld(src), _cabi.iptr(rowptr), _cabi.iptr(idx), _cabi.fptr(val, True), _cabi.fptr(pre, True),
             _cabi.fptr(post, True), _cabi.iptr(order, True), n_rows, C, replicas, 0 if rank1 else n_rows,
             n_rows if rank1 else 0, post_mode, int(relative),
             None if addend is None else _vptr(addend), 0 if addend is None else _ld(addend),
             _vptr(out), _ld(out), None if self_out is None else _vptr(self_out),
             0 if self_out is None else _ld(self_out), None if mask is None else _vptr(mask),
-            0 if mask is None else _ld(mask), float(mask_slope), _cabi.fptr(reduce_scale, True), _cabi.stream_ptr()),
-            "mlg_gather_sum")
+            0 if mask is None else _ld(mask), float(mask_slope), _cabi.fptr(reduce_scale, True))
+    with torch.cuda.device(src.device), _cabi.span(tag, nbytes):
+        if act_slope is None:
+            _cabi.check(L.mlg_gather_sum(*args, _cabi.stream_ptr()), "mlg_gather_sum")
+        else:     # fused output activation (replicated path)
+            _cabi.check(L.mlg_gather_sum_act(*args, 1, float(act_slope), _cabi.stream_ptr()), "mlg_gather_sum_act")
     return out
 
 
@@ -487,6 +489,15 @@ class SageAggregate(torch.autograd.Function):
 # first layer of MultilevelGNN through mlg_sage_rank1_fwd / mlg_sage_rank1_bwd_rows; "gather": backward through the
 # by-source gather mlg_sage_rank1_bwd (any width); False: [x0 | agg] buffer + GEMMs
 FACTORED_RANK1 = True
+# SAGE layers with out_channels < in_channels evaluated transform-first (gather on the narrower rows); False: [x | agg] + GEMM
+TRANSFORM_FIRST = True
+RANK1_SIGN_BITS = True    # factored first layer keeps 64 sign bits per (row, replica) for its own activation backward
+# Row visiting order of the replicated kernels: degree-sorted (balanced lane groups, but output / addend rows are touched
+# in random order) or natural (rows stream through DRAM in address order).  Per kernel family; A/B switches for tuning.
+import os as _os
+ORDER_R1B = _os.environ.get("MLG_ORDER_R1B", "0") == "1"      # mlg_sage_rank1_bwd_rows (warp per row: nothing to balance)
+ORDER_R1F = _os.environ.get("MLG_ORDER_R1F", "1") == "1"      # mlg_sage_rank1_fwd
+ORDER_TF = _os.environ.get("MLG_ORDER_TF", "1") == "1"        # transform-first layer: forward / backward aggregation
 
 
 class SageLayer(torch.autograd.Function):
@@ -536,17 +547,44 @@ class SageLayer(torch.autograd.Function):
             csr = topo.fwd
             bias = None if nn_b is None else _f32c(nn_b.detach())
             nbytes = 4 * cout * n + 4 * n + 8 * csr.col.numel() + 8 * cout * n1
+            # the consumer does not pre-mask our output gradient: keep the sign bits of y (8 bytes per row and replica) so that
+            # the backward kernel applies LeakyReLU' without re-reading y
+            mbits = None
+            if RANK1_SIGN_BITS and cout == 64 and not out_premasked and torch.is_grad_enabled():
+                mbits = torch.empty(n1 * topo.replicas, dtype=torch.int64, device=xd.device)
             with torch.cuda.device(xd.device), _cabi.span("sage_rank1_fwd", nbytes):
                 _cabi.check(L.mlg_sage_rank1_fwd(
                     _cabi.fptr(xs_d), _vptr(e12), 2 * cout, _vptr(e12[:, cout:]), 2 * cout, _cabi.iptr(csr.rowptr),
-                    _cabi.iptr(csr.col), _cabi.fptr(topo.fwd_val, True), _cabi.iptr(topo.fwd_order, True), n1, cout,
-                    topo.replicas, _cabi.fptr(bias, True), float(slope), _cabi.fptr(y), cout, _cabi.stream_ptr()),
-                    "mlg_sage_rank1_fwd")
+                    _cabi.iptr(csr.col), _cabi.fptr(topo.fwd_val, True), _cabi.iptr(topo.fwd_order if ORDER_R1F else None, True),
+                    n1, cout, topo.replicas, _cabi.fptr(bias, True), float(slope), _cabi.fptr(y), cout,
+                    _cabi.lptr(mbits, True), _cabi.stream_ptr()), "mlg_sage_rank1_fwd")
+            ctx.mbits = mbits
             ctx.save_for_backward(xd, y, wst, w_r, w_nn, xs_d)
             ctx.topo, ctx.relative, ctx.slope, ctx.cin, ctx.has_bias = topo, False, float(slope), cin, nn_b is not None
-            ctx.rank1, ctx.factored = True, True
+            ctx.rank1, ctx.factored, ctx.transform_first = True, True, False
             ctx.emb_param = x if isinstance(x, torch.nn.Parameter) else None
             ctx.in_slope = None
+            ctx.out_premasked = bool(out_premasked)
+            return y
+        ctx.transform_first = False
+        if (TRANSFORM_FIRST and not rank1 and not relative and in_slope is None and topo.replicas > 1 and cout < cin
+                and cout % 4 == 0 and cin % 4 == 0 and n == topo.n_single * topo.replicas):
+            # out_channels < in_channels: transform, THEN aggregate -- z = U + mean_j(w_ij V_j) with
+            # [U | V] = x [W1 ; W2 W_r]^T + [b | 0]: the gather (the L2-bandwidth-bound step) runs on cout-wide rows instead of
+            # cin-wide ones, forward and backward, and no [x | agg] buffer is written.
+            wst = wcat.view(cout, 2, cin).permute(1, 0, 2).reshape(2 * cout, cin)      # [W1 ; W2 W_r]   [2cout, cin]
+            bias2 = None
+            if nn_b is not None:
+                bias2 = torch.zeros(2 * cout, dtype=torch.float32, device=xd.device)
+                bias2[:cout].copy_(nn_b.detach())
+            uv = tall_matmul(xd, wst, bias2, tag="sage_update_gemm")                   # [n, 2cout] = [U | V]
+            csr = topo.fwd
+            y = gather_sum(uv[:, cout:], csr.rowptr, csr.col, topo.n_single, val=topo.fwd_val, post_mode=1,
+                           addend=uv[:, :cout], replicas=topo.replicas, order=topo.fwd_order if ORDER_TF else None,
+                           tag="sage_aggr_fwd", act_slope=slope)
+            ctx.save_for_backward(xd, y, wst, w_r, w_nn, None)
+            ctx.topo, ctx.relative, ctx.slope, ctx.cin, ctx.has_bias = topo, False, float(slope), cin, nn_b is not None
+            ctx.rank1, ctx.transform_first, ctx.emb_param, ctx.in_slope = False, True, None, None
             ctx.out_premasked = bool(out_premasked)
             return y
         wsplit = (wbuf[1].view(cout, 2 * cin), wbuf[2].view(cout, 2 * cin))
@@ -575,14 +613,19 @@ class SageLayer(torch.autograd.Function):
         topo, cin = ctx.topo, ctx.cin
         cout = w_nn.shape[0]
         gy = _f32c(gy)
+        L = _cabi.lib()
+        n1, B = topo.n_single, topo.replicas
+        by_rows = FACTORED_RANK1 != "gather" and bool(L.mlg_sage_rank1_bwd_rows_supported(cout))
+        y_mask = None
         if ctx.out_premasked:
             gz = gy
+        elif by_rows:
+            # the kernel applies LeakyReLU'(y) while it loads the gradient rows: from the forward kernel's sign bits, else from y
+            gz, y_mask = gy, (None if ctx.mbits is not None else y)
         else:
             gz = torch.ops.aten.leaky_relu_backward(gy, y, ctx.slope, True) if ctx.slope != 0.0 \
                 else torch.ops.aten.threshold_backward(gy, y, 0.0)
-        L = _cabi.lib()
-        n1, B = topo.n_single, topo.replicas
-        if FACTORED_RANK1 != "gather" and L.mlg_sage_rank1_bwd_rows_supported(cout):
+        if by_rows:
             # by target row: gz read once -> per-entry rows h (+ the self / bias reductions), then a segment sum by source
             fw, bw = topo.fwd, topo.bwd
             g12 = torch.empty(n1, 2 * cout, dtype=torch.float32, device=gz.device)      # [g_E_self | g_E_nbr]
@@ -591,8 +634,12 @@ class SageLayer(torch.autograd.Function):
             nbytes = 4 * cout * gz.shape[0] + 4 * gz.shape[0] + 8 * fw.col.numel() + 4 * (h.numel() + 2 * gbr.numel())
             with torch.cuda.device(gz.device), _cabi.span("sage_rank1_bwd", nbytes):
                 _cabi.check(L.mlg_sage_rank1_bwd_rows(
-                    _cabi.fptr(gz), cout, _cabi.fptr(xs_d), _cabi.iptr(fw.rowptr), _cabi.iptr(fw.col),
-                    _cabi.fptr(topo.fwd_val, True), _cabi.iptr(topo.fwd_order, True), n1, cout, B, _cabi.fptr(h),
+                    _cabi.fptr(gz), cout, _cabi.fptr(y_mask, True),
+                    _cabi.lptr(ctx.mbits if (y_mask is None and not ctx.out_premasked) else None, True), float(ctx.slope),
+                    _cabi.fptr(xs_d), _cabi.iptr(fw.rowptr),
+                    _cabi.iptr(fw.col),
+                    _cabi.fptr(topo.fwd_val, True), _cabi.iptr(topo.fwd_order if ORDER_R1B else None, True), n1, cout, B,
+                    _cabi.fptr(h),
                     _cabi.fptr(g12), 2 * cout, _cabi.fptr(gbr), _cabi.stream_ptr()), "mlg_sage_rank1_bwd_rows")
             gather_sum(h, bw.rowptr, topo.bwd2fwd, n1, out=g12[:, cout:], order=topo.bwd_order, tag="sage_rank1_bwd_seg")
             g_b = None
@@ -630,9 +677,54 @@ class SageLayer(torch.autograd.Function):
         return g_emb, None, g_wr, g_wnn, g_b, None, None, None, None, None
 
     @staticmethod
+    def _backward_transform_first(ctx, gy):
+        x, y, wst, w_r, w_nn, _ = ctx.saved_tensors
+        topo, cin = ctx.topo, ctx.cin
+        cout = w_nn.shape[0]
+        gy = _f32c(gy)
+        if ctx.out_premasked:
+            gz = gy
+        else:
+            gz = torch.ops.aten.leaky_relu_backward(gy, y, ctx.slope, True) if ctx.slope != 0.0 \
+                else torch.ops.aten.threshold_backward(gy, y, 0.0)
+        L = _cabi.lib()
+        n = gz.shape[0]
+        bw = topo.bwd
+        # G = [g_U | g_V] = [gz | A^T gz]: the by-source aggregation runs on the cout-wide gz rows and copies them alongside
+        g_uv = torch.empty(n, 2 * cout, dtype=torch.float32, device=gz.device)
+        gather_sum(gz, bw.rowptr, bw.col, topo.n_single, val=topo.bwd_val, pre=topo.inv_cnt, out=g_uv[:, cout:],
+                   self_out=g_uv[:, :cout], replicas=topo.replicas, order=topo.bwd_order if ORDER_TF else None,
+                   tag="sage_aggr_bwd")
+        needs = ctx.needs_input_grad
+        gx = g_wr = g_wnn = g_b = None
+        if needs[0]:
+            gx = tall_matmul(g_uv, wst.t().contiguous(), tag="sage_dgrad_gemm")         # dL/dx (the producer masks it itself)
+        if needs[2] or needs[3] or needs[4]:
+            if n % 2 == 0 and 4 * cout == 128 and 2 * cin == 128:
+                # tensor-core weight gradient on ROW PAIRS: [G_even | G_odd]^T [x_even | x_odd] is 128 x 128; its two diagonal
+                # blocks are the even- and odd-row halves of G^T x (the off-diagonal blocks are discarded)
+                o2, cs2 = xty(g_uv.view(n // 2, 4 * cout), x.view(n // 2, 2 * cin), want_colsum=ctx.has_bias, tag="sage_wgrad")
+                g_wst = o2[:2 * cout, :cin] + o2[2 * cout:, cin:]
+                if ctx.has_bias:
+                    g_b = cs2[:cout] + cs2[2 * cout:3 * cout]
+            else:
+                g_wst, cs = xty(g_uv, x, want_colsum=ctx.has_bias, tag="sage_wgrad")
+                if ctx.has_bias:
+                    g_b = cs[:cout]
+            g_wcat = g_wst.view(2, cout, cin).permute(1, 0, 2).reshape(cout, 2 * cin)
+            g_wnn, g_wr = torch.empty_like(w_nn), torch.empty_like(w_r)
+            with torch.cuda.device(gz.device):
+                _cabi.check(L.mlg_sage_fold_bwd(_cabi.fptr(g_wcat), _cabi.fptr(w_nn), _cabi.fptr(w_r), cout, cin,
+                                                w_r.shape[0], _cabi.fptr(g_wnn), _cabi.fptr(g_wr), _cabi.stream_ptr()),
+                            "mlg_sage_fold_bwd")
+        return gx, None, g_wr, g_wnn, (g_b if ctx.has_bias else None), None, None, None, None, None
+
+    @staticmethod
     def backward(ctx, gy):
         if ctx.factored:
             return SageLayer._backward_factored(ctx, gy)
+        if ctx.transform_first:
+            return SageLayer._backward_transform_first(ctx, gy)
         xcat, y, wbuf, w_r, w_nn, xs_d = ctx.saved_tensors
         topo, cin = ctx.topo, ctx.cin
         cout = w_nn.shape[0]

@@ -133,6 +133,12 @@ class SAGEConv(nn.Module):
         agg = F.linear(agg_x, self.lin_r.weight)
         return self.update(agg, x)
 
+    def masks_input_grad(self):
+        """Whether this layer, asked to, multiplies its input gradient by the producer's activation derivative inside
+        its own backward kernel.  Not when it runs transform-first (out_channels < in_channels, Fn.SageLayer): its
+        input gradient leaves a GEMM, and the producer applies its own derivative instead."""
+        return not self.relative and not (Fn.TRANSFORM_FIRST and self.out_channels < self.in_channels)
+
     def grad_fusion_slope(self):
         """Slope of this layer's output activation if the layer runs as the fused Fn.SageLayer (so that it can take a
         pre-masked output gradient, and -- when not ``relative`` -- mask its own input gradient); else None."""
@@ -190,6 +196,9 @@ class GraphConv(nn.Module):
 
     def grad_fusion_slope(self):
         return self.gconv.grad_fusion_slope()
+
+    def masks_input_grad(self):
+        return self.gconv.masks_input_grad()
 
     @property
     def relative(self):

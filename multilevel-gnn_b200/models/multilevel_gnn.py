@@ -160,9 +160,10 @@ class MultilevelGNN(nn.Module):
             pool_masks = plain and slopes[-1] is not None and (not args.value_att_mask or args.merge_mode == 'mult')
             for i, layer in enumerate(self.gnn_model):
                 if plain and slopes[i] is not None:
+                    masks = lambda l: getattr(l, "masks_input_grad", lambda: not getattr(l, "relative", True))()
                     consumer_masks = pool_masks if i + 1 == n_layers else \
-                        (slopes[i + 1] is not None and not getattr(self.gnn_model[i + 1], "relative", True))
-                    producer_masked = i > 0 and slopes[i - 1] is not None and not getattr(layer, "relative", True)
+                        (slopes[i + 1] is not None and masks(self.gnn_model[i + 1]))
+                    producer_masked = i > 0 and slopes[i - 1] is not None and masks(layer)
                     layer._mlg_fuse = (slopes[i - 1] if producer_masked else None, bool(consumer_masks))
                 y = layer(x, edge_index, edge_attr)
                 if args.dense_gnn:

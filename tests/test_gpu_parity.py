@@ -587,8 +587,10 @@ def test_factored_first_layer_is_equivalent(mlg):
         b = synth.multilevel_batch(batch_size=5, seed=6).to(DEV)
         params = [p for n, p in model.named_parameters() if p.requires_grad and not n.endswith("lin_l.weight")]
 
-        def run(factored):
+        def run(factored, tfirst=True, sign_bits=True):
             Fn.FACTORED_RANK1 = factored
+            Fn.TRANSFORM_FIRST = tfirst
+            Fn.RANK1_SIGN_BITS = sign_bits
             type(model).FUSE_ACT_BACKWARD = fuse
             torch.manual_seed(11)                     # same dropout masks
             timer = _cabi.KernelTimer()
@@ -601,17 +603,23 @@ def test_factored_first_layer_is_equivalent(mlg):
             finally:
                 _cabi.TIMER = None
                 Fn.FACTORED_RANK1 = True
+                Fn.TRANSFORM_FIRST = True
+                Fn.RANK1_SIGN_BITS = True
                 type(model).FUSE_ACT_BACKWARD = True
             return pred.detach(), feat.detach(), g, set(timer.summary())
 
-        p0, f0, g0, tags0 = run(False)
+        p0, f0, g0, tags0 = run(False, False)      # [x | agg] buffer + GEMM in both layers
         assert not ({"sage_rank1_fwd", "sage_rank1_bwd"} & tags0), tags0
         names = [n for n, p in model.named_parameters() if p.requires_grad and not n.endswith("lin_l.weight")]
         # True: backward by target row (mlg_sage_rank1_bwd_rows + segment sum); "gather": by-source gather (mlg_sage_rank1_bwd)
-        for mode in (True, "gather"):
-            p1, f1, g1, tags1 = run(mode)
-            assert {"sage_rank1_fwd", "sage_rank1_bwd"} <= tags1, tags1
-            assert ("sage_rank1_bwd_seg" in tags1) == (mode is True), (mode, tags1)
+        # second flag: layer 2 (64 -> 32) transform-first (gathers on 32-wide rows, layer 1 masks its own output gradient)
+        # third flag: layer 1 applies its own LeakyReLU' from the forward kernel's sign bits (False: re-reads y)
+        for mode, tfirst, bits in ((True, True, True), (True, True, False), ("gather", True, True), (True, False, True),
+                                   (False, True, True)):
+            p1, f1, g1, tags1 = run(mode, tfirst, bits)
+            if mode is not False:
+                assert {"sage_rank1_fwd", "sage_rank1_bwd"} <= tags1, tags1
+                assert ("sage_rank1_bwd_seg" in tags1) == (mode is True), (mode, tags1)
             assert_close(p1, p0, rtol=1e-5, atol=1e-6, what="factored vs buffered pred")
             assert_close(f1, f0, rtol=1e-4, atol=1e-6, what="factored vs buffered pooled features")
             for n, a, c in zip(names, g1, g0):
@@ -619,7 +627,7 @@ def test_factored_first_layer_is_equivalent(mlg):
                     assert a is None and c is None
                     continue
                 sc = float(c.abs().max().clamp_min(1e-30))      # compare at unit scale: atol is then relative to the largest entry
-                assert_close(a / sc, c / sc, rtol=1e-4, atol=2e-6, what="factored (%s) vs buffered grad %s" % (mode, n))
+                assert_close(a / sc, c / sc, rtol=1e-4, atol=2e-6, what="factored (%s, transform-first %s) vs buffered grad %s" % (mode, tfirst, n))
 
 
 def test_maxpool_channel_last_matches_torch(mlg):
