@@ -491,11 +491,21 @@ class SageAggregate(torch.autograd.Function):
 FACTORED_RANK1 = True
 # SAGE layers with out_channels < in_channels evaluated transform-first (gather on the narrower rows); False: [x | agg] + GEMM
 TRANSFORM_FIRST = True
-RANK1_SIGN_BITS = True    # factored first layer keeps 64 sign bits per (row, replica) for its own activation backward
-# Row visiting order of the replicated kernels: degree-sorted (balanced lane groups, but output / addend rows are touched
-# in random order) or natural (rows stream through DRAM in address order).  Per kernel family; A/B switches for tuning.
+# When no consumer pre-masks the factored first layer's output gradient (the next layer runs transform-first), the layer has
+# to apply LeakyReLU'(y) itself.  RANK1_SELF_MASK: inside mlg_sage_rank1_bwd_rows, from y or (RANK1_SIGN_BITS) from 64 sign bits
+# per (row, replica) its forward kernel wrote.  Measured on B200 (tools/ab_layer2.sh, gbm shape): the in-kernel variants run
+# that kernel at 179-185 us against 61 us unmasked, so one library leaky_relu_backward pass + the unmasked kernel is FASTER
+# (step 1.000 ms vs 1.086 ms) and is the default; the in-kernel paths stay selectable (and tested) until an ncu capture
+# explains the regression.
+RANK1_SIGN_BITS = True
+RANK1_SELF_MASK = False
+# Row visiting order of the replicated kernels: degree-sorted (heavy rows first, balanced lane groups) or natural.  Measured
+# on B200 (tools/ab_order.sh, gbm shape): sorted wins everywhere -- rank-1 forward 109 vs 166 us, layer-2 aggregations 150 vs
+# 288 us per step, rank-1 backward 184 vs 215 us.  Per kernel family; the switches stay for tuning.
 import os as _os
-ORDER_R1B = _os.environ.get("MLG_ORDER_R1B", "0") == "1"      # mlg_sage_rank1_bwd_rows (warp per row: nothing to balance)
+ORDER_R1B = _os.environ.get("MLG_ORDER_R1B", "1") == "1"      # mlg_sage_rank1_bwd_rows
+TRANSFORM_FIRST = _os.environ.get("MLG_TRANSFORM_FIRST", "1") == "1"
+RANK1_SELF_MASK = _os.environ.get("MLG_R1_SELF_MASK", "0") == "1"
 ORDER_R1F = _os.environ.get("MLG_ORDER_R1F", "1") == "1"      # mlg_sage_rank1_fwd
 ORDER_TF = _os.environ.get("MLG_ORDER_TF", "1") == "1"        # transform-first layer: forward / backward aggregation
 
@@ -550,7 +560,7 @@ class SageLayer(torch.autograd.Function):
             # the consumer does not pre-mask our output gradient: keep the sign bits of y (8 bytes per row and replica) so that
             # the backward kernel applies LeakyReLU' without re-reading y
             mbits = None
-            if RANK1_SIGN_BITS and cout == 64 and not out_premasked and torch.is_grad_enabled():
+            if RANK1_SIGN_BITS and RANK1_SELF_MASK and cout == 64 and not out_premasked and torch.is_grad_enabled():
                 mbits = torch.empty(n1 * topo.replicas, dtype=torch.int64, device=xd.device)
             with torch.cuda.device(xd.device), _cabi.span("sage_rank1_fwd", nbytes):
                 _cabi.check(L.mlg_sage_rank1_fwd(
@@ -619,7 +629,7 @@ class SageLayer(torch.autograd.Function):
         y_mask = None
         if ctx.out_premasked:
             gz = gy
-        elif by_rows:
+        elif by_rows and RANK1_SELF_MASK:
             # the kernel applies LeakyReLU'(y) while it loads the gradient rows: from the forward kernel's sign bits, else from y
             gz, y_mask = gy, (None if ctx.mbits is not None else y)
         else:
@@ -697,8 +707,8 @@ class SageLayer(torch.autograd.Function):
                    tag="sage_aggr_bwd")
         needs = ctx.needs_input_grad
         gx = g_wr = g_wnn = g_b = None
-        if needs[0]:
-            gx = tall_matmul(g_uv, wst.t().contiguous(), tag="sage_dgrad_gemm")         # dL/dx (the producer masks it itself)
+        # weight gradient FIRST, input gradient LAST: the producer's backward kernel reads gx right away, and it only finds it
+        # in L2 if nothing streams 250 MB through the cache in between (measured: 58 us vs 185 us for that kernel)
         if needs[2] or needs[3] or needs[4]:
             if n % 2 == 0 and 4 * cout == 128 and 2 * cin == 128:
                 # tensor-core weight gradient on ROW PAIRS: [G_even | G_odd]^T [x_even | x_odd] is 128 x 128; its two diagonal
@@ -717,6 +727,8 @@ class SageLayer(torch.autograd.Function):
                 _cabi.check(L.mlg_sage_fold_bwd(_cabi.fptr(g_wcat), _cabi.fptr(w_nn), _cabi.fptr(w_r), cout, cin,
                                                 w_r.shape[0], _cabi.fptr(g_wnn), _cabi.fptr(g_wr), _cabi.stream_ptr()),
                             "mlg_sage_fold_bwd")
+        if needs[0]:
+            gx = tall_matmul(g_uv, wst.t().contiguous(), tag="sage_dgrad_gemm")         # dL/dx (the producer masks it itself)
         return gx, None, g_wr, g_wnn, (g_b if ctx.has_bias else None), None, None, None, None, None
 
     @staticmethod

@@ -587,10 +587,13 @@ def test_factored_first_layer_is_equivalent(mlg):
         b = synth.multilevel_batch(batch_size=5, seed=6).to(DEV)
         params = [p for n, p in model.named_parameters() if p.requires_grad and not n.endswith("lin_l.weight")]
 
-        def run(factored, tfirst=True, sign_bits=True):
+        defaults = (Fn.FACTORED_RANK1, Fn.TRANSFORM_FIRST, Fn.RANK1_SIGN_BITS, Fn.RANK1_SELF_MASK)
+
+        def run(factored, tfirst=True, sign_bits=True, self_mask=False):
             Fn.FACTORED_RANK1 = factored
             Fn.TRANSFORM_FIRST = tfirst
             Fn.RANK1_SIGN_BITS = sign_bits
+            Fn.RANK1_SELF_MASK = self_mask
             type(model).FUSE_ACT_BACKWARD = fuse
             torch.manual_seed(11)                     # same dropout masks
             timer = _cabi.KernelTimer()
@@ -602,9 +605,7 @@ def test_factored_first_layer_is_equivalent(mlg):
                 torch.cuda.synchronize()
             finally:
                 _cabi.TIMER = None
-                Fn.FACTORED_RANK1 = True
-                Fn.TRANSFORM_FIRST = True
-                Fn.RANK1_SIGN_BITS = True
+                Fn.FACTORED_RANK1, Fn.TRANSFORM_FIRST, Fn.RANK1_SIGN_BITS, Fn.RANK1_SELF_MASK = defaults
                 type(model).FUSE_ACT_BACKWARD = True
             return pred.detach(), feat.detach(), g, set(timer.summary())
 
@@ -613,10 +614,11 @@ def test_factored_first_layer_is_equivalent(mlg):
         names = [n for n, p in model.named_parameters() if p.requires_grad and not n.endswith("lin_l.weight")]
         # True: backward by target row (mlg_sage_rank1_bwd_rows + segment sum); "gather": by-source gather (mlg_sage_rank1_bwd)
         # second flag: layer 2 (64 -> 32) transform-first (gathers on 32-wide rows, layer 1 masks its own output gradient)
-        # third flag: layer 1 applies its own LeakyReLU' from the forward kernel's sign bits (False: re-reads y)
-        for mode, tfirst, bits in ((True, True, True), (True, True, False), ("gather", True, True), (True, False, True),
-                                   (False, True, True)):
-            p1, f1, g1, tags1 = run(mode, tfirst, bits)
+        # fourth flag: layer 1 applies its own LeakyReLU' inside its backward kernel -- third flag: from the forward kernel's
+        # sign bits (False: re-reads y) -- instead of one library pass before it
+        for mode, tfirst, bits, smask in ((True, True, True, False), (True, True, True, True), (True, True, False, True),
+                                          ("gather", True, True, False), (True, False, True, False), (False, True, True, False)):
+            p1, f1, g1, tags1 = run(mode, tfirst, bits, smask)
             if mode is not False:
                 assert {"sage_rank1_fwd", "sage_rank1_bwd"} <= tags1, tags1
                 assert ("sage_rank1_bwd_seg" in tags1) == (mode is True), (mode, tags1)
