@@ -626,12 +626,13 @@ class SageLayer(torch.autograd.Function):
         L = _cabi.lib()
         n1, B = topo.n_single, topo.replicas
         by_rows = FACTORED_RANK1 != "gather" and bool(L.mlg_sage_rank1_bwd_rows_supported(cout))
-        y_mask = None
+        y_mask = bits = None
         if ctx.out_premasked:
             gz = gy
         elif by_rows and RANK1_SELF_MASK:
             # the kernel applies LeakyReLU'(y) while it loads the gradient rows: from the forward kernel's sign bits, else from y
-            gz, y_mask = gy, (None if ctx.mbits is not None else y)
+            gz, bits = gy, ctx.mbits
+            y_mask = y if bits is None else None
         else:
             gz = torch.ops.aten.leaky_relu_backward(gy, y, ctx.slope, True) if ctx.slope != 0.0 \
                 else torch.ops.aten.threshold_backward(gy, y, 0.0)
@@ -645,7 +646,7 @@ class SageLayer(torch.autograd.Function):
             with torch.cuda.device(gz.device), _cabi.span("sage_rank1_bwd", nbytes):
                 _cabi.check(L.mlg_sage_rank1_bwd_rows(
                     _cabi.fptr(gz), cout, _cabi.fptr(y_mask, True),
-                    _cabi.lptr(ctx.mbits if (y_mask is None and not ctx.out_premasked) else None, True), float(ctx.slope),
+                    _cabi.lptr(bits, True), float(ctx.slope),
                     _cabi.fptr(xs_d), _cabi.iptr(fw.rowptr),
                     _cabi.iptr(fw.col),
                     _cabi.fptr(topo.fwd_val, True), _cabi.iptr(topo.fwd_order if ORDER_R1B else None, True), n1, cout, B,
