@@ -1,0 +1,81 @@
+"""Shapes of the reformulated SAGE layers that the gbm-shape tests do not reach: more than 32 graphs per batch (the
+kirc / lgg configs train with 64: the by-row backward of the factored first layer then makes several replica passes), and
+the one-kernel pathway independence loss against the library expression of the reference
+(models/multilevel_gnn.py:336-346).  Runs after the other GPU files (file name order)."""
+import pytest
+import torch
+
+from conftest import assert_close
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+@pytest.fixture(scope="module")
+def mlg():
+    import multilevel_gnn_b200 as m
+    m._cabi.lib()
+    return m
+
+
+def test_reformulated_layers_with_more_than_32_graphs(mlg):
+    """B = 40 graphs: replica blocks of 32 + 8 in mlg_sage_rank1_bwd_rows, 8-replica chunks with a ragged tail in
+    mlg_sage_rank1_fwd, odd slice sizes in the aggregations -- against the buffered [x | agg] + GEMM path."""
+    from multilevel_gnn_b200 import configs, functional as Fn, synth
+    args = configs.make_args("gbm")
+    torch.manual_seed(5)
+    model = mlg.MultilevelGNN(args)
+    synth.multilevel_params(model)
+    model.to(DEV).train()
+    model.pathway_indexs = model.pathway_indexs.to(DEV)
+    b = synth.multilevel_batch(batch_size=40, seed=9).to(DEV)
+    names = [n for n, p in model.named_parameters() if p.requires_grad and not n.endswith("lin_l.weight")]
+    params = [p for n, p in model.named_parameters() if p.requires_grad and not n.endswith("lin_l.weight")]
+    defaults = (Fn.FACTORED_RANK1, Fn.TRANSFORM_FIRST)
+
+    def run(factored, tfirst):
+        Fn.FACTORED_RANK1, Fn.TRANSFORM_FIRST = factored, tfirst
+        torch.manual_seed(11)
+        try:
+            pred, feat = model(b)
+            loss = (pred * torch.arange(pred.numel(), device=DEV).reshape(pred.shape)).sum() + feat.square().mean()
+            g = torch.autograd.grad(loss, params, allow_unused=True)
+            torch.cuda.synchronize()
+        finally:
+            Fn.FACTORED_RANK1, Fn.TRANSFORM_FIRST = defaults
+        return pred.detach(), feat.detach(), g
+
+    p0, f0, g0 = run(False, False)
+    p1, f1, g1 = run(True, True)
+    assert_close(p1, p0, rtol=1e-5, atol=1e-6, what="pred")
+    assert_close(f1, f0, rtol=1e-4, atol=1e-6, what="pooled features")
+    for n, a, c in zip(names, g1, g0):
+        if a is None or c is None:
+            assert a is None and c is None
+            continue
+        sc = float(c.abs().max().clamp_min(1e-30))
+        assert_close(a / sc, c / sc, rtol=1e-4, atol=2e-6, what="grad " + n)
+
+
+@pytest.mark.parametrize("P", [2, 3, 5])
+def test_pca_indep_kernel_matches_library_expression(mlg, P):
+    """mlg_pca_indep_loss vs the index_add / sqrt / abs / mean expression it replaces, incl. empty segments."""
+    from multilevel_gnn_b200 import _cabi
+    g = torch.Generator().manual_seed(100 + P)
+    G, nseg = 5003, 211
+    idx = torch.sort(torch.randint(0, nseg, (G,), generator=g)).values
+    idx[idx == 17] = 18                                   # an empty segment in the middle
+    idx = torch.sort(idx).values
+    w = torch.randn(G, P, generator=g) * 0.05
+    mask = (torch.rand(G, generator=g) > 0.5).float()
+    wm = (w * mask[:, None]).double()
+    a, bcol = wm[:, :P - 1], wm[:, P - 1:P]
+    seg = torch.zeros(nseg, 2 * (P - 1) + 1, dtype=torch.float64).index_add_(0, idx, torch.cat([a * bcol, a * a, bcol * bcol], 1))
+    mul, ln = seg[:, :P - 1], torch.sqrt(seg[:, P - 1:2 * (P - 1)] * seg[:, 2 * (P - 1):])
+    ref = torch.abs(mul / (ln + 1e-7)).mean(0).sum() / (P * (P - 1) // 2)
+    segptr = torch.searchsorted(idx, torch.arange(nseg + 1)).to(torch.int32).to(DEV)
+    out = torch.empty(1, device=DEV)
+    wd, md = w.to(DEV).contiguous(), mask.to(DEV).contiguous()
+    _cabi.check(_cabi.lib().mlg_pca_indep_loss(_cabi.fptr(wd), _cabi.fptr(md), _cabi.iptr(segptr), nseg, P, _cabi.fptr(out),
+                                              _cabi.stream_ptr()), "mlg_pca_indep_loss")
+    assert_close(out.cpu().double(), ref.reshape(1), rtol=1e-4, atol=1e-7, what="pca_indep P=%d" % P)
