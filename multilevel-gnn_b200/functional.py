@@ -3,6 +3,8 @@
 Each Function cites the reference lines whose autograd graph it replaces.  Tensors are allocated by
 torch, the kernels only fill them (include/mlg_b200.h conventions).
 """
+import os
+
 import torch
 
 from . import _cabi
@@ -486,28 +488,30 @@ class SageAggregate(torch.autograd.Function):
         return gx, None, None
 
 
+def _flag(name, default):
+    """Evaluation-order / tuning switches below can be set per process through the environment (tools/ab_*.sh)."""
+    return os.environ.get(name, "1" if default else "0") == "1"
+
+
 # first layer of MultilevelGNN through mlg_sage_rank1_fwd / mlg_sage_rank1_bwd_rows; "gather": backward through the
 # by-source gather mlg_sage_rank1_bwd (any width); False: [x0 | agg] buffer + GEMMs
 FACTORED_RANK1 = True
 # SAGE layers with out_channels < in_channels evaluated transform-first (gather on the narrower rows); False: [x | agg] + GEMM
-TRANSFORM_FIRST = True
+TRANSFORM_FIRST = _flag("MLG_TRANSFORM_FIRST", True)
 # When no consumer pre-masks the factored first layer's output gradient (the next layer runs transform-first), the layer has
 # to apply LeakyReLU'(y) itself.  RANK1_SELF_MASK: inside mlg_sage_rank1_bwd_rows, from y or (RANK1_SIGN_BITS) from 64 sign bits
-# per (row, replica) its forward kernel wrote.  Measured on B200 (tools/ab_layer2.sh, gbm shape): the in-kernel variants run
-# that kernel at 179-185 us against 61 us unmasked, so one library leaky_relu_backward pass + the unmasked kernel is FASTER
-# (step 1.000 ms vs 1.086 ms) and is the default; the in-kernel paths stay selectable (and tested) until an ncu capture
-# explains the regression.
+# per (row, replica) its forward kernel wrote.  Measured on B200 (tools/ab_layer2.sh, gbm shape): with the dX GEMM's output as
+# its direct input that kernel runs at 179-185 us against 61 us behind an elementwise pass, so one library
+# leaky_relu_backward pass + the unmasked kernel is FASTER (step 1.000 ms vs 1.086 ms) and is the default; the in-kernel
+# paths stay selectable (and tested) until an ncu capture explains the regression (tools/rank1_bwd_probe.py, DESIGN section 6).
 RANK1_SIGN_BITS = True
-RANK1_SELF_MASK = False
+RANK1_SELF_MASK = _flag("MLG_R1_SELF_MASK", False)
 # Row visiting order of the replicated kernels: degree-sorted (heavy rows first, balanced lane groups) or natural.  Measured
 # on B200 (tools/ab_order.sh, gbm shape): sorted wins everywhere -- rank-1 forward 109 vs 166 us, layer-2 aggregations 150 vs
 # 288 us per step, rank-1 backward 184 vs 215 us.  Per kernel family; the switches stay for tuning.
-import os as _os
-ORDER_R1B = _os.environ.get("MLG_ORDER_R1B", "1") == "1"      # mlg_sage_rank1_bwd_rows
-TRANSFORM_FIRST = _os.environ.get("MLG_TRANSFORM_FIRST", "1") == "1"
-RANK1_SELF_MASK = _os.environ.get("MLG_R1_SELF_MASK", "0") == "1"
-ORDER_R1F = _os.environ.get("MLG_ORDER_R1F", "1") == "1"      # mlg_sage_rank1_fwd
-ORDER_TF = _os.environ.get("MLG_ORDER_TF", "1") == "1"        # transform-first layer: forward / backward aggregation
+ORDER_R1B = _flag("MLG_ORDER_R1B", True)       # mlg_sage_rank1_bwd_rows
+ORDER_R1F = _flag("MLG_ORDER_R1F", True)       # mlg_sage_rank1_fwd
+ORDER_TF = _flag("MLG_ORDER_TF", True)         # transform-first layer: forward / backward aggregation
 
 
 class SageLayer(torch.autograd.Function):
