@@ -12,6 +12,13 @@
 // every entry issues RB independent row loads (memory-level parallelism even for 1-entry rows).
 //
 // HBM-bound: algorithmic bytes = 4*C*rows*2 + 8*nnz.
+//
+// Also here, because they share the row / lane-group / replica-slice geometry and the helpers:
+//   * the fast replicated epilogue's extras -- the row's own src rows copied alongside (self_out: left half of cat(x, agg)),
+//     addend, activation-derivative mask, fused output activation (mlg_gather_sum_act: transform-first SAGE layer);
+//   * the fully factored first SAGE layer of MultilevelGNN: sage_rank1_fwd_kernel (mlg_sage_rank1_fwd),
+//     sage_rank1_bwd_rows_kernel (mlg_sage_rank1_bwd_rows, by target row) and the by-source gather variant
+//     (gather_sum_rep_kernel<.., RED, AUX>, mlg_sage_rank1_bwd) for widths the by-row kernel does not cover.
 #include <cstdlib>
 
 #include "common.cuh"
