@@ -397,6 +397,10 @@ def run_b200(a):
     ksum = timer.summary()
     barrier(world)
 
+    if tr.peer is not None and tr.peer.status() != 0:
+        # a rank gave up waiting for a peer's flag inside the fused update kernel: the replicas are no longer in step
+        raise SystemExit("bench.py: rank %d: a peer wait of the fused NVLink update kernel timed out; the measurement is void "
+                         "(re-run with --nccl-update to take the library path)" % rank)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
