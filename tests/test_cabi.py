@@ -35,6 +35,41 @@ def test_header_symbols_exported(lib):
     assert sorted(_cabi.exported_symbols()) == names, "ctypes table and header disagree"
 
 
+def test_ctypes_signatures_match_header():
+    """Every prototype of include/mlg_b200.h against the ctypes table: same argument count, pointers bound as c_void_p,
+    int64_t / int / float / double as the matching scalar -- a drifted binding would push garbage into a kernel launch."""
+    from multilevel_gnn_b200 import _cabi
+    hdr = open(os.path.join(ROOT, "include", "mlg_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    hdr = re.sub(r"//[^\n]*", "", hdr)
+    kinds = {ctypes.c_void_p: "ptr", ctypes.c_char_p: "ptr", ctypes.c_int64: "i64", ctypes.c_int: "int",
+             ctypes.c_float: "f32", ctypes.c_double: "f64"}
+    seen = 0
+    for ret, name, args in re.findall(r"([A-Za-z_][A-Za-z0-9_ \*]*?)\b(mlg_[a-z0-9_]+)\s*\(([^)]*)\)\s*;", hdr):
+        res, argtypes = _cabi._SIGNATURES[name]
+        params = [a.strip() for a in args.split(",") if a.strip() and a.strip() != "void"]
+        want = []
+        for prm in params:
+            if "*" in prm:
+                want.append("ptr")
+            elif re.match(r"(const\s+)?(int64_t|uint64_t)\b", prm):
+                want.append("i64")
+            elif re.match(r"(const\s+)?int\b", prm):
+                want.append("int")
+            elif re.match(r"(const\s+)?float\b", prm):
+                want.append("f32")
+            elif re.match(r"(const\s+)?double\b", prm):
+                want.append("f64")
+            else:
+                raise AssertionError("%s: unrecognised parameter %r" % (name, prm))
+        got = [kinds[t] for t in argtypes]
+        assert got == want, "%s: header %s vs ctypes %s" % (name, want, got)
+        rk = "ptr" if "*" in ret else ("i64" if "int64_t" in ret else "int")
+        assert kinds[res] == rk, "%s: return type %s vs ctypes %s" % (name, ret.strip(), kinds[res])
+        seen += 1
+    assert seen == len(_cabi._SIGNATURES), "parsed %d prototypes, table has %d" % (seen, len(_cabi._SIGNATURES))
+
+
 def test_abi_version_and_errors(lib):
     from multilevel_gnn_b200 import _cabi
     assert lib.mlg_abi_version() == 1
