@@ -104,10 +104,28 @@ __device__ __forceinline__ float4 lds128(unsigned addr) {
 __device__ __forceinline__ void sts128(unsigned addr, float4 v) {
   asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
+// MLG_TF32X3_STORE_HINT (A/B switch, default 0 = no hint): 1 = L2 evict_first, 2 = L2 evict_last on the output tiles.  The
+// kernel that reads a GEMM output right away was measured 3x slower than behind an elementwise pass (DESIGN.md section 6
+// item 1); the hint decides whether the 126 MB of output lines should stream through L2 or stay in it.
+#ifndef MLG_TF32X3_STORE_HINT
+#define MLG_TF32X3_STORE_HINT 0
+#endif
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, unsigned src, int c0, int c1) {
+#if MLG_TF32X3_STORE_HINT == 0
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(src), "r"(c0),
                "r"(c1)
                : "memory");
+#else
+  unsigned long long policy;
+#if MLG_TF32X3_STORE_HINT == 1
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+#else
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(policy));
+#endif
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3}], [%1], %4;" ::"l"(map),
+               "r"(src), "r"(c0), "r"(c1), "l"(policy)
+               : "memory");
+#endif
 }
 
 // shared memory: [B_hi: kb][N x 128 B] [B_lo: kb][...] [stages][A_hi 16 KB | A_lo 16 KB] [out staging 32 KB] Ctl
