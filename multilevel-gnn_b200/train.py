@@ -251,6 +251,14 @@ class Trainer:
         NCCL process group, peer access between all ranks, no gradient clipping -- clipping needs the averaged gradient
         on every rank before the update); False = NCCL all-reduce + replicated FlatAdam; True = require PeerAdam."""
         self.model, self.args, self.world = model, args, world_size
+        # reference flags this trainer does not implement must not be silently ignored (train.py:52-57 per-sample
+        # criterion weights with reduction='none'; train.py:113-116 StepLR)
+        for flag in ("weighted_loss", "batch_weighted_loss"):
+            if getattr(args, flag, False):
+                raise NotImplementedError("Trainer: args.%s (per-sample BCE weights, train.py:52-57) is not implemented" % flag)
+        if getattr(args, "step", 0) and getattr(args, "step", 0) > 0:
+            raise NotImplementedError("Trainer: args.step > 0 (StepLR, train.py:113-116) is not implemented: lr is a launch "
+                                      "constant of the captured update kernel")
         self.params = [p for n, p in model.named_parameters() if p.requires_grad and not n.endswith("lin_l.weight")]
         dev = self.params[0].device
         self.peer = None
@@ -363,8 +371,20 @@ class Trainer:
         return sum(getattr(host_batch, k).numel() * getattr(host_batch, k).element_size()
                    for k in self._step_fields(host_batch))
 
+    def _check_topology(self, host_batch):
+        """The CSR, pooling layout, degree tables and visiting orders are built in the warm-up steps and BAKED into the
+        captured graph: a batch with another edge list / match table would silently train on the stale topology.  Batches
+        must therefore carry the ``topology_key`` the graph was captured with (loaders: data.TopologyLoader)."""
+        key = getattr(self.static_batch, "topology_key", None)
+        other = getattr(host_batch, "topology_key", None)
+        if key is None or other != key:
+            raise ValueError("Trainer: the topology is frozen at capture(); this batch has topology_key=%r, the captured "
+                             "graph %r -- re-capture for a new topology, or step eagerly" % (other, key))
+
     def load_batch(self, host_batch):
-        """Copy a (pinned) host batch into the captured graph's static device buffers (async H2D)."""
+        """Copy a (pinned) host batch into the captured graph's static device buffers (async H2D).  Only per-step
+        fields are copied: the topology fields are frozen at capture()."""
+        self._check_topology(host_batch)
         for k in self._step_fields(host_batch):
             getattr(self.static_batch, k).copy_(getattr(host_batch, k), non_blocking=True)
 
@@ -373,6 +393,7 @@ class Trainer:
         graph is still running; ``step_prefetched`` then moves it into the static buffers (device-to-device)
         and replays.  This is the double buffering the reference's synchronous ``batch.to(device)``
         (train.py:42) lacks."""
+        self._check_topology(host_batch)
         if self._copy_stream is None:
             self._copy_stream = torch.cuda.Stream()
             self._staging = {k: torch.empty_like(getattr(self.static_batch, k)) for k in self._step_fields(host_batch)}

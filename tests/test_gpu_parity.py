@@ -538,7 +538,8 @@ def test_skinny_linear_and_head_wgrad(mlg):
 
 def test_activation_backward_fusion_is_equivalent(mlg):
     """The cross-layer fusion (consumer kernels apply LeakyReLU' of their input; producers take dL/dz) must give the
-    gradients of the unfused chain, and must actually remove the per-layer activation-backward pass."""
+    gradients of the unfused chain (numerics only; which kernels ran is asserted in tests/test_gpu_zz_structure.py,
+    which sorts last so that a structural regression can never hide numerical tests behind ``-x``)."""
     from multilevel_gnn_b200 import configs, synth
     args = configs.make_args("gbm")
     torch.manual_seed(3)
@@ -555,21 +556,18 @@ def test_activation_backward_fusion_is_equivalent(mlg):
         try:
             pred, feat = model(b)
             loss = (pred * torch.arange(pred.numel(), device=DEV).reshape(pred.shape)).sum() + feat.square().mean()
-            with torch.profiler.profile(activities=[torch.profiler.ProfilerActivity.CPU]) as prof:
-                g = torch.autograd.grad(loss, params, allow_unused=True)
-            seen = [e.key for e in prof.key_averages() if "leaky_relu_backward" in e.key]
+            g = torch.autograd.grad(loss, params, allow_unused=True)
         finally:
             type(model).FUSE_ACT_BACKWARD = True
-        return g, seen
+        return g
 
-    g1, seen1 = grads(True)
-    g0, seen0 = grads(False)
+    g1 = grads(True)
+    g0 = grads(False)
     for a, c in zip(g1, g0):
         if a is None or c is None:
             assert a is None and c is None
             continue
         assert_close(a, c, rtol=1e-5, atol=1e-7, what="fused vs unfused grad")
-    assert len(seen0) >= 1 and len(seen1) == 0, (seen0, seen1)
 
 
 def test_factored_first_layer_is_equivalent(mlg):

@@ -33,7 +33,7 @@ def _virtual_ranks(mlg, shapes, world, seed, wd):
     return init, arenas, ranks, g
 
 
-@pytest.mark.parametrize("world,wd", [(1, 0.0), (2, 0.0), (3, 0.0), (4, 1e-2)])
+@pytest.mark.parametrize("world,wd", [(1, 0.0), (1, 1e-2)])
 def test_peer_adam_matches_torch_adam(mlg, world, wd):
     shapes = [(257, 33), (1000,), (64, 64), (3,), (50001,)]
     init, arenas, ranks, g = _virtual_ranks(mlg, shapes, world, 7 + world, wd)
