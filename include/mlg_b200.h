@@ -280,6 +280,39 @@ int mlg_skinny_linear(const float* x, int64_t ld_x, const float* W, int64_t ld_w
                       int64_t N, int64_t K, int act, float slope, float* out, int64_t ld_out, void* workspace,
                       int64_t workspace_bytes, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * MultilevelGNN's classification head + loss, fused (models/multilevel_gnn.py:262-290; train.py:60,118).
+ * Replaces: Conv2d(32->32,1x1)+ReLU, Conv2d(32->64,1x1)+ReLU, MaxPool2d((kh,kw)) (stride = kernel, floor mode), Dropout,
+ * flatten, cat(age), Linear(K->D)+ReLU+Dropout, Linear(D->2), Softmax, BCELoss(weight) and their backward ops.
+ *
+ * x_cl [B,H,W,32]: the pooled pathway features, channel-last (mlg_pool_fwd's layout).  a0 [B, ld]: the flattened head
+ * input in NCHW order (column c*Ho*Wo + ho*Wo + wo, c < 64) and, when age != NULL, age[b] in column 64*Ho*Wo.
+ * Dropout: element kept iff drop_bits[i] >= p * 2^31 and scaled by 1/(1-p); drop_bits are caller-provided uniform
+ * int32 words in [0, 2^31) (NULL / p == 0: no dropout) indexed like the tensor they mask ([B, 64*Ho*Wo] and [R, D]).
+ * Backward of conv/pool recomputes both convolutions; the gradient of a window goes to its FIRST maximum (ATen).
+ * g_x_cl [B,H,W,32] is fully written (zeros for pixels the floor-mode pool drops). */
+int mlg_head_conv_pool_supported(int64_t cin, int64_t c1, int64_t c2);
+int64_t mlg_head_conv_pool_bwd_workspace_bytes(int64_t B, int64_t H, int64_t W, int64_t kh, int64_t kw);
+int mlg_head_conv_pool_fwd(const float* x_cl, const float* W1, const float* b1, const float* W2, const float* b2,
+                           const float* age, const int32_t* drop_bits, float drop_p, int64_t B, int64_t H, int64_t W,
+                           int64_t kh, int64_t kw, float* a0, int64_t ld, void* stream);
+int mlg_head_conv_pool_bwd(const float* g_a0, int64_t ld, const float* x_cl, const float* W1, const float* b1,
+                           const float* W2, const float* b2, const int32_t* drop_bits, float drop_p, int64_t B, int64_t H,
+                           int64_t W, int64_t kh, int64_t kw, float* g_x_cl, float* g_W1, float* g_b1, float* g_W2,
+                           float* g_b2, void* workspace, int64_t workspace_bytes, void* stream);
+/* a1 [R,D] = dropout(relu(a0[:, :K] W0^T + b0)); pred [R,2] = softmax(a1 W3^T + b3); with y [R,2] given also
+ * loss[0] = mean(weight * BCE(pred, y)) (weight [R,2] or NULL; logs clamped at -100 like ATen).  R <= 64.
+ * Backward: g_pred [R,2] and / or g_loss [1] (device scalars) -> g_a0 [R, ld_g] (NULL: not needed), g_W0 [D,K], g_b0,
+ * g_W3 [2,D], g_b3; D a multiple of 32 up to 512. */
+int64_t mlg_head_mlp_workspace_bytes(int64_t R, int64_t D, int64_t K);
+int mlg_head_mlp_fwd(const float* a0, int64_t ld_a, const float* W0, const float* b0, const float* W3, const float* b3,
+                     const int32_t* drop_bits, float drop_p, const float* y, const float* weight, int64_t R, int64_t D,
+                     int64_t K, float* a1, float* pred, float* loss, void* workspace, int64_t workspace_bytes, void* stream);
+int mlg_head_mlp_bwd(const float* g_pred, const float* g_loss, const float* pred, const float* y, const float* weight,
+                     const float* a0, int64_t ld_a, const float* a1, const float* W0, const float* W3, float drop_p,
+                     int64_t R, int64_t D, int64_t K, float* g_a0, int64_t ld_g, float* g_W0, float* g_b0, float* g_W3,
+                     float* g_b3, void* stream);
+
 /* z[r,c] = LeakyReLU_slope(z[r,c] + bias[c]) in place (bias NULL ok; slope 0 = ReLU): the bias + activation
  * of SAGEConv.update's MLP (torch_vertex.py:288-291) after the update GEMM. */
 int mlg_bias_act(float* z, const float* bias, int64_t rows, int64_t C, float slope, void* stream);

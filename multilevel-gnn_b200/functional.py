@@ -505,7 +505,7 @@ TRANSFORM_FIRST = _flag("MLG_TRANSFORM_FIRST", True)
 # leaky_relu_backward pass + the unmasked kernel is FASTER (step 1.000 ms vs 1.086 ms) and is the default; the in-kernel
 # paths stay selectable (and tested) until an ncu capture explains the regression (tools/rank1_bwd_probe.py).
 RANK1_SIGN_BITS = True
-RANK1_SELF_MASK = _flag("MLG_R1_SELF_MASK", False)
+RANK1_SELF_MASK = _flag("MLG_R1_SELF_MASK", True)
 # Row visiting order of the replicated kernels: degree-sorted (heavy rows first, balanced lane groups) or natural.  Measured
 # on B200 (tools/ab_order.sh, gbm shape): sorted wins everywhere -- rank-1 forward 109 vs 166 us, layer-2 aggregations 150 vs
 # 288 us per step, rank-1 backward 184 vs 215 us.  Per kernel family; the switches stay for tuning.
@@ -1002,3 +1002,151 @@ class PathwayPool(torch.autograd.Function):
         if gx is not None and ctx.in_slope is not None:      # unfused fallback of the activation-derivative mask
             gx = torch.where(xd > 0, gx, gx * ctx.in_slope)
         return gx, gw, None, None, None
+
+
+def _drop_bits(n, device):
+    """Uniform int32 words in [0, 2^31) from torch's CUDA generator (graph-safe; torch.manual_seed applies): the dropout
+    masks of the fused head kernels (kept iff bits >= p * 2^31)."""
+    return torch.empty(n, dtype=torch.int32, device=device).random_()
+
+
+class HeadConvPool(torch.autograd.Function):
+    """Conv2d(32->32,1x1)+ReLU, Conv2d(32->64,1x1)+ReLU, MaxPool2d((kh,kw)), Dropout(p), flatten, cat(age) of
+    MultilevelGNN's head (models/multilevel_gnn.py:262-288) as one kernel each way (mlg_head_conv_pool_fwd / _bwd).
+
+    forward(feat [B,32,H,W] whose MEMORY is channel-last, W1 [32,32,1,1], b1, W2 [64,32,1,1], b2, age [B] or None,
+            kh, kw, p, training) -> a0 [B, 64*(H//kh)*(W//kw) (+1)]"""
+
+    @staticmethod
+    def supported(feat, conv1, conv2):
+        return (feat.is_cuda and feat.dtype == torch.float32 and conv1.kernel_size == (1, 1) and conv2.kernel_size == (1, 1)
+                and conv1.bias is not None and conv2.bias is not None
+                and bool(_cabi.lib().mlg_head_conv_pool_supported(conv1.in_channels, conv1.out_channels, conv2.out_channels))
+                and conv2.in_channels == conv1.out_channels and feat.shape[1] == conv1.in_channels)
+
+    @staticmethod
+    def forward(ctx, feat, W1, b1, W2, b2, age, kh, kw, p, training):
+        L = _cabi.lib()
+        _cabi.require_cuda(feat, W1, W2)
+        B, C, H, W = feat.shape
+        x_cl = feat.detach().permute(0, 2, 3, 1)
+        if not x_cl.is_contiguous():
+            x_cl = x_cl.contiguous()
+        Ho, Wo = H // kh, W // kw
+        F_ = W2.shape[0] * Ho * Wo
+        ld = F_ + (1 if age is not None else 0)
+        p = float(p) if training else 0.0
+        bits = _drop_bits(B * F_, feat.device) if p > 0.0 else None
+        a0 = torch.empty(B, ld, dtype=torch.float32, device=feat.device)
+        w1, w2 = _f32c(W1.detach()).view(W1.shape[0], -1), _f32c(W2.detach()).view(W2.shape[0], -1)
+        b1d, b2d = _f32c(b1.detach()), _f32c(b2.detach())
+        aged = None if age is None else _f32c(age.detach().reshape(-1))
+        nbytes = 4 * (x_cl.numel() + a0.numel())
+        with torch.cuda.device(feat.device), _cabi.span("head_conv_pool_fwd", nbytes):
+            _cabi.check(L.mlg_head_conv_pool_fwd(_cabi.fptr(x_cl), _cabi.fptr(w1), _cabi.fptr(b1d), _cabi.fptr(w2),
+                                                 _cabi.fptr(b2d), _cabi.fptr(aged, True), _cabi.iptr(bits, True), p, B, H, W,
+                                                 int(kh), int(kw), _cabi.fptr(a0), ld, _cabi.stream_ptr()),
+                        "mlg_head_conv_pool_fwd")
+        ctx.save_for_backward(x_cl, w1, b1d, w2, b2d, bits)
+        ctx.dims = (B, H, W, int(kh), int(kw), p, ld)
+        ctx.params = (W1, b1, W2, b2)
+        return a0
+
+    @staticmethod
+    def backward(ctx, g):
+        L = _cabi.lib()
+        x_cl, w1, b1d, w2, b2d, bits = ctx.saved_tensors
+        B, H, W, kh, kw, p, ld = ctx.dims
+        W1, b1, W2, b2 = ctx.params
+        g = _f32c(g)
+        gx = torch.empty_like(x_cl)
+        dev = x_cl.device
+
+        def dest(param):
+            slot = grad_slot(param, param.shape)
+            return slot if slot is not None else torch.empty(param.shape, dtype=torch.float32, device=dev)
+
+        gW1, gb1, gW2, gb2 = dest(W1), dest(b1), dest(W2), dest(b2)
+        ws_bytes = L.mlg_head_conv_pool_bwd_workspace_bytes(B, H, W, kh, kw)
+        ws = torch.empty(ws_bytes // 4, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev), _cabi.span("head_conv_pool_bwd", 4 * (2 * x_cl.numel() + g.numel())):
+            _cabi.check(L.mlg_head_conv_pool_bwd(_cabi.fptr(g), ld, _cabi.fptr(x_cl), _cabi.fptr(w1), _cabi.fptr(b1d),
+                                                 _cabi.fptr(w2), _cabi.fptr(b2d), _cabi.iptr(bits, True), p, B, H, W, kh, kw,
+                                                 _cabi.fptr(gx), _cabi.fptr(gW1), _cabi.fptr(gb1), _cabi.fptr(gW2),
+                                                 _cabi.fptr(gb2), _cabi.fptr(ws), ws_bytes, _cabi.stream_ptr()),
+                        "mlg_head_conv_pool_bwd")
+        g_age = g[:, ld - 1] if (ctx.needs_input_grad[5]) else None
+        return gx.permute(0, 3, 1, 2), gW1, gb1, gW2, gb2, g_age, None, None, None, None
+
+
+class HeadMLP(torch.autograd.Function):
+    """Linear(K->D)+ReLU+Dropout(p), Linear(D->2), Softmax (models/multilevel_gnn.py:104-110,288-290) and, when the target
+    is given, BCELoss(weight) (train.py:60,118) in two launches forward, one backward (mlg_head_mlp_fwd / _bwd).
+
+    forward(a0 [B,K], W0 [D,K], b0, W3 [2,D], b3, p, training, y [B,2] or None, weight [B,2] or None) -> (pred [B,2], bce [])"""
+
+    @staticmethod
+    def supported(a0, lin0, lin3):
+        return (a0.is_cuda and a0.dtype == torch.float32 and a0.dim() == 2 and a0.shape[0] <= 64 and lin3.out_features == 2
+                and lin0.out_features % 32 == 0 and lin0.out_features <= 512 and lin0.bias is not None
+                and lin3.bias is not None and lin3.in_features == lin0.out_features and a0.shape[1] == lin0.in_features)
+
+    @staticmethod
+    def forward(ctx, a0, W0, b0, W3, b3, p, training, y, weight):
+        L = _cabi.lib()
+        _cabi.require_cuda(a0, W0, W3)
+        ctx.set_materialize_grads(False)
+        R, K = a0.shape
+        D = W0.shape[0]
+        dev = a0.device
+        a0d = a0.detach()
+        a0d = a0d if (a0d.stride(1) == 1 and a0d.dtype == torch.float32) else _f32c(a0d)
+        w0, w3 = _f32c(W0.detach()), _f32c(W3.detach())
+        b0d, b3d = _f32c(b0.detach()), _f32c(b3.detach())
+        p = float(p) if training else 0.0
+        bits = _drop_bits(R * D, dev) if p > 0.0 else None
+        yd = None if y is None else _f32c(y.detach().reshape(R, 2))
+        wd = None if weight is None else _f32c(weight.detach().expand(R, 2))
+        a1 = torch.empty(R, D, dtype=torch.float32, device=dev)
+        pred = torch.empty(R, 2, dtype=torch.float32, device=dev)
+        loss = torch.zeros((), dtype=torch.float32, device=dev) if yd is None else torch.empty((), dtype=torch.float32, device=dev)
+        ws_bytes = L.mlg_head_mlp_workspace_bytes(R, D, K)
+        ws = torch.empty(ws_bytes // 4, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev), _cabi.span("head_mlp_fwd", 4 * (D * K + R * K)):
+            _cabi.check(L.mlg_head_mlp_fwd(_vptr(a0d), a0d.stride(0), _cabi.fptr(w0), _cabi.fptr(b0d), _cabi.fptr(w3),
+                                           _cabi.fptr(b3d), _cabi.iptr(bits, True), p, _cabi.fptr(yd, True),
+                                           _cabi.fptr(wd, True), R, D, K, _cabi.fptr(a1), _cabi.fptr(pred),
+                                           _vptr(loss), _cabi.fptr(ws), ws_bytes, _cabi.stream_ptr()), "mlg_head_mlp_fwd")
+        ctx.save_for_backward(a0d, a1, pred, w0, w3, yd, wd)
+        ctx.p = p
+        ctx.params = (W0, b0, W3, b3)
+        if yd is None:
+            ctx.mark_non_differentiable(loss)
+        return pred, loss
+
+    @staticmethod
+    def backward(ctx, g_pred, g_loss):
+        L = _cabi.lib()
+        a0d, a1, pred, w0, w3, yd, wd = ctx.saved_tensors
+        if g_pred is None and (g_loss is None or yd is None):
+            return (None,) * 9
+        W0, b0, W3, b3 = ctx.params
+        R, K = a0d.shape
+        D = w0.shape[0]
+        dev = a0d.device
+        gp = None if g_pred is None else _f32c(g_pred)
+        gl = None if (g_loss is None or yd is None) else _f32c(g_loss).reshape(1)
+
+        def dest(param):
+            slot = grad_slot(param, param.shape)
+            return slot if slot is not None else torch.empty(param.shape, dtype=torch.float32, device=dev)
+
+        gW0, gb0, gW3, gb3 = dest(W0), dest(b0), dest(W3), dest(b3)
+        g_a0 = torch.empty(R, K, dtype=torch.float32, device=dev) if ctx.needs_input_grad[0] else None
+        with torch.cuda.device(dev), _cabi.span("head_mlp_bwd", 4 * (2 * D * K + 2 * R * K)):
+            _cabi.check(L.mlg_head_mlp_bwd(_cabi.fptr(gp, True), _cabi.fptr(gl, True), _cabi.fptr(pred), _cabi.fptr(yd, True),
+                                           _cabi.fptr(wd, True), _vptr(a0d), a0d.stride(0), _cabi.fptr(a1), _cabi.fptr(w0),
+                                           _cabi.fptr(w3), ctx.p, R, D, K, _cabi.fptr(g_a0, True), K, _cabi.fptr(gW0),
+                                           _cabi.fptr(gb0), _cabi.fptr(gW3), _cabi.fptr(gb3), _cabi.stream_ptr()),
+                        "mlg_head_mlp_bwd")
+        return g_a0, gW0, gb0, gW3, gb3, None, None, None, None

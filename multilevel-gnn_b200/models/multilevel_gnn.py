@@ -109,8 +109,10 @@ class MultilevelGNN(nn.Module):
         self.init_weight()
 
     # ------------------------------------------------------------------------------------------
-    def forward(self, input_batch, x=None, gene_pca_match=None, raw_indice=None, age=None, require_grad=True):
+    def forward(self, input_batch, x=None, gene_pca_match=None, raw_indice=None, age=None, require_grad=True,
+                _loss_args=None):
         args = self.args
+        loss_args = _loss_args
         with torch.enable_grad() if require_grad else torch.no_grad():
             if x is not None:
                 mask_x = x
@@ -196,6 +198,19 @@ class MultilevelGNN(nn.Module):
                 x = x[:, :, self.reorder_idxs.to(x.device), :]
 
         pca_feature = x
+        if self.FUSED_HEAD and self._fused_head_ok(x):
+            # head + loss as four kernels (csrc/head.cu): conv1x1+ReLU x2 + max-pool + dropout + flatten + cat(age), then
+            # Linear+ReLU+dropout + Linear(->2) + softmax (+ weighted BCE when the trainer passes the target)
+            ks = self.pooling.kernel_size if isinstance(self.pooling.kernel_size, tuple) else (self.pooling.kernel_size,) * 2
+            a0 = Fn.HeadConvPool.apply(x, self.conv_model[0].weight, self.conv_model[0].bias, self.conv_model[2].weight,
+                                       self.conv_model[2].bias, age if args.use_age else None, int(ks[0]), int(ks[1]),
+                                       self.drop1.p, self.training)
+            y, w = loss_args if loss_args is not None else (None, None)
+            pred, bce = Fn.HeadMLP.apply(a0, self.head[0].weight, self.head[0].bias, self.head[3].weight, self.head[3].bias,
+                                         self.head[2].p, self.training, y, w)
+            self._last_bce = bce if y is not None else None
+            return pred, pca_feature
+        self._last_bce = None
         layers, i = list(self.conv_model), 0
         while i < len(layers):
             # Conv2d(1x1) + ReLU pairs: the ReLU runs in the GEMM epilogue (forward hooks on either module: unfused)
@@ -219,6 +234,41 @@ class MultilevelGNN(nn.Module):
             # wide first Linear (6913 / 84096 inputs): weight gradient through mlg_xty (cuBLAS picks a slow large-k kernel)
             x = Fn.tall_linear(x, mod, min_rows=1) if (isinstance(mod, nn.Linear) and mod.in_features >= 1024) else mod(x)
         return x, pca_feature
+
+    def forward_with_loss(self, input_batch, target, weight=None):
+        """(pred, pca_feature, bce): ``forward`` plus torch.nn.BCELoss(weight)(pred, target) (train.py:60,118) computed by
+        the head kernel that produces ``pred`` (one launch instead of the library's softmax / BCE chain)."""
+        pred, feat = self.forward(input_batch, _loss_args=(target, weight))
+        bce = self._last_bce
+        if bce is None:       # unfused head (hooks, other channel counts, CPU tensors never get here)
+            crit = torch.nn.BCELoss(weight=weight) if weight is not None else torch.nn.BCELoss()
+            bce = crit(pred.to(torch.float32), target.to(torch.float32))
+        self._last_bce = None
+        return pred, feat, bce
+
+    FUSED_HEAD = True
+
+    def _fused_head_ok(self, x):
+        """The fused head kernels cover the head every shipped config builds: two 1x1 convs 32 -> 32 -> 64 with ReLUs, a
+        stride = kernel floor-mode max-pool, Linear/ReLU/Dropout/Linear(->2)/Softmax; no forward hooks on those modules."""
+        cm, hd, pool = self.conv_model, self.head, self.pooling
+        if not (len(cm) == 4 and isinstance(cm[0], nn.Conv2d) and isinstance(cm[2], nn.Conv2d) and type(cm[1]) is nn.ReLU
+                and type(cm[3]) is nn.ReLU and len(hd) == 5 and isinstance(hd[0], nn.Linear) and type(hd[1]) is nn.ReLU
+                and isinstance(hd[2], nn.Dropout) and isinstance(hd[3], nn.Linear) and isinstance(hd[4], nn.Softmax)):
+            return False
+        mods = list(cm) + list(hd) + [pool, self.drop1]
+        if any(m._forward_hooks or m._forward_pre_hooks or m._backward_hooks for m in mods):
+            return False
+        ks = pool.kernel_size if isinstance(pool.kernel_size, tuple) else (pool.kernel_size,) * 2
+        if not (pool.stride in (ks, pool.kernel_size) and pool.padding in (0, (0, 0)) and pool.dilation in (1, (1, 1))
+                and not pool.ceil_mode and not pool.return_indices):
+            return False
+        if x.shape[0] > 64 or not Fn.HeadConvPool.supported(x, cm[0], cm[2]):
+            return False
+        f_in = cm[2].out_channels * (x.shape[2] // ks[0]) * (x.shape[3] // ks[1]) + (1 if self.args.use_age else 0)
+        return (hd[0].in_features == f_in and hd[3].out_features == 2 and hd[0].out_features % 32 == 0
+                and hd[0].out_features <= 512 and hd[0].bias is not None and hd[3].bias is not None
+                and hd[4].dim in (1, -1))
 
     @staticmethod
     def _conv(layer, x, relu=False):

@@ -289,8 +289,14 @@ class Trainer:
         self._copy_stream = None
 
     def loss(self, batch):
-        pred, feat = self.model(batch)
-        loss = self.crit(pred.to(torch.float32), batch.y.reshape(-1, 2).to(torch.float32))
+        fused = getattr(self.model, "forward_with_loss", None)
+        if fused is not None and batch.x.is_cuda:
+            # BCE(weight) comes out of the head kernel that produces pred (models/multilevel_gnn.py::forward_with_loss)
+            w = self.weight if self.args.weight_balance else None
+            pred, feat, loss = fused(batch, batch.y.reshape(-1, 2).to(torch.float32), w)
+        else:
+            pred, feat = self.model(batch)
+            loss = self.crit(pred.to(torch.float32), batch.y.reshape(-1, 2).to(torch.float32))
         return loss + self.model.get_feature_loss(feat)
 
     def _fwd_bwd(self, batch):
