@@ -10,7 +10,7 @@ from .gcn_lib.sparse import (GENConv, GenMessagePassing, MsgNorm, GraphConv, SAG
                              DynConv, DilatedKnnGraph, Dilated, knn_graph_matrix, knn_matrix,
                              pairwise_distance, MLP)
 from .gcn_lib.dense import DenseDilatedKnnGraph, DenseDilated, dense_knn_matrix  # noqa: F401
-from .models import (MultilevelGNN, DeeperGCN, DiffPool, DiffPoolLayer, SAGEConvolutions, DenseSAGEConv,  # noqa: F401
+from .models import (MultilevelGNN, VAE, DeeperGCN, DiffPool, DiffPoolLayer, SAGEConvolutions, DenseSAGEConv,  # noqa: F401
                      dense_diff_pool, MODELS, get_model)
 
 __version__ = "0.1.0"

@@ -37,6 +37,9 @@ DEFAULTS = dict(
     # --- DiffPool (models/diff_pooling.py:70-114, opt.py:415-420) ---
     after_pooling_layer=1, pooling_type="correlation", diff_pooling_location="pathway",
     diff_pooling_layer=2, diff_pooling_hidden_dim=32, diff_pooling_output_dim=64,
+    # --- VAE.predict_head / decoders (models/vae.py:48-87,233-300; opt.py:277-278,371-372,382-383) ---
+    reorder_type="pca", pathway_similarity="correlation", decoder_dim=4096, decoder_type="flatten",
+    channel_one=False, vae_generate_train_sample=False,
     # --- optimiser / loss (train.py:112-125) ---
     lr=1e-4, beta1=0.9, beta2=0.999, wd=0.0, weight_balance=False, weighted_loss=False,
     batch_weighted_loss=False, clip_grad=False, batch_size=4,

@@ -2,8 +2,9 @@
 from .multilevel_gnn import MultilevelGNN
 from .deepergcn import DeeperGCN
 from .diff_pooling import DiffPool, DiffPoolLayer, SAGEConvolutions, DenseSAGEConv, dense_diff_pool
+from .vae import VAE
 
-MODELS = {'deepergcn': DeeperGCN, 'multilevel_gnn': MultilevelGNN}
+MODELS = {'deepergcn': DeeperGCN, 'multilevel_gnn': MultilevelGNN, 'vae': VAE}
 
 
 def get_model(model_name):

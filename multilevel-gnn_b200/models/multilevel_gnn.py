@@ -109,90 +109,100 @@ class MultilevelGNN(nn.Module):
         self.init_weight()
 
     # ------------------------------------------------------------------------------------------
+    def pool_genes(self, input_batch, x=None, gene_pca_match=None, raw_indice=None, value_mask=True):
+        """Level 1 -> level 2 (models/multilevel_gnn.py:140-239): embed-scale, the GraphConv stack on the gene graph, the
+        value mask and the gene -> pathway projection pool.  Returns the pooled tensor [B, C, 438, P] (a permuted view of the
+        channel-last buffer the pool kernel writes).  ``value_mask=False``: the VAE encoder's variant (models/vae.py:128-190,
+        where the mask lines are commented out)."""
+        args = self.args
+        if x is not None:
+            mask_x = x
+        else:
+            mask_x = input_batch.x
+            gene_pca_match = input_batch.gene_pca_match
+            raw_indice = input_batch.raw_indice
+        x = mask_x.reshape(-1, 1)
+        if self.input_drop is not None:
+            x = self.input_drop(x)
+        n3 = self.node_num * 3
+        xs = x                                                       # [B*N, 1] scalar node values
+
+        edge_index, edge_attr = input_batch.edge_index, input_batch.edge_attr
+        if isinstance(edge_index, list):
+            raise NotImplementedError("list-valued edge_index (edge_type='merge') is not selected by any shipped config")
+        if args.device_num != 1:
+            n_edge = edge_index.shape[-1] // args.device_num
+            edge_index, edge_attr = edge_index[:, :n_edge].contiguous(), edge_attr[:n_edge]
+        edge_index = edge_index.to(x.device)
+        edge_attr = edge_attr.to(x.device) if args.weighted_edge else None
+        static_key = getattr(input_batch, "topology_key", None)
+        if edge_attr is not None:
+            # one Topology for all layers: the batch is B offset copies of the fold-constant edge list
+            # (multiloader.py:687-698) -> single-graph CSR streamed over the B stacked feature blocks
+            graph.topology(edge_index, x.shape[0], self_loops=True, edge_weight=edge_attr, static_key=static_key,
+                           period=n3)
+
+        feats = []
+        mask_col = mask_x.reshape(-1, 1)
+        n_layers = len(self.gnn_model)
+        if args.node_embedding:
+            if (self.input_emb_drop is None and not args.resgnn and args.gnn_name.lower() in ("sage", "rsage")):
+                # K13 folded into K7: x0 = x * node_embedding stays factored for the first layer
+                x = Fn.RankOne(xs, self.node_embedding)
+            else:
+                x = Fn.EmbedScale.apply(xs, self.node_embedding)     # [B*N, emb_dim]
+                if self.input_emb_drop is not None:
+                    x = self.input_emb_drop(x)
+        # Activation-backward fusion along a plain layer chain (x_{i+1} = y_i, nothing else reads y_i): the consumer
+        # of y_i multiplies its input gradient by LeakyReLU'(y_i) inside its own backward kernel (it has y_i in
+        # hand), and layer i takes that gradient as dL/dz -- one 3-tensor elementwise pass per layer saved.
+        plain = self.FUSE_ACT_BACKWARD and xs.is_cuda and not args.dense_gnn and not args.resgnn \
+            and not args.repeat_mask and torch.is_grad_enabled()
+        slopes = [getattr(l, "grad_fusion_slope", lambda: None)() if plain else None for l in self.gnn_model]
+        pool_masks = plain and slopes[-1] is not None and (not (args.value_att_mask and value_mask) or args.merge_mode == 'mult')
+        for i, layer in enumerate(self.gnn_model):
+            if plain and slopes[i] is not None:
+                masks = lambda l: getattr(l, "masks_input_grad", lambda: not getattr(l, "relative", True))()
+                consumer_masks = pool_masks if i + 1 == n_layers else \
+                    (slopes[i + 1] is not None and masks(self.gnn_model[i + 1]))
+                producer_masked = i > 0 and slopes[i - 1] is not None and masks(layer)
+                layer._mlg_fuse = (slopes[i - 1] if producer_masked else None, bool(consumer_masks))
+            y = layer(x, edge_index, edge_attr)
+            if args.dense_gnn:
+                x = y
+                feats.append(x)
+            elif args.resgnn:
+                x = y + x
+            else:
+                x = y
+            if i + 1 != n_layers and args.repeat_mask and (i + 1) % args.repeat_cyclic == 0:
+                if args.repeat_norm:
+                    x = x / (x ** 2).sum(1).sqrt()[:, None]
+                x = x * mask_col
+        if args.dense_gnn:
+            x = torch.cat(feats, dim=-1)
+
+        vm = None
+        if args.value_att_mask and value_mask:
+            if args.merge_mode == 'mult':
+                vm = mask_x.reshape(-1).detach().float().contiguous()   # folded into the pool kernel
+            else:
+                x = args.add_coef1 * x + args.add_coef2 * mask_col
+
+        layout = graph.pool_layout(gene_pca_match, raw_indice, n3, 146 * 3,
+                                   wrap_negative=not args.pca_match_mask, static_key=static_key)
+        w = self.learnable_pca_params * self.info_mask                   # [G, P]
+        x = Fn.PathwayPool.apply(x, w, vm, layout, slopes[-1] if pool_masks else None)   # [B, C, 438, P]
+        return x
+
     def forward(self, input_batch, x=None, gene_pca_match=None, raw_indice=None, age=None, require_grad=True,
                 _loss_args=None):
         args = self.args
         loss_args = _loss_args
         with torch.enable_grad() if require_grad else torch.no_grad():
-            if x is not None:
-                mask_x = x
-            else:
-                mask_x = input_batch.x
-                gene_pca_match = input_batch.gene_pca_match
-                raw_indice = input_batch.raw_indice
+            if x is None:
                 age = input_batch.age
-            x = mask_x.reshape(-1, 1)
-            if self.input_drop is not None:
-                x = self.input_drop(x)
-            n3 = self.node_num * 3
-            xs = x                                                       # [B*N, 1] scalar node values
-
-            edge_index, edge_attr = input_batch.edge_index, input_batch.edge_attr
-            if isinstance(edge_index, list):
-                raise NotImplementedError("list-valued edge_index (edge_type='merge') is not selected by any shipped config")
-            if args.device_num != 1:
-                n_edge = edge_index.shape[-1] // args.device_num
-                edge_index, edge_attr = edge_index[:, :n_edge].contiguous(), edge_attr[:n_edge]
-            edge_index = edge_index.to(x.device)
-            edge_attr = edge_attr.to(x.device) if args.weighted_edge else None
-            static_key = getattr(input_batch, "topology_key", None)
-            if edge_attr is not None:
-                # one Topology for all layers: the batch is B offset copies of the fold-constant edge list
-                # (multiloader.py:687-698) -> single-graph CSR streamed over the B stacked feature blocks
-                graph.topology(edge_index, x.shape[0], self_loops=True, edge_weight=edge_attr, static_key=static_key,
-                               period=n3)
-
-            feats = []
-            mask_col = mask_x.reshape(-1, 1)
-            n_layers = len(self.gnn_model)
-            if args.node_embedding:
-                if (self.input_emb_drop is None and not args.resgnn and args.gnn_name.lower() in ("sage", "rsage")):
-                    # K13 folded into K7: x0 = x * node_embedding stays factored for the first layer
-                    x = Fn.RankOne(xs, self.node_embedding)
-                else:
-                    x = Fn.EmbedScale.apply(xs, self.node_embedding)     # [B*N, emb_dim]
-                    if self.input_emb_drop is not None:
-                        x = self.input_emb_drop(x)
-            # Activation-backward fusion along a plain layer chain (x_{i+1} = y_i, nothing else reads y_i): the consumer
-            # of y_i multiplies its input gradient by LeakyReLU'(y_i) inside its own backward kernel (it has y_i in
-            # hand), and layer i takes that gradient as dL/dz -- one 3-tensor elementwise pass per layer saved.
-            plain = self.FUSE_ACT_BACKWARD and xs.is_cuda and not args.dense_gnn and not args.resgnn \
-                and not args.repeat_mask and torch.is_grad_enabled()
-            slopes = [getattr(l, "grad_fusion_slope", lambda: None)() if plain else None for l in self.gnn_model]
-            pool_masks = plain and slopes[-1] is not None and (not args.value_att_mask or args.merge_mode == 'mult')
-            for i, layer in enumerate(self.gnn_model):
-                if plain and slopes[i] is not None:
-                    masks = lambda l: getattr(l, "masks_input_grad", lambda: not getattr(l, "relative", True))()
-                    consumer_masks = pool_masks if i + 1 == n_layers else \
-                        (slopes[i + 1] is not None and masks(self.gnn_model[i + 1]))
-                    producer_masked = i > 0 and slopes[i - 1] is not None and masks(layer)
-                    layer._mlg_fuse = (slopes[i - 1] if producer_masked else None, bool(consumer_masks))
-                y = layer(x, edge_index, edge_attr)
-                if args.dense_gnn:
-                    x = y
-                    feats.append(x)
-                elif args.resgnn:
-                    x = y + x
-                else:
-                    x = y
-                if i + 1 != n_layers and args.repeat_mask and (i + 1) % args.repeat_cyclic == 0:
-                    if args.repeat_norm:
-                        x = x / (x ** 2).sum(1).sqrt()[:, None]
-                    x = x * mask_col
-            if args.dense_gnn:
-                x = torch.cat(feats, dim=-1)
-
-            vm = None
-            if args.value_att_mask:
-                if args.merge_mode == 'mult':
-                    vm = mask_x.reshape(-1).detach().float().contiguous()   # folded into the pool kernel
-                else:
-                    x = args.add_coef1 * x + args.add_coef2 * mask_col
-
-            layout = graph.pool_layout(gene_pca_match, raw_indice, n3, 146 * 3,
-                                       wrap_negative=not args.pca_match_mask, static_key=static_key)
-            w = self.learnable_pca_params * self.info_mask                   # [G, P]
-            x = Fn.PathwayPool.apply(x, w, vm, layout, slopes[-1] if pool_masks else None)   # [B, C, 438, P]
+            x = self.pool_genes(input_batch, x, gene_pca_match, raw_indice, value_mask=True)     # [B, C, 438, P]
             x = x.reshape(x.shape[0], x.shape[1], 146, self.pca_dim * 3)
             if args.reorder_pathway and self.reorder_idxs is not None:
                 x = x[:, :, self.reorder_idxs.to(x.device), :]

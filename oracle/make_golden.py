@@ -260,10 +260,57 @@ def make_deepergcn(ns):
     torch.save(out, os.path.join(OUT, "deepergcn.pt"))
 
 
+def make_vae(ns):
+    """VAE.predict_head (the reference's only DiffPool call site, models/vae.py:233-265) for both diff_pooling locations and
+    the plain pooled head, plus the per-pathway decoders (vae.py:216-222), from the reference's own VAE class."""
+    out = {}
+    cases = {"diffpool_pathway": dict(reorder_type="diff_pooling", diff_pooling_location="pathway"),
+             "diffpool_head": dict(reorder_type="diff_pooling", diff_pooling_location="head"),
+             "plain_pool": dict(reorder_type="pca")}
+    for i, (name, extra) in enumerate(cases.items()):
+        g = gen(700 + i)
+        torch.manual_seed(700 + i)
+        over = dict(decoder_type="foreach_diffhidden", decoder_dim=64, head_dim=32 if i == 0 else 8, **extra)
+        args = ref_import.default_args("lgg.yaml", **over)
+        pidx = torch.repeat_interleave(torch.arange(16), torch.randint(1, 40, (16,), generator=g))   # 16 decoder blocks
+        model = ns.vae.VAE(args, pathway_indexs=pidx)
+        model.reconstruct_head(args)
+        a = torch.rand(146, 146, generator=g)
+        sim = (a + a.t()) * 0.5
+        model.set_pathway_similarity_matrix(sim.numpy())
+        model.eval()
+        bsz = 2
+        x = torch.randn(bsz, 32, 146, 9, generator=g).requires_grad_()
+        age = torch.rand(bsz, generator=g)
+        pred, feat, l, e = model.predict_head(x, age)
+        R = torch.randn(pred.shape, generator=g)
+        keep = ("diff_pooling.", "conv_model.", "head.", "decoder.")
+        params = {k: p for k, p in model.named_parameters() if k.startswith(keep[:3])}
+        gs = grads_of((pred * R).sum() + 3.0 * l + 0.5 * e, [x] + list(params.values()))
+        h = torch.randn(bsz, 16, 96, generator=g).requires_grad_()
+        dec = model.foreach_decoder(h)
+        Rd = torch.randn(dec.shape, generator=g)
+        dparams = {k: p for k, p in model.named_parameters() if k.startswith("decoder.")}
+        gd = grads_of((dec * Rd).sum(), [h] + list(dparams.values()))
+        out[name] = dict(overrides=over, pathway_indexs=pidx, sim=sim, x=x.detach(), age=age, R=R, h=h.detach(), Rd=Rd,
+                         state_dict={k: v.detach().clone() for k, v in model.state_dict().items() if k.startswith(keep)},
+                         pred=pred.detach(), link=torch.as_tensor(l).detach(), ent=torch.as_tensor(e).detach(), g_x=gs[0],
+                         g_params={k: g_ for k, g_ in zip(params.keys(), gs[1:])},
+                         dec=dec.detach(), g_h=gd[0], g_dec={k: g_ for k, g_ in zip(dparams.keys(), gd[1:])})
+        if i > 0:      # the decoder blocks are exercised once
+            for k in ("h", "Rd", "dec", "g_h", "g_dec"):
+                out[name].pop(k)
+            out[name]["state_dict"] = {k: v for k, v in out[name]["state_dict"].items() if not k.startswith("decoder.")}
+    torch.save(out, os.path.join(OUT, "vae.pt"))
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ns = ref_import.load()
-    for fn in (make_genconv, make_sage, make_knn, make_multilevel, make_diffpool, make_deepergcn):
+    only = set(sys.argv[1:])
+    for fn in (make_genconv, make_sage, make_knn, make_multilevel, make_diffpool, make_deepergcn, make_vae):
+        if only and fn.__name__ not in only:
+            continue
         fn(ns)
         print("wrote", fn.__name__)
     for f in sorted(os.listdir(OUT)):

@@ -53,6 +53,7 @@ def load():
     ns.multilevel_gnn = importlib.import_module("models.multilevel_gnn")
     ns.deepergcn = importlib.import_module("models.deepergcn")
     ns.diff_pooling = importlib.import_module("models.diff_pooling")
+    ns.vae = importlib.import_module("models.vae")
     return ns
 
 

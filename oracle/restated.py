@@ -400,6 +400,51 @@ def diffpool_forward(sd, x, adj, num_layers=2):
     return x, l_tot, e_tot
 
 
+def predict_head(sd, x, age, args, adj, pca_dim=None):
+    """VAE.predict_head, models/vae.py:233-265 (eval mode: dropout = identity).  x [B, C, 146, d];
+    ``adj`` = get_pathway_adj() (similarity + I, vae.py:305-306).  Returns (pred, pca_feature, l, e)."""
+    l = e = 0
+    pca_feature = x
+    diff = args.reorder_type == "diff_pooling"
+
+    def sub(prefix):
+        return {k[len(prefix):]: v for k, v in sd.items() if k.startswith(prefix)}
+
+    if diff and args.diff_pooling_location == "pathway":
+        b = x.shape[0]
+        x = x.permute(0, 3, 2, 1).reshape(-1, args.pathway_num, args.final_channels)
+        x, l, e = diffpool_forward(sub("diff_pooling."), x, adj, num_layers=args.diff_pooling_layer)
+        x = x.reshape(b, -1)
+    else:
+        for ci in sorted({int(k.split(".")[1]) for k in sd if k.startswith("conv_model.")}):
+            wt = sd["conv_model.%d.weight" % ci]
+            x = F.relu(F.conv2d(x, wt, sd["conv_model.%d.bias" % ci], padding=wt.shape[-1] // 2))
+        if diff and args.diff_pooling_location == "head":
+            b = x.shape[0]
+            x = x.permute(0, 3, 2, 1).reshape(-1, args.pathway_num, args.conv_channel_list[-1])
+            x, l, e = diffpool_forward(sub("diff_pooling."), x, adj, num_layers=args.diff_pooling_layer)
+            x = x.reshape(b, -1)
+        else:
+            if args.reorder_type != "no_pooling":
+                x = F.max_pool2d(x, (args.pathway_pool_dim, args.pca_pool_dim))
+            x = torch.flatten(x, start_dim=1)
+    if args.use_age:
+        x = torch.cat([x, age[:, None]], dim=-1)
+    x = F.relu(F.linear(x, sd["head.0.weight"], sd["head.0.bias"]))
+    pred = F.softmax(F.linear(x, sd["head.3.weight"], sd["head.3.bias"]), dim=1)
+    return pred, pca_feature, l, e
+
+
+def foreach_decoder(sd, h):
+    """VAE.foreach_decoder, models/vae.py:216-222 with the per-pathway Linear-ReLU-Linear blocks of :54-74."""
+    n = len({k.split(".")[1] for k in sd if k.startswith("decoder.")})
+    out = []
+    for i in range(n):
+        z = F.relu(F.linear(h[:, i, :], sd["decoder.%d.0.weight" % i], sd["decoder.%d.0.bias" % i]))
+        out.append(F.linear(z, sd["decoder.%d.2.weight" % i], sd["decoder.%d.2.bias" % i]))
+    return torch.cat(out, dim=-1)
+
+
 # ----------------------------------------------------------------------------
 # DeeperGCN
 # ----------------------------------------------------------------------------

@@ -188,3 +188,37 @@ def test_configs_match_reference_defaults():
                 continue
             assert hasattr(ref, k), k
             assert getattr(ref, k) == v, (cfg, k, getattr(ref, k), v)
+
+
+# ------------------------------------------------------------------------------------------------
+# VAE.predict_head (DiffPool's only call site) and the per-pathway decoders vs the reference's own VAE class
+# ------------------------------------------------------------------------------------------------
+VAEG = load_golden("vae")
+
+
+@pytest.mark.parametrize("name", sorted(VAEG))
+def test_predict_head_restatement(name):
+    from multilevel_gnn_b200 import configs
+    c = VAEG[name]
+    args = configs.make_args("lgg", **c["overrides"])
+    sd = _leafify(c["state_dict"])
+    x = c["x"].clone().requires_grad_()
+    adj = c["sim"] + torch.eye(146)
+    pred, feat, l, e = R.predict_head(sd, x, c["age"], args, adj)
+    assert_close(pred, c["pred"], what=name + ".pred")
+    assert_close(torch.as_tensor(l), c["link"], what=name + ".link")
+    assert_close(torch.as_tensor(e), c["ent"], what=name + ".ent")
+    names = [k for k, g in c["g_params"].items() if g is not None]
+    gs = torch.autograd.grad((pred * c["R"]).sum() + 3.0 * l + 0.5 * e, [x] + [sd[k] for k in names])
+    assert_close(gs[0], c["g_x"], rtol=2e-4, what=name + ".g_x")
+    for k, g in zip(names, gs[1:]):
+        assert_close(g, c["g_params"][k], rtol=2e-4, what=name + ".g_" + k)
+    if "dec" in c:
+        h = c["h"].clone().requires_grad_()
+        dec = R.foreach_decoder(sd, h)
+        assert_close(dec, c["dec"], what=name + ".dec")
+        dn = list(c["g_dec"])
+        gd = torch.autograd.grad((dec * c["Rd"]).sum(), [h] + [sd[k] for k in dn])
+        assert_close(gd[0], c["g_h"], rtol=2e-4, what=name + ".g_h")
+        for k, g in zip(dn, gd[1:]):
+            assert_close(g, c["g_dec"][k], rtol=2e-4, what=name + ".g_" + k)
