@@ -313,6 +313,31 @@ int mlg_head_mlp_bwd(const float* g_pred, const float* g_loss, const float* pred
                      int64_t R, int64_t D, int64_t K, float* g_a0, int64_t ld_g, float* g_W0, float* g_b0, float* g_W3,
                      float* g_b3, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * DiffPool at the reference's size, fused (models/diff_pooling.py:59-65,116-133 with PyG DenseSAGEConv(normalize=True)
+ * and dense_diff_pool; called from VAE.predict_head, models/vae.py:238-243): one persistent CTA per sample keeps the
+ * whole sample in shared memory.  1 or 2 pooling layers, after_pooling_layer = 1, shared adjacency adj [n0, n0].
+ *   dims: HOST array, 4 per layer: (n nodes, c in-channels, k clusters, h embedding channels); layer 1 = (k0, h0, k1, h1)
+ *   weights: HOST array of 9 DEVICE pointers per layer:
+ *            gnn_pool (lin_rel.weight [k,c], lin_root.weight [k,c], lin_root.bias [k]),
+ *            gnn_embed (lin_rel.weight [h,c], lin_root.weight [h,c], lin_root.bias [h]),
+ *            after_pool (lin_rel.weight [h,h], lin_root.weight [h,h], lin_root.bias [h])
+ *   out [b, k_last, h_last]; stats [b, 2*layers] = per sample and layer (||adj_l - S S^T||_F^2, sum_rows sum_k -S log(S+1e-15)):
+ *   link = sum_l sqrt(sum_b F_l) / numel(adj_l), entropy = sum_l sum_b E_l / (b n_l) are formed by the caller.
+ * Backward: g_out [b, k_last, h_last]; coef DEVICE [2*layers] = per layer (g_link / (sqrt(sum_b F_l) numel(adj_l)),
+ *   g_entropy / (b n_l)); g_x [b, n0, c0]; g_weights: ONE device buffer of mlg_diffpool_grad_floats floats, the 9 gradients
+ *   of each layer back to back in the order of `weights`; workspace >= mlg_diffpool_ctas(b) * grad_floats * 4 bytes.
+ * mlg_diffpool_supported: the per-sample working set fits the 227 KB of shared memory of one SM. */
+int64_t mlg_diffpool_smem_bytes(int64_t layers, const int64_t* dims);
+int mlg_diffpool_supported(int64_t layers, const int64_t* dims);
+int64_t mlg_diffpool_grad_floats(int64_t layers, const int64_t* dims);
+int64_t mlg_diffpool_ctas(int64_t b);
+int mlg_diffpool_fwd(const float* x, const float* adj, const float* const* weights, int64_t layers, const int64_t* dims,
+                     int64_t b, float* out, float* stats, void* stream);
+int mlg_diffpool_bwd(const float* g_out, const float* coef, const float* x, const float* adj, const float* const* weights,
+                     int64_t layers, const int64_t* dims, int64_t b, float* g_x, float* g_weights, void* workspace,
+                     int64_t workspace_bytes, void* stream);
+
 /* z[r,c] = LeakyReLU_slope(z[r,c] + bias[c]) in place (bias NULL ok; slope 0 = ReLU): the bias + activation
  * of SAGEConv.update's MLP (torch_vertex.py:288-291) after the update GEMM. */
 int mlg_bias_act(float* z, const float* bias, int64_t rows, int64_t C, float slope, void* stream);

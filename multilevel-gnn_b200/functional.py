@@ -1150,3 +1150,86 @@ class HeadMLP(torch.autograd.Function):
                                            _cabi.fptr(gb0), _cabi.fptr(gW3), _cabi.fptr(gb3), _cabi.stream_ptr()),
                         "mlg_head_mlp_bwd")
         return g_a0, gW0, gb0, gW3, gb3, None, None, None, None
+
+
+class DiffPoolFused(torch.autograd.Function):
+    """DiffPool.forward at the reference's size (models/diff_pooling.py:116-133; 146 -> 37 -> 10 nodes) as one kernel per
+    direction (mlg_diffpool_fwd / _bwd, csrc/diffpool_fused.cu).
+
+    forward(x [b,n,c], adj [n,n], dims, *weights) -> (out [b,k,h], link, entropy); ``weights``: 9 tensors per layer in
+    the order of include/mlg_b200.h; ``dims``: tuple of (n, c, k, h) per layer."""
+
+    @staticmethod
+    def _tables(weights, dims):
+        import ctypes
+        ws = [_f32c(w.detach()) for w in weights]
+        warr = (ctypes.c_void_p * len(ws))(*[w.data_ptr() for w in ws])
+        darr = (ctypes.c_int64 * (4 * len(dims)))(*[int(v) for d in dims for v in d])
+        return ws, warr, darr
+
+    @staticmethod
+    def supported(dims):
+        import ctypes
+        darr = (ctypes.c_int64 * (4 * len(dims)))(*[int(v) for d in dims for v in d])
+        return 1 <= len(dims) <= 2 and bool(_cabi.lib().mlg_diffpool_supported(len(dims), darr))
+
+    @staticmethod
+    def forward(ctx, x, adj, dims, *weights):
+        L = _cabi.lib()
+        _cabi.require_cuda(x, adj, *weights)
+        xd, ad = _f32c(x.detach()), _f32c(adj.detach())
+        b = xd.shape[0]
+        ws, warr, darr = DiffPoolFused._tables(weights, dims)
+        nl = len(dims)
+        out = torch.empty(b, dims[-1][2], dims[-1][3], dtype=torch.float32, device=xd.device)
+        stats = torch.empty(b, nl, 2, dtype=torch.float32, device=xd.device)
+        flops = 2.0 * b * sum(n * n * c + 2 * n * c * (k + h) + n * k * h + 2 * n * n * k + n * k * k for n, c, k, h in dims)
+        with torch.cuda.device(xd.device), _cabi.span("diffpool_fwd", flops):
+            _cabi.check(L.mlg_diffpool_fwd(_cabi.fptr(xd), _cabi.fptr(ad), warr, nl, darr, b, _cabi.fptr(out),
+                                           _cabi.fptr(stats), _cabi.stream_ptr()), "mlg_diffpool_fwd")
+        # link_l = ||adj_l - S S^T||_F / numel(adj_l) over the whole batch (adj_0 is the shared [n, n] matrix, deeper
+        # adjacencies are batched [b, k, k]); entropy_l = mean over (sample, node)
+        tot = stats.sum(0)                                              # [layers, 2]
+        numel = torch.tensor([float(d[0] * d[0] * (1 if i == 0 else b)) for i, d in enumerate(dims)], device=xd.device)
+        rows = torch.tensor([float(b * d[0]) for d in dims], device=xd.device)
+        fro = tot[:, 0].sqrt()
+        link = (fro / numel).sum()
+        ent = (tot[:, 1] / rows).sum()
+        ctx.save_for_backward(xd, ad, fro, numel, rows, *ws)
+        ctx.dims = dims
+        ctx.n_weights = len(weights)
+        ctx.set_materialize_grads(False)
+        return out, link, ent
+
+    @staticmethod
+    def backward(ctx, g_out, g_link, g_ent):
+        L = _cabi.lib()
+        xd, ad, fro, numel, rows = ctx.saved_tensors[:5]
+        ws = list(ctx.saved_tensors[5:])
+        dims = ctx.dims
+        nl = len(dims)
+        b = xd.shape[0]
+        dev = xd.device
+        import ctypes
+        warr = (ctypes.c_void_p * len(ws))(*[w.data_ptr() for w in ws])
+        darr = (ctypes.c_int64 * (4 * nl))(*[int(v) for d in dims for v in d])
+        g_out = torch.zeros(b, dims[-1][2], dims[-1][3], dtype=torch.float32, device=dev) if g_out is None else _f32c(g_out)
+        zero = torch.zeros((), dtype=torch.float32, device=dev)
+        gl = zero if g_link is None else g_link.float()
+        ge = zero if g_ent is None else g_ent.float()
+        coef = torch.stack([gl / (fro * numel), (ge / rows)], dim=1).contiguous()     # [layers, 2]
+        nfl = int(L.mlg_diffpool_grad_floats(nl, darr))
+        ctas = int(L.mlg_diffpool_ctas(b))
+        gx = torch.empty_like(xd)
+        gw = torch.empty(nfl, dtype=torch.float32, device=dev)
+        wsp = torch.empty(ctas * nfl, dtype=torch.float32, device=dev)
+        flops = 6.0 * b * sum(n * n * c + 2 * n * c * (k + h) + n * k * h + 2 * n * n * k + n * k * k for n, c, k, h in dims)
+        with torch.cuda.device(dev), _cabi.span("diffpool_bwd", flops):
+            _cabi.check(L.mlg_diffpool_bwd(_cabi.fptr(g_out), _cabi.fptr(coef), _cabi.fptr(xd), _cabi.fptr(ad), warr, nl, darr,
+                                           b, _cabi.fptr(gx), _cabi.fptr(gw), _cabi.fptr(wsp), wsp.numel() * 4,
+                                           _cabi.stream_ptr()), "mlg_diffpool_bwd")
+        grads, off = [], 0
+        for w in ws:
+            grads.append(gw[off:off + w.numel()].view_as(w))
+            off += w.numel()
+        return (gx, None, None) + tuple(grads)

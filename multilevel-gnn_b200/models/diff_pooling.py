@@ -130,7 +130,43 @@ class DiffPool(nn.Module):
         self.diffpool_layers = nn.ModuleList(pools)
         self.after_pool_layers = nn.ModuleList(afters)
 
+    FUSED = True      # reference-sized problems through the one-kernel path (csrc/diffpool_fused.cu)
+
+    def _fused_plan(self, x, adj, mask):
+        """(dims, weights) when the fused kernel applies: CUDA fp32, no mask, ONE shared 2-D adjacency that needs no
+        gradient, single-conv SAGEConvolutions everywhere, at most two pooling layers, and the per-sample working set
+        fits one SM's shared memory; else None (module path: library GEMMs / the tensor-core path for GEMM-sized inputs)."""
+        from .. import functional as Fn
+        if not (self.FUSED and x.is_cuda and x.dim() == 3 and adj.dim() == 2 and mask is None and not adj.requires_grad
+                and x.dtype == torch.float32 and 1 <= self.num_pooling_layers <= 2):
+            return None
+        dims, weights = [], []
+        n, c = x.shape[1], x.shape[2]
+        for lay, aft in zip(self.diffpool_layers, self.after_pool_layers):
+            convs = (lay.gnn_pool, lay.gnn_embed, aft)
+            if any(sc.num_layers != 1 or not sc.layers[0].normalize for sc in convs):
+                return None
+            k, h = lay.gnn_pool.layers[0].out_channels, lay.gnn_embed.layers[0].out_channels
+            if (lay.gnn_pool.layers[0].in_channels != c or lay.gnn_embed.layers[0].in_channels != c
+                    or aft.layers[0].in_channels != h or aft.layers[0].out_channels != h):
+                return None
+            dims.append((n, c, k, h))
+            for sc in convs:
+                conv = sc.layers[0]
+                if conv.lin_root.bias is None or conv._forward_hooks:
+                    return None
+                weights += [conv.lin_rel.weight, conv.lin_root.weight, conv.lin_root.bias]
+            n, c = k, h
+        dims = tuple(dims)
+        return (dims, weights) if Fn.DiffPoolFused.supported(dims) else None
+
     def forward(self, x, adj, mask=None):
+        from .. import _cabi
+        _cabi.require_cuda(x)            # no CPU path: the product computes on the B200 kernels only
+        plan = self._fused_plan(x, adj, mask)
+        if plan is not None:
+            from .. import functional as Fn
+            return Fn.DiffPoolFused.apply(x, adj, plan[0], *plan[1])
         l_total, e_total = 0, 0
         for i in range(self.num_pooling_layers):
             x, adj, l, e = self.diffpool_layers[i](x, adj, mask if i == 0 else None)
