@@ -36,7 +36,10 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", default="gbm", choices=["gbm", "kirc", "lgg"])
     ap.add_argument("--batch", type=int, default=None, help="graphs per GPU per step (default: the config's batch_size)")
-    ap.add_argument("--cpu-batch", type=int, default=8, help="graphs per CPU-baseline step (bounded sample)")
+    ap.add_argument("--cpu-batch", type=int, default=None,
+                    help="graphs per CPU step of the reference arm / cpu_baseline (default: the GPU arm's batch)")
+    ap.add_argument("--windows", type=int, default=3, help="timed windows of --steps steps each; the median is reported")
+    ap.add_argument("--no-diffpool", action="store_true", help="skip the DiffPool legs (reference size + tensor-core contractions)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-genconv", action="store_true", help="skip the GENConv aggregation roofline microbench")
     ap.add_argument("--no-graph", action="store_true", help="do not capture the step as a CUDA graph")
@@ -153,8 +156,16 @@ class ClockSampler:
         return out
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum per launch from `ncu --set full` captures (profiles/), or None
-NCU_TRAFFIC = {"gather_sum_rep": 302514176, "gather_sum_rep_c32": None, "gen_fwd": 1084807680}   # profiles/r01_ncu_full_summaries.md
+def ncu_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed `ncu --set full` table
+    (profiles/ncu_traffic.json: kernel -> {"dram_bytes": ..., "source": "profiles/<summary>"}), or None."""
+    path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if not os.path.exists(path):
+        return None
+    with open(path) as f:
+        return (json.load(f).get(kernel) or {}).get("dram_bytes")
+
+
 
 
 def max_over_ranks(ms, world, dev):
@@ -173,9 +184,11 @@ def barrier(world):
 
 # ----------------------------------------------------------------------------------------------------
 def cpu_reference_run(cfg, cpu_batch, steps, warmup):
-    """Times the CPU port of the reference train step (oracle/) on the host cores."""
+    """Times one reference training step (train.py:38-68) on the host cores: the reference's OWN modules (oracle/_ref staged
+    by oracle/make_ref.py, or /root/reference in the build container; kind "reference") behind oracle/pyg_stub.py, else the
+    oracle's port of the same step (kind "port").  Returns (graphs/s, ms/step, cores, kind)."""
     import multilevel_gnn_b200 as m
-    from oracle.train_port import CpuTrainer
+    from oracle import ref_train
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     args = m.configs.make_args(cfg)
@@ -184,14 +197,20 @@ def cpu_reference_run(cfg, cpu_batch, steps, warmup):
     m.synth.multilevel_params(model)
     batch = m.synth.multilevel_batch(batch_size=cpu_batch, seed=0)
     weight = torch.tensor([[0.8, 1.3]]).repeat(cpu_batch, 1)
-    tr = CpuTrainer(model.state_dict(), args, weight, model.pathway_indexs)
+    if ref_train.available():
+        tr = ref_train.RefTrainer(cfg, model.state_dict(), weight, model.pathway_indexs, model.info_mask.data)
+        kind = "reference"
+    else:
+        from oracle.train_port import CpuTrainer
+        tr = CpuTrainer(model.state_dict(), args, weight, model.pathway_indexs)
+        kind = "port"
     for _ in range(warmup):
         tr.step(batch)
     t0 = time.perf_counter()
     for _ in range(steps):
         tr.step(batch)
     dt = time.perf_counter() - t0
-    return cpu_batch * steps / dt, dt / steps * 1e3, cores
+    return cpu_batch * steps / dt, dt / steps * 1e3, cores, kind
 
 
 def genconv_microbench(dev, hbm_peak):
@@ -227,9 +246,9 @@ def genconv_microbench(dev, hbm_peak):
     gbs = nbytes / ms / 1e6
     return {"kernel": "gen_fwd_ring_kernel<1> (GENConv softmax aggregation + MsgNorm + residual, N=100k, k=16, H=128)", "bound": "hbm",
             "achieved": round(gbs, 1), "peak": hbm_peak, "unit": "GB/s", "frac": round(gbs / hbm_peak, 4),
-            "ms": round(ms, 4), "bytes": nbytes, "traffic": NCU_TRAFFIC.get("gen_fwd"),
+            "ms": round(ms, 4), "bytes": nbytes, "traffic": ncu_traffic("gen_fwd_ring_kernel<1>"),
             "note": "inputs 0.93 GB > L2; 20 back-to-back launches; training-mode forward (also writes m and the "
-                    "log-sum-exp for backward); traffic = ncu dram bytes per launch (profiles/r01_ncu_full_summaries.md)"}
+                    "log-sum-exp for backward); traffic = ncu dram bytes per launch (profiles/ncu_traffic.json)"}
 
 
 def dominant_kernel_alone(batch, hbm_peak, reps=20):
@@ -274,23 +293,96 @@ def dominant_kernel_alone(batch, hbm_peak, reps=20):
                     % (reps, n, 2 * C, n, C, nnz, topo.replicas)}
 
 
+def diffpool_legs(dev):
+    """DiffPool: (1) forward + backward at the reference's size through DiffPool.forward
+    (x [576, 146, 32], shared adj [146, 146], 146 -> 37 -> 10: the fused one-CTA-per-sample kernels), latency; (2) the four
+    contractions of the synthetic-large shape (N = 10 k, K = 2.5 k, C = 1024) on the tcgen05 bf16 GEMM against the measured
+    dense bf16 peak; (3) one DiffPool.forward at that shape end to end (fp32 in / out, casts included)."""
+    import ctypes
+    import multilevel_gnn_b200 as m
+    from multilevel_gnn_b200 import _cabi
+    L = _cabi.lib()
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    bf16_peak = float(json.load(open(path))["bf16_tflops"]) if os.path.exists(path) else 1590.0
+
+    def timed(fn, reps, warm=2):
+        for _ in range(warm):
+            fn()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        a0.record()
+        for _ in range(reps):
+            fn()
+        a1.record()
+        torch.cuda.synchronize()
+        return a0.elapsed_time(a1) / reps
+
+    out = {}
+    args = m.configs.make_args("lgg")
+    torch.manual_seed(0)
+    dp = m.DiffPool(32, 2, 146, 2, 32, 64, args).to(dev)
+    x, adj = m.synth.diffpool_inputs(576, 146, 32)
+    xg, ag = x.to(dev).requires_grad_(), adj.to(dev)
+    params = list(dp.parameters())
+
+    def fwd_bwd():
+        o, l, e = dp(xg, ag)
+        torch.autograd.grad((o.sum() + l + e), [xg] + params)
+
+    with torch.no_grad():
+        ms_f = timed(lambda: dp(xg, ag), 10)
+    ms_fb = timed(fwd_bwd, 10)
+    dims = [(146, 32, 37, 32), (37, 32, 10, 64)]
+    flop_f = 2.0 * 576 * sum(n * n * c + 2 * n * c * (k + h) + n * k * h + 2 * n * n * k + n * k * k for n, c, k, h in dims)
+    out["reference_size"] = {"shape": "b=576, 146 -> 37 -> 10 nodes, 32 -> 32 -> 64 channels", "fused_kernel": bool(dp._fused_plan(xg, ag, None)),
+                             "fwd_ms": round(ms_f, 4), "fwd_bwd_ms": round(ms_fb, 4), "fwd_GFLOPs_fp32": round(flop_f / ms_f / 1e6, 1),
+                             "bound": "fp32 FMA out of shared memory (146-wide problems: no tensor-core tile fits)"}
+    legs = {}
+    for (M, N, K, what) in [(2500, 10000, 10000, "S^T.A"), (2500, 2500, 10000, "(S^T.A).S"), (10000, 1024, 10000, "A.X"),
+                            (2500, 1024, 10000, "S^T.X")]:
+        A = torch.randn(M, K, device=dev).bfloat16()
+        Bm = torch.randn(N, K, device=dev).bfloat16()
+        C = torch.empty(M, N, device=dev)
+        run = lambda: _cabi.check(L.mlg_gemm_bf16(ctypes.c_void_p(A.data_ptr()), K, 0, ctypes.c_void_p(Bm.data_ptr()), K, 0,
+                                                  _cabi.fptr(C), N, 0, M, N, K, 1, 1.0, _cabi.stream_ptr()), "mlg_gemm_bf16")
+        ms = timed(run, 10)
+        tf = 2.0 * M * N * K / ms / 1e9
+        legs[what] = {"M": M, "N": N, "K": K, "ms": round(ms, 4), "bound": "tensor", "achieved": round(tf, 1), "peak": bf16_peak,
+                      "unit": "TFLOP/s", "frac": round(tf / bf16_peak, 4)}
+        del A, Bm, C
+    out["contractions_tcgen05_bf16"] = legs
+    torch.manual_seed(0)
+    big = m.DiffPool(1024, 2, 10000, 2, 1024, 1024, args).to(dev)
+    xb = torch.randn(1, 10000, 1024, device=dev)
+    ab = torch.rand(10000, 10000, device=dev)
+    with torch.no_grad():
+        ms_big = timed(lambda: big(xb, ab), 3, warm=1)
+    out["large_forward"] = {"shape": "b=1, N=10000 -> 2500 -> 625, C=1024", "ms": round(ms_big, 3),
+                            "note": "DiffPool.forward end to end, fp32 in/out: bf16 casts, softmax / normalise passes and the "
+                                    "N x N link term included"}
+    return out
+
+
 # ----------------------------------------------------------------------------------------------------
 def run_reference(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    v, ms, cores = cpu_reference_run(a.config, a.cpu_batch, a.steps, a.warmup)
+    import multilevel_gnn_b200 as m
+    B = a.cpu_batch or a.batch or m.configs.make_args(a.config).batch_size
+    v, ms, cores, kind = cpu_reference_run(a.config, B, a.steps, a.warmup)
     sample = "%d train steps of %d synthetic %s-shaped graphs (N=15405, E=92430/graph), %d warm-up" % (
-        a.steps, a.cpu_batch, a.config, a.warmup)
+        a.steps, B, a.config, a.warmup)
+    what = ("the reference's own modules (oracle/_ref) behind the pure-torch PyG stub" if kind == "reference"
+            else "CPU port of the reference path (oracle/train_port.py)")
     print(json.dumps({
         "impl": "reference", "metric": "train graphs/sec (%s.yaml shape)" % a.config, "value": round(v, 3),
         "unit": "graphs/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": round(ms, 2),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "config/%s.yaml MultilevelGNN train step (fwd+bwd+Adam), N=15405 nodes, E=92430 edges/graph, "
-                               "G=25015: CPU port of the reference path on a bounded sample of %d graphs per step"
-                               % (a.config, a.cpu_batch),
-                   "graphs_per_step": a.cpu_batch},
-        "cpu_baseline": {"value": round(v, 3), "unit": "graphs/s", "cores": cores, "kind": "port", "sample": sample},
+        "config": {"workload": "config/%s.yaml MultilevelGNN train step (fwd+bwd+allreduce+Adam), %d graphs/GPU, "
+                               "N=15405 nodes, E=92430 edges/graph, G=25015, P=%d" % (a.config, B, m.configs.make_args(a.config).pca_dim),
+                   "graphs_per_gpu": B, "ran_on": "host cores: " + what},
+        "cpu_baseline": {"value": round(v, 3), "unit": "graphs/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": round(v, 3), "unit": "graphs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
@@ -317,12 +409,17 @@ def run_b200(a):
     m.synth.multilevel_params(model)
     model.to(dev)
     model.pathway_indexs = model.pathway_indexs.to(dev)
-    host = m.synth.multilevel_batch(batch_size=B, seed=100 + rank).pin_memory()
-    host.topology_key = "fold0"
+    # batches come out of the loader replacement (data.collate): per-patient records + ONE FoldTopology
+    raw = m.synth.multilevel_batch(batch_size=B, seed=100 + rank)
+    n1 = 3 * m.MultilevelGNN.GENES
+    E1 = raw.edge_index.shape[1] // B
+    topo = m.data.FoldTopology(raw.edge_index[:, :E1], raw.edge_attr[:E1], raw.gene_pca_match[0], raw.raw_indice[0], n1)
+    import types
+    patients = [types.SimpleNamespace(x=raw.x[i * n1:(i + 1) * n1], age=raw.age[i], y=raw.y[2 * i:2 * i + 2]) for i in range(B)]
+    host = m.data.collate(patients, topo, pin=True)
     weight = torch.tensor([[0.8, 1.3]]).repeat(B, 1).to(dev)
     tr = Trainer(model, args, weight, world_size=world, peer_update=False if a.nccl_update else None)
-    resident = host.to(dev)
-    resident.topology_key = "fold0"
+    resident = m.data.to_device(host, topo, dev)
     hbm_peak, peak_src = peaks()
 
     # ---- warm-up (builds the CSR / pool layouts), optional CUDA-graph capture of the whole step ----
@@ -336,56 +433,73 @@ def run_b200(a):
         for _ in range(2):
             tr.step()
 
-    # ---- resident leg: `value` ----
+    # ---- resident leg: `value` = median of `--windows` timed windows of EXACTLY --steps steps each ----
     sampler = ClockSampler(local) if rank == 0 else None
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    windows_ms = []
     barrier(world)
     if sampler:
         sampler.start()
-    e0.record()
-    for _ in range(a.steps):
-        loss = tr.step(resident)
-    e1.record()
-    barrier(world)
-    ms_total = max_over_ranks(e0.elapsed_time(e1), world, dev)
+    for _ in range(max(1, a.windows)):
+        barrier(world)
+        e0.record()
+        for _ in range(a.steps):
+            loss = tr.step(resident)
+        e1.record()
+        barrier(world)
+        windows_ms.append(max_over_ranks(e0.elapsed_time(e1), world, dev))
+    ms_total = statistics.median(windows_ms)
     clocks = sampler.stop() if sampler else None
     launches = launches_per_step * a.steps
     loss_value = float(loss.item())
 
-    # ---- end-to-end leg: pinned host batch -> device EVERY step (train.py:42), loss read back (train.py:62) ----
-    # graph mode: the next batch's H2D runs on a copy stream while the current step's graph executes
-    # the loss of EVERY step reaches the host inside the timed region; in graph mode step i's value is awaited while step
-    # i+1 is already running (Trainer.loss_to_host) instead of idling the GPU on a per-step .item()
-    pending = []
+    # ---- end-to-end legs: pinned host batch -> device EVERY step (train.py:42), loss read back (train.py:62) ----
+    # graph mode: the next batch's H2D runs on a copy stream while the current step's graph executes; the loss of EVERY step
+    # reaches the host inside the timed region, step i's value being awaited while step i+1 runs (Trainer.loss_to_host).
+    # (1) `e2e`: batches from data.collate (the loader replacement): the fold-constant topology travels once under its key,
+    #     per step only node values / labels / age are uploaded.  (2) `e2e_full_upload`: keyless batches as the reference's
+    #     PyG loader emits them -- all 78 MB re-sent every step and verified on the device against the captured topology.
+    def e2e_leg(host_batch):
+        pending = []
 
-    def e2e_step(first=False):
-        if tr.graph is None:
-            return float(tr.step(host.to(dev, non_blocking=True)).item())
-        if first:
-            tr.prefetch(host)
-        handle = tr.loss_to_host(tr.step_prefetched())
-        tr.prefetch(host)                     # H2D of the following step's batch, overlapped with this replay
-        pending.append(handle)
-        return pending.pop(0).get() if len(pending) > 1 else None
+        def step(first=False):
+            if tr.graph is None:
+                return float(tr.step(host_batch.to(dev, non_blocking=True)).item())
+            if first:
+                tr.prefetch(host_batch)
+            handle = tr.loss_to_host(tr.step_prefetched())
+            tr.prefetch(host_batch)                # H2D of the following step's batch, overlapped with this replay
+            pending.append(handle)
+            return pending.pop(0).get() if len(pending) > 1 else None
 
-    def e2e_drain():
-        return [h.get() for h in pending[:]], pending.clear()
+        def drain():
+            out = [h.get() for h in pending]
+            pending.clear()
+            return out
 
-    e2e_step(first=True)
-    e2e_step()
-    e2e_drain()
-    barrier(world)
-    h2d = tr.h2d_bytes(host) if tr.graph is not None else host.nbytes()
-    e2e_losses = []
-    e0.record()
-    for _ in range(a.steps):
-        e2e_losses.append(e2e_step())
-    e2e_losses += e2e_drain()[0]
-    e1.record()
-    barrier(world)
-    e2e_losses = [x for x in e2e_losses if x is not None]
-    assert len(e2e_losses) == a.steps and all(x == x for x in e2e_losses), "every step's loss must reach the host"
-    ms_e2e = max_over_ranks(e0.elapsed_time(e1), world, dev)
+        step(first=True)
+        step()
+        drain()
+        barrier(world)
+        nbytes = tr.h2d_bytes(host_batch) if tr.graph is not None else host_batch.nbytes()
+        losses = []
+        e0.record()
+        for _ in range(a.steps):
+            losses.append(step())
+        losses += drain()
+        e1.record()
+        barrier(world)
+        losses = [x for x in losses if x is not None]
+        assert len(losses) == a.steps and all(x == x for x in losses), "every step's loss must reach the host"
+        if tr.graph is not None:
+            torch.cuda.synchronize()      # the prefetch issued by the last step is still in flight: let it land
+        return max_over_ranks(e0.elapsed_time(e1), world, dev), nbytes
+
+    ms_e2e, h2d = e2e_leg(host)
+    keyless = m.synth.GraphBatch(**{k: v for k, v in vars(host).items() if k != "topology_key"})
+    ms_full, h2d_full = e2e_leg(keyless)
+    if tr.graph is not None:
+        tr.check_topology_flag()
 
     # ---- per-kernel device time (CUDA events around every launch of the same step, eager) ----
     timer = _cabi.KernelTimer()
@@ -423,7 +537,7 @@ def run_b200(a):
         tag, d = max(hbm_kernels.items(), key=lambda kv: kv[1]["ms"])
         gbs = d["bytes"] / d["ms"] / 1e6
         roof = {"kernel": tag, "bound": "hbm", "achieved": round(gbs, 1), "peak": hbm_peak, "unit": "GB/s",
-                "frac": round(gbs / hbm_peak, 4), "traffic": NCU_TRAFFIC.get("gather_sum_rep_c32"), "peak_source": peak_src,
+                "frac": round(gbs / hbm_peak, 4), "traffic": ncu_traffic(tag), "peak_source": peak_src,
                 "launches": d["launches"], "avg_us": round(d["ms"] / d["launches"] * 1e3, 2),
                 "share_of_step": round(d["ms"] / ms_total, 4),
                 "algorithmic_bytes": "8*C*B*N + 8*nnz per launch (rows read once + written once + idx/val per entry), C = 32: the "
@@ -450,13 +564,21 @@ def run_b200(a):
                             if tr.peer is not None else
                             "CUDA graph (fwd+loss+bwd) -> NCCL all-reduce -> CUDA graph (Adam)"),
                    "l2": "no flush: per-step working set (~2 GB of activations) exceeds the 126 MB L2",
-                   "e2e_h2d": "per-step node features, labels, age from pinned memory; the edge list / pooling layout "
-                              "are dataset constants (one gene network for all patients) uploaded once under the "
-                              "batch's topology_key"},
+                   "timing": "median of %d windows of %d steps" % (len(windows_ms), a.steps),
+                   "e2e_h2d": "batches from data.collate (the PyG-collate replacement): per-step node features, labels, age "
+                              "from pinned memory; the edge list / pooling layout are fold constants (one gene network for "
+                              "all patients, multiloader.py:687-698) uploaded once under the batch's topology_key; "
+                              "e2e_full_upload re-sends everything"},
         "e2e": {"value": round(B * world * a.steps / (ms_e2e / 1e3), 2), "unit": "graphs/s",
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "ms_per_step": round(ms_e2e / a.steps, 4),
                 "loss_readback": "every step's loss is copied to pinned host memory and read by the host inside the timed "
                                  "region; step i's value is awaited while step i+1 runs"},
+        "e2e_full_upload": {"value": round(B * world * a.steps / (ms_full / 1e3), 2), "unit": "graphs/s",
+                            "h2d_bytes_per_step": h2d_full, "d2h_bytes_per_step": 8, "ms_per_step": round(ms_full / a.steps, 4),
+                            "note": "keyless batches (the reference loader's layout: every batch re-sends edge list, edge "
+                                    "weights and pooling tables); PCIe-bound; the re-sent topology is compared on the "
+                                    "device with the captured one"},
+        "windows_ms": [round(x, 4) for x in windows_ms],
         "gpu_launches": launches, "clocks": clocks, "roofline": roof, "loss": loss_value,
         "dp_update": (None if world == 1 else "nccl all-reduce + replicated Adam" if tr.peer is None else
                       {"kernel": "peer_adam_kernel (reduce-scatter -> Adam shard -> all-gather over NVLink peer memory)",
@@ -466,10 +588,13 @@ def run_b200(a):
     if world == 1 and not a.no_genconv:
         line["genconv_agg"] = genconv_microbench(dev, hbm_peak)
     if world == 1 and not a.no_cpu_baseline:
-        v, ms, cores = cpu_reference_run(a.config, a.cpu_batch, 2, 1)
-        line["cpu_baseline"] = {"value": round(v, 3), "unit": "graphs/s", "cores": cores, "kind": "port",
+        cb = a.cpu_batch or B
+        v, ms, cores, kind = cpu_reference_run(a.config, cb, 2, 1)
+        line["cpu_baseline"] = {"value": round(v, 3), "unit": "graphs/s", "cores": cores, "kind": kind,
                                 "sample": "2 train steps of %d graphs (same shape), 1 warm-up, torch CPU threads=%d"
-                                          % (a.cpu_batch, cores)}
+                                          % (cb, cores)}
+    if world == 1 and not a.no_diffpool:
+        line["diffpool"] = diffpool_legs(dev)
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

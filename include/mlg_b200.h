@@ -218,9 +218,9 @@ int mlg_sage_fold_bwd(const float* g_wcat, const float* nn_w, const float* lin_r
 /* Pathway-wise independence term of MultilevelGNN.get_feature_loss (models/multilevel_gnn.py:336-346; no gradient, the
  * reference reads .data):  out[0] = (1 / (P(P-1)/2)) * sum_{i < P-1} mean_s | sum_g w_gi w_gL | / (sqrt(sum_g w_gi^2 *
  * sum_g w_gL^2) + 1e-7),  L = P-1, w = w_raw * mask (mask [G] or NULL), g over the genes of pathway segment s =
- * [segptr[s], segptr[s+1]) (genes sorted by segment).  One launch, fixed summation order.  2 <= P <= 8. */
+ * [segptr[s], segptr[s+1]) (genes sorted by segment).  Fixed summation order.  2 <= P <= 8; workspace: nseg floats. */
 int mlg_pca_indep_loss(const float* w, const float* mask, const int32_t* segptr, int64_t nseg, int64_t P, float* out,
-                       void* stream);
+                       float* workspace, void* stream);
 
 /* Head max-pool over a channel-LAST activation (nn.MaxPool2d((kh, kw)), stride = kernel, floor mode, of
  * multilevel_gnn.py:286): x_cl [B, H, W, C] in memory -> out_nchw [B, C, H/kh, W/kw] (the order flatten() expects) and the

@@ -30,45 +30,40 @@ constexpr int kGradFloats = C1 * CIN + C1 + C2 * C1 + C2;   // gW1, gb1, gW2, gb
 
 __device__ __forceinline__ bool drop_keep(const int* bits, size_t i, int thr) { return bits == nullptr || __ldg(bits + i) >= thr; }
 
-struct HeadW {   // shared-memory copies: *t = transposed, so that lane = output channel reads are conflict-free
-  float w1[C1 * CIN];    // [j][i]
-  float w1t[CIN * C1];   // [i][j]
-  float w2[C2 * C1];     // [c][i]
-  float w2t[C1 * C2];    // [i][c]
+// ---------------------------------------------------------------------------------------------------------------------
+// conv 1x1 (32 -> 32) + ReLU, conv 1x1 (32 -> 64) + ReLU, max-pool, dropout, flatten.
+// One THREAD per pixel: its 32 inputs, 32 hidden and 64 output values live in registers and every weight is read from
+// shared memory as a warp-wide broadcast (LDS.128: four output channels per load), so the inner loops are pure FMA
+// streams (1 LDS per 4 FMA).  A block owns whole "bands" (kh image rows = Wo pooling windows side by side), so pooling is
+// a shared-memory exchange inside the block.  (The first version walked one warp per window with 32-lane shuffled
+// mat-vecs: 28 us forward / 276 us backward on B200 -- shuffle / LDS bound; see profiles/r02_step_launches.md.)
+constexpr int kPix = 256;          // threads per block = pixel slots per block
+constexpr int ZLD = C2 + 1;        // row pitch of the [pixel][64] tile: conflict-free for "thread = pixel" row access
+constexpr int HLD = C1 + 4;        // row pitch of the [pixel][32] tiles (16-byte aligned rows)
+
+struct ConvW {   // shared-memory weight copies; *t = [in][out] (forward), plain = [out][in] (backward)
+  float w1t[CIN * C1];
+  float w2t[C1 * C2];
+  float w1[C1 * CIN];
+  float w2[C2 * C1];
   float b1[C1];
   float b2[C2];
 };
 
-__device__ __forceinline__ void load_weights(HeadW& S, const float* W1, const float* b1, const float* W2, const float* b2) {
+__device__ __forceinline__ void load_conv_weights(ConvW& S, const float* W1, const float* b1, const float* W2, const float* b2,
+                                                  bool backward) {
   for (int t = threadIdx.x; t < C1 * CIN; t += blockDim.x) {
     const float v = __ldg(W1 + t);
-    S.w1[t] = v;
     S.w1t[(t % CIN) * C1 + t / CIN] = v;
+    if (backward) S.w1[t] = v;
   }
   for (int t = threadIdx.x; t < C2 * C1; t += blockDim.x) {
     const float v = __ldg(W2 + t);
-    S.w2[t] = v;
     S.w2t[(t % C1) * C2 + t / C1] = v;
+    if (backward) S.w2[t] = v;
   }
   for (int t = threadIdx.x; t < C1; t += blockDim.x) S.b1[t] = __ldg(b1 + t);
   for (int t = threadIdx.x; t < C2; t += blockDim.x) S.b2[t] = __ldg(b2 + t);
-  __syncthreads();
-}
-
-// both 1x1 convs of one pixel: lane holds x[lane] -> h1[lane] (post-ReLU), z2[lane], z2[lane+32] (pre-ReLU)
-__device__ __forceinline__ void pixel_forward(const HeadW& S, float x, int lane, float& h1, float& za, float& zb) {
-  float a = S.b1[lane];
-#pragma unroll
-  for (int i = 0; i < CIN; ++i) a = fmaf(S.w1t[i * C1 + lane], __shfl_sync(0xffffffffu, x, i), a);
-  h1 = fmaxf(a, 0.f);
-  za = S.b2[lane];
-  zb = S.b2[lane + 32];
-#pragma unroll
-  for (int i = 0; i < C1; ++i) {
-    const float hv = __shfl_sync(0xffffffffu, h1, i);
-    za = fmaf(S.w2t[i * C2 + lane], hv, za);
-    zb = fmaf(S.w2t[i * C2 + lane + 32], hv, zb);
-  }
 }
 
 struct ConvPoolP {
@@ -79,6 +74,8 @@ struct ConvPoolP {
   int thr;            // keep iff bits >= thr
   float keep_scale;   // 1 / (1 - p)
   int B, H, W, kh, kw, Ho, Wo;
+  int PB, NB, nbands;  // pixels per band (kh * W), bands per block, B * Ho
+  int table;           // backward: per-(window, channel) argmax table in shared memory (kh * kw > 1)
   long long ld;       // row pitch of the flattened matrix
   float* a0;          // fwd out [B, ld]
   // backward
@@ -87,145 +84,259 @@ struct ConvPoolP {
   float* partial;     // [blocks, kGradFloats]
 };
 
-__global__ void __launch_bounds__(kThreads) head_conv_pool_fwd_kernel(const ConvPoolP P) {
-  __shared__ HeadW S;
-  load_weights(S, P.W1, P.b1, P.W2, P.b2);
-  const int lane = threadIdx.x & 31;
-  const long long nwin = (long long)P.B * P.Ho * P.Wo;
-  const long long HoWo = (long long)P.Ho * P.Wo;
-  const long long F = C2 * HoWo;
-  for (long long o = ((long long)blockIdx.x * kThreads + threadIdx.x) >> 5; o < nwin; o += (long long)gridDim.x * kWarps) {
-    const int wo = (int)(o % P.Wo);
-    const int ho = (int)((o / P.Wo) % P.Ho);
-    const int b = (int)(o / HoWo);
-    float best_a = -INFINITY, best_b = -INFINITY;
-    for (int dh = 0; dh < P.kh; ++dh)
-      for (int dw = 0; dw < P.kw; ++dw) {
-        const size_t pix = ((size_t)b * P.H + (size_t)ho * P.kh + dh) * P.W + (size_t)wo * P.kw + dw;
-        const float x = __ldg(P.x + pix * CIN + lane);
-        float h1, za, zb;
-        pixel_forward(S, x, lane, h1, za, zb);
-        best_a = fmaxf(best_a, fmaxf(za, 0.f));
-        best_b = fmaxf(best_b, fmaxf(zb, 0.f));
-      }
-    const size_t col_a = (size_t)lane * HoWo + (size_t)ho * P.Wo + wo, col_b = col_a + (size_t)32 * HoWo;
-    float* row = P.a0 + (size_t)b * P.ld;
-    row[col_a] = drop_keep(P.bits, (size_t)b * F + col_a, P.thr) ? best_a * P.keep_scale : 0.f;
-    row[col_b] = drop_keep(P.bits, (size_t)b * F + col_b, P.thr) ? best_b * P.keep_scale : 0.f;
-    if (P.age && ho == 0 && wo == 0 && lane == 0) row[F] = __ldg(P.age + b);
+// this thread's pixel: returns false for idle slots.  band = (b, ho); p = dh * W + w inside the band.
+__device__ __forceinline__ bool my_pixel(const ConvPoolP& P, int& bl, int& p, int& b, int& ho, size_t& pix) {
+  bl = threadIdx.x / P.PB;
+  p = threadIdx.x - bl * P.PB;
+  const long long band = (long long)blockIdx.x * P.NB + bl;
+  if (bl >= P.NB || band >= P.nbands) return false;
+  b = (int)(band / P.Ho);
+  ho = (int)(band - (long long)b * P.Ho);
+  const int dh = p / P.W, w = p - dh * P.W;
+  pix = ((size_t)b * P.H + (size_t)ho * P.kh + dh) * P.W + w;
+  return true;
+}
+
+__device__ __forceinline__ void load_x(const float* x, size_t pix, float (&v)[CIN]) {
+  const float4* src = reinterpret_cast<const float4*>(x + pix * CIN);
+#pragma unroll
+  for (int q = 0; q < CIN / 4; ++q) {
+    const float4 t = __ldg(src + q);
+    v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
   }
 }
 
-__global__ void __launch_bounds__(kThreads) head_conv_pool_bwd_kernel(const ConvPoolP P) {
-  __shared__ HeadW S;
-  __shared__ float red[kGradFloats];
-  load_weights(S, P.W1, P.b1, P.W2, P.b2);
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const long long HoWo = (long long)P.Ho * P.Wo;
-  const long long F = C2 * HoWo;
-  const long long nwin = (long long)P.B * HoWo;
-  // pixels the floor-mode pool never reads (tail rows / columns) get a zero gradient: extra work items after the windows
-  const int tail_rows = P.H - P.Ho * P.kh, tail_cols = P.W - P.Wo * P.kw;
-  const long long tail_per_b = (long long)tail_rows * P.W + (long long)(P.H - tail_rows) * tail_cols;
-  const long long nitems = nwin + (long long)P.B * tail_per_b;
-  float gw1[CIN], gw2a[C1], gw2b[C1], gb1 = 0.f, gb2a = 0.f, gb2b = 0.f;
+// h1 = relu(W1 x + b1): weights broadcast from shared memory, four outputs per load
+__device__ __forceinline__ void conv1(const ConvW& S, const float (&x)[CIN], float (&h)[C1]) {
 #pragma unroll
-  for (int i = 0; i < CIN; ++i) gw1[i] = 0.f;
+  for (int j = 0; j < C1; ++j) h[j] = S.b1[j];
 #pragma unroll
-  for (int i = 0; i < C1; ++i) gw2a[i] = gw2b[i] = 0.f;
-  for (long long o = ((long long)blockIdx.x * kThreads + threadIdx.x) >> 5; o < nitems; o += (long long)gridDim.x * kWarps) {
-    if (o >= nwin) {   // a dropped pixel
-      const long long t = o - nwin;
-      const int b = (int)(t / tail_per_b);
-      long long r = t % tail_per_b;
-      int h, w;
-      if (r < (long long)tail_rows * P.W) {
-        h = P.Ho * P.kh + (int)(r / P.W);
-        w = (int)(r % P.W);
-      } else {
-        r -= (long long)tail_rows * P.W;
-        h = (int)(r / tail_cols);
-        w = P.Wo * P.kw + (int)(r % tail_cols);
-      }
-      P.g_x[(((size_t)b * P.H + h) * P.W + w) * CIN + lane] = 0.f;
-      continue;
+  for (int i = 0; i < CIN; ++i) {
+#pragma unroll
+    for (int j4 = 0; j4 < C1 / 4; ++j4) {
+      const float4 w = *reinterpret_cast<const float4*>(&S.w1t[i * C1 + 4 * j4]);
+      h[4 * j4] = fmaf(x[i], w.x, h[4 * j4]);
+      h[4 * j4 + 1] = fmaf(x[i], w.y, h[4 * j4 + 1]);
+      h[4 * j4 + 2] = fmaf(x[i], w.z, h[4 * j4 + 2]);
+      h[4 * j4 + 3] = fmaf(x[i], w.w, h[4 * j4 + 3]);
     }
-    const int wo = (int)(o % P.Wo);
-    const int ho = (int)((o / P.Wo) % P.Ho);
-    const int b = (int)(o / HoWo);
-    // pass 1: window maximum and its FIRST position (ATen: strict >) per channel
-    float best_a = -INFINITY, best_b = -INFINITY;
-    int arg_a = 0, arg_b = 0;
-    for (int dh = 0; dh < P.kh; ++dh)
-      for (int dw = 0; dw < P.kw; ++dw) {
-        const size_t pix = ((size_t)b * P.H + (size_t)ho * P.kh + dh) * P.W + (size_t)wo * P.kw + dw;
-        const float x = __ldg(P.x + pix * CIN + lane);
-        float h1, za, zb;
-        pixel_forward(S, x, lane, h1, za, zb);
-        const float ra = fmaxf(za, 0.f), rb = fmaxf(zb, 0.f);
-        if (ra > best_a) { best_a = ra; arg_a = dh * P.kw + dw; }
-        if (rb > best_b) { best_b = rb; arg_b = dh * P.kw + dw; }
-      }
-    const size_t col_a = (size_t)lane * HoWo + (size_t)ho * P.Wo + wo, col_b = col_a + (size_t)32 * HoWo;
-    const float* grow = P.g_a0 + (size_t)b * P.ld;
-    // gradient reaching the maximum: dropout scale, and ReLU'(z) = 0 where the maximum is the clamped 0
-    float go_a = drop_keep(P.bits, (size_t)b * F + col_a, P.thr) ? __ldg(grow + col_a) * P.keep_scale : 0.f;
-    float go_b = drop_keep(P.bits, (size_t)b * F + col_b, P.thr) ? __ldg(grow + col_b) * P.keep_scale : 0.f;
-    if (!(best_a > 0.f)) go_a = 0.f;
-    if (!(best_b > 0.f)) go_b = 0.f;
-    // pass 2: per pixel, back through conv2 / ReLU / conv1
-    for (int dh = 0; dh < P.kh; ++dh)
-      for (int dw = 0; dw < P.kw; ++dw) {
-        const int pos = dh * P.kw + dw;
-        const size_t pix = ((size_t)b * P.H + (size_t)ho * P.kh + dh) * P.W + (size_t)wo * P.kw + dw;
-        const float gza = arg_a == pos ? go_a : 0.f, gzb = arg_b == pos ? go_b : 0.f;
-        float gx = 0.f;
-        if (__any_sync(0xffffffffu, gza != 0.f || gzb != 0.f)) {
-          const float x = __ldg(P.x + pix * CIN + lane);
-          float h1, za, zb;
-          pixel_forward(S, x, lane, h1, za, zb);
-          gb2a += gza;
-          gb2b += gzb;
-          float gh = 0.f;   // dL/dh1[lane]
-#pragma unroll
-          for (int i = 0; i < C1; ++i) {
-            const float hv = __shfl_sync(0xffffffffu, h1, i);
-            gw2a[i] = fmaf(gza, hv, gw2a[i]);
-            gw2b[i] = fmaf(gzb, hv, gw2b[i]);
-            gh = fmaf(S.w2[i * C1 + lane], __shfl_sync(0xffffffffu, gza, i), gh);
-            gh = fmaf(S.w2[(i + 32) * C1 + lane], __shfl_sync(0xffffffffu, gzb, i), gh);
-          }
-          const float gz1 = h1 > 0.f ? gh : 0.f;
-          gb1 += gz1;
-#pragma unroll
-          for (int i = 0; i < CIN; ++i) {
-            gw1[i] = fmaf(gz1, __shfl_sync(0xffffffffu, x, i), gw1[i]);
-            gx = fmaf(S.w1[i * CIN + lane], __shfl_sync(0xffffffffu, gz1, i), gx);
-          }
-        }
-        P.g_x[pix * CIN + lane] = gx;
-      }
   }
-  // block partial: warps add their register accumulators in turn (fixed order), then one row of the workspace
-  for (int t = threadIdx.x; t < kGradFloats; t += kThreads) red[t] = 0.f;
+#pragma unroll
+  for (int j = 0; j < C1; ++j) h[j] = fmaxf(h[j], 0.f);
+}
+
+// relu(W2 h + b2) in four 16-channel chunks, written to this pixel's row of the [pixel][64] tile
+__device__ __forceinline__ void conv2_to_tile(const ConvW& S, const float (&h)[C1], float* zrow) {
+#pragma unroll
+  for (int c0 = 0; c0 < C2; c0 += 16) {
+    float a[16];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) a[c] = S.b2[c0 + c];
+#pragma unroll
+    for (int i = 0; i < C1; ++i) {
+#pragma unroll
+      for (int c4 = 0; c4 < 4; ++c4) {
+        const float4 w = *reinterpret_cast<const float4*>(&S.w2t[i * C2 + c0 + 4 * c4]);
+        a[4 * c4] = fmaf(h[i], w.x, a[4 * c4]);
+        a[4 * c4 + 1] = fmaf(h[i], w.y, a[4 * c4 + 1]);
+        a[4 * c4 + 2] = fmaf(h[i], w.z, a[4 * c4 + 2]);
+        a[4 * c4 + 3] = fmaf(h[i], w.w, a[4 * c4 + 3]);
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < 16; ++c) zrow[c0 + c] = fmaxf(a[c], 0.f);
+  }
+}
+
+__global__ void __launch_bounds__(kPix) head_conv_pool_fwd_kernel(const ConvPoolP P) {
+  extern __shared__ __align__(16) unsigned char head_smem[];
+  ConvW& S = *reinterpret_cast<ConvW*>(head_smem);
+  float* zt = reinterpret_cast<float*>(head_smem + sizeof(ConvW));   // [kPix][ZLD]
+  load_conv_weights(S, P.W1, P.b1, P.W2, P.b2, false);
   __syncthreads();
-  for (int w = 0; w < kWarps; ++w) {
-    if (warp == w) {
-#pragma unroll
-      for (int i = 0; i < CIN; ++i) red[lane * CIN + i] += gw1[i];
-      red[C1 * CIN + lane] += gb1;
-      float* r2 = red + C1 * CIN + C1;
-#pragma unroll
-      for (int i = 0; i < C1; ++i) {
-        r2[lane * C1 + i] += gw2a[i];
-        r2[(lane + 32) * C1 + i] += gw2b[i];
-      }
-      r2[C2 * C1 + lane] += gb2a;
-      r2[C2 * C1 + lane + 32] += gb2b;
-    }
-    __syncthreads();
+  int bl, p, b, ho;
+  size_t pix;
+  if (my_pixel(P, bl, p, b, ho, pix)) {
+    float x[CIN], h[C1];
+    load_x(P.x, pix, x);
+    conv1(S, x, h);
+    conv2_to_tile(S, h, zt + threadIdx.x * ZLD);
   }
-  for (int t = threadIdx.x; t < kGradFloats; t += kThreads) P.partial[(size_t)blockIdx.x * kGradFloats + t] = red[t];
+  __syncthreads();
+  const long long HoWo = (long long)P.Ho * P.Wo, F = C2 * HoWo;
+  for (int o = threadIdx.x; o < P.NB * P.Wo * C2; o += kPix) {
+    const int c = o % C2, win = o / C2;
+    const int wbl = win / P.Wo, wo = win - wbl * P.Wo;
+    const long long band = (long long)blockIdx.x * P.NB + wbl;
+    if (band >= P.nbands) break;
+    const int bb = (int)(band / P.Ho), hho = (int)(band - (long long)bb * P.Ho);
+    float best = 0.f;    // post-ReLU values are >= 0
+    for (int dh = 0; dh < P.kh; ++dh)
+      for (int dw = 0; dw < P.kw; ++dw) best = fmaxf(best, zt[(wbl * P.PB + dh * P.W + wo * P.kw + dw) * ZLD + c]);
+    const size_t col = (size_t)c * HoWo + (size_t)hho * P.Wo + wo;
+    P.a0[(size_t)bb * P.ld + col] = drop_keep(P.bits, (size_t)bb * F + col, P.thr) ? best * P.keep_scale : 0.f;
+    if (P.age && c == 0 && hho == 0 && wo == 0) P.a0[(size_t)bb * P.ld + F] = __ldg(P.age + bb);
+  }
+}
+
+__global__ void __launch_bounds__(kPix) head_conv_pool_bwd_kernel(const ConvPoolP P) {
+  extern __shared__ __align__(16) unsigned char head_smem[];
+  ConvW& S = *reinterpret_cast<ConvW*>(head_smem);
+  float* zt = reinterpret_cast<float*>(head_smem + sizeof(ConvW));   // [kPix][ZLD]: relu(z2), then dL/dz2
+  float* Ht = zt + kPix * ZLD;                                        // [kPix][HLD]: h1
+  float* Xt = Ht + kPix * HLD;                                        // [kPix][HLD]: x
+  float* G1 = Xt + kPix * HLD;                                        // [kPix][HLD]: dL/dz1
+  float* gval = G1 + kPix * HLD;                                      // [NB * Wo][64]: gradient reaching each window maximum
+  unsigned char* garg = reinterpret_cast<unsigned char*>(gval + P.NB * P.Wo * C2);   // its window position (255: none)
+  load_conv_weights(S, P.W1, P.b1, P.W2, P.b2, true);
+  __syncthreads();
+  int bl = 0, p = 0, b = 0, ho = 0;
+  size_t pix = 0;
+  const bool live = my_pixel(P, bl, p, b, ho, pix);
+  float h[C1];
+  {
+    float x[CIN];
+    if (live) {
+      load_x(P.x, pix, x);
+      conv1(S, x, h);
+      conv2_to_tile(S, h, zt + threadIdx.x * ZLD);
+    } else {
+#pragma unroll
+      for (int i = 0; i < CIN; ++i) x[i] = 0.f;
+#pragma unroll
+      for (int i = 0; i < C1; ++i) h[i] = 0.f;
+      for (int c = 0; c < C2; ++c) zt[threadIdx.x * ZLD + c] = 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < CIN; ++i) Xt[threadIdx.x * HLD + i] = x[i];
+#pragma unroll
+    for (int i = 0; i < C1; ++i) Ht[threadIdx.x * HLD + i] = h[i];
+  }
+  __syncthreads();
+  // gradient routed to the FIRST maximum of every (window, channel); nothing where the maximum is the clamped 0
+  const long long HoWo = (long long)P.Ho * P.Wo, F = C2 * HoWo;
+  for (int o = threadIdx.x; o < (P.table ? P.NB * P.Wo * C2 : 0); o += kPix) {
+    const int c = o % C2, win = o / C2;
+    const int wbl = win / P.Wo, wo = win - wbl * P.Wo;
+    const long long band = (long long)blockIdx.x * P.NB + wbl;
+    float g = 0.f;
+    int arg = 255;
+    if (band < P.nbands) {
+      const int bb = (int)(band / P.Ho), hho = (int)(band - (long long)bb * P.Ho);
+      float best = 0.f;
+      for (int dh = 0; dh < P.kh; ++dh)
+        for (int dw = 0; dw < P.kw; ++dw) {
+          const float v = zt[(wbl * P.PB + dh * P.W + wo * P.kw + dw) * ZLD + c];
+          if (v > best) { best = v; arg = dh * P.W + wo * P.kw + dw; }     // position inside the band
+        }
+      if (arg != 255) {
+        const size_t col = (size_t)c * HoWo + (size_t)hho * P.Wo + wo;
+        g = drop_keep(P.bits, (size_t)bb * F + col, P.thr) ? __ldg(P.g_a0 + (size_t)bb * P.ld + col) * P.keep_scale : 0.f;
+      }
+    }
+    gval[o] = g;
+    garg[o] = (unsigned char)arg;
+  }
+  __syncthreads();
+  // per pixel: dL/dz2 (into the tile), back through conv2 / ReLU / conv1
+  {
+    float gh[C1];
+#pragma unroll
+    for (int i = 0; i < C1; ++i) gh[i] = 0.f;
+    const int dh = p / P.W, w = p - dh * P.W;
+    const int wo = w / P.kw;
+    const bool in_window = live && wo < P.Wo;
+    float* zrow = zt + threadIdx.x * ZLD;
+    for (int c = 0; c < C2; ++c) {
+      float gz = 0.f;
+      if (in_window) {
+        if (P.table) {
+          const int o = (bl * P.Wo + wo) * C2 + c;
+          gz = (int)garg[o] == p ? gval[o] : 0.f;
+        } else if (zrow[c] > 0.f) {        // 1 x 1 windows: every pixel is its own maximum
+          const size_t col = (size_t)c * HoWo + (size_t)ho * P.Wo + wo;
+          gz = drop_keep(P.bits, (size_t)b * F + col, P.thr) ? __ldg(P.g_a0 + (size_t)b * P.ld + col) * P.keep_scale : 0.f;
+        }
+      }
+      zrow[c] = gz;
+      if (gz != 0.f) {
+#pragma unroll
+        for (int i4 = 0; i4 < C1 / 4; ++i4) {
+          const float4 wv = *reinterpret_cast<const float4*>(&S.w2[c * C1 + 4 * i4]);
+          gh[4 * i4] = fmaf(gz, wv.x, gh[4 * i4]);
+          gh[4 * i4 + 1] = fmaf(gz, wv.y, gh[4 * i4 + 1]);
+          gh[4 * i4 + 2] = fmaf(gz, wv.z, gh[4 * i4 + 2]);
+          gh[4 * i4 + 3] = fmaf(gz, wv.w, gh[4 * i4 + 3]);
+        }
+      }
+    }
+    float gx[CIN];
+#pragma unroll
+    for (int i = 0; i < CIN; ++i) gx[i] = 0.f;
+#pragma unroll
+    for (int j = 0; j < C1; ++j) {
+      const float gz1 = h[j] > 0.f ? gh[j] : 0.f;
+      G1[threadIdx.x * HLD + j] = gz1;
+#pragma unroll
+      for (int i4 = 0; i4 < CIN / 4; ++i4) {
+        const float4 wv = *reinterpret_cast<const float4*>(&S.w1[j * CIN + 4 * i4]);
+        gx[4 * i4] = fmaf(gz1, wv.x, gx[4 * i4]);
+        gx[4 * i4 + 1] = fmaf(gz1, wv.y, gx[4 * i4 + 1]);
+        gx[4 * i4 + 2] = fmaf(gz1, wv.z, gx[4 * i4 + 2]);
+        gx[4 * i4 + 3] = fmaf(gz1, wv.w, gx[4 * i4 + 3]);
+      }
+    }
+    if (live) {
+      float4* dst = reinterpret_cast<float4*>(P.g_x + pix * CIN);
+#pragma unroll
+      for (int q = 0; q < CIN / 4; ++q) dst[q] = make_float4(gx[4 * q], gx[4 * q + 1], gx[4 * q + 2], gx[4 * q + 3]);
+    }
+  }
+  __syncthreads();
+  // parameter gradients of this block: gW2 = Gz2^T H1 (64 x 32), gW1 = Gz1^T X (32 x 32), column sums; fixed order over pixels
+  float* part = P.partial + (size_t)blockIdx.x * kGradFloats;
+  {
+    const int c = threadIdx.x >> 2, i0 = (threadIdx.x & 3) * 8;      // 64 x (4 x 8)
+    float acc[8], sb = 0.f;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) acc[q] = 0.f;
+    for (int t = 0; t < kPix; ++t) {
+      const float g = zt[t * ZLD + c];
+      const float4 h0 = *reinterpret_cast<const float4*>(&Ht[t * HLD + i0]);
+      const float4 h1v = *reinterpret_cast<const float4*>(&Ht[t * HLD + i0 + 4]);
+      acc[0] = fmaf(g, h0.x, acc[0]); acc[1] = fmaf(g, h0.y, acc[1]); acc[2] = fmaf(g, h0.z, acc[2]); acc[3] = fmaf(g, h0.w, acc[3]);
+      acc[4] = fmaf(g, h1v.x, acc[4]); acc[5] = fmaf(g, h1v.y, acc[5]); acc[6] = fmaf(g, h1v.z, acc[6]); acc[7] = fmaf(g, h1v.w, acc[7]);
+      sb += g;
+    }
+    float* gw2 = part + C1 * CIN + C1;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) gw2[c * C1 + i0 + q] = acc[q];
+    if ((threadIdx.x & 3) == 0) gw2[C2 * C1 + c] = sb;
+  }
+  {
+    const int j = threadIdx.x >> 3, i0 = (threadIdx.x & 7) * 4;      // 32 x (8 x 4)
+    float acc[4] = {0.f, 0.f, 0.f, 0.f}, sb = 0.f;
+    for (int t = 0; t < kPix; ++t) {
+      const float g = G1[t * HLD + j];
+      const float4 xv = *reinterpret_cast<const float4*>(&Xt[t * HLD + i0]);
+      acc[0] = fmaf(g, xv.x, acc[0]); acc[1] = fmaf(g, xv.y, acc[1]); acc[2] = fmaf(g, xv.z, acc[2]); acc[3] = fmaf(g, xv.w, acc[3]);
+      sb += g;
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) part[j * CIN + i0 + q] = acc[q];
+    if ((threadIdx.x & 7) == 0) part[C1 * CIN + j] = sb;
+  }
+}
+
+// zero gradient for the image rows the floor-mode pool never reads (pixels of whole tail rows; tail COLUMNS are written
+// by the band threads above)
+__global__ void head_conv_tail_zero_kernel(float4* __restrict__ g_x, int B, int H, int W, int row0) {
+  const long long per_b = (long long)(H - row0) * W * (CIN / 4);
+  const long long total = per_b * B;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long b = i / per_b, r = i - b * per_b;
+    g_x[((size_t)b * H + row0) * W * (CIN / 4) + r] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
 }
 
 __global__ void head_conv_reduce_kernel(const float* __restrict__ partial, int nblocks, float* __restrict__ gW1,
@@ -240,15 +351,33 @@ __global__ void head_conv_reduce_kernel(const float* __restrict__ partial, int n
   else gb2[t - C1 * CIN - C1 - C2 * C1] = s;
 }
 
-inline int conv_pool_blocks(long long items) {
-  long long b = (items + kWarps - 1) / kWarps;
-  const long long cap = 148 * 4;
-  return (int)(b < 1 ? 1 : (b > cap ? cap : b));
+// geometry shared by both directions: bands per block and grid size; false when a band does not fit one block
+inline size_t conv_pool_smem(const ConvPoolP& P, bool backward) {
+  size_t s = sizeof(ConvW) + (size_t)kPix * ZLD * 4;
+  if (backward) s += 3 * (size_t)kPix * HLD * 4 + (P.table ? (size_t)P.NB * P.Wo * C2 * 5 : 0) + 16;
+  return s;
 }
+inline bool conv_pool_geometry(ConvPoolP& P) {
+  P.PB = P.kh * P.W;
+  if (P.PB > kPix || P.PB > 255) return false;
+  P.NB = kPix / P.PB;
+  P.nbands = P.B * P.Ho;
+  P.table = (P.kh * P.kw > 1) ? 1 : 0;
+  while (P.NB > 1 && conv_pool_smem(P, true) > 227 * 1024) --P.NB;     // the argmax table of many small windows
+  return true;
+}
+inline int conv_pool_blocks(const ConvPoolP& P) { return (P.nbands + P.NB - 1) / P.NB; }
 
 // ------------------------------------------------------------------------------------------------------------
 // MLP + loss
 // ------------------------------------------------------------------------------------------------------------
+// One block = one 64-column slice of K, one thread = one hidden unit n (blockDim = D): the slice of W0 [D x 64] and of
+// a0 [R x 64] (transposed) are staged in shared memory once; every thread then owns acc[r] for all R samples and streams
+// its W row against broadcast a0 values (LDS.128: four samples per load).  The backward kernel has the same geometry and
+// produces, from ONE staged W slice, both the slice of the weight gradient and the slice of the input gradient.
+// K columns per block: 64, or 32 when 64 samples x 512 hidden units would not fit shared memory next to a 64-wide slice
+// (row pitch of the staged W slice = KSL + 1: "thread = row" access is conflict-free)
+
 struct MlpP {
   const float* a0;   // [R, ld_a] (K columns used)
   const float* W0;   // [D, K] row pitch K
@@ -260,7 +389,7 @@ struct MlpP {
   float keep_scale;
   const float* y;        // [R, 2] or NULL (no loss)
   const float* weight;   // [R, 2] or NULL
-  int R, D, K, slices, kps;
+  int R, D, K, slices;
   long long ld_a;
   float* partial;   // [slices, R, D]
   float* a1;        // [R, D] post ReLU + dropout
@@ -270,34 +399,52 @@ struct MlpP {
   unsigned* counter;
 };
 
-template <int RT>
-__global__ void __launch_bounds__(kThreads) head_mlp_partial_kernel(const MlpP P) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int n = blockIdx.x * kWarps + warp;
-  const int k_lo = blockIdx.y * P.kps, k_hi = min(P.K, k_lo + P.kps);
-  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *P.counter = 0u;   // the finish kernel's arrival counter
+// stage W0[:, k0 : k0 + 64] as Ws[n][k] and a0[:, k0 : k0 + 64] as As[k][r] (zero padded past K / R)
+template <int RT, int KSL>
+__device__ __forceinline__ void stage_slices(const float* W0, int D, int K, const float* a0, long long ld_a, int R, int k0,
+                                             float* Ws, float* As) {
+  constexpr int WLD = KSL + 1;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  for (int n = warp; n < D; n += nwarps) {
+    const float* row = W0 + (size_t)n * K + k0;
+#pragma unroll
+    for (int q = 0; q < KSL; q += 32) Ws[n * WLD + lane + q] = (k0 + lane + q < K) ? __ldg(row + lane + q) : 0.f;
+  }
+  for (int t = threadIdx.x; t < RT * KSL; t += blockDim.x) {
+    const int r = t / KSL, k = t - r * KSL;
+    As[k * RT + r] = (r < R && k0 + k < K) ? __ldg(a0 + (size_t)r * ld_a + k0 + k) : 0.f;
+  }
+}
+
+template <int RT, int KSL>
+__global__ void __launch_bounds__(512) head_mlp_partial_kernel(const MlpP P) {
+  constexpr int KS = KSL, WLD = KSL + 1;
+  extern __shared__ __align__(16) float mlp_sm[];
+  float* Ws = mlp_sm;                 // [D][WLD]
+  float* As = mlp_sm + P.D * WLD;     // [KS][RT]
+  const int n = threadIdx.x, k0 = blockIdx.x * KS;
+  if (blockIdx.x == 0 && threadIdx.x == 0) *P.counter = 0u;   // the finish kernel's arrival counter
+  stage_slices<RT, KSL>(P.W0, P.D, P.K, P.a0, P.ld_a, P.R, k0, Ws, As);
+  __syncthreads();
   float acc[RT];
 #pragma unroll
   for (int r = 0; r < RT; ++r) acc[r] = 0.f;
-  if (n < P.D) {
-    const float* wrow = P.W0 + (size_t)n * P.K;
-    for (int k = k_lo + lane; k < k_hi; k += 32) {
-      const float w = __ldg(wrow + k);
+#pragma unroll 4
+  for (int k = 0; k < KS; ++k) {
+    const float w = Ws[n * WLD + k];
 #pragma unroll
-      for (int r = 0; r < RT; ++r) {
-        const float xv = (r < P.R) ? __ldg(P.a0 + (size_t)r * P.ld_a + k) : 0.f;
-        acc[r] = fmaf(w, xv, acc[r]);
-      }
+    for (int r4 = 0; r4 < RT / 4; ++r4) {
+      const float4 a = *reinterpret_cast<const float4*>(&As[k * RT + 4 * r4]);
+      acc[4 * r4] = fmaf(w, a.x, acc[4 * r4]);
+      acc[4 * r4 + 1] = fmaf(w, a.y, acc[4 * r4 + 1]);
+      acc[4 * r4 + 2] = fmaf(w, a.z, acc[4 * r4 + 2]);
+      acc[4 * r4 + 3] = fmaf(w, a.w, acc[4 * r4 + 3]);
     }
   }
+  float* p = P.partial + (size_t)blockIdx.x * P.R * P.D + n;
 #pragma unroll
-  for (int r = 0; r < RT; ++r) acc[r] = warp_sum(acc[r]);
-  if (n < P.D && lane == 0) {
-    float* p = P.partial + ((size_t)blockIdx.y * P.R) * P.D + n;
-#pragma unroll
-    for (int r = 0; r < RT; ++r)
-      if (r < P.R) p[(size_t)r * P.D] = acc[r];
-  }
+  for (int r = 0; r < RT; ++r)
+    if (r < P.R) p[(size_t)r * P.D] = acc[r];
 }
 
 // one block per sample r: slice reduction + bias + ReLU + dropout -> a1[r, :]; logits, softmax, weighted BCE; the last
@@ -308,8 +455,18 @@ __global__ void __launch_bounds__(kThreads) head_mlp_finish_kernel(const MlpP P)
   const int r = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float z0 = 0.f, z1 = 0.f;
   for (int n = threadIdx.x; n < P.D; n += kThreads) {
-    float s = 0.f;
-    for (int g = 0; g < P.slices; ++g) s += P.partial[((size_t)g * P.R + r) * P.D + n];
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;     // four independent chains, combined in a fixed order
+    const float* pp = P.partial + (size_t)r * P.D + n;
+    const size_t st = (size_t)P.R * P.D;
+    int g = 0;
+    for (; g + 4 <= P.slices; g += 4) {
+      s0 += pp[(size_t)g * st];
+      s1 += pp[(size_t)(g + 1) * st];
+      s2 += pp[(size_t)(g + 2) * st];
+      s3 += pp[(size_t)(g + 3) * st];
+    }
+    for (; g < P.slices; ++g) s0 += pp[(size_t)g * st];
+    float s = (s0 + s1) + (s2 + s3);
     s += __ldg(P.b0 + n);
     s = fmaxf(s, 0.f);
     s = drop_keep(P.bits, (size_t)r * P.D + n, P.thr) ? s * P.keep_scale : 0.f;
@@ -365,104 +522,119 @@ struct MlpBwdP {
   float *g_a0, *g_W0, *g_b0, *g_W3, *g_b3;
 };
 
-// Block = one 32-column chunk of K; warp w = output rows n in [32w, 32w + 32) of that chunk (D / 32 warps).
-// shared: gz1 [R][D] (dL/dz1, recomputed by every block); the same storage then holds the per-warp partials
-// [warps][R][32] of the input gradient (warps * 32 == D).
-template <int RT>
+template <int RT, int KSL>
 __global__ void __launch_bounds__(512) head_mlp_bwd_kernel(const MlpBwdP P) {
-  extern __shared__ float sm[];
-  float* gz1 = sm;                                  // [R][D]
-  float* accs = sm;                                 // [nwarps][R][32], after the main loop
-  float* gz2 = sm + (size_t)P.R * P.D;              // [R][2]
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-  // ---- phase A: softmax + BCE backward, Linear(D -> 2) backward, ReLU / dropout mask ----
-  for (int r = threadIdx.x; r < P.R; r += blockDim.x) {
-    const float p0 = __ldg(P.pred + 2 * r), p1 = __ldg(P.pred + 2 * r + 1);
-    float g0 = P.g_pred ? __ldg(P.g_pred + 2 * r) : 0.f, g1 = P.g_pred ? __ldg(P.g_pred + 2 * r + 1) : 0.f;
-    if (P.g_loss && P.y) {
-      const float gl = __ldg(P.g_loss) / (2.f * (float)P.R);
-      const float y0 = __ldg(P.y + 2 * r), y1 = __ldg(P.y + 2 * r + 1);
-      const float w0 = P.weight ? __ldg(P.weight + 2 * r) : 1.f, w1 = P.weight ? __ldg(P.weight + 2 * r + 1) : 1.f;
-      // ATen binary_cross_entropy_backward: (p - y) / max((1 - p) p, 1e-12) * weight
-      g0 += gl * w0 * (p0 - y0) / fmaxf((1.f - p0) * p0, 1e-12f);
-      g1 += gl * w1 * (p1 - y1) / fmaxf((1.f - p1) * p1, 1e-12f);
+  constexpr int KS = KSL, WLD = KSL + 1;
+  extern __shared__ __align__(16) float mlp_sm[];
+  float* Ws = mlp_sm;                   // [D][WLD]: W0 slice, later the gW0 slice
+  float* As = Ws + P.D * WLD;           // [KS][RT]
+  float* Gs = As + KS * RT;             // [RT][D]: dL/dz1
+  float* gz2 = Gs + RT * P.D;           // [RT][2]
+  const int n = threadIdx.x, k0 = blockIdx.x * KS, D = P.D;
+  stage_slices<RT, KSL>(P.W0, D, P.K, P.a0, P.ld_a, P.R, k0, Ws, As);
+  // ---- softmax + BCE backward -> dL/dlogits (every block recomputes these R x 2 values) ----
+  for (int r = threadIdx.x; r < RT; r += blockDim.x) {
+    float o0 = 0.f, o1 = 0.f;
+    if (r < P.R) {
+      const float p0 = __ldg(P.pred + 2 * r), p1 = __ldg(P.pred + 2 * r + 1);
+      float g0 = P.g_pred ? __ldg(P.g_pred + 2 * r) : 0.f, g1 = P.g_pred ? __ldg(P.g_pred + 2 * r + 1) : 0.f;
+      if (P.g_loss && P.y) {
+        const float gl = __ldg(P.g_loss) / (2.f * (float)P.R);
+        const float y0 = __ldg(P.y + 2 * r), y1 = __ldg(P.y + 2 * r + 1);
+        const float w0 = P.weight ? __ldg(P.weight + 2 * r) : 1.f, w1 = P.weight ? __ldg(P.weight + 2 * r + 1) : 1.f;
+        // ATen binary_cross_entropy_backward: (p - y) / max((1 - p) p, 1e-12) * weight
+        g0 += gl * w0 * (p0 - y0) / fmaxf((1.f - p0) * p0, 1e-12f);
+        g1 += gl * w1 * (p1 - y1) / fmaxf((1.f - p1) * p1, 1e-12f);
+      }
+      const float dot = g0 * p0 + g1 * p1;
+      o0 = p0 * (g0 - dot);
+      o1 = p1 * (g1 - dot);
     }
-    const float dot = g0 * p0 + g1 * p1;
-    gz2[2 * r] = p0 * (g0 - dot);
-    gz2[2 * r + 1] = p1 * (g1 - dot);
+    gz2[2 * r] = o0;
+    gz2[2 * r + 1] = o1;
   }
   __syncthreads();
-  for (int t = threadIdx.x; t < P.R * P.D; t += blockDim.x) {
-    const int r = t / P.D, n = t % P.D;
-    const float ga1 = gz2[2 * r] * __ldg(P.W3 + n) + gz2[2 * r + 1] * __ldg(P.W3 + P.D + n);
-    gz1[t] = __ldg(P.a1 + t) > 0.f ? ga1 * P.keep_scale : 0.f;
-  }
-  __syncthreads();
-  if (blockIdx.x == 0) {   // the small parameter gradients, fixed order
-    for (int n = threadIdx.x; n < P.D; n += blockDim.x) {
+  // ---- this thread's hidden unit: dL/dz1[r][n] for every sample, in registers and in shared memory ----
+  float gz[RT];
+  {
+    const float w30 = __ldg(P.W3 + n), w31 = __ldg(P.W3 + D + n);
+    float a1v[RT];
+#pragma unroll
+    for (int r = 0; r < RT; ++r) a1v[r] = r < P.R ? __ldg(P.a1 + (size_t)r * D + n) : 0.f;
+#pragma unroll
+    for (int r = 0; r < RT; ++r) {
+      gz[r] = a1v[r] > 0.f ? (gz2[2 * r] * w30 + gz2[2 * r + 1] * w31) * P.keep_scale : 0.f;
+      Gs[r * D + n] = gz[r];
+    }
+    if (blockIdx.x == 0) {   // the small parameter gradients, fixed order over the samples
       float s = 0.f, u0 = 0.f, u1 = 0.f;
-      for (int r = 0; r < P.R; ++r) {
-        s += gz1[(size_t)r * P.D + n];
-        const float a = __ldg(P.a1 + (size_t)r * P.D + n);
-        u0 = fmaf(gz2[2 * r], a, u0);
-        u1 = fmaf(gz2[2 * r + 1], a, u1);
+#pragma unroll
+      for (int r = 0; r < RT; ++r) {
+        s += gz[r];
+        u0 = fmaf(gz2[2 * r], a1v[r], u0);
+        u1 = fmaf(gz2[2 * r + 1], a1v[r], u1);
       }
       P.g_b0[n] = s;
       P.g_W3[n] = u0;
-      P.g_W3[P.D + n] = u1;
-    }
-    if (threadIdx.x < 2) {
-      float s = 0.f;
-      for (int r = 0; r < P.R; ++r) s += gz2[2 * r + threadIdx.x];
-      P.g_b3[threadIdx.x] = s;
-    }
-  }
-  // ---- phase B: this block's 32 columns of K ----
-  const int k = blockIdx.x * 32 + lane;
-  const bool kok = k < P.K;
-  float a0r[RT], accA[RT];
-#pragma unroll
-  for (int r = 0; r < RT; ++r) {
-    a0r[r] = (kok && r < P.R) ? __ldg(P.a0 + (size_t)r * P.ld_a + k) : 0.f;
-    accA[r] = 0.f;
-  }
-#pragma unroll 4
-  for (int n = warp * 32; n < warp * 32 + 32; ++n) {
-    const float w = kok ? __ldg(P.W0 + (size_t)n * P.K + k) : 0.f;
-    float accW = 0.f;
-#pragma unroll
-    for (int r = 0; r < RT; ++r) {
-      const float g = r < P.R ? gz1[(size_t)r * P.D + n] : 0.f;
-      accA[r] = fmaf(g, w, accA[r]);
-      accW = fmaf(g, a0r[r], accW);
-    }
-    if (kok) P.g_W0[(size_t)n * P.K + k] = accW;
-  }
-  __syncthreads();   // every warp is done with gz1: its storage becomes the partials buffer
-#pragma unroll
-  for (int r = 0; r < RT; ++r)
-    if (r < P.R) accs[((size_t)warp * P.R + r) * 32 + lane] = accA[r];
-  __syncthreads();
-  if (P.g_a0) {
-    for (int t = threadIdx.x; t < P.R * 32; t += blockDim.x) {
-      const int r = t >> 5, l = t & 31;
-      const int kk = blockIdx.x * 32 + l;
-      if (kk < P.K) {
-        float s = 0.f;
-        for (int w = 0; w < nwarps; ++w) s += accs[((size_t)w * P.R + r) * 32 + l];
-        P.g_a0[(size_t)r * P.ld_g + kk] = s;
+      P.g_W3[D + n] = u1;
+      if (n < 2) {
+        float t = 0.f;
+        for (int r = 0; r < P.R; ++r) t += gz2[2 * r + n];
+        P.g_b3[n] = t;
       }
+    }
+  }
+  __syncthreads();
+  // ---- input gradient slice: g_a0[r][k0 + k] = sum_n dz1[r][n] W0[n][k0 + k]; thread = (k, group of rows) ----
+  if (P.g_a0) {
+    const int k = threadIdx.x & (KS - 1), grp = threadIdx.x / KS, ngrp = blockDim.x / KS;
+    const int rpg = (RT + ngrp - 1) / ngrp;            // rows per group (<= 16)
+    float acc[16];
+#pragma unroll
+    for (int q = 0; q < 16; ++q) acc[q] = 0.f;
+    const int r0 = grp * rpg;
+    for (int nn = 0; nn < D; ++nn) {
+      const float w = Ws[nn * WLD + k];
+#pragma unroll
+      for (int q = 0; q < 16; ++q)
+        if (q < rpg) acc[q] = fmaf(Gs[(r0 + q < RT ? r0 + q : 0) * D + nn], w, acc[q]);
+    }
+    if (k0 + k < P.K) {
+#pragma unroll
+      for (int q = 0; q < 16; ++q)
+        if (q < rpg && r0 + q < P.R) P.g_a0[(size_t)(r0 + q) * P.ld_g + k0 + k] = acc[q];
+    }
+  }
+  __syncthreads();
+  // ---- weight gradient slice: gW0[n][k0 + k] = sum_r dz1[r][n] a0[r][k0 + k]; staged in Ws, then written row by row ----
+#pragma unroll 4
+  for (int k = 0; k < KS; ++k) {
+    float v = 0.f;
+#pragma unroll
+    for (int r4 = 0; r4 < RT / 4; ++r4) {
+      const float4 a = *reinterpret_cast<const float4*>(&As[k * RT + 4 * r4]);
+      v = fmaf(gz[4 * r4], a.x, v);
+      v = fmaf(gz[4 * r4 + 1], a.y, v);
+      v = fmaf(gz[4 * r4 + 2], a.z, v);
+      v = fmaf(gz[4 * r4 + 3], a.w, v);
+    }
+    Ws[n * WLD + k] = v;
+  }
+  __syncthreads();
+  {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    for (int row = warp; row < D; row += nwarps) {
+      float* dst = P.g_W0 + (size_t)row * P.K + k0;
+#pragma unroll
+      for (int q = 0; q < KS; q += 32)
+        if (k0 + lane + q < P.K) dst[lane + q] = Ws[row * WLD + lane + q];
     }
   }
 }
 
-inline int mlp_slices(int64_t D, int64_t K) {
-  const int64_t col_blocks = (D + kWarps - 1) / kWarps;
-  int64_t s = (148 * 8 + col_blocks - 1) / col_blocks;
-  const int64_t max_s = (K + 255) / 256;
-  if (s > max_s) s = max_s;
-  return (int)(s < 1 ? 1 : s);
-}
+// K columns per block (see head_mlp_*_kernel) and the resulting number of K slices; one choice for forward and backward
+inline int mlp_ks(int64_t R, int64_t D) { return (R > 32 && D > 256) ? 32 : 64; }
+inline int mlp_slices(int64_t R, int64_t D, int64_t K) { const int ks = mlp_ks(R, D); return (int)((K + ks - 1) / ks); }
 
 inline int drop_threshold(float p) {
   if (!(p > 0.f)) return 0;
@@ -475,9 +647,25 @@ inline int drop_threshold(float p) {
 
 extern "C" int mlg_head_conv_pool_supported(int64_t cin, int64_t c1, int64_t c2) { return cin == CIN && c1 == C1 && c2 == C2; }
 
+static int conv_pool_fill(ConvPoolP& P, const float* x_cl, const float* W1, const float* b1, const float* W2, const float* b2,
+                          const int32_t* drop_bits, float drop_p, int64_t B, int64_t H, int64_t W, int64_t kh, int64_t kw) {
+  memset(&P, 0, sizeof(P));
+  P.x = x_cl; P.W1 = W1; P.b1 = b1; P.W2 = W2; P.b2 = b2;
+  P.bits = drop_p > 0.f ? drop_bits : nullptr;
+  P.thr = drop_threshold(drop_p); P.keep_scale = 1.f / (1.f - drop_p);
+  P.B = (int)B; P.H = (int)H; P.W = (int)W; P.kh = (int)kh; P.kw = (int)kw; P.Ho = (int)(H / kh); P.Wo = (int)(W / kw);
+  MLG_CHECK_ARG(conv_pool_geometry(P), "mlg_head_conv_pool: one band (kh * W = %lld pixels) must fit a 255-pixel block", (long long)(kh * W));
+  MLG_CHECK_ARG((uintptr_t)x_cl % 16 == 0, "mlg_head_conv_pool: x_cl must be 16-byte aligned");
+  return MLG_OK;
+}
+
 extern "C" int64_t mlg_head_conv_pool_bwd_workspace_bytes(int64_t B, int64_t H, int64_t W, int64_t kh, int64_t kw) {
-  if (kh < 1 || kw < 1) return 0;
-  return (int64_t)conv_pool_blocks(B * H * W) * kGradFloats * 4;
+  if (kh < 1 || kw < 1 || kh * W > 255) return 0;
+  ConvPoolP P;
+  memset(&P, 0, sizeof(P));
+  P.B = (int)B; P.H = (int)H; P.W = (int)W; P.kh = (int)kh; P.kw = (int)kw; P.Ho = (int)(H / kh); P.Wo = (int)(W / kw);
+  conv_pool_geometry(P);
+  return (int64_t)conv_pool_blocks(P) * kGradFloats * 4;
 }
 
 extern "C" int mlg_head_conv_pool_fwd(const float* x_cl, const float* W1, const float* b1, const float* W2, const float* b2,
@@ -486,17 +674,16 @@ extern "C" int mlg_head_conv_pool_fwd(const float* x_cl, const float* W1, const 
   MLG_CHECK_ARG(x_cl && W1 && b1 && W2 && b2 && a0, "mlg_head_conv_pool_fwd: null pointer");
   MLG_CHECK_ARG(B >= 1 && H >= 1 && W >= 1 && kh >= 1 && kw >= 1 && kh <= H && kw <= W, "mlg_head_conv_pool_fwd: bad sizes");
   MLG_CHECK_ARG(drop_p >= 0.f && drop_p < 1.f, "mlg_head_conv_pool_fwd: dropout p must be in [0, 1)");
-  ConvPoolP P;
-  memset(&P, 0, sizeof(P));
-  P.x = x_cl; P.W1 = W1; P.b1 = b1; P.W2 = W2; P.b2 = b2; P.age = age;
-  P.bits = drop_p > 0.f ? drop_bits : nullptr;
   MLG_CHECK_ARG(drop_p == 0.f || drop_bits, "mlg_head_conv_pool_fwd: dropout needs drop_bits");
-  P.thr = drop_threshold(drop_p); P.keep_scale = 1.f / (1.f - drop_p);
-  P.B = (int)B; P.H = (int)H; P.W = (int)W; P.kh = (int)kh; P.kw = (int)kw; P.Ho = (int)(H / kh); P.Wo = (int)(W / kw);
+  ConvPoolP P;
+  if (int rc = conv_pool_fill(P, x_cl, W1, b1, W2, b2, drop_bits, drop_p, B, H, W, kh, kw)) return rc;
+  P.age = age;
   const long long F = (long long)C2 * P.Ho * P.Wo;
   MLG_CHECK_ARG(ld >= F + (age ? 1 : 0), "mlg_head_conv_pool_fwd: ld too small");
   P.ld = ld; P.a0 = a0;
-  head_conv_pool_fwd_kernel<<<conv_pool_blocks((long long)B * P.Ho * P.Wo), kThreads, 0, (cudaStream_t)stream>>>(P);
+  const size_t smem = conv_pool_smem(P, false);
+  MLG_CUDA(cudaFuncSetAttribute(head_conv_pool_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  head_conv_pool_fwd_kernel<<<conv_pool_blocks(P), kPix, smem, (cudaStream_t)stream>>>(P);
   MLG_CHECK_LAUNCH("mlg_head_conv_pool_fwd");
   return MLG_OK;
 }
@@ -508,25 +695,32 @@ extern "C" int mlg_head_conv_pool_bwd(const float* g_a0, int64_t ld, const float
   MLG_CHECK_ARG(g_a0 && x_cl && W1 && b1 && W2 && b2 && g_x_cl && g_W1 && g_b1 && g_W2 && g_b2 && workspace,
                 "mlg_head_conv_pool_bwd: null pointer");
   MLG_CHECK_ARG(B >= 1 && H >= 1 && W >= 1 && kh >= 1 && kw >= 1 && kh <= H && kw <= W, "mlg_head_conv_pool_bwd: bad sizes");
-  MLG_CHECK_ARG(workspace_bytes >= mlg_head_conv_pool_bwd_workspace_bytes(B, H, W, kh, kw), "mlg_head_conv_pool_bwd: workspace too small");
   MLG_CHECK_ARG(drop_p == 0.f || drop_bits, "mlg_head_conv_pool_bwd: dropout needs drop_bits");
   ConvPoolP P;
-  memset(&P, 0, sizeof(P));
-  P.x = x_cl; P.W1 = W1; P.b1 = b1; P.W2 = W2; P.b2 = b2;
-  P.bits = drop_p > 0.f ? drop_bits : nullptr;
-  P.thr = drop_threshold(drop_p); P.keep_scale = 1.f / (1.f - drop_p);
-  P.B = (int)B; P.H = (int)H; P.W = (int)W; P.kh = (int)kh; P.kw = (int)kw; P.Ho = (int)(H / kh); P.Wo = (int)(W / kw);
+  if (int rc = conv_pool_fill(P, x_cl, W1, b1, W2, b2, drop_bits, drop_p, B, H, W, kh, kw)) return rc;
+  MLG_CHECK_ARG(workspace_bytes >= mlg_head_conv_pool_bwd_workspace_bytes(B, H, W, kh, kw), "mlg_head_conv_pool_bwd: workspace too small");
+  MLG_CHECK_ARG((uintptr_t)g_x_cl % 16 == 0, "mlg_head_conv_pool_bwd: g_x_cl must be 16-byte aligned");
   P.ld = ld; P.g_a0 = g_a0; P.g_x = g_x_cl; P.partial = (float*)workspace;
-  const int blocks = conv_pool_blocks(B * H * W);
-  head_conv_pool_bwd_kernel<<<blocks, kThreads, 0, (cudaStream_t)stream>>>(P);
+  const int blocks = conv_pool_blocks(P);
+  const size_t smem = conv_pool_smem(P, true);
+  MLG_CHECK_ARG(smem <= 227 * 1024, "mlg_head_conv_pool_bwd: %lld windows per block do not fit shared memory", (long long)P.NB * P.Wo);
+  cudaStream_t st = (cudaStream_t)stream;
+  MLG_CUDA(cudaFuncSetAttribute(head_conv_pool_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  head_conv_pool_bwd_kernel<<<blocks, kPix, smem, st>>>(P);
   MLG_CHECK_LAUNCH("mlg_head_conv_pool_bwd");
-  head_conv_reduce_kernel<<<mlg_ceil_div(kGradFloats, 128), 128, 0, (cudaStream_t)stream>>>(P.partial, blocks, g_W1, g_b1, g_W2, g_b2);
+  if (P.Ho * P.kh < P.H) {
+    const long long n4 = (long long)B * (P.H - P.Ho * P.kh) * P.W * (CIN / 4);
+    head_conv_tail_zero_kernel<<<(unsigned)((n4 + 255) / 256 > 1024 ? 1024 : (n4 + 255) / 256), 256, 0, st>>>(
+        reinterpret_cast<float4*>(g_x_cl), (int)B, P.H, P.W, P.Ho * P.kh);
+    MLG_CHECK_LAUNCH("mlg_head_conv_pool_bwd(tail)");
+  }
+  head_conv_reduce_kernel<<<mlg_ceil_div(kGradFloats, 128), 128, 0, st>>>(P.partial, blocks, g_W1, g_b1, g_W2, g_b2);
   MLG_CHECK_LAUNCH("mlg_head_conv_pool_bwd(reduce)");
   return MLG_OK;
 }
 
 extern "C" int64_t mlg_head_mlp_workspace_bytes(int64_t R, int64_t D, int64_t K) {
-  return ((int64_t)mlp_slices(D, K) * R * D + R + 4) * 4;
+  return ((int64_t)mlp_slices(R, D, K) * R * D + R + 4) * 4;
 }
 
 extern "C" int mlg_head_mlp_fwd(const float* a0, int64_t ld_a, const float* W0, const float* b0, const float* W3,
@@ -534,7 +728,8 @@ extern "C" int mlg_head_mlp_fwd(const float* a0, int64_t ld_a, const float* W0, 
                                 int64_t R, int64_t D, int64_t K, float* a1, float* pred, float* loss, void* workspace,
                                 int64_t workspace_bytes, void* stream) {
   MLG_CHECK_ARG(a0 && W0 && b0 && W3 && b3 && a1 && pred && workspace, "mlg_head_mlp_fwd: null pointer");
-  MLG_CHECK_ARG(R >= 1 && R <= 64 && D >= 1 && K >= 1 && ld_a >= K, "mlg_head_mlp_fwd: need 1 <= rows <= 64 (got %lld)", (long long)R);
+  MLG_CHECK_ARG(R >= 1 && R <= 64 && D >= 32 && D % 32 == 0 && D <= 512 && K >= 1 && ld_a >= K,
+                "mlg_head_mlp_fwd: need 1 <= rows <= 64 (got %lld), D a multiple of 32 up to 512 (got %lld)", (long long)R, (long long)D);
   MLG_CHECK_ARG(!y || loss, "mlg_head_mlp_fwd: y given without a loss output");
   MLG_CHECK_ARG(drop_p >= 0.f && drop_p < 1.f && (drop_p == 0.f || drop_bits), "mlg_head_mlp_fwd: bad dropout arguments");
   MLG_CHECK_ARG(workspace_bytes >= mlg_head_mlp_workspace_bytes(R, D, K), "mlg_head_mlp_fwd: workspace too small");
@@ -545,19 +740,23 @@ extern "C" int mlg_head_mlp_fwd(const float* a0, int64_t ld_a, const float* W0, 
   P.thr = drop_threshold(drop_p); P.keep_scale = 1.f / (1.f - drop_p);
   P.y = y; P.weight = weight;
   P.R = (int)R; P.D = (int)D; P.K = (int)K; P.ld_a = ld_a;
-  P.slices = mlp_slices(D, K);
-  int kps = (int)((K + P.slices - 1) / P.slices);
-  P.kps = ((kps + 31) / 32) * 32;
+  P.slices = mlp_slices(R, D, K);
   P.partial = (float*)workspace;
   P.rowloss = P.partial + (size_t)P.slices * R * D;
   P.counter = (unsigned*)(P.rowloss + R);
   P.a1 = a1; P.pred = pred; P.loss = loss;
   cudaStream_t st = (cudaStream_t)stream;
-  dim3 grid((unsigned)((D + kWarps - 1) / kWarps), (unsigned)P.slices);
-  if (R <= 8) head_mlp_partial_kernel<8><<<grid, kThreads, 0, st>>>(P);
-  else if (R <= 16) head_mlp_partial_kernel<16><<<grid, kThreads, 0, st>>>(P);
-  else if (R <= 32) head_mlp_partial_kernel<32><<<grid, kThreads, 0, st>>>(P);
-  else head_mlp_partial_kernel<64><<<grid, kThreads, 0, st>>>(P);
+  const int RT = R <= 32 ? 32 : 64, ks = mlp_ks(R, D);
+  const size_t smem = ((size_t)D * (ks + 1) + (size_t)ks * RT) * 4;
+#define MLG_MLP_F(RR, KK)                                                                                                    \
+  do {                                                                                                                       \
+    MLG_CUDA(cudaFuncSetAttribute(head_mlp_partial_kernel<RR, KK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    head_mlp_partial_kernel<RR, KK><<<P.slices, (unsigned)D, smem, st>>>(P);                                                 \
+  } while (0)
+  if (RT == 32) MLG_MLP_F(32, 64);
+  else if (ks == 64) MLG_MLP_F(64, 64);
+  else MLG_MLP_F(64, 32);
+#undef MLG_MLP_F
   MLG_CHECK_LAUNCH("mlg_head_mlp_fwd(partial)");
   head_mlp_finish_kernel<<<(unsigned)R, kThreads, 0, st>>>(P);
   MLG_CHECK_LAUNCH("mlg_head_mlp_fwd(finish)");
@@ -580,17 +779,20 @@ extern "C" int mlg_head_mlp_bwd(const float* g_pred, const float* g_loss, const 
   P.R = (int)R; P.D = (int)D; P.K = (int)K; P.ld_a = ld_a; P.ld_g = ld_g;
   P.keep_scale = 1.f / (1.f - drop_p);
   P.g_a0 = g_a0; P.g_W0 = g_W0; P.g_b0 = g_b0; P.g_W3 = g_W3; P.g_b3 = g_b3;
-  const int nwarps = (int)(D / 32);
-  const size_t smem = ((size_t)R * D + 2 * R) * 4;
+  const int RT = R <= 32 ? 32 : 64, ks = mlp_ks(R, D);
+  const size_t smem = ((size_t)D * (ks + 1) + (size_t)ks * RT + (size_t)RT * D + 2 * RT) * 4;
+  MLG_CHECK_ARG(smem <= 227 * 1024, "mlg_head_mlp_bwd: %lld rows x %lld hidden units exceed shared memory", (long long)R, (long long)D);
   cudaStream_t st = (cudaStream_t)stream;
-  const unsigned blocks = (unsigned)((K + 31) / 32);
-  if (R <= 32) {
-    MLG_CUDA(cudaFuncSetAttribute(head_mlp_bwd_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    head_mlp_bwd_kernel<32><<<blocks, nwarps * 32, smem, st>>>(P);
-  } else {
-    MLG_CUDA(cudaFuncSetAttribute(head_mlp_bwd_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    head_mlp_bwd_kernel<64><<<blocks, nwarps * 32, smem, st>>>(P);
-  }
+  const unsigned blocks = (unsigned)mlp_slices(R, D, K);
+#define MLG_MLP_B(RR, KK)                                                                                                \
+  do {                                                                                                                   \
+    MLG_CUDA(cudaFuncSetAttribute(head_mlp_bwd_kernel<RR, KK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    head_mlp_bwd_kernel<RR, KK><<<blocks, (unsigned)D, smem, st>>>(P);                                                   \
+  } while (0)
+  if (RT == 32) MLG_MLP_B(32, 64);
+  else if (ks == 64) MLG_MLP_B(64, 64);
+  else MLG_MLP_B(64, 32);
+#undef MLG_MLP_B
   MLG_CHECK_LAUNCH("mlg_head_mlp_bwd");
   return MLG_OK;
 }

@@ -564,7 +564,7 @@ class SageLayer(torch.autograd.Function):
             # the consumer does not pre-mask our output gradient: keep the sign bits of y (8 bytes per row and replica) so that
             # the backward kernel applies LeakyReLU' without re-reading y
             mbits = None
-            if RANK1_SIGN_BITS and RANK1_SELF_MASK and cout == 64 and not out_premasked and torch.is_grad_enabled():
+            if RANK1_SIGN_BITS and RANK1_SELF_MASK and cout == 64 and not out_premasked and any(ctx.needs_input_grad):
                 mbits = torch.empty(n1 * topo.replicas, dtype=torch.int64, device=xd.device)
             with torch.cuda.device(xd.device), _cabi.span("sage_rank1_fwd", nbytes):
                 _cabi.check(L.mlg_sage_rank1_fwd(

@@ -346,8 +346,10 @@ class MultilevelGNN(nn.Module):
                 wr = wr if (wr.dtype == torch.float32 and wr.is_contiguous()) else wr.float().contiguous()
                 mk = mk if (mk.dtype == torch.float32 and mk.is_contiguous()) else mk.float().contiguous()
                 with torch.cuda.device(w.device):
+                    ws = torch.empty(nseg, dtype=torch.float32, device=w.device)
                     _cabi.check(_cabi.lib().mlg_pca_indep_loss(_cabi.fptr(wr), _cabi.fptr(mk), _cabi.iptr(segptr), nseg, P,
-                                                              _cabi.fptr(out), _cabi.stream_ptr()), "mlg_pca_indep_loss")
+                                                              _cabi.fptr(out), _cabi.fptr(ws), _cabi.stream_ptr()),
+                                "mlg_pca_indep_loss")
                 return loss + out[0]
             if P > 1:
                 a, b = w[:, :P - 1], w[:, P - 1:P]

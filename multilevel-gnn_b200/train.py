@@ -232,13 +232,16 @@ def peer_update_available(world, device):
 
 
 class _PendingLoss:
-    """A loss value on its way to pinned host memory (Trainer.loss_to_host)."""
+    """A loss value on its way to pinned host memory (Trainer.loss_to_host); slot[1] != 0: a keyless batch uploaded after
+    capture() did not match the captured topology."""
 
     def __init__(self, slot, event):
         self.slot, self.event = slot, event
 
     def get(self):
         self.event.synchronize()
+        if float(self.slot[1]) != 0.0:
+            raise RuntimeError("Trainer: a batch uploaded after capture() carried a different topology than the captured graph")
         return float(self.slot[0])
 
 
@@ -332,6 +335,10 @@ class Trainer:
         loss, bwd) -> the NCCL all-reduce issued eagerly on the same stream -> graph B (Adam); the collective stays
         outside the capture so that NCCL's own stream/event management never interferes with it."""
         self.static_batch = batch
+        # reference copies of the topology fields: keyless batches (full upload) are verified against them on the device
+        self._topo_ref = {k: getattr(batch, k).clone() for k in self.STATIC_TOPOLOGY_FIELDS
+                          if torch.is_tensor(getattr(batch, k, None))}
+        self._topo_bad = torch.zeros((), dtype=torch.bool, device=self.flat.device)
         cur = torch.cuda.current_stream()
         side = torch.cuda.Stream()
         side.wait_stream(cur)
@@ -379,20 +386,40 @@ class Trainer:
 
     def _check_topology(self, host_batch):
         """The CSR, pooling layout, degree tables and visiting orders are built in the warm-up steps and BAKED into the
-        captured graph: a batch with another edge list / match table would silently train on the stale topology.  Batches
-        must therefore carry the ``topology_key`` the graph was captured with (loaders: data.TopologyLoader)."""
+        captured graph: a batch with another edge list / match table would silently train on the stale topology.  A keyed
+        batch (data.collate / data.TopologyLoader) must carry the key the graph was captured with.  A batch WITHOUT a key
+        (the reference's loader: every batch re-sends its own copy of the topology, train.py:42) is accepted, uploaded in
+        full, and its topology fields are compared ON THE DEVICE with the captured ones; a mismatch raises when the host
+        next reads a loss (``loss_to_host(...).get()``) or calls ``check_topology_flag()``."""
         key = getattr(self.static_batch, "topology_key", None)
         other = getattr(host_batch, "topology_key", None)
-        if key is None or other != key:
+        if other is not None and other != key:
             raise ValueError("Trainer: the topology is frozen at capture(); this batch has topology_key=%r, the captured "
                              "graph %r -- re-capture for a new topology, or step eagerly" % (other, key))
+
+    def _verify_uploaded_topology(self, fields):
+        """After a full upload into the static buffers: flag |= any(static != captured) per topology field (device only)."""
+        ref = getattr(self, "_topo_ref", None)
+        if ref is None:
+            return
+        for k in fields:
+            if k in ref:
+                self._topo_bad.logical_or_((getattr(self.static_batch, k) != ref[k]).any())
+
+    def check_topology_flag(self):
+        """Host-side check (one sync) that no keyless batch with a different topology was fed to the captured graph."""
+        if getattr(self, "_topo_bad", None) is not None and bool(self._topo_bad.item()):
+            raise RuntimeError("Trainer: a batch uploaded after capture() carried a different edge list / pooling layout than "
+                               "the captured graph was built for (topology is frozen at capture())")
 
     def load_batch(self, host_batch):
         """Copy a (pinned) host batch into the captured graph's static device buffers (async H2D).  Only per-step
         fields are copied: the topology fields are frozen at capture()."""
         self._check_topology(host_batch)
-        for k in self._step_fields(host_batch):
+        fields = self._step_fields(host_batch)
+        for k in fields:
             getattr(self.static_batch, k).copy_(getattr(host_batch, k), non_blocking=True)
+        self._verify_uploaded_topology(fields)
 
     def prefetch(self, host_batch):
         """Start the H2D copy of the NEXT batch on a side stream into staging buffers while the current step's
@@ -400,7 +427,9 @@ class Trainer:
         and replays.  This is the double buffering the reference's synchronous ``batch.to(device)``
         (train.py:42) lacks."""
         self._check_topology(host_batch)
-        if self._copy_stream is None:
+        if self._copy_stream is None or set(self._staging) != set(self._step_fields(host_batch)):
+            if self._copy_stream is not None:
+                torch.cuda.current_stream().synchronize()        # switching keyed <-> keyless batches: new staging set
             self._copy_stream = torch.cuda.Stream()
             self._staging = {k: torch.empty_like(getattr(self.static_batch, k)) for k in self._step_fields(host_batch)}
             self._staged = torch.cuda.Event()
@@ -421,6 +450,7 @@ class Trainer:
         for k, v in self._staging.items():
             getattr(self.static_batch, k).copy_(v, non_blocking=True)
         self._consumed.record()
+        self._verify_uploaded_topology(self._staging)
         return self._replay()
 
     def loss_to_host(self, loss):
@@ -428,12 +458,14 @@ class Trainer:
         THAT copy only.  train.py:62 reads ``loss.item()`` right after the step, which idles the GPU for a launch latency
         every step; reading step i's loss while step i+1 runs gives the host the same number one step later."""
         if getattr(self, "_loss_ring", None) is None:
-            self._loss_ring = [torch.empty(1, dtype=torch.float32).pin_memory() for _ in range(4)]
+            self._loss_ring = [torch.zeros(2, dtype=torch.float32).pin_memory() for _ in range(4)]
             self._loss_events = [torch.cuda.Event() for _ in range(4)]
             self._loss_slot = 0
         i = self._loss_slot
         self._loss_slot = (i + 1) % len(self._loss_ring)
-        self._loss_ring[i].copy_(loss.reshape(1), non_blocking=True)
+        self._loss_ring[i][:1].copy_(loss.reshape(1), non_blocking=True)
+        if getattr(self, "_topo_bad", None) is not None:
+            self._loss_ring[i][1:].copy_(self._topo_bad.reshape(1), non_blocking=True)
         self._loss_events[i].record()
         return _PendingLoss(self._loss_ring[i], self._loss_events[i])
 

@@ -16,7 +16,18 @@ import os
 import sys
 import types
 
-REF_ROOT = os.environ.get("MLG_REFERENCE_ROOT", "/root/reference")
+_STAGED = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+
+
+def _default_root():
+    """/root/reference in the build container; on the GPU box the copy oracle/make_ref.py staged under oracle/_ref/."""
+    for cand in (os.environ.get("MLG_REFERENCE_ROOT"), "/root/reference", _STAGED):
+        if cand and os.path.isdir(os.path.join(cand, "models", "gcn_lib")):
+            return cand
+    return "/root/reference"
+
+
+REF_ROOT = _default_root()
 
 
 def available():

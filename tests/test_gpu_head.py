@@ -77,16 +77,20 @@ def test_head_conv_pool_dropout_uses_torch_generator(mlg):
     a0 = Fn.HeadConvPool.apply(feat, W1, b1, W2, b2, None, kh, kw, p, True)
     torch.manual_seed(77)
     bits = torch.empty(a0.numel(), dtype=torch.int32, device=DEV).random_()
-    mask = (bits >= int(p * 2 ** 31)).float()
+    mask = (bits >= int(p * 2 ** 31)).double().cpu()
     assert 0.70 < float(mask.mean()) < 0.80
-    ref = _ref_conv_pool(feat, W1, b1, W2, b2, None, kh, kw, mask=mask, p=p)
-    assert_close(a0, ref, what="dropout fwd")
-    Rw = torch.randn_like(a0)
-    g1 = torch.autograd.grad((a0 * Rw).sum(), x_cl, retain_graph=True)[0]
-    g2 = torch.autograd.grad((ref * Rw).sum(), x_cl)[0]
-    assert_close(g1, g2, rtol=1e-4, atol=2e-6, what="dropout bwd")
+    # fp64 reference on the CPU (a GPU conv2d reference would run in TF32)
+    xr = x_cl.detach().cpu().double().requires_grad_()
+    wr = [t.detach().cpu().double() for t in (W1, b1, W2, b2)]
+    ref = _ref_conv_pool(xr.permute(0, 3, 1, 2), wr[0], wr[1], wr[2], wr[3], None, kh, kw, mask=mask, p=p)
+    assert_close(a0, ref.float(), what="dropout fwd")
+    Rw = torch.randn(a0.shape, generator=g)
+    g1 = torch.autograd.grad((a0 * Rw.to(DEV)).sum(), x_cl)[0]
+    g2 = torch.autograd.grad((ref * Rw.double()).sum(), xr)[0]
+    assert_close(g1, g2.float(), rtol=1e-4, atol=2e-6, what="dropout bwd")
     a_eval = Fn.HeadConvPool.apply(feat, W1, b1, W2, b2, None, kh, kw, p, False)
-    assert_close(a_eval, _ref_conv_pool(feat, W1, b1, W2, b2, None, kh, kw), what="eval: no dropout")
+    ref_eval = _ref_conv_pool(xr.permute(0, 3, 1, 2), wr[0], wr[1], wr[2], wr[3], None, kh, kw)
+    assert_close(a_eval, ref_eval.float(), what="eval: no dropout")
 
 
 @pytest.mark.parametrize("R,K,D", [(32, 6913, 256), (64, 1000, 512), (3, 77, 32), (17, 300, 64)])
@@ -112,7 +116,7 @@ def test_head_mlp_and_loss_match_torch(mlg, R, K, D):
         assert_close(pred, pr.float(), what="pred")
         assert_close(bce, lr.float(), what="bce")
         gs = torch.autograd.grad((pred * Rw.to(DEV)).sum() + 3.0 * bce, dev)
-        gr = torch.autograd.grad((pr * Rw.double()).sum() + 3.0 * lr, ref_in)
+        gr = torch.autograd.grad((pr * Rw.double()).sum() + 3.0 * lr, ref_in, retain_graph=True)
         for name, a, c in zip(("g_a0", "g_W0", "g_b0", "g_W3", "g_b3"), gs, gr):
             assert_close(a, c.float(), rtol=1e-4, atol=2e-6, what="%s (weight=%s)" % (name, use_w))
         # loss only / pred only
@@ -139,15 +143,16 @@ def test_head_mlp_dropout(mlg):
     pred, _ = Fn.HeadMLP.apply(a0, W0, b0, W3, b3, p, True, None, None)
     torch.manual_seed(9)
     bits = torch.empty(R * D, dtype=torch.int32, device=DEV).random_()
-    mask = (bits >= int(p * 2 ** 31)).float().view(R, D)
-    hid = F.relu(F.linear(a0, W0, b0)) * mask / (1 - p)
-    ref = F.softmax(F.linear(hid, W3, b3), dim=1)
-    assert_close(pred, ref, what="mlp dropout pred")
-    Rw = torch.randn_like(pred)
-    g1 = torch.autograd.grad((pred * Rw).sum(), [a0, W0])
-    g2 = torch.autograd.grad((ref * Rw).sum(), [a0, W0])
-    assert_close(g1[0], g2[0], rtol=1e-4, atol=2e-6, what="mlp dropout g_a0")
-    assert_close(g1[1], g2[1], rtol=1e-4, atol=2e-6, what="mlp dropout g_W0")
+    mask = (bits >= int(p * 2 ** 31)).double().view(R, D).cpu()
+    ar, wr = a0.detach().cpu().double().requires_grad_(), W0.detach().cpu().double().requires_grad_()
+    hid = F.relu(F.linear(ar, wr, b0.cpu().double())) * mask / (1 - p)
+    ref = F.softmax(F.linear(hid, W3.cpu().double(), b3.cpu().double()), dim=1)
+    assert_close(pred, ref.float(), what="mlp dropout pred")
+    Rw = torch.randn(pred.shape, generator=g)
+    g1 = torch.autograd.grad((pred * Rw.to(DEV)).sum(), [a0, W0])
+    g2 = torch.autograd.grad((ref * Rw.double()).sum(), [ar, wr])
+    assert_close(g1[0], g2[0].float(), rtol=1e-4, atol=2e-6, what="mlp dropout g_a0")
+    assert_close(g1[1], g2[1].float(), rtol=1e-4, atol=2e-6, what="mlp dropout g_W0")
 
 
 @pytest.mark.parametrize("cfg", ["gbm", "kirc"])

@@ -80,6 +80,6 @@ def test_vae_encoder_and_forward_shapes(mlg):
     assert out["pred_x"].shape == (2, 25015) and out["embedding"].shape == (2, 438, 2 * 96)
     assert bool(torch.isfinite(out["pred_x"]).all())
     pred, feat, l, e, _ = model.train_step(b)
-    assert pred.shape == (2, 2) and feat.shape == (2, 32, 146, 3)
+    assert pred.shape == (2, 2) and feat.shape == (2, 96, 146, 3)      # mu half of the latent: C*P channels (vae.py:97)
     (pred.sum() + l + e + out["pred_x"].square().mean()).backward()
     assert model.node_embedding.grad is not None and bool(torch.isfinite(model.node_embedding.grad).all())

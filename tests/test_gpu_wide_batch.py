@@ -76,6 +76,7 @@ def test_pca_indep_kernel_matches_library_expression(mlg, P):
     segptr = torch.searchsorted(idx, torch.arange(nseg + 1)).to(torch.int32).to(DEV)
     out = torch.empty(1, device=DEV)
     wd, md = w.to(DEV).contiguous(), mask.to(DEV).contiguous()
+    ws = torch.empty(nseg, dtype=torch.float32, device=DEV)
     _cabi.check(_cabi.lib().mlg_pca_indep_loss(_cabi.fptr(wd), _cabi.fptr(md), _cabi.iptr(segptr), nseg, P, _cabi.fptr(out),
-                                              _cabi.stream_ptr()), "mlg_pca_indep_loss")
+                                              _cabi.fptr(ws), _cabi.stream_ptr()), "mlg_pca_indep_loss")
     assert_close(out.cpu().double(), ref.reshape(1), rtol=1e-4, atol=1e-7, what="pca_indep P=%d" % P)
