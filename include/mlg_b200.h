@@ -179,11 +179,22 @@ int mlg_sage_rank1_bwd(const float* gz, int64_t ld_g, const float* xs, const int
  * (single graph, idx = by-source position -> forward position).  h must hold rowptr[n_rows] rows of C floats.
  * y != NULL: gz is dL/dy of the layer's LeakyReLU(slope) output y (same layout as gz) and the kernel multiplies by the
  * activation derivative while loading (no separate activation-backward pass); mask_bits != NULL (C == 64): the same
- * from the sign bits mlg_sage_rank1_fwd wrote (y is then not read). */
+ * from the sign bits mlg_sage_rank1_fwd wrote (y is then not read).  xs_transposed != 0: xs is [n_rows, replicas]. */
 int mlg_sage_rank1_bwd_rows_supported(int64_t C);
-int mlg_sage_rank1_bwd_rows(const float* gz, int64_t ld_g, const float* y, const uint64_t* mask_bits, float slope, const float* xs, const int32_t* rowptr, const int32_t* idx,
+int mlg_sage_rank1_bwd_rows(const float* gz, int64_t ld_g, const float* y, const uint64_t* mask_bits, float slope, const float* xs, int xs_transposed, const int32_t* rowptr, const int32_t* idx,
                             const float* val, const int32_t* order, int64_t n_rows, int64_t C, int64_t replicas, float* h,
                             float* g_self, int64_t ld_self, float* g_bias_rows, void* stream);
+
+/* The forward pass with one WARP per gene for all replicas (C == 32 or 64): the neighbour's table row and its replica values
+ * are loaded once per CSR entry.  xs_t [n_rows, replicas]: the node values TRANSPOSED (mlg_transpose_bn of xs [replicas,
+ * n_rows]); the same matrix serves mlg_sage_rank1_bwd_rows (xs_transposed = 1).  Other arguments as mlg_sage_rank1_fwd;
+ * tables / out 8-byte aligned with even leading dimensions. */
+int mlg_transpose_bn(const float* xs, int64_t B, int64_t n, float* xs_t, void* stream);
+int mlg_sage_rank1_fwd_rows_supported(int64_t C);
+int mlg_sage_rank1_fwd_rows(const float* xs_t, const float* e_self, int64_t ld_self, const float* e_nbr, int64_t ld_nbr,
+                            const int32_t* rowptr, const int32_t* idx, const float* val, const int32_t* order, int64_t n_rows,
+                            int64_t C, int64_t replicas, const float* bias, float slope, float* out, int64_t ld_out,
+                            uint64_t* mask_bits, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Tall-skinny transposed product: out[M,K] = A[rows,M]^T * X[rows,K], colsum[M] = sum_r A[r,:] (NULL ok).

@@ -621,6 +621,7 @@ struct R1B {
   float* g_bias_rows;
   unsigned ld_g, ld_self;
   int n, B;
+  int xs_t;            // xs is the transposed node-value matrix [n][B] (one coalesced load per entry) instead of [B][n]
 };
 
 #ifndef MLG_R1B_MINB
@@ -675,10 +676,12 @@ __global__ void __launch_bounds__(kThreads, MLG_R1B_MINB) sage_rank1_bwd_rows_ke
           for (int k = 0; k < CPL; ++k) g[k][b8 + b] *= yv[k][b] > 0.f ? 1.f : P.slope;
       }
     }
-    const float* xp = P.xs + (size_t)(rb0 + min(lane, nb - 1)) * P.n;   // lane b reads replica rb0+b (clamped; masked below)
+    // lane b reads replica rb0+b (clamped; masked below): element (replica, node) = xp[node * xstride]
+    const float* xp = P.xs_t ? P.xs + rb0 + min(lane, nb - 1) : P.xs + (size_t)(rb0 + min(lane, nb - 1)) * P.n;
+    const size_t xstride = P.xs_t ? (size_t)P.B : 1;
     const float lane_live = lane < nb ? 1.f : 0.f;
     {
-      const float xv = __ldg(xp + row) * lane_live;
+      const float xv = __ldg(xp + row * xstride) * lane_live;
       float e1[CPL], gb[CPL];
 #pragma unroll
       for (int k = 0; k < CPL; ++k) e1[k] = gb[k] = 0.f;
@@ -709,7 +712,7 @@ __global__ void __launch_bounds__(kThreads, MLG_R1B_MINB) sage_rank1_bwd_rows_ke
 #pragma unroll
         for (int u = 0; u < EU; ++u) {
           const unsigned s = __shfl_sync(0xffffffffu, my_idx, min(j + u, cnt - 1));
-          xv[u] = __ldg(xp + s) * lane_live;
+          xv[u] = __ldg(xp + s * xstride) * lane_live;
         }
 #pragma unroll
         for (int u = 0; u < EU; ++u) {
@@ -973,7 +976,7 @@ extern "C" int mlg_sage_rank1_bwd(const float* gz, int64_t ld_g, const float* xs
 
 extern "C" int mlg_sage_rank1_bwd_rows_supported(int64_t C) { return C == 32 || C == 64; }
 
-extern "C" int mlg_sage_rank1_bwd_rows(const float* gz, int64_t ld_g, const float* y, const uint64_t* mask_bits, float slope, const float* xs, const int32_t* rowptr,
+extern "C" int mlg_sage_rank1_bwd_rows(const float* gz, int64_t ld_g, const float* y, const uint64_t* mask_bits, float slope, const float* xs, int xs_transposed, const int32_t* rowptr,
                                        const int32_t* idx, const float* val, const int32_t* order, int64_t n_rows,
                                        int64_t C, int64_t replicas, float* h, float* g_self, int64_t ld_self,
                                        float* g_bias_rows, void* stream) {
@@ -987,6 +990,7 @@ extern "C" int mlg_sage_rank1_bwd_rows(const float* gz, int64_t ld_g, const floa
   P.mbits = reinterpret_cast<const unsigned long long*>(mask_bits);
   P.gz = gz; P.y = y; P.slope = slope; P.xs = xs; P.rowptr = rowptr; P.idx = idx; P.val = val; P.order = order; P.h = h; P.g_self = g_self;
   P.g_bias_rows = g_bias_rows; P.ld_g = (unsigned)ld_g; P.ld_self = (unsigned)ld_self; P.n = (int)n_rows; P.B = (int)replicas;
+  P.xs_t = xs_transposed;
   const unsigned grid = (unsigned)mlg_ceil_div(n_rows, kThreads / 32);
   cudaStream_t st = (cudaStream_t)stream;
   if (C == 64) sage_rank1_bwd_rows_kernel<2><<<grid, kThreads, 0, st>>>(P);

@@ -18,6 +18,8 @@
 //                        accumulates the four parameter gradients in registers; fixed-order two-level reduction.
 // Dropout masks come from caller-provided random int32 words (torch's generator: graph-safe, torch.manual_seed applies);
 // element kept iff bits >= p * 2^31.  Everything is fp32 FMA with fixed summation orders (deterministic).
+#include <type_traits>
+
 #include "common.cuh"
 #include "../../include/mlg_b200.h"
 
@@ -404,15 +406,41 @@ template <int RT, int KSL>
 __device__ __forceinline__ void stage_slices(const float* W0, int D, int K, const float* a0, long long ld_a, int R, int k0,
                                              float* Ws, float* As) {
   constexpr int WLD = KSL + 1;
+  constexpr int RU = 8;     // rows whose loads are in flight together (r02 ncu: one row at a time = 25 us of pure latency)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-  for (int n = warp; n < D; n += nwarps) {
-    const float* row = W0 + (size_t)n * K + k0;
+  for (int n0 = warp; n0 < D; n0 += nwarps * RU) {
+    float v[RU][KSL / 32];
 #pragma unroll
-    for (int q = 0; q < KSL; q += 32) Ws[n * WLD + lane + q] = (k0 + lane + q < K) ? __ldg(row + lane + q) : 0.f;
+    for (int u = 0; u < RU; ++u) {
+      const int n = n0 + u * nwarps;
+      const float* row = W0 + (size_t)(n < D ? n : 0) * K + k0;
+#pragma unroll
+      for (int q = 0; q < KSL / 32; ++q) v[u][q] = (n < D && k0 + lane + 32 * q < K) ? __ldg(row + lane + 32 * q) : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < RU; ++u) {
+      const int n = n0 + u * nwarps;
+      if (n < D) {
+#pragma unroll
+        for (int q = 0; q < KSL / 32; ++q) Ws[n * WLD + lane + 32 * q] = v[u][q];
+      }
+    }
   }
-  for (int t = threadIdx.x; t < RT * KSL; t += blockDim.x) {
-    const int r = t / KSL, k = t - r * KSL;
-    As[k * RT + r] = (r < R && k0 + k < K) ? __ldg(a0 + (size_t)r * ld_a + k0 + k) : 0.f;
+  // a0 slice transposed to [k][r]: thread -> (k = t % KSL, rows r = t / KSL, + step), loads batched like above
+  const int kk = threadIdx.x % KSL, rstep = blockDim.x / KSL;
+  {
+    float v[RT / 4];     // blockDim >= 4 * KSL  =>  rstep >= 4  =>  at most RT / 4 rows per thread
+    const int rfirst = threadIdx.x / KSL;
+#pragma unroll
+    for (int c = 0; c < RT / 4; ++c) {
+      const int r = rfirst + c * rstep;
+      v[c] = (r < R && k0 + kk < K) ? __ldg(a0 + (size_t)r * ld_a + k0 + kk) : 0.f;
+    }
+#pragma unroll
+    for (int c = 0; c < RT / 4; ++c) {
+      const int r = rfirst + c * rstep;
+      if (r < RT) As[kk * RT + r] = v[c];
+    }
   }
 }
 
@@ -426,6 +454,7 @@ __global__ void __launch_bounds__(512) head_mlp_partial_kernel(const MlpP P) {
   if (blockIdx.x == 0 && threadIdx.x == 0) *P.counter = 0u;   // the finish kernel's arrival counter
   stage_slices<RT, KSL>(P.W0, P.D, P.K, P.a0, P.ld_a, P.R, k0, Ws, As);
   __syncthreads();
+  if (n >= P.D) return;     // helper threads of a narrow layer (blockDim = max(D, 256)) only stage
   float acc[RT];
 #pragma unroll
   for (int r = 0; r < RT; ++r) acc[r] = 0.f;
@@ -455,18 +484,22 @@ __global__ void __launch_bounds__(kThreads) head_mlp_finish_kernel(const MlpP P)
   const int r = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float z0 = 0.f, z1 = 0.f;
   for (int n = threadIdx.x; n < P.D; n += kThreads) {
-    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;     // four independent chains, combined in a fixed order
+    // eight loads in flight, eight independent chains combined in a fixed order
+    float c8[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) c8[q] = 0.f;
     const float* pp = P.partial + (size_t)r * P.D + n;
     const size_t st = (size_t)P.R * P.D;
     int g = 0;
-    for (; g + 4 <= P.slices; g += 4) {
-      s0 += pp[(size_t)g * st];
-      s1 += pp[(size_t)(g + 1) * st];
-      s2 += pp[(size_t)(g + 2) * st];
-      s3 += pp[(size_t)(g + 3) * st];
+    for (; g + 8 <= P.slices; g += 8) {
+      float v[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) v[q] = pp[(size_t)(g + q) * st];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) c8[q] += v[q];
     }
-    for (; g < P.slices; ++g) s0 += pp[(size_t)g * st];
-    float s = (s0 + s1) + (s2 + s3);
+    for (; g < P.slices; ++g) c8[0] += pp[(size_t)g * st];
+    float s = ((c8[0] + c8[1]) + (c8[2] + c8[3])) + ((c8[4] + c8[5]) + (c8[6] + c8[7]));
     s += __ldg(P.b0 + n);
     s = fmaxf(s, 0.f);
     s = drop_keep(P.bits, (size_t)r * P.D + n, P.thr) ? s * P.keep_scale : 0.f;
@@ -556,7 +589,10 @@ __global__ void __launch_bounds__(512) head_mlp_bwd_kernel(const MlpBwdP P) {
   __syncthreads();
   // ---- this thread's hidden unit: dL/dz1[r][n] for every sample, in registers and in shared memory ----
   float gz[RT];
-  {
+  const bool unit = n < D;      // helper threads of a narrow layer (blockDim = max(D, 256)) own no hidden unit
+#pragma unroll
+  for (int r = 0; r < RT; ++r) gz[r] = 0.f;
+  if (unit) {
     const float w30 = __ldg(P.W3 + n), w31 = __ldg(P.W3 + D + n);
     float a1v[RT];
 #pragma unroll
@@ -588,16 +624,27 @@ __global__ void __launch_bounds__(512) head_mlp_bwd_kernel(const MlpBwdP P) {
   // ---- input gradient slice: g_a0[r][k0 + k] = sum_n dz1[r][n] W0[n][k0 + k]; thread = (k, group of rows) ----
   if (P.g_a0) {
     const int k = threadIdx.x & (KS - 1), grp = threadIdx.x / KS, ngrp = blockDim.x / KS;
-    const int rpg = (RT + ngrp - 1) / ngrp;            // rows per group (<= 16)
+    const int rpg = (RT + ngrp - 1) / ngrp;            // rows per group: 4, 8 or 16
+    const int r0 = grp * rpg;
     float acc[16];
 #pragma unroll
     for (int q = 0; q < 16; ++q) acc[q] = 0.f;
-    const int r0 = grp * rpg;
-    for (int nn = 0; nn < D; ++nn) {
-      const float w = Ws[nn * WLD + k];
+    auto run = [&](auto rpg_c) {
+      constexpr int RPG = decltype(rpg_c)::value;
+      const float* gp = Gs + (size_t)(r0 < RT ? r0 : 0) * D;
+      for (int nn = 0; nn < D; nn += 4) {
+        const float w0 = Ws[nn * WLD + k], w1 = Ws[(nn + 1) * WLD + k], w2 = Ws[(nn + 2) * WLD + k], w3 = Ws[(nn + 3) * WLD + k];
 #pragma unroll
-      for (int q = 0; q < 16; ++q)
-        if (q < rpg) acc[q] = fmaf(Gs[(r0 + q < RT ? r0 + q : 0) * D + nn], w, acc[q]);
+        for (int q = 0; q < RPG; ++q) {
+          const float4 g4 = *reinterpret_cast<const float4*>(gp + (size_t)q * D + nn);
+          acc[q] = fmaf(g4.x, w0, fmaf(g4.y, w1, fmaf(g4.z, w2, fmaf(g4.w, w3, acc[q]))));
+        }
+      }
+    };
+    if (r0 + rpg <= RT) {
+      if (rpg == 4) run(std::integral_constant<int, 4>());
+      else if (rpg == 8) run(std::integral_constant<int, 8>());
+      else run(std::integral_constant<int, 16>());
     }
     if (k0 + k < P.K) {
 #pragma unroll
@@ -607,18 +654,20 @@ __global__ void __launch_bounds__(512) head_mlp_bwd_kernel(const MlpBwdP P) {
   }
   __syncthreads();
   // ---- weight gradient slice: gW0[n][k0 + k] = sum_r dz1[r][n] a0[r][k0 + k]; staged in Ws, then written row by row ----
+  if (unit) {
 #pragma unroll 4
-  for (int k = 0; k < KS; ++k) {
-    float v = 0.f;
+    for (int k = 0; k < KS; ++k) {
+      float v = 0.f;
 #pragma unroll
-    for (int r4 = 0; r4 < RT / 4; ++r4) {
-      const float4 a = *reinterpret_cast<const float4*>(&As[k * RT + 4 * r4]);
-      v = fmaf(gz[4 * r4], a.x, v);
-      v = fmaf(gz[4 * r4 + 1], a.y, v);
-      v = fmaf(gz[4 * r4 + 2], a.z, v);
-      v = fmaf(gz[4 * r4 + 3], a.w, v);
+      for (int r4 = 0; r4 < RT / 4; ++r4) {
+        const float4 a = *reinterpret_cast<const float4*>(&As[k * RT + 4 * r4]);
+        v = fmaf(gz[4 * r4], a.x, v);
+        v = fmaf(gz[4 * r4 + 1], a.y, v);
+        v = fmaf(gz[4 * r4 + 2], a.z, v);
+        v = fmaf(gz[4 * r4 + 3], a.w, v);
+      }
+      Ws[n * WLD + k] = v;
     }
-    Ws[n * WLD + k] = v;
   }
   __syncthreads();
   {
@@ -751,7 +800,7 @@ extern "C" int mlg_head_mlp_fwd(const float* a0, int64_t ld_a, const float* W0, 
 #define MLG_MLP_F(RR, KK)                                                                                                    \
   do {                                                                                                                       \
     MLG_CUDA(cudaFuncSetAttribute(head_mlp_partial_kernel<RR, KK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    head_mlp_partial_kernel<RR, KK><<<P.slices, (unsigned)D, smem, st>>>(P);                                                 \
+    head_mlp_partial_kernel<RR, KK><<<P.slices, (unsigned)(D < 256 ? 256 : D), smem, st>>>(P);                                                \
   } while (0)
   if (RT == 32) MLG_MLP_F(32, 64);
   else if (ks == 64) MLG_MLP_F(64, 64);
@@ -787,7 +836,7 @@ extern "C" int mlg_head_mlp_bwd(const float* g_pred, const float* g_loss, const 
 #define MLG_MLP_B(RR, KK)                                                                                                \
   do {                                                                                                                   \
     MLG_CUDA(cudaFuncSetAttribute(head_mlp_bwd_kernel<RR, KK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    head_mlp_bwd_kernel<RR, KK><<<blocks, (unsigned)D, smem, st>>>(P);                                                   \
+    head_mlp_bwd_kernel<RR, KK><<<blocks, (unsigned)(D < 256 ? 256 : D), smem, st>>>(P);                                                 \
   } while (0)
   if (RT == 32) MLG_MLP_B(32, 64);
   else if (ks == 64) MLG_MLP_B(64, 64);

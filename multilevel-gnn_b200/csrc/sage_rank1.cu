@@ -1,0 +1,174 @@
+// Fully factored first SAGE layer of MultilevelGNN, forward, one WARP per gene (sm_100a).
+//
+//     out[b, i, :] = LeakyReLU( x[b, i] E_self[i, :] + (1 / cnt_i) sum_{q in row i} val_q x[b, idx_q] E_nbr[idx_q, :] + bias )
+// (models/multilevel_gnn.py:150-151 feeding SAGEConv, gcn_lib/sparse/torch_vertex.py:269-294; see include/mlg_b200.h).
+//
+// r01's kernel gave every (row, 8 replicas) pair to a 16-lane group: each group re-fetched the row's table entries for its
+// replica slice, 47.7 M warp instructions and 82 us for a 126 MB output (ncu: issue slots 56 % busy, DRAM 12 %).  Here a
+// warp owns ONE gene for ALL (up to 32) replicas at once: lane l keeps channels (2l, 2l+1) of the 32 replicas in 64
+// accumulator registers; per CSR entry the warp loads the neighbour's table row ONCE (one coalesced 256-byte load) and the
+// neighbour's 32 replica values ONCE (one coalesced 128-byte load from the transposed node-value matrix xs_t [n][B]),
+// then broadcasts the replica values by shuffle: 32 SHFL + 32 FMUL + 64 FFMA per entry, four entries' loads in flight.
+// The epilogue writes 32 coalesced 256-byte rows and (optionally) the 64 sign bits per (gene, replica) the backward kernel
+// uses instead of re-reading the activation.
+#include "common.cuh"
+#include "../../include/mlg_b200.h"
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int EU = 4;   // entries whose loads are in flight together
+
+struct R1F {
+  const float* xs_t;   // [n][B]
+  const float* e_self;
+  const float* e_nbr;
+  const int* rowptr;
+  const int* idx;
+  const float* val;
+  const int* order;
+  const float* bias;
+  float* out;
+  unsigned long long* mbits;   // optional [n][B]
+  unsigned ld_self, ld_nbr, ld_out;
+  float slope;
+  int n, B;
+};
+
+template <int CPL>
+__device__ __forceinline__ void ld_cpl(float (&v)[CPL], const float* p) {
+  if (CPL == 2) {
+    const float2 t = __ldg(reinterpret_cast<const float2*>(p));
+    v[0] = t.x;
+    v[CPL - 1] = t.y;
+  } else {
+    v[0] = __ldg(p);
+  }
+}
+
+template <int CPL>
+__global__ void __launch_bounds__(kThreads, 2) sage_rank1_fwd_rows_kernel(const R1F P) {
+  const int lane = threadIdx.x & 31;
+  const long long slot = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (slot >= P.n) return;
+  const unsigned row = P.order ? (unsigned)__ldg(P.order + slot) : (unsigned)slot;
+  const int beg = __ldg(P.rowptr + row), end = __ldg(P.rowptr + row + 1);
+  const float inv = end > beg ? 1.f / (float)(end - beg) : 0.f;
+  float es[CPL], bs[CPL];
+  ld_cpl<CPL>(es, P.e_self + (size_t)row * P.ld_self + CPL * lane);
+#pragma unroll
+  for (int k = 0; k < CPL; ++k) bs[k] = P.bias ? __ldg(P.bias + CPL * lane + k) : 0.f;
+  for (int rb0 = 0; rb0 < P.B; rb0 += 32) {
+    const int nb = min(32, P.B - rb0);
+    const bool live = lane < nb;
+    float acc[32][CPL];
+#pragma unroll
+    for (int b = 0; b < 32; ++b)
+#pragma unroll
+      for (int k = 0; k < CPL; ++k) acc[b][k] = 0.f;
+    const float* xcol = P.xs_t + rb0 + (live ? lane : 0);
+    for (int base = beg; base < end; base += 32) {
+      const int q = min(base + lane, end - 1);
+      const unsigned my_idx = (unsigned)__ldg(P.idx + q);
+      const float my_w = P.val ? __ldg(P.val + q) : 1.f;
+      const int cnt = min(32, end - base);
+      for (int j = 0; j < cnt; j += EU) {
+        float e[EU][CPL], xv[EU], w[EU];
+#pragma unroll
+        for (int u = 0; u < EU; ++u) {
+          const int jj = min(j + u, cnt - 1);
+          const unsigned s = __shfl_sync(0xffffffffu, my_idx, jj);
+          w[u] = (j + u < cnt) ? __shfl_sync(0xffffffffu, my_w, jj) : 0.f;
+          ld_cpl<CPL>(e[u], P.e_nbr + (size_t)s * P.ld_nbr + CPL * lane);
+          xv[u] = live ? __ldg(xcol + (size_t)s * P.B) : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < EU; ++u) {
+          const float xw = xv[u] * w[u];
+#pragma unroll
+          for (int b = 0; b < 32; ++b) {
+            if (b >= nb) break;   // warp-uniform
+            const float f = __shfl_sync(0xffffffffu, xw, b);
+#pragma unroll
+            for (int k = 0; k < CPL; ++k) acc[b][k] = fmaf(f, e[u][k], acc[b][k]);
+          }
+        }
+      }
+    }
+    const float xself = live ? __ldg(xcol + (size_t)row * P.B) : 0.f;
+#pragma unroll
+    for (int b = 0; b < 32; ++b) {
+      if (b >= nb) break;   // warp-uniform
+      const float xb = __shfl_sync(0xffffffffu, xself, b);
+      float y[CPL];
+#pragma unroll
+      for (int k = 0; k < CPL; ++k) {
+        const float z = fmaf(es[k], xb, fmaf(acc[b][k], inv, bs[k]));
+        y[k] = z > 0.f ? z : z * P.slope;
+      }
+      float* dst = P.out + ((size_t)(rb0 + b) * P.n + row) * P.ld_out + CPL * lane;
+      if (CPL == 2) *reinterpret_cast<float2*>(dst) = make_float2(y[0], y[CPL - 1]);
+      else dst[0] = y[0];
+      if (CPL == 2 && P.mbits) {
+        // sign bits of this (gene, replica): channel c -> bit 16 * (c % 4) + c / 4 (the layout mlg_sage_rank1_bwd_rows reads):
+        // channels (2l, 2l+1) of even lanes land in the low word, of odd lanes in the high word
+        const unsigned mine = ((y[0] > 0.f ? 1u : 0u) << (lane >> 1)) | ((y[CPL - 1] > 0.f ? 1u : 0u) << (16 + (lane >> 1)));
+        const unsigned lo = __reduce_or_sync(0xffffffffu, (lane & 1) ? 0u : mine);
+        const unsigned hi = __reduce_or_sync(0xffffffffu, (lane & 1) ? mine : 0u);
+        if (lane == 0) P.mbits[(size_t)row * P.B + rb0 + b] = ((unsigned long long)hi << 32) | lo;
+      }
+    }
+  }
+}
+
+__global__ void transpose_bn_kernel(const float* __restrict__ xs, int B, int n, float* __restrict__ xs_t) {
+  __shared__ float tile[32][33];
+  const int n0 = blockIdx.x * 32, b0 = blockIdx.y * 32;
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int b = b0 + r, i = n0 + threadIdx.x;
+    tile[r][threadIdx.x] = (b < B && i < n) ? __ldg(xs + (size_t)b * n + i) : 0.f;
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int i = n0 + r, b = b0 + threadIdx.x;
+    if (i < n && b < B) xs_t[(size_t)i * B + b] = tile[threadIdx.x][r];
+  }
+}
+
+}  // namespace
+
+extern "C" int mlg_transpose_bn(const float* xs, int64_t B, int64_t n, float* xs_t, void* stream) {
+  MLG_CHECK_ARG(xs && xs_t && B >= 1 && n >= 1, "mlg_transpose_bn: bad arguments");
+  dim3 grid((unsigned)mlg_ceil_div(n, 32), (unsigned)mlg_ceil_div(B, 32)), block(32, 8);
+  transpose_bn_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(xs, (int)B, (int)n, xs_t);
+  MLG_CHECK_LAUNCH("mlg_transpose_bn");
+  return MLG_OK;
+}
+
+extern "C" int mlg_sage_rank1_fwd_rows_supported(int64_t C) { return C == 32 || C == 64; }
+
+extern "C" int mlg_sage_rank1_fwd_rows(const float* xs_t, const float* e_self, int64_t ld_self, const float* e_nbr, int64_t ld_nbr,
+                                       const int32_t* rowptr, const int32_t* idx, const float* val, const int32_t* order,
+                                       int64_t n_rows, int64_t C, int64_t replicas, const float* bias, float slope, float* out,
+                                       int64_t ld_out, uint64_t* mask_bits, void* stream) {
+  MLG_CHECK_ARG(xs_t && e_self && e_nbr && rowptr && idx && out, "mlg_sage_rank1_fwd_rows: null pointer");
+  MLG_CHECK_ARG(mlg_sage_rank1_fwd_rows_supported(C), "mlg_sage_rank1_fwd_rows: C=%lld (needs 32 or 64)", (long long)C);
+  MLG_CHECK_ARG(n_rows >= 0 && replicas >= 1 && replicas * n_rows < (1ll << 31) && ld_self >= C && ld_nbr >= C && ld_out >= C,
+                "mlg_sage_rank1_fwd_rows: bad sizes");
+  MLG_CHECK_ARG(ld_self % 2 == 0 && ld_nbr % 2 == 0 && ld_out % 2 == 0 &&
+                    ((uintptr_t)e_self | (uintptr_t)e_nbr | (uintptr_t)out) % 8 == 0,
+                "mlg_sage_rank1_fwd_rows: tables / out must be 8-byte aligned with even leading dimensions");
+  MLG_CHECK_ARG(!mask_bits || C == 64, "mlg_sage_rank1_fwd_rows: mask_bits needs C == 64");
+  if (n_rows == 0) return MLG_OK;
+  R1F P;
+  P.xs_t = xs_t; P.e_self = e_self; P.e_nbr = e_nbr; P.rowptr = rowptr; P.idx = idx; P.val = val; P.order = order;
+  P.bias = bias; P.out = out; P.mbits = reinterpret_cast<unsigned long long*>(mask_bits);
+  P.ld_self = (unsigned)ld_self; P.ld_nbr = (unsigned)ld_nbr; P.ld_out = (unsigned)ld_out; P.slope = slope;
+  P.n = (int)n_rows; P.B = (int)replicas;
+  const unsigned grid = (unsigned)mlg_ceil_div(n_rows, kThreads / 32);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (C == 64) sage_rank1_fwd_rows_kernel<2><<<grid, kThreads, 0, st>>>(P);
+  else sage_rank1_fwd_rows_kernel<1><<<grid, kThreads, 0, st>>>(P);
+  MLG_CHECK_LAUNCH("mlg_sage_rank1_fwd_rows");
+  return MLG_OK;
+}

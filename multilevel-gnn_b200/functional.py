@@ -505,6 +505,8 @@ TRANSFORM_FIRST = _flag("MLG_TRANSFORM_FIRST", True)
 # leaky_relu_backward pass + the unmasked kernel is FASTER (step 1.000 ms vs 1.086 ms) and is the default; the in-kernel
 # paths stay selectable (and tested) until an ncu capture explains the regression (tools/rank1_bwd_probe.py).
 RANK1_SIGN_BITS = True
+# forward of the factored first layer with one warp per gene for all replicas (mlg_sage_rank1_fwd_rows); False: r01's kernel
+RANK1_FWD_ROWS = _flag("MLG_R1_FWD_ROWS", True)
 RANK1_SELF_MASK = _flag("MLG_R1_SELF_MASK", True)
 # Row visiting order of the replicated kernels: degree-sorted (heavy rows first, balanced lane groups) or natural.  Measured
 # on B200 (tools/ab_order.sh, gbm shape): sorted wins everywhere -- rank-1 forward 109 vs 166 us, layer-2 aggregations 150 vs
@@ -566,12 +568,30 @@ class SageLayer(torch.autograd.Function):
             mbits = None
             if RANK1_SIGN_BITS and RANK1_SELF_MASK and cout == 64 and not out_premasked and any(ctx.needs_input_grad):
                 mbits = torch.empty(n1 * topo.replicas, dtype=torch.int64, device=xd.device)
-            with torch.cuda.device(xd.device), _cabi.span("sage_rank1_fwd", nbytes):
-                _cabi.check(L.mlg_sage_rank1_fwd(
-                    _cabi.fptr(xs_d), _vptr(e12), 2 * cout, _vptr(e12[:, cout:]), 2 * cout, _cabi.iptr(csr.rowptr),
-                    _cabi.iptr(csr.col), _cabi.fptr(topo.fwd_val, True), _cabi.iptr(topo.fwd_order if ORDER_R1F else None, True),
-                    n1, cout, topo.replicas, _cabi.fptr(bias, True), float(slope), _cabi.fptr(y), cout,
-                    _cabi.lptr(mbits, True), _cabi.stream_ptr()), "mlg_sage_rank1_fwd")
+            rows_ok = RANK1_FWD_ROWS and bool(L.mlg_sage_rank1_fwd_rows_supported(cout))
+            xs_t = None
+            with torch.cuda.device(xd.device):
+                if rows_ok:
+                    # node values transposed to [n1, B]: one coalesced load per CSR entry in the forward AND the backward kernel
+                    xs_t = torch.empty(n1 * topo.replicas, dtype=torch.float32, device=xd.device)
+                    _cabi.check(L.mlg_transpose_bn(_cabi.fptr(xs_d), topo.replicas, n1, _cabi.fptr(xs_t), _cabi.stream_ptr()),
+                                "mlg_transpose_bn")
+                with _cabi.span("sage_rank1_fwd", nbytes):
+                    if rows_ok:
+                        _cabi.check(L.mlg_sage_rank1_fwd_rows(
+                            _cabi.fptr(xs_t), _vptr(e12), 2 * cout, _vptr(e12[:, cout:]), 2 * cout, _cabi.iptr(csr.rowptr),
+                            _cabi.iptr(csr.col), _cabi.fptr(topo.fwd_val, True),
+                            _cabi.iptr(topo.fwd_order if ORDER_R1F else None, True), n1, cout, topo.replicas,
+                            _cabi.fptr(bias, True), float(slope), _cabi.fptr(y), cout, _cabi.lptr(mbits, True),
+                            _cabi.stream_ptr()), "mlg_sage_rank1_fwd_rows")
+                    else:
+                        _cabi.check(L.mlg_sage_rank1_fwd(
+                            _cabi.fptr(xs_d), _vptr(e12), 2 * cout, _vptr(e12[:, cout:]), 2 * cout, _cabi.iptr(csr.rowptr),
+                            _cabi.iptr(csr.col), _cabi.fptr(topo.fwd_val, True),
+                            _cabi.iptr(topo.fwd_order if ORDER_R1F else None, True), n1, cout, topo.replicas,
+                            _cabi.fptr(bias, True), float(slope), _cabi.fptr(y), cout, _cabi.lptr(mbits, True),
+                            _cabi.stream_ptr()), "mlg_sage_rank1_fwd")
+            ctx.xs_t = xs_t
             ctx.mbits = mbits
             ctx.save_for_backward(xd, y, wst, w_r, w_nn, xs_d)
             ctx.topo, ctx.relative, ctx.slope, ctx.cin, ctx.has_bias = topo, False, float(slope), cin, nn_b is not None
@@ -648,10 +668,11 @@ class SageLayer(torch.autograd.Function):
             h = torch.empty(fw.cap, cout, dtype=torch.float32, device=gz.device)
             nbytes = 4 * cout * gz.shape[0] + 4 * gz.shape[0] + 8 * fw.col.numel() + 4 * (h.numel() + 2 * gbr.numel())
             with torch.cuda.device(gz.device), _cabi.span("sage_rank1_bwd", nbytes):
+                xs_t = getattr(ctx, "xs_t", None)
                 _cabi.check(L.mlg_sage_rank1_bwd_rows(
                     _cabi.fptr(gz), cout, _cabi.fptr(y_mask, True),
                     _cabi.lptr(bits, True), float(ctx.slope),
-                    _cabi.fptr(xs_d), _cabi.iptr(fw.rowptr),
+                    _cabi.fptr(xs_d if xs_t is None else xs_t), 0 if xs_t is None else 1, _cabi.iptr(fw.rowptr),
                     _cabi.iptr(fw.col),
                     _cabi.fptr(topo.fwd_val, True), _cabi.iptr(topo.fwd_order if ORDER_R1B else None, True), n1, cout, B,
                     _cabi.fptr(h),

@@ -49,7 +49,7 @@ def main():
     def rows(gz, mode):
         _cabi.check(L.mlg_sage_rank1_bwd_rows(
             _cabi.fptr(gz), C, _cabi.fptr(y if mode == "y" else None, True), _cabi.lptr(bits if mode == "bits" else None, True),
-            0.2, _cabi.fptr(xs), _cabi.iptr(fw.rowptr), _cabi.iptr(fw.col), _cabi.fptr(topo.fwd_val, True),
+            0.2, _cabi.fptr(xs), 0, _cabi.iptr(fw.rowptr), _cabi.iptr(fw.col), _cabi.fptr(topo.fwd_val, True),
             _cabi.iptr(topo.fwd_order, True), n1, C, B, _cabi.fptr(h), _cabi.fptr(g12), 2 * C, _cabi.fptr(gbr),
             _cabi.stream_ptr()), "mlg_sage_rank1_bwd_rows")
 
