@@ -84,40 +84,63 @@ struct MemMap {
 
 // ---------------------------------------------------------------------------------------------------------------------
 // C[M x N] (ldc) = alpha * A[M x K] * B[K x N] (+ C when acc); A, B addressed by (row stride, column stride): a transposed
-// operand is just swapped strides.  4 x 4 register tile per work item.
-MLG_DEV void mm(float* C, int ldc, const float* A, int rsA, int csA, const float* B, int rsB, int csB, int M, int N, int K,
-                float alpha, bool acc) {
-  const int tm = (M + 3) >> 2, tn = (N + 3) >> 2;
+// operand is just swapped strides.  TM x TN register tile per work item.
+template <int TM, int TN>
+MLG_DEV void mm_tile(float* C, int ldc, const float* A, int rsA, int csA, const float* B, int rsB, int csB, int M, int N, int K,
+                     float alpha, bool acc) {
+  const int tm = (M + TM - 1) / TM, tn = (N + TN - 1) / TN;
   MLG_PFOR(t, tm * tn) {
-    const int i0 = (t / tn) << 2, j0 = (t % tn) << 2;
-    float c[4][4];
+    const int i0 = (t / tn) * TM, j0 = (t % tn) * TN;
+    float c[TM][TN];
 #pragma unroll
-    for (int r = 0; r < 4; ++r)
+    for (int r = 0; r < TM; ++r)
 #pragma unroll
-      for (int s = 0; s < 4; ++s) c[r][s] = 0.f;
-    const int ia[4] = {i0, i0 + 1 < M ? i0 + 1 : i0, i0 + 2 < M ? i0 + 2 : i0, i0 + 3 < M ? i0 + 3 : i0};
-    const int jb[4] = {j0, j0 + 1 < N ? j0 + 1 : j0, j0 + 2 < N ? j0 + 2 : j0, j0 + 3 < N ? j0 + 3 : j0};
+      for (int s = 0; s < TN; ++s) c[r][s] = 0.f;
+    const float* ap[TM];
+    const float* bp[TN];
+#pragma unroll
+    for (int r = 0; r < TM; ++r) ap[r] = A + (i0 + r < M ? i0 + r : i0) * rsA;
+#pragma unroll
+    for (int s = 0; s < TN; ++s) bp[s] = B + (j0 + s < N ? j0 + s : j0) * csB;
+#pragma unroll 2
     for (int k = 0; k < K; ++k) {
-      float a[4], bb[4];
+      float a[TM], bb[TN];
 #pragma unroll
-      for (int r = 0; r < 4; ++r) a[r] = A[ia[r] * rsA + k * csA];
+      for (int r = 0; r < TM; ++r) a[r] = ap[r][k * csA];
 #pragma unroll
-      for (int s = 0; s < 4; ++s) bb[s] = B[k * rsB + jb[s] * csB];
+      for (int s = 0; s < TN; ++s) bb[s] = bp[s][k * rsB];
 #pragma unroll
-      for (int r = 0; r < 4; ++r)
+      for (int r = 0; r < TM; ++r)
 #pragma unroll
-        for (int s = 0; s < 4; ++s) c[r][s] = fmaf(a[r], bb[s], c[r][s]);
+        for (int s = 0; s < TN; ++s) c[r][s] = fmaf(a[r], bb[s], c[r][s]);
     }
 #pragma unroll
-    for (int r = 0; r < 4; ++r)
+    for (int r = 0; r < TM; ++r)
 #pragma unroll
-      for (int s = 0; s < 4; ++s)
+      for (int s = 0; s < TN; ++s)
         if (i0 + r < M && j0 + s < N) {
           float* p = C + (i0 + r) * ldc + j0 + s;
           *p = acc ? fmaf(alpha, c[r][s], *p) : alpha * c[r][s];
         }
   }
   MLG_SYNC();
+}
+
+// tile shape by output size: the largest tile that still gives (nearly) every thread of the block a work item -- the small
+// pooled products ([37 x 32] over K = 146) would otherwise keep 80 of 512 threads busy (r02 ncu: 40 % of the stall samples
+// sat on the reconvergence points in front of the barriers)
+#ifndef MLG_HOST_EMU
+#define MLG_NTHREADS ((int)blockDim.x)
+#else
+#define MLG_NTHREADS 512
+#endif
+MLG_DEV void mm(float* C, int ldc, const float* A, int rsA, int csA, const float* B, int rsB, int csB, int M, int N, int K,
+                float alpha, bool acc) {
+  const int want = (MLG_NTHREADS * 3) / 4;
+  if (((M + 3) / 4) * ((N + 3) / 4) >= want) mm_tile<4, 4>(C, ldc, A, rsA, csA, B, rsB, csB, M, N, K, alpha, acc);
+  else if (((M + 1) / 2) * ((N + 3) / 4) >= want) mm_tile<2, 4>(C, ldc, A, rsA, csA, B, rsB, csB, M, N, K, alpha, acc);
+  else if (((M + 1) / 2) * ((N + 1) / 2) >= want) mm_tile<2, 2>(C, ldc, A, rsA, csA, B, rsB, csB, M, N, K, alpha, acc);
+  else mm_tile<1, 2>(C, ldc, A, rsA, csA, B, rsB, csB, M, N, K, alpha, acc);
 }
 
 // sum of v[0..n) in index order by one work item -> *dst (after the barrier everyone may read it)
