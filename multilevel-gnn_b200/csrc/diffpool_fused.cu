@@ -126,21 +126,12 @@ MLG_DEV void mm_tile(float* C, int ldc, const float* A, int rsA, int csA, const 
   MLG_SYNC();
 }
 
-// tile shape by output size: the largest tile that still gives (nearly) every thread of the block a work item -- the small
-// pooled products ([37 x 32] over K = 146) would otherwise keep 80 of 512 threads busy (r02 ncu: 40 % of the stall samples
-// sat on the reconvergence points in front of the barriers)
-#ifndef MLG_HOST_EMU
-#define MLG_NTHREADS ((int)blockDim.x)
-#else
-#define MLG_NTHREADS 512
-#endif
+// 4 x 4 tiles throughout: smaller tiles for the small pooled products ([37 x 32] over K = 146 keeps 80 of 512 threads busy)
+// were measured SLOWER on B200 (b = 576 forward + backward 5.1 ms vs 3.5 ms): the kernel is bound by its instruction count
+// (r02 ncu: 229 M warp instructions forward, 41 % of them FFMA), not by idle threads.
 MLG_DEV void mm(float* C, int ldc, const float* A, int rsA, int csA, const float* B, int rsB, int csB, int M, int N, int K,
                 float alpha, bool acc) {
-  const int want = (MLG_NTHREADS * 3) / 4;
-  if (((M + 3) / 4) * ((N + 3) / 4) >= want) mm_tile<4, 4>(C, ldc, A, rsA, csA, B, rsB, csB, M, N, K, alpha, acc);
-  else if (((M + 1) / 2) * ((N + 3) / 4) >= want) mm_tile<2, 4>(C, ldc, A, rsA, csA, B, rsB, csB, M, N, K, alpha, acc);
-  else if (((M + 1) / 2) * ((N + 1) / 2) >= want) mm_tile<2, 2>(C, ldc, A, rsA, csA, B, rsB, csB, M, N, K, alpha, acc);
-  else mm_tile<1, 2>(C, ldc, A, rsA, csA, B, rsB, csB, M, N, K, alpha, acc);
+  mm_tile<4, 4>(C, ldc, A, rsA, csA, B, rsB, csB, M, N, K, alpha, acc);
 }
 
 // sum of v[0..n) in index order by one work item -> *dst (after the barrier everyone may read it)

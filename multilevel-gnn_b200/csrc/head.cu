@@ -444,36 +444,79 @@ __device__ __forceinline__ void stage_slices(const float* W0, int D, int K, cons
   }
 }
 
-template <int RT, int KSL>
-__global__ void __launch_bounds__(512) head_mlp_partial_kernel(const MlpP P) {
-  constexpr int KS = KSL, WLD = KSL + 1;
+// Forward partial products.  Block = (32 hidden units) x (one K group of KG = 512 columns); thread = (unit n = lane,
+// sub-slice g = warp of 64 columns): acc[r] over its 64 columns for all samples, then the 8 sub-slices are added in a fixed
+// order through shared memory -> ONE partial per (K group, sample, unit): 14 partial slices for K = 6913 instead of 109
+// (the finish kernel then has 14 loads per output instead of 109: r02 ncu 49 us -> see profiles/r02_ncu_head.md).
+constexpr int KG = 512, KSUB = 64, NG = 32;
+constexpr int WG_LD = KG + 1;
+
+template <int RT>
+__global__ void __launch_bounds__(256) head_mlp_partial_kernel(const MlpP P) {
   extern __shared__ __align__(16) float mlp_sm[];
-  float* Ws = mlp_sm;                 // [D][WLD]
-  float* As = mlp_sm + P.D * WLD;     // [KS][RT]
-  const int n = threadIdx.x, k0 = blockIdx.x * KS;
-  if (blockIdx.x == 0 && threadIdx.x == 0) *P.counter = 0u;   // the finish kernel's arrival counter
-  stage_slices<RT, KSL>(P.W0, P.D, P.K, P.a0, P.ld_a, P.R, k0, Ws, As);
+  float* Ws = mlp_sm;                   // [NG][WG_LD]
+  float* As = Ws + NG * WG_LD;          // [KG][RT]; afterwards the [8][RT][NG] reduction buffer
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int n0 = blockIdx.x * NG, k0 = blockIdx.y * KG;
+  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *P.counter = 0u;   // the finish kernel's arrival counter
+  // stage W0[n0 : n0 + 32, k0 : k0 + 512] (each row: 2 KB contiguous) -- four rows' loads in flight per warp step
+  for (int rr = warp; rr < NG; rr += 8 * 4) {
+    float v[4][KG / 32];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int n = n0 + rr + 8 * u;
+      const float* row = P.W0 + (size_t)(n < P.D ? n : 0) * P.K + k0;
+#pragma unroll
+      for (int q = 0; q < KG / 32; ++q) v[u][q] = (n < P.D && k0 + lane + 32 * q < P.K) ? __ldg(row + lane + 32 * q) : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int q = 0; q < KG / 32; ++q) Ws[(rr + 8 * u) * WG_LD + lane + 32 * q] = v[u][q];
+  }
+  // a0[:, k0 : k0 + 512] transposed to As[k][r]: thread -> column k = tid (+256), RT loads in flight
+#pragma unroll
+  for (int half = 0; half < KG / 256; ++half) {
+    const int k = threadIdx.x + 256 * half;
+    float v[RT];
+#pragma unroll
+    for (int r = 0; r < RT; ++r) v[r] = (r < P.R && k0 + k < P.K) ? __ldg(P.a0 + (size_t)r * P.ld_a + k0 + k) : 0.f;
+#pragma unroll
+    for (int r4 = 0; r4 < RT / 4; ++r4)
+      *reinterpret_cast<float4*>(&As[k * RT + 4 * r4]) = make_float4(v[4 * r4], v[4 * r4 + 1], v[4 * r4 + 2], v[4 * r4 + 3]);
+  }
   __syncthreads();
-  if (n >= P.D) return;     // helper threads of a narrow layer (blockDim = max(D, 256)) only stage
   float acc[RT];
 #pragma unroll
   for (int r = 0; r < RT; ++r) acc[r] = 0.f;
+  const float* wrow = Ws + lane * WG_LD + warp * KSUB;
+  const float* arow = As + (size_t)warp * KSUB * RT;
 #pragma unroll 4
-  for (int k = 0; k < KS; ++k) {
-    const float w = Ws[n * WLD + k];
+  for (int k = 0; k < KSUB; ++k) {
+    const float w = wrow[k];
 #pragma unroll
     for (int r4 = 0; r4 < RT / 4; ++r4) {
-      const float4 a = *reinterpret_cast<const float4*>(&As[k * RT + 4 * r4]);
+      const float4 a = *reinterpret_cast<const float4*>(&arow[k * RT + 4 * r4]);
       acc[4 * r4] = fmaf(w, a.x, acc[4 * r4]);
       acc[4 * r4 + 1] = fmaf(w, a.y, acc[4 * r4 + 1]);
       acc[4 * r4 + 2] = fmaf(w, a.z, acc[4 * r4 + 2]);
       acc[4 * r4 + 3] = fmaf(w, a.w, acc[4 * r4 + 3]);
     }
   }
-  float* p = P.partial + (size_t)blockIdx.x * P.R * P.D + n;
+  __syncthreads();                       // As is dead: reuse it as [8 sub-slices][RT][NG]
+  float* red = As;
 #pragma unroll
-  for (int r = 0; r < RT; ++r)
-    if (r < P.R) p[(size_t)r * P.D] = acc[r];
+  for (int r = 0; r < RT; ++r) red[(warp * RT + r) * NG + lane] = acc[r];
+  __syncthreads();
+  for (int t = threadIdx.x; t < RT * NG; t += 256) {
+    const int r = t / NG, l = t - r * NG;
+    if (r < P.R && n0 + l < P.D) {
+      float s = 0.f;
+#pragma unroll
+      for (int g = 0; g < 8; ++g) s += red[(g * RT + r) * NG + l];
+      P.partial[((size_t)blockIdx.y * P.R + r) * P.D + n0 + l] = s;
+    }
+  }
 }
 
 // one block per sample r: slice reduction + bias + ReLU + dropout -> a1[r, :]; logits, softmax, weighted BCE; the last
@@ -683,7 +726,8 @@ __global__ void __launch_bounds__(512) head_mlp_bwd_kernel(const MlpBwdP P) {
 
 // K columns per block (see head_mlp_*_kernel) and the resulting number of K slices; one choice for forward and backward
 inline int mlp_ks(int64_t R, int64_t D) { return (R > 32 && D > 256) ? 32 : 64; }
-inline int mlp_slices(int64_t R, int64_t D, int64_t K) { const int ks = mlp_ks(R, D); return (int)((K + ks - 1) / ks); }
+inline int mlp_slices(int64_t R, int64_t D, int64_t K) { const int ks = mlp_ks(R, D); return (int)((K + ks - 1) / ks); }   // backward
+inline int mlp_fwd_slices(int64_t K) { return (int)((K + KG - 1) / KG); }
 
 inline int drop_threshold(float p) {
   if (!(p > 0.f)) return 0;
@@ -769,7 +813,7 @@ extern "C" int mlg_head_conv_pool_bwd(const float* g_a0, int64_t ld, const float
 }
 
 extern "C" int64_t mlg_head_mlp_workspace_bytes(int64_t R, int64_t D, int64_t K) {
-  return ((int64_t)mlp_slices(R, D, K) * R * D + R + 4) * 4;
+  return ((int64_t)mlp_fwd_slices(K) * R * D + R + 4) * 4;
 }
 
 extern "C" int mlg_head_mlp_fwd(const float* a0, int64_t ld_a, const float* W0, const float* b0, const float* W3,
@@ -789,23 +833,22 @@ extern "C" int mlg_head_mlp_fwd(const float* a0, int64_t ld_a, const float* W0, 
   P.thr = drop_threshold(drop_p); P.keep_scale = 1.f / (1.f - drop_p);
   P.y = y; P.weight = weight;
   P.R = (int)R; P.D = (int)D; P.K = (int)K; P.ld_a = ld_a;
-  P.slices = mlp_slices(R, D, K);
+  P.slices = mlp_fwd_slices(K);
   P.partial = (float*)workspace;
   P.rowloss = P.partial + (size_t)P.slices * R * D;
   P.counter = (unsigned*)(P.rowloss + R);
   P.a1 = a1; P.pred = pred; P.loss = loss;
   cudaStream_t st = (cudaStream_t)stream;
-  const int RT = R <= 32 ? 32 : 64, ks = mlp_ks(R, D);
-  const size_t smem = ((size_t)D * (ks + 1) + (size_t)ks * RT) * 4;
-#define MLG_MLP_F(RR, KK)                                                                                                    \
-  do {                                                                                                                       \
-    MLG_CUDA(cudaFuncSetAttribute(head_mlp_partial_kernel<RR, KK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    head_mlp_partial_kernel<RR, KK><<<P.slices, (unsigned)(D < 256 ? 256 : D), smem, st>>>(P);                                                \
-  } while (0)
-  if (RT == 32) MLG_MLP_F(32, 64);
-  else if (ks == 64) MLG_MLP_F(64, 64);
-  else MLG_MLP_F(64, 32);
-#undef MLG_MLP_F
+  const int RT = R <= 32 ? 32 : 64;
+  const size_t smem = ((size_t)NG * WG_LD + (size_t)KG * RT) * 4;
+  dim3 grid((unsigned)((D + NG - 1) / NG), (unsigned)P.slices);
+  if (RT == 32) {
+    MLG_CUDA(cudaFuncSetAttribute(head_mlp_partial_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    head_mlp_partial_kernel<32><<<grid, 256, smem, st>>>(P);
+  } else {
+    MLG_CUDA(cudaFuncSetAttribute(head_mlp_partial_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    head_mlp_partial_kernel<64><<<grid, 256, smem, st>>>(P);
+  }
   MLG_CHECK_LAUNCH("mlg_head_mlp_fwd(partial)");
   head_mlp_finish_kernel<<<(unsigned)R, kThreads, 0, st>>>(P);
   MLG_CHECK_LAUNCH("mlg_head_mlp_fwd(finish)");

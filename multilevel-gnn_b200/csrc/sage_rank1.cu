@@ -46,6 +46,83 @@ __device__ __forceinline__ void ld_cpl(float (&v)[CPL], const float* p) {
   }
 }
 
+// FULL: all 32 replica slots of the pass are live (B a multiple of 32): no per-replica bound checks in the unrolled loops
+template <int CPL, bool FULL>
+__device__ __forceinline__ void rank1_rows_pass(const R1F& P, unsigned row, int beg, int end, float inv, const float (&es)[CPL],
+                                                const float (&bs)[CPL], int rb0, int nb, int lane) {
+  const bool live = FULL || lane < nb;
+  float acc[32][CPL];
+#pragma unroll
+  for (int b = 0; b < 32; ++b)
+#pragma unroll
+    for (int k = 0; k < CPL; ++k) acc[b][k] = 0.f;
+  const float* xcol = P.xs_t + rb0 + (live ? lane : 0);
+  for (int base = beg; base < end; base += 32) {
+    const int q = min(base + lane, end - 1);
+    const unsigned my_idx = (unsigned)__ldg(P.idx + q);
+    const float my_w = P.val ? __ldg(P.val + q) : 1.f;
+    const int cnt = min(32, end - base);
+    for (int j = 0; j < cnt; j += EU) {
+      float e[EU][CPL], xw[EU];
+#pragma unroll
+      for (int u = 0; u < EU; ++u) {
+        const int jj = min(j + u, cnt - 1);
+        const unsigned s = __shfl_sync(0xffffffffu, my_idx, jj);
+        const float w = (j + u < cnt) ? __shfl_sync(0xffffffffu, my_w, jj) : 0.f;
+        ld_cpl<CPL>(e[u], P.e_nbr + (size_t)s * P.ld_nbr + CPL * lane);
+        xw[u] = live ? __ldg(xcol + (size_t)s * P.B) * w : 0.f;
+      }
+#pragma unroll
+      for (int b = 0; b < 32; ++b) {
+        if (!FULL && b >= nb) break;   // warp-uniform
+#pragma unroll
+        for (int u = 0; u < EU; ++u) {
+          const float f = __shfl_sync(0xffffffffu, xw[u], b);
+#pragma unroll
+          for (int k = 0; k < CPL; ++k) acc[b][k] = fmaf(f, e[u][k], acc[b][k]);
+        }
+      }
+    }
+  }
+  const float xself = live ? __ldg(xcol + (size_t)row * P.B) : 0.f;
+  unsigned lo_w = 0u, hi_w = 0u;     // lane b keeps the sign words of replica rb0 + b; one coalesced 8-byte store per lane
+#pragma unroll
+  for (int b = 0; b < 32; ++b) {
+    if (!FULL && b >= nb) break;   // warp-uniform
+    const float xb = __shfl_sync(0xffffffffu, xself, b);
+    float y[CPL];
+#pragma unroll
+    for (int k = 0; k < CPL; ++k) {
+      const float z = fmaf(es[k], xb, fmaf(acc[b][k], inv, bs[k]));
+      y[k] = z > 0.f ? z : z * P.slope;
+    }
+    float* dst = P.out + ((size_t)(rb0 + b) * P.n + row) * P.ld_out + CPL * lane;
+    if (CPL == 2) *reinterpret_cast<float2*>(dst) = make_float2(y[0], y[CPL - 1]);
+    else dst[0] = y[0];
+    if (CPL == 2 && P.mbits) {
+      // sign bits of this (gene, replica): channel c -> bit 16 * (c % 4) + c / 4 (the layout mlg_sage_rank1_bwd_rows reads):
+      // ballot bit l of the first / second channel of lane l = channel 2l / 2l + 1; even lanes feed the low word, odd lanes
+      // the high word, at bit (l >> 1) resp. 16 + (l >> 1)
+      const unsigned b0 = __ballot_sync(0xffffffffu, y[0] > 0.f), b1 = __ballot_sync(0xffffffffu, y[CPL - 1] > 0.f);
+      if (lane == b) { lo_w = b0; hi_w = b1; }
+    }
+  }
+  if (CPL == 2 && P.mbits && live) {
+    // compress: even bits of b0 -> low word bits 0..15, even bits of b1 -> low word bits 16..31; odd bits -> high word
+    auto even = [](unsigned v) {   // gather bits 0, 2, 4, ... into the low 16 bits
+      v &= 0x55555555u;
+      v = (v | (v >> 1)) & 0x33333333u;
+      v = (v | (v >> 2)) & 0x0f0f0f0fu;
+      v = (v | (v >> 4)) & 0x00ff00ffu;
+      v = (v | (v >> 8)) & 0x0000ffffu;
+      return v;
+    };
+    const unsigned lo = even(lo_w) | (even(hi_w) << 16);
+    const unsigned hi = even(lo_w >> 1) | (even(hi_w >> 1) << 16);
+    P.mbits[(size_t)row * P.B + rb0 + lane] = ((unsigned long long)hi << 32) | lo;
+  }
+}
+
 template <int CPL>
 __global__ void __launch_bounds__(kThreads, 2) sage_rank1_fwd_rows_kernel(const R1F P) {
   const int lane = threadIdx.x & 31;
@@ -60,64 +137,8 @@ __global__ void __launch_bounds__(kThreads, 2) sage_rank1_fwd_rows_kernel(const 
   for (int k = 0; k < CPL; ++k) bs[k] = P.bias ? __ldg(P.bias + CPL * lane + k) : 0.f;
   for (int rb0 = 0; rb0 < P.B; rb0 += 32) {
     const int nb = min(32, P.B - rb0);
-    const bool live = lane < nb;
-    float acc[32][CPL];
-#pragma unroll
-    for (int b = 0; b < 32; ++b)
-#pragma unroll
-      for (int k = 0; k < CPL; ++k) acc[b][k] = 0.f;
-    const float* xcol = P.xs_t + rb0 + (live ? lane : 0);
-    for (int base = beg; base < end; base += 32) {
-      const int q = min(base + lane, end - 1);
-      const unsigned my_idx = (unsigned)__ldg(P.idx + q);
-      const float my_w = P.val ? __ldg(P.val + q) : 1.f;
-      const int cnt = min(32, end - base);
-      for (int j = 0; j < cnt; j += EU) {
-        float e[EU][CPL], xv[EU], w[EU];
-#pragma unroll
-        for (int u = 0; u < EU; ++u) {
-          const int jj = min(j + u, cnt - 1);
-          const unsigned s = __shfl_sync(0xffffffffu, my_idx, jj);
-          w[u] = (j + u < cnt) ? __shfl_sync(0xffffffffu, my_w, jj) : 0.f;
-          ld_cpl<CPL>(e[u], P.e_nbr + (size_t)s * P.ld_nbr + CPL * lane);
-          xv[u] = live ? __ldg(xcol + (size_t)s * P.B) : 0.f;
-        }
-#pragma unroll
-        for (int u = 0; u < EU; ++u) {
-          const float xw = xv[u] * w[u];
-#pragma unroll
-          for (int b = 0; b < 32; ++b) {
-            if (b >= nb) break;   // warp-uniform
-            const float f = __shfl_sync(0xffffffffu, xw, b);
-#pragma unroll
-            for (int k = 0; k < CPL; ++k) acc[b][k] = fmaf(f, e[u][k], acc[b][k]);
-          }
-        }
-      }
-    }
-    const float xself = live ? __ldg(xcol + (size_t)row * P.B) : 0.f;
-#pragma unroll
-    for (int b = 0; b < 32; ++b) {
-      if (b >= nb) break;   // warp-uniform
-      const float xb = __shfl_sync(0xffffffffu, xself, b);
-      float y[CPL];
-#pragma unroll
-      for (int k = 0; k < CPL; ++k) {
-        const float z = fmaf(es[k], xb, fmaf(acc[b][k], inv, bs[k]));
-        y[k] = z > 0.f ? z : z * P.slope;
-      }
-      float* dst = P.out + ((size_t)(rb0 + b) * P.n + row) * P.ld_out + CPL * lane;
-      if (CPL == 2) *reinterpret_cast<float2*>(dst) = make_float2(y[0], y[CPL - 1]);
-      else dst[0] = y[0];
-      if (CPL == 2 && P.mbits) {
-        // sign bits of this (gene, replica): channel c -> bit 16 * (c % 4) + c / 4 (the layout mlg_sage_rank1_bwd_rows reads):
-        // channels (2l, 2l+1) of even lanes land in the low word, of odd lanes in the high word
-        const unsigned mine = ((y[0] > 0.f ? 1u : 0u) << (lane >> 1)) | ((y[CPL - 1] > 0.f ? 1u : 0u) << (16 + (lane >> 1)));
-        const unsigned lo = __reduce_or_sync(0xffffffffu, (lane & 1) ? 0u : mine);
-        const unsigned hi = __reduce_or_sync(0xffffffffu, (lane & 1) ? mine : 0u);
-        if (lane == 0) P.mbits[(size_t)row * P.B + rb0 + b] = ((unsigned long long)hi << 32) | lo;
-      }
-    }
+    if (nb == 32) rank1_rows_pass<CPL, true>(P, row, beg, end, inv, es, bs, rb0, nb, lane);
+    else rank1_rows_pass<CPL, false>(P, row, beg, end, inv, es, bs, rb0, nb, lane);
   }
 }
 

@@ -150,7 +150,9 @@ def test_genconv_100k_vs_oracle(mlg):
     for kk, a, c in zip(names, gs[2:], g_r[2:]):
         if c is None:
             continue
-        _check(a, c, "GENConv 100k g_" + kk, rtol=5e-4, atol=2e-5, l2=2e-3, outliers=1e-3)
+        # t / msg_scale: scalar parameters whose gradient is ONE fp32 sum over 12.8 M cancelling terms
+        _check(a, c, "GENConv 100k g_" + kk, rtol=5e-4 if a.numel() > 1 else 5e-3, atol=2e-5, l2=2e-3 if a.numel() > 1 else 5e-3,
+               outliers=1e-3)
 
 
 def test_diffpool_tensor_core_path_vs_oracle(mlg):

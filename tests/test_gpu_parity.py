@@ -580,8 +580,6 @@ def test_factored_first_layer_is_equivalent(mlg):
         torch.manual_seed(3)
         model = mlg.MultilevelGNN(args)
         synth.multilevel_params(model)
-        with torch.no_grad():
-            model.head[3].weight.mul_(0.01)      # unsaturated softmax: see tests/test_gpu_wide_batch.py
         model.to(DEV).train()
         model.pathway_indexs = model.pathway_indexs.to(DEV)
         b = synth.multilevel_batch(batch_size=5, seed=6).to(DEV)

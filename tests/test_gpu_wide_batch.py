@@ -26,10 +26,6 @@ def test_reformulated_layers_with_more_than_32_graphs(mlg):
     torch.manual_seed(5)
     model = mlg.MultilevelGNN(args)
     synth.multilevel_params(model)
-    with torch.no_grad():
-        # keep the 2-class softmax away from saturation: at p ~ 1e-5 its backward (p * (g - p.g), ATen's formula as well) loses
-        # eps / p ~ 1 % to cancellation, which would turn last-bit differences of the two paths' logits into visible ones
-        model.head[3].weight.mul_(0.01)
     model.to(DEV).train()
     model.pathway_indexs = model.pathway_indexs.to(DEV)
     b = synth.multilevel_batch(batch_size=40, seed=9).to(DEV)
@@ -37,12 +33,18 @@ def test_reformulated_layers_with_more_than_32_graphs(mlg):
     params = [p for n, p in model.named_parameters() if p.requires_grad and not n.endswith("lin_l.weight")]
     defaults = (Fn.FACTORED_RANK1, Fn.TRANSFORM_FIRST)
 
+    Rw = torch.randn(40, 32, 146, 6, generator=torch.Generator().manual_seed(2)).to(DEV)
+
     def run(factored, tfirst):
         Fn.FACTORED_RANK1, Fn.TRANSFORM_FIRST = factored, tfirst
         torch.manual_seed(11)
         try:
             pred, feat = model(b)
-            loss = (pred * torch.arange(pred.numel(), device=DEV).reshape(pred.shape)).sum() + feat.square().mean()
+            # a smooth loss on the pooled features: the head (max-pool / ReLU branches, dropout) is NOT what this test is about,
+            # and one hidden unit whose pre-activation sits within fp32 rounding of 0 flips between the two paths (found on
+            # B200: replica 4 alone off by 21 % in dL/dfeat, every other replica identical) -- tests/test_gpu_head.py and
+            # the full-size oracle tests cover the head
+            loss = (feat * Rw).sum() + 50.0 * feat.square().sum()
             g = torch.autograd.grad(loss, params, allow_unused=True)
             torch.cuda.synchronize()
         finally:
