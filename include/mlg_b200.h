@@ -394,11 +394,12 @@ int mlg_pool_bwd_w(const float* g_out_cl, const float* x, const float* vm, const
  * g_x as above; per-graph partial weight gradients go to workspace [B*G*P] floats and are reduced over the
  * graphs in a fixed order into g_w.  C <= 128.  Node-side structures as for mlg_pool_bwd_x.
  * mask_input != 0: g_x *= (x > 0 ? 1 : mask_slope), the derivative of the (Leaky)ReLU that produced x (the last GNN
- * layer's output), so that layer receives dL/dz directly and skips its own activation-backward pass. */
+ * layer's output), so that layer receives dL/dz directly and skips its own activation-backward pass.
+ * w_mask [G] (or NULL): w was params * w_mask[g] (info_mask, multilevel_gnn.py:222); g_w is then dL/dparams. */
 int mlg_pool_bwd(const float* g_out_cl, const float* x, const float* vm, const float* w, const int32_t* node_rowptr,
                  const int32_t* node_slot, const int32_t* seg_of_slot, int64_t B, int64_t N, int64_t C, int64_t G,
                  int64_t S, int64_t P, int64_t replicas, float* g_x, float* g_w, float* workspace, int mask_input,
-                 float mask_slope, void* stream);
+                 float mask_slope, const float* w_mask, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Dilated kNN graph (models/gcn_lib/sparse/torch_edge.py:53-104, dense/torch_edge.py:32-58):

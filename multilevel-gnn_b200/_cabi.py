@@ -106,7 +106,7 @@ _SIGNATURES = {
     "mlg_pool_bwd_w": (_c_int, [_c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_i64, _c_i64, _c_i64, _c_i64, _c_i64,
                                 _c_i64, _c_int, _c_i64, _c_vp, _c_vp]),
     "mlg_pool_bwd": (_c_int, [_c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_i64, _c_i64, _c_i64, _c_i64, _c_i64, _c_i64,
-                              _c_i64, _c_vp, _c_vp, _c_vp, _c_int, _c_f32, _c_vp]),
+                              _c_i64, _c_vp, _c_vp, _c_vp, _c_int, _c_f32, _c_vp, _c_vp]),
     "mlg_cast_bf16": (_c_int, [_c_vp, _c_i64, _c_i64, _c_i64, _c_i64, _c_int, _c_vp, _c_i64, _c_vp]),
     "mlg_gemm_bf16": (_c_int, [_c_vp, _c_i64, _c_i64, _c_vp, _c_i64, _c_i64, _c_vp, _c_i64, _c_i64, _c_i64, _c_i64,
                                _c_i64, _c_i64, _c_f32, _c_vp]),

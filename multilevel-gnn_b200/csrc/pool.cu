@@ -525,12 +525,15 @@ pool_bwd_fused2_kernel(const float* __restrict__ g_cl, const float* __restrict__
   }
 }
 
-__global__ void pool_wgrad_reduce_kernel(const float* __restrict__ part, int B, long long gp, float* __restrict__ g_w) {
+// g_w = sum over the graphs' partials (fixed order); w_mask: the projection weights were w = params * mask[g] (info_mask of
+// multilevel_gnn.py:222), so the gradient w.r.t. params is the sum times mask[g] -- no separate elementwise backward pass
+__global__ void pool_wgrad_reduce_kernel(const float* __restrict__ part, int B, long long gp, int P, const float* __restrict__ w_mask,
+                                         float* __restrict__ g_w) {
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (i >= gp) return;
   float s = 0.f;
   for (int b = 0; b < B; ++b) s += part[(size_t)b * gp + i];
-  g_w[i] = s;
+  g_w[i] = w_mask ? s * __ldg(w_mask + i / P) : s;
 }
 
 #define MLG_P_SWITCH(P, CALL)                                           \
@@ -618,7 +621,8 @@ extern "C" int mlg_pool_bwd_w(const float* g_out_cl, const float* x, const float
 extern "C" int mlg_pool_bwd(const float* g_out_cl, const float* x, const float* vm, const float* w,
                             const int32_t* node_rowptr, const int32_t* node_slot, const int32_t* seg_of_slot,
                             int64_t B, int64_t N, int64_t C, int64_t G, int64_t S, int64_t P, int64_t replicas,
-                            float* g_x, float* g_w, float* workspace, int mask_input, float mask_slope, void* stream) {
+                            float* g_x, float* g_w, float* workspace, int mask_input, float mask_slope, const float* w_mask,
+                            void* stream) {
   MLG_CHECK_ARG(g_out_cl && x && w && node_rowptr && node_slot && seg_of_slot && g_x && g_w && workspace,
                 "mlg_pool_bwd: null pointer");
   int rc = check_dims("mlg_pool_bwd", B, N, C, G, S, P);
@@ -644,7 +648,7 @@ extern "C" int mlg_pool_bwd(const float* g_out_cl, const float* x, const float* 
     else { MLG_POOL_F2(4, 0); }
 #undef MLG_POOL_F2
     MLG_CHECK_LAUNCH("mlg_pool_bwd(fused2)");
-    pool_wgrad_reduce_kernel<<<mlg_ceil_div(G * P, 256), 256, 0, st>>>(workspace, (int)B, G * P, g_w);
+    pool_wgrad_reduce_kernel<<<mlg_ceil_div(G * P, 256), 256, 0, st>>>(workspace, (int)B, G * P, (int)P, w_mask, g_w);
     MLG_CHECK_LAUNCH("mlg_pool_bwd(reduce)");
     return MLG_OK;
   }
@@ -661,7 +665,7 @@ extern "C" int mlg_pool_bwd(const float* g_out_cl, const float* x, const float* 
   else { MLG_POOL_FUSED(4); }
 #undef MLG_POOL_FUSED
   MLG_CHECK_LAUNCH("mlg_pool_bwd(fused)");
-  pool_wgrad_reduce_kernel<<<mlg_ceil_div(G * P, 256), 256, 0, st>>>(workspace, (int)B, G * P, g_w);
+  pool_wgrad_reduce_kernel<<<mlg_ceil_div(G * P, 256), 256, 0, st>>>(workspace, (int)B, G * P, (int)P, w_mask, g_w);
   MLG_CHECK_LAUNCH("mlg_pool_bwd(reduce)");
   return MLG_OK;
 }

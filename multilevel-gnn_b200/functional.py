@@ -72,6 +72,12 @@ GRAD_SLOTS_ENABLED = False   # set by train.Trainer around its own autograd.grad
                              # the in-place result to .grad a second time)
 
 
+def _slot_or_empty(param, like):
+    """The parameter's bucket slot (functional.grad_slot) or a fresh buffer shaped like ``like``."""
+    slot = grad_slot(param, like.shape) if param is not None else None
+    return slot if slot is not None else torch.empty_like(like)
+
+
 def grad_slot(param, shape):
     """A preallocated gradient destination for ``param`` if the trainer registered one (train.GradBucket marks its
     views with ``_mlg_grad_slot``): backward kernels then write the gradient straight into the flat bucket and the
@@ -516,6 +522,66 @@ ORDER_R1F = _flag("MLG_ORDER_R1F", True)       # mlg_sage_rank1_fwd
 ORDER_TF = _flag("MLG_ORDER_TF", True)         # transform-first layer: forward / backward aggregation
 
 
+# Independent branches of the backward pass on forked streams (captured by the trainer's CUDA graph as parallel branches):
+# a layer's weight gradient does not feed the input-gradient chain, so it runs next to it instead of in front of it.
+# Both branches are HBM streams, so the win is the latency / tail overlap, not 2x.  The fork is joined back into the
+# launching stream at the END of the backward pass (autograd engine callback); tensors the side branch reads stay
+# referenced until then (no cross-stream reuse by the caching allocator).
+PARALLEL_BACKWARD = _flag("MLG_PARALLEL_BACKWARD", True)
+# Set by train.Trainer around its own autograd.grad call only: the gradients a forked branch produces may not be touched
+# before the end-of-backward join, which holds for the trainer (it stores them after the pass) but not for an arbitrary
+# loss.backward(), whose AccumulateGrad nodes run on the launching stream as soon as a Function returns.
+PARALLEL_ACTIVE = False
+_SIDE_STREAMS = {}
+
+
+def _side_stream(device, idx):
+    key = (device.index if device.index is not None else torch.cuda.current_device(), idx)
+    if key not in _SIDE_STREAMS:
+        _SIDE_STREAMS[key] = torch.cuda.Stream(device=device)
+    return _SIDE_STREAMS[key]
+
+
+class _Forked:
+    """with _Forked(device, idx, keep=[tensors the branch reads]) as f: ... enqueue the branch ...
+    Inside the block the current stream is a side stream that waits for everything enqueued so far; leaving the block
+    registers the join for the end of the backward pass.  Outside a backward pass, or with PARALLEL_BACKWARD off, the
+    block simply runs on the current stream."""
+
+    def __init__(self, device, idx, keep=()):
+        self.device, self.idx, self.keep = device, idx, list(keep)
+        self.active = False
+
+    def __enter__(self):
+        if not (PARALLEL_BACKWARD and PARALLEL_ACTIVE and self.device.type == "cuda"):
+            return self
+        self.main = torch.cuda.current_stream(self.device)
+        self.side = _side_stream(self.device, self.idx)
+        self.side.wait_stream(self.main)
+        self.ctx = torch.cuda.stream(self.side)
+        self.ctx.__enter__()
+        self.active = True
+        return self
+
+    def hold(self, *tensors):
+        self.keep.extend(t for t in tensors if t is not None)
+
+    def __exit__(self, *exc):
+        if not self.active:
+            return False
+        self.ctx.__exit__(*exc)
+        main, side, keep = self.main, self.side, self.keep
+
+        def join(_keep=keep):
+            main.wait_stream(side)
+
+        try:
+            torch.autograd.Variable._execution_engine.queue_callback(join)
+        except RuntimeError:          # not inside a backward pass: join right away
+            join()
+        return False
+
+
 class SageLayer(torch.autograd.Function):
     """One whole SAGEConv layer (torch_vertex.py:269-294 with RSAGEConv's Linear+activation MLP):
         out = act( [x | agg_x] @ [W1 | W2 @ W_r]^T + b ),   nn.0.weight = [W1 | W2], lin_r.weight = W_r
@@ -534,6 +600,7 @@ class SageLayer(torch.autograd.Function):
         gradient is multiplied by the activation derivative inside the backward aggregation's epilogue;
         ``out_premasked`` -- the consumer of y does the same for this layer, so backward takes gy as dL/dz."""
         _cabi.require_cuda(x, lin_r_w, nn_w)
+        ctx.wparams = (lin_r_w, nn_w, nn_b)      # their gradients are written straight into the trainer's bucket slots
         xd = _f32c(x.detach())
         rank1 = xs is not None
         xs_d = _f32c(xs.detach().reshape(-1)) if rank1 else None
@@ -677,15 +744,19 @@ class SageLayer(torch.autograd.Function):
                     _cabi.fptr(topo.fwd_val, True), _cabi.iptr(topo.fwd_order if ORDER_R1B else None, True), n1, cout, B,
                     _cabi.fptr(h),
                     _cabi.fptr(g12), 2 * cout, _cabi.fptr(gbr), _cabi.stream_ptr()), "mlg_sage_rank1_bwd_rows")
-            gather_sum(h, bw.rowptr, topo.bwd2fwd, n1, out=g12[:, cout:], order=topo.bwd_order, tag="sage_rank1_bwd_seg")
             g_b = None
             if ctx.has_bias:       # column sums of the per-row partials: one streaming pass, fixed order (mlg_wcolsum)
-                g_b = torch.empty(cout, dtype=torch.float32, device=gz.device)
-                ws_bytes = L.mlg_wcolsum_workspace_bytes(n1, cout)
-                ws = torch.empty(ws_bytes // 4, dtype=torch.float32, device=gz.device)
-                with torch.cuda.device(gz.device):
-                    _cabi.check(L.mlg_wcolsum(_cabi.fptr(gbr), cout, None, n1, cout, None, _cabi.fptr(g_b), _cabi.fptr(ws),
-                                              ws_bytes, _cabi.stream_ptr()), "mlg_wcolsum")
+                with _Forked(gz.device, 1, keep=(gbr,)) as fk:      # independent of the segment sum below
+                    g_b = grad_slot(ctx.wparams[2], (cout,))
+                    if g_b is None:
+                        g_b = torch.empty(cout, dtype=torch.float32, device=gz.device)
+                    ws_bytes = L.mlg_wcolsum_workspace_bytes(n1, cout)
+                    ws = torch.empty(ws_bytes // 4, dtype=torch.float32, device=gz.device)
+                    with torch.cuda.device(gz.device):
+                        _cabi.check(L.mlg_wcolsum(_cabi.fptr(gbr), cout, None, n1, cout, None, _cabi.fptr(g_b), _cabi.fptr(ws),
+                                                  ws_bytes, _cabi.stream_ptr()), "mlg_wcolsum")
+                    fk.hold(g_b, ws)
+            gather_sum(h, bw.rowptr, topo.bwd2fwd, n1, out=g12[:, cout:], order=topo.bwd_order, tag="sage_rank1_bwd_seg")
         else:
             slices = L.mlg_gather_sum_slices(n1, cout, B)
             parts = torch.empty(slices * n1 * 3 * cout, dtype=torch.float32, device=gz.device)
@@ -700,16 +771,19 @@ class SageLayer(torch.autograd.Function):
                     _cabi.fptr(p12), _cabi.fptr(pb), _cabi.stream_ptr()), "mlg_sage_rank1_bwd")
             g12 = p12.sum(0) if slices > 1 else p12[0]                 # [n1, 2cout] = [g_E_self | g_E_nbr]
             g_b = pb.sum(0) if ctx.has_bias else None
+        # [2cout, cin] = [g_W1 ; g_(W2 W_r)] = g12^T emb (a 15 405-deep reduction) + the weight un-folding: on a forked stream
+        # next to the table -> embedding product
+        with _Forked(gz.device, 2, keep=(g12, emb, w_nn, w_r)) as fk:
+            g_wst, _ = xty(g12, emb, tag="sage_rank1_wgrad")
+            g_wcat = g_wst.view(2, cout, cin).permute(1, 0, 2).reshape(cout, 2 * cin)
+            g_wnn, g_wr = _slot_or_empty(ctx.wparams[1], w_nn), _slot_or_empty(ctx.wparams[0], w_r)
+            with torch.cuda.device(gz.device):
+                _cabi.check(L.mlg_sage_fold_bwd(_cabi.fptr(g_wcat), _cabi.fptr(w_nn), _cabi.fptr(w_r), cout, cin,
+                                                w_r.shape[0], _cabi.fptr(g_wnn), _cabi.fptr(g_wr), _cabi.stream_ptr()),
+                            "mlg_sage_fold_bwd")
+            fk.hold(g_wst, g_wcat, g_wnn, g_wr)
         slot = grad_slot(ctx.emb_param, (n1, cin)) if ctx.emb_param is not None else None
         g_emb = torch.mm(g12, wst, out=slot) if slot is not None else torch.mm(g12, wst)
-        # [2cout, cin] = [g_W1 ; g_(W2 W_r)] = g12^T emb: a 15 405-deep reduction (cuBLAS picks a one-wave SIMT kernel: 48 us)
-        g_wst, _ = xty(g12, emb, tag="sage_rank1_wgrad")
-        g_wcat = g_wst.view(2, cout, cin).permute(1, 0, 2).reshape(cout, 2 * cin)
-        g_wnn, g_wr = torch.empty_like(w_nn), torch.empty_like(w_r)
-        with torch.cuda.device(gz.device):
-            _cabi.check(L.mlg_sage_fold_bwd(_cabi.fptr(g_wcat), _cabi.fptr(w_nn), _cabi.fptr(w_r), cout, cin,
-                                            w_r.shape[0], _cabi.fptr(g_wnn), _cabi.fptr(g_wr), _cabi.stream_ptr()),
-                        "mlg_sage_fold_bwd")
         return g_emb, None, g_wr, g_wnn, g_b, None, None, None, None, None
 
     @staticmethod
@@ -733,26 +807,28 @@ class SageLayer(torch.autograd.Function):
                    tag="sage_aggr_bwd")
         needs = ctx.needs_input_grad
         gx = g_wr = g_wnn = g_b = None
-        # weight gradient FIRST, input gradient LAST: the producer's backward kernel reads gx right away, and it only finds it
-        # in L2 if nothing streams 250 MB through the cache in between (measured: 58 us vs 185 us for that kernel)
+        # the weight gradient (tensor-core x^T G over the row pairs + fold) on a forked stream next to the input-gradient GEMM
+        # and everything autograd runs after it (the first layer's backward); joined at the end of the backward pass
         if needs[2] or needs[3] or needs[4]:
-            if n % 2 == 0 and 4 * cout == 128 and 2 * cin == 128:
-                # tensor-core weight gradient on ROW PAIRS: [G_even | G_odd]^T [x_even | x_odd] is 128 x 128; its two diagonal
-                # blocks are the even- and odd-row halves of G^T x (the off-diagonal blocks are discarded)
-                o2, cs2 = xty(g_uv.view(n // 2, 4 * cout), x.view(n // 2, 2 * cin), want_colsum=ctx.has_bias, tag="sage_wgrad")
-                g_wst = o2[:2 * cout, :cin] + o2[2 * cout:, cin:]
-                if ctx.has_bias:
-                    g_b = cs2[:cout] + cs2[2 * cout:3 * cout]
-            else:
-                g_wst, cs = xty(g_uv, x, want_colsum=ctx.has_bias, tag="sage_wgrad")
-                if ctx.has_bias:
-                    g_b = cs[:cout]
-            g_wcat = g_wst.view(2, cout, cin).permute(1, 0, 2).reshape(cout, 2 * cin)
-            g_wnn, g_wr = torch.empty_like(w_nn), torch.empty_like(w_r)
-            with torch.cuda.device(gz.device):
-                _cabi.check(L.mlg_sage_fold_bwd(_cabi.fptr(g_wcat), _cabi.fptr(w_nn), _cabi.fptr(w_r), cout, cin,
-                                                w_r.shape[0], _cabi.fptr(g_wnn), _cabi.fptr(g_wr), _cabi.stream_ptr()),
-                            "mlg_sage_fold_bwd")
+            with _Forked(gz.device, 0, keep=(g_uv, x, w_nn, w_r)) as fk:
+                if n % 2 == 0 and 4 * cout == 128 and 2 * cin == 128:
+                    # tensor-core weight gradient on ROW PAIRS: [G_even | G_odd]^T [x_even | x_odd] is 128 x 128; its two
+                    # diagonal blocks are the even- and odd-row halves of G^T x (the off-diagonal blocks are discarded)
+                    o2, cs2 = xty(g_uv.view(n // 2, 4 * cout), x.view(n // 2, 2 * cin), want_colsum=ctx.has_bias, tag="sage_wgrad")
+                    g_wst = o2[:2 * cout, :cin] + o2[2 * cout:, cin:]
+                    if ctx.has_bias:
+                        g_b = torch.add(cs2[:cout], cs2[2 * cout:3 * cout], out=grad_slot(ctx.wparams[2], (cout,)))
+                else:
+                    g_wst, cs = xty(g_uv, x, want_colsum=ctx.has_bias, tag="sage_wgrad")
+                    if ctx.has_bias:
+                        g_b = cs[:cout]
+                g_wcat = g_wst.view(2, cout, cin).permute(1, 0, 2).reshape(cout, 2 * cin)
+                g_wnn, g_wr = _slot_or_empty(ctx.wparams[1], w_nn), _slot_or_empty(ctx.wparams[0], w_r)
+                with torch.cuda.device(gz.device):
+                    _cabi.check(L.mlg_sage_fold_bwd(_cabi.fptr(g_wcat), _cabi.fptr(w_nn), _cabi.fptr(w_r), cout, cin,
+                                                    w_r.shape[0], _cabi.fptr(g_wnn), _cabi.fptr(g_wr), _cabi.stream_ptr()),
+                                "mlg_sage_fold_bwd")
+                fk.hold(g_wst, g_wcat, g_wnn, g_wr, g_b)
         if needs[0]:
             gx = tall_matmul(g_uv, wst.t().contiguous(), tag="sage_dgrad_gemm")         # dL/dx (the producer masks it itself)
         return gx, None, g_wr, g_wnn, (g_b if ctx.has_bias else None), None, None, None, None, None
@@ -776,7 +852,7 @@ class SageLayer(torch.autograd.Function):
         gx = g_wr = g_wnn = g_b = None
         if needs[2] or needs[3] or needs[4]:
             g_wcat, g_b = xty(gz, xcat, want_colsum=ctx.has_bias, tag="sage_wgrad")       # [cout, 2cin], [cout]
-            g_wnn, g_wr = torch.empty_like(w_nn), torch.empty_like(w_r)
+            g_wnn, g_wr = _slot_or_empty(ctx.wparams[1], w_nn), _slot_or_empty(ctx.wparams[0], w_r)
             with torch.cuda.device(gz.device):
                 _cabi.check(_cabi.lib().mlg_sage_fold_bwd(_cabi.fptr(g_wcat), _cabi.fptr(w_nn), _cabi.fptr(w_r), cout, cin,
                                                           w_r.shape[0], _cabi.fptr(g_wnn), _cabi.fptr(g_wr),
@@ -965,10 +1041,17 @@ class PathwayPool(torch.autograd.Function):
     permute(0,3,1,2) VIEW of the channel-last buffer [B,S,P,C] the kernel writes."""
 
     @staticmethod
-    def forward(ctx, x, w, vm, layout, in_slope=None):
-        """``in_slope``: x is the output of a (Leaky)ReLU with that slope whose producer expects dL/dz (see SageLayer)."""
+    def forward(ctx, x, w, vm, layout, in_slope=None, w_mask=None):
+        """``in_slope``: x is the output of a (Leaky)ReLU with that slope whose producer expects dL/dz (see SageLayer).
+        ``w_mask`` [G, 1] or [G]: the projection weights are w * w_mask (learnable_pca_params * info_mask,
+        multilevel_gnn.py:222); the product and its backward are folded in (the gradient returned for ``w`` is dL/dw)."""
         L = _cabi.lib()
         _cabi.require_cuda(x, w)
+        ctx.w_param = w
+        ctx.w_mask = None
+        if w_mask is not None:
+            ctx.w_mask = _f32c(w_mask.detach().reshape(-1))
+            w = w.detach() * ctx.w_mask.reshape(-1, 1)
         xd, wd = _f32c(x.detach()), _f32c(w.detach())
         B, N, G, S = layout.B, layout.N, layout.G, layout.S
         C, P = xd.shape[1], wd.shape[1]
@@ -994,7 +1077,8 @@ class PathwayPool(torch.autograd.Function):
         g_cl = g.float().permute(0, 2, 3, 1).contiguous()     # [B,S,P,C]; no copy when g is already channel-last
         gx = gw = None
         if ctx.needs_input_grad[0] and ctx.needs_input_grad[1] and C <= 128 and not lay.wrap_negative:
-            gx, gw = torch.empty_like(xd), torch.empty_like(wd)
+            slot = grad_slot(ctx.w_param, wd.shape)
+            gx, gw = torch.empty_like(xd), (slot if slot is not None else torch.empty_like(wd))
             node = lay.node_csr
             ws = torch.empty(B * G * P, dtype=torch.float32, device=xd.device)
             with torch.cuda.device(xd.device), _cabi.span("pool_bwd", 2 * (4 * C * B * N) + 4 * B * C * S * P):
@@ -1002,8 +1086,8 @@ class PathwayPool(torch.autograd.Function):
                                            _cabi.iptr(node.rowptr), _cabi.iptr(node.col), _cabi.iptr(lay.seg_of_slot),
                                            B, N, C, G, S, P, lay.replicas, _cabi.fptr(gx), _cabi.fptr(gw), _cabi.fptr(ws),
                                            0 if ctx.in_slope is None else 1, 0.0 if ctx.in_slope is None else ctx.in_slope,
-                                           _cabi.stream_ptr()), "mlg_pool_bwd")
-            return gx, gw, None, None, None
+                                           _cabi.fptr(ctx.w_mask, True), _cabi.stream_ptr()), "mlg_pool_bwd")
+            return gx, gw, None, None, None, None
         with torch.cuda.device(xd.device):
             if ctx.needs_input_grad[0]:
                 gx = torch.empty_like(xd)
@@ -1022,7 +1106,9 @@ class PathwayPool(torch.autograd.Function):
                                 "mlg_pool_bwd_w")
         if gx is not None and ctx.in_slope is not None:      # unfused fallback of the activation-derivative mask
             gx = torch.where(xd > 0, gx, gx * ctx.in_slope)
-        return gx, gw, None, None, None
+        if gw is not None and ctx.w_mask is not None:
+            gw = gw * ctx.w_mask.reshape(-1, 1)
+        return gx, gw, None, None, None, None
 
 
 def _drop_bits(n, device):

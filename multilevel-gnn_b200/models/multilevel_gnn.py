@@ -191,8 +191,10 @@ class MultilevelGNN(nn.Module):
 
         layout = graph.pool_layout(gene_pca_match, raw_indice, n3, 146 * 3,
                                    wrap_negative=not args.pca_match_mask, static_key=static_key)
-        w = self.learnable_pca_params * self.info_mask                   # [G, P]
-        x = Fn.PathwayPool.apply(x, w, vm, layout, slopes[-1] if pool_masks else None)   # [B, C, 438, P]
+        # w = learnable_pca_params * info_mask [G, P] (multilevel_gnn.py:222): the mask product and its backward are folded
+        # into the pool Function (the projection gradient lands in the parameter's bucket slot)
+        x = Fn.PathwayPool.apply(x, self.learnable_pca_params, vm, layout, slopes[-1] if pool_masks else None,
+                                 self.info_mask)                                      # [B, C, 438, P]
         return x
 
     def forward(self, input_batch, x=None, gene_pca_match=None, raw_indice=None, age=None, require_grad=True,

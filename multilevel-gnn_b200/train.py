@@ -307,11 +307,11 @@ class Trainer:
         loss = self.loss(batch)
         # == optimizer.zero_grad(); loss.backward() with the gradients landing in the bucket views (p.grad)
         from . import functional as Fn
-        Fn.GRAD_SLOTS_ENABLED = loss.is_cuda
+        Fn.GRAD_SLOTS_ENABLED = Fn.PARALLEL_ACTIVE = loss.is_cuda
         try:
             grads = torch.autograd.grad(loss, self.params, allow_unused=True)
         finally:
-            Fn.GRAD_SLOTS_ENABLED = False
+            Fn.GRAD_SLOTS_ENABLED = Fn.PARALLEL_ACTIVE = False
         self.bucket.store(grads)
         return loss.detach()
 
