@@ -454,11 +454,17 @@ int mlg_adam_step(float* params, const float* grads, float* exp_avg, float* exp_
  * gradient bucket, flat parameter buffer and a flag block (mlg_peer_flag_bytes(), zero-initialised) in device memory
  * from mlg_peer_alloc (cudaMalloc, zeroed) that the other ranks of the box map with mlg_peer_export / mlg_peer_open
  * (CUDA IPC, 64-byte handle).  peer_grads / peer_params / peer_flags are HOST arrays of `world` device pointers indexed
- * by rank (entry `rank` = this rank's own buffers).  n_padded: elements per buffer, a multiple of 4*world; rank r owns
- * [r, r+1) * n_padded/world, and exp_avg / exp_avg_sq hold only that shard.  Gradients are summed in rank order and
- * scaled by 1/world, so every rank ends with bitwise identical parameters.  step_dev as in mlg_adam_step.  The kernel
- * synchronises the ranks itself (system-scope flags): every rank must issue the same sequence of calls; a wait longer
- * than timeout_s (<= 0: 5 s) gives up and sets the status word read by mlg_peer_status (0 = ok).  Graph-capturable. */
+ * by rank (entry `rank` = this rank's own buffers).  [lo, hi): the CHUNK of the flat buffers this call updates (lo a multiple
+ * of 4, hi - lo a multiple of 4*world; one flag block, one step counter and one optimizer-state shard PER CHUNK); rank r owns
+ * the r-th 1/world of the chunk, and exp_avg / exp_avg_sq hold only that shard.  Chunks let the trainer update parameters
+ * whose gradients are final early (the classifier head) on a forked branch while backward still runs.  Gradients are summed
+ * in rank order and scaled by 1/world, so every rank ends with bitwise identical parameters.  step_dev as in mlg_adam_step.
+ * The kernel synchronises the ranks itself (system-scope flags): every rank must issue the same sequence of calls.  A wait
+ * longer than timeout_s (<= 0: 5 s) is a hard failure: the update is skipped (parameters and optimizer state untouched), the
+ * status word of this rank AND of every peer is set (sticky: later calls return immediately; mlg_peer_status, 0 = ok) and,
+ * when host_status != NULL (a pinned host int32, device-addressable), 1 is stored there so that the host can poll without a
+ * device synchronisation.  max_blocks > 0 caps the grid (default 96 blocks of 512 threads) for a chunk that runs next to
+ * other kernels.  Graph-capturable. */
 int64_t mlg_peer_flag_bytes(void);
 void* mlg_peer_alloc(int64_t bytes);
 int mlg_peer_free(void* ptr);
@@ -466,8 +472,17 @@ int mlg_peer_export(void* ptr, void* handle64);
 void* mlg_peer_open(const void* handle64);
 int mlg_peer_close(void* ptr);
 int mlg_peer_adam_step(const float* const* peer_grads, float* const* peer_params, void* const* peer_flags, int world,
-                       int rank, int64_t n_padded, float* exp_avg, float* exp_avg_sq, float* step_dev, float lr,
-                       float beta1, float beta2, float eps, float weight_decay, double timeout_s, void* stream);
+                       int rank, int64_t lo, int64_t hi, float* exp_avg, float* exp_avg_sq, float* step_dev, float lr,
+                       float beta1, float beta2, float eps, float weight_decay, double timeout_s, int32_t* host_status,
+                       int max_blocks, void* stream);
+/* Test support (one GPU): `world` ranks whose arenas all live on this device, stepped by ONE cooperative launch (blocks that
+ * wait on one another must be co-resident).  exp_avg / exp_avg_sq / step_dev: HOST arrays of one device pointer per rank;
+ * ranks_dev: device scratch of mlg_peer_emulated_bytes(world) bytes.  Synchronises the stream once (argument upload). */
+int64_t mlg_peer_emulated_bytes(int world);
+int mlg_peer_adam_step_emulated(const float* const* peer_grads, float* const* peer_params, void* const* peer_flags, int world,
+                                int64_t lo, int64_t hi, float* const* exp_avg, float* const* exp_avg_sq, float* const* step_dev,
+                                float lr, float beta1, float beta2, float eps, float weight_decay, double timeout_s,
+                                void* ranks_dev, void* stream);
 int mlg_peer_status(const void* flags, int* status_out);
 
 #ifdef __cplusplus

@@ -120,8 +120,11 @@ _SIGNATURES = {
     "mlg_peer_export": (_c_int, [_c_vp, _c_vp]),
     "mlg_peer_open": (_c_vp, [_c_vp]),
     "mlg_peer_close": (_c_int, [_c_vp]),
-    "mlg_peer_adam_step": (_c_int, [_c_vp, _c_vp, _c_vp, _c_int, _c_int, _c_i64, _c_vp, _c_vp, _c_vp, _c_f32, _c_f32, _c_f32,
-                                    _c_f32, _c_f32, ctypes.c_double, _c_vp]),
+    "mlg_peer_adam_step": (_c_int, [_c_vp, _c_vp, _c_vp, _c_int, _c_int, _c_i64, _c_i64, _c_vp, _c_vp, _c_vp, _c_f32, _c_f32,
+                                    _c_f32, _c_f32, _c_f32, ctypes.c_double, _c_vp, _c_int, _c_vp]),
+    "mlg_peer_emulated_bytes": (_c_i64, [_c_int]),
+    "mlg_peer_adam_step_emulated": (_c_int, [_c_vp, _c_vp, _c_vp, _c_int, _c_i64, _c_i64, _c_vp, _c_vp, _c_vp, _c_f32, _c_f32,
+                                             _c_f32, _c_f32, _c_f32, ctypes.c_double, _c_vp, _c_vp]),
     "mlg_peer_status": (_c_int, [_c_vp, _c_vp]),
     "mlg_adam_step": (_c_int, [_c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_i64, _c_f32, _c_f32, _c_f32, _c_f32, _c_f32, _c_vp]),
     "mlg_knn_graph": (_c_int, [_c_vp, _c_i64, _c_i64, _c_i64, _c_i64, _c_i64, _c_int, _c_vp, _c_vp, _c_vp, _c_vp,

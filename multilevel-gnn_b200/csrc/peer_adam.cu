@@ -13,8 +13,17 @@
 // with fixed pointers the whole training step (forward, loss, backward, this kernel) is ONE CUDA graph per rank.
 // Per-GPU traffic: (world-1)/world * 4n bytes read and the same written over NVLink + 16 B/parameter of local state.
 //
-// Flag block (uint32, one per rank, peer-writable):  [0..7] ready[src]   [8..15] done[src]   [16] epoch   [17] block
-// counter   [18] status (1 = a wait timed out: peers out of step; the host checks it outside the timed path).
+// The bucket may be updated in CHUNKS (mlg_peer_adam_step's [lo, hi) range + a flag block per chunk): the trainer launches the
+// chunk holding the classifier head -- 62 % of the gbm parameters, final right after the head's backward kernel -- on a forked
+// graph branch while the rest of backward still runs, so only the last chunk's exchange sits on the critical path.
+//
+// Flag block (uint32, one per rank and chunk, peer-writable):  [0..7] ready[src]   [8..15] done[src]   [16] epoch   [17] block
+// counter   [18] status.  A wait that exceeds the timeout is a HARD failure: the rank sets its own status word, the status
+// word of EVERY peer and the host-visible status word (pinned memory), skips the update (parameters and optimizer state stay
+// untouched, so the replicas do not silently diverge) and every later launch returns immediately; the host (Trainer.step)
+// reads the pinned word before each step and raises on all ranks.
+#include <cooperative_groups.h>
+
 #include "common.cuh"
 #include "../../include/mlg_b200.h"
 
@@ -30,7 +39,8 @@ struct PeerP {
   unsigned* flags[kMaxWorld];
   float* m;          // exp_avg of the owned shard      [hi - lo]
   float* v;          // exp_avg_sq of the owned shard   [hi - lo]
-  float* step_dev;   // Adam step counter (float, as mlg_adam_step)
+  float* step_dev;   // Adam step counter of this chunk (float, as mlg_adam_step)
+  int* host_status;  // pinned host word (or NULL)
   long long lo, hi;  // owned shard, multiples of 4
   int world, rank;
   float lr, b1, b2, eps, wd;
@@ -51,20 +61,30 @@ __device__ __forceinline__ float4 ld_peer4(const float* p) {   // never cached: 
   return v;
 }
 
-// wait until flag[i] has reached `epoch` for every rank i < world (threads 0..world-1 poll one flag each)
-__device__ __forceinline__ void wait_all(unsigned* mine, int base, int world, unsigned epoch, long long timeout) {
-  if ((int)threadIdx.x < world) {
+// a failed wait: sticky on this rank, broadcast to every peer and to the host
+__device__ __forceinline__ void fail_everywhere(const PeerP& P) {
+  for (int r = 0; r < P.world; ++r) st_release_sys(P.flags[r] + F_STATUS, 1u);
+  if (P.host_status) *reinterpret_cast<volatile int*>(P.host_status) = 1;
+  __threadfence_system();
+}
+
+// wait until flag[i] has reached `epoch` for every rank i < world (threads 0..world-1 poll one flag each); false = gave up
+__device__ __forceinline__ bool wait_all(const PeerP& P, unsigned* mine, int base, unsigned epoch, int* shared_ok) {
+  if (threadIdx.x == 0) *shared_ok = 1;
+  __syncthreads();
+  if ((int)threadIdx.x < P.world) {
     const unsigned* f = mine + base + threadIdx.x;
     const long long t0 = clock64();
     while ((int)(ld_acquire_sys(f) - epoch) < 0) {
-      if (clock64() - t0 > timeout) {
-        mine[F_STATUS] = 1u;
+      if (clock64() - t0 > P.timeout_clocks || ld_acquire_sys(mine + F_STATUS) != 0u) {
+        *shared_ok = 0;
         break;
       }
       __nanosleep(64);
     }
   }
   __syncthreads();
+  return *shared_ok != 0;
 }
 
 __device__ __forceinline__ void adam_one(float& p, float g, float& m, float& v, float b1, float b2, float eps, float wd,
@@ -76,27 +96,31 @@ __device__ __forceinline__ void adam_one(float& p, float g, float& m, float& v, 
   p -= step_size * (m / denom);
 }
 
-__global__ void __launch_bounds__(kThreads) peer_adam_kernel(const PeerP P) {
-  __shared__ int is_last;
+__device__ __forceinline__ void peer_adam_body(const PeerP& P, int block, int nblocks) {
+  __shared__ int is_last, ok;
   unsigned* mine = P.flags[P.rank];
   const int world = P.world;
+  if (*reinterpret_cast<volatile unsigned*>(mine + F_STATUS) != 0u) return;   // sticky failure: do nothing
   // the epoch word is only advanced by the LAST block of a run, after every block of that run has read it
   const unsigned epoch = *reinterpret_cast<volatile unsigned*>(mine + F_EPOCH) + 1u;
 
   // ---- 0. gradients of every rank are final ----
-  if (blockIdx.x == 0 && (int)threadIdx.x < world) {
+  if (block == 0 && (int)threadIdx.x < world) {
     __threadfence_system();
     st_release_sys(P.flags[threadIdx.x] + F_READY + P.rank, epoch);
   }
-  wait_all(mine, F_READY, world, epoch, P.timeout_clocks);
+  if (!wait_all(P, mine, F_READY, epoch, &ok)) {
+    if (threadIdx.x == 0) fail_everywhere(P);
+    return;                      // parameters and optimizer state untouched
+  }
 
   // ---- 1. owned shard: sum over ranks in rank order, Adam, broadcast the new values ----
   const float t = *reinterpret_cast<volatile float*>(P.step_dev) + 1.f;
   const float bc1 = 1.f - powf(P.b1, t), bc2 = 1.f - powf(P.b2, t);
   const float step_size = P.lr / bc1, inv_sqrt_bc2 = 1.f / sqrtf(bc2);
   const float inv_world = 1.f / (float)world;
-  const long long stride = (long long)gridDim.x * kThreads * 4;
-  for (long long i = P.lo + ((long long)blockIdx.x * kThreads + threadIdx.x) * 4; i < P.hi; i += stride) {
+  const long long stride = (long long)nblocks * kThreads * 4;
+  for (long long i = P.lo + ((long long)block * kThreads + threadIdx.x) * 4; i < P.hi; i += stride) {
     float4 g[kMaxWorld];
 #pragma unroll
     for (int r = 0; r < kMaxWorld; ++r)
@@ -128,7 +152,7 @@ __global__ void __launch_bounds__(kThreads) peer_adam_kernel(const PeerP P) {
   if (threadIdx.x == 0) {
     const unsigned c = atomicAdd(mine + F_COUNT, 1u);
     __threadfence();
-    is_last = (c == gridDim.x - 1);
+    is_last = (c == (unsigned)nblocks - 1);
   }
   __syncthreads();
   if (!is_last) return;
@@ -136,13 +160,50 @@ __global__ void __launch_bounds__(kThreads) peer_adam_kernel(const PeerP P) {
     __threadfence_system();
     st_release_sys(P.flags[threadIdx.x] + F_DONE + P.rank, epoch);
   }
-  wait_all(mine, F_DONE, world, epoch, P.timeout_clocks);
+  const bool done = wait_all(P, mine, F_DONE, epoch, &ok);
   if (threadIdx.x == 0) {
+    if (!done) fail_everywhere(P);
     mine[F_COUNT] = 0u;
     *reinterpret_cast<volatile float*>(P.step_dev) = t;
     __threadfence();
     *reinterpret_cast<volatile unsigned*>(mine + F_EPOCH) = epoch;
   }
+}
+
+__global__ void __launch_bounds__(kThreads) peer_adam_kernel(const PeerP P) { peer_adam_body(P, blockIdx.x, gridDim.x); }
+
+// TEST SUPPORT: all ranks of a job as ONE cooperative launch on one GPU (blockIdx.y = rank), so that the blocks that wait on
+// one another are guaranteed co-resident (separate launches on one GPU are not: B200_PROFILING.md)
+__global__ void __launch_bounds__(kThreads) peer_adam_emulated_kernel(const PeerP* __restrict__ ranks) {
+  __shared__ PeerP P;
+  if (threadIdx.x == 0) P = ranks[blockIdx.y];
+  __syncthreads();
+  peer_adam_body(P, blockIdx.x, gridDim.x);
+}
+
+int fill_peer(PeerP& P, const float* const* peer_grads, float* const* peer_params, void* const* peer_flags, int world, int rank,
+              int64_t lo, int64_t hi, float* exp_avg, float* exp_avg_sq, float* step_dev, float lr, float beta1, float beta2,
+              float eps, float weight_decay, double timeout_s, int* host_status) {
+  MLG_CHECK_ARG(peer_grads && peer_params && peer_flags && exp_avg && exp_avg_sq && step_dev, "mlg_peer_adam_step: null pointer");
+  MLG_CHECK_ARG(world >= 1 && world <= kMaxWorld && rank >= 0 && rank < world, "mlg_peer_adam_step: world must be 1..8");
+  MLG_CHECK_ARG(lo >= 0 && hi >= lo && lo % 4 == 0 && (hi - lo) % (4 * world) == 0,
+                "mlg_peer_adam_step: chunk [lo, hi) must start at a multiple of 4 and hold a multiple of 4*world elements");
+  memset(&P, 0, sizeof(P));
+  for (int r = 0; r < world; ++r) {
+    MLG_CHECK_ARG(peer_grads[r] && peer_params[r] && peer_flags[r], "mlg_peer_adam_step: null peer pointer");
+    MLG_CHECK_ARG(((uintptr_t)peer_grads[r] | (uintptr_t)peer_params[r]) % 16 == 0, "mlg_peer_adam_step: 16-byte alignment");
+    P.grad[r] = peer_grads[r];
+    P.param[r] = peer_params[r];
+    P.flags[r] = (unsigned*)peer_flags[r];
+  }
+  MLG_CHECK_ARG(((uintptr_t)exp_avg | (uintptr_t)exp_avg_sq) % 16 == 0, "mlg_peer_adam_step: 16-byte alignment");
+  const long long shard = (hi - lo) / world;
+  P.m = exp_avg; P.v = exp_avg_sq; P.step_dev = step_dev; P.host_status = host_status;
+  P.lo = lo + shard * rank; P.hi = P.lo + shard;
+  P.world = world; P.rank = rank;
+  P.lr = lr; P.b1 = beta1; P.b2 = beta2; P.eps = eps; P.wd = weight_decay;
+  P.timeout_clocks = (long long)((timeout_s > 0 ? timeout_s : 5.0) * 1.9e9);
+  return MLG_OK;
 }
 
 }  // namespace
@@ -208,36 +269,58 @@ extern "C" int mlg_peer_close(void* ptr) {
 }
 
 extern "C" int mlg_peer_adam_step(const float* const* peer_grads, float* const* peer_params, void* const* peer_flags,
-                                  int world, int rank, int64_t n_padded, float* exp_avg, float* exp_avg_sq,
+                                  int world, int rank, int64_t lo, int64_t hi, float* exp_avg, float* exp_avg_sq,
                                   float* step_dev, float lr, float beta1, float beta2, float eps, float weight_decay,
-                                  double timeout_s, void* stream) {
-  MLG_CHECK_ARG(peer_grads && peer_params && peer_flags && exp_avg && exp_avg_sq && step_dev, "mlg_peer_adam_step: null pointer");
-  MLG_CHECK_ARG(world >= 1 && world <= kMaxWorld && rank >= 0 && rank < world, "mlg_peer_adam_step: world must be 1..8");
-  MLG_CHECK_ARG(n_padded >= 0 && n_padded % (4 * world) == 0, "mlg_peer_adam_step: n_padded must be a multiple of 4*world");
-  if (n_padded == 0) return MLG_OK;
+                                  double timeout_s, int32_t* host_status, int max_blocks, void* stream) {
+  if (hi == lo) return MLG_OK;
   PeerP P;
-  memset(&P, 0, sizeof(P));
-  for (int r = 0; r < world; ++r) {
-    MLG_CHECK_ARG(peer_grads[r] && peer_params[r] && peer_flags[r], "mlg_peer_adam_step: null peer pointer");
-    MLG_CHECK_ARG(((uintptr_t)peer_grads[r] | (uintptr_t)peer_params[r]) % 16 == 0, "mlg_peer_adam_step: 16-byte alignment");
-    P.grad[r] = peer_grads[r];
-    P.param[r] = peer_params[r];
-    P.flags[r] = (unsigned*)peer_flags[r];
-  }
-  MLG_CHECK_ARG(((uintptr_t)exp_avg | (uintptr_t)exp_avg_sq) % 16 == 0, "mlg_peer_adam_step: 16-byte alignment");
-  const long long shard = n_padded / world;
-  P.m = exp_avg; P.v = exp_avg_sq; P.step_dev = step_dev;
-  P.lo = shard * rank; P.hi = P.lo + shard;
-  P.world = world; P.rank = rank;
-  P.lr = lr; P.b1 = beta1; P.b2 = beta2; P.eps = eps; P.wd = weight_decay;
-  P.timeout_clocks = (long long)((timeout_s > 0 ? timeout_s : 5.0) * 1.9e9);
+  if (int rc = fill_peer(P, peer_grads, peer_params, peer_flags, world, rank, lo, hi, exp_avg, exp_avg_sq, step_dev, lr, beta1,
+                         beta2, eps, weight_decay, timeout_s, host_status))
+    return rc;
   // enough blocks to keep ~world float4 loads per thread in flight on every NVLink, few enough that the whole grid is
   // resident next to whatever else the stream overlaps
-  long long blocks = (shard / 4 + kThreads - 1) / kThreads;
-  if (blocks > 96) blocks = 96;
+  // (max_blocks > 0: a chunk that runs NEXT TO other kernels -- the early head chunk -- takes fewer SMs away from them)
+  long long blocks = ((P.hi - P.lo) / 4 + kThreads - 1) / kThreads;
+  const long long cap = max_blocks > 0 ? max_blocks : 96;
+  if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   peer_adam_kernel<<<(unsigned)blocks, kThreads, 0, (cudaStream_t)stream>>>(P);
   MLG_CHECK_LAUNCH("mlg_peer_adam_step");
+  return MLG_OK;
+}
+
+// TEST SUPPORT (single GPU): `world` ranks whose arenas live on this device, stepped by ONE cooperative launch.
+// peer_* tables: world pointers each, shared by all ranks; exp_avg / exp_avg_sq / step_dev: one per rank.
+// ranks_dev: device scratch of mlg_peer_emulated_bytes(world) bytes.
+extern "C" int64_t mlg_peer_emulated_bytes(int world) { return (int64_t)world * (int64_t)sizeof(PeerP); }
+
+extern "C" int mlg_peer_adam_step_emulated(const float* const* peer_grads, float* const* peer_params, void* const* peer_flags,
+                                           int world, int64_t lo, int64_t hi, float* const* exp_avg, float* const* exp_avg_sq,
+                                           float* const* step_dev, float lr, float beta1, float beta2, float eps,
+                                           float weight_decay, double timeout_s, void* ranks_dev, void* stream) {
+  MLG_CHECK_ARG(exp_avg && exp_avg_sq && step_dev && ranks_dev, "mlg_peer_adam_step_emulated: null pointer");
+  if (hi == lo) return MLG_OK;
+  PeerP host[kMaxWorld];
+  for (int r = 0; r < world; ++r)
+    if (int rc = fill_peer(host[r], peer_grads, peer_params, peer_flags, world, r, lo, hi, exp_avg[r], exp_avg_sq[r], step_dev[r],
+                           lr, beta1, beta2, eps, weight_decay, timeout_s, nullptr))
+      return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  MLG_CUDA(cudaMemcpyAsync(ranks_dev, host, sizeof(PeerP) * world, cudaMemcpyHostToDevice, st));
+  MLG_CUDA(cudaStreamSynchronize(st));            // `host` is a stack array
+  int per_sm = 0, dev = 0, sms = 0;
+  MLG_CUDA(cudaGetDevice(&dev));
+  MLG_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  MLG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, peer_adam_emulated_kernel, kThreads, 0));
+  long long blocks = ((host[0].hi - host[0].lo) / 4 + kThreads - 1) / kThreads;
+  const long long cap = (long long)per_sm * sms / world;
+  if (blocks > cap) blocks = cap;
+  if (blocks > 32) blocks = 32;
+  MLG_CHECK_ARG(blocks >= 1, "mlg_peer_adam_step_emulated: %d ranks do not fit one cooperative launch", world);
+  dim3 grid((unsigned)blocks, (unsigned)world);
+  const PeerP* arg = (const PeerP*)ranks_dev;
+  void* args[] = {(void*)&arg};
+  MLG_CUDA(cudaLaunchCooperativeKernel((void*)peer_adam_emulated_kernel, grid, dim3(kThreads), args, 0, st));
   return MLG_OK;
 }
 

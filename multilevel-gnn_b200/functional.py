@@ -527,11 +527,16 @@ ORDER_TF = _flag("MLG_ORDER_TF", True)         # transform-first layer: forward 
 # Both branches are HBM streams, so the win is the latency / tail overlap, not 2x.  The fork is joined back into the
 # launching stream at the END of the backward pass (autograd engine callback); tensors the side branch reads stay
 # referenced until then (no cross-stream reuse by the caching allocator).
-PARALLEL_BACKWARD = _flag("MLG_PARALLEL_BACKWARD", True)
+# measured on B200 (gpurun_out r02_bench_quick: 0.8455 ms forked vs 0.8463 ms serial): no gain today -- the big backward kernels
+# (gemm_tf32x3, xty_tc) are persistent one-CTA-per-SM kernels that cannot co-reside, so the branches serialise anyway; off by default
+PARALLEL_BACKWARD = _flag("MLG_PARALLEL_BACKWARD", False)
 # Set by train.Trainer around its own autograd.grad call only: the gradients a forked branch produces may not be touched
 # before the end-of-backward join, which holds for the trainer (it stores them after the pass) but not for an arbitrary
 # loss.backward(), whose AccumulateGrad nodes run on the launching stream as soon as a Function returns.
 PARALLEL_ACTIVE = False
+# set by train.Trainer (data parallel, fused peer update): called at the end of HeadMLP.backward, when the classifier head's
+# gradients are final, to start that chunk's reduce-scatter / Adam / all-gather while the rest of backward runs
+AFTER_HEAD_BACKWARD = None
 _SIDE_STREAMS = {}
 
 
@@ -548,12 +553,12 @@ class _Forked:
     registers the join for the end of the backward pass.  Outside a backward pass, or with PARALLEL_BACKWARD off, the
     block simply runs on the current stream."""
 
-    def __init__(self, device, idx, keep=()):
-        self.device, self.idx, self.keep = device, idx, list(keep)
+    def __init__(self, device, idx, keep=(), force=False):
+        self.device, self.idx, self.keep, self.force = device, idx, list(keep), force
         self.active = False
 
     def __enter__(self):
-        if not (PARALLEL_BACKWARD and PARALLEL_ACTIVE and self.device.type == "cuda"):
+        if not ((PARALLEL_BACKWARD or self.force) and PARALLEL_ACTIVE and self.device.type == "cuda"):
             return self
         self.main = torch.cuda.current_stream(self.device)
         self.side = _side_stream(self.device, self.idx)
@@ -1256,6 +1261,8 @@ class HeadMLP(torch.autograd.Function):
                                            _cabi.fptr(w3), ctx.p, R, D, K, _cabi.fptr(g_a0, True), K, _cabi.fptr(gW0),
                                            _cabi.fptr(gb0), _cabi.fptr(gW3), _cabi.fptr(gb3), _cabi.stream_ptr()),
                         "mlg_head_mlp_bwd")
+        if AFTER_HEAD_BACKWARD is not None:
+            AFTER_HEAD_BACKWARD()
         return g_a0, gW0, gb0, gW3, gb3, None, None, None, None
 
 

@@ -28,21 +28,40 @@ def shard_indices(n_items, rank, world, per_rank_batch, epoch_seed=0, drop_last=
 class GradBucket:
     """Flat fp32 gradient bucket: every ``p.grad`` is a view into one contiguous buffer, so the data-parallel
     synchronisation is ONE all-reduce with no packing/unpacking (NCCL: op=AVG folds the 1/world scale in;
-    gloo has no AVG, so SUM + scale).  Parameters that never get a gradient are not in the bucket."""
+    gloo has no AVG, so SUM + scale).  Parameters that never get a gradient are not in the bucket.
+    ``segments``: the parameters in groups that start at offsets aligned to ``align`` elements (the chunks of the fused
+    peer update: each chunk's length must divide by 4 * world); ``bounds`` = the (lo, hi) element range of every group."""
 
-    def __init__(self, params, flat=None):
-        self.params = list(params)
+    def __init__(self, params, flat=None, segments=None, align=1):
+        segments = [list(params)] if segments is None else [list(g) for g in segments]
+        self.params = [p for g in segments for p in g]
         dev = self.params[0].device
-        n = sum(p.numel() for p in self.params)
+        self.offsets, self.bounds, off = {}, [], 0
+        for g in segments:
+            lo = off
+            for p in g:
+                self.offsets[id(p)] = off
+                off += p.numel()
+            off = -(-off // align) * align          # group end rounded up: padding elements stay zero
+            self.bounds.append((lo, off))
+        n = off
+        self.n = n
         # ``flat``: caller-provided storage (PeerArena: peer-mapped device memory, padded past n)
         self.flat = torch.zeros(n, dtype=torch.float32, device=dev) if flat is None else flat
         assert self.flat.numel() >= n and self.flat.is_contiguous()
-        off = 0
         for p in self.params:
-            p.grad = self.flat[off:off + p.numel()].view_as(p)
+            o = self.offsets[id(p)]
+            p.grad = self.flat[o:o + p.numel()].view_as(p)
             # backward kernels that produce a whole parameter gradient may write it here directly (functional.grad_slot)
             p._mlg_grad_slot = {"view": p.grad, "claimed": False}
-            off += p.numel()
+
+    @staticmethod
+    def padded_size(segments, align):
+        off = 0
+        for g in segments:
+            off += sum(p.numel() for p in g)
+            off = -(-off // align) * align
+        return off
 
     def zero(self):
         self.flat.zero_()
@@ -84,13 +103,11 @@ class FlatAdam:
     def __init__(self, bucket, lr, betas, eps=1e-8, weight_decay=0.0):
         self.bucket, self.lr, self.betas, self.eps, self.wd = bucket, lr, betas, eps, weight_decay
         flat_g = bucket.flat
-        self.flat_p = torch.empty_like(flat_g)
-        off = 0
+        self.flat_p = torch.zeros_like(flat_g)
         for p in bucket.params:
-            n = p.numel()
+            n, off = p.numel(), bucket.offsets[id(p)]
             self.flat_p[off:off + n].copy_(p.data.reshape(-1))
             p.data = self.flat_p[off:off + n].view_as(p)
-            off += n
         self.exp_avg = torch.zeros_like(flat_g)
         self.exp_avg_sq = torch.zeros_like(flat_g)
         self.step_dev = torch.zeros(1, dtype=torch.float32, device=flat_g.device)
@@ -114,17 +131,17 @@ class _DeviceSpan:
 
 
 class PeerArena:
-    """This rank's peer-visible device memory [gradient bucket | parameters | flag block] (mlg_peer_alloc) and the
-    mappings of every other rank's arena (CUDA IPC handles exchanged once through torch.distributed).  ``group_arenas``
-    lets several arenas of ONE process stand in for the ranks (single-GPU protocol test)."""
+    """This rank's peer-visible device memory [gradient bucket | parameters | one flag block per chunk] (mlg_peer_alloc) and
+    the mappings of every other rank's arena (CUDA IPC handles exchanged once through torch.distributed)."""
 
-    def __init__(self, n, world, rank, device, exchange=True):
+    def __init__(self, n_padded, world, rank, device, exchange=True, n_chunks=1):
         from . import _cabi
         L = _cabi.lib()
-        self.world, self.rank, self.device = world, rank, device
-        self.n_padded = -(-n // (4 * world)) * (4 * world)
+        self.world, self.rank, self.device, self.n_chunks = world, rank, device, n_chunks
+        assert n_padded % 4 == 0
+        self.n_padded = n_padded
         self.flag_bytes = int(L.mlg_peer_flag_bytes())
-        self.bytes = 2 * 4 * self.n_padded + self.flag_bytes
+        self.bytes = 2 * 4 * self.n_padded + self.flag_bytes * n_chunks
         with torch.cuda.device(device):
             self.base = L.mlg_peer_alloc(self.bytes)
         if not self.base:
@@ -157,21 +174,26 @@ class PeerArena:
                 self._opened.append(ptr)
                 self.peer_base[r] = ptr
 
-    def pointer_tables(self):
-        """(grads, params, flags): ctypes arrays of ``world`` device pointers, indexed by rank."""
+    def pointer_tables(self, chunk=0):
+        """(grads, params, flags): ctypes arrays of ``world`` device pointers, indexed by rank (flags: of ``chunk``)."""
         import ctypes
         arr = ctypes.c_void_p * self.world
         g = arr(*[b for b in self.peer_base])
         p = arr(*[b + 4 * self.n_padded for b in self.peer_base])
-        f = arr(*[b + 8 * self.n_padded for b in self.peer_base])
+        f = arr(*[b + 8 * self.n_padded + chunk * self.flag_bytes for b in self.peer_base])
         return g, p, f
 
     def status(self):
+        """Non-zero when a wait of any chunk's update kernel gave up on this rank (device read: synchronises)."""
         import ctypes
         from . import _cabi
-        out = ctypes.c_int(0)
-        _cabi.check(_cabi.lib().mlg_peer_status(self.base + 8 * self.n_padded, ctypes.byref(out)), "mlg_peer_status")
-        return out.value
+        worst = 0
+        for c in range(self.n_chunks):
+            out = ctypes.c_int(0)
+            _cabi.check(_cabi.lib().mlg_peer_status(self.base + 8 * self.n_padded + c * self.flag_bytes, ctypes.byref(out)),
+                        "mlg_peer_status")
+            worst = max(worst, out.value)
+        return worst
 
     def close(self):
         from . import _cabi
@@ -183,37 +205,57 @@ class PeerArena:
 
 
 class PeerAdam:
-    """Data-parallel optimizer step as ONE kernel over NVLink peer memory (mlg_peer_adam_step): reduce-scatter of the
-    gradient buckets, torch.optim.Adam on the owned 1/world shard (ZeRO-1: the moment buffers exist once per box),
+    """Data-parallel optimizer step as ONE kernel per chunk over NVLink peer memory (mlg_peer_adam_step): reduce-scatter of
+    the gradient buckets, torch.optim.Adam on the owned 1/world shard (ZeRO-1: the moment buffers exist once per box),
     all-gather of the updated parameters -- no NCCL call, no second graph, every rank bitwise in step.  Parameters are
-    re-homed as views of the arena's parameter buffer (like FlatAdam)."""
+    re-homed as views of the arena's parameter buffer (like FlatAdam).  ``bucket.bounds`` are the chunks: ``step(c)`` updates
+    chunk c only (the trainer launches the classifier-head chunk from inside backward), ``step()`` whatever has not run yet
+    this round, ``finish_round()`` re-arms.  A wait that times out is a hard failure on every rank (``failed()``)."""
 
     def __init__(self, bucket, arena, lr, betas, eps=1e-8, weight_decay=0.0, timeout_s=5.0):
         self.bucket, self.arena = bucket, arena
         self.lr, self.betas, self.eps, self.wd, self.timeout_s = lr, betas, eps, weight_decay, timeout_s
         self.flat_p = arena.param
-        off = 0
         for p in bucket.params:
-            n = p.numel()
+            n, off = p.numel(), bucket.offsets[id(p)]
             self.flat_p[off:off + n].copy_(p.data.reshape(-1))
             p.data = self.flat_p[off:off + n].view_as(p)
-            off += n
-        shard = arena.n_padded // arena.world
-        self.exp_avg = torch.zeros(shard, dtype=torch.float32, device=arena.device)
-        self.exp_avg_sq = torch.zeros(shard, dtype=torch.float32, device=arena.device)
-        self.step_dev = torch.zeros(1, dtype=torch.float32, device=arena.device)
-        self._tables = arena.pointer_tables()
+        self.chunks = list(bucket.bounds)
+        assert len(self.chunks) <= arena.n_chunks
+        dev = arena.device
+        self.exp_avg = [torch.zeros((hi - lo) // arena.world, dtype=torch.float32, device=dev) for lo, hi in self.chunks]
+        self.exp_avg_sq = [torch.zeros_like(t) for t in self.exp_avg]
+        self.step_dev = [torch.zeros(1, dtype=torch.float32, device=dev) for _ in self.chunks]
+        self._tables = [arena.pointer_tables(c) for c in range(len(self.chunks))]
+        # pinned host word the kernels set on a failed wait: read by the host without synchronising the device
+        self.host_status = torch.zeros(1, dtype=torch.int32).pin_memory()
+        self._done = [False] * len(self.chunks)
 
-    def step(self):
+    def failed(self):
+        return int(self.host_status[0]) != 0
+
+    EARLY_BLOCKS = 24      # grid cap of a chunk launched next to the backward kernels
+
+    def step(self, chunk=None):
+        import ctypes
         from . import _cabi
         L = _cabi.lib()
         a = self.arena
-        g, p, f = self._tables
+        todo = [c for c in range(len(self.chunks)) if not self._done[c]] if chunk is None else [chunk]
         with torch.cuda.device(a.device):
-            _cabi.check(L.mlg_peer_adam_step(g, p, f, a.world, a.rank, a.n_padded, _cabi.fptr(self.exp_avg),
-                                             _cabi.fptr(self.exp_avg_sq), _cabi.fptr(self.step_dev), float(self.lr),
-                                             float(self.betas[0]), float(self.betas[1]), float(self.eps), float(self.wd),
-                                             float(self.timeout_s), _cabi.stream_ptr()), "mlg_peer_adam_step")
+            for c in todo:
+                g, p, f = self._tables[c]
+                lo, hi = self.chunks[c]
+                _cabi.check(L.mlg_peer_adam_step(g, p, f, a.world, a.rank, lo, hi, _cabi.fptr(self.exp_avg[c]),
+                                                 _cabi.fptr(self.exp_avg_sq[c]), _cabi.fptr(self.step_dev[c]), float(self.lr),
+                                                 float(self.betas[0]), float(self.betas[1]), float(self.eps), float(self.wd),
+                                                 float(self.timeout_s), ctypes.c_void_p(self.host_status.data_ptr()),
+                                                 self.EARLY_BLOCKS if chunk is not None else 0, _cabi.stream_ptr()),
+                            "mlg_peer_adam_step")
+                self._done[c] = True
+
+    def finish_round(self):
+        self._done = [False] * len(self.chunks)
 
 
 def peer_update_available(world, device):
@@ -272,9 +314,19 @@ class Trainer:
                 raise RuntimeError("peer_update=True but the ranks do not all have CUDA peer access on one box")
             want_peer = False
         if want_peer:
-            self.peer = PeerArena(sum(p.numel() for p in self.params), world_size, dist.get_rank(), dev)
-            self.bucket = GradBucket(self.params, flat=self.peer.grad)
+            # two chunks of the fused update: [classifier head] -- 62 % of the gbm parameters, gradients final right after the
+            # head's backward kernel, updated on a forked branch while the rest of backward runs -- and [everything else]
+            head_ids = {id(p) for n, p in model.named_parameters() if n.startswith("head.")}
+            early = [p for p in self.params if id(p) in head_ids]
+            late = [p for p in self.params if id(p) not in head_ids]
+            segments = [early, late] if (early and late) else [self.params]
+            align = 4 * world_size
+            self.early_params = early if len(segments) == 2 else []
+            self.peer = PeerArena(GradBucket.padded_size(segments, align), world_size, dist.get_rank(), dev,
+                                  n_chunks=len(segments))
+            self.bucket = GradBucket(self.params, flat=self.peer.grad, segments=segments, align=align)
         else:
+            self.early_params = []
             self.bucket = GradBucket(self.params)
         self.flat = self.bucket.flat
         if self.peer is not None:
@@ -308,17 +360,31 @@ class Trainer:
         # == optimizer.zero_grad(); loss.backward() with the gradients landing in the bucket views (p.grad)
         from . import functional as Fn
         Fn.GRAD_SLOTS_ENABLED = Fn.PARALLEL_ACTIVE = loss.is_cuda
+        Fn.AFTER_HEAD_BACKWARD = self._early_update if (self.peer is not None and self.early_params) else None
         try:
             grads = torch.autograd.grad(loss, self.params, allow_unused=True)
         finally:
             Fn.GRAD_SLOTS_ENABLED = Fn.PARALLEL_ACTIVE = False
+            Fn.AFTER_HEAD_BACKWARD = None
         self.bucket.store(grads)
         return loss.detach()
+
+    def _early_update(self):
+        """Called by functional.HeadMLP.backward once the classifier head's gradients sit in their bucket slots: launch the
+        head chunk of the fused peer update on a forked stream (joined at the end of the backward pass).  The head's weights
+        are not read again in this step on any rank: every rank signals 'ready' only after its own head backward."""
+        from . import functional as Fn
+        if not all(p._mlg_grad_slot["claimed"] for p in self.early_params):
+            return          # a gradient took the copy path (bucket.store): the chunk runs with the rest, after backward
+        with Fn._Forked(self.flat.device, 3, keep=(), force=True):
+            self.opt.step(0)
 
     def _update(self):
         if self.args.clip_grad:
             torch.nn.utils.clip_grad_norm_(self.params, max_norm=20, norm_type=2)
         self.opt.step()
+        if self.peer is not None:
+            self.opt.finish_round()
 
     def _step_eager(self, batch):
         loss = self._fwd_bwd(batch)
@@ -445,6 +511,8 @@ class Trainer:
             self._staged.record()
 
     def step_prefetched(self):
+        if self.peer is not None and self.opt.failed():
+            raise RuntimeError("Trainer: the fused NVLink update timed out waiting for a peer rank")
         cur = torch.cuda.current_stream()
         cur.wait_event(self._staged)
         for k, v in self._staging.items():
@@ -473,6 +541,11 @@ class Trainer:
         """forward, loss, backward, (all-reduce), Adam.  Returns the loss as a device scalar (the
         reference's ``loss.item()`` host sync is the caller's choice).  With a captured graph, ``batch`` must
         be the static batch (or None); use ``load_batch`` to feed new data."""
+        if self.peer is not None and self.opt.failed():
+            # a rank gave up waiting for a peer inside the fused update kernel (rank skew beyond the timeout, a dead rank): the
+            # kernels skipped that update on every rank and refuse to run again -- stop here instead of training on
+            raise RuntimeError("Trainer: the fused NVLink update timed out waiting for a peer rank; parameters were left "
+                               "untouched by the failed step.  Restart the job (or run with peer_update=False).")
         if self.graph is not None:
             if batch is not None and batch is not self.static_batch:
                 self.load_batch(batch)

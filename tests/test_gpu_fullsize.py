@@ -109,12 +109,14 @@ def test_genconv_100k_vs_oracle(mlg):
     torch.manual_seed(7)
     conv = mlg.GENConv(H, H, aggr="softmax", learn_t=True, msg_norm=True, learn_msg_scale=True, encode_edge=True,
                        edge_feat_dim=H, norm="layer")
-    sd = {kk: v.detach().clone().requires_grad_() for kk, v in conv.state_dict().items()}
-    xr, er = x.clone().requires_grad_(), ea.clone().requires_grad_()
+    # the oracle in fp64: the weight gradients are sums over 1.6 M edges / 100 k nodes, where an fp32 CPU reduction is itself only
+    # good to ~1e-3 of the result (measured: half of edge_encoder.weight's entries 9e-4 of the scale apart between two fp32 orders)
+    sd = {kk: v.detach().clone().double().requires_grad_() for kk, v in conv.state_dict().items()}
+    xr, er = x.clone().double().requires_grad_(), ea.clone().double().requires_grad_()
     Rw = torch.randn(n, H, generator=g)
     yr = R.genconv_forward(sd, xr, ei, er, aggr="softmax", learn_t=True, msg_norm_on=True, encode_edge=True, norm="layer")
     names = list(sd)
-    g_r = torch.autograd.grad((yr * Rw).sum(), [xr, er] + [sd[kk] for kk in names], allow_unused=True)
+    g_r = torch.autograd.grad((yr * Rw.double()).sum(), [xr, er] + [sd[kk] for kk in names], allow_unused=True)
     conv.to(DEV).train()
     xg, eg = x.to(DEV).requires_grad_(), ea.to(DEV).requires_grad_()
     y = conv(xg, ei.to(DEV), eg)

@@ -31,10 +31,10 @@ def flat_check(dev, world, rank):
     shapes = [(257, 33), (1000,), (64, 64), (3,), (500001,)]
     g0 = torch.Generator().manual_seed(5)
     init = [torch.randn(s, generator=g0) for s in shapes]
-    n = sum(t.numel() for t in init)
-    arena = PeerArena(n, world, rank, dev)
     params = [torch.nn.Parameter(t.clone().to(dev)) for t in init]
-    bucket = GradBucket(params, flat=arena.grad)
+    segs = [params[:2], params[2:]]                       # two chunks, as the trainer splits head / rest
+    arena = PeerArena(GradBucket.padded_size(segs, 4 * world), world, rank, dev, n_chunks=2)
+    bucket = GradBucket(params, flat=arena.grad, segments=segs, align=4 * world)
     opt = PeerAdam(bucket, arena, lr=1e-2, betas=(0.9, 0.999), weight_decay=1e-2)
     ref = [torch.nn.Parameter(t.clone().to(dev)) for t in init]
     ref_opt = torch.optim.Adam(ref, lr=1e-2, betas=(0.9, 0.999), weight_decay=1e-2)
@@ -47,7 +47,9 @@ def flat_check(dev, world, rank):
             dist.all_reduce(p.grad, op=dist.ReduceOp.AVG)
         ref_opt.step()
         bucket.store(grads)
+        opt.step(0)               # chunk by chunk, like the trainer's early head chunk
         opt.step()
+        opt.finish_round()
     torch.cuda.synchronize()
     assert arena.status() == 0, "rank %d: a peer wait timed out" % rank
     err = 0.0
@@ -55,7 +57,7 @@ def flat_check(dev, world, rank):
         assert same_on_all_ranks(p.data, world), "replicas differ across ranks"
         torch.testing.assert_close(p.data, q.data, rtol=2e-5, atol=2e-6)
         err = max(err, float((p.data - q.data).abs().max()))
-    assert float(opt.step_dev.item()) == 6.0
+    assert all(float(t.item()) == 6.0 for t in opt.step_dev) and not opt.failed()
     return err
 
 
@@ -73,6 +75,7 @@ def trainer_check(dev, world, rank, graph):
         model.pathway_indexs = model.pathway_indexs.to(dev)
         batch = m.synth.multilevel_batch(batch_size=B, seed=100 + rank).to(dev)
         batch.topology_key = "fold0"
+
         weight = torch.tensor([[0.8, 1.3]]).repeat(B, 1).to(dev)
         tr = Trainer(model, args, weight, world_size=world, peer_update=(mode == "peer"))
         assert (tr.peer is not None) == (mode == "peer")
