@@ -328,6 +328,7 @@ class Trainer:
         else:
             self.early_params = []
             self.bucket = GradBucket(self.params)
+        self.params = self.bucket.params          # bucket order (chunks of the fused update first): autograd.grad / store use it
         self.flat = self.bucket.flat
         if self.peer is not None:
             self.opt = PeerAdam(self.bucket, self.peer, lr=args.lr, betas=(args.beta1, args.beta2), weight_decay=args.wd)
