@@ -89,7 +89,8 @@ def trainer_check(dev, world, rank, graph):
         torch.cuda.synchronize()
         if tr.peer is not None:
             assert tr.peer.status() == 0, "rank %d: a peer wait timed out" % rank
-        flat = torch.cat([p.data.reshape(-1) for p in tr.params])
+        ids = {id(p) for p in tr.params}          # model order: the two trainers order their buckets differently
+        flat = torch.cat([p.data.reshape(-1) for p in model.parameters() if id(p) in ids])
         assert same_on_all_ranks(flat, world), "%s: parameters differ across ranks" % mode
         out[mode] = (losses, flat.clone())
         dist.barrier()
