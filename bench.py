@@ -40,6 +40,8 @@ def parse():
                     help="graphs per CPU step of the reference arm / cpu_baseline (default: the GPU arm's batch)")
     ap.add_argument("--windows", type=int, default=3, help="timed windows of --steps steps each; the median is reported")
     ap.add_argument("--no-diffpool", action="store_true", help="skip the DiffPool legs (reference size + tensor-core contractions)")
+    ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling leg (fixed global batch 256, SURVEY section 8d cfg5)")
+    ap.add_argument("--strong-batch", type=int, default=256, help="global batch of the strong-scaling leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-genconv", action="store_true", help="skip the GENConv aggregation roofline microbench")
     ap.add_argument("--no-graph", action="store_true", help="do not capture the step as a CUDA graph")
@@ -166,6 +168,20 @@ def ncu_traffic(kernel):
         return (json.load(f).get(kernel) or {}).get("dram_bytes")
 
 
+
+
+# per timer tag: the ncu kernel names behind it (profiles/ncu_traffic.json) and the ALGORITHMIC bytes of one launch
+KERNEL_INFO = {
+    "gather_sum_rep_kernel (SAGE mean aggregation fwd+bwd)": {
+        "ncu": ["gather_sum_rep_kernel<8, 4, 0, 0, 0>", "gather_sum_rep_kernel<8, 4, 0, 0, 0>#2"],
+        "alg": "8*C*B*N + 8*nnz per launch counted by the timer (rows read once + written once + idx/val per entry), C = 32: the "
+               "second SAGE layer (64 -> 32) runs transform-first, so its forward and backward aggregations gather 32-wide rows "
+               "(with the addend row U / the copied self row: 12*C*B*N = 190 MB); bounded by L2 -> SM row gathers (441 MB re-read "
+               "per launch: every source row once per CSR entry), not by DRAM"},
+    "sage_rank1_fwd": {"ncu": ["sage_rank1_fwd_rows_kernel<2>"],
+                       "alg": "4*C*B*N (output) + 4*B*N + 8*nnz + 8*C*N (tables), C = 64: 137 MB, write bound"},
+    "pool_bwd": {"ncu": ["pool_bwd_fused2_kernel<2, 1, 8>"], "alg": "2 * 4*C*B*N + 4*B*C*S*P: x read, g_x written, pooled gradient read"},
+}
 
 
 def max_over_ranks(ms, world, dev):
@@ -387,6 +403,42 @@ def run_reference(a):
     }))
 
 
+def strong_scaling_leg(a, args, world, rank, dev, steps):
+    """SURVEY section 8(d) cfg5, second half: a FIXED global batch (256 graphs) split over the ranks -- per-GPU batch 256 / N --
+    through the same Trainer (own model replica, captured graph, fused peer update).  Returns (graphs/s, ms/step, per-GPU batch)."""
+    import types
+    import multilevel_gnn_b200 as m
+    from multilevel_gnn_b200.train import Trainer
+    Bs = a.strong_batch // world
+    torch.manual_seed(0)
+    model = m.MultilevelGNN(args)
+    m.synth.multilevel_params(model)
+    model.to(dev)
+    model.pathway_indexs = model.pathway_indexs.to(dev)
+    raw = m.synth.multilevel_batch(batch_size=Bs, seed=300 + rank)
+    n1 = 3 * m.MultilevelGNN.GENES
+    E1 = raw.edge_index.shape[1] // Bs
+    topo = m.data.FoldTopology(raw.edge_index[:, :E1], raw.edge_attr[:E1], raw.gene_pca_match[0], raw.raw_indice[0], n1)
+    patients = [types.SimpleNamespace(x=raw.x[i * n1:(i + 1) * n1], age=raw.age[i], y=raw.y[2 * i:2 * i + 2]) for i in range(Bs)]
+    resident = m.data.to_device(m.data.collate(patients, topo, pin=False), topo, dev)
+    weight = torch.tensor([[0.8, 1.3]]).repeat(Bs, 1).to(dev)
+    tr = Trainer(model, args, weight, world_size=world, peer_update=False if a.nccl_update else None)
+    for _ in range(3):
+        tr.step(resident)
+    if not a.no_graph:
+        tr.capture(resident)
+        tr.step()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier(world)
+    e0.record()
+    for _ in range(steps):
+        tr.step(resident)
+    e1.record()
+    barrier(world)
+    ms = max_over_ranks(e0.elapsed_time(e1), world, dev)
+    return Bs * world * steps / (ms / 1e3), ms / steps, Bs
+
+
 def run_b200(a):
     import multilevel_gnn_b200 as m
     from multilevel_gnn_b200 import _cabi
@@ -511,6 +563,15 @@ def run_b200(a):
     ksum = timer.summary()
     barrier(world)
 
+    strong = None
+    strong_err = None
+    if not a.no_strong and a.strong_batch % world == 0:
+        try:
+            strong = strong_scaling_leg(a, args, world, rank, dev, a.steps)
+        except Exception as exc:          # an extra key must never take the headline line down with it
+            if world > 1:
+                raise                     # (a rank that stops here would leave its peers waiting in a collective)
+            strong_err = "%s: %s" % (type(exc).__name__, exc)
     if tr.peer is not None and tr.peer.status() != 0:
         # a rank gave up waiting for a peer's flag inside the fused update kernel: the replicas are no longer in step
         raise SystemExit("bench.py: rank %d: a peer wait of the fused NVLink update kernel timed out; the measurement is void "
@@ -536,15 +597,15 @@ def run_b200(a):
     if hbm_kernels:
         tag, d = max(hbm_kernels.items(), key=lambda kv: kv[1]["ms"])
         gbs = d["bytes"] / d["ms"] / 1e6
+        info = KERNEL_INFO.get(tag, {})
+        tr_vals = [t for t in (ncu_traffic(k) for k in info.get("ncu", [])) if t]
         roof = {"kernel": tag, "bound": "hbm", "achieved": round(gbs, 1), "peak": hbm_peak, "unit": "GB/s",
-                "frac": round(gbs / hbm_peak, 4), "traffic": ncu_traffic(tag), "peak_source": peak_src,
+                "frac": round(gbs / hbm_peak, 4), "traffic": (int(sum(tr_vals) / len(tr_vals)) if tr_vals else None),
+                "traffic_source": ("profiles/ncu_traffic.json: mean of " + ", ".join(info.get("ncu", []))) if tr_vals else None,
+                "peak_source": peak_src,
                 "launches": d["launches"], "avg_us": round(d["ms"] / d["launches"] * 1e3, 2),
                 "share_of_step": round(d["ms"] / ms_total, 4),
-                "algorithmic_bytes": "8*C*B*N + 8*nnz per launch (rows read once + written once + idx/val per entry), C = 32: the "
-                                     "second SAGE layer (64 -> 32) runs transform-first, so its forward and backward aggregations "
-                                     "gather 32-wide rows; the kernel is limited by L2 row gathers (7 entries/row on average), not "
-                                     "by DRAM; traffic = ncu dram bytes of one launch at this shape (null: not captured at C = 32; "
-                                     "the C = 64 capture in profiles/r01_ncu_full_summaries.md read 1.2x its algorithmic bytes)",
+                "algorithmic_bytes": info.get("alg", "see DESIGN.md section 4"),
                 "timed": "CUDA events around each launch in an eager pass of the same %d steps (the timed region itself "
                          "is a CUDA-graph replay)" % a.steps,
                 "back_to_back": dominant_kernel_alone(resident, hbm_peak),
@@ -579,6 +640,10 @@ def run_b200(a):
                                     "weights and pooling tables); PCIe-bound; the re-sent topology is compared on the "
                                     "device with the captured one"},
         "windows_ms": [round(x, 4) for x in windows_ms],
+        "strong_scaling": ({"error": strong_err} if strong_err else None if strong is None else
+                           {"global_batch": a.strong_batch, "graphs_per_gpu": strong[2], "value": round(strong[0], 2),
+                            "unit": "graphs/s", "ms_per_step": round(strong[1], 4),
+                            "note": "SURVEY section 8(d) cfg5: fixed global batch, per-GPU batch = global / N; same trainer, resident batch"}),
         "gpu_launches": launches, "clocks": clocks, "roofline": roof, "loss": loss_value,
         "dp_update": (None if world == 1 else "nccl all-reduce + replicated Adam" if tr.peer is None else
                       {"kernel": "peer_adam_kernel (reduce-scatter -> Adam shard -> all-gather over NVLink peer memory)",

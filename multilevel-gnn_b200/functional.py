@@ -210,9 +210,10 @@ def tall_matmul(a, w, bias=None, act=0, slope=0.0, tag="gemm_tf32x3", w_split=No
 
 
 class TallLinear(torch.autograd.Function):
-    """y = x @ W^T + b for a TALL x (rows >> features): forward and dX are cuBLAS fp32, the weight / bias gradient
-    (a [out, rows] x [rows, in] product with a tiny output, which library GEMMs handle poorly) is mlg_xty.
-    Used for GENConv's per-layer edge encoder on [E, H] edge embeddings (torch_vertex.py:76-77)."""
+    """y = x @ W^T + b for a TALL x (rows >> features): forward and dX on the 3xTF32 tcgen05 GEMM (mlg_gemm_tf32x3, bias /
+    ReLU in its epilogue; cuBLAS fp32 only for shapes it does not cover), the weight / bias gradient (a [out, rows] x
+    [rows, in] product with a tiny output) on mlg_xty_tc / mlg_xty.  Used for GENConv's per-layer edge encoder on [E, H]
+    edge embeddings (torch_vertex.py:76-77), its node-side MLP Linears, and 1x1 convolutions outside the fused head."""
 
     MIN_ROWS = 65536
 
@@ -495,32 +496,23 @@ class SageAggregate(torch.autograd.Function):
 
 
 def _flag(name, default):
-    """Evaluation-order / tuning switches below can be set per process through the environment (tools/ab_*.sh)."""
+    """Tuning switches that are worth flipping from the shell for an A/B run (tools/): everything else is a module constant."""
     return os.environ.get(name, "1" if default else "0") == "1"
 
 
-# first layer of MultilevelGNN through mlg_sage_rank1_fwd / mlg_sage_rank1_bwd_rows; "gather": backward through the
+# Evaluation order of a SAGE layer (same algebra, torch_vertex.py:269-294; DESIGN.md section 4).  Module constants -- the parity
+# tests flip them to compare each order with the buffered one -- not environment switches.
+# first layer of MultilevelGNN through mlg_sage_rank1_fwd_rows / mlg_sage_rank1_bwd_rows; "gather": backward through the
 # by-source gather mlg_sage_rank1_bwd (any width); False: [x0 | agg] buffer + GEMMs
 FACTORED_RANK1 = True
 # SAGE layers with out_channels < in_channels evaluated transform-first (gather on the narrower rows); False: [x | agg] + GEMM
-TRANSFORM_FIRST = _flag("MLG_TRANSFORM_FIRST", True)
-# When no consumer pre-masks the factored first layer's output gradient (the next layer runs transform-first), the layer has
-# to apply LeakyReLU'(y) itself.  RANK1_SELF_MASK: inside mlg_sage_rank1_bwd_rows, from y or (RANK1_SIGN_BITS) from 64 sign bits
-# per (row, replica) its forward kernel wrote.  Measured on B200 (tools/ab_layer2.sh, gbm shape): with the dX GEMM's output as
-# its direct input that kernel runs at 179-185 us against 61 us behind an elementwise pass, so one library
-# leaky_relu_backward pass + the unmasked kernel is FASTER (step 1.000 ms vs 1.086 ms) and is the default; the in-kernel
-# paths stay selectable (and tested) until an ncu capture explains the regression (tools/rank1_bwd_probe.py, DESIGN section 6).
+TRANSFORM_FIRST = True
+# The factored first layer applies LeakyReLU'(y) to its output gradient INSIDE mlg_sage_rank1_bwd_rows, from 64 sign bits per
+# (gene, replica) its forward kernel wrote (B200: 66 us vs 61 us unmasked; re-reading the 126 MB activation instead costs
+# 175 us, profiles/r02_rank1_bwd_probe.jsonl).  Widths without sign words (!= 64): one library leaky_relu_backward pass.
 RANK1_SIGN_BITS = True
 # forward of the factored first layer with one warp per gene for all replicas (mlg_sage_rank1_fwd_rows); False: r01's kernel
-RANK1_FWD_ROWS = _flag("MLG_R1_FWD_ROWS", True)
-RANK1_SELF_MASK = _flag("MLG_R1_SELF_MASK", True)
-# Row visiting order of the replicated kernels: degree-sorted (heavy rows first, balanced lane groups) or natural.  Measured
-# on B200 (tools/ab_order.sh, gbm shape): sorted wins everywhere -- rank-1 forward 109 vs 166 us, layer-2 aggregations 150 vs
-# 288 us per step, rank-1 backward 184 vs 215 us.  Per kernel family; the switches stay for tuning.
-ORDER_R1B = _flag("MLG_ORDER_R1B", True)       # mlg_sage_rank1_bwd_rows
-ORDER_R1F = _flag("MLG_ORDER_R1F", True)       # mlg_sage_rank1_fwd
-ORDER_TF = _flag("MLG_ORDER_TF", True)         # transform-first layer: forward / backward aggregation
-
+RANK1_FWD_ROWS = True
 
 # Independent branches of the backward pass on forked streams (captured by the trainer's CUDA graph as parallel branches):
 # a layer's weight gradient does not feed the input-gradient chain, so it runs next to it instead of in front of it.
@@ -529,7 +521,7 @@ ORDER_TF = _flag("MLG_ORDER_TF", True)         # transform-first layer: forward 
 # referenced until then (no cross-stream reuse by the caching allocator).
 # measured on B200 (gpurun_out r02_bench_quick: 0.8455 ms forked vs 0.8463 ms serial): no gain today -- the big backward kernels
 # (gemm_tf32x3, xty_tc) are persistent one-CTA-per-SM kernels that cannot co-reside, so the branches serialise anyway; off by default
-PARALLEL_BACKWARD = _flag("MLG_PARALLEL_BACKWARD", False)
+PARALLEL_BACKWARD = _flag("MLG_PARALLEL_BACKWARD", False)     # A/B switch (tools/gpu_quick.sh)
 # Set by train.Trainer around its own autograd.grad call only: the gradients a forked branch produces may not be touched
 # before the end-of-backward join, which holds for the trainer (it stores them after the pass) but not for an arbitrary
 # loss.backward(), whose AccumulateGrad nodes run on the launching stream as soon as a Function returns.
@@ -638,7 +630,7 @@ class SageLayer(torch.autograd.Function):
             # the consumer does not pre-mask our output gradient: keep the sign bits of y (8 bytes per row and replica) so that
             # the backward kernel applies LeakyReLU' without re-reading y
             mbits = None
-            if RANK1_SIGN_BITS and RANK1_SELF_MASK and cout == 64 and not out_premasked and any(ctx.needs_input_grad):
+            if RANK1_SIGN_BITS and cout == 64 and not out_premasked and any(ctx.needs_input_grad):
                 mbits = torch.empty(n1 * topo.replicas, dtype=torch.int64, device=xd.device)
             rows_ok = RANK1_FWD_ROWS and bool(L.mlg_sage_rank1_fwd_rows_supported(cout))
             xs_t = None
@@ -653,14 +645,14 @@ class SageLayer(torch.autograd.Function):
                         _cabi.check(L.mlg_sage_rank1_fwd_rows(
                             _cabi.fptr(xs_t), _vptr(e12), 2 * cout, _vptr(e12[:, cout:]), 2 * cout, _cabi.iptr(csr.rowptr),
                             _cabi.iptr(csr.col), _cabi.fptr(topo.fwd_val, True),
-                            _cabi.iptr(topo.fwd_order if ORDER_R1F else None, True), n1, cout, topo.replicas,
+                            _cabi.iptr(topo.fwd_order, True), n1, cout, topo.replicas,
                             _cabi.fptr(bias, True), float(slope), _cabi.fptr(y), cout, _cabi.lptr(mbits, True),
                             _cabi.stream_ptr()), "mlg_sage_rank1_fwd_rows")
                     else:
                         _cabi.check(L.mlg_sage_rank1_fwd(
                             _cabi.fptr(xs_d), _vptr(e12), 2 * cout, _vptr(e12[:, cout:]), 2 * cout, _cabi.iptr(csr.rowptr),
                             _cabi.iptr(csr.col), _cabi.fptr(topo.fwd_val, True),
-                            _cabi.iptr(topo.fwd_order if ORDER_R1F else None, True), n1, cout, topo.replicas,
+                            _cabi.iptr(topo.fwd_order, True), n1, cout, topo.replicas,
                             _cabi.fptr(bias, True), float(slope), _cabi.fptr(y), cout, _cabi.lptr(mbits, True),
                             _cabi.stream_ptr()), "mlg_sage_rank1_fwd")
             ctx.xs_t = xs_t
@@ -686,7 +678,7 @@ class SageLayer(torch.autograd.Function):
             uv = tall_matmul(xd, wst, bias2, tag="sage_update_gemm")                   # [n, 2cout] = [U | V]
             csr = topo.fwd
             y = gather_sum(uv[:, cout:], csr.rowptr, csr.col, topo.n_single, val=topo.fwd_val, post_mode=1,
-                           addend=uv[:, :cout], replicas=topo.replicas, order=topo.fwd_order if ORDER_TF else None,
+                           addend=uv[:, :cout], replicas=topo.replicas, order=topo.fwd_order,
                            tag="sage_aggr_fwd", act_slope=slope)
             ctx.save_for_backward(xd, y, wst, w_r, w_nn, None)
             ctx.topo, ctx.relative, ctx.slope, ctx.cin, ctx.has_bias = topo, False, float(slope), cin, nn_b is not None
@@ -725,10 +717,9 @@ class SageLayer(torch.autograd.Function):
         y_mask = bits = None
         if ctx.out_premasked:
             gz = gy
-        elif by_rows and RANK1_SELF_MASK:
-            # the kernel applies LeakyReLU'(y) while it loads the gradient rows: from the forward kernel's sign bits, else from y
+        elif by_rows and ctx.mbits is not None:
+            # the kernel applies LeakyReLU'(y) while it loads the gradient rows, from the forward kernel's sign bits
             gz, bits = gy, ctx.mbits
-            y_mask = y if bits is None else None
         else:
             gz = torch.ops.aten.leaky_relu_backward(gy, y, ctx.slope, True) if ctx.slope != 0.0 \
                 else torch.ops.aten.threshold_backward(gy, y, 0.0)
@@ -746,7 +737,7 @@ class SageLayer(torch.autograd.Function):
                     _cabi.lptr(bits, True), float(ctx.slope),
                     _cabi.fptr(xs_d if xs_t is None else xs_t), 0 if xs_t is None else 1, _cabi.iptr(fw.rowptr),
                     _cabi.iptr(fw.col),
-                    _cabi.fptr(topo.fwd_val, True), _cabi.iptr(topo.fwd_order if ORDER_R1B else None, True), n1, cout, B,
+                    _cabi.fptr(topo.fwd_val, True), _cabi.iptr(topo.fwd_order, True), n1, cout, B,
                     _cabi.fptr(h),
                     _cabi.fptr(g12), 2 * cout, _cabi.fptr(gbr), _cabi.stream_ptr()), "mlg_sage_rank1_bwd_rows")
             g_b = None
@@ -808,7 +799,7 @@ class SageLayer(torch.autograd.Function):
         # G = [g_U | g_V] = [gz | A^T gz]: the by-source aggregation runs on the cout-wide gz rows and copies them alongside
         g_uv = torch.empty(n, 2 * cout, dtype=torch.float32, device=gz.device)
         gather_sum(gz, bw.rowptr, bw.col, topo.n_single, val=topo.bwd_val, pre=topo.inv_cnt, out=g_uv[:, cout:],
-                   self_out=g_uv[:, :cout], replicas=topo.replicas, order=topo.bwd_order if ORDER_TF else None,
+                   self_out=g_uv[:, :cout], replicas=topo.replicas, order=topo.bwd_order,
                    tag="sage_aggr_bwd")
         needs = ctx.needs_input_grad
         gx = g_wr = g_wnn = g_b = None

@@ -1,9 +1,12 @@
 """The caller of the hot path: one training step as the reference's ``train()`` runs it
 (train.py:38-68; optimizer / criterion set-up train.py:112-125), plus the data-parallel wrapper the
 reference lacks: patient graphs are independent, so every rank steps on its own
-batch and ONE NCCL all-reduce (op=AVG, the 1/world scale folded in) over a flat fp32 gradient bucket
-synchronises the replicas.  Parameters that never receive a gradient (``lin_l.weight`` of every
-SAGEConv, ``info_mask``) are left out of the bucket and of the optimizer state.
+batch and the replicas are synchronised by ONE fused kernel per parameter chunk over NVLink peer memory
+(gradient reduce-scatter -> Adam on the owned shard -> parameter all-gather, csrc/peer_adam.cu; the
+classifier-head chunk is launched from inside backward) -- or, selectably, one NCCL all-reduce (op=AVG)
+over the flat fp32 gradient bucket followed by a replicated flat Adam.  Parameters that never receive a
+gradient (``lin_l.weight`` of every SAGEConv, ``info_mask``) are left out of the bucket and of the
+optimizer state.
 """
 import torch
 import torch.distributed as dist
@@ -288,8 +291,9 @@ class _PendingLoss:
 
 
 class Trainer:
-    """One training step of train.py:38-68 on the B200 kernels; ``capture()`` turns the whole step
-    (forward, loss, backward, NCCL all-reduce, fused Adam) into ONE CUDA graph replayed per step."""
+    """One training step of train.py:38-68 on the B200 kernels; ``capture()`` turns the whole step (forward, loss,
+    backward, optimizer update -- with several ranks the fused NVLink reduce-scatter / Adam / all-gather kernels) into ONE
+    CUDA graph replayed per step (the NCCL path keeps its all-reduce between two graphs)."""
 
     def __init__(self, model, args, criterion_weight=None, world_size=1, fused_adam=True, peer_update=None):
         """peer_update: None = use the fused NVLink peer-memory update (PeerAdam) whenever the job allows it (one box,
