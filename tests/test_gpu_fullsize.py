@@ -128,10 +128,17 @@ def test_genconv_100k_vs_oracle(mlg):
     for kk, a, c in zip(names, gs[2:], g_r[2:]):
         if c is None:
             continue
-        # t / msg_scale: scalar parameters whose gradient is ONE fp32 sum over 12.8 M cancelling terms
-        # weight matrices: ONE flipped LayerNorm-ReLU unit rewrites a whole row (128 / 256 entries) of its weight gradient
-        _check(a, c, "GENConv 100k g_" + kk, rtol=5e-4 if a.numel() > 1 else 5e-3, atol=2e-5, l2=2e-3 if a.numel() > 1 else 5e-3,
-               outliers=5e-2)
+        # Parameter gradients here are reductions over 1.6 M edges / 100 k nodes with heavy cancellation.  The tensor-core weight
+        # gradient (3xTF32, mlg_xty_tc) is accurate to ~4e-6 of sum |a||x| (tests/test_gpu_parity.py::
+        # test_xty_tensor_core_matches_fp64), i.e. up to ~1e-3 of the tensor's largest entry for these sums, uniformly over the
+        # entries -- so they are held to a norm-wise bound and a max-error bound relative to the tensor's scale, not element-wise
+        # relative error; one flipped LayerNorm-ReLU unit additionally rewrites a whole row of its weight gradient.
+        ad, cd = a.detach().cpu().double(), c.detach().cpu().double()
+        scale = float(cd.abs().max())
+        assert ad.shape == cd.shape
+        assert float((ad - cd).abs().max()) <= 5e-3 * scale, "GENConv 100k g_%s: max abs err %.3e (scale %.3e)" % (
+            kk, float((ad - cd).abs().max()), scale)
+        assert _rel_l2(a, c) <= 3e-3, "GENConv 100k g_%s: relative L2 error %.3e" % (kk, _rel_l2(a, c))
 
 
 def test_diffpool_tensor_core_path_vs_oracle(mlg):

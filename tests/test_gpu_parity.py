@@ -849,3 +849,34 @@ def test_knn_ragged_sizes_and_full_k(mlg):
         _check_knn(x, None, k, got, R.knn_graph_matrix(x, k), "n%d" % n)
     with pytest.raises(RuntimeError):
         mlg.knn_graph_matrix(torch.randn(5, 3, device=DEV), 6)          # k > N: torch.topk raises in the reference too
+
+
+def test_dynconv_knn_then_conv(mlg):
+    """DynConv.forward (gcn_lib/sparse/torch_vertex.py:366-380): rebuild the dilated kNN graph from the features, then run the
+    static convolution on it -- the kNN -> conv call site.  In the reference this path raises for every conv its configs could
+    select (GraphConv.forward passes edge_attr= to EdgConv / MRConv.forward, which do not take it, and SAGEConv.forward calls
+    edge_attr.dim() on None); here the 'sage' / 'rsage' convolutions run with unit edge weights, which is what the oracle's
+    sage_forward computes for edge_attr=None.  Checked: the edge list (against the kNN oracle), the output and the input
+    gradient, for two graphs in one batch, with dilation."""
+    g = torch.Generator().manual_seed(21)
+    n, c, k, d = 300, 16, 6, 2
+    x = torch.randn(2 * n, c, generator=g)
+    batch = torch.arange(2).repeat_interleave(n)
+    for conv in ("sage", "rsage"):
+        torch.manual_seed(5)
+        dyn = mlg.DynConv(c, 24, kernel_size=k, dilation=d, conv=conv, act="leakyrelu", norm=None).to(DEV).eval()
+        xg = x.to(DEV).requires_grad_()
+        y = dyn(xg, batch.to(DEV))
+        ei_ref = R.dilate(R.knn_graph_matrix(x, k * d, batch), d)
+        ei = dyn.dilated_knn_graph(x.to(DEV), batch.to(DEV))
+        assert torch.equal(ei.cpu(), ei_ref), conv + ": dilated kNN edge list"
+        sd = {kk: v.detach().cpu().clone() for kk, v in dyn.state_dict().items()}
+        xr = x.clone().requires_grad_()
+        yr = R.sage_forward(sd, xr, ei_ref, None, relative=(conv == "rsage"), act="leakyrelu")
+        assert_close(y, yr, what="DynConv(%s) output" % conv)
+        Rw = torch.randn(yr.shape, generator=g)
+        (gx,) = torch.autograd.grad((y * Rw.to(DEV)).sum(), xg)
+        (gr,) = torch.autograd.grad((yr * Rw).sum(), xr)
+        assert_close(gx, gr, rtol=2e-4, what="DynConv(%s) input gradient" % conv)
+    with pytest.raises(NotImplementedError):
+        mlg.DynConv(c, 24)            # default conv='edge': a torch_geometric wrapper, out of scope (SURVEY section 2 row 2)

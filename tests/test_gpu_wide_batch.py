@@ -62,7 +62,9 @@ def test_reformulated_layers_with_more_than_32_graphs(mlg):
         sc = float(c.abs().max().clamp_min(1e-30))
         # 59 M LeakyReLU units at B = 40: a handful sit within fp32 rounding of 0 and take the other branch in one of the two
         # evaluation orders; each moves the ~19 fan-in rows of its gene (conftest.assert_close_flips)
-        assert_close_flips(a / sc, c / sc, "grad " + n, rtol=1e-4, atol=2e-6, l2=1e-4, outliers=1e-3)
+        # atol 5e-5 of the largest entry: the buffered path takes its weight gradients from the 3xTF32 tensor-core product over
+        # 616 k rows (accurate to ~4e-6 of sum |a||x|, not of the cancelled result), the factored path from fp32 FMA sums
+        assert_close_flips(a / sc, c / sc, "grad " + n, rtol=1e-4, atol=5e-5, l2=1e-4, outliers=1e-3)
 
 
 @pytest.mark.parametrize("P", [2, 3, 5])
