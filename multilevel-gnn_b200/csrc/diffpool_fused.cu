@@ -83,55 +83,113 @@ struct MemMap {
 };
 
 // ---------------------------------------------------------------------------------------------------------------------
+// Shared-memory matrices are stored with leading dimensions rounded up to a multiple of 4 floats (P4) at 16-byte aligned
+// offsets, so that 4 x 4 operand blocks are four 128-bit loads; global operands (x, weights, gradients) keep their natural
+// layout and take the vector path only when it happens to be aligned (c = 32 / 64 in the shipped sizes).
+MLG_DEV int P4(int v) { return (v + 3) & ~3; }
+
+struct alignas(16) F4 { float x, y, z, w; };
+MLG_DEV F4 ld4(const float* p) { return *reinterpret_cast<const F4*>(p); }
+MLG_DEV bool vec_ok(const float* p, int ld) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0 && (ld & 3) == 0; }
+
 // C[M x N] (ldc) = alpha * A[M x K] * B[K x N] (+ C when acc); A, B addressed by (row stride, column stride): a transposed
-// operand is just swapped strides.  TM x TN register tile per work item.
-template <int TM, int TN>
+// operand is just swapped strides.  4 x 4 register tile per work item, 4 k per step.
+// AM / BM: how the operand's 4 x 4 block is fetched -- 0: sixteen scalar loads (any strides); 1: contiguous along K (four
+// 128-bit loads, one per row / column of the tile); 2: contiguous along the tile's own dimension (M for A, N for B: four
+// 128-bit loads, one per k).  Rows / columns past M / N are clamped (mode 0, 1) or read from the row's padding (mode 2) and
+// never stored; the K tail (K % 4) runs scalar.
+template <int AM, int BM>
 MLG_DEV void mm_tile(float* C, int ldc, const float* A, int rsA, int csA, const float* B, int rsB, int csB, int M, int N, int K,
                      float alpha, bool acc) {
-  const int tm = (M + TM - 1) / TM, tn = (N + TN - 1) / TN;
+  const int tm = (M + 3) >> 2, tn = (N + 3) >> 2;
+  const int K4 = K & ~3;
   MLG_PFOR(t, tm * tn) {
-    const int i0 = (t / tn) * TM, j0 = (t % tn) * TN;
-    float c[TM][TN];
+    const int i0 = (t / tn) << 2, j0 = (t % tn) << 2;
+    float c[4][4];
 #pragma unroll
-    for (int r = 0; r < TM; ++r)
+    for (int r = 0; r < 4; ++r)
 #pragma unroll
-      for (int s = 0; s < TN; ++s) c[r][s] = 0.f;
-    const float* ap[TM];
-    const float* bp[TN];
+      for (int q = 0; q < 4; ++q) c[r][q] = 0.f;
+    const float* ap[4];
+    const float* bp[4];
 #pragma unroll
-    for (int r = 0; r < TM; ++r) ap[r] = A + (i0 + r < M ? i0 + r : i0) * rsA;
+    for (int r = 0; r < 4; ++r) ap[r] = A + (i0 + r < M ? i0 + r : i0) * rsA;
 #pragma unroll
-    for (int s = 0; s < TN; ++s) bp[s] = B + (j0 + s < N ? j0 + s : j0) * csB;
-#pragma unroll 2
-    for (int k = 0; k < K; ++k) {
-      float a[TM], bb[TN];
+    for (int q = 0; q < 4; ++q) bp[q] = B + (j0 + q < N ? j0 + q : j0) * csB;
+    for (int k = 0; k < K4; k += 4) {
+      float a[4][4], bb[4][4];     // a[r][kk], bb[kk][q]
+      if (AM == 1) {
 #pragma unroll
-      for (int r = 0; r < TM; ++r) a[r] = ap[r][k * csA];
+        for (int r = 0; r < 4; ++r) { const F4 v = ld4(ap[r] + k); a[r][0] = v.x; a[r][1] = v.y; a[r][2] = v.z; a[r][3] = v.w; }
+      } else if (AM == 2) {
 #pragma unroll
-      for (int s = 0; s < TN; ++s) bb[s] = bp[s][k * rsB];
+        for (int kk = 0; kk < 4; ++kk) { const F4 v = ld4(A + (k + kk) * csA + i0); a[0][kk] = v.x; a[1][kk] = v.y; a[2][kk] = v.z; a[3][kk] = v.w; }
+      } else {
 #pragma unroll
-      for (int r = 0; r < TM; ++r)
+        for (int r = 0; r < 4; ++r)
 #pragma unroll
-        for (int s = 0; s < TN; ++s) c[r][s] = fmaf(a[r], bb[s], c[r][s]);
+          for (int kk = 0; kk < 4; ++kk) a[r][kk] = ap[r][(k + kk) * csA];
+      }
+      if (BM == 1) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { const F4 v = ld4(bp[q] + k); bb[0][q] = v.x; bb[1][q] = v.y; bb[2][q] = v.z; bb[3][q] = v.w; }
+      } else if (BM == 2) {
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) { const F4 v = ld4(B + (k + kk) * rsB + j0); bb[kk][0] = v.x; bb[kk][1] = v.y; bb[kk][2] = v.z; bb[kk][3] = v.w; }
+      } else {
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk)
+#pragma unroll
+          for (int q = 0; q < 4; ++q) bb[kk][q] = bp[q][(k + kk) * rsB];
+      }
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk)
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+          for (int q = 0; q < 4; ++q) c[r][q] = fmaf(a[r][kk], bb[kk][q], c[r][q]);
+    }
+    for (int k = K4; k < K; ++k) {
+      float a[4], bb[4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) a[r] = ap[r][k * csA];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) bb[q] = bp[q][k * rsB];
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) c[r][q] = fmaf(a[r], bb[q], c[r][q]);
     }
 #pragma unroll
-    for (int r = 0; r < TM; ++r)
+    for (int r = 0; r < 4; ++r)
 #pragma unroll
-      for (int s = 0; s < TN; ++s)
-        if (i0 + r < M && j0 + s < N) {
-          float* p = C + (i0 + r) * ldc + j0 + s;
-          *p = acc ? fmaf(alpha, c[r][s], *p) : alpha * c[r][s];
+      for (int q = 0; q < 4; ++q)
+        if (i0 + r < M && j0 + q < N) {
+          float* p = C + (i0 + r) * ldc + j0 + q;
+          *p = acc ? fmaf(alpha, c[r][q], *p) : alpha * c[r][q];
         }
   }
   MLG_SYNC();
 }
 
-// 4 x 4 tiles throughout: smaller tiles for the small pooled products ([37 x 32] over K = 146 keeps 80 of 512 threads busy)
-// were measured SLOWER on B200 (b = 576 forward + backward 5.1 ms vs 3.5 ms): the kernel is bound by its instruction count
-// (r02 ncu: 229 M warp instructions forward, 41 % of them FFMA), not by idle threads.
-MLG_DEV void mm(float* C, int ldc, const float* A, int rsA, int csA, const float* B, int rsB, int csB, int M, int N, int K,
-                float alpha, bool acc) {
-  mm_tile<4, 4>(C, ldc, A, rsA, csA, B, rsB, csB, M, N, K, alpha, acc);
+// operand mode from its strides and alignment (uniform over the block).  Mode 2 reads up to 3 elements past the tile's own
+// dimension: only allowed for shared-memory operands, whose rows are padded (`padded`), or when that dimension is a
+// multiple of 4 anyway.
+MLG_DEV int op_mode(const float* p, int s_k, int s_own, bool padded, int own) {
+  if (s_k == 1 && vec_ok(p, s_own)) return 1;
+  if (s_own == 1 && (padded || (own & 3) == 0) && vec_ok(p, s_k)) return 2;
+  return 0;
+}
+
+// a_pad / b_pad: the operand lives in shared memory with P4-padded rows (mode 2 allowed)
+MLG_DEV void mm(float* C, int ldc, const float* A, int rsA, int csA, bool a_pad, const float* B, int rsB, int csB, bool b_pad,
+                int M, int N, int K, float alpha, bool acc) {
+  const int am = op_mode(A, csA, rsA, a_pad, M), bm = op_mode(B, rsB, csB, b_pad, N);
+#define MLG_MM(AM_, BM_) mm_tile<AM_, BM_>(C, ldc, A, rsA, csA, B, rsB, csB, M, N, K, alpha, acc)
+  if (am == 1) { if (bm == 1) MLG_MM(1, 1); else if (bm == 2) MLG_MM(1, 2); else MLG_MM(1, 0); }
+  else if (am == 2) { if (bm == 1) MLG_MM(2, 1); else if (bm == 2) MLG_MM(2, 2); else MLG_MM(2, 0); }
+  else { if (bm == 1) MLG_MM(0, 1); else if (bm == 2) MLG_MM(0, 2); else MLG_MM(0, 0); }
+#undef MLG_MM
 }
 
 // sum of v[0..n) in index order by one work item -> *dst (after the barrier everyone may read it)
@@ -145,28 +203,30 @@ MLG_DEV void ordered_sum(const float* v, int n, float* dst) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// DenseSAGEConv forward: U = ((A X) / deg) Wrel^T + X Wroot^T + b, then row-normalise.  Leaves M = A X / deg, the row
-// norms r (clamped at eps) and Y = U / r.  X: [n x c] (ldx), A: [n x n] (lda), Y: [n x o] (ldy = o).
-MLG_DEV void sage_fwd(const float* X, int ldx, const float* A, int lda, const float* deg, int n, int c, int o, const SageW& W,
-                      float* M, float* Y, float* r, bool have_M) {
+// DenseSAGEConv forward: U = ((A X) / deg) Wrel^T + X Wroot^T + b, then row-normalise.  Leaves M = A X / deg [n x c] (ld
+// P4(c)), the row norms r (clamped at eps) and Y = U / r [n x o] (ld P4(o)).  X: [n x c] (ldx; x_pad: shared memory),
+// A: [n x n] (lda), both A and the outputs in shared memory.
+MLG_DEV void sage_fwd(const float* X, int ldx, bool x_pad, const float* A, int lda, const float* deg, int n, int c, int o,
+                      const SageW& W, float* M, float* Y, float* r, bool have_M) {
+  const int cp = P4(c), op = P4(o);
   if (!have_M) {
-    mm(M, c, A, lda, 1, X, ldx, 1, n, c, n, 1.f, false);
-    MLG_PFOR(t, n * c) M[t] /= deg[t / c];
+    mm(M, cp, A, lda, 1, true, X, ldx, 1, x_pad, n, c, n, 1.f, false);
+    MLG_PFOR(t, n * c) M[(t / c) * cp + t % c] /= deg[t / c];
     MLG_SYNC();
   }
-  mm(Y, o, M, c, 1, W.rel, 1, c, n, o, c, 1.f, false);      // M Wrel^T: B(k, j) = Wrel[j][k]
-  mm(Y, o, X, ldx, 1, W.root, 1, c, n, o, c, 1.f, true);
+  mm(Y, op, M, cp, 1, true, W.rel, 1, c, false, n, o, c, 1.f, false);      // M Wrel^T: B(k, j) = Wrel[j][k]
+  mm(Y, op, X, ldx, 1, x_pad, W.root, 1, c, false, n, o, c, 1.f, true);
   MLG_PFOR(i, n) {
     float ss = 0.f;
     for (int j = 0; j < o; ++j) {
-      const float u = Y[i * o + j] + W.bias[j];
-      Y[i * o + j] = u;
+      const float u = Y[i * op + j] + W.bias[j];
+      Y[i * op + j] = u;
       ss = fmaf(u, u, ss);
     }
     const float rr = fmaxf(sqrtf(ss), kNormEps);
     r[i] = rr;
     const float inv = 1.f / rr;
-    for (int j = 0; j < o; ++j) Y[i * o + j] *= inv;
+    for (int j = 0; j < o; ++j) Y[i * op + j] *= inv;
   }
   MLG_SYNC();
 }
@@ -182,26 +242,28 @@ MLG_DEV void row_degrees(const float* A, int lda, int n, float* deg) {
 
 // One DiffPool layer + its after-pool DenseSAGE, forward.  X [n x c] (ldx) -> Xn [k x h] (in shared memory, the next
 // layer's input) ; the layer's pooled adjacency Ap [k x k] is the next layer's A.  stats: (F, E) of this sample.
-MLG_DEV void layer_fwd(const Params& P, int l, float* sm, const MemMap& mp, const float* X, int ldx, float* stats) {
+MLG_DEV void layer_fwd(const Params& P, int l, float* sm, const MemMap& mp, const float* X, int ldx, bool x_pad, float* stats) {
   const LayerDims d = P.d[l];
   const LayerMem& m = mp.L[l];
   const int n = d.n, c = d.c, k = d.k, h = d.h;
+  const int np = P4(n), kp = P4(k), hp = P4(h);
   float *A = sm + m.A, *deg = sm + m.deg, *M = sm + m.M, *S = sm + m.S, *Z = sm + m.Z;
   float *T1 = sm + m.T1, *small = sm + mp.small;
-  sage_fwd(X, ldx, A, n, deg, n, c, k, P.pool[l], M, S, sm + m.rp, false);
-  sage_fwd(X, ldx, A, n, deg, n, c, h, P.embed[l], M, Z, sm + m.re, true);
+  sage_fwd(X, ldx, x_pad, A, np, deg, n, c, k, P.pool[l], M, S, sm + m.rp, false);
+  sage_fwd(X, ldx, x_pad, A, np, deg, n, c, h, P.embed[l], M, Z, sm + m.re, true);
   // softmax over clusters + entropy, per row
   MLG_PFOR(i, n) {
+    float* s_ = S + i * kp;
     float mx = -INFINITY;
-    for (int j = 0; j < k; ++j) mx = fmaxf(mx, S[i * k + j]);
+    for (int j = 0; j < k; ++j) mx = fmaxf(mx, s_[j]);
     float den = 0.f;
-    for (int j = 0; j < k; ++j) den += expf(S[i * k + j] - mx);
+    for (int j = 0; j < k; ++j) den += expf(s_[j] - mx);
     const float lse = mx + logf(den);
     sm[m.lse + i] = lse;
     float ent = 0.f;
     for (int j = 0; j < k; ++j) {
-      const float s = expf(S[i * k + j] - lse);
-      S[i * k + j] = s;
+      const float s = expf(s_[j] - lse);
+      s_[j] = s;
       ent -= s * logf(s + kEntEps);
     }
     small[i] = ent;
@@ -209,33 +271,49 @@ MLG_DEV void layer_fwd(const Params& P, int l, float* sm, const MemMap& mp, cons
   MLG_SYNC();
   ordered_sum(small, n, stats + 1);
   // Xp = S^T Z ; Q = A S ; Ap = S^T Q
-  mm(sm + m.Xp, h, S, 1, k, Z, h, 1, k, h, n, 1.f, false);
-  mm(T1, k, A, n, 1, S, k, 1, n, k, n, 1.f, false);
-  mm(sm + m.Ap, k, S, 1, k, T1, k, 1, k, k, n, 1.f, false);
-  // F = ||A - S S^T||_F^2: 4 x 4 tiles of S S^T formed on the fly, one partial per row block, summed in order
+  mm(sm + m.Xp, hp, S, 1, kp, true, Z, hp, 1, true, k, h, n, 1.f, false);
+  mm(T1, kp, A, np, 1, true, S, kp, 1, true, n, k, n, 1.f, false);
+  mm(sm + m.Ap, kp, S, 1, kp, true, T1, kp, 1, true, k, k, n, 1.f, false);
+  // F = ||A - S S^T||_F^2: 4 x 4 tiles of S S^T formed on the fly (rows of S: 128-bit loads along the clusters), one partial
+  // per row block (single writer), summed in order
   {
-    const int tn = (n + 3) >> 2;
-    MLG_PFOR(t, tn) small[t] = 0.f;
-    MLG_SYNC();
-    // each work item owns ONE row block (4 rows) and walks its column tiles: partial[t] has a single writer
+    const int tn = (n + 3) >> 2, k4 = k & ~3;
     MLG_PFOR(t, tn) {
       const int i0 = t << 2;
+      const float* si[4];
+      for (int r = 0; r < 4; ++r) si[r] = S + (i0 + r < n ? i0 + r : i0) * kp;
       float f = 0.f;
       for (int j0 = 0; j0 < n; j0 += 4) {
+        const float* sj[4];
+        for (int q = 0; q < 4; ++q) sj[q] = S + (j0 + q < n ? j0 + q : j0) * kp;
         float cc[4][4];
+#pragma unroll
         for (int r = 0; r < 4; ++r)
-          for (int s = 0; s < 4; ++s) cc[r][s] = 0.f;
-        for (int q = 0; q < k; ++q) {
-          float a[4], bb[4];
-          for (int r = 0; r < 4; ++r) a[r] = S[(i0 + r < n ? i0 + r : i0) * k + q];
-          for (int s = 0; s < 4; ++s) bb[s] = S[(j0 + s < n ? j0 + s : j0) * k + q];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) cc[r][q] = 0.f;
+        for (int q0 = 0; q0 < k4; q0 += 4) {
+          F4 a[4], bq[4];
+#pragma unroll
+          for (int r = 0; r < 4; ++r) a[r] = ld4(si[r] + q0);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) bq[q] = ld4(sj[q] + q0);
+#pragma unroll
           for (int r = 0; r < 4; ++r)
-            for (int s = 0; s < 4; ++s) cc[r][s] = fmaf(a[r], bb[s], cc[r][s]);
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              cc[r][q] = fmaf(a[r].x, bq[q].x, fmaf(a[r].y, bq[q].y, fmaf(a[r].z, bq[q].z, fmaf(a[r].w, bq[q].w, cc[r][q]))));
         }
+        for (int q0 = k4; q0 < k; ++q0)
+#pragma unroll
+          for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) cc[r][q] = fmaf(si[r][q0], sj[q][q0], cc[r][q]);
+#pragma unroll
         for (int r = 0; r < 4; ++r)
-          for (int s = 0; s < 4; ++s)
-            if (i0 + r < n && j0 + s < n) {
-              const float dlt = A[(i0 + r) * n + j0 + s] - cc[r][s];
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            if (i0 + r < n && j0 + q < n) {
+              const float dlt = A[(i0 + r) * np + j0 + q] - cc[r][q];
               f = fmaf(dlt, dlt, f);
             }
       }
@@ -245,8 +323,8 @@ MLG_DEV void layer_fwd(const Params& P, int l, float* sm, const MemMap& mp, cons
     ordered_sum(small, tn, stats + 0);
   }
   // after-pool DenseSAGE on (Xp, Ap)
-  row_degrees(sm + m.Ap, k, k, sm + m.degp);
-  sage_fwd(sm + m.Xp, h, sm + m.Ap, k, sm + m.degp, k, h, h, P.after[l], sm + m.Mp, sm + m.Xn, sm + m.ra, false);
+  row_degrees(sm + m.Ap, kp, k, sm + m.degp);
+  sage_fwd(sm + m.Xp, hp, true, sm + m.Ap, kp, sm + m.degp, k, h, h, P.after[l], sm + m.Mp, sm + m.Xn, sm + m.ra, false);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -260,108 +338,113 @@ MLG_DEV void normalize_bwd_row(float* dY, const float* Y, float r, int o) {
   for (int j = 0; j < o; ++j) dY[j] = (dY[j] - Y[j] * dot) * inv;
 }
 
-// gW[o x c] += dU^T X ; partial accumulators in global memory (this CTA's slice): single writer per element
-MLG_DEV void wgrad(float* gW, const float* dU, int o, const float* X, int ldx, int c, int n) {
-  mm(gW, c, dU, 1, o, X, ldx, 1, o, c, n, 1.f, true);
+// gW[o x c] (global partial, ld c) += dU^T X ; single writer per element
+MLG_DEV void wgrad(float* gW, const float* dU, int ldu, int o, const float* X, int ldx, bool x_pad, int c, int n) {
+  mm(gW, c, dU, 1, ldu, true, X, ldx, 1, x_pad, o, c, n, 1.f, true);
 }
-MLG_DEV void bgrad(float* gb, const float* dU, int o, int n) {
+MLG_DEV void bgrad(float* gb, const float* dU, int ldu, int o, int n) {
   MLG_PFOR(j, o) {
     float s = 0.f;
-    for (int i = 0; i < n; ++i) s += dU[i * o + j];
+    for (int i = 0; i < n; ++i) s += dU[i * ldu + j];
     gb[j] += s;
   }
   MLG_SYNC();
 }
 
-// DenseSAGEConv backward given dU [n x o] (gradient at the pre-normalisation output).  Accumulates the parameter
-// gradients, adds dL/dX into dX [n x c] (ldd) and, when dA != nullptr, dL/dA (A is itself a function of earlier layers).
-// T: [n x c] scratch.  M = A X / deg (from forward), rowsum(A) > 1 <=> deg > 1 (deg == 1 may be the clamp: no gradient).
-MLG_DEV void sage_bwd(const float* dU, int o, const float* X, int ldx, const float* A, int lda, const float* deg, const float* M,
-                      int n, int c, const SageW& W, float* gWrel, float* gWroot, float* gb, float* T, bool first_into_T,
-                      float* dX, int ldd, bool acc_dX, bool finish, float* dA) {
-  wgrad(gWrel, dU, o, M, c, c, n);
-  wgrad(gWroot, dU, o, X, ldx, c, n);
-  bgrad(gb, dU, o, n);
+// DenseSAGEConv backward given dU [n x o] (ld P4(o), shared memory; gradient at the pre-normalisation output).  Accumulates
+// the parameter gradients, adds dL/dX into dX [n x c] (ldd) and, when dA != nullptr, dL/dA (A is itself a function of
+// earlier layers).  T: [n x c] scratch (ld P4(c)).  M = A X / deg (from forward, ld P4(c)); rowsum(A) > 1 <=> deg > 1.
+MLG_DEV void sage_bwd(const float* dU, int o, const float* X, int ldx, bool x_pad, const float* A, int lda, const float* deg,
+                      const float* M, int n, int c, const SageW& W, float* gWrel, float* gWroot, float* gb, float* T,
+                      bool first_into_T, float* dX, int ldd, bool acc_dX, bool finish, float* dA) {
+  const int cp = P4(c), op = P4(o);
+  wgrad(gWrel, dU, op, o, M, cp, true, c, n);
+  wgrad(gWroot, dU, op, o, X, ldx, x_pad, c, n);
+  bgrad(gb, dU, op, o, n);
   // T (+)= dU Wrel  (dL/dM, summed over the convolutions that share M) ; dX (+)= dU Wroot
-  mm(T, c, dU, o, 1, W.rel, c, 1, n, c, o, 1.f, !first_into_T);
-  mm(dX, ldd, dU, o, 1, W.root, c, 1, n, c, o, 1.f, acc_dX);
+  mm(T, cp, dU, op, 1, true, W.rel, c, 1, false, n, c, o, 1.f, !first_into_T);
+  mm(dX, ldd, dU, op, 1, true, W.root, c, 1, false, n, c, o, 1.f, acc_dX);
   if (!finish) return;
   if (dA) {   // through deg: d/d deg_i of (A X)_i / deg_i = -M_i / deg_i, only where the row sum exceeds the clamp
     MLG_PFOR(t, n * n) {
       const int i = t / n;
       if (deg[i] > 1.f) {
         float dot = 0.f;
-        for (int q = 0; q < c; ++q) dot = fmaf(T[i * c + q], M[i * c + q], dot);
+        for (int q = 0; q < c; ++q) dot = fmaf(T[i * cp + q], M[i * cp + q], dot);
         dA[i * lda + (t - i * n)] -= dot / deg[i];
       }
     }
     MLG_SYNC();
   }
-  MLG_PFOR(t, n * c) T[t] /= deg[t / c];
+  MLG_PFOR(t, n * c) T[(t / c) * cp + t % c] /= deg[t / c];
   MLG_SYNC();
-  mm(dX, ldd, A, 1, lda, T, c, 1, n, c, n, 1.f, true);          // A^T T
-  if (dA) mm(dA, lda, T, c, 1, X, 1, ldx, n, n, c, 1.f, true);   // T X^T
+  mm(dX, ldd, A, 1, lda, true, T, cp, 1, true, n, c, n, 1.f, true);          // A^T T
+  if (dA) mm(dA, lda, T, cp, 1, true, X, 1, ldx, x_pad, n, n, c, 1.f, true);   // T X^T
 }
 
-// One DiffPool layer backward.  In: dXn [k x h] = dL/d(after-pool output) (shared memory, overwritten), dAp_in [k x k] =
-// dL/dAp from later layers (nullptr: none).  Out: dX [n x c] (ldd; global for layer 0) and, for l > 0, dA [n x n] added.
-MLG_DEV void layer_bwd(const Params& P, int l, float* sm, const MemMap& mp, const float* X, int ldx, float* dXn, const float* dAp_in,
-                       float* dX, int ldd, float* dA, float* gpart) {
+// One DiffPool layer backward.  In: dXn [k x h] (ld P4(h)) = dL/d(after-pool output) (shared memory, overwritten), dAp_in
+// [k x k] (ld P4(k)) = dL/dAp from later layers (nullptr: none; overwritten).  Out: dX [n x c] (ldd; global for layer 0) and, for l > 0,
+// dA [n x n] (ld P4(n)) added.
+MLG_DEV void layer_bwd(const Params& P, int l, float* sm, const MemMap& mp, const float* X, int ldx, bool x_pad, float* dXn,
+                       float* dAp_in, float* dX, int ldd, float* dA, float* gpart) {
   const LayerDims d = P.d[l];
   const LayerMem& m = mp.L[l];
   const int n = d.n, c = d.c, k = d.k, h = d.h;
+  const int np = P4(n), cp = P4(c), kp = P4(k), hp = P4(h);
   float *A = sm + m.A, *deg = sm + m.deg, *M = sm + m.M, *S = sm + m.S, *Z = sm + m.Z;
   float *T1 = sm + m.T1, *T2 = sm + m.T2, *small = sm + mp.small;
   const float c_link = P.coef[2 * l], c_ent = P.coef[2 * l + 1];
   const int* go = P.grad_off[l];
-  // scratch inside `small`: dXp [k x h], dAp [k x k], G [k x k] (later S^T S), Tp [k x h]
+  // scratch inside `small`: dXp [k x hp], dAp [k x kp], G [k x kp] (later S^T S), Tp [k x hp]
+  // (dAp: the caller's dAp_in is consumed in place when there is one -- only the last layer needs its own)
   float* dXp = small;
-  float* dAp = dXp + k * h;
-  float* G = dAp + k * k;
+  float* G = dXp + k * hp;
   float* SS = G;
-  float* Tp = G + k * k;
+  float* Tp = G + k * kp;
+  float* dAp = dAp_in ? dAp_in : Tp + k * hp;
   // ---- after-pool DenseSAGE: Xn = normalize(U_a) ----
-  MLG_PFOR(i, k) normalize_bwd_row(dXn + i * h, sm + m.Xn + i * h, sm[m.ra + i], h);
+  MLG_PFOR(i, k) normalize_bwd_row(dXn + i * hp, sm + m.Xn + i * hp, sm[m.ra + i], h);
   MLG_SYNC();
-  MLG_PFOR(t, k * k) dAp[t] = dAp_in ? dAp_in[t] : 0.f;
+  if (!dAp_in) {
+    MLG_PFOR(t, k * kp) dAp[t] = 0.f;
+  }
   MLG_SYNC();
-  sage_bwd(dXn, h, sm + m.Xp, h, sm + m.Ap, k, sm + m.degp, sm + m.Mp, k, h, P.after[l], gpart + go[6], gpart + go[7],
-           gpart + go[8], Tp, true, dXp, h, false, true, dAp);
+  sage_bwd(dXn, h, sm + m.Xp, hp, true, sm + m.Ap, kp, sm + m.degp, sm + m.Mp, k, h, P.after[l], gpart + go[6], gpart + go[7],
+           gpart + go[8], Tp, true, dXp, hp, false, true, dAp);
   // ---- pooling: Xp = S^T Z, Ap = S^T A S, link, entropy ----
-  // row pass: dS_i = Z_i dXp^T (into T2) ; dZ_i = S_i dXp -> dU_e_i (over Z)
-  mm(T2, k, Z, h, 1, dXp, 1, h, n, k, h, 1.f, false);
-  mm(T1, h, S, k, 1, dXp, h, 1, n, h, k, 1.f, false);     // dZ into T1 (as [n x h])
+  // dS = Z dXp^T (into T2) ; dZ = S dXp (T1, as [n x hp]) -> dU_e (over Z)
+  mm(T2, kp, Z, hp, 1, true, dXp, 1, hp, true, n, k, h, 1.f, false);
+  mm(T1, hp, S, kp, 1, true, dXp, hp, 1, true, n, h, k, 1.f, false);
   MLG_PFOR(i, n) {
-    normalize_bwd_row(T1 + i * h, Z + i * h, sm[m.re + i], h);
-    for (int j = 0; j < h; ++j) Z[i * h + j] = T1[i * h + j];      // Z now holds dU_e
+    normalize_bwd_row(T1 + i * hp, Z + i * hp, sm[m.re + i], h);
+    for (int j = 0; j < h; ++j) Z[i * hp + j] = T1[i * hp + j];      // Z now holds dU_e
   }
   MLG_SYNC();
   // G1 = dAp^T - c_link I ; Q = A S (T1) ; dS += Q G1
-  MLG_PFOR(t, k * k) G[t] = dAp[(t % k) * k + t / k] - ((t % k) == (t / k) ? c_link : 0.f);
+  MLG_PFOR(t, k * k) G[(t / k) * kp + t % k] = dAp[(t % k) * kp + t / k] - ((t % k) == (t / k) ? c_link : 0.f);
   MLG_SYNC();
-  mm(T1, k, A, n, 1, S, k, 1, n, k, n, 1.f, false);
-  mm(T2, k, T1, k, 1, G, k, 1, n, k, k, 1.f, true);
-  if (dA) {   // dA += S dAp S^T + c_link (A - S S^T)   (A of this layer is the previous layer's pooled adjacency)
-    // R = S dAp (reuse T1 after Q is consumed), then dA += R S^T - c_link S S^T + c_link A = (R - c_link S) S^T + c_link A
-    mm(T1, k, S, k, 1, dAp, k, 1, n, k, k, 1.f, false);
-    MLG_PFOR(t, n * k) T1[t] -= c_link * S[t];
+  mm(T1, kp, A, np, 1, true, S, kp, 1, true, n, k, n, 1.f, false);
+  mm(T2, kp, T1, kp, 1, true, G, kp, 1, true, n, k, k, 1.f, true);
+  if (dA) {   // dA += S dAp S^T + c_link (A - S S^T) = (S dAp - c_link S) S^T + c_link A   (this layer's A = previous Ap)
+    mm(T1, kp, S, kp, 1, true, dAp, kp, 1, true, n, k, k, 1.f, false);
+    MLG_PFOR(t, n * k) T1[(t / k) * kp + t % k] -= c_link * S[(t / k) * kp + t % k];
     MLG_SYNC();
-    mm(dA, n, T1, k, 1, S, 1, k, n, n, k, 1.f, true);
-    MLG_PFOR(t, n * n) dA[t] = fmaf(c_link, A[t], dA[t]);
+    mm(dA, np, T1, kp, 1, true, S, 1, kp, true, n, n, k, 1.f, true);
+    MLG_PFOR(t, n * n) dA[(t / n) * np + t % n] = fmaf(c_link, A[(t / n) * np + t % n], dA[(t / n) * np + t % n]);
     MLG_SYNC();
   }
   // G2 = dAp - c_link I ; Q2 = A^T S (T1) ; dS += Q2 G2
-  MLG_PFOR(t, k * k) G[t] = dAp[t] - ((t % k) == (t / k) ? c_link : 0.f);
+  MLG_PFOR(t, k * k) G[(t / k) * kp + t % k] = dAp[(t / k) * kp + t % k] - ((t % k) == (t / k) ? c_link : 0.f);
   MLG_SYNC();
-  mm(T1, k, A, 1, n, S, k, 1, n, k, n, 1.f, false);
-  mm(T2, k, T1, k, 1, G, k, 1, n, k, k, 1.f, true);
+  mm(T1, kp, A, 1, np, true, S, kp, 1, true, n, k, n, 1.f, false);
+  mm(T2, kp, T1, kp, 1, true, G, kp, 1, true, n, k, k, 1.f, true);
   // + 2 c_link S (S^T S)
-  mm(SS, k, S, 1, k, S, k, 1, k, k, n, 1.f, false);
-  mm(T2, k, S, k, 1, SS, k, 1, n, k, k, 2.f * c_link, true);
+  mm(SS, kp, S, 1, kp, true, S, kp, 1, true, k, k, n, 1.f, false);
+  mm(T2, kp, S, kp, 1, true, SS, kp, 1, true, n, k, k, 2.f * c_link, true);
   // entropy, softmax backward, normalisation backward: T2 row i -> dU_p_i
   MLG_PFOR(i, n) {
-    float* dS = T2 + i * k;
-    const float* s = S + i * k;
+    float* dS = T2 + i * kp;
+    const float* s = S + i * kp;
     float dot = 0.f;
     for (int j = 0; j < k; ++j) {
       dS[j] -= c_ent * (logf(s[j] + kEntEps) + s[j] / (s[j] + kEntEps));
@@ -382,43 +465,46 @@ MLG_DEV void layer_bwd(const Params& P, int l, float* sm, const MemMap& mp, cons
   // ---- the two DenseSAGE convolutions that produced S and Z (shared M) ----
   if (m.recompute_M) {   // S is dead from here on: its storage takes M = A X / deg again
     M = S;
-    mm(M, c, A, n, 1, X, ldx, 1, n, c, n, 1.f, false);
-    MLG_PFOR(t, n * c) M[t] /= deg[t / c];
+    mm(M, cp, A, np, 1, true, X, ldx, 1, x_pad, n, c, n, 1.f, false);
+    MLG_PFOR(t, n * c) M[(t / c) * cp + t % c] /= deg[t / c];
     MLG_SYNC();
   }
-  sage_bwd(T2, k, X, ldx, A, n, deg, M, n, c, P.pool[l], gpart + go[0], gpart + go[1], gpart + go[2], T1, true, dX, ldd, false,
-           false, nullptr);
-  sage_bwd(Z, h, X, ldx, A, n, deg, M, n, c, P.embed[l], gpart + go[3], gpart + go[4], gpart + go[5], T1, false, dX, ldd, true,
-           true, dA);
+  sage_bwd(T2, k, X, ldx, x_pad, A, np, deg, M, n, c, P.pool[l], gpart + go[0], gpart + go[1], gpart + go[2], T1, true, dX, ldd,
+           false, false, nullptr);
+  sage_bwd(Z, h, X, ldx, x_pad, A, np, deg, M, n, c, P.embed[l], gpart + go[3], gpart + go[4], gpart + go[5], T1, false, dX, ldd,
+           true, true, dA);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
 MLG_DEV void load_adj(const Params& P, float* sm, const MemMap& mp) {
-  const int n = P.d[0].n;
-  MLG_PFOR(t, n * n) sm[mp.L[0].A + t] = P.adj[t];
+  const int n = P.d[0].n, np = P4(n);
+  MLG_PFOR(t, n * n) sm[mp.L[0].A + (t / n) * np + t % n] = P.adj[t];
   MLG_SYNC();
-  row_degrees(sm + mp.L[0].A, n, n, sm + mp.L[0].deg);
+  row_degrees(sm + mp.L[0].A, np, n, sm + mp.L[0].deg);
 }
 
 MLG_DEV void sample_fwd(const Params& P, float* sm, const MemMap& mp, int s, float* stats) {
   const float* X = P.x + (size_t)s * P.d[0].n * P.d[0].c;
   int ldx = P.d[0].c;
+  bool x_pad = false;
   for (int l = 0; l < P.layers; ++l) {
-    if (l > 0) row_degrees(sm + mp.L[l].A, P.d[l].n, P.d[l].n, sm + mp.L[l].deg);
-    layer_fwd(P, l, sm, mp, X, ldx, stats + 2 * l);
+    if (l > 0) row_degrees(sm + mp.L[l].A, P4(P.d[l].n), P.d[l].n, sm + mp.L[l].deg);
+    layer_fwd(P, l, sm, mp, X, ldx, x_pad, stats + 2 * l);
     X = sm + mp.L[l].Xn;
-    ldx = P.d[l].h;
+    ldx = P4(P.d[l].h);
+    x_pad = true;
   }
 }
 
 MLG_DEV void forward_body(const Params& P, float* sm, const MemMap& mp, int cta, int nctas) {
   load_adj(P, sm, mp);
   const LayerDims dl = P.d[P.layers - 1];
+  const int hp = P4(dl.h);
   for (int s = cta; s < P.b; s += nctas) {
     sample_fwd(P, sm, mp, s, P.stats + (size_t)s * 2 * P.layers);
     float* o = P.out + (size_t)s * dl.k * dl.h;
     const float* xn = sm + mp.L[P.layers - 1].Xn;
-    MLG_PFOR(t, dl.k * dl.h) o[t] = xn[t];
+    MLG_PFOR(t, dl.k * dl.h) o[t] = xn[(t / dl.h) * hp + t % dl.h];
     MLG_SYNC();
   }
 }
@@ -430,69 +516,68 @@ MLG_DEV void backward_body(const Params& P, float* sm, const MemMap& mp, int cta
   MLG_SYNC();
   const int Lz = P.layers;
   const LayerDims dl = P.d[Lz - 1];
+  const int hpl = P4(dl.h);
   float* small = sm + mp.small;
-  float stats_dummy[2 * kMaxLayers];
+  // tail of `small` (see build_map): forward statistics (not needed again), dL/d(out) [k_last x hp], and for two layers
+  // dL/dXn0 [k0 x hp0] + dL/dAp0 [k0 x kp0]
+  float* st = small + mp.small_floats - 2 * kMaxLayers;
+  float* dXn = st - dl.k * hpl;
   for (int s = cta; s < P.b; s += nctas) {
-#ifndef MLG_HOST_EMU
-    float* st = small + mp.small_floats - 2 * kMaxLayers;   // forward statistics are not needed again: park them in scratch
-#else
-    float* st = stats_dummy;
-#endif
-    (void)stats_dummy;
     sample_fwd(P, sm, mp, s, st);
-    // dL/d(output) into the last layer's Xn-shaped gradient buffer: reuse Mp of the last layer's after-pool? no: keep
-    // a dedicated [k x h] slot at the end of `small`
-    float* dXn = small + mp.small_floats - 2 * kMaxLayers - dl.k * dl.h;
     const float* go = P.g_out + (size_t)s * dl.k * dl.h;
-    MLG_PFOR(t, dl.k * dl.h) dXn[t] = go[t];
+    MLG_PFOR(t, dl.k * dl.h) dXn[(t / dl.h) * hpl + t % dl.h] = go[t];
     MLG_SYNC();
     if (Lz == 1) {
-      layer_bwd(P, 0, sm, mp, P.x + (size_t)s * P.d[0].n * P.d[0].c, P.d[0].c, dXn, nullptr,
+      layer_bwd(P, 0, sm, mp, P.x + (size_t)s * P.d[0].n * P.d[0].c, P.d[0].c, false, dXn, nullptr,
                 P.g_x + (size_t)s * P.d[0].n * P.d[0].c, P.d[0].c, nullptr, gpart);
     } else {
       // layer 1: its input is layer 0's after-pool output Xn0 [k0 x h0], its adjacency layer 0's Ap0 [k0 x k0]
       const LayerDims d0 = P.d[0];
-      float* dX1 = small + mp.small_floats - 2 * kMaxLayers - dl.k * dl.h - d0.k * d0.h;     // dL/dXn0
-      float* dA1 = dX1 - d0.k * d0.k;                                                          // dL/dAp0
-      MLG_PFOR(t, d0.k * d0.k) dA1[t] = 0.f;
+      const int hp0 = P4(d0.h), kp0 = P4(d0.k);
+      float* dX1 = dXn - d0.k * hp0;     // dL/dXn0
+      float* dA1 = dX1 - d0.k * kp0;     // dL/dAp0
+      MLG_PFOR(t, d0.k * kp0) dA1[t] = 0.f;
       MLG_SYNC();
-      layer_bwd(P, 1, sm, mp, sm + mp.L[0].Xn, d0.h, dXn, nullptr, dX1, d0.h, dA1, gpart);
-      layer_bwd(P, 0, sm, mp, P.x + (size_t)s * d0.n * d0.c, d0.c, dX1, dA1, P.g_x + (size_t)s * d0.n * d0.c, d0.c, nullptr,
-                gpart);
+      layer_bwd(P, 1, sm, mp, sm + mp.L[0].Xn, hp0, true, dXn, nullptr, dX1, hp0, dA1, gpart);
+      layer_bwd(P, 0, sm, mp, P.x + (size_t)s * d0.n * d0.c, d0.c, false, dX1, dA1, P.g_x + (size_t)s * d0.n * d0.c, d0.c,
+                nullptr, gpart);
     }
   }
 }
 
-// host side: shared-memory map (float offsets).  Layer l > 0 aliases its adjacency onto layer l-1's pooled adjacency.
+// host side: shared-memory map (float offsets, every matrix with P4-padded rows at a 16-byte aligned offset).  Layer l > 0
+// aliases its adjacency onto layer l-1's pooled adjacency.
 static inline int build_map(const Params& P, MemMap& mp) {
   int off = 0;
   auto take = [&](int nfl) { const int o = off; off += (nfl + 3) & ~3; return o; };
-  auto tsize = [](const LayerDims& d) { const int kk = d.k > d.h ? d.k : d.h; return d.n * (kk > d.c ? kk : d.c); };
+  auto p4 = [](int v) { return (v + 3) & ~3; };
+  auto tsize = [&](const LayerDims& d) { const int kk = d.k > d.h ? d.k : d.h; return d.n * p4(kk > d.c ? kk : d.c); };
   auto state = [&](int l, bool own_M) {
     const LayerDims d = P.d[l];
     LayerMem& m = mp.L[l];
     m.deg = take(d.n);
-    if (own_M) m.M = take(d.n * d.c);
-    m.S = take(d.n * (own_M ? d.k : (d.k > d.c ? d.k : d.c)));
-    m.Z = take(d.n * d.h);
+    if (own_M) m.M = take(d.n * p4(d.c));
+    m.S = take(d.n * p4(own_M ? d.k : (d.k > d.c ? d.k : d.c)));
+    m.Z = take(d.n * p4(d.h));
     m.rp = take(d.n);
     m.re = take(d.n);
     m.lse = take(d.n);
-    m.Xp = take(d.k * d.h);
-    m.Ap = take(d.k * d.k);
+    m.Xp = take(d.k * p4(d.h));
+    m.Ap = take(d.k * p4(d.k));
     m.degp = take(d.k);
-    m.Mp = take(d.k * d.h);
-    m.Xn = take(d.k * d.h);
+    m.Mp = take(d.k * p4(d.h));
+    m.Xn = take(d.k * p4(d.h));
     m.ra = take(d.k);
   };
   int smax = 0;
   for (int l = 0; l < P.layers; ++l) {
     const LayerDims d = P.d[l];
-    const int sl = d.n + 2 * d.k * d.h + 2 * d.k * d.k;   // per-row scratch (n), layer_bwd's dXp, dAp, G, Tp
+    // per-row scratch (n) ; layer_bwd's dXp, Tp, G and -- last layer only -- dAp
+    const int sl = p4(d.n) + 2 * d.k * p4(d.h) + (l == P.layers - 1 ? 2 : 1) * d.k * p4(d.k);
     smax = sl > smax ? sl : smax;
   }
   // layer 0
-  mp.L[0].A = take(P.d[0].n * P.d[0].n);
+  mp.L[0].A = take(P.d[0].n * p4(P.d[0].n));
   state(0, false);
   mp.L[0].recompute_M = 1;
   const int region = off;
@@ -510,10 +595,12 @@ static inline int build_map(const Params& P, MemMap& mp) {
     if (off > region_end) region_end = off;
   }
   off = region_end;
-  // tail of `small`: statistics, dL/d(out), and for two layers dL/dXn0 + dL/dAp0
-  int tail = 2 * kMaxLayers + P.d[P.layers - 1].k * P.d[P.layers - 1].h;
-  if (P.layers > 1) tail += P.d[0].k * P.d[0].h + P.d[0].k * P.d[0].k;
-  mp.small_floats = ((smax + tail) + 3) & ~3;
+  // tail of `small`: statistics, dL/d(out), and for two layers dL/dXn0 + dL/dAp0 (all P4-padded rows)
+  const LayerDims dl = P.d[P.layers - 1];
+  int tail = 2 * kMaxLayers + dl.k * p4(dl.h);
+  if (P.layers > 1) tail += P.d[0].k * p4(P.d[0].h) + P.d[0].k * p4(P.d[0].k);
+  smax = (smax + 3) & ~3;
+  mp.small_floats = smax + ((tail + 3) & ~3) + 4;
   mp.small = take(mp.small_floats);
   mp.total = off;
   return off;

@@ -152,7 +152,7 @@ def diffpool(quick):
     sd = {k: v.detach().cpu() for k, v in dp.state_dict().items()}
     bs = 64 if quick else 144
     c_ms = cpu_ms(lambda: R.diffpool_forward(sd, x[:bs], adj))
-    emit(row="a11 DiffPool at the reference size (fp32 library GEMMs; launch-bound)", shape="b=576 N=146->37->10 C=32->32->64",
+    emit(row="a11 DiffPool at the reference size (one fused fp32 kernel per direction, a sample per CTA)", shape="b=576 N=146->37->10 C=32->32->64",
          fwd_bwd_ms=round(ms, 3), cpu_oracle_fwd_ms=round(c_ms * 576 / bs, 1),
          cpu_sample="%d of 576 samples, scaled" % bs)
     import ctypes
