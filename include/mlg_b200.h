@@ -338,16 +338,20 @@ int mlg_head_mlp_bwd(const float* g_pred, const float* g_loss, const float* pred
  * Backward: g_out [b, k_last, h_last]; coef DEVICE [2*layers] = per layer (g_link / (sqrt(sum_b F_l) numel(adj_l)),
  *   g_entropy / (b n_l)); g_x [b, n0, c0]; g_weights: ONE device buffer of mlg_diffpool_grad_floats floats, the 9 gradients
  *   of each layer back to back in the order of `weights`; workspace >= mlg_diffpool_ctas(b) * grad_floats * 4 bytes.
+ *   state (16-byte aligned DEVICE buffer of b * mlg_diffpool_state_floats floats, or NULL): the forward intermediates
+ *   backward reads again.  Forward writes it when given; backward given the same buffer skips recomputing the forward pass
+ *   (NULL: it recomputes).
  * mlg_diffpool_supported: the per-sample working set fits the 227 KB of shared memory of one SM. */
 int64_t mlg_diffpool_smem_bytes(int64_t layers, const int64_t* dims);
 int mlg_diffpool_supported(int64_t layers, const int64_t* dims);
 int64_t mlg_diffpool_grad_floats(int64_t layers, const int64_t* dims);
+int64_t mlg_diffpool_state_floats(int64_t layers, const int64_t* dims);
 int64_t mlg_diffpool_ctas(int64_t b);
 int mlg_diffpool_fwd(const float* x, const float* adj, const float* const* weights, int64_t layers, const int64_t* dims,
-                     int64_t b, float* out, float* stats, void* stream);
+                     int64_t b, float* out, float* stats, float* state, void* stream);
 int mlg_diffpool_bwd(const float* g_out, const float* coef, const float* x, const float* adj, const float* const* weights,
-                     int64_t layers, const int64_t* dims, int64_t b, float* g_x, float* g_weights, void* workspace,
-                     int64_t workspace_bytes, void* stream);
+                     int64_t layers, const int64_t* dims, int64_t b, float* g_x, float* g_weights, const float* state,
+                     void* workspace, int64_t workspace_bytes, void* stream);
 
 /* z[r,c] = LeakyReLU_slope(z[r,c] + bias[c]) in place (bias NULL ok; slope 0 = ReLU): the bias + activation
  * of SAGEConv.update's MLP (torch_vertex.py:288-291) after the update GEMM. */

@@ -70,10 +70,11 @@ _SIGNATURES = {
     "mlg_diffpool_smem_bytes": (_c_i64, [_c_i64, _c_vp]),
     "mlg_diffpool_supported": (_c_int, [_c_i64, _c_vp]),
     "mlg_diffpool_grad_floats": (_c_i64, [_c_i64, _c_vp]),
+    "mlg_diffpool_state_floats": (_c_i64, [_c_i64, _c_vp]),
     "mlg_diffpool_ctas": (_c_i64, [_c_i64]),
-    "mlg_diffpool_fwd": (_c_int, [_c_vp, _c_vp, _c_vp, _c_i64, _c_vp, _c_i64, _c_vp, _c_vp, _c_vp]),
-    "mlg_diffpool_bwd": (_c_int, [_c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_i64, _c_vp, _c_i64, _c_vp, _c_vp, _c_vp, _c_i64,
-                                  _c_vp]),
+    "mlg_diffpool_fwd": (_c_int, [_c_vp, _c_vp, _c_vp, _c_i64, _c_vp, _c_i64, _c_vp, _c_vp, _c_vp, _c_vp]),
+    "mlg_diffpool_bwd": (_c_int, [_c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_i64, _c_vp, _c_i64, _c_vp, _c_vp, _c_vp, _c_vp,
+                                  _c_i64, _c_vp]),
     "mlg_sage_fold_fwd": (_c_int, [_c_vp, _c_vp, _c_i64, _c_i64, _c_i64, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp]),
     "mlg_sage_fold_bwd": (_c_int, [_c_vp, _c_vp, _c_vp, _c_i64, _c_i64, _c_i64, _c_vp, _c_vp, _c_vp]),
     "mlg_pca_indep_loss": (_c_int, [_c_vp, _c_vp, _c_vp, _c_i64, _c_i64, _c_vp, _c_vp, _c_vp]),

@@ -12,9 +12,11 @@
 // Here one persistent CTA walks the samples; everything of one sample (A, M = A X / deg, S, Z, A S, pooled X / A of both
 // layers) lives in shared memory (<= 227 KB), all contractions are register-tiled (4 x 4 per thread) loops over shared
 // memory, and only x, the output [k_last, h_last], four scalars (link / entropy partial sums of both layers) and, in
-// backward, dL/dx and a per-CTA partial of the 18 parameter gradients ever touch global memory.  The backward kernel
-// recomputes the forward pass of its sample (cheaper than spilling ~200 KB of intermediates per sample) and then walks it
-// in reverse; parameter-gradient partials are reduced over the CTAs in a fixed order by a second tiny kernel.
+// backward, dL/dx and a per-CTA partial of the 18 parameter gradients ever touch global memory -- plus, when a backward
+// pass will follow, the ~90 KB per sample of forward state backward reads again (S, Z, the pooled X / A, the row norms:
+// two contiguous shared-memory ranges, written / read with 128-bit moves; 52 MB at b = 576 against 0.6 ms of recomputation).
+// Without a state buffer the backward kernel recomputes the forward pass of its sample.  Parameter-gradient partials are
+// reduced over the CTAs in a fixed order by a second tiny kernel.
 //
 // Every phase is written as "parallel for over work items, then barrier" (MLG_PFOR / MLG_SYNC) without warp-level
 // primitives, so the SAME source also compiles as plain host C++ (-DMLG_HOST_EMU, tests/ only) where the items of a phase
@@ -60,6 +62,8 @@ struct Params {
   int b;
   float* out;          // [b, k_last, h_last]
   float* stats;        // [b, 2 * layers]: (F, E) per layer: ||A - S S^T||_F^2 and sum -S log(S + eps) of this sample
+  float* state;        // [b, MemMap::state_floats] or nullptr: forward writes it (when given), backward reads it (when given;
+                       // nullptr: backward recomputes the forward pass of every sample)
   // backward
   const float* g_out;  // [b, k_last, h_last]
   const float* coef;   // [2 * layers]: (c_link, c_ent) per layer: g_l / (sqrt(sum_b F) numel(adj)), g_e / (b n)
@@ -80,6 +84,10 @@ struct MemMap {
   LayerMem L[kMaxLayers];
   int small, total;    // scratch for reductions and the small [k x k] / [k x h] gradients
   int small_floats;
+  // what backward needs from forward is one contiguous range of shared memory per layer (deg .. ra): the forward kernel can
+  // write it out per sample (Params::state) and the backward kernel reads it back instead of recomputing the forward pass
+  int state_off[kMaxLayers], state_len[kMaxLayers];   // floats, multiples of 4
+  int state_floats;                                    // per sample
 };
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -192,8 +200,22 @@ MLG_DEV void mm(float* C, int ldc, const float* A, int rsA, int csA, bool a_pad,
 #undef MLG_MM
 }
 
-// sum of v[0..n) in index order by one work item -> *dst (after the barrier everyone may read it)
-MLG_DEV void ordered_sum(const float* v, int n, float* dst) {
+// sum of v[0..n) -> *dst in a fixed tree (fan-in 16 per level; the levels' partials go to the scratch right behind v, so
+// v needs ~1.07 n + 8 floats).  After the closing barrier everyone may read *dst.
+MLG_DEV void block_sum(float* v, int n, float* dst) {
+  while (n > 16) {
+    const int m = (n + 15) >> 4;
+    float* w = v + P4(n);
+    MLG_PFOR(t, m) {
+      const int e = 16 * t + 16 < n ? 16 * t + 16 : n;
+      float s = 0.f;
+      for (int i = 16 * t; i < e; ++i) s += v[i];
+      w[t] = s;
+    }
+    MLG_SYNC();
+    v = w;
+    n = m;
+  }
   MLG_PFOR(t, 1) {
     float s = 0.f;
     for (int i = 0; i < n; ++i) s += v[i];
@@ -201,6 +223,11 @@ MLG_DEV void ordered_sum(const float* v, int n, float* dst) {
   }
   MLG_SYNC();
 }
+
+// Row-per-work-item loops walk their row starting at column (row % len): concurrently running rows then touch different
+// shared-memory banks although the leading dimensions are multiples of 4 (a plain j = 0.. walk is a 32-way conflict for
+// ld = 32).  The order is fixed per row, so results stay deterministic.
+#define MLG_ROT(j, jj, i, len) int j = (jj) + (i) % (len); if (j >= (len)) j -= (len)
 
 // ---------------------------------------------------------------------------------------------------------------------
 // DenseSAGEConv forward: U = ((A X) / deg) Wrel^T + X Wroot^T + b, then row-normalise.  Leaves M = A X / deg [n x c] (ld
@@ -218,7 +245,8 @@ MLG_DEV void sage_fwd(const float* X, int ldx, bool x_pad, const float* A, int l
   mm(Y, op, X, ldx, 1, x_pad, W.root, 1, c, false, n, o, c, 1.f, true);
   MLG_PFOR(i, n) {
     float ss = 0.f;
-    for (int j = 0; j < o; ++j) {
+    for (int jj = 0; jj < o; ++jj) {
+      MLG_ROT(j, jj, i, o);
       const float u = Y[i * op + j] + W.bias[j];
       Y[i * op + j] = u;
       ss = fmaf(u, u, ss);
@@ -226,7 +254,10 @@ MLG_DEV void sage_fwd(const float* X, int ldx, bool x_pad, const float* A, int l
     const float rr = fmaxf(sqrtf(ss), kNormEps);
     r[i] = rr;
     const float inv = 1.f / rr;
-    for (int j = 0; j < o; ++j) Y[i * op + j] *= inv;
+    for (int jj = 0; jj < o; ++jj) {
+      MLG_ROT(j, jj, i, o);
+      Y[i * op + j] *= inv;
+    }
   }
   MLG_SYNC();
 }
@@ -234,7 +265,10 @@ MLG_DEV void sage_fwd(const float* X, int ldx, bool x_pad, const float* A, int l
 MLG_DEV void row_degrees(const float* A, int lda, int n, float* deg) {
   MLG_PFOR(i, n) {
     float s = 0.f;
-    for (int j = 0; j < n; ++j) s += A[i * lda + j];
+    for (int jj = 0; jj < n; ++jj) {
+      MLG_ROT(j, jj, i, n);
+      s += A[i * lda + j];
+    }
     deg[i] = fmaxf(s, 1.f);
   }
   MLG_SYNC();
@@ -249,19 +283,34 @@ MLG_DEV void layer_fwd(const Params& P, int l, float* sm, const MemMap& mp, cons
   const int np = P4(n), kp = P4(k), hp = P4(h);
   float *A = sm + m.A, *deg = sm + m.deg, *M = sm + m.M, *S = sm + m.S, *Z = sm + m.Z;
   float *T1 = sm + m.T1, *small = sm + mp.small;
+  if (!x_pad) {   // global input: one copy into T1 (free until Q = A S) instead of three latency-bound passes over global
+    const int cp = P4(c);
+    MLG_PFOR(t, n * c) T1[(t / c) * cp + t % c] = X[t / c * ldx + t % c];
+    MLG_SYNC();
+    X = T1;
+    ldx = cp;
+    x_pad = true;
+  }
   sage_fwd(X, ldx, x_pad, A, np, deg, n, c, k, P.pool[l], M, S, sm + m.rp, false);
   sage_fwd(X, ldx, x_pad, A, np, deg, n, c, h, P.embed[l], M, Z, sm + m.re, true);
   // softmax over clusters + entropy, per row
   MLG_PFOR(i, n) {
     float* s_ = S + i * kp;
     float mx = -INFINITY;
-    for (int j = 0; j < k; ++j) mx = fmaxf(mx, s_[j]);
+    for (int jj = 0; jj < k; ++jj) {
+      MLG_ROT(j, jj, i, k);
+      mx = fmaxf(mx, s_[j]);
+    }
     float den = 0.f;
-    for (int j = 0; j < k; ++j) den += expf(s_[j] - mx);
+    for (int jj = 0; jj < k; ++jj) {
+      MLG_ROT(j, jj, i, k);
+      den += expf(s_[j] - mx);
+    }
     const float lse = mx + logf(den);
     sm[m.lse + i] = lse;
     float ent = 0.f;
-    for (int j = 0; j < k; ++j) {
+    for (int jj = 0; jj < k; ++jj) {
+      MLG_ROT(j, jj, i, k);
       const float s = expf(s_[j] - lse);
       s_[j] = s;
       ent -= s * logf(s + kEntEps);
@@ -269,22 +318,28 @@ MLG_DEV void layer_fwd(const Params& P, int l, float* sm, const MemMap& mp, cons
     small[i] = ent;
   }
   MLG_SYNC();
-  ordered_sum(small, n, stats + 1);
+  block_sum(small, n, stats + 1);
   // Xp = S^T Z ; Q = A S ; Ap = S^T Q
   mm(sm + m.Xp, hp, S, 1, kp, true, Z, hp, 1, true, k, h, n, 1.f, false);
   mm(T1, kp, A, np, 1, true, S, kp, 1, true, n, k, n, 1.f, false);
   mm(sm + m.Ap, kp, S, 1, kp, true, T1, kp, 1, true, k, k, n, 1.f, false);
-  // F = ||A - S S^T||_F^2: 4 x 4 tiles of S S^T formed on the fly (rows of S: 128-bit loads along the clusters), one partial
-  // per row block (single writer), summed in order
+  // F = ||A - S S^T||_F^2.  S S^T is symmetric: one work item per unordered pair of 4-row blocks {ti, tj} forms the 4 x 4
+  // tile once (rows of S: 128-bit loads along the clusters) and charges it against A[ti, tj] and, off the diagonal,
+  // A[tj, ti].  Pairs are enumerated as (ti, (ti + d) % tn), d = 0 .. tn / 2 (each unordered pair exactly once); one partial
+  // per item (single writer), summed in a fixed tree.
   {
-    const int tn = (n + 3) >> 2, k4 = k & ~3;
-    MLG_PFOR(t, tn) {
-      const int i0 = t << 2;
-      const float* si[4];
-      for (int r = 0; r < 4; ++r) si[r] = S + (i0 + r < n ? i0 + r : i0) * kp;
+    const int tn = (n + 3) >> 2, k4 = k & ~3, nd = tn / 2 + 1;
+    MLG_PFOR(t, tn * nd) {
+      const int ti = t / nd, dd = t - ti * nd;
+      int tj = ti + dd;
+      if (tj >= tn) tj -= tn;
       float f = 0.f;
-      for (int j0 = 0; j0 < n; j0 += 4) {
+      // even tn: the d = tn / 2 pairs would appear from both ends
+      if (!((tn & 1) == 0 && dd == tn / 2 && ti >= tn / 2)) {
+        const int i0 = ti << 2, j0 = tj << 2;
+        const float* si[4];
         const float* sj[4];
+        for (int r = 0; r < 4; ++r) si[r] = S + (i0 + r < n ? i0 + r : i0) * kp;
         for (int q = 0; q < 4; ++q) sj[q] = S + (j0 + q < n ? j0 + q : j0) * kp;
         float cc[4][4];
 #pragma unroll
@@ -313,14 +368,18 @@ MLG_DEV void layer_fwd(const Params& P, int l, float* sm, const MemMap& mp, cons
 #pragma unroll
           for (int q = 0; q < 4; ++q)
             if (i0 + r < n && j0 + q < n) {
-              const float dlt = A[(i0 + r) * np + j0 + q] - cc[r][q];
-              f = fmaf(dlt, dlt, f);
+              const float d1 = A[(i0 + r) * np + j0 + q] - cc[r][q];
+              f = fmaf(d1, d1, f);
+              if (ti != tj) {
+                const float d2 = A[(j0 + q) * np + i0 + r] - cc[r][q];
+                f = fmaf(d2, d2, f);
+              }
             }
       }
       small[t] = f;
     }
     MLG_SYNC();
-    ordered_sum(small, tn, stats + 0);
+    block_sum(small, tn * nd, stats + 0);
   }
   // after-pool DenseSAGE on (Xp, Ap)
   row_degrees(sm + m.Ap, kp, k, sm + m.degp);
@@ -330,12 +389,18 @@ MLG_DEV void layer_fwd(const Params& P, int l, float* sm, const MemMap& mp, cons
 // ---------------------------------------------------------------------------------------------------------------------
 // backward helpers
 // dU_i = (dY_i - Y_i (Y_i . dY_i)) / r_i   (r_i = max(||U_i||, eps); at the clamp the norm is a constant: dU = dY / eps)
-MLG_DEV void normalize_bwd_row(float* dY, const float* Y, float r, int o) {
+MLG_DEV void normalize_bwd_row(float* dY, const float* Y, float r, int o, int i) {
   float dot = 0.f;
   if (r > kNormEps)
-    for (int j = 0; j < o; ++j) dot = fmaf(Y[j], dY[j], dot);
+    for (int jj = 0; jj < o; ++jj) {
+      MLG_ROT(j, jj, i, o);
+      dot = fmaf(Y[j], dY[j], dot);
+    }
   const float inv = 1.f / r;
-  for (int j = 0; j < o; ++j) dY[j] = (dY[j] - Y[j] * dot) * inv;
+  for (int jj = 0; jj < o; ++jj) {
+    MLG_ROT(j, jj, i, o);
+    dY[j] = (dY[j] - Y[j] * dot) * inv;
+  }
 }
 
 // gW[o x c] (global partial, ld c) += dU^T X ; single writer per element
@@ -370,7 +435,7 @@ MLG_DEV void sage_bwd(const float* dU, int o, const float* X, int ldx, bool x_pa
       const int i = t / n;
       if (deg[i] > 1.f) {
         float dot = 0.f;
-        for (int q = 0; q < c; ++q) dot = fmaf(T[i * cp + q], M[i * cp + q], dot);
+        for (int q = 0; q < c; ++q) dot = fmaf(T[i * cp + q], M[i * cp + q], dot);   // (same row for a whole warp: broadcast)
         dA[i * lda + (t - i * n)] -= dot / deg[i];
       }
     }
@@ -403,7 +468,7 @@ MLG_DEV void layer_bwd(const Params& P, int l, float* sm, const MemMap& mp, cons
   float* Tp = G + k * kp;
   float* dAp = dAp_in ? dAp_in : Tp + k * hp;
   // ---- after-pool DenseSAGE: Xn = normalize(U_a) ----
-  MLG_PFOR(i, k) normalize_bwd_row(dXn + i * hp, sm + m.Xn + i * hp, sm[m.ra + i], h);
+  MLG_PFOR(i, k) normalize_bwd_row(dXn + i * hp, sm + m.Xn + i * hp, sm[m.ra + i], h, i);
   MLG_SYNC();
   if (!dAp_in) {
     MLG_PFOR(t, k * kp) dAp[t] = 0.f;
@@ -416,8 +481,11 @@ MLG_DEV void layer_bwd(const Params& P, int l, float* sm, const MemMap& mp, cons
   mm(T2, kp, Z, hp, 1, true, dXp, 1, hp, true, n, k, h, 1.f, false);
   mm(T1, hp, S, kp, 1, true, dXp, hp, 1, true, n, h, k, 1.f, false);
   MLG_PFOR(i, n) {
-    normalize_bwd_row(T1 + i * hp, Z + i * hp, sm[m.re + i], h);
-    for (int j = 0; j < h; ++j) Z[i * hp + j] = T1[i * hp + j];      // Z now holds dU_e
+    normalize_bwd_row(T1 + i * hp, Z + i * hp, sm[m.re + i], h, i);
+    for (int jj = 0; jj < h; ++jj) {
+      MLG_ROT(j, jj, i, h);
+      Z[i * hp + j] = T1[i * hp + j];      // Z now holds dU_e
+    }
   }
   MLG_SYNC();
   // G1 = dAp^T - c_link I ; Q = A S (T1) ; dS += Q G1
@@ -446,20 +514,25 @@ MLG_DEV void layer_bwd(const Params& P, int l, float* sm, const MemMap& mp, cons
     float* dS = T2 + i * kp;
     const float* s = S + i * kp;
     float dot = 0.f;
-    for (int j = 0; j < k; ++j) {
+    for (int jj = 0; jj < k; ++jj) {
+      MLG_ROT(j, jj, i, k);
       dS[j] -= c_ent * (logf(s[j] + kEntEps) + s[j] / (s[j] + kEntEps));
       dot = fmaf(s[j], dS[j], dot);
     }
     const float lse = sm[m.lse + i], r = sm[m.rp + i];
     // dR = S (dS - S.dS) ; S_raw = log S + lse (the normalised pre-softmax row) ; dU_p = normalize_bwd(dR, S_raw, r)
     float dn = 0.f;
-    for (int j = 0; j < k; ++j) {
+    for (int jj = 0; jj < k; ++jj) {
+      MLG_ROT(j, jj, i, k);
       const float dr = s[j] * (dS[j] - dot);
       dS[j] = dr;
       if (r > kNormEps) dn = fmaf(logf(s[j]) + lse, dr, dn);
     }
     const float inv = 1.f / r;
-    for (int j = 0; j < k; ++j) dS[j] = (dS[j] - (logf(s[j]) + lse) * dn) * inv;
+    for (int jj = 0; jj < k; ++jj) {
+      MLG_ROT(j, jj, i, k);
+      dS[j] = (dS[j] - (logf(s[j]) + lse) * dn) * inv;
+    }
   }
   MLG_SYNC();
   // ---- the two DenseSAGE convolutions that produced S and Z (shared M) ----
@@ -496,12 +569,30 @@ MLG_DEV void sample_fwd(const Params& P, float* sm, const MemMap& mp, int s, flo
   }
 }
 
+// copy the per-layer state ranges of the current sample to / from global memory (128-bit moves)
+MLG_DEV void state_io(const Params& P, float* sm, const MemMap& mp, int s, bool save) {
+  float* g = P.state + (size_t)s * mp.state_floats;
+  for (int l = 0; l < P.layers; ++l) {
+    F4* a = reinterpret_cast<F4*>(sm + mp.state_off[l]);
+    F4* d = reinterpret_cast<F4*>(g);
+    const int n4 = mp.state_len[l] >> 2;
+    if (save) {
+      MLG_PFOR(t, n4) d[t] = a[t];
+    } else {
+      MLG_PFOR(t, n4) a[t] = d[t];
+    }
+    g += mp.state_len[l];
+  }
+  MLG_SYNC();
+}
+
 MLG_DEV void forward_body(const Params& P, float* sm, const MemMap& mp, int cta, int nctas) {
   load_adj(P, sm, mp);
   const LayerDims dl = P.d[P.layers - 1];
   const int hp = P4(dl.h);
   for (int s = cta; s < P.b; s += nctas) {
     sample_fwd(P, sm, mp, s, P.stats + (size_t)s * 2 * P.layers);
+    if (P.state) state_io(P, sm, mp, s, true);
     float* o = P.out + (size_t)s * dl.k * dl.h;
     const float* xn = sm + mp.L[P.layers - 1].Xn;
     MLG_PFOR(t, dl.k * dl.h) o[t] = xn[(t / dl.h) * hp + t % dl.h];
@@ -523,7 +614,8 @@ MLG_DEV void backward_body(const Params& P, float* sm, const MemMap& mp, int cta
   float* st = small + mp.small_floats - 2 * kMaxLayers;
   float* dXn = st - dl.k * hpl;
   for (int s = cta; s < P.b; s += nctas) {
-    sample_fwd(P, sm, mp, s, st);
+    if (P.state) state_io(P, sm, mp, s, false);
+    else sample_fwd(P, sm, mp, s, st);
     const float* go = P.g_out + (size_t)s * dl.k * dl.h;
     MLG_PFOR(t, dl.k * dl.h) dXn[(t / dl.h) * hpl + t % dl.h] = go[t];
     MLG_SYNC();
@@ -555,6 +647,7 @@ static inline int build_map(const Params& P, MemMap& mp) {
   auto state = [&](int l, bool own_M) {
     const LayerDims d = P.d[l];
     LayerMem& m = mp.L[l];
+    mp.state_off[l] = off;
     m.deg = take(d.n);
     if (own_M) m.M = take(d.n * p4(d.c));
     m.S = take(d.n * p4(own_M ? d.k : (d.k > d.c ? d.k : d.c)));
@@ -568,13 +661,19 @@ static inline int build_map(const Params& P, MemMap& mp) {
     m.Mp = take(d.k * p4(d.h));
     m.Xn = take(d.k * p4(d.h));
     m.ra = take(d.k);
+    mp.state_len[l] = off - mp.state_off[l];
   };
   int smax = 0;
+  mp.state_floats = 0;
+  for (int l = 0; l < kMaxLayers; ++l) mp.state_off[l] = mp.state_len[l] = 0;
   for (int l = 0; l < P.layers; ++l) {
     const LayerDims d = P.d[l];
     // per-row scratch (n) ; layer_bwd's dXp, Tp, G and -- last layer only -- dAp
     const int sl = p4(d.n) + 2 * d.k * p4(d.h) + (l == P.layers - 1 ? 2 : 1) * d.k * p4(d.k);
     smax = sl > smax ? sl : smax;
+    // block_sum over the F partials (one per pair of 4-row blocks) and its tree levels
+    const int tn = (d.n + 3) / 4, items = tn * (tn / 2 + 1), sf = items + items / 8 + 64;
+    smax = sf > smax ? sf : smax;
   }
   // layer 0
   mp.L[0].A = take(P.d[0].n * p4(P.d[0].n));
@@ -603,6 +702,7 @@ static inline int build_map(const Params& P, MemMap& mp) {
   mp.small_floats = smax + ((tail + 3) & ~3) + 4;
   mp.small = take(mp.small_floats);
   mp.total = off;
+  for (int l = 0; l < P.layers; ++l) mp.state_floats += mp.state_len[l];
   return off;
 }
 
@@ -697,10 +797,21 @@ extern "C" int64_t mlg_diffpool_grad_floats(int64_t layers, const int64_t* dims)
   return tot;
 }
 
+extern "C" int64_t mlg_diffpool_state_floats(int64_t layers, const int64_t* dims) {
+  if (!dims || layers < 1 || layers > dpf::kMaxLayers) return -1;
+  dpf::Params P;
+  memset(&P, 0, sizeof(P));
+  P.layers = (int)layers;
+  for (int l = 0; l < layers; ++l) P.d[l] = {(int)dims[4 * l], (int)dims[4 * l + 1], (int)dims[4 * l + 2], (int)dims[4 * l + 3]};
+  dpf::MemMap mp;
+  dpf::build_map(P, mp);
+  return mp.state_floats;
+}
+
 extern "C" int64_t mlg_diffpool_ctas(int64_t b) { return b < 148 ? (b < 1 ? 1 : b) : 148; }
 
 extern "C" int mlg_diffpool_fwd(const float* x, const float* adj, const float* const* weights, int64_t layers,
-                                const int64_t* dims, int64_t b, float* out, float* stats, void* stream) {
+                                const int64_t* dims, int64_t b, float* out, float* stats, float* state, void* stream) {
   MLG_CHECK_ARG(x && adj && weights && dims && out && stats && b >= 1, "mlg_diffpool_fwd: bad arguments");
   if (int rc = check_dims(layers, dims)) return rc;
   MLG_CHECK_ARG(mlg_diffpool_supported(layers, dims), "mlg_diffpool_fwd: %lld bytes of shared memory needed (limit %d)",
@@ -709,6 +820,8 @@ extern "C" int mlg_diffpool_fwd(const float* x, const float* adj, const float* c
   fill_params(P, layers, dims, weights, x, adj, b);
   P.out = out;
   P.stats = stats;
+  P.state = state;
+  MLG_CHECK_ARG(((uintptr_t)state & 15) == 0, "mlg_diffpool_fwd: state must be 16-byte aligned");
   dpf::MemMap mp;
   const size_t smem = (size_t)dpf::build_map(P, mp) * 4;
   MLG_CUDA(cudaFuncSetAttribute(diffpool_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -719,7 +832,7 @@ extern "C" int mlg_diffpool_fwd(const float* x, const float* adj, const float* c
 
 extern "C" int mlg_diffpool_bwd(const float* g_out, const float* coef, const float* x, const float* adj,
                                 const float* const* weights, int64_t layers, const int64_t* dims, int64_t b, float* g_x,
-                                float* g_weights, void* workspace, int64_t workspace_bytes, void* stream) {
+                                float* g_weights, const float* state, void* workspace, int64_t workspace_bytes, void* stream) {
   MLG_CHECK_ARG(g_out && coef && x && adj && weights && dims && g_x && g_weights && workspace && b >= 1, "mlg_diffpool_bwd: bad arguments");
   if (int rc = check_dims(layers, dims)) return rc;
   MLG_CHECK_ARG(mlg_diffpool_supported(layers, dims), "mlg_diffpool_bwd: shared-memory limit exceeded");
@@ -731,6 +844,8 @@ extern "C" int mlg_diffpool_bwd(const float* g_out, const float* coef, const flo
   P.coef = coef;
   P.g_x = g_x;
   P.partial = (float*)workspace;
+  P.state = const_cast<float*>(state);
+  MLG_CHECK_ARG(((uintptr_t)state & 15) == 0, "mlg_diffpool_bwd: state must be 16-byte aligned");
   dpf::MemMap mp;
   const size_t smem = (size_t)dpf::build_map(P, mp) * 4;
   cudaStream_t st = (cudaStream_t)stream;

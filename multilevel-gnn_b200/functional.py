@@ -1288,10 +1288,16 @@ class DiffPoolFused(torch.autograd.Function):
         nl = len(dims)
         out = torch.empty(b, dims[-1][2], dims[-1][3], dtype=torch.float32, device=xd.device)
         stats = torch.empty(b, nl, 2, dtype=torch.float32, device=xd.device)
+        # forward state for backward (S, Z, pooled X / A, row norms: ~90 KB per sample at the reference size) -- only when a
+        # backward pass can follow; without it the backward kernel recomputes the forward pass
+        state = None
+        if any(ctx.needs_input_grad):
+            state = torch.empty(b * int(L.mlg_diffpool_state_floats(nl, darr)), dtype=torch.float32, device=xd.device)
         flops = 2.0 * b * sum(n * n * c + 2 * n * c * (k + h) + n * k * h + 2 * n * n * k + n * k * k for n, c, k, h in dims)
         with torch.cuda.device(xd.device), _cabi.span("diffpool_fwd", flops):
             _cabi.check(L.mlg_diffpool_fwd(_cabi.fptr(xd), _cabi.fptr(ad), warr, nl, darr, b, _cabi.fptr(out),
-                                           _cabi.fptr(stats), _cabi.stream_ptr()), "mlg_diffpool_fwd")
+                                           _cabi.fptr(stats), _cabi.fptr(state) if state is not None else None,
+                                           _cabi.stream_ptr()), "mlg_diffpool_fwd")
         # link_l = ||adj_l - S S^T||_F / numel(adj_l) over the whole batch (adj_0 is the shared [n, n] matrix, deeper
         # adjacencies are batched [b, k, k]); entropy_l = mean over (sample, node)
         tot = stats.sum(0)                                              # [layers, 2]
@@ -1302,6 +1308,7 @@ class DiffPoolFused(torch.autograd.Function):
         ent = (tot[:, 1] / rows).sum()
         ctx.save_for_backward(xd, ad, fro, numel, rows, *ws)
         ctx.dims = dims
+        ctx.state = state
         ctx.n_weights = len(weights)
         ctx.set_materialize_grads(False)
         return out, link, ent
@@ -1331,8 +1338,9 @@ class DiffPoolFused(torch.autograd.Function):
         flops = 6.0 * b * sum(n * n * c + 2 * n * c * (k + h) + n * k * h + 2 * n * n * k + n * k * k for n, c, k, h in dims)
         with torch.cuda.device(dev), _cabi.span("diffpool_bwd", flops):
             _cabi.check(L.mlg_diffpool_bwd(_cabi.fptr(g_out), _cabi.fptr(coef), _cabi.fptr(xd), _cabi.fptr(ad), warr, nl, darr,
-                                           b, _cabi.fptr(gx), _cabi.fptr(gw), _cabi.fptr(wsp), wsp.numel() * 4,
-                                           _cabi.stream_ptr()), "mlg_diffpool_bwd")
+                                           b, _cabi.fptr(gx), _cabi.fptr(gw),
+                                           _cabi.fptr(ctx.state) if ctx.state is not None else None, _cabi.fptr(wsp),
+                                           wsp.numel() * 4, _cabi.stream_ptr()), "mlg_diffpool_bwd")
         grads, off = [], 0
         for w in ws:
             grads.append(gw[off:off + w.numel()].view_as(w))

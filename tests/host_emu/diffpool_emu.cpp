@@ -27,10 +27,16 @@ extern "C" long emu_diffpool_smem_floats(int layers, const int64_t* dims) {
   dpf::MemMap mp; return dpf::build_map(P, mp);
 }
 
+extern "C" long emu_diffpool_state_floats(int layers, const int64_t* dims) {
+  dpf::Params P; memset(&P, 0, sizeof(P)); P.layers = layers;
+  for (int l = 0; l < layers; ++l) P.d[l] = {(int)dims[4 * l], (int)dims[4 * l + 1], (int)dims[4 * l + 2], (int)dims[4 * l + 3]};
+  dpf::MemMap mp; dpf::build_map(P, mp); return mp.state_floats;
+}
+
 extern "C" int emu_diffpool_fwd(const float* x, const float* adj, const float* const* weights, int layers, const int64_t* dims,
-                                int b, float* out, float* stats) {
+                                int b, float* out, float* stats, float* state) {
   dpf::Params P; fill(P, layers, dims, weights, x, adj, b);
-  P.out = out; P.stats = stats;
+  P.out = out; P.stats = stats; P.state = state;
   dpf::MemMap mp; const int nfl = dpf::build_map(P, mp);
   float* sm = (float*)calloc(nfl, 4);
   dpf::forward_body(P, sm, mp, 0, 1);
@@ -39,9 +45,10 @@ extern "C" int emu_diffpool_fwd(const float* x, const float* adj, const float* c
 }
 
 extern "C" int emu_diffpool_bwd(const float* g_out, const float* coef, const float* x, const float* adj, const float* const* weights,
-                                int layers, const int64_t* dims, int b, float* g_x, float* g_weights) {
+                                int layers, const int64_t* dims, int b, float* g_x, float* g_weights, float* state) {
   dpf::Params P; const int n = fill(P, layers, dims, weights, x, adj, b);
   P.g_out = g_out; P.coef = coef; P.g_x = g_x; P.partial = g_weights;   // one "CTA": its partial IS the result
+  P.state = state;
   dpf::MemMap mp; const int nfl = dpf::build_map(P, mp);
   float* sm = (float*)calloc(nfl, 4);
   dpf::backward_body(P, sm, mp, 0, 1);

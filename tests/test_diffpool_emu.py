@@ -34,6 +34,7 @@ def emu(tmp_path_factory):
     subprocess.run(["g++", "-O2", "-shared", "-fPIC", "-x", "c++", "-o", so, src], check=True)
     lib = ctypes.CDLL(so)
     lib.emu_diffpool_smem_floats.restype = ctypes.c_long
+    lib.emu_diffpool_state_floats.restype = ctypes.c_long
     return lib
 
 
@@ -41,7 +42,9 @@ def _ptr(t):
     return ctypes.c_void_p(t.data_ptr())
 
 
-def run_emu(lib, sd, x, adj, dims, g_out=None, coef=None):
+def run_emu(lib, sd, x, adj, dims, g_out=None, coef=None, state=None):
+    """Forward: (out, stats, state) -- ``state`` is what the forward kernel stores for backward.  Backward (g_out given):
+    with ``state`` the stored forward is read back, without it the forward pass is recomputed; both must agree."""
     layers = len(dims)
     names = weight_names(layers)
     ws = [sd[k].detach().float().contiguous() for k in names]
@@ -53,13 +56,15 @@ def run_emu(lib, sd, x, adj, dims, g_out=None, coef=None):
     if g_out is None:
         out = torch.zeros(b, dims[-1][2], dims[-1][3])
         stats = torch.zeros(b, 2 * layers)
-        lib.emu_diffpool_fwd(_ptr(x), _ptr(adj), warr, layers, darr, b, _ptr(out), _ptr(stats))
-        return out, stats
+        st = torch.zeros(b * lib.emu_diffpool_state_floats(layers, darr))
+        lib.emu_diffpool_fwd(_ptr(x), _ptr(adj), warr, layers, darr, b, _ptr(out), _ptr(stats), _ptr(st))
+        return out, stats, st
     gx = torch.zeros_like(x)
     nfl = sum(w.numel() for w in ws)
     gw = torch.zeros(nfl)
     g_out, coef = g_out.float().contiguous(), coef.float().contiguous()
-    n = lib.emu_diffpool_bwd(_ptr(g_out), _ptr(coef), _ptr(x), _ptr(adj), warr, layers, darr, b, _ptr(gx), _ptr(gw))
+    n = lib.emu_diffpool_bwd(_ptr(g_out), _ptr(coef), _ptr(x), _ptr(adj), warr, layers, darr, b, _ptr(gx), _ptr(gw),
+                             _ptr(state) if state is not None else None)
     assert n == nfl
     grads, off = {}, 0
     for k, w in zip(names, ws):
@@ -92,7 +97,7 @@ def test_fused_diffpool_algebra_matches_reference_golden(emu, name):
     dims = dims_of(c)
     b = c["x"].shape[0]
     assert emu.emu_diffpool_smem_floats(2, (ctypes.c_int64 * 8)(*[v for d in dims for v in d])) * 4 <= 227 * 1024
-    out, stats = run_emu(emu, c["state_dict"], c["x"], c["adj"], dims)
+    out, stats, state = run_emu(emu, c["state_dict"], c["x"], c["adj"], dims)
     l, e = losses_from_stats(stats, dims, b)
     assert_close(out, c["out"], what=name + ".out")
     assert_close(l, c["link"], what=name + ".link")
@@ -102,10 +107,11 @@ def test_fused_diffpool_algebra_matches_reference_golden(emu, name):
     for i, d in enumerate(dims):
         numel = d[0] * d[0] * (1 if i == 0 else b)
         coef += [3.0 / (float(stats[:, 2 * i].sum().sqrt()) * numel), 0.5 / (b * d[0])]
-    gx, grads = run_emu(emu, c["state_dict"], c["x"], c["adj"], dims, g_out=c["R"], coef=torch.tensor(coef))
-    assert_close(gx, c["g_x"], rtol=2e-4, what=name + ".g_x")
-    for k, g in grads.items():
-        assert_close(g, c["g_params"][k], rtol=2e-4, what=name + ".g_" + k)
+    for st in (state, None):   # stored forward state / recomputed forward
+        gx, grads = run_emu(emu, c["state_dict"], c["x"], c["adj"], dims, g_out=c["R"], coef=torch.tensor(coef), state=st)
+        assert_close(gx, c["g_x"], rtol=2e-4, what=name + ".g_x")
+        for k, g in grads.items():
+            assert_close(g, c["g_params"][k], rtol=2e-4, what=name + ".g_" + k)
 
 
 def test_fused_diffpool_algebra_single_layer_vs_oracle(emu):
@@ -121,7 +127,7 @@ def test_fused_diffpool_algebra_single_layer_vs_oracle(emu):
     xr = x.clone().requires_grad_()
     out_r, l_r, e_r = R.diffpool_forward(sd, xr, adj, num_layers=1)
     dims = [(n, c, k, h)]
-    out, stats = run_emu(emu, sd, x, adj, dims)
+    out, stats, state = run_emu(emu, sd, x, adj, dims)
     l, e = losses_from_stats(stats, dims, b)
     assert_close(out, out_r, what="out")
     assert_close(l, l_r, what="link")
@@ -130,7 +136,8 @@ def test_fused_diffpool_algebra_single_layer_vs_oracle(emu):
     names = weight_names(1)
     gr = torch.autograd.grad((out_r * Rw).sum() + 2.0 * l_r + 0.7 * e_r, [xr] + [sd[kk] for kk in names])
     coef = torch.tensor([2.0 / (float(stats[:, 0].sum().sqrt()) * n * n), 0.7 / (b * n)])
-    gx, grads = run_emu(emu, sd, x, adj, dims, g_out=Rw, coef=coef)
-    assert_close(gx, gr[0], rtol=2e-4, what="g_x")
-    for kk, gg in zip(names, gr[1:]):
-        assert_close(grads[kk], gg, rtol=2e-4, what="g_" + kk)
+    for st in (state, None):
+        gx, grads = run_emu(emu, sd, x, adj, dims, g_out=Rw, coef=coef, state=st)
+        assert_close(gx, gr[0], rtol=2e-4, what="g_x")
+        for kk, gg in zip(names, gr[1:]):
+            assert_close(grads[kk], gg, rtol=2e-4, what="g_" + kk)
