@@ -353,6 +353,23 @@ int mlg_diffpool_bwd(const float* g_out, const float* coef, const float* x, cons
                      int64_t layers, const int64_t* dims, int64_t b, float* g_x, float* g_weights, const float* state,
                      void* workspace, int64_t workspace_bytes, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Per-pathway decoders of the VAE, grouped (models/vae.py:54-74 builds one Linear(F, D_i)-ReLU-Linear(D_i, n_i) block per
+ * pathway, foreach_decoder :216-222 runs them on h[:, i, :] and concatenates): one CTA per pathway, one launch per row chunk.
+ *   x [B, S, F]; packed: all blocks' parameters in one DEVICE buffer; table: DEVICE int64 [S, 8], per pathway the float offsets
+ *   into `packed` of (W1 [D,F], b1 [D], W2 [n,D], b2 [n]) and (D, n, first output column, first hidden column);
+ *   Dmax = max_i D_i; out [B, total_out] (total_out = sum n_i); h_saved [B, total_hidden] (sum D_i) = post-ReLU activations,
+ *   written by forward when non-NULL and required by backward.
+ * Backward: g_out [B, total_out] -> g_x [B, S, F] (NULL: not needed) and g_packed (same layout as packed; only the
+ *   parameter elements are written, one writer each -- gaps between arrays are left untouched).
+ * mlg_decoder_max_rows: batch rows one launch holds in shared memory; larger B is processed in chunks internally. */
+int64_t mlg_decoder_max_rows(int64_t F, int64_t Dmax, int backward);
+int mlg_decoder_fwd(const float* x, const float* packed, const int64_t* table, int64_t B, int64_t S, int64_t F,
+                    int64_t Dmax, int64_t total_out, int64_t total_hidden, float* out, float* h_saved, void* stream);
+int mlg_decoder_bwd(const float* g_out, const float* x, const float* h_saved, const float* packed, const int64_t* table,
+                    int64_t B, int64_t S, int64_t F, int64_t Dmax, int64_t total_out, int64_t total_hidden, float* g_x,
+                    float* g_packed, void* stream);
+
 /* z[r,c] = LeakyReLU_slope(z[r,c] + bias[c]) in place (bias NULL ok; slope 0 = ReLU): the bias + activation
  * of SAGEConv.update's MLP (torch_vertex.py:288-291) after the update GEMM. */
 int mlg_bias_act(float* z, const float* bias, int64_t rows, int64_t C, float slope, void* stream);

@@ -1272,6 +1272,19 @@ class DiffPoolFused(torch.autograd.Function):
         darr = (ctypes.c_int64 * (4 * len(dims)))(*[int(v) for d in dims for v in d])
         return ws, warr, darr
 
+    _NORMS = {}
+
+    @staticmethod
+    def _norms(dims, b, device):
+        """(numel(adj_l), b * n_l) per layer as device tensors, uploaded once per (dims, b, device)."""
+        key = (tuple(tuple(d) for d in dims), b, str(device))
+        got = DiffPoolFused._NORMS.get(key)
+        if got is None:
+            got = (torch.tensor([float(d[0] * d[0] * (1 if i == 0 else b)) for i, d in enumerate(dims)], device=device),
+                   torch.tensor([float(b * d[0]) for d in dims], device=device))
+            DiffPoolFused._NORMS[key] = got
+        return got
+
     @staticmethod
     def supported(dims):
         import ctypes
@@ -1301,8 +1314,7 @@ class DiffPoolFused(torch.autograd.Function):
         # link_l = ||adj_l - S S^T||_F / numel(adj_l) over the whole batch (adj_0 is the shared [n, n] matrix, deeper
         # adjacencies are batched [b, k, k]); entropy_l = mean over (sample, node)
         tot = stats.sum(0)                                              # [layers, 2]
-        numel = torch.tensor([float(d[0] * d[0] * (1 if i == 0 else b)) for i, d in enumerate(dims)], device=xd.device)
-        rows = torch.tensor([float(b * d[0]) for d in dims], device=xd.device)
+        numel, rows = DiffPoolFused._norms(dims, b, xd.device)
         fro = tot[:, 0].sqrt()
         link = (fro / numel).sum()
         ent = (tot[:, 1] / rows).sum()
@@ -1346,3 +1358,48 @@ class DiffPoolFused(torch.autograd.Function):
             grads.append(gw[off:off + w.numel()].view_as(w))
             off += w.numel()
         return (gx, None, None) + tuple(grads)
+
+
+class DecoderGrouped(torch.autograd.Function):
+    """All per-pathway decoder blocks Linear-ReLU-Linear of VAE.foreach_decoder (models/vae.py:54-74,216-222) in one launch
+    per direction (mlg_decoder_fwd / _bwd, csrc/decoder_grouped.cu).  x [B, S, F], packed: every block's parameters (layout:
+    models/decoder.py), table [S, 8] int64 on the device -> pred [B, total_out]."""
+
+    @staticmethod
+    def forward(ctx, x, packed, table, d_max, total_out, total_hidden):
+        L = _cabi.lib()
+        _cabi.require_cuda(x, packed, table)
+        xd, pd = _f32c(x.detach()), _f32c(packed.detach())
+        B, S, F = xd.shape
+        out = torch.empty(B, total_out, dtype=torch.float32, device=xd.device)
+        need = any(ctx.needs_input_grad)
+        h = torch.empty(B, total_hidden, dtype=torch.float32, device=xd.device) if need else None
+        flops = 2.0 * B * (F * total_hidden + pd.numel())
+        with torch.cuda.device(xd.device), _cabi.span("decoder_fwd", flops):
+            _cabi.check(L.mlg_decoder_fwd(_cabi.fptr(xd), _cabi.fptr(pd), _cabi.lptr(table), B, S, F, d_max, total_out,
+                                          total_hidden, _cabi.fptr(out), _cabi.fptr(h, allow_none=True),
+                                          _cabi.stream_ptr()), "mlg_decoder_fwd")
+        if need:
+            ctx.save_for_backward(xd, pd, table, h)
+            ctx.meta = (d_max, total_out, total_hidden)
+            ctx.packed_param = packed
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        L = _cabi.lib()
+        xd, pd, table, h = ctx.saved_tensors
+        d_max, total_out, total_hidden = ctx.meta
+        B, S, F = xd.shape
+        g = _f32c(g_out)
+        gx = torch.empty_like(xd) if ctx.needs_input_grad[0] else None
+        # every element of a block's arrays has exactly one writer; the alignment gaps between the arrays stay zero
+        gp = grad_slot(ctx.packed_param, pd.shape)
+        if gp is None:
+            gp = torch.zeros_like(pd)
+        flops = 4.0 * B * (F * total_hidden + pd.numel())
+        with torch.cuda.device(xd.device), _cabi.span("decoder_bwd", flops):
+            _cabi.check(L.mlg_decoder_bwd(_cabi.fptr(g), _cabi.fptr(xd), _cabi.fptr(h), _cabi.fptr(pd), _cabi.lptr(table), B, S,
+                                          F, d_max, total_out, total_hidden, _cabi.fptr(gx, allow_none=True), _cabi.fptr(gp),
+                                          _cabi.stream_ptr()), "mlg_decoder_bwd")
+        return gx, gp, None, None, None, None

@@ -2,6 +2,8 @@
 from .multilevel_gnn import MultilevelGNN
 from .deepergcn import DeeperGCN
 from .diff_pooling import DiffPool, DiffPoolLayer, SAGEConvolutions, DenseSAGEConv, dense_diff_pool
+from . import decoder
+from .decoder import GroupedDecoder
 from .vae import VAE
 
 MODELS = {'deepergcn': DeeperGCN, 'multilevel_gnn': MultilevelGNN, 'vae': VAE}

@@ -8,8 +8,8 @@ Same constructor (``args``, ``pca_params``, ``pathway_indexs``), same state_dict
 
 What runs where: the gene-level GNN stack and the gene -> pathway pool are MultilevelGNN's kernels (``pool_genes``);
 ``predict_head`` feeds DiffPool (fused small-graph kernel at the reference's 146-pathway size, tensor-core GEMMs at
-GEMM sizes) and the fused Linear/softmax head kernel; the per-pathway decoders ("unpool", vae.py:54-74,216-222) are still
-per-pathway library Linears (a grouped kernel is the next step there).
+GEMM sizes) and the fused Linear/softmax head kernel; the per-pathway decoders ("unpool", vae.py:54-74,216-222; SURVEY
+section 8 row f4) are one grouped kernel per direction over a packed parameter (models/decoder.py).
 """
 import math
 
@@ -17,6 +17,7 @@ import torch
 import torch.nn as nn
 
 from .. import functional as Fn
+from .decoder import GroupedDecoder
 from .diff_pooling import DiffPool
 from .multilevel_gnn import MultilevelGNN
 
@@ -39,11 +40,10 @@ class VAE(MultilevelGNN):
                                           nn.Linear(self.decoder_dim, self.node_num * 3)])
         elif self.decoder_type in ("foreach", "foreach_diffhidden"):
             counts = torch.bincount(pathway_indexs.reshape(-1).long(), minlength=int(pathway_indexs.max()) + 1).tolist()
-            blocks = []
-            for n_out in counts:
-                hid = self.decoder_dim if self.decoder_type == "foreach" else next_pow2(int(math.sqrt(n_out * args.final_channels)))
-                blocks.append(nn.Sequential(nn.Linear(feat, hid), nn.ReLU(), nn.Linear(hid, n_out)))
-            self.decoder = nn.ModuleList(blocks)
+            hidden = [self.decoder_dim if self.decoder_type == "foreach" else next_pow2(int(math.sqrt(n_out * args.final_channels)))
+                      for n_out in counts]
+            # one packed parameter + one kernel per direction for all blocks; state_dict keys stay decoder.{i}.{0,2}.*
+            self.decoder = GroupedDecoder(feat, hidden, counts)
         if args.reorder_type == "diff_pooling":
             cin = {"pathway": args.final_channels, "head": args.conv_channel_list[-1]}.get(args.diff_pooling_location)
             if cin is not None:
@@ -81,8 +81,9 @@ class VAE(MultilevelGNN):
         return x
 
     def foreach_decoder(self, h):
-        """pred[:, genes of pathway i] = decoder[i](h[:, i, :]) for all pathways (vae.py:216-222), concatenated."""
-        return torch.cat([block(h[:, i, :]) for i, block in enumerate(self.decoder)], dim=-1)
+        """pred[:, genes of pathway i] = decoder[i](h[:, i, :]) for all pathways (vae.py:216-222), concatenated: one grouped
+        kernel (models/decoder.py)."""
+        return self.decoder(h)
 
     def forward(self, input_batch, x=None, gene_pca_match=None, raw_indice=None, age=None):
         q_z, h, loss, _ = self.encoder(input_batch)

@@ -54,12 +54,49 @@ def test_foreach_decoder_golden(mlg):
     h = c["h"].to(DEV).requires_grad_()
     dec = model.foreach_decoder(h)
     assert_close(dec, c["dec"], what="dec")
-    dn = list(c["g_dec"])
-    params = dict(model.named_parameters())
-    gd = torch.autograd.grad((dec * c["Rd"].to(DEV)).sum(), [h] + [params[k] for k in dn])
-    assert_close(gd[0], c["g_h"], rtol=2e-4, what="g_h")
-    for k, g in zip(dn, gd[1:]):
-        assert_close(g, c["g_dec"][k], rtol=2e-4, what="g_" + k)
+    # one packed parameter holds every block (models/decoder.py); its gradient is compared block by block with the
+    # reference's per-Linear gradients
+    assert [k for k, _ in model.named_parameters() if k.startswith("decoder.")] == ["decoder.packed"]
+    g_h, g_packed = torch.autograd.grad((dec * c["Rd"].to(DEV)).sum(), [h, model.decoder.packed])
+    assert_close(g_h, c["g_h"], rtol=2e-4, what="g_h")
+    seen = 0
+    for i in range(len(model.decoder)):
+        for key, view in zip(mlg.models.decoder.KEYS, model.decoder.block(i, g_packed)):
+            k = "decoder.%d.%s" % (i, key)
+            assert_close(view, c["g_dec"][k], rtol=2e-4, what="g_" + k)
+            seen += 1
+    assert seen == len(c["g_dec"])
+    # and the state_dict still carries the reference's keys
+    sd = model.state_dict()
+    for k in c["g_dec"]:
+        assert torch.equal(sd[k].cpu(), c["state_dict"][k]), k
+
+
+def test_grouped_decoder_row_chunks_and_full_size(mlg):
+    """The lgg-sized decoder stack (438 pathways, F = 96, D = 128, 15 405 output genes) with a batch larger than one launch
+    holds in shared memory (row chunks, accumulated parameter gradients) against the per-block library formulation in fp64."""
+    torch.manual_seed(3)
+    g = torch.Generator().manual_seed(4)
+    S, F, D = 438, 96, 128
+    outs = torch.randint(1, 70, (S,), generator=g).tolist()
+    dec = mlg.models.decoder.GroupedDecoder(F, [D] * S, outs).to(DEV)
+    B = int(mlg._cabi.lib().mlg_decoder_max_rows(F, D, 1)) + 37
+    x = torch.randn(B, S, F, generator=g).to(DEV).requires_grad_()
+    Rw = torch.randn(B, sum(outs), generator=g).to(DEV)
+    y = dec(x)
+    gx, gp = torch.autograd.grad((y * Rw).sum(), [x, dec.packed])
+    xr = x.detach().double().requires_grad_()
+    blocks = [[t.double().requires_grad_() for t in dec.block(i)] for i in range(S)]
+    yr = torch.cat([torch.relu(xr[:, i] @ w1.t() + b1) @ w2.t() + b2 for i, (w1, b1, w2, b2) in enumerate(blocks)], dim=1)
+    flat = [t for blk in blocks for t in blk]
+    gr = torch.autograd.grad((yr * Rw.double()).sum(), [xr] + flat)
+    assert_close(y, yr.float(), what="pred")
+    assert_close(gx, gr[0].float(), rtol=2e-4, what="g_x")
+    q = 1
+    for i in range(S):
+        for view in dec.block(i, gp):
+            assert_close(view, gr[q].float(), rtol=2e-4, what="g_block%d[%d]" % (i, q))
+            q += 1
 
 
 def test_vae_encoder_and_forward_shapes(mlg):
