@@ -10,7 +10,7 @@
 #include "common.cuh"
 #include "../../include/mlg_b200.h"
 #define MLG_DEV __device__ __forceinline__
-#define MLG_DEV_CALL __device__ __noinline__   /* big phase-level routines: one copy per kernel (compile time, code size) */
+#define MLG_DEV_CALL static __device__ __noinline__   /* big phase-level routines: one copy per kernel (compile time, code size) */
 #define MLG_PFOR(i, n) for (int i = threadIdx.x; i < (n); i += blockDim.x)
 #define MLG_SYNC() __syncthreads()
 #else
