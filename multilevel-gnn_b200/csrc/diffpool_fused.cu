@@ -82,7 +82,7 @@ struct MemMap {
 // DenseSAGEConv forward: U = ((A X) / deg) Wrel^T + X Wroot^T + b, then row-normalise.  Leaves M = A X / deg [n x c] (ld
 // P4(c)), the row norms r (clamped at eps) and Y = U / r [n x o] (ld P4(o)).  X: [n x c] (ldx; x_pad: shared memory),
 // A: [n x n] (lda), both A and the outputs in shared memory.
-MLG_DEV_CALL void sage_fwd(const float* X, int ldx, bool x_pad, const float* A, int lda, const float* deg, int n, int c, int o,
+MLG_DEV void sage_fwd(const float* X, int ldx, bool x_pad, const float* A, int lda, const float* deg, int n, int c, int o,
                       const SageW& W, float* M, float* Y, float* r, bool have_M) {
   const int cp = P4(c), op = P4(o);
   if (!have_M) {
@@ -268,7 +268,7 @@ MLG_DEV void bgrad(float* gb, const float* dU, int ldu, int o, int n) {
 // DenseSAGEConv backward given dU [n x o] (ld P4(o), shared memory; gradient at the pre-normalisation output).  Accumulates
 // the parameter gradients, adds dL/dX into dX [n x c] (ldd) and, when dA != nullptr, dL/dA (A is itself a function of
 // earlier layers).  T: [n x c] scratch (ld P4(c)).  M = A X / deg (from forward, ld P4(c)); rowsum(A) > 1 <=> deg > 1.
-MLG_DEV_CALL void sage_bwd(const float* dU, int o, const float* X, int ldx, bool x_pad, const float* A, int lda, const float* deg,
+MLG_DEV void sage_bwd(const float* dU, int o, const float* X, int ldx, bool x_pad, const float* A, int lda, const float* deg,
                       const float* M, int n, int c, const SageW& W, float* gWrel, float* gWroot, float* gb, float* T,
                       bool first_into_T, float* dX, int ldd, bool acc_dX, bool finish, float* dA) {
   const int cp = P4(c), op = P4(o);
