@@ -6,7 +6,7 @@ The directory name carries a hyphen (fixed by the project layout); import it thr
 compute entry point needs ``lib/libmlg_b200.so`` and CUDA tensors and raises otherwise.
 """
 from . import _cabi, configs, data, dense_ops, functional, graph, synth  # noqa: F401
-from .gcn_lib.sparse import (GENConv, GenMessagePassing, MsgNorm, GraphConv, SAGEConv, RSAGEConv,  # noqa: F401
+from .gcn_lib.sparse import (GENConv, PathwayConv, GenMessagePassing, MsgNorm, GraphConv, SAGEConv, RSAGEConv,  # noqa: F401
                              DynConv, DilatedKnnGraph, Dilated, knn_graph_matrix, knn_matrix,
                              pairwise_distance, MLP)
 from .gcn_lib.dense import DenseDilatedKnnGraph, DenseDilated, dense_knn_matrix  # noqa: F401

@@ -62,6 +62,18 @@ class GenMessagePassing(nn.Module):
                                      Fn.EPI_NONE, learn)
 
 
+class PathwayMessagePassing(GenMessagePassing):
+    """torch_message.py:88-165: the same aggregation arithmetic as GenMessagePassing under another name (used by
+    PathwayConv).  The reference's constructor cannot build the power modes (it calls ``super(GenMessagePassing, self)``
+    on a class that is not a GenMessagePassing, :111): mirrored as the same TypeError."""
+
+    def __init__(self, aggr='softmax', t=1.0, learn_t=False, p=1.0, learn_p=False, y=0.0, learn_y=False):
+        if aggr in _POWER:
+            raise TypeError("super(type, obj): obj must be an instance or subtype of type "
+                            "(PathwayMessagePassing with a power aggregation fails the same way in the reference)")
+        super().__init__(aggr=aggr, t=t, learn_t=learn_t, p=p, learn_p=learn_p, y=y, learn_y=learn_y)
+
+
 class MsgNorm(nn.Module):
     """msg / max(||msg||_2, 1e-12) * ||x||_2 * msg_scale (torch_message.py:175-179).
 

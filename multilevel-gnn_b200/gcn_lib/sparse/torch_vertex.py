@@ -9,7 +9,7 @@ from torch import nn
 from ... import functional as Fn
 from ... import graph
 from .torch_edge import DilatedKnnGraph
-from .torch_message import GenMessagePassing, MsgNorm
+from .torch_message import GenMessagePassing, MsgNorm, PathwayMessagePassing
 from .torch_nn import MLP
 
 
@@ -76,6 +76,64 @@ class GENConv(GenMessagePassing):
     def message(self, x_j, edge_attr=None):
         msg = x_j + edge_attr if edge_attr is not None else x_j
         return self.msg_encoder(msg) + self.eps
+
+    def update(self, aggr_out):
+        return aggr_out
+
+
+class PathwayConv(PathwayMessagePassing):
+    """torch_vertex.py:107-178 (the 'multiomix' model's pathway-level convolution): the message of edge j -> i is
+    msg_encoder(flatten(x_j outer e_ji)) with msg_encoder = Linear(2 * in_dim, in_dim) (so e has 2 features), aggregated
+    by PathwayMessagePassing; out = relu(mlp(x + m)) (* mask).
+
+    The message is linear in x_j for a fixed edge: msg = sum_f e[f] * (W_f x_j) + b with W_f = weight[:, f::F_e].  So the
+    node features are transformed ONCE per node (one [N, in] x [in, F_e * in] GEMM instead of a [E, 2 in] x [2 in, in] GEMM
+    on the materialised outer products -- E / N times fewer flops and no [E, in * F_e] tensor), the per-edge combination is
+    a gather + F_e scaled adds, and the aggregation runs in the segment-softmax kernel on explicit messages
+    (GenMessagePassing.aggregate)."""
+
+    def __init__(self, in_dim, emb_dim, aggr='softmax', t=1.0, learn_t=False, p=1.0, learn_p=False, y=0.0, learn_y=False,
+                 msg_norm=False, learn_msg_scale=True, encode_edge=False, bond_encoder=False, edge_feat_dim=None,
+                 norm='batch', mlp_layers=2, eps=1e-7):
+        super().__init__(aggr=aggr, t=t, learn_t=learn_t, p=p, learn_p=learn_p, y=y, learn_y=learn_y)
+        self.mlp = MLP(channels=[in_dim] + [in_dim * 2] * (mlp_layers - 1) + [emb_dim], norm=norm, last_lin=True)
+        self.msg_encoder = nn.Linear(2 * in_dim, in_dim)
+        self.in_dim = in_dim
+        self.eps = eps
+        self.encode_edge = encode_edge
+        self.bond_encoder = bond_encoder
+        self.msg_norm = MsgNorm(learn_msg_scale=learn_msg_scale) if msg_norm else None    # built but never applied (:155-165)
+        if encode_edge:
+            if bond_encoder:
+                raise NotImplementedError("BondEncoder (OGB molecule leftovers) is out of scope, SURVEY.md section 2 row 4")
+            self.edge_encoder = nn.Linear(edge_feat_dim, in_dim)                          # likewise unused by forward
+
+    def message(self, x_j, edge_attr=None):
+        """Reference formulation on gathered rows (kept for callers that use it directly)."""
+        msg = torch.matmul(x_j[:, :, None], edge_attr[:, None, :]).flatten(1) if edge_attr is not None else x_j
+        return self.msg_encoder(msg)
+
+    def _messages(self, x, edge_index, edge_attr):
+        src = edge_index[0]
+        if edge_attr is None:
+            return self.msg_encoder(x.index_select(0, src))      # shape error for in_dim != 2 * in_dim, as in the reference
+        fe = edge_attr.shape[1]
+        if fe * self.in_dim != self.msg_encoder.in_features:
+            raise RuntimeError("mat1 and mat2 shapes cannot be multiplied (%dx%d and %dx%d)" % (
+                edge_attr.shape[0], fe * self.in_dim, self.msg_encoder.in_features, self.in_dim))
+        # W[o, c * fe + f] -> Wcat[f * in + o, c]: y[:, f * in + o] = (W_f x)[o]
+        wcat = self.msg_encoder.weight.view(self.in_dim, self.in_dim, fe).permute(2, 0, 1).reshape(fe * self.in_dim, self.in_dim)
+        if x.is_cuda and x.dim() == 2 and x.shape[0] >= Fn.TallLinear.MIN_ROWS and x.dtype == torch.float32:
+            y = Fn.TallLinear.apply(x, wcat.contiguous(), None, False)      # 3xTF32 tensor-core GEMM + mlg_xty weight gradient
+        else:
+            y = F.linear(x, wcat)
+        yj = y.index_select(0, src).view(-1, fe, self.in_dim)
+        return (yj * edge_attr.unsqueeze(-1)).sum(1) + self.msg_encoder.bias
+
+    def forward(self, x, edge_index, edge_attr=None, mask=None):
+        m = self.aggregate(self._messages(x, edge_index, edge_attr), edge_index[1], dim_size=x.shape[0])
+        out = F.relu(self.mlp(x + m))
+        return out * mask if mask is not None else out
 
     def update(self, aggr_out):
         return aggr_out

@@ -87,6 +87,38 @@ def make_genconv(ns):
     torch.save(out, os.path.join(OUT, "genconv.pt"))
 
 
+PATHWAY_CASES = [
+    ("softmax_learn_t", dict(aggr="softmax", t=0.8, learn_t=True, norm="layer"), 32, True),
+    ("softmax_sum_mask", dict(aggr="softmax_sum", t=1.0, learn_t=True, y=0.2, learn_y=True, norm="batch"), 24, True),
+    ("mean", dict(aggr="mean", norm="layer", mlp_layers=1), 20, False),
+    ("max", dict(aggr="max", norm="layer"), 16, False),
+]
+
+
+def make_pathwayconv(ns):
+    """PathwayConv (torch_vertex.py:107-178) from the reference's own class: outer-product message through msg_encoder,
+    PathwayMessagePassing aggregation, residual, MLP, ReLU, optional mask."""
+    out = {}
+    for i, (name, kw, H, use_mask) in enumerate(PATHWAY_CASES):
+        g = gen(700 + i)
+        torch.manual_seed(700 + i)
+        n, e = 41, 230
+        conv = ns.torch_vertex.PathwayConv(H, H, **kw)
+        conv.train()
+        x = torch.randn(n, H, generator=g).requires_grad_()
+        ea = torch.randn(e, 2, generator=g).requires_grad_()
+        ei = random_graph(n, e, g)
+        mask = (torch.rand(n, 1, generator=g) > 0.3).float() if use_mask else None
+        R = torch.randn(n, H, generator=g)
+        y = conv(x, ei, ea, mask)
+        names = [k for k, p in conv.named_parameters() if p.requires_grad]
+        gs = grads_of((y * R).sum(), [x, ea] + [p for p in conv.parameters() if p.requires_grad])
+        out[name] = dict(kw=kw, H=H, x=x.detach(), edge_attr=ea.detach(), edge_index=ei, mask=mask, R=R,
+                         state_dict={k: v.detach().clone() for k, v in conv.state_dict().items()},
+                         y=y.detach(), g_x=gs[0], g_edge_attr=gs[1], g_params={k: v for k, v in zip(names, gs[2:])})
+    torch.save(out, os.path.join(OUT, "pathwayconv.pt"))
+
+
 def make_sage(ns):
     out = {}
     for i, (conv_name, cin, cout) in enumerate([("sage", 64, 64), ("sage", 64, 32), ("rsage", 32, 32), ("sage", 10, 6)]):
@@ -308,7 +340,7 @@ def main():
     os.makedirs(OUT, exist_ok=True)
     ns = ref_import.load()
     only = set(sys.argv[1:])
-    for fn in (make_genconv, make_sage, make_knn, make_multilevel, make_diffpool, make_deepergcn, make_vae):
+    for fn in (make_genconv, make_pathwayconv, make_sage, make_knn, make_multilevel, make_diffpool, make_deepergcn, make_vae):
         if only and fn.__name__ not in only:
             continue
         fn(ns)

@@ -158,6 +158,26 @@ def genconv_forward(sd, x, edge_index, edge_attr, aggr="softmax", t=1.0, learn_t
     return out
 
 
+def pathway_conv_forward(sd, x, edge_index, edge_attr=None, mask=None, aggr="softmax", t=1.0, learn_t=False, norm="batch"):
+    """PathwayConv.forward, models/gcn_lib/sparse/torch_vertex.py:155-178 over PathwayMessagePassing.aggregate
+    (torch_message.py:124-145, the same arithmetic as GenMessagePassing.aggregate):
+      message (:167-175): msg = msg_encoder(flatten(x_j outer edge_attr)) -- a Linear(2*in_dim, in_dim) on the
+      [E, in_dim * F_e] outer product, index c * F_e + f -- (no ReLU, no eps: the ``+ self.eps`` line is commented out);
+      forward (:155-165): h = x + aggregate(msg); out = relu(mlp(h)); out * mask when a mask is given.
+    ``sd``: mlp.{0,1,3}.*, msg_encoder.*, t / y when learnable.  The power modes cannot be constructed in the reference
+    (PathwayMessagePassing.__init__ calls super(GenMessagePassing, self), torch_message.py:111: TypeError)."""
+    xj = x.index_select(0, edge_index[0])
+    if edge_attr is not None:
+        msg = torch.matmul(xj[:, :, None], edge_attr[:, None, :]).flatten(1)
+    else:
+        msg = xj
+    msg = F.linear(msg, sd["msg_encoder.weight"], sd["msg_encoder.bias"])
+    t_eff = sd["t"] if "t" in sd else t
+    m = gen_aggregate(msg, edge_index[1], x.shape[0], aggr=aggr, t=t_eff, learn_t=learn_t and "t" in sd, y=sd.get("y"))
+    out = F.relu(mlp_forward(sd, "mlp.", x + m, norm=norm, act="relu", last_lin=True))
+    return out * mask if mask is not None else out
+
+
 # ----------------------------------------------------------------------------
 # SAGE / RSAGE (the conv all three shipped configs use)
 # ----------------------------------------------------------------------------

@@ -64,6 +64,55 @@ def test_gen_aggregate_golden(mlg, name):
     assert_close(g, c["g_msg"], what=name + ".g_msg")
 
 
+PWC = load_golden("pathwayconv")
+
+
+@pytest.mark.parametrize("name", sorted(PWC))
+def test_pathwayconv_golden(mlg, name):
+    """PathwayConv (torch_vertex.py:107-178): transform-first message + the aggregation kernel on
+    explicit messages, against the reference's own class."""
+    c = PWC[name]
+    H = c["H"]
+    conv = _load(mlg.PathwayConv(H, H, **c["kw"]), c["state_dict"])
+    conv.train()
+    x = c["x"].to(DEV).requires_grad_()
+    ea = c["edge_attr"].to(DEV).requires_grad_()
+    mask = None if c["mask"] is None else c["mask"].to(DEV)
+    y = conv(x, c["edge_index"].to(DEV), ea, mask)
+    assert_close(y, c["y"], what=name + ".y")
+    names = [k for k, g in c["g_params"].items() if g is not None]
+    params = dict(conv.named_parameters())
+    gs = torch.autograd.grad((y * c["R"].to(DEV)).sum(), [x, ea] + [params[k] for k in names], allow_unused=True)
+    assert_close(gs[0], c["g_x"], rtol=2e-4, what=name + ".g_x")
+    assert_close(gs[1], c["g_edge_attr"], rtol=2e-4, what=name + ".g_edge_attr")
+    for k, g in zip(names, gs[2:]):
+        assert_close(g, c["g_params"][k], rtol=2e-4, what=name + ".g_" + k)
+
+
+def test_pathwayconv_tall_vs_oracle(mlg):
+    """PathwayConv with enough nodes for the tensor-core (3xTF32) transform-first GEMM: forward and input gradient against
+    the oracle's direct outer-product formulation."""
+    from conftest import assert_close_flips
+    n, e, H = 70000, 280000, 32
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(n, H, generator=g)
+    ea = torch.randn(e, 2, generator=g)
+    ei = torch.stack([torch.randint(0, n, (e,), generator=g), torch.randint(0, n, (e,), generator=g)])
+    torch.manual_seed(12)
+    conv = mlg.PathwayConv(H, H, aggr="softmax", t=0.9, learn_t=True, norm="layer")
+    sd = {k: v.detach().clone() for k, v in conv.state_dict().items()}
+    xr = x.clone().requires_grad_()
+    yr = R.pathway_conv_forward(sd, xr, ei, ea, aggr="softmax", learn_t=True, norm="layer")
+    Rw = torch.randn(n, H, generator=g)
+    gr = torch.autograd.grad((yr * Rw).sum(), xr)[0]
+    conv.to(DEV).train()
+    xg = x.to(DEV).requires_grad_()
+    y = conv(xg, ei.to(DEV), ea.to(DEV))
+    assert_close(y, yr, what="pathwayconv tall y")
+    gx = torch.autograd.grad((y * Rw.to(DEV)).sum(), xg)[0]
+    assert_close_flips(gx, gr, "pathwayconv tall g_x", rtol=2e-4, l2=1e-3, outliers=1e-3)
+
+
 # ------------------------------------------------------------------------------------------------
 # SAGE / RSAGE vs golden
 # ------------------------------------------------------------------------------------------------

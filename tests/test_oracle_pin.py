@@ -17,6 +17,29 @@ def _leafify(d):
 
 
 GEN = load_golden("genconv")
+PWC = load_golden("pathwayconv")
+
+
+@pytest.mark.parametrize("name", sorted(PWC))
+def test_pathwayconv_restatement(name):
+    """R.pathway_conv_forward against the reference's own PathwayConv (torch_vertex.py:107-178): output and all gradients."""
+    c = PWC[name]
+    kw = c["kw"]
+    sd = _leafify(c["state_dict"])
+    x, ea = c["x"].clone().requires_grad_(), c["edge_attr"].clone().requires_grad_()
+    y = R.pathway_conv_forward(sd, x, c["edge_index"], ea, mask=c["mask"], aggr=kw["aggr"], t=kw.get("t", 1.0),
+                               learn_t=kw.get("learn_t", False), norm=kw["norm"])
+    assert_close(y, c["y"], what=name + ".y")
+    names = list(c["g_params"])
+    gs = torch.autograd.grad((y * c["R"]).sum(), [x, ea] + [sd[k] for k in names], allow_unused=True)
+    assert_close(gs[0], c["g_x"], what=name + ".g_x")
+    assert_close(gs[1], c["g_edge_attr"], what=name + ".g_edge_attr")
+    for k, g in zip(names, gs[2:]):
+        if c["g_params"][k] is None:
+            assert g is None, k
+        else:
+            assert_close(g, c["g_params"][k], what=name + ".g_" + k)
+
 
 
 @pytest.mark.parametrize("name", sorted(GEN))
