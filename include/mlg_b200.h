@@ -427,8 +427,12 @@ int mlg_pool_bwd(const float* g_out_cl, const float* x, const float* vm, const f
  * fp32 distance d_ij = (|x_i|^2 + (-2 x_i.x_j)) + |x_j|^2, k*dilation nearest per point (self
  * included), ascending distance, ties by lowest index; every dilation-th rank is kept.
  * x [B, N, D]; out_nbr / out_ctr int64 [B*N*k] with per-graph node offsets (sparse layout, offset != 0)
- * or without (dense layout).  out_dist [B*N*k] optional (NULL ok).  workspace: >= B*N*4 bytes (squared norms).
+ * or without (dense layout).  out_dist [B*N*k] optional (NULL ok).
+ * workspace: mlg_knn_workspace_bytes(B, N, D, k, dilation) bytes.  With at least B*N*4 bytes (squared norms) the fp32
+ * kernel runs; with the full amount, graphs of >= 4096 points (k*dilation <= 16, D <= 128) search their candidates on
+ * the tensor cores (3xTF32) and re-evaluate / certify them in fp32 -- the output is identical to the fp32 kernel's.
  */
+int64_t mlg_knn_workspace_bytes(int64_t B, int64_t N, int64_t D, int64_t k, int64_t dilation);
 int mlg_knn_graph(const float* x, int64_t B, int64_t N, int64_t D, int64_t k, int64_t dilation,
                   int add_offset, int64_t* out_nbr, int64_t* out_ctr, float* out_dist, void* workspace,
                   int64_t workspace_bytes, void* stream);

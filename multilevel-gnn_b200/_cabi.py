@@ -132,6 +132,7 @@ _SIGNATURES = {
                                              _c_f32, _c_f32, _c_f32, ctypes.c_double, _c_vp, _c_vp]),
     "mlg_peer_status": (_c_int, [_c_vp, _c_vp]),
     "mlg_adam_step": (_c_int, [_c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_i64, _c_f32, _c_f32, _c_f32, _c_f32, _c_f32, _c_vp]),
+    "mlg_knn_workspace_bytes": (_c_i64, [_c_i64, _c_i64, _c_i64, _c_i64, _c_i64]),
     "mlg_knn_graph": (_c_int, [_c_vp, _c_i64, _c_i64, _c_i64, _c_i64, _c_i64, _c_int, _c_vp, _c_vp, _c_vp, _c_vp,
                                _c_i64, _c_vp]),
 }

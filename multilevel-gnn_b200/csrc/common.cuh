@@ -100,4 +100,8 @@ __device__ __forceinline__ void block_sum(float (&v)[NV], float* smem /* >= NV*3
     }
   }
 }
+
+// csrc/gemm_tf32x3.cu: one column chunk of the tensor-core kNN candidate search (internal, used by csrc/knn.cu)
+int mlg_tf32x3_knn_chunk(const float* A, const float* B_hi, const float* B_lo, const float* sq_cols, int64_t M, int64_t Nc,
+                         int64_t valid, int64_t K, int kc, float* list_d, int* list_i, int col0, void* stream);
 #endif

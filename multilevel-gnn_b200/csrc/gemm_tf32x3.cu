@@ -128,12 +128,58 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, unsigned sr
 #endif
 }
 
+// kNN candidate selection as the epilogue (csrc/knn.cu, tensor-core path): the N columns of this launch are candidate
+// points, bias = their squared norms (+inf past `valid`), and instead of storing C every accumulator row keeps the kc
+// smallest keys  |x_j|^2 - 2 x_i.x_j  (= distance minus the row constant |x_i|^2) seen so far, with their column ids, in a
+// per-row list that lives in global memory between launches and in shared memory (the output staging area) during one.
+constexpr int kKnnKC = 24;   // candidates kept per row (= csrc/knn.cu kTcCand)
+constexpr int kKnnLd = 28;   // shared-memory row stride of a list, words
+struct KnnEpi {
+  int kc;          // kKnnKC, or 0: plain GEMM epilogue
+  float* d;        // [M, kc] keys, unordered
+  int* i;          // [M, kc] column ids
+  int col0;        // id of this launch's first column
+  int valid;       // columns < valid exist
+};
+__device__ __forceinline__ float lds32(unsigned addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ int lds32i(unsigned addr) {
+  int v;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts32(unsigned addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory"); }
+__device__ __forceinline__ void sts32i(unsigned addr, int v) { asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
+
+// one admission: the key replaces the list's largest entry (slot pmax); the new largest and its slot come from one vector
+// scan (six 128-bit loads, a max tree, a match mask)
+// (returns (new threshold, bit pattern of the new slot) in registers: reference arguments of an out-of-line routine live
+// in local memory)
+__device__ __noinline__ float2 knn_admit(unsigned ld_u32, unsigned li_u32, float key, int id, int pmax) {
+  sts32(ld_u32 + (unsigned)pmax * 4u, key);
+  sts32i(li_u32 + (unsigned)pmax * 4u, id);
+  float4 v[kKnnKC / 4];
+#pragma unroll
+  for (int e = 0; e < kKnnKC / 4; ++e) v[e] = lds128(ld_u32 + (unsigned)e * 16u);
+  float m = -INFINITY;
+#pragma unroll
+  for (int e = 0; e < kKnnKC / 4; ++e) m = fmaxf(m, fmaxf(fmaxf(v[e].x, v[e].y), fmaxf(v[e].z, v[e].w)));
+  unsigned hit = 0;
+#pragma unroll
+  for (int e = 0; e < kKnnKC / 4; ++e)
+    hit |= ((v[e].x == m ? 1u : 0u) | (v[e].y == m ? 2u : 0u) | (v[e].z == m ? 4u : 0u) | (v[e].w == m ? 8u : 0u)) << (4 * e);
+  return make_float2(m, __int_as_float(__ffs(hit) - 1));
+}
+
 // shared memory: [B_hi: kb][N x 128 B] [B_lo: kb][...] [stages][A_hi 16 KB | A_lo 16 KB] [out staging 32 KB] Ctl
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_bh,
                    const __grid_constant__ CUtensorMap map_bl, const __grid_constant__ CUtensorMap map_c,
                    const float* __restrict__ bias, float* __restrict__ C, long long ldc, int M, int N, int K,
-                   int n_stages, int tmem_cols, int act, float slope, int tma_out, int skip_hi) {
+                   int n_stages, int tmem_cols, int act, float slope, int tma_out, int skip_hi, const KnnEpi knn) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* base = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   const int k_blocks = K / BKF;
@@ -221,10 +267,102 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     }
   } else if (warp >= 4 && warp < 8) {  // ===== epilogue =====
     const int q = warp & 3;
-    for (int i = threadIdx.x - 128; i < N; i += 128) S.bias_s[i] = bias ? __ldg(bias + i) : 0.f;
+    for (int i = threadIdx.x - 128; i < N; i += 128)
+      S.bias_s[i] = knn.kc ? (i < knn.valid ? __ldg(bias + i) : INFINITY) : (bias ? __ldg(bias + i) : 0.f);
     asm volatile("bar.sync 1, 128;" ::: "memory");
     int tl = 0;
-    if (tma_out) {
+    if (knn.kc) {
+      // thread = accumulator row.  List of row r: kKnnKC keys (UNORDERED; the largest one is the admission threshold and
+      // the slot the next admitted key replaces -- the refinement pass orders the survivors by their exact distances
+      // anyway) then kKnnKC ids; row stride kKnnLd words (16-byte aligned rows, conflict-free 128-bit loads).
+      // Cost model: a warp pays for every admission of any of its 32 rows, ~768 / m of them in the m-th column chunk, so
+      // the admission itself must be cheap: two stores, six 128-bit loads, a max tree and a match mask (~100 cycles; a
+      // sorted list with dependent shifts was ~800 cycles and made a 128 x 256 tile cost 29 us against 1.6 us of MMA).
+      const unsigned rl = (unsigned)(q * 32 + lane);
+      const unsigned ld_u32 = smem_u32(out_st) + rl * (unsigned)kKnnLd * 4u;
+      const unsigned li_u32 = ld_u32 + 128u * (unsigned)kKnnLd * 4u;
+      const unsigned bias_u32 = smem_u32(&S.bias_s[0]);
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tl) {
+        const int buf = tl & 1;
+        const long long row = (long long)tile * BM + rl;
+        const bool ok = row < M;
+        float thr = -INFINITY;   // rows past M never admit anything
+        int pmax = 0;
+        if (ok) {
+          const float4* gd = reinterpret_cast<const float4*>(knn.d + row * kKnnKC);
+          const int4* gi = reinterpret_cast<const int4*>(knn.i + row * kKnnKC);
+#pragma unroll
+          for (int e = 0; e < kKnnKC / 4; ++e) {
+            const float4 dv = gd[e];
+            const int4 iv = gi[e];
+            sts128(ld_u32 + (unsigned)e * 16u, dv);
+            sts128(li_u32 + (unsigned)e * 16u, make_float4(__int_as_float(iv.x), __int_as_float(iv.y), __int_as_float(iv.z),
+                                                           __int_as_float(iv.w)));
+            const float dd[4] = {dv.x, dv.y, dv.z, dv.w};
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+              if (dd[u] > thr) { thr = dd[u]; pmax = 4 * e + u; }
+          }
+        }
+        mbar_wait(&S.tmem_full[buf], (tl >> 1) & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        for (int c0 = 0; c0 < N; c0 += 32) {
+          unsigned r[32];
+          const unsigned taddr = tmem + ((unsigned)(q * 32) << 16) + (unsigned)(buf * N + c0);
+          asm volatile(
+              "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+              "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+              "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+              : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+              : "r"(taddr));
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          // all 32 keys and their admission mask first (independent instructions, ONE branch per 32 columns on the common
+          // path); admitted keys are then handled nibble by nibble through an out-of-line routine.  Testing and admitting
+          // column by column serialised FFMA -> FSETP -> BRA on the single epilogue warp of each scheduler and unrolled
+          // the admission code 32 times (53 KB of SASS, 39 % of the stalls were instruction fetch).
+          unsigned mask = 0;
+#pragma unroll
+          for (int j4 = 0; j4 < 8; ++j4) {
+            const float4 sv = lds128(bias_u32 + (unsigned)((c0 + j4 * 4) * 4));
+            const float k0 = fmaf(-2.f, __uint_as_float(r[4 * j4]), sv.x), k1 = fmaf(-2.f, __uint_as_float(r[4 * j4 + 1]), sv.y);
+            const float k2 = fmaf(-2.f, __uint_as_float(r[4 * j4 + 2]), sv.z), k3 = fmaf(-2.f, __uint_as_float(r[4 * j4 + 3]), sv.w);
+            r[4 * j4] = __float_as_uint(k0); r[4 * j4 + 1] = __float_as_uint(k1);
+            r[4 * j4 + 2] = __float_as_uint(k2); r[4 * j4 + 3] = __float_as_uint(k3);
+            mask |= ((k0 < thr ? 1u : 0u) | (k1 < thr ? 2u : 0u) | (k2 < thr ? 4u : 0u) | (k3 < thr ? 8u : 0u)) << (4 * j4);
+          }
+          if (mask) {
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4) {
+              if ((mask >> (4 * j4)) & 15u) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                  const float key = __uint_as_float(r[4 * j4 + u]);
+                  if (((mask >> (4 * j4 + u)) & 1u) && key < thr) {   // the threshold may have tightened since the mask
+                    const float2 t = knn_admit(ld_u32, li_u32, key, knn.col0 + c0 + j4 * 4 + u, pmax);
+                    thr = t.x;
+                    pmax = __float_as_int(t.y);
+                  }
+                }
+              }
+            }
+          }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        mbar_arrive(&S.tmem_empty[buf]);
+        if (ok) {
+          float4* gd = reinterpret_cast<float4*>(knn.d + row * kKnnKC);
+          float4* gi = reinterpret_cast<float4*>(knn.i + row * kKnnKC);
+#pragma unroll
+          for (int e = 0; e < kKnnKC / 4; ++e) {
+            gd[e] = lds128(ld_u32 + (unsigned)e * 16u);
+            gi[e] = lds128(li_u32 + (unsigned)e * 16u);
+          }
+        }
+      }
+    } else if (tma_out) {
       // accumulator rows (lane = row) -> bias/act -> this warp's private [32 rows x 32 cols] staging tile (128 B rows,
       // hand-applied 128 B swizzle: conflict-free STS.128) -> one TMA store per 32-column group.  Row-per-lane global
       // stores wrote 32 half-filled sectors per instruction and kept these warps 100 % busy (ncu r01).
@@ -393,6 +531,8 @@ int make_map_f32(CUtensorMap* map, const void* basep, long long K, long long row
   return MLG_OK;
 }
 
+int g_attr_smem = 0;
+
 }  // namespace
 
 extern "C" int mlg_split_tf32(const float* w, int64_t n, float* hi, float* lo, void* stream) {
@@ -443,18 +583,58 @@ extern "C" int mlg_gemm_tf32x3(const float* A, int64_t lda, const float* B_hi, c
   int tmem_cols = 32;
   while (tmem_cols < 2 * N) tmem_cols *= 2;
   const int smem = (int)(bbytes + (long long)stages * 2 * kTileBytes + kStageOutBytes + 2048 + 1024);
-  static int attr_smem = 0;
-  if (smem > attr_smem) {
+  if (smem > g_attr_smem) {   // one high-water mark for both launchers of this kernel
     MLG_CUDA(cudaFuncSetAttribute(gemm_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_smem = smem;
+    g_attr_smem = smem;
   }
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int n_tiles = (int)((M + BM - 1) / BM);
   const int grid = n_tiles < sms ? n_tiles : sms;
+  KnnEpi none;
+  memset(&none, 0, sizeof(none));
   gemm_tf32x3_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(ma, mbh, mbl, mc, bias, C, ldc, (int)M, (int)N,
-                                                                    (int)K, stages, tmem_cols, act, slope, tma_out, skip_hi);
+                                                                    (int)K, stages, tmem_cols, act, slope, tma_out, skip_hi,
+                                                                    none);
   MLG_CHECK_LAUNCH("mlg_gemm_tf32x3");
+  return MLG_OK;
+}
+
+// One column chunk of the tensor-core kNN candidate search (csrc/knn.cu): rows = the M points of a graph (A [M, K], K a
+// multiple of 32, zero padded), columns = `valid` <= Nc candidate points starting at id col0 (B_hi / B_lo [valid, K],
+// pre-split), sq_cols = their squared norms.  Updates the per-row candidate lists (see KnnEpi).
+int mlg_tf32x3_knn_chunk(const float* A, const float* B_hi, const float* B_lo, const float* sq_cols, int64_t M, int64_t Nc,
+                         int64_t valid, int64_t K, int kc, float* list_d, int* list_i, int col0, void* stream) {
+  MLG_CHECK_ARG(mlg_gemm_tf32x3_supported(M, Nc, K) && valid >= 1 && valid <= Nc && kc == kKnnKC && 128 * kKnnLd * 8 <= kStageOutBytes,
+                "mlg_tf32x3_knn_chunk: unsupported shape");
+  CUtensorMap ma, mbh, mbl;
+  int rc = make_map_f32(&ma, A, K, M, K, BM);
+  if (rc) return rc;
+  rc = make_map_f32(&mbh, B_hi, K, valid, K, (int)Nc);    // rows past `valid` are zero-filled by TMA
+  if (rc) return rc;
+  rc = make_map_f32(&mbl, B_lo, K, valid, K, (int)Nc);
+  if (rc) return rc;
+  const long long bbytes = 2ll * (K / 32) * Nc * 128;
+  int stages = (int)((224 * 1024 - kStageOutBytes - bbytes) / (2 * kTileBytes));
+  if (stages > 4) stages = 4;
+  static const int skip_hi = getenv("MLG_TF32_WRITE_HI") ? 0 : 1;
+  int tmem_cols = 32;
+  while (tmem_cols < 2 * Nc) tmem_cols *= 2;
+  const int smem = (int)(bbytes + (long long)stages * 2 * kTileBytes + kStageOutBytes + 2048 + 1024);
+  if (smem > g_attr_smem) {   // one high-water mark for both launchers of this kernel
+    MLG_CUDA(cudaFuncSetAttribute(gemm_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    g_attr_smem = smem;
+  }
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int n_tiles = (int)((M + BM - 1) / BM);
+  const int grid = n_tiles < sms ? n_tiles : sms;
+  KnnEpi e;
+  e.kc = kc; e.d = list_d; e.i = list_i; e.col0 = col0; e.valid = (int)valid;
+  gemm_tf32x3_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(ma, mbh, mbl, ma, sq_cols, nullptr, 0, (int)M, (int)Nc,
+                                                                    (int)K, stages, tmem_cols, 0, 0.f, 0, skip_hi, e);
+  MLG_CHECK_LAUNCH("mlg_tf32x3_knn_chunk");
   return MLG_OK;
 }

@@ -1,7 +1,8 @@
 """Dilated kNN graph construction, sparse layout (models/gcn_lib/sparse/torch_edge.py:6-104).
 
 The distance matrix is never materialised: ``mlg_knn_graph`` fuses the tiled fp32 distance with a
-per-row top-k and the dilation stride.  Tie contract: ascending distance, lowest index first inside
+per-row top-k and the dilation stride; graphs of >= 4096 points search their candidates on the tensor cores (3xTF32) and
+certify them in fp32 (csrc/knn.cu) -- same output.  Tie contract: ascending distance, lowest index first inside
 exact fp32 ties (``torch.topk`` leaves tie order unspecified)."""
 import torch
 from torch import nn
@@ -17,7 +18,7 @@ def _knn_call(xb, k, dilation, add_offset):
     B, N, D = xb.shape
     nbr = torch.empty(B * N * k, dtype=torch.int64, device=xb.device)
     ctr = torch.empty_like(nbr)
-    ws = torch.empty(B * N, dtype=torch.float32, device=xb.device)
+    ws = torch.empty((int(L.mlg_knn_workspace_bytes(B, N, D, k, dilation)) + 3) // 4, dtype=torch.float32, device=xb.device)
     with torch.cuda.device(xb.device):
         _cabi.check(L.mlg_knn_graph(_cabi.fptr(xb), B, N, D, k, dilation, int(add_offset), _cabi.lptr(nbr),
                                     _cabi.lptr(ctr), None, _cabi.fptr(ws), ws.numel() * 4, _cabi.stream_ptr()),

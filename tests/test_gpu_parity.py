@@ -900,6 +900,49 @@ def test_knn_ragged_sizes_and_full_k(mlg):
         mlg.knn_graph_matrix(torch.randn(5, 3, device=DEV), 6)          # k > N: torch.topk raises in the reference too
 
 
+def _knn_raw(mlg, xb, k, dil, tensor_path):
+    """mlg_knn_graph through the C ABI with either the full workspace (tensor-core candidate search where eligible) or just
+    the squared-norm workspace (forces the fp32 kernel)."""
+    L = mlg._cabi.lib()
+    B, N, D = xb.shape
+    nbr = torch.empty(B * N * k, dtype=torch.int64, device=DEV)
+    ctr = torch.empty_like(nbr)
+    dist = torch.empty(B * N * k, dtype=torch.float32, device=DEV)
+    nbytes = int(L.mlg_knn_workspace_bytes(B, N, D, k, dil)) if tensor_path else B * N * 4
+    ws = torch.empty((nbytes + 3) // 4, dtype=torch.float32, device=DEV)
+    mlg._cabi.check(L.mlg_knn_graph(mlg._cabi.fptr(xb), B, N, D, k, dil, 1, mlg._cabi.lptr(nbr), mlg._cabi.lptr(ctr),
+                                    mlg._cabi.fptr(dist), mlg._cabi.fptr(ws), nbytes, mlg._cabi.stream_ptr()), "mlg_knn_graph")
+    torch.cuda.synchronize()
+    return nbr, ctr, dist
+
+
+@pytest.mark.parametrize("case", ["gauss_d64", "batch2_pad_dil", "d100_chunk128", "lattice_ties", "duplicates"])
+def test_knn_tensor_core_path_equals_fp32_kernel(mlg, case):
+    """Graphs of >= 4096 points: candidates from 3xTF32 distance products on the tensor cores, fp32 re-evaluation,
+    certificate, repair pass (csrc/knn.cu) -- neighbours, order and distances must be IDENTICAL to the fp32 kernel's, which the
+    tests above hold to the oracle.  The lattice / duplicate cases are dense in exact ties, so no row can be certified and
+    the repair pass has to reproduce everything."""
+    g = torch.Generator().manual_seed(31)
+    if case == "gauss_d64":
+        x, k, dil = torch.randn(1, 5000, 64, generator=g), 16, 1
+    elif case == "batch2_pad_dil":
+        x, k, dil = torch.randn(2, 4500, 20, generator=g) * 3.0, 5, 3
+    elif case == "d100_chunk128":
+        x, k, dil = torch.randn(1, 4200, 100, generator=g), 9, 1
+    elif case == "lattice_ties":
+        x, k, dil = torch.randint(0, 6, (1, 4096, 3), generator=g).float(), 16, 1
+    else:
+        base = torch.randn(1, 1024, 32, generator=g)
+        x, k, dil = base.repeat(1, 4, 1), 8, 2
+    xb = x.to(DEV).contiguous()
+    assert int(mlg._cabi.lib().mlg_knn_workspace_bytes(x.shape[0], x.shape[1], x.shape[2], k, dil)) > x.shape[0] * x.shape[1] * 4 + 256
+    n1, c1, d1 = _knn_raw(mlg, xb, k, dil, True)
+    n0, c0, d0 = _knn_raw(mlg, xb, k, dil, False)
+    assert torch.equal(c1, c0)
+    assert torch.equal(n1, n0), "%s: %d of %d neighbours differ" % (case, int((n1 != n0).sum()), n0.numel())
+    assert torch.equal(d1, d0)
+
+
 def test_dynconv_knn_then_conv(mlg):
     """DynConv.forward (gcn_lib/sparse/torch_vertex.py:366-380): rebuild the dilated kNN graph from the features, then run the
     static convolution on it -- the kNN -> conv call site.  In the reference this path raises for every conv its configs could

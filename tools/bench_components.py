@@ -132,7 +132,9 @@ def knn(quick):
         ns = 2000 if quick else 4000
         xc = x[:ns].cpu()
         c_ms = cpu_ms(lambda: R.knn_graph_matrix(xc, 16))
-        emit(row="a10 kNN graph (tiled fp32 distance + warp top-k)", shape="N=%d D=%d k=16" % (n, d), ms=round(ms, 3),
+        path = ("3xTF32 tcgen05 candidate search + fp32 re-evaluation / certificate" if n >= 4096 and d <= 128
+                else "tiled fp32 distance + warp top-k")
+        emit(row="a10 kNN graph (%s)" % path, shape="N=%d D=%d k=16" % (n, d), ms=round(ms, 3),
              bound="fp32-fma", achieved_TFLOPs=round(fl / ms / 1e9, 2), peak_TFLOPs=round(FP32_PEAK, 1),
              frac=round(fl / ms / 1e9 / FP32_PEAK, 4), cpu_oracle_ms=round(c_ms * (n / ns) ** 2, 1),
              cpu_sample="%d points, scaled by (N/%d)^2 (the reference materialises [N,N]: %.1f GB at this N)" % (ns, ns, n * n * 4 / 1e9))
