@@ -781,6 +781,257 @@ __global__ void __launch_bounds__(kRingWarps * 32) gen_fwd_ring_kernel(const Gen
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// backward, shared-memory staged variant (softmax family, H = 128 * NV; AFF = false: x + e messages, AFF = true: the
+// rank-1 affine edge term a_e * p + q): the same flat edge stream per warp as gen_fwd_ring_kernel -- source rows (and
+// edge-feature rows) arrive by 16-byte cp.async, kDepth edges in flight per warp without holding registers -- instead of
+// the register-staged gather of gen_bwd_kernel (UN rows per lane group in flight: 0.42 of HBM at N = 100 k, k = 16,
+// H = 128).  Per row: MsgNorm statistics and the direct term into g_x first, then one pass over its edges writes
+// g_edge (streaming stores).  Per-block partials as gen_bwd_kernel: (d/dt, d/dy_raw, d/dmsg_scale) and, for AFF with
+// pq_part, the sums of (a_e * g_edge, g_edge) over the block's edges.
+// ------------------------------------------------------------------------------------------------
+template <int NV, bool AFF>
+__global__ void __launch_bounds__(kRingWarps * 32) gen_bwd_ring_kernel(const GenP P) {
+  extern __shared__ __align__(16) unsigned char ring_raw[];
+  __shared__ float red[3 * 32];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const long long gw = (long long)blockIdx.x * kRingWarps + wib;
+  const long long r0 = gw * kRPW;
+  const unsigned H = P.H;
+  constexpr unsigned kSlotBytes = (AFF ? 1 : 2) * NV * 512;
+  const unsigned sbase = (unsigned)__cvta_generic_to_shared(ring_raw) + wib * kDepth * kSlotBytes + lane * 16;
+  float acc[3] = {0.f, 0.f, 0.f};
+  float su[NV][4], sv[NV][4];   // AFF: sums over this warp's edges of a_e * g_edge and g_edge
+#pragma unroll
+  for (int v = 0; v < NV; ++v)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) su[v][k] = sv[v][k] = 0.f;
+
+  if (r0 < P.n) {
+    const int r1 = (int)min((long long)P.n, r0 + kRPW);
+    unsigned long long pol_stream;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_stream));
+    const int rp = __ldg(P.rowptr + min((long long)P.n, r0 + min(lane, kRPW)));
+    const int qb = __shfl_sync(0xffffffffu, rp, 0);
+    const int qe = __shfl_sync(0xffffffffu, rp, r1 - (int)r0);
+    const int* eidp = P.eid;
+    const bool learn = P.learn != 0;
+    const float t = P.t_dev ? __ldg(P.t_dev) : P.t;
+    const float tl2 = t * MLG_LOG2E;
+    const float eps = P.eps;
+    float ysig = 0.f;
+    if (P.y_dev) ysig = sigmoidf_(__ldg(P.y_dev));
+    const float* xc = P.x + lane * 4;
+    const float* ec = AFF ? nullptr : P.e + lane * 4;
+    float4 pv[NV], qv[NV];
+    if (AFF) {
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+        pv[v] = ld_gather4(P.ep + lane * 4 + v * 128);
+        qv[v] = ld_gather4(P.eq + lane * 4 + v * 128);
+      }
+    }
+    const int n_groups = (qe - qb + kGroup - 1) / kGroup;
+
+    unsigned nxt_s[kGroup], nxt_e[kGroup];
+    auto fetch_ids = [&](int g) {
+#pragma unroll
+      for (int u = 0; u < kGroup; ++u) {
+        const int q = min(qb + g * kGroup + u, qe - 1);
+        nxt_s[u] = (unsigned)__ldg(P.col + q);
+        nxt_e[u] = eidp ? (unsigned)__ldg(eidp + q) : (unsigned)q;
+      }
+    };
+    auto issue = [&](int g) {
+      if (g < n_groups) {
+        const unsigned slot0 = sbase + (unsigned)((g % kGroups) * kGroup) * kSlotBytes;
+#pragma unroll
+        for (int u = 0; u < kGroup; ++u) {
+          const unsigned slot = slot0 + u * kSlotBytes;
+#pragma unroll
+          for (int v = 0; v < NV; ++v) {
+            cp_async16_plain(slot + v * 512, row_ptr(xc, nxt_s[u], H) + v * 128);
+            if (!AFF) cp_async16_pol(slot + (NV + v) * 512, row_ptr(ec, nxt_e[u], H) + v * 128, pol_stream);
+          }
+        }
+        if (g + 1 < n_groups) fetch_ids(g + 1);
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    if (n_groups > 0) fetch_ids(0);
+#pragma unroll
+    for (int i = 0; i < kGroups - 1; ++i) issue(i);
+
+    // ---- per-row state ----
+    int row = (int)r0;
+    int rend = __shfl_sync(0xffffffffu, rp, 1);
+    int rbeg = qb;
+    float gin[NV][4], oi[NV][4], au[NV][4];
+    auto begin_row = [&]() {
+      const int deg = rend - rbeg;
+      float degpow = 1.f, ycoef = 0.f;
+      if (P.y_dev) {
+        degpow = powf((float)deg, ysig);
+        ycoef = deg > 0 ? logf((float)deg) * ysig * (1.f - ysig) : 0.f;
+      }
+      float4 gr[NV], mr[NV], xr[NV];
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+        const unsigned off = lane * 4 + v * 128;
+        gr[v] = ld_gather4(row_ptr(P.g, (unsigned)row, H) + off);
+        mr[v] = ld_gather4(row_ptr(P.m_in, (unsigned)row, H) + off);
+        const float4 a = ld_gather4(row_ptr(P.aux_in, (unsigned)row, H) + off);
+        au[v][0] = a.x; au[v][1] = a.y; au[v][2] = a.z; au[v][3] = a.w;
+        xr[v] = (P.epi == MLG_EPI_MSGNORM) ? ld_gather4(row_ptr(P.x, (unsigned)row, H) + off) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      float f_gm = 1.f, f_u = 0.f, f_x = 0.f;   // g_m = f_gm * g - f_u * m ; g_x = g + f_x * x
+      if (P.epi == MLG_EPI_MSGNORM) {
+        float sx2 = 0.f, sm2 = 0.f, sgm = 0.f;
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+          sx2 += xr[v].x * xr[v].x + xr[v].y * xr[v].y + xr[v].z * xr[v].z + xr[v].w * xr[v].w;
+          sm2 += mr[v].x * mr[v].x + mr[v].y * mr[v].y + mr[v].z * mr[v].z + mr[v].w * mr[v].w;
+          sgm += gr[v].x * mr[v].x + gr[v].y * mr[v].y + gr[v].z * mr[v].z + gr[v].w * mr[v].w;
+        }
+        sx2 = warp_sum(sx2);
+        sm2 = warp_sum(sm2);
+        sgm = warp_sum(sgm);
+        const float s = __ldg(P.scale_dev);
+        const float r = sqrtf(sx2), nm = sqrtf(sm2);
+        const float nn = fmaxf(nm, 1e-12f);
+        const float dot = sgm / nn;
+        f_gm = s * r / nn;
+        f_u = (nm >= 1e-12f) ? f_gm * dot / nn : 0.f;
+        f_x = (r > 0.f) ? s * dot / r : 0.f;
+        if (lane == 0) acc[2] += dot * r;
+      }
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+        const unsigned off = lane * 4 + v * 128;
+        const float g4[4] = {gr[v].x, gr[v].y, gr[v].z, gr[v].w};
+        const float m4[4] = {mr[v].x, mr[v].y, mr[v].z, mr[v].w};
+        const float x4[4] = {xr[v].x, xr[v].y, xr[v].z, xr[v].w};
+        float gx[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          gx[k] = P.epi == MLG_EPI_NONE ? 0.f : (P.epi == MLG_EPI_RESIDUAL ? g4[k] : fmaf(f_x, x4[k], g4[k]));
+          const float gm = (P.epi == MLG_EPI_MSGNORM) ? (f_gm * g4[k] - f_u * m4[k]) : g4[k];
+          if (P.y_dev) acc[1] = fmaf(gm * m4[k], ycoef, acc[1]);
+          gin[v][k] = gm * degpow;
+          oi[v][k] = (P.y_dev && deg > 0) ? m4[k] / degpow : m4[k];
+        }
+        st4(row_ptr(P.g_x, (unsigned)row, H) + off, make_float4(gx[0], gx[1], gx[2], gx[3]));
+      }
+    };
+    begin_row();
+    for (int g = 0; g < n_groups; ++g) {
+      issue(g + kGroups - 1);
+      asm volatile("cp.async.wait_group %0;" ::"n"(kGroups - 1) : "memory");
+      const unsigned slot0 = sbase + (unsigned)((g % kGroups) * kGroup) * kSlotBytes;
+      const int q0 = qb + g * kGroup;
+#pragma unroll
+      for (int u = 0; u < kGroup; ++u) {
+        const int q = q0 + u;
+        if (q >= qe) break;
+        while (q >= rend) {   // next row (also walks over rows without edges: their g_x still has to be written)
+          ++row;
+          rbeg = rend;
+          rend = __shfl_sync(0xffffffffu, rp, row - (int)r0 + 1);
+          begin_row();
+        }
+        const unsigned eo = eidp ? (unsigned)__ldg(eidp + q) : (unsigned)q;   // uniform, L1-resident (fetched at issue time)
+        const float a_e = AFF ? __ldg(P.ea + eo) : 0.f;
+        const unsigned slot = slot0 + u * kSlotBytes;
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+          const float4 xv = lds128(slot + v * 512);
+          float4 ev;
+          if (AFF) ev = make_float4(fmaf(a_e, pv[v].x, qv[v].x), fmaf(a_e, pv[v].y, qv[v].y), fmaf(a_e, pv[v].z, qv[v].z),
+                                    fmaf(a_e, pv[v].w, qv[v].w));
+          else ev = lds128(slot + (NV + v) * 512);
+          const float pre[4] = {xv.x + ev.x, xv.y + ev.y, xv.z + ev.z, xv.w + ev.w};
+          float ge[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float val = fmaxf(pre[k], 0.f) + eps;
+            const float w = ex2_approx(fmaf(val, tl2, -au[v][k]));
+            const float gwt = gin[v][k] * w;
+            float gv = gwt;
+            if (learn) {
+              const float dv = val - oi[v][k];
+              gv = gwt * fmaf(t, dv, 1.f);
+              acc[0] = fmaf(gwt * val, dv, acc[0]);
+            }
+            ge[k] = pre[k] > 0.f ? gv : 0.f;
+            if (AFF) {
+              su[v][k] = fmaf(a_e, ge[k], su[v][k]);
+              sv[v][k] += ge[k];
+            }
+          }
+          st_stream4(row_ptr(P.g_edge, eo, H) + lane * 4 + v * 128, make_float4(ge[0], ge[1], ge[2], ge[3]));
+        }
+      }
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    while (row + 1 < r1) {   // trailing rows without edges
+      ++row;
+      rbeg = rend;
+      rend = __shfl_sync(0xffffffffu, rp, row - (int)r0 + 1);
+      begin_row();
+    }
+  }
+
+  if (AFF && P.pq_part) {   // block sums in warp order: reuse the (now idle) ring as [warps][2][H]
+    __syncthreads();
+    float* stage = reinterpret_cast<float*>(ring_raw);
+#pragma unroll
+    for (int v = 0; v < NV; ++v)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        stage[(size_t)wib * 2 * H + lane * 4 + v * 128 + k] = su[v][k];
+        stage[(size_t)wib * 2 * H + H + lane * 4 + v * 128 + k] = sv[v][k];
+      }
+    __syncthreads();
+    for (unsigned j = threadIdx.x; j < 2 * H; j += kRingWarps * 32) {
+      float sum = 0.f;
+#pragma unroll
+      for (int w = 0; w < kRingWarps; ++w) sum += stage[(size_t)w * 2 * H + j];
+      P.pq_part[(size_t)blockIdx.x * 2 * H + j] = sum;
+    }
+  }
+  block_sum<3>(acc, red);
+  if (threadIdx.x == 0) {
+    float* o = P.partials + (size_t)blockIdx.x * 4;
+    o[0] = acc[0];
+    o[1] = acc[1];
+    o[2] = acc[2];
+    o[3] = 0.f;
+  }
+}
+
+// host side of the ring backward: true when it ran
+inline bool ring_bwd_ok(const GenP& P) {
+  return P.mode == MLG_AGGR_SOFTMAX && P.x && (P.e || P.ea) && (P.H == 128 || P.H == 256) && ((uintptr_t)P.x % 16 == 0) &&
+         (!P.e || (uintptr_t)P.e % 16 == 0) && ((uintptr_t)P.g_edge % 16 == 0) && ((uintptr_t)P.g % 16 == 0) &&
+         ((uintptr_t)P.m_in % 16 == 0) && ((uintptr_t)P.aux_in % 16 == 0) && ((uintptr_t)P.g_x % 16 == 0) &&
+         (!P.ea || ((uintptr_t)P.ep % 16 == 0 && (uintptr_t)P.eq % 16 == 0));
+}
+inline long long ring_grid(long long n) { return (n + kRingWarps * kRPW - 1) / (kRingWarps * kRPW); }
+
+template <int NV, bool AFF>
+int launch_ring_bwd(const GenP& P, cudaStream_t st) {
+  int smem = kRingWarps * kDepth * (AFF ? 1 : 2) * NV * 512;
+  const int stage = kRingWarps * 2 * (int)P.H * 4;      // the pq block sums reuse the ring
+  if (AFF && P.pq_part && stage > smem) smem = stage;
+  static bool attr = false;
+  if (!attr) {
+    MLG_CUDA(cudaFuncSetAttribute(gen_bwd_ring_kernel<NV, AFF>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    attr = true;
+  }
+  gen_bwd_ring_kernel<NV, AFF><<<(unsigned)ring_grid(P.n), kRingWarps * 32, smem, st>>>(P);
+  return MLG_OK;
+}
+
 struct Cfg {
   int lanes, vec;
   bool full;
@@ -930,6 +1181,17 @@ extern "C" int mlg_gen_aggr_bwd(const float* g, const float* x, const float* e, 
   P.t = t; P.p = p; P.eps = eps; P.t_dev = t_dev; P.p_dev = p_dev; P.y_dev = y_dev;
   P.scale_dev = msg_scale_dev; P.g = g; P.m_in = m; P.aux_in = aux;
   P.g_edge = g_edge; P.g_x = g_x; P.partials = partials;
+#ifndef MLG_GEN_NO_RING
+  if (ring_bwd_ok(P)) {
+    // fewer blocks than the register-staged kernel: the unused partial rows must read as zero
+    const long long used = ring_grid(n), rows = mlg_gen_aggr_bwd_partial_rows(n, H);
+    if (rows > used) MLG_CUDA(cudaMemsetAsync(partials + used * 4, 0, (size_t)(rows - used) * 16, (cudaStream_t)stream));
+    rc = H == 128 ? launch_ring_bwd<1, false>(P, (cudaStream_t)stream) : launch_ring_bwd<2, false>(P, (cudaStream_t)stream);
+    if (rc) return rc;
+    MLG_CHECK_LAUNCH("mlg_gen_aggr_bwd(ring)");
+    return MLG_OK;
+  }
+#endif
   rc = dispatch<false>(P, (cudaStream_t)stream);
   if (rc) return rc;
   MLG_CHECK_LAUNCH("mlg_gen_aggr_bwd");
@@ -1014,11 +1276,25 @@ extern "C" int mlg_gen_aggr_bwd_affine(const float* g, const float* x, const flo
   P.g_edge = g_edge; P.g_x = g_x; P.partials = partials;
   const bool fused = want_pq && pq_fused(H);
   if (fused) P.pq_part = (float*)workspace;
+  long long parts = grid_for(n, pick_cfg(H));
+#ifndef MLG_GEN_NO_RING
+  if (ring_bwd_ok(P) && (fused || !want_pq)) {
+    const long long used = ring_grid(n);
+    if (parts > used) MLG_CUDA(cudaMemsetAsync(partials + used * 4, 0, (size_t)(parts - used) * 16, (cudaStream_t)stream));
+    rc = H == 128 ? launch_ring_bwd<1, true>(P, (cudaStream_t)stream) : launch_ring_bwd<2, true>(P, (cudaStream_t)stream);
+    if (rc) return rc;
+    MLG_CHECK_LAUNCH("mlg_gen_aggr_bwd_affine(ring)");
+    if (fused)   // the partial layout [blocks][2][H] is the same, there are just fewer blocks; the scratch stays where the
+                 // workspace size function put it
+      return mlg_detail_colsum_partials((const float*)workspace, used, H, g_p, g_q, (float*)workspace + parts * 2 * H,
+                                        (cudaStream_t)stream);
+    return MLG_OK;
+  }
+#endif
   rc = dispatch<false>(P, (cudaStream_t)stream);
   if (rc) return rc;
   MLG_CHECK_LAUNCH("mlg_gen_aggr_bwd_affine");
   if (fused) {
-    const long long parts = grid_for(n, pick_cfg(H));
     return mlg_detail_colsum_partials((const float*)workspace, parts, H, g_p, g_q, (float*)workspace + parts * 2 * H,
                                       (cudaStream_t)stream);
   }

@@ -429,7 +429,7 @@ __device__ __forceinline__ void stvec(float* p, const float (&d)[VEC]) {
 }
 
 template <int P_, int VEC, int RB2>
-__global__ void __launch_bounds__(kThreads, (VEC == 1 && RB2 <= 2) ? 6 : ((VEC == 1 && RB2 <= 4) ? 4 : 2))
+__global__ void __launch_bounds__(kThreads, (VEC == 1 && RB2 <= 4) ? 4 : 2)
 pool_bwd_fused2_kernel(const float* __restrict__ g_cl, const float* __restrict__ x, const float* __restrict__ vm,
                        const float* __restrict__ w, const int* __restrict__ rowptr, const int* __restrict__ slots,
                        const int* __restrict__ seg_of_slot, int n_rows, int replicas, int S, int G,
@@ -639,16 +639,15 @@ extern "C" int mlg_pool_bwd(const float* g_out_cl, const float* x, const float* 
     // C = 32: 4 replicas per warp (64 registers, 32 warps / SM) instead of 8 (124 registers, 16 warps / SM): the kernel is
     // bound by its dependent loads (rowptr -> slot -> segment -> rows), so resident warps matter more than work per warp
     // (step 0.850 -> 0.834 ms at the gbm shape).
-    static const int rb_env = getenv("MLG_POOL_RB") ? atoi(getenv("MLG_POOL_RB")) : 0;
-    const int rb2 = C == 32 ? (rb_env == 2 ? 2 : 4) : (P <= 4 ? 8 : 4);
+    // (2 per warp at 40 registers / 48 warps was slower again: 0.846 ms.)
+    const int rb2 = C == 32 ? 4 : (P <= 4 ? 8 : 4);
     const long long warps2 = n_rows * ((replicas + rb2 - 1) / rb2);
     const int grid2 = mlg_ceil_div(warps2, kThreads / 32);
 #define MLG_POOL_F2(VV, RR)                                                                                           \
   MLG_P_SWITCH(P, (pool_bwd_fused2_kernel<P_, VV, RR><<<grid2, kThreads, 0, st>>>(                                     \
                       g_out_cl, x, vm, w, node_rowptr, node_slot, seg_of_slot, (int)n_rows, (int)replicas, (int)S,     \
                       (int)G, g_x, workspace, mask_input, mask_slope)))
-    if (C == 32 && rb2 == 2) { MLG_POOL_F2(1, 2); }
-    else if (C == 32) { MLG_POOL_F2(1, 4); }
+    if (C == 32) { MLG_POOL_F2(1, 4); }
     else if (C == 64) { MLG_POOL_F2(2, (P_ <= 4 ? 8 : 4)); }
     else { MLG_POOL_F2(4, (P_ <= 4 ? 8 : 4)); }
 #undef MLG_POOL_F2
