@@ -359,8 +359,10 @@ def diffpool_legs(dev):
         A = torch.randn(M, K, device=dev).bfloat16()
         Bm = torch.randn(N, K, device=dev).bfloat16()
         C = torch.empty(M, N, device=dev)
-        run = lambda: _cabi.check(L.mlg_gemm_bf16(ctypes.c_void_p(A.data_ptr()), K, 0, ctypes.c_void_p(Bm.data_ptr()), K, 0,
-                                                  _cabi.fptr(C), N, 0, M, N, K, 1, 1.0, _cabi.stream_ptr()), "mlg_gemm_bf16")
+        ws = torch.zeros(L.mlg_gemm_bf16_workspace_bytes(), dtype=torch.uint8, device=A.device)   # stream-K partials + flags
+        run = lambda: _cabi.check(L.mlg_gemm_bf16_ws(ctypes.c_void_p(A.data_ptr()), K, 0, ctypes.c_void_p(Bm.data_ptr()), K, 0,
+                                                     _cabi.fptr(C), N, 0, M, N, K, 1, 1.0, ctypes.c_void_p(ws.data_ptr()),
+                                                     ws.numel(), _cabi.stream_ptr()), "mlg_gemm_bf16_ws")
         ms = timed(run, 10)
         tf = 2.0 * M * N * K / ms / 1e9
         legs[what] = {"M": M, "N": N, "K": K, "ms": round(ms, 4), "bound": "tensor", "achieved": round(tf, 1), "peak": bf16_peak,

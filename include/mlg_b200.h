@@ -451,6 +451,15 @@ int mlg_cast_bf16(const float* src, int64_t ld_src, int64_t rows, int64_t cols, 
 int mlg_gemm_bf16(const void* A, int64_t lda, int64_t stride_a, const void* B, int64_t ldb, int64_t stride_b,
                   float* C, int64_t ldc, int64_t stride_c, int64_t M, int64_t N, int64_t K, int64_t batch,
                   float alpha, void* stream);
+/* Same product with a caller-owned workspace (mlg_gemm_bf16_workspace_bytes() bytes, 16-byte aligned, ZEROED ONCE when
+ * it is allocated, one per stream): for M, N >= 256 a persistent stream-K grid of SM pairs splits the (tile, k block)
+ * stream evenly, so products with fewer tiles than SM pairs (S^T.X) still fill the machine; partial tiles meet in the
+ * workspace and are added in a fixed order (reproducible).  Other shapes fall through to mlg_gemm_bf16.  Replaces
+ * the same torch.matmul call sites (PyG dense_diff_pool / DenseSAGEConv behind models/diff_pooling.py:61-64). */
+int64_t mlg_gemm_bf16_workspace_bytes(void);
+int mlg_gemm_bf16_ws(const void* A, int64_t lda, int64_t stride_a, const void* B, int64_t ldb, int64_t stride_b,
+                     float* C, int64_t ldc, int64_t stride_c, int64_t M, int64_t N, int64_t K, int64_t batch,
+                     float alpha, void* workspace, int64_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * fp32-accurate tall GEMM on the tensor cores (3xTF32 split, fp32 accumulation in tensor memory):

@@ -115,6 +115,9 @@ _SIGNATURES = {
     "mlg_cast_bf16": (_c_int, [_c_vp, _c_i64, _c_i64, _c_i64, _c_i64, _c_int, _c_vp, _c_i64, _c_vp]),
     "mlg_gemm_bf16": (_c_int, [_c_vp, _c_i64, _c_i64, _c_vp, _c_i64, _c_i64, _c_vp, _c_i64, _c_i64, _c_i64, _c_i64,
                                _c_i64, _c_i64, _c_f32, _c_vp]),
+    "mlg_gemm_bf16_workspace_bytes": (_c_i64, []),
+    "mlg_gemm_bf16_ws": (_c_int, [_c_vp, _c_i64, _c_i64, _c_vp, _c_i64, _c_i64, _c_vp, _c_i64, _c_i64, _c_i64, _c_i64,
+                                  _c_i64, _c_i64, _c_f32, _c_vp, _c_i64, _c_vp]),
     "mlg_split_tf32": (_c_int, [_c_vp, _c_i64, _c_vp, _c_vp, _c_vp]),
     "mlg_gemm_tf32x3_supported": (_c_int, [_c_i64, _c_i64, _c_i64]),
     "mlg_gemm_tf32x3": (_c_int, [_c_vp, _c_i64, _c_vp, _c_vp, _c_vp, _c_vp, _c_i64, _c_i64, _c_i64, _c_i64, _c_int, _c_f32,

@@ -29,9 +29,24 @@ def _cast(src, transpose):
     return dst, ld
 
 
+_WORKSPACES = {}
+
+
+def _workspace(device):
+    """Stream-K workspace of the current stream (partial tiles + flags), zeroed once: the kernel's consumers reset
+    the flags they read, so it stays reusable across launches on that stream."""
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    ws = _WORKSPACES.get(key)
+    if ws is None:
+        ws = _WORKSPACES[key] = torch.zeros(_cabi.lib().mlg_gemm_bf16_workspace_bytes(), dtype=torch.uint8, device=device)
+    return ws
+
+
 def _gemm_tn(a_bf, lda, b_bf, ldb, M, N, K, batch, a_batched, b_batched):
     """C[b] = A[b] (M x K) . B[b]^T (N x K), operands already bf16 K-major."""
     L = _cabi.lib()
+    ws = _workspace(a_bf.device)
+    wsp, wsb = ctypes.c_void_p(ws.data_ptr()), ws.numel()
     c = torch.empty(batch, M, N, dtype=torch.float32, device=a_bf.device)
     sa = a_bf.stride(0) if a_batched else 0
     sb = b_bf.stride(0) if b_batched else 0
@@ -42,11 +57,13 @@ def _gemm_tn(a_bf, lda, b_bf, ldb, M, N, K, batch, a_batched, b_batched):
             for i in range(batch):
                 ai = a_bf[i] if a_batched else a_bf[0]
                 bi = b_bf[i] if b_batched else b_bf[0]
-                _cabi.check(L.mlg_gemm_bf16(ctypes.c_void_p(ai.data_ptr()), lda, 0, ctypes.c_void_p(bi.data_ptr()), ldb, 0,
-                                            _cabi.fptr(c[i]), N, 0, M, N, K, 1, 1.0, _cabi.stream_ptr()), "mlg_gemm_bf16")
+                _cabi.check(L.mlg_gemm_bf16_ws(ctypes.c_void_p(ai.data_ptr()), lda, 0, ctypes.c_void_p(bi.data_ptr()), ldb,
+                                               0, _cabi.fptr(c[i]), N, 0, M, N, K, 1, 1.0, wsp, wsb, _cabi.stream_ptr()),
+                            "mlg_gemm_bf16_ws")
         else:
-            _cabi.check(L.mlg_gemm_bf16(ctypes.c_void_p(a_bf.data_ptr()), lda, sa, ctypes.c_void_p(b_bf.data_ptr()), ldb, sb,
-                                        _cabi.fptr(c), N, M * N, M, N, K, batch, 1.0, _cabi.stream_ptr()), "mlg_gemm_bf16")
+            _cabi.check(L.mlg_gemm_bf16_ws(ctypes.c_void_p(a_bf.data_ptr()), lda, sa, ctypes.c_void_p(b_bf.data_ptr()), ldb,
+                                           sb, _cabi.fptr(c), N, M * N, M, N, K, batch, 1.0, wsp, wsb, _cabi.stream_ptr()),
+                        "mlg_gemm_bf16_ws")
     return c
 
 

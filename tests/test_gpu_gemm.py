@@ -36,6 +36,27 @@ def test_gemm_bf16_matches_rounded_reference(gemm, shape):
     assert err <= 2 ** -7 * math.sqrt(K) * 4, "vs fp32 product: %g" % err
 
 
+@pytest.mark.parametrize("shape", [(512, 512, 4096, 1), (256, 256, 10000, 1), (2500, 1024, 10000, 1), (300, 260, 100, 1),
+                                   (1000, 700, 2100, 3), (2500, 2500, 3000, 1), (257, 513, 64, 5)])
+def test_gemm_bf16_stream_k(gemm, shape):
+    """M, N >= 256: persistent stream-K grid of SM pairs (mlg_gemm_bf16_ws).  Shapes where tiles are split between
+    pairs (few tiles x long K), pairs that span several tiles (many tiles x short K), ragged edges, batches.  Each is
+    launched three times on the same workspace (the consumers reset the flags) and must give bit-identical
+    results (partials are added in pair order)."""
+    M, N, K, B = shape
+    g = torch.Generator().manual_seed(M + N + K)
+    a = torch.randn(B, M, K, generator=g).to(DEV)
+    b = torch.randn(B, K, N, generator=g).to(DEV)
+    ref = torch.matmul(a.bfloat16().double(), b.bfloat16().double()).float()
+    first = None
+    for _ in range(3):
+        c = gemm.matmul_bf16(a, b)
+        assert_close(c, ref, rtol=1e-4, atol=1e-4, what="stream-K %s" % (shape,))
+        if first is None:
+            first = c.clone()
+        assert torch.equal(c, first)
+
+
 def test_gemm_bf16_batched_and_grad(gemm):
     g = torch.Generator().manual_seed(5)
     a = torch.randn(3, 200, 320, generator=g).to(DEV).requires_grad_()

@@ -165,8 +165,10 @@ def diffpool(quick):
         A = torch.randn(M, K, device=DEV).bfloat16()
         Bm = torch.randn(N, K, device=DEV).bfloat16()
         C = torch.empty(M, N, device=DEV)
-        run = lambda: _cabi.check(L.mlg_gemm_bf16(ctypes.c_void_p(A.data_ptr()), K, 0, ctypes.c_void_p(Bm.data_ptr()), K, 0,
-                                                  _cabi.fptr(C), N, 0, M, N, K, 1, 1.0, _cabi.stream_ptr()), "mlg_gemm_bf16")
+        ws = torch.zeros(L.mlg_gemm_bf16_workspace_bytes(), dtype=torch.uint8, device=A.device)   # stream-K partials + flags
+        run = lambda: _cabi.check(L.mlg_gemm_bf16_ws(ctypes.c_void_p(A.data_ptr()), K, 0, ctypes.c_void_p(Bm.data_ptr()), K, 0,
+                                                     _cabi.fptr(C), N, 0, M, N, K, 1, 1.0, ctypes.c_void_p(ws.data_ptr()),
+                                                     ws.numel(), _cabi.stream_ptr()), "mlg_gemm_bf16_ws")
         ms = gpu_ms(run, reps=10)
         tf = 2.0 * M * N * K / ms / 1e9
         emit(row="a11 DiffPool contraction %s on tcgen05 (bf16 in, fp32 accumulate)" % what, shape="M=%d N=%d K=%d" % (M, N, K),
