@@ -38,7 +38,10 @@ __device__ __forceinline__ bool drop_keep(const int* bits, size_t i, int thr) { 
 // shared memory as a warp-wide broadcast (LDS.128: four output channels per load), so the inner loops are pure FMA
 // streams (1 LDS per 4 FMA).  A block owns whole "bands" (kh image rows = Wo pooling windows side by side), so pooling is
 // a shared-memory exchange inside the block.  (The first version walked one warp per window with 32-lane shuffled
-// mat-vecs: 28 us forward / 276 us backward on B200 -- shuffle / LDS bound; see profiles/r02_step_launches.md.)
+// mat-vecs: 28 us forward / 276 us backward on B200 -- shuffle / LDS bound; see profiles/r02_ncu_head.md.  Tried after this
+// version and dropped: four threads per pixel in 64-pixel blocks, 576 blocks instead of 109 -- as adjacent lanes the
+// weight reads stop being broadcasts (4 wavefronts per LDS.128: 31 / 68 us), as four warps per pixel group 27 / 54 us under
+// ncu and the SAME step time in the captured graph, A/B on one box: 0.8276 vs 0.8271 ms.)
 constexpr int kPix = 256;          // threads per block = pixel slots per block
 constexpr int ZLD = C2 + 1;        // row pitch of the [pixel][64] tile: conflict-free for "thread = pixel" row access
 constexpr int HLD = C1 + 4;        // row pitch of the [pixel][32] tiles (16-byte aligned rows)

@@ -32,7 +32,7 @@ def _ref_conv_pool(x, W1, b1, W2, b2, age, kh, kw, mask=None, p=0.0):
 
 
 @pytest.mark.parametrize("B,H,W,kh,kw,with_age", [(32, 146, 6, 4, 2, True), (5, 146, 9, 1, 1, False), (3, 7, 5, 2, 2, True),
-                                                   (2, 9, 4, 3, 4, False)])
+                                                   (2, 9, 4, 3, 4, False), (2, 30, 20, 4, 2, True), (3, 40, 16, 4, 4, False)])
 def test_head_conv_pool_matches_torch(mlg, B, H, W, kh, kw, with_age):
     from multilevel_gnn_b200 import functional as Fn
     g = torch.Generator().manual_seed(100 + B)
