@@ -102,6 +102,18 @@ int mlg_gen_aggr_bwd(const float* g, const float* x, const float* e, const int32
                      float eps, int epilogue, const float* msg_scale_dev, const float* m,
                      const float* aux, float* g_edge, float* g_x, float* partials, void* stream);
 
+/* Same backward with the source-side sum done inside the kernel (softmax family, H = 128 or 256, messages built from x:
+ * mlg_gen_aggr_bwd_src_supported): g_x [n,H] = direct term + sum over out-edges of g_edge, accumulated with 16-byte
+ * vector reductions into L2 (g_x is zeroed by the call) -- no second pass over g_edge [E,H].  g_edge may be NULL when the
+ * caller does not need the edge gradients.  The order of the additions, hence the last bits of g_x, is not reproducible
+ * (as with the reference's scatter-add backward, torch_scatter behind gcn_lib/sparse/torch_message.py:44-85). */
+int mlg_gen_aggr_bwd_src_supported(int64_t H, int mode, int have_x);
+int mlg_gen_aggr_bwd_src(const float* g, const float* x, const float* e, const int32_t* rowptr,
+                         const int32_t* col, const int32_t* eid, int64_t n, int64_t H, int mode, int learn,
+                         float t, const float* t_dev, float p, const float* p_dev, const float* y_dev,
+                         float eps, int epilogue, const float* msg_scale_dev, const float* m,
+                         const float* aux, float* g_edge, float* g_x, float* partials, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Weighted segment gather-sum (CSR SpMM with feature rows), all matrices row-major with a leading
  * dimension (floats) so that halves of a concatenated buffer can be read / written in place:
@@ -276,6 +288,15 @@ int mlg_gen_aggr_bwd_affine(const float* g, const float* x, const float* edge_sc
                             const float* p_dev, const float* y_dev, float eps, int epilogue, const float* msg_scale_dev,
                             const float* m, const float* aux, float* g_edge, float* g_x, float* partials, float* g_p,
                             float* g_q, void* workspace, int64_t workspace_bytes, void* stream);
+/* mlg_gen_aggr_bwd_affine with the source-side sum inside the kernel (see mlg_gen_aggr_bwd_src; same support query; needs
+ * g_p / g_q either both NULL or the fused per-block sums, i.e. H <= 256): g_edge may be NULL -- then no [E,H] tensor is
+ * written at all. */
+int mlg_gen_aggr_bwd_affine_src(const float* g, const float* x, const float* edge_scalar, const float* edge_p,
+                                const float* edge_q, const int32_t* rowptr, const int32_t* col, const int32_t* eid, int64_t n,
+                                int64_t n_edges, int64_t H, int mode, int learn, float t, const float* t_dev, float p,
+                                const float* p_dev, const float* y_dev, float eps, int epilogue, const float* msg_scale_dev,
+                                const float* m, const float* aux, float* g_edge, float* g_x, float* partials, float* g_p,
+                                float* g_q, void* workspace, int64_t workspace_bytes, void* stream);
 /* Weighted column sums of a tall matrix: u[c] = sum_r a[r] * G[r,c] (u NULL ok), v[c] = sum_r G[r,c] (v NULL ok); one
  * streaming pass, fixed summation order.  C % 4 == 0, C <= 1024.  workspace >= mlg_wcolsum_workspace_bytes(rows, C). */
 int64_t mlg_wcolsum_workspace_bytes(int64_t rows, int64_t C);

@@ -28,6 +28,10 @@ _SIGNATURES = {
     "mlg_gen_aggr_bwd": (_c_int, [_c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_i64, _c_i64, _c_int, _c_int,
                                   _c_f32, _c_vp, _c_f32, _c_vp, _c_vp, _c_f32, _c_int, _c_vp, _c_vp, _c_vp,
                                   _c_vp, _c_vp, _c_vp, _c_vp]),
+    "mlg_gen_aggr_bwd_src_supported": (_c_int, [_c_i64, _c_int, _c_int]),
+    "mlg_gen_aggr_bwd_src": (_c_int, [_c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_i64, _c_i64, _c_int, _c_int,
+                                  _c_f32, _c_vp, _c_f32, _c_vp, _c_vp, _c_f32, _c_int, _c_vp, _c_vp, _c_vp,
+                                  _c_vp, _c_vp, _c_vp, _c_vp]),
     "mlg_gather_sum": (_c_int, [_c_vp, _c_i64, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_i64, _c_i64, _c_i64,
                                 _c_i64, _c_i64, _c_int, _c_int, _c_vp, _c_i64, _c_vp, _c_i64, _c_vp, _c_i64, _c_vp, _c_i64,
                                 _c_f32, _c_vp, _c_vp]),
@@ -95,6 +99,9 @@ _SIGNATURES = {
     # (g, x, edge_scalar, edge_p, edge_q, rowptr, col, eid, n, n_edges, H, mode, learn, t, t_dev, p, p_dev, y_dev, eps, epilogue,
     #  scale, m, aux, g_edge, g_x, partials, g_p, g_q, workspace, workspace_bytes, stream)
     "mlg_gen_aggr_bwd_affine": (_c_int, [_c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_i64, _c_i64, _c_i64, _c_int,
+                                         _c_int, _c_f32, _c_vp, _c_f32, _c_vp, _c_vp, _c_f32, _c_int, _c_vp, _c_vp, _c_vp,
+                                         _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_i64, _c_vp]),
+    "mlg_gen_aggr_bwd_affine_src": (_c_int, [_c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_i64, _c_i64, _c_i64, _c_int,
                                          _c_int, _c_f32, _c_vp, _c_f32, _c_vp, _c_vp, _c_f32, _c_int, _c_vp, _c_vp, _c_vp,
                                          _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_i64, _c_vp]),
     "mlg_gen_aggr_bwd_affine_workspace_bytes": (_c_i64, [_c_i64, _c_i64, _c_i64]),
@@ -174,7 +181,7 @@ def last_error():
 
 
 # kernels launched per C call (own kernels only; CUB's sort passes inside mlg_csr_build are not counted)
-_LAUNCHES_PER_CALL = {"mlg_csr_build": 2, "mlg_knn_graph": 2, "mlg_xty": 2, "mlg_xty_tc": 2, "mlg_skinny_linear": 2, "mlg_wcolsum": 2, "mlg_gen_aggr_bwd_affine": 3, "mlg_layernorm_bwd": 2, "mlg_pool_bwd": 2, "mlg_adam_step": 2,
+_LAUNCHES_PER_CALL = {"mlg_csr_build": 2, "mlg_knn_graph": 2, "mlg_xty": 2, "mlg_xty_tc": 2, "mlg_skinny_linear": 2, "mlg_wcolsum": 2, "mlg_gen_aggr_bwd_affine": 3, "mlg_gen_aggr_bwd_affine_src": 3, "mlg_layernorm_bwd": 2, "mlg_pool_bwd": 2, "mlg_adam_step": 2,
                       "mlg_head_conv_pool_bwd": 2, "mlg_head_mlp_fwd": 2, "mlg_diffpool_bwd": 2, "mlg_pca_indep_loss": 2}
 LAUNCH_COUNT = 0
 TIMER = None        # a KernelTimer while bench.py measures per-kernel device time

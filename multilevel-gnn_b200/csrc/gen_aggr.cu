@@ -52,9 +52,10 @@ struct GenP {
   const float* g;
   const float* m_in;
   const float* aux_in;
-  float* g_edge;
+  float* g_edge;     // ring backward with src_sum: may be nullptr (edge gradients not wanted)
   float* g_x;
   float* partials;
+  int src_sum;       // ring backward: also add every edge gradient into g_x[source] (red.global.add.v4.f32; g_x zeroed first)
 };
 
 constexpr int kThreads = 256;
@@ -790,6 +791,15 @@ __global__ void __launch_bounds__(kRingWarps * 32) gen_fwd_ring_kernel(const Gen
 // g_edge (streaming stores).  Per-block partials as gen_bwd_kernel: (d/dt, d/dy_raw, d/dmsg_scale) and, for AFF with
 // pq_part, the sums of (a_e * g_edge, g_edge) over the block's edges.
 // ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void red_add4(float* p, float4 v) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+// P.src_sum: the source-side sum g_x[j] += sum over out-edges (j -> i) of g_edge is done HERE with 16-byte vector reductions
+// into the L2-resident g_x (probe tools/probes/red_v4.cu: 1.6 M scattered 512-byte rows in 0.144 ms = 5.7 TB/s of payload,
+// the speed of a plain read-modify-write) instead of a second kernel that reads all of g_edge [E, H] again; with the affine
+// edge term g_edge is then not written at all.  The order of the additions is not reproducible (as in the reference's own
+// scatter-add backward); the two-pass path stays available (functional.GEN_BWD_SRC_ATOMIC = False).
 template <int NV, bool AFF>
 __global__ void __launch_bounds__(kRingWarps * 32) gen_bwd_ring_kernel(const GenP P) {
   extern __shared__ __align__(16) unsigned char ring_raw[];
@@ -920,7 +930,8 @@ __global__ void __launch_bounds__(kRingWarps * 32) gen_bwd_ring_kernel(const Gen
           gin[v][k] = gm * degpow;
           oi[v][k] = (P.y_dev && deg > 0) ? m4[k] / degpow : m4[k];
         }
-        st4(row_ptr(P.g_x, (unsigned)row, H) + off, make_float4(gx[0], gx[1], gx[2], gx[3]));
+        if (!P.src_sum) st4(row_ptr(P.g_x, (unsigned)row, H) + off, make_float4(gx[0], gx[1], gx[2], gx[3]));
+        else if (P.epi != MLG_EPI_NONE) red_add4(row_ptr(P.g_x, (unsigned)row, H) + off, make_float4(gx[0], gx[1], gx[2], gx[3]));
       }
     };
     begin_row();
@@ -940,6 +951,7 @@ __global__ void __launch_bounds__(kRingWarps * 32) gen_bwd_ring_kernel(const Gen
           begin_row();
         }
         const unsigned eo = eidp ? (unsigned)__ldg(eidp + q) : (unsigned)q;   // uniform, L1-resident (fetched at issue time)
+        const unsigned src = P.src_sum ? (unsigned)__ldg(P.col + q) : 0u;
         const float a_e = AFF ? __ldg(P.ea + eo) : 0.f;
         const unsigned slot = slot0 + u * kSlotBytes;
 #pragma unroll
@@ -968,7 +980,8 @@ __global__ void __launch_bounds__(kRingWarps * 32) gen_bwd_ring_kernel(const Gen
               sv[v][k] += ge[k];
             }
           }
-          st_stream4(row_ptr(P.g_edge, eo, H) + lane * 4 + v * 128, make_float4(ge[0], ge[1], ge[2], ge[3]));
+          if (P.g_edge) st_stream4(row_ptr(P.g_edge, eo, H) + lane * 4 + v * 128, make_float4(ge[0], ge[1], ge[2], ge[3]));
+          if (P.src_sum) red_add4(row_ptr(P.g_x, src, H) + lane * 4 + v * 128, make_float4(ge[0], ge[1], ge[2], ge[3]));
         }
       }
     }
@@ -1012,7 +1025,8 @@ __global__ void __launch_bounds__(kRingWarps * 32) gen_bwd_ring_kernel(const Gen
 // host side of the ring backward: true when it ran
 inline bool ring_bwd_ok(const GenP& P) {
   return P.mode == MLG_AGGR_SOFTMAX && P.x && (P.e || P.ea) && (P.H == 128 || P.H == 256) && ((uintptr_t)P.x % 16 == 0) &&
-         (!P.e || (uintptr_t)P.e % 16 == 0) && ((uintptr_t)P.g_edge % 16 == 0) && ((uintptr_t)P.g % 16 == 0) &&
+         (!P.e || (uintptr_t)P.e % 16 == 0) && (P.g_edge || P.src_sum) && ((uintptr_t)P.g_edge % 16 == 0) &&
+         ((uintptr_t)P.g % 16 == 0) &&
          ((uintptr_t)P.m_in % 16 == 0) && ((uintptr_t)P.aux_in % 16 == 0) && ((uintptr_t)P.g_x % 16 == 0) &&
          (!P.ea || ((uintptr_t)P.ep % 16 == 0 && (uintptr_t)P.eq % 16 == 0));
 }
@@ -1162,15 +1176,16 @@ extern "C" int64_t mlg_gen_aggr_bwd_partial_rows(int64_t n, int64_t H) {
   return grid_for(n, pick_cfg(H));
 }
 
-extern "C" int mlg_gen_aggr_bwd(const float* g, const float* x, const float* e, const int32_t* rowptr,
-                                const int32_t* col, const int32_t* eid, int64_t n, int64_t H, int mode,
-                                int learn, float t, const float* t_dev, float p, const float* p_dev,
-                                const float* y_dev, float eps, int epilogue, const float* msg_scale_dev,
-                                const float* m, const float* aux, float* g_edge, float* g_x,
-                                float* partials, void* stream) {
+// src_sum: 1 = g_x also receives the source-side sums (ring kernel only; g_edge may then be nullptr)
+static int gen_aggr_bwd_impl(const float* g, const float* x, const float* e, const int32_t* rowptr,
+                             const int32_t* col, const int32_t* eid, int64_t n, int64_t H, int mode,
+                             int learn, float t, const float* t_dev, float p, const float* p_dev,
+                             const float* y_dev, float eps, int epilogue, const float* msg_scale_dev,
+                             const float* m, const float* aux, float* g_edge, float* g_x,
+                             float* partials, int src_sum, void* stream) {
   int rc = check_common("mlg_gen_aggr_bwd", x, e, rowptr, col, n, H, epilogue, msg_scale_dev);
   if (rc) return rc;
-  MLG_CHECK_ARG(g && m && g_edge && g_x && partials, "mlg_gen_aggr_bwd: null g/m/g_edge/g_x/partials");
+  MLG_CHECK_ARG(g && m && (g_edge || src_sum) && g_x && partials, "mlg_gen_aggr_bwd: null g/m/g_edge/g_x/partials");
   MLG_CHECK_ARG(aux || (mode != MLG_AGGR_SOFTMAX && mode != MLG_AGGR_POWER),
                 "mlg_gen_aggr_bwd: softmax/power backward needs aux from the forward");
   if (n == 0) return MLG_OK;
@@ -1180,9 +1195,11 @@ extern "C" int mlg_gen_aggr_bwd(const float* g, const float* x, const float* e, 
   P.n = (int)n; P.H = (unsigned)H; P.mode = mode; P.epi = epilogue; P.learn = learn;
   P.t = t; P.p = p; P.eps = eps; P.t_dev = t_dev; P.p_dev = p_dev; P.y_dev = y_dev;
   P.scale_dev = msg_scale_dev; P.g = g; P.m_in = m; P.aux_in = aux;
-  P.g_edge = g_edge; P.g_x = g_x; P.partials = partials;
+  P.g_edge = g_edge; P.g_x = g_x; P.partials = partials; P.src_sum = src_sum;
+  MLG_CHECK_ARG(!src_sum || ring_bwd_ok(P), "mlg_gen_aggr_bwd_src: shape / mode not supported (see mlg_gen_aggr_bwd_src_supported)");
 #ifndef MLG_GEN_NO_RING
   if (ring_bwd_ok(P)) {
+    if (src_sum) MLG_CUDA(cudaMemsetAsync(g_x, 0, (size_t)n * H * 4, (cudaStream_t)stream));
     // fewer blocks than the register-staged kernel: the unused partial rows must read as zero
     const long long used = ring_grid(n), rows = mlg_gen_aggr_bwd_partial_rows(n, H);
     if (rows > used) MLG_CUDA(cudaMemsetAsync(partials + used * 4, 0, (size_t)(rows - used) * 16, (cudaStream_t)stream));
@@ -1196,6 +1213,34 @@ extern "C" int mlg_gen_aggr_bwd(const float* g, const float* x, const float* e, 
   if (rc) return rc;
   MLG_CHECK_LAUNCH("mlg_gen_aggr_bwd");
   return MLG_OK;
+}
+
+extern "C" int mlg_gen_aggr_bwd(const float* g, const float* x, const float* e, const int32_t* rowptr,
+                                const int32_t* col, const int32_t* eid, int64_t n, int64_t H, int mode,
+                                int learn, float t, const float* t_dev, float p, const float* p_dev,
+                                const float* y_dev, float eps, int epilogue, const float* msg_scale_dev,
+                                const float* m, const float* aux, float* g_edge, float* g_x,
+                                float* partials, void* stream) {
+  return gen_aggr_bwd_impl(g, x, e, rowptr, col, eid, n, H, mode, learn, t, t_dev, p, p_dev, y_dev, eps, epilogue,
+                           msg_scale_dev, m, aux, g_edge, g_x, partials, 0, stream);
+}
+
+extern "C" int mlg_gen_aggr_bwd_src_supported(int64_t H, int mode, int have_x) {
+#ifdef MLG_GEN_NO_RING
+  return 0;
+#else
+  return mode == MLG_AGGR_SOFTMAX && (H == 128 || H == 256) && have_x;
+#endif
+}
+
+extern "C" int mlg_gen_aggr_bwd_src(const float* g, const float* x, const float* e, const int32_t* rowptr,
+                                    const int32_t* col, const int32_t* eid, int64_t n, int64_t H, int mode,
+                                    int learn, float t, const float* t_dev, float p, const float* p_dev,
+                                    const float* y_dev, float eps, int epilogue, const float* msg_scale_dev,
+                                    const float* m, const float* aux, float* g_edge, float* g_x,
+                                    float* partials, void* stream) {
+  return gen_aggr_bwd_impl(g, x, e, rowptr, col, eid, n, H, mode, learn, t, t_dev, p, p_dev, y_dev, eps, epilogue,
+                           msg_scale_dev, m, aux, g_edge, g_x, partials, 1, stream);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1246,13 +1291,13 @@ extern "C" int64_t mlg_gen_aggr_bwd_affine_workspace_bytes(int64_t n, int64_t n_
   return mlg_wcolsum_workspace_bytes(n_edges, H);
 }
 
-extern "C" int mlg_gen_aggr_bwd_affine(const float* g, const float* x, const float* edge_scalar, const float* edge_p,
-                                       const float* edge_q, const int32_t* rowptr, const int32_t* col, const int32_t* eid,
-                                       int64_t n, int64_t n_edges, int64_t H, int mode, int learn, float t,
-                                       const float* t_dev, float p, const float* p_dev, const float* y_dev, float eps,
-                                       int epilogue, const float* msg_scale_dev, const float* m, const float* aux,
-                                       float* g_edge, float* g_x, float* partials, float* g_p, float* g_q, void* workspace,
-                                       int64_t workspace_bytes, void* stream) {
+static int gen_aggr_bwd_affine_impl(const float* g, const float* x, const float* edge_scalar, const float* edge_p,
+                                    const float* edge_q, const int32_t* rowptr, const int32_t* col, const int32_t* eid,
+                                    int64_t n, int64_t n_edges, int64_t H, int mode, int learn, float t,
+                                    const float* t_dev, float p, const float* p_dev, const float* y_dev, float eps,
+                                    int epilogue, const float* msg_scale_dev, const float* m, const float* aux,
+                                    float* g_edge, float* g_x, float* partials, float* g_p, float* g_q, void* workspace,
+                                    int64_t workspace_bytes, int src_sum, void* stream) {
   const bool want_pq = g_p != nullptr || g_q != nullptr;
   MLG_CHECK_ARG(!want_pq || (workspace && workspace_bytes >= mlg_gen_aggr_bwd_affine_workspace_bytes(n, n_edges, H)),
                 "mlg_gen_aggr_bwd_affine: g_p / g_q need a workspace of mlg_gen_aggr_bwd_affine_workspace_bytes()");
@@ -1263,7 +1308,7 @@ extern "C" int mlg_gen_aggr_bwd_affine(const float* g, const float* x, const flo
   MLG_CHECK_ARG(x && edge_scalar && edge_p && edge_q, "mlg_gen_aggr_bwd_affine: null x / edge_scalar / edge_p / edge_q");
   int rc = check_common("mlg_gen_aggr_bwd_affine", x, nullptr, rowptr, col, n, H, epilogue, msg_scale_dev);
   if (rc) return rc;
-  MLG_CHECK_ARG(g && m && g_edge && g_x && partials, "mlg_gen_aggr_bwd_affine: null g/m/g_edge/g_x/partials");
+  MLG_CHECK_ARG(g && m && (g_edge || src_sum) && g_x && partials, "mlg_gen_aggr_bwd_affine: null g/m/g_edge/g_x/partials");
   MLG_CHECK_ARG(aux || (mode != MLG_AGGR_SOFTMAX && mode != MLG_AGGR_POWER),
                 "mlg_gen_aggr_bwd_affine: softmax/power backward needs aux from the forward");
   if (n == 0) return MLG_OK;
@@ -1273,12 +1318,15 @@ extern "C" int mlg_gen_aggr_bwd_affine(const float* g, const float* x, const flo
   P.n = (int)n; P.H = (unsigned)H; P.mode = mode; P.epi = epilogue; P.learn = learn;
   P.t = t; P.p = p; P.eps = eps; P.t_dev = t_dev; P.p_dev = p_dev; P.y_dev = y_dev;
   P.scale_dev = msg_scale_dev; P.g = g; P.m_in = m; P.aux_in = aux;
-  P.g_edge = g_edge; P.g_x = g_x; P.partials = partials;
+  P.g_edge = g_edge; P.g_x = g_x; P.partials = partials; P.src_sum = src_sum;
   const bool fused = want_pq && pq_fused(H);
   if (fused) P.pq_part = (float*)workspace;
   long long parts = grid_for(n, pick_cfg(H));
+  MLG_CHECK_ARG(!src_sum || (ring_bwd_ok(P) && (fused || !want_pq)),
+                "mlg_gen_aggr_bwd_affine_src: shape / mode not supported (see mlg_gen_aggr_bwd_src_supported)");
 #ifndef MLG_GEN_NO_RING
   if (ring_bwd_ok(P) && (fused || !want_pq)) {
+    if (src_sum) MLG_CUDA(cudaMemsetAsync(g_x, 0, (size_t)n * H * 4, (cudaStream_t)stream));
     const long long used = ring_grid(n);
     if (parts > used) MLG_CUDA(cudaMemsetAsync(partials + used * 4, 0, (size_t)(parts - used) * 16, (cudaStream_t)stream));
     rc = H == 128 ? launch_ring_bwd<1, true>(P, (cudaStream_t)stream) : launch_ring_bwd<2, true>(P, (cudaStream_t)stream);
@@ -1301,4 +1349,28 @@ extern "C" int mlg_gen_aggr_bwd_affine(const float* g, const float* x, const flo
   if (want_pq)   // very wide rows: one extra streaming pass over g_edge
     return mlg_wcolsum(g_edge, H, edge_scalar, n_edges, H, g_p, g_q, workspace, workspace_bytes, stream);
   return MLG_OK;
+}
+
+extern "C" int mlg_gen_aggr_bwd_affine(const float* g, const float* x, const float* edge_scalar, const float* edge_p,
+                                       const float* edge_q, const int32_t* rowptr, const int32_t* col, const int32_t* eid,
+                                       int64_t n, int64_t n_edges, int64_t H, int mode, int learn, float t,
+                                       const float* t_dev, float p, const float* p_dev, const float* y_dev, float eps,
+                                       int epilogue, const float* msg_scale_dev, const float* m, const float* aux,
+                                       float* g_edge, float* g_x, float* partials, float* g_p, float* g_q, void* workspace,
+                                       int64_t workspace_bytes, void* stream) {
+  return gen_aggr_bwd_affine_impl(g, x, edge_scalar, edge_p, edge_q, rowptr, col, eid, n, n_edges, H, mode, learn, t, t_dev, p,
+                                  p_dev, y_dev, eps, epilogue, msg_scale_dev, m, aux, g_edge, g_x, partials, g_p, g_q,
+                                  workspace, workspace_bytes, 0, stream);
+}
+
+extern "C" int mlg_gen_aggr_bwd_affine_src(const float* g, const float* x, const float* edge_scalar, const float* edge_p,
+                                           const float* edge_q, const int32_t* rowptr, const int32_t* col,
+                                           const int32_t* eid, int64_t n, int64_t n_edges, int64_t H, int mode, int learn,
+                                           float t, const float* t_dev, float p, const float* p_dev, const float* y_dev,
+                                           float eps, int epilogue, const float* msg_scale_dev, const float* m,
+                                           const float* aux, float* g_edge, float* g_x, float* partials, float* g_p,
+                                           float* g_q, void* workspace, int64_t workspace_bytes, void* stream) {
+  return gen_aggr_bwd_affine_impl(g, x, edge_scalar, edge_p, edge_q, rowptr, col, eid, n, n_edges, H, mode, learn, t, t_dev, p,
+                                  p_dev, y_dev, eps, epilogue, msg_scale_dev, m, aux, g_edge, g_x, partials, g_p, g_q,
+                                  workspace, workspace_bytes, 1, stream);
 }

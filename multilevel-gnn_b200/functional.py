@@ -90,6 +90,11 @@ def grad_slot(param, shape):
     return slot["view"]
 
 
+# GENConv aggregation backward: the source-side sum g_x[j] += sum over out-edges of g_edge runs inside the backward kernel as
+# vector reductions into L2 (mlg_gen_aggr_bwd_src / _affine_src) instead of a second pass over g_edge [E, H]; with the
+# affine edge term no [E, H] gradient tensor exists at all.  The order of those additions is not reproducible (neither is
+# the reference's scatter-add backward); False / MLG_GEN_BWD_DETERMINISTIC=1 selects the two-pass fixed-order path.
+GEN_BWD_SRC_ATOMIC = not bool(int(__import__("os").environ.get("MLG_GEN_BWD_DETERMINISTIC", "0")))
 XTY_TC_MIN_ROWS = 8192   # below this the SIMT kernel's single launch wins
 
 
@@ -320,23 +325,29 @@ class GenAggregate(torch.autograd.Function):
         p_h, p_d = _scalar_args(ctx.p)
         y_d = None if ctx.y is None else _cabi.fptr(ctx.y.detach().reshape(1))
         s_d = None if ctx.scale is None else _cabi.fptr(ctx.scale.detach().reshape(1))
-        g_edge = torch.empty(max(n_edges, 1), H, dtype=torch.float32, device=dev)
+        needs = ctx.needs_input_grad
+        want_ge = ctx.has_e and needs[1]
+        src = (GEN_BWD_SRC_ATOMIC and ctx.has_x and needs[0] and n_edges > 0
+               and bool(L.mlg_gen_aggr_bwd_src_supported(H, ctx.mode, int(xd is not None))))
+        g_edge = torch.empty(max(n_edges, 1), H, dtype=torch.float32, device=dev) if (want_ge or not src) else None
         g_x = torch.empty(n, H, dtype=torch.float32, device=dev)
         rows = L.mlg_gen_aggr_bwd_partial_rows(n, H)
         partials = torch.empty(rows, 4, dtype=torch.float32, device=dev)
         bwd_bytes = 4 * H * (2 * n_edges + 3 * n) + 8 * n_edges          # SURVEY.md section 8d (no learn_t)
+        fn, name = (L.mlg_gen_aggr_bwd_src, "mlg_gen_aggr_bwd_src") if src else (L.mlg_gen_aggr_bwd, "mlg_gen_aggr_bwd")
         with torch.cuda.device(dev), _cabi.span("gen_aggr_bwd", bwd_bytes):
-            _cabi.check(L.mlg_gen_aggr_bwd(
+            _cabi.check(fn(
                 _cabi.fptr(g), _cabi.fptr(xd, True), _cabi.fptr(ed, True), _cabi.iptr(csr.rowptr),
                 _cabi.iptr(csr.col), None if topo.fwd_identity else _cabi.iptr(csr.eid), n, H, ctx.mode, int(ctx.learn), t_h, t_d, p_h, p_d,
-                y_d, ctx.eps, ctx.epilogue, s_d, _cabi.fptr(m), _cabi.fptr(aux, True), _cabi.fptr(g_edge),
-                _cabi.fptr(g_x), _cabi.fptr(partials), _cabi.stream_ptr()), "mlg_gen_aggr_bwd")
-        needs = ctx.needs_input_grad
+                y_d, ctx.eps, ctx.epilogue, s_d, _cabi.fptr(m), _cabi.fptr(aux, True), _cabi.fptr(g_edge, True),
+                _cabi.fptr(g_x), _cabi.fptr(partials), _cabi.stream_ptr()), name)
         gx = None
-        if ctx.has_x and needs[0]:
+        if src:
+            gx = g_x           # direct term + source-side sums, accumulated by the kernel
+        elif ctx.has_x and needs[0]:
             bw = topo.bwd      # rows = sources; eid = edge ids whose g_edge rows are summed
             gx = gather_sum(g_edge, bw.rowptr, bw.eid, n, out=g_x, addend=g_x, tag="gen_aggr_bwd_src")
-        ge = g_edge[:n_edges].reshape(ctx.e_shape) if (ctx.has_e and needs[1]) else None
+        ge = g_edge[:n_edges].reshape(ctx.e_shape) if want_ge else None
         sums = None
 
         def part(i):
@@ -426,27 +437,33 @@ class GenAggregateAffine(torch.autograd.Function):
         p_h, p_d = _scalar_args(ctx.p)
         y_d = None if ctx.y is None else _cabi.fptr(ctx.y.detach().reshape(1))
         s_d = None if ctx.scale is None else _cabi.fptr(ctx.scale.detach().reshape(1))
-        g_edge = torch.empty(max(n_edges, 1), H, dtype=torch.float32, device=dev)
+        needs = ctx.needs_input_grad
+        want_pq = needs[2] or needs[3]
+        src = (GEN_BWD_SRC_ATOMIC and needs[0] and n_edges > 0 and H <= 256
+               and bool(L.mlg_gen_aggr_bwd_src_supported(H, ctx.mode, 1)))
+        g_edge = torch.empty(max(n_edges, 1), H, dtype=torch.float32, device=dev) if (needs[1] or not src) else None
         g_x = torch.empty(n, H, dtype=torch.float32, device=dev)
         rows = L.mlg_gen_aggr_bwd_partial_rows(n, H)
         partials = torch.empty(rows, 4, dtype=torch.float32, device=dev)
-        needs = ctx.needs_input_grad
-        want_pq = needs[2] or needs[3]
         gp = gq = ws = None
         ws_bytes = 0
         if want_pq:
             gp, gq = torch.empty_like(pd), torch.empty_like(qd)
             ws_bytes = L.mlg_gen_aggr_bwd_affine_workspace_bytes(n, n_edges, H)
             ws = torch.empty((ws_bytes + 3) // 4, dtype=torch.float32, device=dev)
+        fn, name = ((L.mlg_gen_aggr_bwd_affine_src, "mlg_gen_aggr_bwd_affine_src") if src
+                    else (L.mlg_gen_aggr_bwd_affine, "mlg_gen_aggr_bwd_affine"))
         with torch.cuda.device(dev), _cabi.span("gen_aggr_bwd_affine", 4 * H * (n_edges + 4 * n) + 12 * n_edges):
-            _cabi.check(L.mlg_gen_aggr_bwd_affine(
+            _cabi.check(fn(
                 _cabi.fptr(g), _cabi.fptr(xd), _cabi.fptr(ad), _cabi.fptr(pd), _cabi.fptr(qd), _cabi.iptr(csr.rowptr),
                 _cabi.iptr(csr.col), None if topo.fwd_identity else _cabi.iptr(csr.eid), n, n_edges, H, ctx.mode,
                 int(ctx.learn), t_h, t_d, p_h, p_d, y_d, ctx.eps, ctx.epilogue, s_d, _cabi.fptr(m), _cabi.fptr(aux, True),
-                _cabi.fptr(g_edge), _cabi.fptr(g_x), _cabi.fptr(partials), _cabi.fptr(gp, True), _cabi.fptr(gq, True),
-                _cabi.fptr(ws, True), ws_bytes, _cabi.stream_ptr()), "mlg_gen_aggr_bwd_affine")
+                _cabi.fptr(g_edge, True), _cabi.fptr(g_x), _cabi.fptr(partials), _cabi.fptr(gp, True), _cabi.fptr(gq, True),
+                _cabi.fptr(ws, True), ws_bytes, _cabi.stream_ptr()), name)
         gx = None
-        if needs[0]:
+        if src:
+            gx = g_x
+        elif needs[0]:
             bw = topo.bwd
             gx = gather_sum(g_edge, bw.rowptr, bw.eid, n, out=g_x, addend=g_x, tag="gen_aggr_bwd_src")
         ga = None

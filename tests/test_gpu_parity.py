@@ -318,6 +318,48 @@ def test_gen_aggregate_affine_vs_materialized(mlg, aggr, H, epi):
             assert_close(u, v, rtol=2e-4, atol=1e-5 * max(1.0, float(v.abs().max())), what="grad[%d]" % i)
 
 
+@pytest.mark.parametrize("H,epi,affine,edge_grad", [(128, "msgnorm", False, True), (128, "msgnorm", False, False),
+                                                    (256, "residual", False, True), (128, "msgnorm", True, False),
+                                                    (256, "residual", True, False), (128, "residual", True, True)])
+def test_gen_backward_source_sum_in_kernel(mlg, H, epi, affine, edge_grad):
+    """mlg_gen_aggr_bwd_src / _affine_src (the source-side sum as vector reductions inside the backward kernel; default) vs
+    the two-pass fixed-order path (mlg_gen_aggr_bwd + mlg_gather_sum) on the same inputs -- hub sources with thousands of
+    out-edges, rows without in-edges, edge gradients wanted or not: every gradient within fp32 summation-order noise."""
+    Fn = mlg.functional
+    n, e = 3000, 48000
+    ei, g = _rand_graph(n, e, 31)
+    ei[0, :5000] = 7                       # hub: node 7 is the source of 5000 edges
+    ei[1, ei[1] == 11] = 12                # node 11 has no in-edges
+    topo = mlg.graph.topology(ei.to(DEV), n)
+    x0 = torch.randn(n, H, generator=g).to(DEV)
+    a0 = torch.rand(e, generator=g).to(DEV)
+    p0, q0 = torch.randn(H, generator=g).to(DEV), (0.3 * torch.randn(H, generator=g)).to(DEV)
+    e0 = torch.randn(e, H, generator=g).to(DEV)
+    Rm = torch.randn(n, H, generator=g).to(DEV)
+    code = Fn.EPI_MSGNORM if epi == "msgnorm" else Fn.EPI_RESIDUAL
+    outs = []
+    old = Fn.GEN_BWD_SRC_ATOMIC
+    try:
+        for atomic in (True, False):
+            Fn.GEN_BWD_SRC_ATOMIC = atomic
+            x, a, pp, q, ee = (v.clone().requires_grad_() for v in (x0, a0, p0, q0, e0))
+            t = torch.tensor([0.9], device=DEV, requires_grad=True)
+            sc = torch.tensor([1.3], device=DEV, requires_grad=True) if epi == "msgnorm" else None
+            if affine:
+                h = Fn.GenAggregateAffine.apply(x, a, pp, q, t, 1.0, None, sc, topo, "softmax", 1e-7, code, True)
+                leaves = [x, pp, q, t] + ([a] if edge_grad else [])
+            else:
+                h = Fn.GenAggregate.apply(x, ee, t, 1.0, None, sc, topo, "softmax", 1e-7, code, True)
+                leaves = [x, t] + ([ee] if edge_grad else [])
+            if sc is not None:
+                leaves.append(sc)
+            outs.append(torch.autograd.grad((h * Rm).sum(), leaves))
+    finally:
+        Fn.GEN_BWD_SRC_ATOMIC = old
+    for i, (u, v) in enumerate(zip(*outs)):
+        assert_close(u, v, rtol=1e-4, atol=2e-6 * max(1.0, float(v.abs().max())), what="grad[%d]" % i)
+
+
 @pytest.mark.parametrize("C", [128, 64, 32, 20, 256])
 def test_gather_sum_hub_rows(mlg, C):
     """Rows far longer than the mean (hubs of a by-source kNN CSR) are walked by the whole block: same sums as a
