@@ -791,8 +791,22 @@ __global__ void __launch_bounds__(kRingWarps * 32) gen_fwd_ring_kernel(const Gen
 // g_edge (streaming stores).  Per-block partials as gen_bwd_kernel: (d/dt, d/dy_raw, d/dmsg_scale) and, for AFF with
 // pq_part, the sums of (a_e * g_edge, g_edge) over the block's edges.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void red_add4(float* p, float4 v) {
-  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+__device__ __forceinline__ void red_add4(float* p, float4 v, unsigned long long pol) {
+  asm volatile("red.global.add.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z),
+               "f"(v.w), "l"(pol)
+               : "memory");
+}
+__device__ __forceinline__ float4 ld_pol4(const float* p, unsigned long long pol) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(p), "l"(pol));
+  return r;
+}
+__device__ __forceinline__ void st_pol4(float* p, float4 v, unsigned long long pol) {
+  asm volatile("st.global.L1::no_allocate.L2::cache_hint.v4.f32 [%0], {%1,%2,%3,%4}, %5;" ::"l"(p), "f"(v.x), "f"(v.y),
+               "f"(v.z), "f"(v.w), "l"(pol)
+               : "memory");
 }
 
 // P.src_sum: the source-side sum g_x[j] += sum over out-edges (j -> i) of g_edge is done HERE with 16-byte vector reductions
@@ -800,7 +814,40 @@ __device__ __forceinline__ void red_add4(float* p, float4 v) {
 // the speed of a plain read-modify-write) instead of a second kernel that reads all of g_edge [E, H] again; with the affine
 // edge term g_edge is then not written at all.  The order of the additions is not reproducible (as in the reference's own
 // scatter-add backward); the two-pass path stays available (functional.GEN_BWD_SRC_ATOMIC = False).
-template <int NV, bool AFF>
+// L2 residency: x (gathered) and g_x (reduced into) are the re-used 2 x 4 n H bytes; everything else -- e, g_edge, and the
+// g / m / aux rows -- passes through once.  The first capture of this kernel (profiles/r02_genbwd_raw.csv: 1.75 GB read +
+// 1.18 GB written against 1.07 + 0.87 GB algorithmic) showed the streams evicting g_x / x lines, every reduction on an
+// evicted line costing a DRAM fill and a write-back; hence evict_last on the gathers / reductions and evict_first on all
+// streams.
+// The per-edge loop is instruction-issue bound (first capture, profiles/r02_genaffb_raw.csv: 162 warp instructions per
+// edge, 68 % issue-active, DRAM at 1 TB/s): the element-wise chain runs on PAIRS of channels with the packed fp32
+// instructions of sm_100 (fma / add / mul .rn.f32x2 = FFMA2 / FADD2 / FMUL2: one issue slot for two IEEE-identical
+// results), the run-time switches (source-side sum, g_edge wanted, learn_t) are template parameters, and the edge stream
+// is walked as plain nested loops (rows, then the row's entries; one group test per entry).
+typedef unsigned long long u64;
+__device__ __forceinline__ u64 pk2(float lo, float hi) {
+  u64 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void upk2(u64 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) {
+  u64 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ u64 add2(u64 a, u64 b) {
+  u64 r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ u64 mul2(u64 a, u64 b) {
+  u64 r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+
+template <int NV, bool AFF, bool SRC, bool EDGE, bool LEARN>
 __global__ void __launch_bounds__(kRingWarps * 32) gen_bwd_ring_kernel(const GenP P) {
   extern __shared__ __align__(16) unsigned char ring_raw[];
   __shared__ float red[3 * 32];
@@ -811,34 +858,45 @@ __global__ void __launch_bounds__(kRingWarps * 32) gen_bwd_ring_kernel(const Gen
   constexpr unsigned kSlotBytes = (AFF ? 1 : 2) * NV * 512;
   const unsigned sbase = (unsigned)__cvta_generic_to_shared(ring_raw) + wib * kDepth * kSlotBytes + lane * 16;
   float acc[3] = {0.f, 0.f, 0.f};
-  float su[NV][4], sv[NV][4];   // AFF: sums over this warp's edges of a_e * g_edge and g_edge
+  u64 acc0p = 0ull;              // learn_t: (even, odd) channel halves of the d/dt sum
+  u64 su2[NV][2], sv2[NV][2];    // AFF: sums over this warp's edges of a_e * g_edge and g_edge
 #pragma unroll
-  for (int v = 0; v < NV; ++v)
-#pragma unroll
-    for (int k = 0; k < 4; ++k) su[v][k] = sv[v][k] = 0.f;
+  for (int v = 0; v < NV; ++v) su2[v][0] = su2[v][1] = sv2[v][0] = sv2[v][1] = 0ull;
 
   if (r0 < P.n) {
     const int r1 = (int)min((long long)P.n, r0 + kRPW);
-    unsigned long long pol_stream;
+    unsigned long long pol_stream, pol_keep;
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_stream));
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_keep));
     const int rp = __ldg(P.rowptr + min((long long)P.n, r0 + min(lane, kRPW)));
     const int qb = __shfl_sync(0xffffffffu, rp, 0);
     const int qe = __shfl_sync(0xffffffffu, rp, r1 - (int)r0);
-    const int* eidp = P.eid;
-    const bool learn = P.learn != 0;
+    // kernel parameters used inside the edge loop, read once
+    const int* const eidp = P.eid;
+    const int* const colp = P.col;
+    const float* const eap = P.ea;
+    float* const gedge = P.g_edge;
+    float* const gxp = P.g_x;
+    const float* const gp = P.g;
+    const float* const mp = P.m_in;
+    const float* const auxp = P.aux_in;
+    const int epi = P.epi;
+    const bool has_y = P.y_dev != nullptr;
     const float t = P.t_dev ? __ldg(P.t_dev) : P.t;
-    const float tl2 = t * MLG_LOG2E;
     const float eps = P.eps;
+    const u64 t2 = pk2(t, t), tl2 = pk2(t * MLG_LOG2E, t * MLG_LOG2E), eps2 = pk2(eps, eps), one2 = pk2(1.f, 1.f);
     float ysig = 0.f;
-    if (P.y_dev) ysig = sigmoidf_(__ldg(P.y_dev));
+    if (has_y) ysig = sigmoidf_(__ldg(P.y_dev));
+    const float msg_scale = epi == MLG_EPI_MSGNORM ? __ldg(P.scale_dev) : 0.f;
     const float* xc = P.x + lane * 4;
     const float* ec = AFF ? nullptr : P.e + lane * 4;
-    float4 pv[NV], qv[NV];
+    u64 pv2[NV][2], qv2[NV][2];
     if (AFF) {
 #pragma unroll
       for (int v = 0; v < NV; ++v) {
-        pv[v] = ld_gather4(P.ep + lane * 4 + v * 128);
-        qv[v] = ld_gather4(P.eq + lane * 4 + v * 128);
+        const float4 pp = ld_gather4(P.ep + lane * 4 + v * 128), qq = ld_gather4(P.eq + lane * 4 + v * 128);
+        pv2[v][0] = pk2(pp.x, pp.y); pv2[v][1] = pk2(pp.z, pp.w);
+        qv2[v][0] = pk2(qq.x, qq.y); qv2[v][1] = pk2(qq.z, qq.w);
       }
     }
     const int n_groups = (qe - qb + kGroup - 1) / kGroup;
@@ -848,7 +906,7 @@ __global__ void __launch_bounds__(kRingWarps * 32) gen_bwd_ring_kernel(const Gen
 #pragma unroll
       for (int u = 0; u < kGroup; ++u) {
         const int q = min(qb + g * kGroup + u, qe - 1);
-        nxt_s[u] = (unsigned)__ldg(P.col + q);
+        nxt_s[u] = (unsigned)__ldg(colp + q);
         nxt_e[u] = eidp ? (unsigned)__ldg(eidp + q) : (unsigned)q;
       }
     };
@@ -860,7 +918,7 @@ __global__ void __launch_bounds__(kRingWarps * 32) gen_bwd_ring_kernel(const Gen
           const unsigned slot = slot0 + u * kSlotBytes;
 #pragma unroll
           for (int v = 0; v < NV; ++v) {
-            cp_async16_plain(slot + v * 512, row_ptr(xc, nxt_s[u], H) + v * 128);
+            cp_async16_pol(slot + v * 512, row_ptr(xc, nxt_s[u], H) + v * 128, pol_keep);
             if (!AFF) cp_async16_pol(slot + (NV + v) * 512, row_ptr(ec, nxt_e[u], H) + v * 128, pol_stream);
           }
         }
@@ -872,126 +930,126 @@ __global__ void __launch_bounds__(kRingWarps * 32) gen_bwd_ring_kernel(const Gen
 #pragma unroll
     for (int i = 0; i < kGroups - 1; ++i) issue(i);
 
-    // ---- per-row state ----
-    int row = (int)r0;
-    int rend = __shfl_sync(0xffffffffu, rp, 1);
-    int rbeg = qb;
-    float gin[NV][4], oi[NV][4], au[NV][4];
-    auto begin_row = [&]() {
-      const int deg = rend - rbeg;
-      float degpow = 1.f, ycoef = 0.f;
-      if (P.y_dev) {
-        degpow = powf((float)deg, ysig);
-        ycoef = deg > 0 ? logf((float)deg) * ysig * (1.f - ysig) : 0.f;
-      }
-      float4 gr[NV], mr[NV], xr[NV];
-#pragma unroll
-      for (int v = 0; v < NV; ++v) {
-        const unsigned off = lane * 4 + v * 128;
-        gr[v] = ld_gather4(row_ptr(P.g, (unsigned)row, H) + off);
-        mr[v] = ld_gather4(row_ptr(P.m_in, (unsigned)row, H) + off);
-        const float4 a = ld_gather4(row_ptr(P.aux_in, (unsigned)row, H) + off);
-        au[v][0] = a.x; au[v][1] = a.y; au[v][2] = a.z; au[v][3] = a.w;
-        xr[v] = (P.epi == MLG_EPI_MSGNORM) ? ld_gather4(row_ptr(P.x, (unsigned)row, H) + off) : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-      float f_gm = 1.f, f_u = 0.f, f_x = 0.f;   // g_m = f_gm * g - f_u * m ; g_x = g + f_x * x
-      if (P.epi == MLG_EPI_MSGNORM) {
-        float sx2 = 0.f, sm2 = 0.f, sgm = 0.f;
+    for (int row = (int)r0; row < r1; ++row) {
+      const int rbeg = __shfl_sync(0xffffffffu, rp, row - (int)r0);
+      const int rend = __shfl_sync(0xffffffffu, rp, row - (int)r0 + 1);
+      // ---- per-row state: MsgNorm statistics, the direct term into g_x, and (gin, -oi, -aux) for the row's edges ----
+      u64 gin2[NV][2], noi2[NV][2], nau2[NV][2];
+      {
+        const int deg = rend - rbeg;
+        float degpow = 1.f, ycoef = 0.f;
+        if (has_y) {
+          degpow = powf((float)deg, ysig);
+          ycoef = deg > 0 ? logf((float)deg) * ysig * (1.f - ysig) : 0.f;
+        }
+        float4 gr[NV], mr[NV], xr[NV], ar[NV];
 #pragma unroll
         for (int v = 0; v < NV; ++v) {
-          sx2 += xr[v].x * xr[v].x + xr[v].y * xr[v].y + xr[v].z * xr[v].z + xr[v].w * xr[v].w;
-          sm2 += mr[v].x * mr[v].x + mr[v].y * mr[v].y + mr[v].z * mr[v].z + mr[v].w * mr[v].w;
-          sgm += gr[v].x * mr[v].x + gr[v].y * mr[v].y + gr[v].z * mr[v].z + gr[v].w * mr[v].w;
+          const unsigned off = lane * 4 + v * 128;
+          gr[v] = ld_pol4(row_ptr(gp, (unsigned)row, H) + off, pol_stream);
+          mr[v] = ld_pol4(row_ptr(mp, (unsigned)row, H) + off, pol_stream);
+          ar[v] = ld_pol4(row_ptr(auxp, (unsigned)row, H) + off, pol_stream);
+          xr[v] = (epi == MLG_EPI_MSGNORM) ? ld_gather4(row_ptr(P.x, (unsigned)row, H) + off) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        sx2 = warp_sum(sx2);
-        sm2 = warp_sum(sm2);
-        sgm = warp_sum(sgm);
-        const float s = __ldg(P.scale_dev);
-        const float r = sqrtf(sx2), nm = sqrtf(sm2);
-        const float nn = fmaxf(nm, 1e-12f);
-        const float dot = sgm / nn;
-        f_gm = s * r / nn;
-        f_u = (nm >= 1e-12f) ? f_gm * dot / nn : 0.f;
-        f_x = (r > 0.f) ? s * dot / r : 0.f;
-        if (lane == 0) acc[2] += dot * r;
+        float f_gm = 1.f, f_u = 0.f, f_x = 0.f;   // g_m = f_gm * g - f_u * m ; g_x = g + f_x * x
+        if (epi == MLG_EPI_MSGNORM) {
+          float sx2 = 0.f, sm2 = 0.f, sgm = 0.f;
+#pragma unroll
+          for (int v = 0; v < NV; ++v) {
+            sx2 += xr[v].x * xr[v].x + xr[v].y * xr[v].y + xr[v].z * xr[v].z + xr[v].w * xr[v].w;
+            sm2 += mr[v].x * mr[v].x + mr[v].y * mr[v].y + mr[v].z * mr[v].z + mr[v].w * mr[v].w;
+            sgm += gr[v].x * mr[v].x + gr[v].y * mr[v].y + gr[v].z * mr[v].z + gr[v].w * mr[v].w;
+          }
+          sx2 = warp_sum(sx2);
+          sm2 = warp_sum(sm2);
+          sgm = warp_sum(sgm);
+          const float r = sqrtf(sx2), nm = sqrtf(sm2);
+          const float nn = fmaxf(nm, 1e-12f);
+          const float dot = sgm / nn;
+          f_gm = msg_scale * r / nn;
+          f_u = (nm >= 1e-12f) ? f_gm * dot / nn : 0.f;
+          f_x = (r > 0.f) ? msg_scale * dot / r : 0.f;
+          if (lane == 0) acc[2] += dot * r;
+        }
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+          const unsigned off = lane * 4 + v * 128;
+          const float g4[4] = {gr[v].x, gr[v].y, gr[v].z, gr[v].w};
+          const float m4[4] = {mr[v].x, mr[v].y, mr[v].z, mr[v].w};
+          const float x4[4] = {xr[v].x, xr[v].y, xr[v].z, xr[v].w};
+          float gx[4], gi[4], oi[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            gx[k] = epi == MLG_EPI_NONE ? 0.f : (epi == MLG_EPI_RESIDUAL ? g4[k] : fmaf(f_x, x4[k], g4[k]));
+            const float gm = (epi == MLG_EPI_MSGNORM) ? (f_gm * g4[k] - f_u * m4[k]) : g4[k];
+            if (has_y) acc[1] = fmaf(gm * m4[k], ycoef, acc[1]);
+            gi[k] = gm * degpow;
+            oi[k] = (has_y && deg > 0) ? m4[k] / degpow : m4[k];
+          }
+          gin2[v][0] = pk2(gi[0], gi[1]); gin2[v][1] = pk2(gi[2], gi[3]);
+          noi2[v][0] = pk2(-oi[0], -oi[1]); noi2[v][1] = pk2(-oi[2], -oi[3]);
+          nau2[v][0] = pk2(-ar[v].x, -ar[v].y); nau2[v][1] = pk2(-ar[v].z, -ar[v].w);
+          if (!SRC) st4(row_ptr(gxp, (unsigned)row, H) + off, make_float4(gx[0], gx[1], gx[2], gx[3]));
+          else if (epi != MLG_EPI_NONE) red_add4(row_ptr(gxp, (unsigned)row, H) + off, make_float4(gx[0], gx[1], gx[2], gx[3]), pol_keep);
+        }
       }
-#pragma unroll
-      for (int v = 0; v < NV; ++v) {
-        const unsigned off = lane * 4 + v * 128;
-        const float g4[4] = {gr[v].x, gr[v].y, gr[v].z, gr[v].w};
-        const float m4[4] = {mr[v].x, mr[v].y, mr[v].z, mr[v].w};
-        const float x4[4] = {xr[v].x, xr[v].y, xr[v].z, xr[v].w};
-        float gx[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          gx[k] = P.epi == MLG_EPI_NONE ? 0.f : (P.epi == MLG_EPI_RESIDUAL ? g4[k] : fmaf(f_x, x4[k], g4[k]));
-          const float gm = (P.epi == MLG_EPI_MSGNORM) ? (f_gm * g4[k] - f_u * m4[k]) : g4[k];
-          if (P.y_dev) acc[1] = fmaf(gm * m4[k], ycoef, acc[1]);
-          gin[v][k] = gm * degpow;
-          oi[v][k] = (P.y_dev && deg > 0) ? m4[k] / degpow : m4[k];
+      // ---- the row's edges ----
+      for (int q = rbeg; q < rend; ++q) {
+        const int rel = q - qb;
+        if ((rel & (kGroup - 1)) == 0) {
+          issue(rel / kGroup + kGroups - 1);
+          asm volatile("cp.async.wait_group %0;" ::"n"(kGroups - 1) : "memory");
         }
-        if (!P.src_sum) st4(row_ptr(P.g_x, (unsigned)row, H) + off, make_float4(gx[0], gx[1], gx[2], gx[3]));
-        else if (P.epi != MLG_EPI_NONE) red_add4(row_ptr(P.g_x, (unsigned)row, H) + off, make_float4(gx[0], gx[1], gx[2], gx[3]));
-      }
-    };
-    begin_row();
-    for (int g = 0; g < n_groups; ++g) {
-      issue(g + kGroups - 1);
-      asm volatile("cp.async.wait_group %0;" ::"n"(kGroups - 1) : "memory");
-      const unsigned slot0 = sbase + (unsigned)((g % kGroups) * kGroup) * kSlotBytes;
-      const int q0 = qb + g * kGroup;
-#pragma unroll
-      for (int u = 0; u < kGroup; ++u) {
-        const int q = q0 + u;
-        if (q >= qe) break;
-        while (q >= rend) {   // next row (also walks over rows without edges: their g_x still has to be written)
-          ++row;
-          rbeg = rend;
-          rend = __shfl_sync(0xffffffffu, rp, row - (int)r0 + 1);
-          begin_row();
-        }
+        const unsigned slot = sbase + (unsigned)(rel & (kDepth - 1)) * kSlotBytes;
         const unsigned eo = eidp ? (unsigned)__ldg(eidp + q) : (unsigned)q;   // uniform, L1-resident (fetched at issue time)
-        const unsigned src = P.src_sum ? (unsigned)__ldg(P.col + q) : 0u;
-        const float a_e = AFF ? __ldg(P.ea + eo) : 0.f;
-        const unsigned slot = slot0 + u * kSlotBytes;
+        const unsigned src = SRC ? (unsigned)__ldg(colp + q) : 0u;
+        const float a_e = AFF ? __ldg(eap + eo) : 0.f;
+        const u64 a2 = pk2(a_e, a_e);
 #pragma unroll
         for (int v = 0; v < NV; ++v) {
           const float4 xv = lds128(slot + v * 512);
-          float4 ev;
-          if (AFF) ev = make_float4(fmaf(a_e, pv[v].x, qv[v].x), fmaf(a_e, pv[v].y, qv[v].y), fmaf(a_e, pv[v].z, qv[v].z),
-                                    fmaf(a_e, pv[v].w, qv[v].w));
-          else ev = lds128(slot + (NV + v) * 512);
-          const float pre[4] = {xv.x + ev.x, xv.y + ev.y, xv.z + ev.z, xv.w + ev.w};
+          float4 ev4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (!AFF) ev4 = lds128(slot + (NV + v) * 512);
+          const u64 x2[2] = {pk2(xv.x, xv.y), pk2(xv.z, xv.w)};
           float ge[4];
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const float val = fmaxf(pre[k], 0.f) + eps;
-            const float w = ex2_approx(fmaf(val, tl2, -au[v][k]));
-            const float gwt = gin[v][k] * w;
-            float gv = gwt;
-            if (learn) {
-              const float dv = val - oi[v][k];
-              gv = gwt * fmaf(t, dv, 1.f);
-              acc[0] = fmaf(gwt * val, dv, acc[0]);
+          for (int j = 0; j < 2; ++j) {
+            const u64 e2 = AFF ? fma2(a2, pv2[v][j], qv2[v][j]) : (j == 0 ? pk2(ev4.x, ev4.y) : pk2(ev4.z, ev4.w));
+            const u64 pre2 = add2(x2[j], e2);
+            float p0, p1;
+            upk2(pre2, p0, p1);
+            const u64 val2 = add2(pk2(fmaxf(p0, 0.f), fmaxf(p1, 0.f)), eps2);
+            float a0, a1;
+            upk2(fma2(val2, tl2, nau2[v][j]), a0, a1);
+            const u64 gwt2 = mul2(gin2[v][j], pk2(ex2_approx(a0), ex2_approx(a1)));
+            u64 gv2 = gwt2;
+            if (LEARN) {
+              const u64 dv2 = add2(val2, noi2[v][j]);
+              gv2 = mul2(gwt2, fma2(t2, dv2, one2));
+              acc0p = fma2(mul2(gwt2, val2), dv2, acc0p);
             }
-            ge[k] = pre[k] > 0.f ? gv : 0.f;
+            float g0, g1;
+            upk2(gv2, g0, g1);
+            ge[2 * j] = p0 > 0.f ? g0 : 0.f;
+            ge[2 * j + 1] = p1 > 0.f ? g1 : 0.f;
             if (AFF) {
-              su[v][k] = fmaf(a_e, ge[k], su[v][k]);
-              sv[v][k] += ge[k];
+              const u64 ge2 = pk2(ge[2 * j], ge[2 * j + 1]);
+              su2[v][j] = fma2(a2, ge2, su2[v][j]);
+              sv2[v][j] = add2(sv2[v][j], ge2);
             }
           }
-          if (P.g_edge) st_stream4(row_ptr(P.g_edge, eo, H) + lane * 4 + v * 128, make_float4(ge[0], ge[1], ge[2], ge[3]));
-          if (P.src_sum) red_add4(row_ptr(P.g_x, src, H) + lane * 4 + v * 128, make_float4(ge[0], ge[1], ge[2], ge[3]));
+          const float4 ge4 = make_float4(ge[0], ge[1], ge[2], ge[3]);
+          if (EDGE) st_pol4(row_ptr(gedge, eo, H) + lane * 4 + v * 128, ge4, pol_stream);
+          if (SRC) red_add4(row_ptr(gxp, src, H) + lane * 4 + v * 128, ge4, pol_keep);
         }
       }
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
-    while (row + 1 < r1) {   // trailing rows without edges
-      ++row;
-      rbeg = rend;
-      rend = __shfl_sync(0xffffffffu, rp, row - (int)r0 + 1);
-      begin_row();
-    }
+  }
+  if (LEARN) {
+    float lo, hi;
+    upk2(acc0p, lo, hi);
+    acc[0] = lo + hi;
   }
 
   if (AFF && P.pq_part) {   // block sums in warp order: reuse the (now idle) ring as [warps][2][H]
@@ -1000,9 +1058,13 @@ __global__ void __launch_bounds__(kRingWarps * 32) gen_bwd_ring_kernel(const Gen
 #pragma unroll
     for (int v = 0; v < NV; ++v)
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        stage[(size_t)wib * 2 * H + lane * 4 + v * 128 + k] = su[v][k];
-        stage[(size_t)wib * 2 * H + H + lane * 4 + v * 128 + k] = sv[v][k];
+      for (int j = 0; j < 2; ++j) {
+        float s0, s1, t0, t1;
+        upk2(su2[v][j], s0, s1);
+        upk2(sv2[v][j], t0, t1);
+        const size_t o = (size_t)wib * 2 * H + lane * 4 + v * 128 + 2 * j;
+        stage[o] = s0; stage[o + 1] = s1;
+        stage[o + H] = t0; stage[o + H + 1] = t1;
       }
     __syncthreads();
     for (unsigned j = threadIdx.x; j < 2 * H; j += kRingWarps * 32) {
@@ -1032,18 +1094,28 @@ inline bool ring_bwd_ok(const GenP& P) {
 }
 inline long long ring_grid(long long n) { return (n + kRingWarps * kRPW - 1) / (kRingWarps * kRPW); }
 
-template <int NV, bool AFF>
-int launch_ring_bwd(const GenP& P, cudaStream_t st) {
+template <int NV, bool AFF, bool SRC, bool EDGE, bool LEARN>
+int launch_ring_bwd_k(const GenP& P, cudaStream_t st) {
   int smem = kRingWarps * kDepth * (AFF ? 1 : 2) * NV * 512;
   const int stage = kRingWarps * 2 * (int)P.H * 4;      // the pq block sums reuse the ring
   if (AFF && P.pq_part && stage > smem) smem = stage;
   static bool attr = false;
   if (!attr) {
-    MLG_CUDA(cudaFuncSetAttribute(gen_bwd_ring_kernel<NV, AFF>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    MLG_CUDA(cudaFuncSetAttribute(gen_bwd_ring_kernel<NV, AFF, SRC, EDGE, LEARN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  64 * 1024));
     attr = true;
   }
-  gen_bwd_ring_kernel<NV, AFF><<<(unsigned)ring_grid(P.n), kRingWarps * 32, smem, st>>>(P);
+  gen_bwd_ring_kernel<NV, AFF, SRC, EDGE, LEARN><<<(unsigned)ring_grid(P.n), kRingWarps * 32, smem, st>>>(P);
   return MLG_OK;
+}
+template <int NV, bool AFF, bool SRC, bool EDGE>
+int launch_ring_bwd_l(const GenP& P, cudaStream_t st) {
+  return P.learn ? launch_ring_bwd_k<NV, AFF, SRC, EDGE, true>(P, st) : launch_ring_bwd_k<NV, AFF, SRC, EDGE, false>(P, st);
+}
+template <int NV, bool AFF>
+int launch_ring_bwd(const GenP& P, cudaStream_t st) {
+  if (!P.src_sum) return launch_ring_bwd_l<NV, AFF, false, true>(P, st);
+  return P.g_edge ? launch_ring_bwd_l<NV, AFF, true, true>(P, st) : launch_ring_bwd_l<NV, AFF, true, false>(P, st);
 }
 
 struct Cfg {

@@ -1,0 +1,9 @@
+#!/bin/bash
+cd "$(dirname "$0")/.."
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests -m gpu -q -p no:cacheprovider -k "genconv or gen_ or deepergcn or affine" 2>&1 | tail -3
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:'gen_bwd_ring' -s 4 -c 1 \
+    -o /tmp/r02_genaffb python tools/bench_components.py --only deepergcn --quick > gpurun_out/r02_ncu_genaffb.log 2>&1
+echo "ncu rc=$?"
+ncu -i /tmp/r02_genaffb.ncu-rep --page raw --csv > gpurun_out/r02_genaffb2_raw.csv 2>/dev/null
+ncu -i /tmp/r02_genaffb.ncu-rep --page source --csv 2>/dev/null | gzip -9 > gpurun_out/r02_genaffb2_source.csv.gz

@@ -105,8 +105,10 @@ def gemm(a):
         A = torch.randn(M, K, device=DEV).bfloat16()
         B = torch.randn(N, K, device=DEV).bfloat16()
         C = torch.empty(M, N, device=DEV)
-        run = lambda: _cabi.check(L.mlg_gemm_bf16(ctypes.c_void_p(A.data_ptr()), K, 0, ctypes.c_void_p(B.data_ptr()), K, 0,
-                                                  _cabi.fptr(C), N, 0, M, N, K, 1, 1.0, _cabi.stream_ptr()), "mlg_gemm_bf16")
+        ws = torch.zeros(L.mlg_gemm_bf16_workspace_bytes(), dtype=torch.uint8, device=DEV)
+        run = lambda: _cabi.check(L.mlg_gemm_bf16_ws(ctypes.c_void_p(A.data_ptr()), K, 0, ctypes.c_void_p(B.data_ptr()), K, 0,
+                                                     _cabi.fptr(C), N, 0, M, N, K, 1, 1.0, ctypes.c_void_p(ws.data_ptr()),
+                                                     ws.numel(), _cabi.stream_ptr()), "mlg_gemm_bf16_ws")
         ms = timeit(run, reps=10, warm=2)
         ref = timeit(lambda: torch.matmul(A, B.t()), reps=10, warm=2)
         tf = 2.0 * M * N * K / ms / 1e9
