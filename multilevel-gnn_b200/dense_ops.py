@@ -9,7 +9,9 @@ meet fp32 rtol 1e-4 and is never used for parity runs at the reference's shapes.
 """
 import torch
 
-TENSOR_CORE_MIN = 1024      # smallest M, N and K for which the tensor-core path is taken
+TENSOR_CORE_MIN = 512       # smallest M, N and K for which the tensor-core path is taken (the second pooling layer of the
+                            # N = 10 000 shape has 2 500 nodes -> 625 clusters)
+LINEAR_MIN_FEATURES = 256   # nn.Linear projections: tensor cores from this width on (with >= TENSOR_CORE_MIN rows)
 FORCE_FP32 = False          # parity switch: keep everything on the fp32 library path
 
 
@@ -26,3 +28,20 @@ def matmul(a, b):
         from . import gemm
         return gemm.matmul_bf16(a, b)
     return torch.matmul(a, b)
+
+
+def linear(x, lin):
+    """``lin(x)`` for an nn.Linear: on the tensor cores (bf16 operands, fp32 accumulate) in the same size regime as
+    ``matmul`` -- at N = 10 000 nodes the fp32 SIMT library GEMMs of the two DenseSAGEConv projections were 45 % of
+    the large DiffPool forward -- and the module itself below it."""
+    rows = x.numel() // x.shape[-1]
+    if (not FORCE_FP32 and x.is_cuda and lin.weight.is_cuda and not lin._forward_hooks
+            and rows >= TENSOR_CORE_MIN and min(lin.in_features, lin.out_features) >= LINEAR_MIN_FEATURES):
+        from . import gemm
+        return gemm.linear_bf16(x, lin.weight, lin.bias)
+    return lin(x)
+
+
+def operand_cache():
+    from . import gemm
+    return gemm.operand_cache()

@@ -15,8 +15,40 @@ def _pad8(n):
     return (n + 7) // 8 * 8
 
 
+_OPERANDS = None     # {key: (source tensor kept alive, bf16 operand, ld)} while an operand_cache() block is open
+
+
+class operand_cache:
+    """``with gemm.operand_cache():`` -- inside the block the K-major bf16 copy of an fp32 operand is made once per
+    (tensor, version, orientation) and shared by every product that reads it: DiffPool multiplies the SAME adjacency
+    four times per layer (A.X for the assignment and the embedding conv, S^T.A, and A's transpose in backward), and each
+    cast of a 10 000 x 10 000 matrix is a 600 MB pass.  Re-entrant; the copies are dropped when the outermost block ends."""
+
+    def __enter__(self):
+        global _OPERANDS
+        self.outer = _OPERANDS
+        if _OPERANDS is None:
+            _OPERANDS = {}
+        return self
+
+    def __exit__(self, *exc):
+        global _OPERANDS
+        _OPERANDS = self.outer
+        return False
+
+
 def _cast(src, transpose):
     """fp32 [b, R, C] (rows contiguous) -> bf16 K-major [b, R, ld] (or [b, C, ld] when transposed)."""
+    if _OPERANDS is not None:
+        key = (src.data_ptr(), tuple(src.shape), tuple(src.stride()), src._version, bool(transpose))
+        hit = _OPERANDS.get(key)
+        if hit is None:
+            hit = _OPERANDS[key] = (src,) + _cast_now(src, transpose)
+        return hit[1], hit[2]
+    return _cast_now(src, transpose)
+
+
+def _cast_now(src, transpose):
     L = _cabi.lib()
     b, R, C = src.shape
     rows, cols = (C, R) if transpose else (R, C)
@@ -112,3 +144,37 @@ def matmul_bf16(a, b):
     if a.dim() > 3 or b.dim() > 3:
         raise NotImplementedError("matmul_bf16 handles 2-D / 3-D operands")
     return _MatmulBf16.apply(a, b)
+
+
+class _LinearBf16(torch.autograd.Function):
+    """x [..., K] @ w[N, K]^T: the weight is already K-major, so neither operand is transposed on the way in."""
+
+    @staticmethod
+    def forward(ctx, x, w):
+        _cabi.require_cuda(x, w)
+        ctx.save_for_backward(x, w)
+        x3 = _as3(x.detach()).float()
+        x3 = x3 if x3.stride(2) == 1 and x3.stride(1) >= x3.shape[2] else x3.contiguous()
+        w3 = w.detach().float().contiguous().unsqueeze(0)
+        rows = x3.shape[0] * x3.shape[1]
+        x2 = x3.reshape(1, rows, x3.shape[2])
+        a_bf, lda = _cast(x2, False)
+        b_bf, ldb = _cast(w3, False)
+        out = _gemm_tn(a_bf, lda, b_bf, ldb, rows, w.shape[0], x3.shape[2], 1, False, False)
+        return out.reshape(*x.shape[:-1], w.shape[0])
+
+    @staticmethod
+    def backward(ctx, g):
+        x, w = ctx.saved_tensors
+        g2 = g.reshape(-1, g.shape[-1])
+        gx = gw = None
+        if ctx.needs_input_grad[0]:
+            gx = _mm(g2, w.detach())[0].reshape(x.shape)                       # [rows, N] @ [N, K]
+        if ctx.needs_input_grad[1]:
+            gw = _mm(g2.t(), x.detach().reshape(-1, x.shape[-1]))[0]           # [N, rows] @ [rows, K]
+        return gx, gw
+
+
+def linear_bf16(x, weight, bias=None):
+    out = _LinearBf16.apply(x, weight)
+    return out if bias is None else out + bias

@@ -26,12 +26,19 @@ class DenseSAGEConv(nn.Module):
         self.lin_rel = nn.Linear(in_channels, out_channels, bias=False)
         self.lin_root = nn.Linear(in_channels, out_channels, bias=bias)
 
-    def forward(self, x, adj, mask=None):
+    @staticmethod
+    def aggregate(x, adj):
+        """(A.X) / clamp(rowsum(A), 1): depends on the input only, so the assignment conv and the embedding conv of one
+        DiffPool layer (same x, same adj) share it."""
         x = x.unsqueeze(0) if x.dim() == 2 else x
         adj = adj.unsqueeze(0) if adj.dim() == 2 else adj
-        out = dense_ops.matmul(adj, x)
-        out = out / adj.sum(dim=-1, keepdim=True).clamp(min=1)
-        out = self.lin_rel(out) + self.lin_root(x)
+        return dense_ops.matmul(adj, x) / adj.sum(dim=-1, keepdim=True).clamp(min=1)
+
+    def forward(self, x, adj, mask=None, agg=None):
+        x = x.unsqueeze(0) if x.dim() == 2 else x
+        adj = adj.unsqueeze(0) if adj.dim() == 2 else adj
+        out = self.aggregate(x, adj) if agg is None else agg
+        out = dense_ops.linear(out, self.lin_rel) + dense_ops.linear(x, self.lin_root)
         if self.normalize:
             out = F.normalize(out, p=2.0, dim=-1)
         if mask is not None:
@@ -83,13 +90,14 @@ class SAGEConvolutions(nn.Module):
             self.bns.append(nn.BatchNorm1d(out_channels))
         self.layers.append(DenseSAGEConv(in_channels if num_layers == 1 else out_channels, out_channels, normalize=True))
 
-    def forward(self, x, adj, mask=None):
+    def forward(self, x, adj, mask=None, agg=None):
+        """``agg``: the first layer's neighbourhood mean when the caller already has it (DiffPoolLayer)."""
         for i in range(self.num_layers - 1):
-            x_new = F.relu(self.layers[i](x, adj, mask))
+            x_new = F.relu(self.layers[i](x, adj, mask, agg if i == 0 else None))
             b, n, c = x_new.size()
             x_new = self.bns[i](x_new.view(-1, c)).view(b, n, c)
             x = x + x_new if (self.residual and x.shape == x_new.shape) else x_new
-        return self.layers[self.num_layers - 1](x, adj, mask)
+        return self.layers[self.num_layers - 1](x, adj, mask, agg if self.num_layers == 1 else None)
 
 
 class DiffPoolLayer(nn.Module):
@@ -99,8 +107,9 @@ class DiffPoolLayer(nn.Module):
         self.gnn_embed = SAGEConvolutions(1, dim_input, dim_embedding)
 
     def forward(self, x, adj, mask=None):
-        s = self.gnn_pool(x, adj, mask)
-        x = self.gnn_embed(x, adj, mask)
+        agg = DenseSAGEConv.aggregate(x, adj)       # one A.X for both convs (the reference computes it twice)
+        s = self.gnn_pool(x, adj, mask, agg)
+        x = self.gnn_embed(x, adj, mask, agg)
         return dense_diff_pool(x, adj, s, mask)
 
 
@@ -168,9 +177,10 @@ class DiffPool(nn.Module):
             from .. import functional as Fn
             return Fn.DiffPoolFused.apply(x, adj, plan[0], *plan[1])
         l_total, e_total = 0, 0
-        for i in range(self.num_pooling_layers):
-            x, adj, l, e = self.diffpool_layers[i](x, adj, mask if i == 0 else None)
-            x = self.after_pool_layers[i](x, adj)
-            l_total = l_total + l
-            e_total = e_total + e
+        with dense_ops.operand_cache():      # one bf16 copy per operand and orientation for the whole forward
+            for i in range(self.num_pooling_layers):
+                x, adj, l, e = self.diffpool_layers[i](x, adj, mask if i == 0 else None)
+                x = self.after_pool_layers[i](x, adj)
+                l_total = l_total + l
+                e_total = e_total + e
         return x, l_total, e_total
