@@ -260,7 +260,31 @@ def genconv_microbench(dev, hbm_peak):
     ms = a.elapsed_time(b) / reps
     nbytes = 4 * H * (n * k + 2 * n) + 4 * n * k + 4 * (n + 1)
     gbs = nbytes / ms / 1e6
-    return {"kernel": "gen_fwd_ring_kernel<1> (GENConv softmax aggregation + MsgNorm + residual, N=100k, k=16, H=128)", "bound": "hbm",
+    # backward of the same call (edge + node + t + msg_scale gradients): forward + backward minus forward
+    xg, eg, tg, sg = (v.clone().requires_grad_() for v in (x, e, t, scale))
+    go = torch.randn(n, H, generator=g).to(dev)
+
+    def run_fb():
+        h = Fn.GenAggregate.apply(xg, eg, tg, 1.0, None, sg, topo, "softmax", 1e-7, Fn.EPI_MSGNORM, True)
+        return torch.autograd.grad(h, [xg, eg, tg, sg], go)
+
+    for _ in range(2):
+        run_fb()
+    torch.cuda.synchronize()
+    a.record()
+    for _ in range(10):
+        run_fb()
+    b.record()
+    torch.cuda.synchronize()
+    ms_b = a.elapsed_time(b) / 10 - ms
+    bbytes = 4 * H * (2 * n * k + 3 * n) + 8 * n * k
+    bwd = {"kernel": "gen_bwd_ring_kernel (source-side sum inside the kernel)", "ms": round(ms_b, 4), "bytes": bbytes,
+           "achieved": round(bbytes / ms_b / 1e6, 1), "peak": hbm_peak, "unit": "GB/s", "frac": round(bbytes / ms_b / 1e6 / hbm_peak, 4),
+           "traffic": ncu_traffic("gen_bwd_ring_kernel<1, 0, 1, 1, 1>"),
+           "note": "4H(2E+3N)+8E bytes; (forward+backward) - forward, 10 back-to-back repetitions"}
+    del xg, eg, go
+    return {"backward": bwd,
+            "kernel": "gen_fwd_ring_kernel<1> (GENConv softmax aggregation + MsgNorm + residual, N=100k, k=16, H=128)", "bound": "hbm",
             "achieved": round(gbs, 1), "peak": hbm_peak, "unit": "GB/s", "frac": round(gbs / hbm_peak, 4),
             "ms": round(ms, 4), "bytes": nbytes, "traffic": ncu_traffic("gen_fwd_ring_kernel<1>"),
             "note": "inputs 0.93 GB > L2; 20 back-to-back launches; training-mode forward (also writes m and the "

@@ -36,7 +36,7 @@ def genconv(a):
     n, k, H = a.n, a.k, a.H
     g = torch.Generator().manual_seed(0)
     pts = None
-    src = torch.randint(0, n, (n * k,), generator=g)
+    src = torch.randint(0, max(1, int(n * a.src_frac)), (n * k,), generator=g)   # --src-frac < 1: smaller gather / reduce hot set
     dst = torch.arange(n).repeat_interleave(k)
     ei = torch.stack([src, dst]).to(DEV)
     x = torch.randn(n, H, generator=g).to(DEV).requires_grad_()
@@ -127,6 +127,7 @@ if __name__ == "__main__":
     ap.add_argument("--B", type=int, default=32)
     ap.add_argument("--aggr", default="softmax")
     ap.add_argument("--bwd", action="store_true")
+    ap.add_argument("--src-frac", type=float, default=1.0)
     ap.add_argument("--generic", action="store_true")
     a = ap.parse_args()
     {"genconv": genconv, "sage": sage, "knn": knn, "gemm": gemm}[a.what](a)
