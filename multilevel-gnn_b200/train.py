@@ -8,8 +8,16 @@ over the flat fp32 gradient bucket followed by a replicated flat Adam.  Paramete
 gradient (``lin_l.weight`` of every SAGEConv, ``info_mask``) are left out of the bucket and of the
 optimizer state.
 """
+import os
+
 import torch
 import torch.distributed as dist
+
+# Chunks of the fused peer update.  2 = the classifier-head chunk is exchanged from inside backward (VERDICT r01 item 6); it
+# was built, is tested, and measured SLOWER than one kernel after backward: N=2 on one box, 20-step windows, 0.8755 ms with
+# two chunks against 0.8613 ms with one (single GPU 0.833 ms; 8 / 24 / 64 early blocks alike) -- the early kernel's blocks
+# share SMs with the persistent backward kernels, whose duration is set by their slowest CTA.  MLG_PEER_CHUNKS=2 selects it.
+PEER_CHUNKS = int(os.environ.get("MLG_PEER_CHUNKS", "1"))
 
 
 def shard_indices(n_items, rank, world, per_rank_batch, epoch_seed=0, drop_last=True):
@@ -237,7 +245,7 @@ class PeerAdam:
     def failed(self):
         return int(self.host_status[0]) != 0
 
-    EARLY_BLOCKS = 24      # grid cap of a chunk launched next to the backward kernels
+    EARLY_BLOCKS = int(os.environ.get("MLG_PEER_EARLY_BLOCKS", "24"))      # grid cap of a chunk launched next to the backward kernels
 
     def step(self, chunk=None):
         import ctypes
@@ -318,12 +326,13 @@ class Trainer:
                 raise RuntimeError("peer_update=True but the ranks do not all have CUDA peer access on one box")
             want_peer = False
         if want_peer:
-            # two chunks of the fused update: [classifier head] -- 62 % of the gbm parameters, gradients final right after the
-            # head's backward kernel, updated on a forked branch while the rest of backward runs -- and [everything else]
+            # PEER_CHUNKS = 2: two chunks of the fused update: [classifier head] -- 62 % of the gbm parameters, gradients final
+            # right after the head's backward kernel, updated on a forked branch while the rest of backward runs -- and
+            # [everything else].  Default 1: see PEER_CHUNKS.
             head_ids = {id(p) for n, p in model.named_parameters() if n.startswith("head.")}
             early = [p for p in self.params if id(p) in head_ids]
             late = [p for p in self.params if id(p) not in head_ids]
-            segments = [early, late] if (early and late) else [self.params]
+            segments = [early, late] if (early and late and PEER_CHUNKS >= 2) else [self.params]
             align = 4 * world_size
             self.early_params = early if len(segments) == 2 else []
             self.peer = PeerArena(GradBucket.padded_size(segments, align), world_size, dist.get_rank(), dev,
