@@ -43,6 +43,14 @@ constexpr int UN = MLG_GS_UN;   // entries in flight (single-graph path)
 #define MLG_GS_MINB 3
 #endif
 constexpr int RB = MLG_GS_RB;   // replicas in flight (replicated path)
+// CSR entries per step of the replicated kernel (per-replica source rows): JU entries' rows (JU x RB loads per lane) are
+// requested before the first FMA.  Measured at the gbm shape (one box, A/B libraries): JU = 2 (79 registers) 61.7 us vs 61.2 us
+// for JU = 1, step 0.829 ms either way; JU = 4 (121 registers, 2 blocks/SM) 70.4 us, step 0.850 ms -- the kernel is not
+// bound by the per-row chain of round trips, so the default stays 1.
+#ifndef MLG_GS_JU
+#define MLG_GS_JU 1
+#endif
+constexpr int JUX = MLG_GS_JU;
 
 struct GsP {
   const float* src;
@@ -257,7 +265,7 @@ template <int LANES, int VEC, bool RANK1, bool RED = false, bool AUX = false>
 __global__ void __launch_bounds__(kThreads, MLG_GS_MINB) gather_sum_rep_kernel(const GsP P, int gy) {
   constexpr int RPW = 32 / LANES;
   constexpr int CW = LANES * VEC;
-  constexpr int JU = RANK1 ? 2 : 1;   // entries per step
+  constexpr int JU = RANK1 ? 2 : JUX;   // entries per step
   const int lane = threadIdx.x & 31;
   const int sub = lane / LANES, sl = lane % LANES;
   const unsigned gmask = (LANES == 32) ? 0xffffffffu : (((1u << LANES) - 1u) << (sub * LANES));
@@ -341,18 +349,30 @@ __global__ void __launch_bounds__(kThreads, MLG_GS_MINB) gather_sum_rep_kernel(c
                 for (int k = 0; k < VEC; ++k) acc[r][k] = fmaf(f, xv[u][k], acc[r][k]);
               }
           } else {
-            const unsigned s = __shfl_sync(gmask, my_idx, j, LANES);
-            const float w = __shfl_sync(gmask, my_w, j, LANES);
-            float xv[RB][VEC];
-            // all RB row loads are issued before the first FMA (volatile asm keeps ptxas from re-using one pair of
+            unsigned s[JU];
+            float w[JU], xv[JU][RB][VEC];
+#pragma unroll
+            for (int u = 0; u < JU; ++u) {
+              const int jj = min(j + u, cnt - 1);     // past the end: re-request the last entry's rows (L1 hits), not added
+              s[u] = __shfl_sync(gmask, my_idx, jj, LANES);
+              w[u] = __shfl_sync(gmask, my_w, jj, LANES);
+            }
+            // all JU * RB row loads are issued before the first FMA (volatile asm keeps ptxas from re-using one pair of
             // registers for the loads, which serialised them into RB/2 round trips: ncu source page, r01)
-            const float* p0 = rowp(sc, (unsigned)b0 * P.rep_rows_src + s, P.ld_src);
 #pragma unroll
-            for (int r = 0; r < RB; ++r) ldv_now<VEC>(xv[r], p0 + (size_t)min(r, nb - 1) * rep_stride);
+            for (int u = 0; u < JU; ++u) {
+              const float* p0 = rowp(sc, (unsigned)b0 * P.rep_rows_src + s[u], P.ld_src);
 #pragma unroll
-            for (int r = 0; r < RB; ++r)
+              for (int r = 0; r < RB; ++r) ldv_now<VEC>(xv[u][r], p0 + (size_t)min(r, nb - 1) * rep_stride);
+            }
 #pragma unroll
-              for (int k = 0; k < VEC; ++k) acc[r][k] = fmaf(w, xv[r][k], acc[r][k]);
+            for (int u = 0; u < JU; ++u)      // entries in CSR order: the same sequence of FMAs for every JU
+              if (u == 0 || j + u < cnt) {
+#pragma unroll
+                for (int r = 0; r < RB; ++r)
+#pragma unroll
+                  for (int k = 0; k < VEC; ++k) acc[r][k] = fmaf(w[u], xv[u][r][k], acc[r][k]);
+              }
           }
         }
       }
