@@ -180,7 +180,7 @@ KERNEL_INFO = {
                "per launch: every source row once per CSR entry), not by DRAM"},
     "sage_rank1_fwd": {"ncu": ["sage_rank1_fwd_rows_kernel<2>"],
                        "alg": "4*C*B*N (output) + 4*B*N + 8*nnz + 8*C*N (tables), C = 64: 137 MB, write bound"},
-    "pool_bwd": {"ncu": ["pool_bwd_fused2_kernel<2, 1, 8>"], "alg": "2 * 4*C*B*N + 4*B*C*S*P: x read, g_x written, pooled gradient read"},
+    "pool_bwd": {"ncu": ["pool_bwd_fused2_kernel<2, 1, 4>", "pool_bwd_fused2_kernel<2, 1, 8>"], "alg": "2 * 4*C*B*N + 4*B*C*S*P: x read, g_x written, pooled gradient read"},
 }
 
 

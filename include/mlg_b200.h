@@ -266,6 +266,13 @@ int mlg_layernorm_fwd(const float* x, const float* gamma, const float* beta, int
 int mlg_layernorm_bwd(const float* x, const float* g, const float* gamma, const float* mean, const float* rstd,
                       int64_t rows, int64_t C, float* gx, float* dgamma, float* dbeta, void* workspace,
                       int64_t workspace_bytes, void* stream);
+/* The same norm followed by ReLU in one pass each way (deepergcn.py:268-270 `F.relu(norm(h))`, torch_nn.py MLP
+ * Lin -> norm -> act): y = max(LN(x), 0); bwd masks g where the output was not positive (rebuilt from xhat, gamma, beta). */
+int mlg_layernorm_relu_fwd(const float* x, const float* gamma, const float* beta, int64_t rows, int64_t C, float eps,
+                           float* y, float* mean, float* rstd, void* stream);
+int mlg_layernorm_relu_bwd(const float* x, const float* g, const float* gamma, const float* beta, const float* mean,
+                           const float* rstd, int64_t rows, int64_t C, float* gx, float* dgamma, float* dbeta,
+                           void* workspace, int64_t workspace_bytes, void* stream);
 
 /* GENConv aggregation with a rank-1 AFFINE edge term: message_ij = relu(x_j + a_e * p + q) + eps, a_e = edge_scalar[e]
  * (one number per edge), p = edge_p, q = edge_q ([H]).  Same semantics, epilogues and outputs as mlg_gen_aggr_fwd / _bwd

@@ -9,6 +9,10 @@
 //   y = (x - mean) * rstd * gamma + beta,   rstd = 1 / sqrt(var_biased + eps)
 //   gx = rstd * (dy - mean_c(dy) - xhat * mean_c(dy * xhat)),   dy = g * gamma
 // HBM-bound: forward 8*rows*C bytes, backward 12*rows*C.
+// RELU variants (mlg_layernorm_relu_fwd / _bwd): the ReLU that follows both norms (deepergcn.py:268-270 `F.relu(h1)`,
+// torch_nn.py MLP: Lin -> norm -> act) is applied in the same pass; backward rebuilds the mask from
+// xhat * gamma + beta > 0 (= output > 0, ATen's rule) instead of reading the activation: two elementwise passes over
+// [rows, C] per norm less (a ReLU forward and a threshold backward, 17-45 us each at 100 k rows).
 #include "common.cuh"
 #include "../../include/mlg_b200.h"
 
@@ -16,7 +20,7 @@ namespace {
 
 constexpr int kWarps = 8;
 
-template <int NV>   // C == 128 * NV: lane holds NV float4 at columns v*128 + lane*4
+template <int NV, bool RELU>   // C == 128 * NV: lane holds NV float4 at columns v*128 + lane*4
 __global__ void __launch_bounds__(kWarps * 32)
 ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta, long long rows,
               float eps, float* __restrict__ y, float* __restrict__ mean_out, float* __restrict__ rstd_out) {
@@ -44,8 +48,10 @@ ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, cons
   for (int i = 0; i < NV; ++i) {
     const float4 g = gamma ? ld_gather4(gamma + i * 128 + lane * 4) : make_float4(1.f, 1.f, 1.f, 1.f);
     const float4 b = beta ? ld_gather4(beta + i * 128 + lane * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-    st4(yr + i * 128, make_float4(fmaf((v[i].x - mean) * rstd, g.x, b.x), fmaf((v[i].y - mean) * rstd, g.y, b.y),
-                                  fmaf((v[i].z - mean) * rstd, g.z, b.z), fmaf((v[i].w - mean) * rstd, g.w, b.w)));
+    float4 o = make_float4(fmaf((v[i].x - mean) * rstd, g.x, b.x), fmaf((v[i].y - mean) * rstd, g.y, b.y),
+                           fmaf((v[i].z - mean) * rstd, g.z, b.z), fmaf((v[i].w - mean) * rstd, g.w, b.w));
+    if (RELU) o = make_float4(fmaxf(o.x, 0.f), fmaxf(o.y, 0.f), fmaxf(o.z, 0.f), fmaxf(o.w, 0.f));
+    st4(yr + i * 128, o);
   }
   if (lane == 0) {
     mean_out[row] = mean;
@@ -53,20 +59,21 @@ ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, cons
   }
 }
 
-template <int NV>
+template <int NV, bool RELU>
 __global__ void __launch_bounds__(kWarps * 32)
 ln_bwd_kernel(const float* __restrict__ x, const float* __restrict__ g, const float* __restrict__ gamma,
-              const float* __restrict__ mean_in, const float* __restrict__ rstd_in, long long rows,
+              const float* __restrict__ beta, const float* __restrict__ mean_in, const float* __restrict__ rstd_in, long long rows,
               float* __restrict__ gx, float* __restrict__ partial /* [gridDim.x][2][C] */) {
   constexpr int C = 128 * NV;
   extern __shared__ float stage[];   // [kWarps][2][C]
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const long long warp0 = (long long)blockIdx.x * kWarps + wib;
   const long long stride = (long long)gridDim.x * kWarps;
-  float4 gam[NV], dg[NV], db[NV];
+  float4 gam[NV], bet[RELU ? NV : 1], dg[NV], db[NV];
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     gam[i] = gamma ? ld_gather4(gamma + i * 128 + lane * 4) : make_float4(1.f, 1.f, 1.f, 1.f);
+    if (RELU) bet[i] = beta ? ld_gather4(beta + i * 128 + lane * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
     dg[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     db[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
@@ -84,6 +91,12 @@ ln_bwd_kernel(const float* __restrict__ x, const float* __restrict__ g, const fl
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       xh[i] = make_float4((xh[i].x - mean) * rstd, (xh[i].y - mean) * rstd, (xh[i].z - mean) * rstd, (xh[i].w - mean) * rstd);
+      if (RELU) {   // gradient reaches the norm only where its output was positive (the forward's own expression)
+        if (!(fmaf(xh[i].x, gam[i].x, bet[i].x) > 0.f)) dy[i].x = 0.f;
+        if (!(fmaf(xh[i].y, gam[i].y, bet[i].y) > 0.f)) dy[i].y = 0.f;
+        if (!(fmaf(xh[i].z, gam[i].z, bet[i].z) > 0.f)) dy[i].z = 0.f;
+        if (!(fmaf(xh[i].w, gam[i].w, bet[i].w) > 0.f)) dy[i].w = 0.f;
+      }
       dg[i].x = fmaf(dy[i].x, xh[i].x, dg[i].x); dg[i].y = fmaf(dy[i].y, xh[i].y, dg[i].y);
       dg[i].z = fmaf(dy[i].z, xh[i].z, dg[i].z); dg[i].w = fmaf(dy[i].w, xh[i].w, dg[i].w);
       db[i].x += dy[i].x; db[i].y += dy[i].y; db[i].z += dy[i].z; db[i].w += dy[i].w;
@@ -159,8 +172,8 @@ extern "C" int64_t mlg_layernorm_bwd_workspace_bytes(int64_t rows, int64_t C) {
   return (int64_t)bwd_blocks(rows) * 2 * C * 4;
 }
 
-extern "C" int mlg_layernorm_fwd(const float* x, const float* gamma, const float* beta, int64_t rows, int64_t C, float eps,
-                                 float* y, float* mean, float* rstd, void* stream) {
+static int layernorm_fwd_impl(const float* x, const float* gamma, const float* beta, int64_t rows, int64_t C, float eps,
+                              float* y, float* mean, float* rstd, bool relu, void* stream) {
   MLG_CHECK_ARG(x && y && mean && rstd, "mlg_layernorm_fwd: null pointer");
   MLG_CHECK_ARG(mlg_layernorm_supported(C) && rows >= 0, "mlg_layernorm_fwd: C=%lld not supported (128/256/384/512)", (long long)C);
   MLG_CHECK_ARG(((uintptr_t)x | (uintptr_t)y) % 16 == 0 && (!gamma || (uintptr_t)gamma % 16 == 0) &&
@@ -168,22 +181,27 @@ extern "C" int mlg_layernorm_fwd(const float* x, const float* gamma, const float
   if (rows == 0) return MLG_OK;
   const unsigned grid = (unsigned)mlg_ceil_div(rows, kWarps);
   cudaStream_t st = (cudaStream_t)stream;
+#define MLG_LN_F(NV)                                                                                         \
+  if (relu) ln_fwd_kernel<NV, true><<<grid, kWarps * 32, 0, st>>>(x, gamma, beta, rows, eps, y, mean, rstd); \
+  else ln_fwd_kernel<NV, false><<<grid, kWarps * 32, 0, st>>>(x, gamma, beta, rows, eps, y, mean, rstd);
   switch (C / 128) {
-    case 1: ln_fwd_kernel<1><<<grid, kWarps * 32, 0, st>>>(x, gamma, beta, rows, eps, y, mean, rstd); break;
-    case 2: ln_fwd_kernel<2><<<grid, kWarps * 32, 0, st>>>(x, gamma, beta, rows, eps, y, mean, rstd); break;
-    case 3: ln_fwd_kernel<3><<<grid, kWarps * 32, 0, st>>>(x, gamma, beta, rows, eps, y, mean, rstd); break;
-    default: ln_fwd_kernel<4><<<grid, kWarps * 32, 0, st>>>(x, gamma, beta, rows, eps, y, mean, rstd); break;
+    case 1: MLG_LN_F(1) break;
+    case 2: MLG_LN_F(2) break;
+    case 3: MLG_LN_F(3) break;
+    default: MLG_LN_F(4) break;
   }
+#undef MLG_LN_F
   MLG_CHECK_LAUNCH("mlg_layernorm_fwd");
   return MLG_OK;
 }
 
-extern "C" int mlg_layernorm_bwd(const float* x, const float* g, const float* gamma, const float* mean, const float* rstd,
-                                 int64_t rows, int64_t C, float* gx, float* dgamma, float* dbeta, void* workspace,
-                                 int64_t workspace_bytes, void* stream) {
+static int layernorm_bwd_impl(const float* x, const float* g, const float* gamma, const float* beta, const float* mean,
+                              const float* rstd, int64_t rows, int64_t C, float* gx, float* dgamma, float* dbeta,
+                              void* workspace, int64_t workspace_bytes, bool relu, void* stream) {
   MLG_CHECK_ARG(x && g && mean && rstd && gx && workspace, "mlg_layernorm_bwd: null pointer");
   MLG_CHECK_ARG(mlg_layernorm_supported(C) && rows >= 0, "mlg_layernorm_bwd: C=%lld not supported (128/256/384/512)", (long long)C);
-  MLG_CHECK_ARG(((uintptr_t)x | (uintptr_t)g | (uintptr_t)gx) % 16 == 0 && (!gamma || (uintptr_t)gamma % 16 == 0),
+  MLG_CHECK_ARG(((uintptr_t)x | (uintptr_t)g | (uintptr_t)gx) % 16 == 0 && (!gamma || (uintptr_t)gamma % 16 == 0) &&
+                    (!beta || (uintptr_t)beta % 16 == 0),
                 "mlg_layernorm_bwd: operands must be 16-byte aligned");
   MLG_CHECK_ARG(workspace_bytes >= mlg_layernorm_bwd_workspace_bytes(rows, C), "mlg_layernorm_bwd: workspace too small");
   cudaStream_t st = (cudaStream_t)stream;
@@ -195,16 +213,39 @@ extern "C" int mlg_layernorm_bwd(const float* x, const float* g, const float* ga
   const int grid = bwd_blocks(rows);
   const size_t smem = (size_t)kWarps * 2 * C * 4;
   float* part = (float*)workspace;
+#define MLG_LN_B(NV)                                                                                                 \
+  if (relu) ln_bwd_kernel<NV, true><<<grid, kWarps * 32, smem, st>>>(x, g, gamma, beta, mean, rstd, rows, gx, part); \
+  else ln_bwd_kernel<NV, false><<<grid, kWarps * 32, smem, st>>>(x, g, gamma, beta, mean, rstd, rows, gx, part);
   switch (C / 128) {
-    case 1: ln_bwd_kernel<1><<<grid, kWarps * 32, smem, st>>>(x, g, gamma, mean, rstd, rows, gx, part); break;
-    case 2: ln_bwd_kernel<2><<<grid, kWarps * 32, smem, st>>>(x, g, gamma, mean, rstd, rows, gx, part); break;
-    case 3: ln_bwd_kernel<3><<<grid, kWarps * 32, smem, st>>>(x, g, gamma, mean, rstd, rows, gx, part); break;
-    default: ln_bwd_kernel<4><<<grid, kWarps * 32, smem, st>>>(x, g, gamma, mean, rstd, rows, gx, part); break;
+    case 1: MLG_LN_B(1) break;
+    case 2: MLG_LN_B(2) break;
+    case 3: MLG_LN_B(3) break;
+    default: MLG_LN_B(4) break;
   }
+#undef MLG_LN_B
   MLG_CHECK_LAUNCH("mlg_layernorm_bwd");
   if (dgamma || dbeta) {
     ln_param_reduce_kernel<<<(unsigned)mlg_ceil_div(2 * C, 32), 256, 0, st>>>(part, grid, (int)(2 * C), dgamma, dbeta);
     MLG_CHECK_LAUNCH("mlg_layernorm_bwd(reduce)");
   }
   return MLG_OK;
+}
+
+extern "C" int mlg_layernorm_fwd(const float* x, const float* gamma, const float* beta, int64_t rows, int64_t C, float eps,
+                                 float* y, float* mean, float* rstd, void* stream) {
+  return layernorm_fwd_impl(x, gamma, beta, rows, C, eps, y, mean, rstd, false, stream);
+}
+extern "C" int mlg_layernorm_bwd(const float* x, const float* g, const float* gamma, const float* mean, const float* rstd,
+                                 int64_t rows, int64_t C, float* gx, float* dgamma, float* dbeta, void* workspace,
+                                 int64_t workspace_bytes, void* stream) {
+  return layernorm_bwd_impl(x, g, gamma, nullptr, mean, rstd, rows, C, gx, dgamma, dbeta, workspace, workspace_bytes, false, stream);
+}
+extern "C" int mlg_layernorm_relu_fwd(const float* x, const float* gamma, const float* beta, int64_t rows, int64_t C,
+                                      float eps, float* y, float* mean, float* rstd, void* stream) {
+  return layernorm_fwd_impl(x, gamma, beta, rows, C, eps, y, mean, rstd, true, stream);
+}
+extern "C" int mlg_layernorm_relu_bwd(const float* x, const float* g, const float* gamma, const float* beta,
+                                      const float* mean, const float* rstd, int64_t rows, int64_t C, float* gx,
+                                      float* dgamma, float* dbeta, void* workspace, int64_t workspace_bytes, void* stream) {
+  return layernorm_bwd_impl(x, g, gamma, beta, mean, rstd, rows, C, gx, dgamma, dbeta, workspace, workspace_bytes, true, stream);
 }

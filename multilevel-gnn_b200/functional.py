@@ -970,7 +970,8 @@ class LayerNormFn(torch.autograd.Function):
                 and bool(_cabi.lib().mlg_layernorm_supported(x.shape[1])))
 
     @staticmethod
-    def forward(ctx, x, weight, bias, eps):
+    def forward(ctx, x, weight, bias, eps, relu=False):
+        """``relu``: max(LN(x), 0) in the same pass (mlg_layernorm_relu_fwd / _bwd)."""
         L = _cabi.lib()
         xd = _f32c(x.detach())
         rows, C = xd.shape
@@ -979,18 +980,18 @@ class LayerNormFn(torch.autograd.Function):
         rstd = torch.empty(rows, dtype=torch.float32, device=xd.device)
         wd = None if weight is None else _f32c(weight.detach())
         bd = None if bias is None else _f32c(bias.detach())
+        fn, name = (L.mlg_layernorm_relu_fwd, "mlg_layernorm_relu_fwd") if relu else (L.mlg_layernorm_fwd, "mlg_layernorm_fwd")
         with torch.cuda.device(xd.device), _cabi.span("layernorm_fwd", 8 * rows * C):
-            _cabi.check(L.mlg_layernorm_fwd(_cabi.fptr(xd), _cabi.fptr(wd, True), _cabi.fptr(bd, True), rows, C, float(eps),
-                                            _cabi.fptr(y), _cabi.fptr(mean), _cabi.fptr(rstd), _cabi.stream_ptr()),
-                        "mlg_layernorm_fwd")
-        ctx.save_for_backward(xd, wd, mean, rstd)
-        ctx.has_w, ctx.has_b = weight is not None, bias is not None
+            _cabi.check(fn(_cabi.fptr(xd), _cabi.fptr(wd, True), _cabi.fptr(bd, True), rows, C, float(eps),
+                           _cabi.fptr(y), _cabi.fptr(mean), _cabi.fptr(rstd), _cabi.stream_ptr()), name)
+        ctx.save_for_backward(xd, wd, bd if relu else None, mean, rstd)
+        ctx.has_w, ctx.has_b, ctx.relu = weight is not None, bias is not None, bool(relu)
         return y
 
     @staticmethod
     def backward(ctx, g):
         L = _cabi.lib()
-        xd, wd, mean, rstd = ctx.saved_tensors
+        xd, wd, bd, mean, rstd = ctx.saved_tensors
         rows, C = xd.shape
         g = _f32c(g)
         gx = torch.empty_like(xd)
@@ -1001,11 +1002,17 @@ class LayerNormFn(torch.autograd.Function):
         ws_bytes = L.mlg_layernorm_bwd_workspace_bytes(rows, C)
         ws = torch.empty(ws_bytes // 4, dtype=torch.float32, device=xd.device)
         with torch.cuda.device(xd.device), _cabi.span("layernorm_bwd", 12 * rows * C):
-            _cabi.check(L.mlg_layernorm_bwd(_cabi.fptr(xd), _cabi.fptr(g), _cabi.fptr(wd, True), _cabi.fptr(mean),
-                                            _cabi.fptr(rstd), rows, C, _cabi.fptr(gx), _cabi.fptr(dgam, True),
-                                            _cabi.fptr(dbet, True), _cabi.fptr(ws), ws_bytes, _cabi.stream_ptr()),
-                        "mlg_layernorm_bwd")
-        return gx, dgam, dbet, None
+            if ctx.relu:
+                _cabi.check(L.mlg_layernorm_relu_bwd(_cabi.fptr(xd), _cabi.fptr(g), _cabi.fptr(wd, True), _cabi.fptr(bd, True),
+                                                     _cabi.fptr(mean), _cabi.fptr(rstd), rows, C, _cabi.fptr(gx),
+                                                     _cabi.fptr(dgam, True), _cabi.fptr(dbet, True), _cabi.fptr(ws), ws_bytes,
+                                                     _cabi.stream_ptr()), "mlg_layernorm_relu_bwd")
+            else:
+                _cabi.check(L.mlg_layernorm_bwd(_cabi.fptr(xd), _cabi.fptr(g), _cabi.fptr(wd, True), _cabi.fptr(mean),
+                                                _cabi.fptr(rstd), rows, C, _cabi.fptr(gx), _cabi.fptr(dgam, True),
+                                                _cabi.fptr(dbet, True), _cabi.fptr(ws), ws_bytes, _cabi.stream_ptr()),
+                            "mlg_layernorm_bwd")
+        return gx, dgam, dbet, None, None
 
 
 class MaxPoolCL(torch.autograd.Function):

@@ -31,6 +31,14 @@ class LayerNorm(nn.LayerNorm):
             return Fn.LayerNormFn.apply(x, self.weight, self.bias, self.eps)
         return super().forward(x)
 
+    def forward_relu(self, x):
+        """relu(self(x)) -- one pass each way on the kernel path (the ReLU that follows the norm in the res+ block and in
+        the MLP stages)."""
+        from ... import functional as Fn
+        if Fn.LayerNormFn.supported(x, self.normalized_shape) and not self._forward_hooks:
+            return Fn.LayerNormFn.apply(x, self.weight, self.bias, self.eps, True)
+        return torch.relu(self(x))
+
 
 def norm_layer(norm_type, nc):
     key = norm_type.lower()
@@ -67,9 +75,17 @@ class MLP(nn.Sequential):
         functional.tall_linear: 3xTF32 tensor-core forward and dX where the shape allows, tensor-core / fp32-FMA weight and
         bias gradient instead of the library's split-K SIMT GEMM + separate bias reductions."""
         from ... import functional as Fn
-        for mod in self:
+        mods = list(self)
+        i = 0
+        while i < len(mods):
+            mod = mods[i]
             if isinstance(mod, nn.Linear) and torch.is_tensor(x) and x.is_cuda and x.dim() == 2:
                 x = Fn.tall_linear(x, mod)
+            elif (isinstance(mod, LayerNorm) and i + 1 < len(mods) and type(mods[i + 1]) is nn.ReLU
+                  and not mods[i + 1]._forward_hooks and torch.is_tensor(x) and x.is_cuda):
+                x = mod.forward_relu(x)      # norm + act in one pass
+                i += 1
             else:
                 x = mod(x)
+            i += 1
         return x

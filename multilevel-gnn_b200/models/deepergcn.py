@@ -146,8 +146,14 @@ class DeeperGCN(nn.Module):
         if self.block == 'res+':
             h = self.gcns[0](h, edge_index, edge_emb)
             for l in range(1, L):
-                h1 = h if self.no_inter_norm else self.norms[l - 1](h)
-                h = self.gcns[l](drop(F.relu(h1)), edge_index, edge_emb) + h
+                norm = self.norms[l - 1]
+                if self.no_inter_norm:
+                    a = F.relu(h)
+                elif hasattr(norm, "forward_relu"):
+                    a = norm.forward_relu(h)          # LayerNorm + ReLU in one pass each way
+                else:
+                    a = F.relu(norm(h))
+                h = self.gcns[l](drop(a), edge_index, edge_emb) + h
             h = drop(self.norms[L - 1](h))
         elif self.block == 'res':
             h = F.dropout(F.relu(self.norms[0](self.gcns[0](h, edge_index, edge_emb))), p=self.dropout, training=self.training)

@@ -77,6 +77,40 @@ def test_gemm_bf16_batched_and_grad(gemm):
     assert_close(y, torch.matmul(adj.bfloat16().double(), x.bfloat16().double()).float(), rtol=1e-4, atol=1e-4, what="2D x 3D")
 
 
+@pytest.mark.parametrize("rows,K,N,bias", [(4096, 1024, 2500, True), (2500, 1024, 625, False), (1030, 260, 300, True)])
+def test_linear_bf16_and_operand_cache(gemm, rows, K, N, bias):
+    """gemm.linear_bf16 (x @ W^T with the weight as the K-major B operand: DenseSAGEConv's projections on the tensor cores)
+    against the bf16-rounded fp64 product, forward and both gradients; inside gemm.operand_cache() the bf16 copy of an
+    operand is made once and the results are bit-identical to the uncached calls."""
+    g = torch.Generator().manual_seed(rows + N)
+    x = torch.randn(2, rows // 2, K, generator=g).to(DEV).requires_grad_()
+    w = (torch.randn(N, K, generator=g) / math.sqrt(K)).to(DEV).requires_grad_()
+    b = torch.randn(N, generator=g).to(DEV) if bias else None
+    y = gemm.linear_bf16(x, w, b)
+    ref = torch.matmul(x.detach().bfloat16().double(), w.detach().bfloat16().double().t())
+    ref = (ref + b.double()) if bias else ref
+    assert_close(y, ref.float(), rtol=1e-4, atol=1e-4, what="linear_bf16")
+    go = torch.randn(y.shape, generator=g).to(DEV)
+    gx, gw = torch.autograd.grad(y, [x, w], go)
+    rx = torch.matmul(go.bfloat16().double(), w.detach().bfloat16().double()).float()
+    rw = torch.matmul(go.reshape(-1, N).bfloat16().double().t(), x.detach().reshape(-1, K).bfloat16().double()).float()
+    assert_close(gx, rx, rtol=1e-4, atol=1e-4, what="linear_bf16 grad x")
+    assert_close(gw, rw, rtol=1e-4, atol=1e-4 * math.sqrt(rows), what="linear_bf16 grad w")
+    calls = []
+    real = gemm._cast_now
+    gemm._cast_now = lambda src, tr: (calls.append((src.data_ptr(), tr)), real(src, tr))[1]
+    try:
+        with gemm.operand_cache():
+            y1 = gemm.linear_bf16(x.detach(), w.detach(), b)
+            y2 = gemm.linear_bf16(x.detach(), w.detach(), b)
+            z = gemm.matmul_bf16(x.detach()[0], w.detach().t())          # w transposed: another orientation of the same data
+    finally:
+        gemm._cast_now = real
+    assert torch.equal(y1, y.detach()) and torch.equal(y2, y1)
+    assert len([c for c in calls if c[0] == w.data_ptr()]) == 1, "the weight is cast once inside the block"
+    assert_close(z, y1[0] - (b if bias else 0), rtol=1e-4, atol=1e-4, what="matmul_bf16 vs linear_bf16")
+
+
 def test_diffpool_tensor_core_path_close_to_fp32():
     """DiffPool at a size where dense_ops takes the tcgen05 path (N=1024 nodes): outputs within the bf16
     tolerance of the fp32 library path on the same weights."""

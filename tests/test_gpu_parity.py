@@ -766,7 +766,29 @@ def test_layernorm_matches_torch(mlg):
         y2 = Fn.LayerNormFn.apply(x, w, b, 1e-5)
         g2 = torch.autograd.grad(y2, [x, w, b], go)
         assert torch.equal(y, y2) and all(torch.equal(a, c) for a, c in zip((gx, gw, gb), g2))
+    # norm + ReLU in one pass each way (mlg_layernorm_relu_fwd / _bwd) vs relu(layer_norm) in fp64; entries whose
+    # pre-activation is within fp32 rounding of 0 may take the other branch: excluded from the gradient comparison
+    for rows, C in [(100146, 128), (5003, 256)]:
+        x = (torch.randn(rows, C, generator=g) * 2 + 0.7).to(DEV).requires_grad_(True)
+        w = (torch.rand(C, generator=g) + 0.5).to(DEV).requires_grad_(True)
+        b = torch.randn(C, generator=g).to(DEV).requires_grad_(True)
+        go = torch.randn(rows, C, generator=g).to(DEV)
+        y = Fn.LayerNormFn.apply(x, w, b, 1e-5, True)
+        xd, wd, bd = x.detach().double().requires_grad_(True), w.detach().double().requires_grad_(True), b.detach().double().requires_grad_(True)
+        pre = torch.nn.functional.layer_norm(xd, (C,), wd, bd, 1e-5)
+        safe = (pre.detach().abs() > 1e-5)
+        gom = go.double() * safe                                   # no gradient through the borderline entries on either side
+        yr = torch.relu(pre)
+        rx, rw, rb = torch.autograd.grad(yr, [xd, wd, bd], gom)
+        gx, gw, gb = torch.autograd.grad(y, [x, w, b], gom.float())
+        assert_close(y, yr.float(), rtol=1e-5, atol=1e-5, what="ln+relu y")
+        assert float((y < 0).sum()) == 0
+        assert_close(gx, rx.float(), rtol=1e-4, atol=1e-5, what="ln+relu gx")
+        assert_close(gw, rw.float(), rtol=1e-4, atol=2e-3, what="ln+relu dgamma")
+        assert_close(gb, rb.float(), rtol=1e-4, atol=2e-3, what="ln+relu dbeta")
     ln = norm_layer("layer", 256).to(DEV)
+    xr = torch.randn(5000, 256, generator=g).to(DEV)
+    assert torch.equal(ln.forward_relu(xr), torch.relu(ln(xr)))   # same kernel arithmetic, then max(., 0)
     assert type(ln).__mro__[1] is torch.nn.LayerNorm and set(ln.state_dict()) == {"weight", "bias"}
     xs = torch.randn(10, 256, device=DEV)                     # too few rows: library path
     assert_close(ln(xs), torch.nn.functional.layer_norm(xs, (256,), ln.weight, ln.bias, ln.eps), what="ln small")
