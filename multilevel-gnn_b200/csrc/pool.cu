@@ -157,6 +157,85 @@ pool_fwd_vec_kernel(const float* __restrict__ x, const float* __restrict__ vm, c
   }
 }
 
+// C == 32 forward on 128-bit lanes: an 8-lane group covers one 128-byte row, so a warp has FOUR slots of its segment in
+// flight per load instruction (UN4 loads per lane: 32 slots per batch) instead of one; the four groups' partial sums are
+// combined with two xor-shuffles per value at the end (fixed order: deterministic).  pool_fwd_vec_kernel<P, 1> walked the
+// ~57 slots of a gbm segment in 8 dependent batches of 128-byte loads (36 us for 69 MB); this one needs two.
+constexpr int UN4 = 8;
+template <int P_>
+__global__ void __launch_bounds__(kThreads)
+pool_fwd_c32_kernel(const float* __restrict__ x, const float* __restrict__ vm, const long long* __restrict__ match,
+                    const float* __restrict__ w, const int* __restrict__ rowptr, const int* __restrict__ slots,
+                    int B, int N, int G, int S, int wrap, float* __restrict__ out_cl) {
+  constexpr int C = 32;
+  const int lane = threadIdx.x & 31;
+  const int sub = lane >> 3, sl = lane & 7;
+  const long long row = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  if (row >= (long long)B * S) return;
+  const int beg = __ldg(rowptr + row), end = __ldg(rowptr + row + 1);
+  const long long BN = (long long)B * N;
+  const float* xc = x + sl * 4;
+  float acc[P_][4];
+#pragma unroll
+  for (int p = 0; p < P_; ++p)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) acc[p][k] = 0.f;
+  for (int base = beg; base < end; base += 32) {
+    const int q = min(base + lane, end - 1);
+    const int slot = __ldg(slots + q);
+    const int g = slot % G;
+    long long node = __ldg(match + slot);
+    float scale = 1.f;
+    if (node < 0) {
+      if (wrap) node = ((long long)(slot / G) * N + node + BN) % BN;  // python negative index
+      else { node = 0; scale = 0.f; }
+    } else {
+      node += (long long)(slot / G) * N;
+    }
+    if (vm) scale *= __ldg(vm + node);
+    float wl[P_];
+#pragma unroll
+    for (int p = 0; p < P_; ++p) wl[p] = scale * __ldg(w + (size_t)g * P_ + p);
+    const int cnt = min(32, end - base);
+    const int inode = (int)node;
+    float4 xv[UN4];
+#pragma unroll
+    for (int u = 0; u < UN4; ++u) {
+      if (u * 4 < cnt) {   // warp-uniform
+        const int nj = __shfl_sync(0xffffffffu, inode, min(u * 4 + sub, cnt - 1));
+        xv[u] = ld_gather4(xc + (size_t)nj * C);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < UN4; ++u) {
+      if (u * 4 < cnt) {
+        const bool on = u * 4 + sub < cnt;
+#pragma unroll
+        for (int p = 0; p < P_; ++p) {
+          float wj = __shfl_sync(0xffffffffu, wl[p], min(u * 4 + sub, cnt - 1));
+          wj = on ? wj : 0.f;
+          acc[p][0] = fmaf(xv[u].x, wj, acc[p][0]);
+          acc[p][1] = fmaf(xv[u].y, wj, acc[p][1]);
+          acc[p][2] = fmaf(xv[u].z, wj, acc[p][2]);
+          acc[p][3] = fmaf(xv[u].w, wj, acc[p][3]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int p = 0; p < P_; ++p)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      acc[p][k] += __shfl_xor_sync(0xffffffffu, acc[p][k], 8);
+      acc[p][k] += __shfl_xor_sync(0xffffffffu, acc[p][k], 16);
+    }
+  if (sub == 0) {
+    float* o = out_cl + (size_t)row * P_ * C + sl * 4;
+#pragma unroll
+    for (int p = 0; p < P_; ++p) st4(o + (size_t)p * C, make_float4(acc[p][0], acc[p][1], acc[p][2], acc[p][3]));
+  }
+}
+
 // g_x[b*N + n, c] = vm * sum_{slot -> node n} sum_p w[g,p] * g_cl[b*S + seg(g), p, c]
 // The node-side CSR covers `n_rows` nodes; replicas > 1: one graph's CSR shared by all B graphs
 // (gene_pca_match / raw_indice identical for every patient, multiloader.py:697,81-82).
@@ -525,6 +604,131 @@ pool_bwd_fused2_kernel(const float* __restrict__ g_cl, const float* __restrict__
   }
 }
 
+// C == 32 fused backward on 128-bit lanes: an 8-lane group covers one 128-byte row and owns RBS replicas, so a warp
+// covers 4 * RBS replicas of its node with a quarter of the load instructions of pool_bwd_fused2_kernel<P, 1, 4> and half
+// as many warps walk the (rowptr -> slot -> segment -> rows) chain; the RBS * P dot products of a slot are reduced inside
+// the 8-lane group with the packed butterfly.
+template <int K>
+__device__ __forceinline__ float reduce_packed8(float (&v)[K], int sl) {
+  static_assert(K >= 1 && K <= 8 && (K & (K - 1)) == 0, "K must be a power of two <= 8");
+  int off = 4;
+#pragma unroll
+  for (int n = K; n > 1; n >>= 1, off >>= 1) {
+    const bool up = (sl & off) != 0;
+#pragma unroll
+    for (int i = 0; i < n / 2; ++i) {
+      const float send = up ? v[i] : v[i + n / 2];
+      const float keep = up ? v[i + n / 2] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+#pragma unroll
+  for (; off >= 1; off >>= 1) v[0] += __shfl_xor_sync(0xffffffffu, v[0], off);
+  return v[0];   // total of value index (sl >> (3 - log2 K)), replicated over the lanes sharing that index
+}
+
+template <int P_, int RBS>
+__global__ void __launch_bounds__(kThreads, 4)
+pool_bwd_c32_kernel(const float* __restrict__ g_cl, const float* __restrict__ x, const float* __restrict__ vm,
+                    const float* __restrict__ w, const int* __restrict__ rowptr, const int* __restrict__ slots,
+                    const int* __restrict__ seg_of_slot, int n_rows, int replicas, int S, int G,
+                    float* __restrict__ g_x, float* __restrict__ part, int mask_input, float mask_slope) {
+  constexpr int C = 32;
+  constexpr int P2 = P_ <= 1 ? 1 : (P_ <= 2 ? 2 : (P_ <= 4 ? 4 : 8));
+  constexpr int K = RBS * P2;
+  constexpr int KSHIFT = K == 1 ? 3 : (K == 2 ? 2 : (K == 4 ? 1 : 0));
+  const int lane = threadIdx.x & 31;
+  const int sub = lane >> 3, sl = lane & 7;
+  const long long wid = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  constexpr int RW = 4 * RBS;   // replicas per warp
+  const int chunks = (replicas + RW - 1) / RW;
+  const long long row = wid / chunks;
+  if (row >= n_rows) return;
+  const int bs = (int)(wid % chunks) * RW + sub * RBS;   // this group's first replica
+  const int nb = min(RBS, replicas - bs);                // <= 0: idle group (still takes part in the shuffles)
+  const int b0 = nb > 0 ? bs : 0;
+  const int nbc = max(nb, 1);
+  const int beg = __ldg(rowptr + row), end = __ldg(rowptr + row + 1);
+  const size_t rep_g = (size_t)S * P_ * C;
+  const size_t rep_x = (size_t)n_rows * C;
+  const unsigned c = sl * 4;
+  float* gx0 = g_x + ((size_t)b0 * n_rows + row) * C + c;
+  if (beg == end) {   // node without a gene slot: zero gradient, nothing to read
+#pragma unroll
+    for (int r = 0; r < RBS; ++r)
+      if (r < nb) st4(gx0 + (size_t)r * rep_x, make_float4(0.f, 0.f, 0.f, 0.f));
+    return;
+  }
+  float4 xr[RBS];
+  float accx[RBS][4], scale[RBS];
+  const float* x0 = x + ((size_t)b0 * n_rows + row) * C + c;
+#pragma unroll
+  for (int r = 0; r < RBS; ++r) xr[r] = ld_stream4(x0 + (size_t)min(r, nbc - 1) * rep_x);
+#pragma unroll
+  for (int r = 0; r < RBS; ++r) {
+    scale[r] = vm ? __ldg(vm + (size_t)(b0 + min(r, nbc - 1)) * n_rows + row) : 1.f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) accx[r][k] = 0.f;
+  }
+  for (int base = beg; base < end; base += 32) {
+    const int q = min(base + lane, end - 1);
+    const int slot = __ldg(slots + q);
+    const int g = slot % G;
+    const int seg = __ldg(seg_of_slot + slot);
+    float wl[P_];
+#pragma unroll
+    for (int p = 0; p < P_; ++p) wl[p] = __ldg(w + (size_t)g * P_ + p);
+    const int cnt = min(32, end - base);
+    for (int j = 0; j < cnt; ++j) {
+      const int sj = __shfl_sync(0xffffffffu, seg, j);
+      const int slotj = __shfl_sync(0xffffffffu, slot, j);
+      float wj[P_];
+#pragma unroll
+      for (int p = 0; p < P_; ++p) wj[p] = __shfl_sync(0xffffffffu, wl[p], j);
+      float4 gv[RBS][P_];
+      const float* gp = g_cl + (size_t)b0 * rep_g + (size_t)sj * P_ * C + c;
+#pragma unroll
+      for (int r = 0; r < RBS; ++r)
+#pragma unroll
+        for (int p = 0; p < P_; ++p) gv[r][p] = ld_gather4(gp + (size_t)min(r, nbc - 1) * rep_g + (size_t)p * C);
+      float d[K];
+#pragma unroll
+      for (int r = 0; r < RBS; ++r)
+#pragma unroll
+        for (int p = 0; p < P2; ++p) {
+          float dot = 0.f;
+          if (p < P_) {
+            const float4 t = gv[r][p < P_ ? p : 0];
+            const float wp = wj[p < P_ ? p : 0];
+            accx[r][0] = fmaf(t.x, wp, accx[r][0]);
+            accx[r][1] = fmaf(t.y, wp, accx[r][1]);
+            accx[r][2] = fmaf(t.z, wp, accx[r][2]);
+            accx[r][3] = fmaf(t.w, wp, accx[r][3]);
+            dot = fmaf(xr[r].x, t.x, dot);
+            dot = fmaf(xr[r].y, t.y, dot);
+            dot = fmaf(xr[r].z, t.z, dot);
+            dot = fmaf(xr[r].w, t.w, dot);
+          }
+          d[r * P2 + p] = dot * scale[r];
+        }
+      const float tot = reduce_packed8<K>(d, sl);
+      const int vi = sl >> KSHIFT;
+      const int r = vi / P2, p = vi % P2;
+      if ((sl & ((1 << KSHIFT) - 1)) == 0 && p < P_ && r < nb)
+        part[((size_t)(b0 + r) * G + slotj) * P_ + p] = tot;   // replicated layout: slot ids are per graph
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < RBS; ++r) {
+    if (r < nb) {
+      const float xs[4] = {xr[r].x, xr[r].y, xr[r].z, xr[r].w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) accx[r][k] *= (mask_input && !(xs[k] > 0.f)) ? scale[r] * mask_slope : scale[r];
+      st4(gx0 + (size_t)r * rep_x, make_float4(accx[r][0], accx[r][1], accx[r][2], accx[r][3]));
+    }
+  }
+}
+
 // g_w = sum over the graphs' partials (fixed order); w_mask: the projection weights were w = params * mask[g] (info_mask of
 // multilevel_gnn.py:222), so the gradient w.r.t. params is the sum times mask[g] -- no separate elementwise backward pass
 __global__ void pool_wgrad_reduce_kernel(const float* __restrict__ part, int B, long long gp, int P, const float* __restrict__ w_mask,
@@ -571,7 +775,13 @@ extern "C" int mlg_pool_fwd(const float* x, const float* vm, const int64_t* matc
   MLG_P_SWITCH(P, (pool_fwd_vec_kernel<P_, VV><<<grid, kThreads, 0, (cudaStream_t)stream>>>(                    \
                       x, vm, (const long long*)match, w, seg_rowptr, seg_slot, (int)B, (int)N, (int)G, (int)S,  \
                       wrap_negative, out_cl)))
-  if (vec_ok && C == 32) { MLG_POOL_FV(1); }
+  static const bool c32_off = getenv("MLG_POOL_C32_OFF") != nullptr;   // A/B switch (measurement only)
+  if (vec_ok && C == 32 && !c32_off) {
+    MLG_P_SWITCH(P, (pool_fwd_c32_kernel<P_><<<grid, kThreads, 0, (cudaStream_t)stream>>>(
+                        x, vm, (const long long*)match, w, seg_rowptr, seg_slot, (int)B, (int)N, (int)G, (int)S,
+                        wrap_negative, out_cl)));
+  }
+  else if (vec_ok && C == 32) { MLG_POOL_FV(1); }
   else if (vec_ok && C == 64) { MLG_POOL_FV(2); }
   else if (vec_ok) { MLG_POOL_FV(4); }
   else {
@@ -640,6 +850,20 @@ extern "C" int mlg_pool_bwd(const float* g_out_cl, const float* x, const float* 
     // bound by its dependent loads (rowptr -> slot -> segment -> rows), so resident warps matter more than work per warp
     // (step 0.850 -> 0.834 ms at the gbm shape).
     // (2 per warp at 40 registers / 48 warps was slower again: 0.846 ms.)
+    static const bool c32_off = getenv("MLG_POOL_C32_OFF") != nullptr;   // A/B switch (measurement only)
+    if (C == 32 && !c32_off) {
+      // 8-lane groups x 128-bit lanes: 4 * RBS replicas per warp, RBS * pow2(P) <= 8 packed dot products per group
+      const int rw = 4 * (P <= 4 ? 2 : 1);
+      const long long warps3 = n_rows * ((replicas + rw - 1) / rw);
+      const int grid3 = mlg_ceil_div(warps3, kThreads / 32);
+      MLG_P_SWITCH(P, (pool_bwd_c32_kernel<P_, (P_ <= 4 ? 2 : 1)><<<grid3, kThreads, 0, st>>>(
+                          g_out_cl, x, vm, w, node_rowptr, node_slot, seg_of_slot, (int)n_rows, (int)replicas, (int)S,
+                          (int)G, g_x, workspace, mask_input, mask_slope)));
+      MLG_CHECK_LAUNCH("mlg_pool_bwd(c32)");
+      pool_wgrad_reduce_kernel<<<mlg_ceil_div(G * P, 256), 256, 0, st>>>(workspace, (int)B, G * P, (int)P, w_mask, g_w);
+      MLG_CHECK_LAUNCH("mlg_pool_bwd(reduce)");
+      return MLG_OK;
+    }
     const int rb2 = C == 32 ? 4 : (P <= 4 ? 8 : 4);
     const long long warps2 = n_rows * ((replicas + rb2 - 1) / rb2);
     const int grid2 = mlg_ceil_div(warps2, kThreads / 32);
