@@ -635,8 +635,7 @@ pool_bwd_c32_kernel(const float* __restrict__ g_cl, const float* __restrict__ x,
                     float* __restrict__ g_x, float* __restrict__ part, int mask_input, float mask_slope) {
   constexpr int C = 32;
   constexpr int P2 = P_ <= 1 ? 1 : (P_ <= 2 ? 2 : (P_ <= 4 ? 4 : 8));
-  constexpr int K = RBS * P2;
-  constexpr int KSHIFT = K == 1 ? 3 : (K == 2 ? 2 : (K == 4 ? 1 : 0));
+  constexpr int KSHIFT = P2 == 1 ? 3 : (P2 == 2 ? 2 : (P2 == 4 ? 1 : 0));
   const int lane = threadIdx.x & 31;
   const int sub = lane >> 3, sl = lane & 7;
   const long long wid = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
@@ -644,7 +643,8 @@ pool_bwd_c32_kernel(const float* __restrict__ g_cl, const float* __restrict__ x,
   const int chunks = (replicas + RW - 1) / RW;
   const long long row = wid / chunks;
   if (row >= n_rows) return;
-  const int bs = (int)(wid % chunks) * RW + sub * RBS;   // this group's first replica
+  const int chunk = (int)(wid % chunks);
+  const int bs = chunk * RW + sub * RBS;                 // this group's first replica
   const int nb = min(RBS, replicas - bs);                // <= 0: idle group (still takes part in the shuffles)
   const int b0 = nb > 0 ? bs : 0;
   const int nbc = max(nb, 1);
@@ -672,12 +672,11 @@ pool_bwd_c32_kernel(const float* __restrict__ g_cl, const float* __restrict__ x,
   }
   for (int base = beg; base < end; base += 32) {
     const int q = min(base + lane, end - 1);
-    const int slot = __ldg(slots + q);
-    const int g = slot % G;
+    const int slot = __ldg(slots + q);   // replicated layout: slot ids are per graph (slot < G is the gene slot itself)
     const int seg = __ldg(seg_of_slot + slot);
     float wl[P_];
 #pragma unroll
-    for (int p = 0; p < P_; ++p) wl[p] = __ldg(w + (size_t)g * P_ + p);
+    for (int p = 0; p < P_; ++p) wl[p] = __ldg(w + (size_t)slot * P_ + p);
     const int cnt = min(32, end - base);
     for (int j = 0; j < cnt; ++j) {
       const int sj = __shfl_sync(0xffffffffu, seg, j);
@@ -691,31 +690,32 @@ pool_bwd_c32_kernel(const float* __restrict__ g_cl, const float* __restrict__ x,
       for (int r = 0; r < RBS; ++r)
 #pragma unroll
         for (int p = 0; p < P_; ++p) gv[r][p] = ld_gather4(gp + (size_t)min(r, nbc - 1) * rep_g + (size_t)p * C);
-      float d[K];
+      // the slot's P weight-gradient terms, summed over this warp's replicas: per group in replica order, the 8 lanes of a
+      // group with the packed butterfly, then the four groups (fixed order: deterministic)
+      float d[P2];
+#pragma unroll
+      for (int p = 0; p < P2; ++p) d[p] = 0.f;
 #pragma unroll
       for (int r = 0; r < RBS; ++r)
 #pragma unroll
-        for (int p = 0; p < P2; ++p) {
-          float dot = 0.f;
-          if (p < P_) {
-            const float4 t = gv[r][p < P_ ? p : 0];
-            const float wp = wj[p < P_ ? p : 0];
-            accx[r][0] = fmaf(t.x, wp, accx[r][0]);
-            accx[r][1] = fmaf(t.y, wp, accx[r][1]);
-            accx[r][2] = fmaf(t.z, wp, accx[r][2]);
-            accx[r][3] = fmaf(t.w, wp, accx[r][3]);
-            dot = fmaf(xr[r].x, t.x, dot);
-            dot = fmaf(xr[r].y, t.y, dot);
-            dot = fmaf(xr[r].z, t.z, dot);
-            dot = fmaf(xr[r].w, t.w, dot);
-          }
-          d[r * P2 + p] = dot * scale[r];
+        for (int p = 0; p < P_; ++p) {
+          const float4 t = gv[r][p];
+          accx[r][0] = fmaf(t.x, wj[p], accx[r][0]);
+          accx[r][1] = fmaf(t.y, wj[p], accx[r][1]);
+          accx[r][2] = fmaf(t.z, wj[p], accx[r][2]);
+          accx[r][3] = fmaf(t.w, wj[p], accx[r][3]);
+          float dot = xr[r].x * t.x;
+          dot = fmaf(xr[r].y, t.y, dot);
+          dot = fmaf(xr[r].z, t.z, dot);
+          dot = fmaf(xr[r].w, t.w, dot);
+          d[p] += r < nb ? dot * scale[r] : 0.f;
         }
-      const float tot = reduce_packed8<K>(d, sl);
-      const int vi = sl >> KSHIFT;
-      const int r = vi / P2, p = vi % P2;
-      if ((sl & ((1 << KSHIFT) - 1)) == 0 && p < P_ && r < nb)
-        part[((size_t)(b0 + r) * G + slotj) * P_ + p] = tot;   // replicated layout: slot ids are per graph
+      float tot = reduce_packed8<P2>(d, sl);
+      tot += __shfl_xor_sync(0xffffffffu, tot, 8);
+      tot += __shfl_xor_sync(0xffffffffu, tot, 16);
+      const int p = sl >> KSHIFT;
+      if (sub == 0 && (sl & ((1 << KSHIFT) - 1)) == 0 && p < P_)
+        part[((size_t)chunk * G + slotj) * P_ + p] = tot;   // one partial per (replica chunk, slot): the reduce adds `chunks`
     }
   }
 #pragma unroll
@@ -840,7 +840,6 @@ extern "C" int mlg_pool_bwd(const float* g_out_cl, const float* x, const float* 
   MLG_CHECK_ARG(replicas == 1 || replicas == B, "mlg_pool_bwd: replicas must be 1 or B");
   MLG_CHECK_ARG(C <= 128, "mlg_pool_bwd: fused backward supports C <= 128 (use mlg_pool_bwd_x / _w)");
   cudaStream_t st = (cudaStream_t)stream;
-  MLG_CUDA(cudaMemsetAsync(workspace, 0, (size_t)B * G * P * sizeof(float), st));   // slots without a node stay zero
   const long long n_rows = replicas > 1 ? N : B * N;
   static const bool v1_only = getenv("MLG_POOL_BWD_V1") != nullptr;
   if (!v1_only && replicas > 1 && (C == 32 || C == 64 || C == 128) && (uintptr_t)g_out_cl % 16 == 0 && (uintptr_t)x % 16 == 0 &&
@@ -852,18 +851,22 @@ extern "C" int mlg_pool_bwd(const float* g_out_cl, const float* x, const float* 
     // (2 per warp at 40 registers / 48 warps was slower again: 0.846 ms.)
     static const bool c32_off = getenv("MLG_POOL_C32_OFF") != nullptr;   // A/B switch (measurement only)
     if (C == 32 && !c32_off) {
-      // 8-lane groups x 128-bit lanes: 4 * RBS replicas per warp, RBS * pow2(P) <= 8 packed dot products per group
-      const int rw = 4 * (P <= 4 ? 2 : 1);
-      const long long warps3 = n_rows * ((replicas + rw - 1) / rw);
+      // 8-lane groups x 128-bit lanes: 8 replicas per warp; the weight-gradient partials are already summed over a warp's
+      // replicas, so the workspace holds one [G, P] slice per replica chunk (B / 8 of them) instead of one per graph
+      constexpr int rw = 8;
+      const long long chunks = (replicas + rw - 1) / rw;
+      const long long warps3 = n_rows * chunks;
       const int grid3 = mlg_ceil_div(warps3, kThreads / 32);
-      MLG_P_SWITCH(P, (pool_bwd_c32_kernel<P_, (P_ <= 4 ? 2 : 1)><<<grid3, kThreads, 0, st>>>(
+      MLG_CUDA(cudaMemsetAsync(workspace, 0, (size_t)chunks * G * P * sizeof(float), st));   // slots without a node stay zero
+      MLG_P_SWITCH(P, (pool_bwd_c32_kernel<P_, 2><<<grid3, kThreads, 0, st>>>(
                           g_out_cl, x, vm, w, node_rowptr, node_slot, seg_of_slot, (int)n_rows, (int)replicas, (int)S,
                           (int)G, g_x, workspace, mask_input, mask_slope)));
       MLG_CHECK_LAUNCH("mlg_pool_bwd(c32)");
-      pool_wgrad_reduce_kernel<<<mlg_ceil_div(G * P, 256), 256, 0, st>>>(workspace, (int)B, G * P, (int)P, w_mask, g_w);
+      pool_wgrad_reduce_kernel<<<mlg_ceil_div(G * P, 256), 256, 0, st>>>(workspace, (int)chunks, G * P, (int)P, w_mask, g_w);
       MLG_CHECK_LAUNCH("mlg_pool_bwd(reduce)");
       return MLG_OK;
     }
+    MLG_CUDA(cudaMemsetAsync(workspace, 0, (size_t)B * G * P * sizeof(float), st));   // slots without a node stay zero
     const int rb2 = C == 32 ? 4 : (P <= 4 ? 8 : 4);
     const long long warps2 = n_rows * ((replicas + rb2 - 1) / rb2);
     const int grid2 = mlg_ceil_div(warps2, kThreads / 32);
@@ -880,6 +883,7 @@ extern "C" int mlg_pool_bwd(const float* g_out_cl, const float* x, const float* 
     MLG_CHECK_LAUNCH("mlg_pool_bwd(reduce)");
     return MLG_OK;
   }
+  MLG_CUDA(cudaMemsetAsync(workspace, 0, (size_t)B * G * P * sizeof(float), st));   // slots without a node stay zero
   const long long warps = n_rows * ((replicas + 3) / 4);
   const int grid = mlg_ceil_div(warps, kThreads / 32);
   const int cch = C <= 32 ? 1 : (C <= 64 ? 2 : 4);

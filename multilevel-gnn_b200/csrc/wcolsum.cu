@@ -53,26 +53,27 @@ wcolsum_kernel(const float* __restrict__ G, unsigned ld, const float* __restrict
   }
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 wcolsum_reduce_kernel(const float* __restrict__ partial, int n_part, int C2, float* __restrict__ u, float* __restrict__ v) {
-  __shared__ float sm[8][32];
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  // blockDim.x / 32 warps share the partials of 32 columns (warp w: p = w, w + nw, ...; two chains each); the warp sums are
+  // added in warp order.  With 8 warps and ~600 partials this was 37 dependent round trips on 4 blocks (9.5 us).
+  __shared__ float sm[32][32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
   const int j = blockIdx.x * 32 + lane;
   float s0 = 0.f, s1 = 0.f;
   if (j < C2) {
     int p = w;
-    for (; p + 8 < n_part; p += 16) {
+    for (; p + nw < n_part; p += 2 * nw) {
       s0 += partial[(size_t)p * C2 + j];
-      s1 += partial[(size_t)(p + 8) * C2 + j];
+      s1 += partial[(size_t)(p + nw) * C2 + j];
     }
-    for (; p < n_part; p += 8) s0 += partial[(size_t)p * C2 + j];
+    for (; p < n_part; p += nw) s0 += partial[(size_t)p * C2 + j];
   }
   sm[w][lane] = s0 + s1;
   __syncthreads();
   if (w == 0 && j < C2) {
     float s = 0.f;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) s += sm[k][lane];
+    for (int k = 0; k < nw; ++k) s += sm[k][lane];
     const int C = C2 / 2;
     if (j < C) { if (u) u[j] = s; }
     else if (v) v[j - C] = s;
@@ -129,7 +130,7 @@ int mlg_detail_colsum_partials(const float* partial, long long n_part, long long
     MLG_CHECK_LAUNCH("colsum_slices");
     wcolsum_reduce_kernel<<<gx, 256, 0, st>>>(scratch, slices, C2, u, v);
   } else {
-    wcolsum_reduce_kernel<<<gx, 256, 0, st>>>(partial, (int)n_part, C2, u, v);
+    wcolsum_reduce_kernel<<<gx, n_part > 64 ? 1024 : 256, 0, st>>>(partial, (int)n_part, C2, u, v);
   }
   MLG_CHECK_LAUNCH("colsum_partials");
   return MLG_OK;
@@ -151,7 +152,7 @@ extern "C" int mlg_wcolsum(const float* G, int64_t ld, const float* a, int64_t r
   if (smem > 48 * 1024) cudaFuncSetAttribute(wcolsum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   wcolsum_kernel<<<grid, kWarps * 32, smem, st>>>(G, (unsigned)ld, a, rows, (int)C, (float*)workspace);
   MLG_CHECK_LAUNCH("mlg_wcolsum");
-  wcolsum_reduce_kernel<<<(unsigned)mlg_ceil_div(2 * C, 32), 256, 0, st>>>((const float*)workspace, grid, (int)(2 * C), u, v);
+  wcolsum_reduce_kernel<<<(unsigned)mlg_ceil_div(2 * C, 32), grid > 64 ? 1024 : 256, 0, st>>>((const float*)workspace, grid, (int)(2 * C), u, v);
   MLG_CHECK_LAUNCH("mlg_wcolsum(reduce)");
   return MLG_OK;
 }
