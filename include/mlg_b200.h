@@ -237,6 +237,16 @@ int mlg_sage_fold_fwd(const float* nn_w, const float* lin_r_w, int64_t cout, int
                       float* wcat_lo, float* wcat_t_hi, float* wcat_t_lo, void* stream);
 int mlg_sage_fold_bwd(const float* g_wcat, const float* nn_w, const float* lin_r_w, int64_t cout, int64_t cin, int64_t r,
                       float* g_nn_w, float* g_lin_r_w, void* stream);
+/* The same folding in the STACKED layout the transform-first layer and the factored first layer use
+ * (z = U + mean_j(w_ij V_j), [U | V] = x Wst^T + [b | 0]):  wst = [W1 ; W2 * W_r] [2cout, cin], its 3xTF32 split, the split
+ * of wst^T [cin, 2cout] (dX GEMM) and bias2 = [nn_b | 0] [2cout] (NULL ok; nn_b NULL ok = zeros) in ONE launch.
+ * bwd: g_wst [2cout, cin] with leading dimension ld, optionally the sum of two addends (g_wst_add NULL ok):
+ * g_nn_w = [g_wst[:cout] | g_wst[cout:] * W_r^T],  g_lin_r_w = W2^T * g_wst[cout:]. */
+int mlg_sage_fold_stacked_fwd(const float* nn_w, const float* lin_r_w, const float* nn_b, int64_t cout, int64_t cin, int64_t r,
+                              float* wst, float* wst_hi, float* wst_lo, float* wst_t_hi, float* wst_t_lo, float* bias2,
+                              void* stream);
+int mlg_sage_fold_stacked_bwd(const float* g_wst, const float* g_wst_add, int64_t ld, const float* nn_w, const float* lin_r_w,
+                              int64_t cout, int64_t cin, int64_t r, float* g_nn_w, float* g_lin_r_w, void* stream);
 
 /* Pathway-wise independence term of MultilevelGNN.get_feature_loss (models/multilevel_gnn.py:336-346; no gradient, the
  * reference reads .data):  out[0] = (1 / (P(P-1)/2)) * sum_{i < P-1} mean_s | sum_g w_gi w_gL | / (sqrt(sum_g w_gi^2 *

@@ -149,9 +149,15 @@ def xty(a, x, want_colsum=False, tag="xty", out=None):
 USE_TF32X3 = True      # tall Linears on the tensor cores with the 3xTF32 split (fp32-accurate); False = cuBLAS fp32
 
 
-def tall_matmul(a, w, bias=None, act=0, slope=0.0, tag="gemm_tf32x3", w_split=None):
+def tall_matmul(a, w, bias=None, act=0, slope=0.0, tag="gemm_tf32x3", w_split=None, out=None):
     """act(a @ w^T + bias) for a tall fp32 matrix a [M, K] and a small weight w [N, K]: mlg_gemm_tf32x3 when the shape
-    is supported, else cuBLAS fp32 (+ mlg_bias_act).  act: 0 none, 1 LeakyReLU(slope)."""
+    is supported, else cuBLAS fp32 (+ mlg_bias_act).  act: 0 none, 1 LeakyReLU(slope).  ``out`` (contiguous [M, N], e.g. a
+    parameter's gradient slot) receives the result on the tensor-core path; the other paths copy into it."""
+    if out is not None:
+        if not (USE_TF32X3 and a.is_cuda and out.is_contiguous() and w_split is not None
+                and _cabi.lib().mlg_gemm_tf32x3_supported(a.shape[0], w.shape[0], a.shape[1])
+                and a.stride(1) == 1 and a.stride(0) % 4 == 0 and a.data_ptr() % 16 == 0):
+            return out.copy_(tall_matmul(a, w, bias, act, slope, tag, w_split))
     L = _cabi.lib()
     M, K = a.shape
     N = w.shape[0]
@@ -181,7 +187,8 @@ def tall_matmul(a, w, bias=None, act=0, slope=0.0, tag="gemm_tf32x3", w_split=No
                                                   _cabi.stream_ptr()), "mlg_gemm_tf32x3")
         return out
     if (tc_ok and L.mlg_gemm_tf32x3_supported(M, N, K)):
-        out = torch.empty(M, N, dtype=torch.float32, device=a.device)
+        if out is None:
+            out = torch.empty(M, N, dtype=torch.float32, device=a.device)
         with torch.cuda.device(a.device):
             if w_split is not None:
                 hi, lo = w_split          # [N, K] hi / lo parts prepared by the caller (mlg_sage_fold_fwd)
@@ -623,23 +630,41 @@ class SageLayer(torch.autograd.Function):
         w_r, w_nn = lin_r_w.detach(), nn_w.detach()
         w_r, w_nn = _f32c(w_r), _f32c(w_nn)
         cout = w_nn.shape[0]
-        wbuf = torch.empty(5, cout * 2 * cin, dtype=torch.float32, device=xd.device)
-        with torch.cuda.device(xd.device):   # Wcat = [W1 | W2 . W_r], its tf32 hi/lo split, and the split of Wcat^T
-            _cabi.check(_cabi.lib().mlg_sage_fold_fwd(_cabi.fptr(w_nn), _cabi.fptr(w_r), cout, cin, w_r.shape[0],
-                                                      _cabi.fptr(wbuf[0]),
-                                                      _cabi.fptr(wbuf[1]), _cabi.fptr(wbuf[2]), _cabi.fptr(wbuf[3]),
-                                                      _cabi.fptr(wbuf[4]), _cabi.stream_ptr()), "mlg_sage_fold_fwd")
-        wcat = wbuf[0].view(cout, 2 * cin)
+        factored_ok = (FACTORED_RANK1 and rank1 and not relative and topo.replicas > 1 and cout % 4 == 0
+                       and xd.shape[0] == topo.n_single and n == topo.n_single * topo.replicas)
+        tfirst_ok = (not factored_ok and TRANSFORM_FIRST and not rank1 and not relative and in_slope is None
+                     and topo.replicas > 1 and cout < cin and cout % 4 == 0 and cin % 4 == 0
+                     and n == topo.n_single * topo.replicas)
+        if factored_ok or tfirst_ok:
+            # Wst = [W1 ; W2 . W_r] [2cout, cin], its tf32 hi / lo split, the split of Wst^T and the bias [b | 0]: one launch
+            sb = torch.empty(5 * 2 * cout * cin + 2 * cout, dtype=torch.float32, device=xd.device)
+            wparts = [sb[i * 2 * cout * cin:(i + 1) * 2 * cout * cin] for i in range(5)]
+            bias2 = sb[5 * 2 * cout * cin:] if (tfirst_ok and nn_b is not None) else None
+            with torch.cuda.device(xd.device):
+                _cabi.check(_cabi.lib().mlg_sage_fold_stacked_fwd(
+                    _cabi.fptr(w_nn), _cabi.fptr(w_r), None if nn_b is None else _cabi.fptr(_f32c(nn_b.detach())), cout, cin,
+                    w_r.shape[0], _cabi.fptr(wparts[0]), _cabi.fptr(wparts[1]), _cabi.fptr(wparts[2]), _cabi.fptr(wparts[3]),
+                    _cabi.fptr(wparts[4]), None if bias2 is None else _cabi.fptr(bias2), _cabi.stream_ptr()),
+                    "mlg_sage_fold_stacked_fwd")
+            wst = wparts[0].view(2 * cout, cin)
+            wst_split = (wparts[1].view(2 * cout, cin), wparts[2].view(2 * cout, cin))
+            ctx.wst_t_split = (wparts[3].view(cin, 2 * cout), wparts[4].view(cin, 2 * cout))    # Wst^T hi / lo: the dX GEMMs
+        else:
+            wbuf = torch.empty(5, cout * 2 * cin, dtype=torch.float32, device=xd.device)
+            with torch.cuda.device(xd.device):   # Wcat = [W1 | W2 . W_r], its tf32 hi/lo split, and the split of Wcat^T
+                _cabi.check(_cabi.lib().mlg_sage_fold_fwd(_cabi.fptr(w_nn), _cabi.fptr(w_r), cout, cin, w_r.shape[0],
+                                                          _cabi.fptr(wbuf[0]),
+                                                          _cabi.fptr(wbuf[1]), _cabi.fptr(wbuf[2]), _cabi.fptr(wbuf[3]),
+                                                          _cabi.fptr(wbuf[4]), _cabi.stream_ptr()), "mlg_sage_fold_fwd")
+            wcat = wbuf[0].view(cout, 2 * cin)
         ctx.factored = False
-        if (FACTORED_RANK1 and rank1 and not relative and topo.replicas > 1 and cout % 4 == 0
-                and xd.shape[0] == topo.n_single and n == topo.n_single * topo.replicas):
+        if factored_ok:
             # Fully factored first layer: x0 = xs * emb is rank-1 per node, so z = xs[b,i] E_self[i] + mean_j(w_ij xs[b,j]
             # E_nbr[j]) + b with the per-gene tables [E_self | E_nbr] = emb [W1 ; W2 W_r]^T (an n_single-row GEMM).  Neither
             # x0, the [x0 | agg] buffer nor the B*N-row update / dgrad / weight-gradient GEMMs exist on this path.
             L = _cabi.lib()
             n1 = topo.n_single
-            wst = wcat.view(cout, 2, cin).permute(1, 0, 2).reshape(2 * cout, cin)      # [W1 ; W2 W_r]   [2cout, cin]
-            e12 = torch.mm(xd, wst.t())                                               # [n1, 2cout]
+            e12 = tall_matmul(xd, wst, tag="sage_rank1_tables", w_split=wst_split)     # [n1, 2cout] = [E_self | E_nbr]
             y = torch.empty(n, cout, dtype=torch.float32, device=xd.device)
             csr = topo.fwd
             bias = None if nn_b is None else _f32c(nn_b.detach())
@@ -682,17 +707,11 @@ class SageLayer(torch.autograd.Function):
             ctx.out_premasked = bool(out_premasked)
             return y
         ctx.transform_first = False
-        if (TRANSFORM_FIRST and not rank1 and not relative and in_slope is None and topo.replicas > 1 and cout < cin
-                and cout % 4 == 0 and cin % 4 == 0 and n == topo.n_single * topo.replicas):
+        if tfirst_ok:
             # out_channels < in_channels: transform, THEN aggregate -- z = U + mean_j(w_ij V_j) with
             # [U | V] = x [W1 ; W2 W_r]^T + [b | 0]: the gather (the L2-bandwidth-bound step) runs on cout-wide rows instead of
             # cin-wide ones, forward and backward, and no [x | agg] buffer is written.
-            wst = wcat.view(cout, 2, cin).permute(1, 0, 2).reshape(2 * cout, cin)      # [W1 ; W2 W_r]   [2cout, cin]
-            bias2 = None
-            if nn_b is not None:
-                bias2 = torch.zeros(2 * cout, dtype=torch.float32, device=xd.device)
-                bias2[:cout].copy_(nn_b.detach())
-            uv = tall_matmul(xd, wst, bias2, tag="sage_update_gemm")                   # [n, 2cout] = [U | V]
+            uv = tall_matmul(xd, wst, bias2, tag="sage_update_gemm", w_split=wst_split)     # [n, 2cout] = [U | V]
             csr = topo.fwd
             y = gather_sum(uv[:, cout:], csr.rowptr, csr.col, topo.n_single, val=topo.fwd_val, post_mode=1,
                            addend=uv[:, :cout], replicas=topo.replicas, order=topo.fwd_order,
@@ -787,16 +806,15 @@ class SageLayer(torch.autograd.Function):
         # [2cout, cin] = [g_W1 ; g_(W2 W_r)] = g12^T emb (a 15 405-deep reduction) + the weight un-folding: on a forked stream
         # next to the table -> embedding product
         with _Forked(gz.device, 2, keep=(g12, emb, w_nn, w_r)) as fk:
-            g_wst, _ = xty(g12, emb, tag="sage_rank1_wgrad")
-            g_wcat = g_wst.view(2, cout, cin).permute(1, 0, 2).reshape(cout, 2 * cin)
+            g_wst, _ = xty(g12, emb, tag="sage_rank1_wgrad")                       # [2cout, cin], stacked like Wst
             g_wnn, g_wr = _slot_or_empty(ctx.wparams[1], w_nn), _slot_or_empty(ctx.wparams[0], w_r)
             with torch.cuda.device(gz.device):
-                _cabi.check(L.mlg_sage_fold_bwd(_cabi.fptr(g_wcat), _cabi.fptr(w_nn), _cabi.fptr(w_r), cout, cin,
-                                                w_r.shape[0], _cabi.fptr(g_wnn), _cabi.fptr(g_wr), _cabi.stream_ptr()),
-                            "mlg_sage_fold_bwd")
-            fk.hold(g_wst, g_wcat, g_wnn, g_wr)
+                _cabi.check(L.mlg_sage_fold_stacked_bwd(_cabi.fptr(g_wst), None, cin, _cabi.fptr(w_nn), _cabi.fptr(w_r), cout,
+                                                        cin, w_r.shape[0], _cabi.fptr(g_wnn), _cabi.fptr(g_wr),
+                                                        _cabi.stream_ptr()), "mlg_sage_fold_stacked_bwd")
+            fk.hold(g_wst, g_wnn, g_wr)
         slot = grad_slot(ctx.emb_param, (n1, cin)) if ctx.emb_param is not None else None
-        g_emb = torch.mm(g12, wst, out=slot) if slot is not None else torch.mm(g12, wst)
+        g_emb = tall_matmul(g12, wst.t(), tag="sage_rank1_demb", w_split=ctx.wst_t_split, out=slot)     # g12 @ Wst
         return g_emb, None, g_wr, g_wnn, g_b, None, None, None, None, None
 
     @staticmethod
@@ -827,23 +845,24 @@ class SageLayer(torch.autograd.Function):
                 if n % 2 == 0 and 4 * cout == 128 and 2 * cin == 128:
                     # tensor-core weight gradient on ROW PAIRS: [G_even | G_odd]^T [x_even | x_odd] is 128 x 128; its two
                     # diagonal blocks are the even- and odd-row halves of G^T x (the off-diagonal blocks are discarded)
+                    # (the two diagonal blocks are added inside the un-folding kernel)
                     o2, cs2 = xty(g_uv.view(n // 2, 4 * cout), x.view(n // 2, 2 * cin), want_colsum=ctx.has_bias, tag="sage_wgrad")
-                    g_wst = o2[:2 * cout, :cin] + o2[2 * cout:, cin:]
+                    ga, gb, ld = o2, o2[2 * cout:, cin:], 2 * cin
                     if ctx.has_bias:
                         g_b = torch.add(cs2[:cout], cs2[2 * cout:3 * cout], out=grad_slot(ctx.wparams[2], (cout,)))
                 else:
-                    g_wst, cs = xty(g_uv, x, want_colsum=ctx.has_bias, tag="sage_wgrad")
+                    o2, cs = xty(g_uv, x, want_colsum=ctx.has_bias, tag="sage_wgrad")
+                    ga, gb, ld = o2, None, cin
                     if ctx.has_bias:
                         g_b = cs[:cout]
-                g_wcat = g_wst.view(2, cout, cin).permute(1, 0, 2).reshape(cout, 2 * cin)
                 g_wnn, g_wr = _slot_or_empty(ctx.wparams[1], w_nn), _slot_or_empty(ctx.wparams[0], w_r)
                 with torch.cuda.device(gz.device):
-                    _cabi.check(L.mlg_sage_fold_bwd(_cabi.fptr(g_wcat), _cabi.fptr(w_nn), _cabi.fptr(w_r), cout, cin,
-                                                    w_r.shape[0], _cabi.fptr(g_wnn), _cabi.fptr(g_wr), _cabi.stream_ptr()),
-                                "mlg_sage_fold_bwd")
-                fk.hold(g_wst, g_wcat, g_wnn, g_wr, g_b)
+                    _cabi.check(L.mlg_sage_fold_stacked_bwd(_vptr(ga), None if gb is None else _vptr(gb), ld, _cabi.fptr(w_nn),
+                                                            _cabi.fptr(w_r), cout, cin, w_r.shape[0], _cabi.fptr(g_wnn),
+                                                            _cabi.fptr(g_wr), _cabi.stream_ptr()), "mlg_sage_fold_stacked_bwd")
+                fk.hold(o2, g_wnn, g_wr, g_b)
         if needs[0]:
-            gx = tall_matmul(g_uv, wst.t().contiguous(), tag="sage_dgrad_gemm")         # dL/dx (the producer masks it itself)
+            gx = tall_matmul(g_uv, wst.t(), tag="sage_dgrad_gemm", w_split=ctx.wst_t_split)     # dL/dx (the producer masks it itself)
         return gx, None, g_wr, g_wnn, (g_b if ctx.has_bias else None), None, None, None, None, None
 
     @staticmethod

@@ -330,29 +330,30 @@ class MultilevelGNN(nn.Module):
             flat = pca_feature.reshape(pca_feature.shape[0], -1)
             loss = loss - self.pca_loss_coef * torch.log(torch.mean(torch.std(flat, dim=0)))
         if self.pca_indep_loss:
-            w = (self.learnable_pca_params * self.info_mask).data
-            idx = self.pathway_indexs.to(w.device)
+            dev = self.learnable_pca_params.device
+            idx = self.pathway_indexs.to(dev)
             nseg = int(self.pathway_indexs.max()) + 1 if not hasattr(self, "_nseg") else self._nseg
             self._nseg = nseg
 
             # only the LAST j of every i survives the reference's loop (j = pca_dim - 1): all pairs (i, P-1) at once,
             # one segment sum over [w_i * w_last | w_i^2 | w_last^2] instead of three index_adds per pair
             P = self.pca_dim
-            segptr = self._segment_pointers(idx, nseg) if (w.is_cuda and 2 <= P <= 8) else None
+            segptr = self._segment_pointers(idx, nseg) if (dev.type == "cuda" and 2 <= P <= 8) else None
             if segptr is not None:
                 # genes sorted by pathway: the whole term is ONE launch (mlg_pca_indep_loss) instead of ~14 tiny ones
                 from .. import _cabi
-                out = torch.empty(1, dtype=torch.float32, device=w.device)
+                out = torch.empty(1, dtype=torch.float32, device=dev)
                 wr = self.learnable_pca_params.data
                 mk = self.info_mask.data.reshape(-1)
                 wr = wr if (wr.dtype == torch.float32 and wr.is_contiguous()) else wr.float().contiguous()
                 mk = mk if (mk.dtype == torch.float32 and mk.is_contiguous()) else mk.float().contiguous()
-                with torch.cuda.device(w.device):
-                    ws = torch.empty(nseg, dtype=torch.float32, device=w.device)
+                with torch.cuda.device(dev):
+                    ws = torch.empty(nseg, dtype=torch.float32, device=dev)
                     _cabi.check(_cabi.lib().mlg_pca_indep_loss(_cabi.fptr(wr), _cabi.fptr(mk), _cabi.iptr(segptr), nseg, P,
                                                               _cabi.fptr(out), _cabi.fptr(ws), _cabi.stream_ptr()),
                                 "mlg_pca_indep_loss")
-                return loss + out[0]
+                return out[0] if (isinstance(loss, int) and loss == 0) else loss + out[0]
+            w = (self.learnable_pca_params * self.info_mask).data     # (the kernel above multiplies the mask in itself)
             if P > 1:
                 a, b = w[:, :P - 1], w[:, P - 1:P]
                 seg = torch.zeros(nseg, 2 * (P - 1) + 1, device=w.device, dtype=w.dtype).index_add_(
