@@ -824,29 +824,6 @@ __device__ __forceinline__ void st_pol4(float* p, float4 v, unsigned long long p
 // instructions of sm_100 (fma / add / mul .rn.f32x2 = FFMA2 / FADD2 / FMUL2: one issue slot for two IEEE-identical
 // results), the run-time switches (source-side sum, g_edge wanted, learn_t) are template parameters, and the edge stream
 // is walked as plain nested loops (rows, then the row's entries; one group test per entry).
-typedef unsigned long long u64;
-__device__ __forceinline__ u64 pk2(float lo, float hi) {
-  u64 r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-  return r;
-}
-__device__ __forceinline__ void upk2(u64 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
-__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) {
-  u64 r;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
-  return r;
-}
-__device__ __forceinline__ u64 add2(u64 a, u64 b) {
-  u64 r;
-  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-  return r;
-}
-__device__ __forceinline__ u64 mul2(u64 a, u64 b) {
-  u64 r;
-  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-  return r;
-}
-
 template <int NV, bool AFF, bool SRC, bool EDGE, bool LEARN>
 __global__ void __launch_bounds__(kRingWarps * 32) gen_bwd_ring_kernel(const GenP P) {
   extern __shared__ __align__(16) unsigned char ring_raw[];

@@ -11,6 +11,8 @@
 // then broadcasts the replica values by shuffle: 32 SHFL + 32 FMUL + 64 FFMA per entry, four entries' loads in flight.
 // The epilogue writes 32 coalesced 256-byte rows and (optionally) the 64 sign bits per (gene, replica) the backward kernel
 // uses instead of re-reading the activation.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "../../include/mlg_b200.h"
 
@@ -123,8 +125,102 @@ __device__ __forceinline__ void rank1_rows_pass(const R1F& P, unsigned row, int 
   }
 }
 
-template <int CPL>
+// CPL == 2, all 32 replica slots live: the same arithmetic on replica PAIRS.  The neighbour's 32 replica values (already
+// scaled by the edge weight, as above) go through a warp-private shared-memory row and come back as eight broadcast
+// LDS.128 -- every lane then holds all 32 values as 16 register pairs -- and the accumulators are pairs (replica 2j,
+// replica 2j + 1) of one channel, so an entry costs 8 LDS.128 + 32 FFMA2 instead of 32 SHFL + 64 FFMA (the kernel is
+// issue bound: 35.6 M warp instructions for a 126 MB output).  Per accumulator the FMAs and their operands are those of
+// the scalar pass, in the same order: bit-identical results.
+__device__ __forceinline__ void rank1_rows_pass_packed(const R1F& P, unsigned row, int beg, int end, float inv,
+                                                       const float (&es)[2], const float (&bs)[2], int rb0, int lane,
+                                                       float* xsm /* warp-private [EU][32], 16-byte aligned */) {
+  u64 acc[2][16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) acc[0][j] = acc[1][j] = 0ull;
+  const float* xcol = P.xs_t + rb0 + lane;
+  for (int base = beg; base < end; base += 32) {
+    const int q = min(base + lane, end - 1);
+    const unsigned my_idx = (unsigned)__ldg(P.idx + q);
+    const float my_w = P.val ? __ldg(P.val + q) : 1.f;
+    const int cnt = min(32, end - base);
+    for (int j = 0; j < cnt; j += EU) {
+      float e[EU][2], xw[EU];
+#pragma unroll
+      for (int u = 0; u < EU; ++u) {
+        const int jj = min(j + u, cnt - 1);
+        const unsigned s = __shfl_sync(0xffffffffu, my_idx, jj);
+        const float w = (j + u < cnt) ? __shfl_sync(0xffffffffu, my_w, jj) : 0.f;
+        ld_cpl<2>(e[u], P.e_nbr + (size_t)s * P.ld_nbr + 2 * lane);
+        xw[u] = __ldg(xcol + (size_t)s * P.B) * w;
+      }
+#pragma unroll
+      for (int u = 0; u < EU; ++u) xsm[u * 32 + lane] = xw[u];
+      __syncwarp();
+#pragma unroll
+      for (int u = 0; u < EU; ++u) {
+        const u64 e0 = pk2(e[u][0], e[u][0]), e1 = pk2(e[u][1], e[u][1]);
+        const ulonglong2* xp = reinterpret_cast<const ulonglong2*>(xsm + u * 32);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const ulonglong2 v = xp[i];   // replicas 4i .. 4i+3
+          acc[0][2 * i] = fma2(v.x, e0, acc[0][2 * i]);
+          acc[0][2 * i + 1] = fma2(v.y, e0, acc[0][2 * i + 1]);
+          acc[1][2 * i] = fma2(v.x, e1, acc[1][2 * i]);
+          acc[1][2 * i + 1] = fma2(v.y, e1, acc[1][2 * i + 1]);
+        }
+      }
+      __syncwarp();   // the next batch overwrites the row
+    }
+  }
+  xsm[lane] = __ldg(xcol + (size_t)row * P.B);
+  __syncwarp();
+  const u64 inv2 = pk2(inv, inv), es0 = pk2(es[0], es[0]), es1 = pk2(es[1], es[1]), bs0 = pk2(bs[0], bs[0]),
+            bs1 = pk2(bs[1], bs[1]);
+  unsigned lo_w = 0u, hi_w = 0u;     // lane b keeps the sign words of replica rb0 + b; one coalesced 8-byte store per lane
+  const ulonglong2* xp = reinterpret_cast<const ulonglong2*>(xsm);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const ulonglong2 v = xp[i];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int j = 2 * i + h;
+      const u64 xb = h ? v.y : v.x;
+      float z[2][2];   // [replica of the pair][channel]
+      upk2(fma2(es0, xb, fma2(acc[0][j], inv2, bs0)), z[0][0], z[1][0]);
+      upk2(fma2(es1, xb, fma2(acc[1][j], inv2, bs1)), z[0][1], z[1][1]);
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const int b = 2 * j + r;
+        const float y0 = z[r][0] > 0.f ? z[r][0] : z[r][0] * P.slope;
+        const float y1 = z[r][1] > 0.f ? z[r][1] : z[r][1] * P.slope;
+        float* dst = P.out + ((size_t)(rb0 + b) * P.n + row) * P.ld_out + 2 * lane;
+        *reinterpret_cast<float2*>(dst) = make_float2(y0, y1);
+        if (P.mbits) {   // same bit layout as the scalar pass
+          const unsigned b0 = __ballot_sync(0xffffffffu, y0 > 0.f), b1 = __ballot_sync(0xffffffffu, y1 > 0.f);
+          if (lane == b) { lo_w = b0; hi_w = b1; }
+        }
+      }
+    }
+  }
+  if (P.mbits) {
+    auto even = [](unsigned v) {   // gather bits 0, 2, 4, ... into the low 16 bits
+      v &= 0x55555555u;
+      v = (v | (v >> 1)) & 0x33333333u;
+      v = (v | (v >> 2)) & 0x0f0f0f0fu;
+      v = (v | (v >> 4)) & 0x00ff00ffu;
+      v = (v | (v >> 8)) & 0x0000ffffu;
+      return v;
+    };
+    const unsigned lo = even(lo_w) | (even(hi_w) << 16);
+    const unsigned hi = even(lo_w >> 1) | (even(hi_w >> 1) << 16);
+    P.mbits[(size_t)row * P.B + rb0 + lane] = ((unsigned long long)hi << 32) | lo;
+  }
+  __syncwarp();
+}
+
+template <int CPL, bool PACKED>
 __global__ void __launch_bounds__(kThreads, 2) sage_rank1_fwd_rows_kernel(const R1F P) {
+  __shared__ __align__(16) float xsm[kThreads / 32][EU][32];
   const int lane = threadIdx.x & 31;
   const long long slot = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (slot >= P.n) return;
@@ -137,8 +233,15 @@ __global__ void __launch_bounds__(kThreads, 2) sage_rank1_fwd_rows_kernel(const 
   for (int k = 0; k < CPL; ++k) bs[k] = P.bias ? __ldg(P.bias + CPL * lane + k) : 0.f;
   for (int rb0 = 0; rb0 < P.B; rb0 += 32) {
     const int nb = min(32, P.B - rb0);
-    if (nb == 32) rank1_rows_pass<CPL, true>(P, row, beg, end, inv, es, bs, rb0, nb, lane);
-    else rank1_rows_pass<CPL, false>(P, row, beg, end, inv, es, bs, rb0, nb, lane);
+    if (nb == 32) {
+      if constexpr (CPL == 2 && PACKED) {
+        rank1_rows_pass_packed(P, row, beg, end, inv, es, bs, rb0, lane, xsm[threadIdx.x >> 5][0]);
+      } else {
+        rank1_rows_pass<CPL, true>(P, row, beg, end, inv, es, bs, rb0, nb, lane);
+      }
+    } else {
+      rank1_rows_pass<CPL, false>(P, row, beg, end, inv, es, bs, rb0, nb, lane);
+    }
   }
 }
 
@@ -188,8 +291,12 @@ extern "C" int mlg_sage_rank1_fwd_rows(const float* xs_t, const float* e_self, i
   P.n = (int)n_rows; P.B = (int)replicas;
   const unsigned grid = (unsigned)mlg_ceil_div(n_rows, kThreads / 32);
   cudaStream_t st = (cudaStream_t)stream;
-  if (C == 64) sage_rank1_fwd_rows_kernel<2><<<grid, kThreads, 0, st>>>(P);
-  else sage_rank1_fwd_rows_kernel<1><<<grid, kThreads, 0, st>>>(P);
+  // the packed-pair pass needs 16-byte aligned rows of the transposed node values (B % 4 == 0, cudaMalloc'ed xs_t)
+  static const bool packed_off = getenv("MLG_R1F_PACKED_OFF") != nullptr;   // A/B switch (measurement only)
+  const int packed = (!packed_off && replicas % 4 == 0 && (uintptr_t)xs_t % 16 == 0) ? 1 : 0;
+  if (C == 64 && packed) sage_rank1_fwd_rows_kernel<2, true><<<grid, kThreads, 0, st>>>(P);
+  else if (C == 64) sage_rank1_fwd_rows_kernel<2, false><<<grid, kThreads, 0, st>>>(P);
+  else sage_rank1_fwd_rows_kernel<1, false><<<grid, kThreads, 0, st>>>(P);
   MLG_CHECK_LAUNCH("mlg_sage_rank1_fwd_rows");
   return MLG_OK;
 }
