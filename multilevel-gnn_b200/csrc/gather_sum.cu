@@ -651,10 +651,16 @@ struct R1B {
 #define MLG_R1B_YB 8       // replicas whose y values (self-masking) are requested together
 #endif
 
-template <int CPL>
+// PACKED (C == 64, B % 32 == 0, transposed node values): the per-entry dot products over the 32 replicas run on replica
+// PAIRS -- the gradient rows are packed once per gene, the neighbour's replica values come back from a warp-private
+// shared-memory row as eight broadcast LDS.128 (16 register pairs), so an entry costs 8 LDS.128 + 32 FFMA2 instead of
+// 32 SHFL + 64 FFMA (same restructuring as sage_rank1.cu's forward; the even / odd replica halves are added at the end).
+template <int CPL, bool PACKED>
 __global__ void __launch_bounds__(kThreads, MLG_R1B_MINB) sage_rank1_bwd_rows_kernel(const R1B P) {
   constexpr int C = 32 * CPL;
   constexpr int EU = 4;   // entries whose x loads are in flight together
+  __shared__ __align__(16) float xsm_all[PACKED ? kThreads / 32 : 1][EU][32];
+  float* xsm = &xsm_all[PACKED ? (threadIdx.x >> 5) : 0][0][0];
   const int lane = threadIdx.x & 31;
   const long long slot = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (slot >= P.n) return;
@@ -700,18 +706,54 @@ __global__ void __launch_bounds__(kThreads, MLG_R1B_MINB) sage_rank1_bwd_rows_ke
     const float* xp = P.xs_t ? P.xs + rb0 + min(lane, nb - 1) : P.xs + (size_t)(rb0 + min(lane, nb - 1)) * P.n;
     const size_t xstride = P.xs_t ? (size_t)P.B : 1;
     const float lane_live = lane < nb ? 1.f : 0.f;
+    u64 gp2[PACKED ? CPL : 1][PACKED ? 16 : 1];   // (replica 2j, replica 2j + 1) of this lane's channels
+    if constexpr (PACKED) {
+#pragma unroll
+      for (int k = 0; k < CPL; ++k)
+#pragma unroll
+        for (int j = 0; j < 16; ++j) gp2[k][j] = pk2(g[k][2 * j], g[k][2 * j + 1]);
+    }
     {
       const float xv = __ldg(xp + row * xstride) * lane_live;
       float e1[CPL], gb[CPL];
+      if constexpr (PACKED) {
+        xsm[lane] = xv;
+        __syncwarp();
+        u64 e2[CPL], b2[CPL];
 #pragma unroll
-      for (int k = 0; k < CPL; ++k) e1[k] = gb[k] = 0.f;
+        for (int k = 0; k < CPL; ++k) e2[k] = b2[k] = 0ull;
+        const ulonglong2* xq = reinterpret_cast<const ulonglong2*>(xsm);
 #pragma unroll
-      for (int b = 0; b < 32; ++b) {
-        const float xb = __shfl_sync(0xffffffffu, xv, b);
+        for (int i = 0; i < 8; ++i) {
+          const ulonglong2 v = xq[i];
+#pragma unroll
+          for (int k = 0; k < CPL; ++k) {
+            e2[k] = fma2(v.x, gp2[k][2 * i], e2[k]);
+            e2[k] = fma2(v.y, gp2[k][2 * i + 1], e2[k]);
+            b2[k] = add2(b2[k], gp2[k][2 * i]);
+            b2[k] = add2(b2[k], gp2[k][2 * i + 1]);
+          }
+        }
 #pragma unroll
         for (int k = 0; k < CPL; ++k) {
-          e1[k] = fmaf(xb, g[k][b], e1[k]);
-          gb[k] += g[k][b];
+          float lo, hi;
+          upk2(e2[k], lo, hi);
+          e1[k] = lo + hi;
+          upk2(b2[k], lo, hi);
+          gb[k] = lo + hi;
+        }
+        __syncwarp();
+      } else {
+#pragma unroll
+        for (int k = 0; k < CPL; ++k) e1[k] = gb[k] = 0.f;
+#pragma unroll
+        for (int b = 0; b < 32; ++b) {
+          const float xb = __shfl_sync(0xffffffffu, xv, b);
+#pragma unroll
+          for (int k = 0; k < CPL; ++k) {
+            e1[k] = fmaf(xb, g[k][b], e1[k]);
+            gb[k] += g[k][b];
+          }
         }
       }
 #pragma unroll
@@ -734,18 +776,45 @@ __global__ void __launch_bounds__(kThreads, MLG_R1B_MINB) sage_rank1_bwd_rows_ke
           const unsigned s = __shfl_sync(0xffffffffu, my_idx, min(j + u, cnt - 1));
           xv[u] = __ldg(xp + s * xstride) * lane_live;
         }
+        if constexpr (PACKED) {
+#pragma unroll
+          for (int u = 0; u < EU; ++u) xsm[u * 32 + lane] = xv[u];
+          __syncwarp();
+        }
 #pragma unroll
         for (int u = 0; u < EU; ++u) {
           if (j + u < cnt) {   // warp-uniform
             const float w = __shfl_sync(0xffffffffu, my_w, j + u);
             float hk[CPL];
+            if constexpr (PACKED) {
+              u64 h2[CPL];
 #pragma unroll
-            for (int k = 0; k < CPL; ++k) hk[k] = 0.f;
+              for (int k = 0; k < CPL; ++k) h2[k] = 0ull;
+              const ulonglong2* xq = reinterpret_cast<const ulonglong2*>(xsm + u * 32);
 #pragma unroll
-            for (int b = 0; b < 32; ++b) {
-              const float xb = __shfl_sync(0xffffffffu, xv[u], b);
+              for (int i = 0; i < 8; ++i) {
+                const ulonglong2 v = xq[i];
 #pragma unroll
-              for (int k = 0; k < CPL; ++k) hk[k] = fmaf(xb, g[k][b], hk[k]);
+                for (int k = 0; k < CPL; ++k) {
+                  h2[k] = fma2(v.x, gp2[k][2 * i], h2[k]);
+                  h2[k] = fma2(v.y, gp2[k][2 * i + 1], h2[k]);
+                }
+              }
+#pragma unroll
+              for (int k = 0; k < CPL; ++k) {
+                float lo, hi;
+                upk2(h2[k], lo, hi);
+                hk[k] = lo + hi;
+              }
+            } else {
+#pragma unroll
+              for (int k = 0; k < CPL; ++k) hk[k] = 0.f;
+#pragma unroll
+              for (int b = 0; b < 32; ++b) {
+                const float xb = __shfl_sync(0xffffffffu, xv[u], b);
+#pragma unroll
+                for (int k = 0; k < CPL; ++k) hk[k] = fmaf(xb, g[k][b], hk[k]);
+              }
             }
 #pragma unroll
             for (int k = 0; k < CPL; ++k) {
@@ -754,6 +823,7 @@ __global__ void __launch_bounds__(kThreads, MLG_R1B_MINB) sage_rank1_bwd_rows_ke
             }
           }
         }
+        if constexpr (PACKED) __syncwarp();   // the next batch overwrites the rows
       }
     }
   }
@@ -1013,8 +1083,10 @@ extern "C" int mlg_sage_rank1_bwd_rows(const float* gz, int64_t ld_g, const floa
   P.xs_t = xs_transposed;
   const unsigned grid = (unsigned)mlg_ceil_div(n_rows, kThreads / 32);
   cudaStream_t st = (cudaStream_t)stream;
-  if (C == 64) sage_rank1_bwd_rows_kernel<2><<<grid, kThreads, 0, st>>>(P);
-  else sage_rank1_bwd_rows_kernel<1><<<grid, kThreads, 0, st>>>(P);
+  static const bool packed_off = getenv("MLG_R1B_PACKED_OFF") != nullptr;   // A/B switch (measurement only)
+  if (C == 64 && !packed_off && P.xs_t && P.B % 32 == 0) sage_rank1_bwd_rows_kernel<2, true><<<grid, kThreads, 0, st>>>(P);
+  else if (C == 64) sage_rank1_bwd_rows_kernel<2, false><<<grid, kThreads, 0, st>>>(P);
+  else sage_rank1_bwd_rows_kernel<1, false><<<grid, kThreads, 0, st>>>(P);
   MLG_CHECK_LAUNCH("mlg_sage_rank1_bwd_rows");
   return MLG_OK;
 }

@@ -1,0 +1,17 @@
+#!/bin/bash
+# packed-pair first-layer backward (MLG_R1B_PACKED_OFF=1 selects the scalar pass): tests + A/B
+cd "$(dirname "$0")/.."
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests -m gpu -q -p no:cacheprovider -k "rank1 or factored or multilevel or fullsize or trainer or wide or sage or activation" > gpurun_out/r02_pytest_r1b.log 2>&1
+echo "pytest rc=$?"; grep -E "^(FAILED|ERROR)" gpurun_out/r02_pytest_r1b.log | head; tail -2 gpurun_out/r02_pytest_r1b.log
+for i in 1 2; do
+MLG_R1B_PACKED_OFF=1 python bench.py --no-cpu-baseline --no-diffpool --no-genconv --no-strong > gpurun_out/r02_ab_r1b_off$i.log 2>&1; echo "off rc=$?"
+python bench.py --no-cpu-baseline --no-diffpool --no-genconv --no-strong > gpurun_out/r02_ab_r1b_on$i.log 2>&1; echo "on rc=$?"
+done
+python - <<'PY'
+import json
+for n in ("off1","on1","off2","on2"):
+    d=json.loads(open(f"gpurun_out/r02_ab_r1b_{n}.log").read().strip().splitlines()[-1])
+    ak=d["roofline"]["all_kernels"]
+    print(n, d["ms_per_step"], d["value"], d["loss"], {k:v["ms_per_step"] for k,v in ak.items() if "rank1" in k})
+PY
