@@ -583,6 +583,9 @@ def run_b200(a):
     timer = _cabi.KernelTimer()
     _cabi.TIMER = timer
     for _ in range(a.steps):
+        # a device-side delay in front of every eager step: the host (a few ms of Python per eager step) enqueues the whole step
+        # while the GPU spins, so a span measures its kernel and not the wait for a launch that had not been issued yet
+        torch.cuda._sleep(16_000_000)
         tr._step_eager(resident)
     torch.cuda.synchronize()
     _cabi.TIMER = None
@@ -632,7 +635,7 @@ def run_b200(a):
                 "launches": d["launches"], "avg_us": round(d["ms"] / d["launches"] * 1e3, 2),
                 "share_of_step": round(d["ms"] / ms_total, 4),
                 "algorithmic_bytes": info.get("alg", "see DESIGN.md section 4"),
-                "timed": "CUDA events around each launch in an eager pass of the same %d steps (the timed region itself "
+                "timed": "CUDA events around each launch in an eager pass of the same %d steps, each step queued behind an 8 ms device-side delay so that no span waits for the host (the timed region itself "
                          "is a CUDA-graph replay)" % a.steps,
                 "back_to_back": dominant_kernel_alone(resident, hbm_peak),
                 "all_kernels": {k: {"bound": v["bound"], "ms_per_step": round(v["ms"] / a.steps, 4),
