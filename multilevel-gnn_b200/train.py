@@ -419,6 +419,7 @@ class Trainer:
         self._topo_ref = {k: getattr(batch, k).clone() for k in self.STATIC_TOPOLOGY_FIELDS
                           if torch.is_tensor(getattr(batch, k, None))}
         self._topo_bad = torch.zeros((), dtype=torch.bool, device=self.flat.device)
+        self._topo_compared = False
         cur = torch.cuda.current_stream()
         side = torch.cuda.Stream()
         side.wait_stream(cur)
@@ -485,6 +486,7 @@ class Trainer:
         for k in fields:
             if k in ref:
                 self._topo_bad.logical_or_((getattr(self.static_batch, k) != ref[k]).any())
+                self._topo_compared = True      # from now on the flag travels to the host with every loss
 
     def check_topology_flag(self):
         """Host-side check (one sync) that no keyless batch with a different topology was fed to the captured graph."""
@@ -529,8 +531,8 @@ class Trainer:
             raise RuntimeError("Trainer: the fused NVLink update timed out waiting for a peer rank")
         cur = torch.cuda.current_stream()
         cur.wait_event(self._staged)
-        for k, v in self._staging.items():
-            getattr(self.static_batch, k).copy_(v, non_blocking=True)
+        # staging -> static buffers: one multi-tensor launch per dtype instead of one copy kernel per field
+        torch._foreach_copy_([getattr(self.static_batch, k) for k in self._staging], list(self._staging.values()))
         self._consumed.record()
         self._verify_uploaded_topology(self._staging)
         return self._replay()
@@ -546,7 +548,7 @@ class Trainer:
         i = self._loss_slot
         self._loss_slot = (i + 1) % len(self._loss_ring)
         self._loss_ring[i][:1].copy_(loss.reshape(1), non_blocking=True)
-        if getattr(self, "_topo_bad", None) is not None:
+        if getattr(self, "_topo_compared", False):      # keyed batches never upload a topology: nothing to report
             self._loss_ring[i][1:].copy_(self._topo_bad.reshape(1), non_blocking=True)
         self._loss_events[i].record()
         return _PendingLoss(self._loss_ring[i], self._loss_events[i])
