@@ -891,6 +891,67 @@ def test_cuda_graph_step_equals_eager(mlg):
         assert_close(results[1][1][k], results[0][1][k], rtol=1e-5, atol=1e-6, what="graph vs eager: " + k)
 
 
+def test_captured_trainer_prefetch_keyed_and_keyless_batches(mlg):
+    """The end-to-end path bench.py's `e2e` legs use (Trainer.prefetch -> step_prefetched -> loss_to_host):
+    * a host batch fed through the staging buffers gives the loss an eager step on the same weights gives;
+    * a keyless batch (the reference loader's layout: topology re-sent every step, train.py:42) with the SAME topology is
+      accepted, one with ANOTHER edge list raises when its loss is read -- the topology is frozen at capture();
+    * a keyed batch with a different key is refused before anything is copied."""
+    import copy
+    from multilevel_gnn_b200.train import Trainer
+    c = load_golden("multilevel")["kirc"]
+    model, args = _build_multilevel(mlg, c)
+    args.lr = 1e-3
+    model.drop1.p = 0.0
+    model.head[2].p = 0.0
+    model.pathway_indexs = model.pathway_indexs.to(DEV)
+    host = as_batch({k: (v.pin_memory() if torch.is_tensor(v) else v) for k, v in c["batch"].items()})
+    twin = copy.deepcopy(model)
+    tr = Trainer(model, args, c["weight"].to(DEV))
+    tr.capture(as_batch(c["batch"], DEV), warmup=3)
+    ref = Trainer(twin, args, c["weight"].to(DEV))
+    for _ in range(3):
+        ref.step(as_batch(c["batch"], DEV))
+    # (1) same data through the staging buffers: step 4 of both trainers
+    host2 = as_batch({k: (v.clone().pin_memory() if torch.is_tensor(v) else v) for k, v in c["batch"].items()})
+    host2.x = (host2.x * 0.5).pin_memory()
+    tr.prefetch(host2)
+    got = tr.loss_to_host(tr.step_prefetched()).get()
+    b2 = as_batch(c["batch"], DEV)
+    b2.x = b2.x * 0.5
+    want = float(ref.step(b2))
+    assert abs(got - want) <= 1e-5 * max(1.0, abs(want)), (got, want)
+    # (2) keyless batch, same topology: fine (and the flag stays clear)
+    tr.prefetch(host)
+    tr.loss_to_host(tr.step_prefetched()).get()
+    tr.check_topology_flag()
+    # (3) keyless batch with another edge list: the mismatch surfaces with the loss
+    bad = as_batch({k: (v.clone().pin_memory() if torch.is_tensor(v) else v) for k, v in c["batch"].items()})
+    ei = bad.edge_index.clone()
+    ei[0, 0] = (ei[0, 0] + 1) % int(ei.max())
+    bad.edge_index = ei.pin_memory()
+    tr.prefetch(bad)
+    with pytest.raises(RuntimeError, match="different topology"):
+        tr.loss_to_host(tr.step_prefetched()).get()
+    # (4) keyed batches: the key the graph was captured with is required
+    model3, args3 = _build_multilevel(mlg, c)
+    model3.pathway_indexs = model3.pathway_indexs.to(DEV)
+    dev_keyed = as_batch(c["batch"], DEV)
+    dev_keyed.topology_key = "fold-0"
+    tr3 = Trainer(model3, args3, c["weight"].to(DEV))
+    tr3.capture(dev_keyed, warmup=3)
+    other = as_batch({k: (v.pin_memory() if torch.is_tensor(v) else v) for k, v in c["batch"].items()})
+    other.topology_key = "fold-1"
+    with pytest.raises(ValueError, match="frozen at capture"):
+        tr3.prefetch(other)
+    same = as_batch({k: (v.pin_memory() if torch.is_tensor(v) else v) for k, v in c["batch"].items()})
+    same.topology_key = "fold-0"
+    tr3.prefetch(same)
+    assert set(tr3._staging) == {k for k in vars(dev_keyed) if torch.is_tensor(getattr(dev_keyed, k))} - set(Trainer.STATIC_TOPOLOGY_FIELDS)
+    loss = tr3.loss_to_host(tr3.step_prefetched()).get()
+    assert loss == loss
+
+
 # ------------------------------------------------------------------------------------------------
 # edge cases: empty / ragged / non-replicated inputs
 # ------------------------------------------------------------------------------------------------
