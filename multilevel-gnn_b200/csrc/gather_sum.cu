@@ -95,6 +95,8 @@ __device__ __forceinline__ void ldv(float (&d)[VEC], const float* p, bool ok) {
   }
 }
 // unconditional load that cannot be sunk below later arithmetic
+// (measured: the same load with L1::no_allocate -- the gathered rows are not re-used by this SM -- is SLOWER, 72 -> 94 us per
+// launch at the gbm shape; the plain read-only path it is)
 template <int VEC>
 __device__ __forceinline__ void ldv_now(float (&d)[VEC], const float* p) {
   if (VEC == 4) {
@@ -1083,8 +1085,7 @@ extern "C" int mlg_sage_rank1_bwd_rows(const float* gz, int64_t ld_g, const floa
   P.xs_t = xs_transposed;
   const unsigned grid = (unsigned)mlg_ceil_div(n_rows, kThreads / 32);
   cudaStream_t st = (cudaStream_t)stream;
-  static const bool packed_off = getenv("MLG_R1B_PACKED_OFF") != nullptr;   // A/B switch (measurement only)
-  if (C == 64 && !packed_off && P.xs_t && P.B % 32 == 0) sage_rank1_bwd_rows_kernel<2, true><<<grid, kThreads, 0, st>>>(P);
+  if (C == 64 && P.xs_t && P.B % 32 == 0) sage_rank1_bwd_rows_kernel<2, true><<<grid, kThreads, 0, st>>>(P);
   else if (C == 64) sage_rank1_bwd_rows_kernel<2, false><<<grid, kThreads, 0, st>>>(P);
   else sage_rank1_bwd_rows_kernel<1, false><<<grid, kThreads, 0, st>>>(P);
   MLG_CHECK_LAUNCH("mlg_sage_rank1_bwd_rows");

@@ -775,13 +775,11 @@ extern "C" int mlg_pool_fwd(const float* x, const float* vm, const int64_t* matc
   MLG_P_SWITCH(P, (pool_fwd_vec_kernel<P_, VV><<<grid, kThreads, 0, (cudaStream_t)stream>>>(                    \
                       x, vm, (const long long*)match, w, seg_rowptr, seg_slot, (int)B, (int)N, (int)G, (int)S,  \
                       wrap_negative, out_cl)))
-  static const bool c32_off = getenv("MLG_POOL_C32_OFF") != nullptr;   // A/B switch (measurement only)
-  if (vec_ok && C == 32 && !c32_off) {
+  if (vec_ok && C == 32) {
     MLG_P_SWITCH(P, (pool_fwd_c32_kernel<P_><<<grid, kThreads, 0, (cudaStream_t)stream>>>(
                         x, vm, (const long long*)match, w, seg_rowptr, seg_slot, (int)B, (int)N, (int)G, (int)S,
                         wrap_negative, out_cl)));
   }
-  else if (vec_ok && C == 32) { MLG_POOL_FV(1); }
   else if (vec_ok && C == 64) { MLG_POOL_FV(2); }
   else if (vec_ok) { MLG_POOL_FV(4); }
   else {
@@ -844,13 +842,11 @@ extern "C" int mlg_pool_bwd(const float* g_out_cl, const float* x, const float* 
   static const bool v1_only = getenv("MLG_POOL_BWD_V1") != nullptr;
   if (!v1_only && replicas > 1 && (C == 32 || C == 64 || C == 128) && (uintptr_t)g_out_cl % 16 == 0 && (uintptr_t)x % 16 == 0 &&
       (uintptr_t)g_x % 16 == 0) {
-    // vector-lane kernel; replicas per warp chosen so that RB2 * pow2(P) <= 32 packed dot products
-    // C = 32: 4 replicas per warp (64 registers, 32 warps / SM) instead of 8 (124 registers, 16 warps / SM): the kernel is
-    // bound by its dependent loads (rowptr -> slot -> segment -> rows), so resident warps matter more than work per warp
-    // (step 0.850 -> 0.834 ms at the gbm shape).
-    // (2 per warp at 40 registers / 48 warps was slower again: 0.846 ms.)
-    static const bool c32_off = getenv("MLG_POOL_C32_OFF") != nullptr;   // A/B switch (measurement only)
-    if (C == 32 && !c32_off) {
+    // vector-lane kernels.  C = 32 has its own kernel (8-lane groups on 128-bit lanes); before it, the 32-lane kernel ran
+    // best at 4 replicas per warp (64 registers, 32 warps / SM; 8 per warp: 124 registers / 16 warps, 2 per warp: 48 warps,
+    // both slower): the kernel is bound by its dependent loads (rowptr -> slot -> segment -> rows), so resident warps
+    // matter more than work per warp.
+    if (C == 32) {
       // 8-lane groups x 128-bit lanes: 8 replicas per warp; the weight-gradient partials are already summed over a warp's
       // replicas, so the workspace holds one [G, P] slice per replica chunk (B / 8 of them) instead of one per graph
       constexpr int rw = 8;
@@ -867,15 +863,15 @@ extern "C" int mlg_pool_bwd(const float* g_out_cl, const float* x, const float* 
       return MLG_OK;
     }
     MLG_CUDA(cudaMemsetAsync(workspace, 0, (size_t)B * G * P * sizeof(float), st));   // slots without a node stay zero
-    const int rb2 = C == 32 ? 4 : (P <= 4 ? 8 : 4);
+    // C = 64 / 128: replicas per warp chosen so that RB2 * pow2(P) <= 32 packed dot products
+    const int rb2 = P <= 4 ? 8 : 4;
     const long long warps2 = n_rows * ((replicas + rb2 - 1) / rb2);
     const int grid2 = mlg_ceil_div(warps2, kThreads / 32);
 #define MLG_POOL_F2(VV, RR)                                                                                           \
   MLG_P_SWITCH(P, (pool_bwd_fused2_kernel<P_, VV, RR><<<grid2, kThreads, 0, st>>>(                                     \
                       g_out_cl, x, vm, w, node_rowptr, node_slot, seg_of_slot, (int)n_rows, (int)replicas, (int)S,     \
                       (int)G, g_x, workspace, mask_input, mask_slope)))
-    if (C == 32) { MLG_POOL_F2(1, 4); }
-    else if (C == 64) { MLG_POOL_F2(2, (P_ <= 4 ? 8 : 4)); }
+    if (C == 64) { MLG_POOL_F2(2, (P_ <= 4 ? 8 : 4)); }
     else { MLG_POOL_F2(4, (P_ <= 4 ? 8 : 4)); }
 #undef MLG_POOL_F2
     MLG_CHECK_LAUNCH("mlg_pool_bwd(fused2)");

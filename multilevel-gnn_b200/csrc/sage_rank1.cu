@@ -11,8 +11,6 @@
 // then broadcasts the replica values by shuffle: 32 SHFL + 32 FMUL + 64 FFMA per entry, four entries' loads in flight.
 // The epilogue writes 32 coalesced 256-byte rows and (optionally) the 64 sign bits per (gene, replica) the backward kernel
 // uses instead of re-reading the activation.
-#include <cstdlib>
-
 #include "common.cuh"
 #include "../../include/mlg_b200.h"
 
@@ -292,8 +290,7 @@ extern "C" int mlg_sage_rank1_fwd_rows(const float* xs_t, const float* e_self, i
   const unsigned grid = (unsigned)mlg_ceil_div(n_rows, kThreads / 32);
   cudaStream_t st = (cudaStream_t)stream;
   // the packed-pair pass needs 16-byte aligned rows of the transposed node values (B % 4 == 0, cudaMalloc'ed xs_t)
-  static const bool packed_off = getenv("MLG_R1F_PACKED_OFF") != nullptr;   // A/B switch (measurement only)
-  const int packed = (!packed_off && replicas % 4 == 0 && (uintptr_t)xs_t % 16 == 0) ? 1 : 0;
+  const int packed = (replicas % 4 == 0 && (uintptr_t)xs_t % 16 == 0) ? 1 : 0;
   if (C == 64 && packed) sage_rank1_fwd_rows_kernel<2, true><<<grid, kThreads, 0, st>>>(P);
   else if (C == 64) sage_rank1_fwd_rows_kernel<2, false><<<grid, kThreads, 0, st>>>(P);
   else sage_rank1_fwd_rows_kernel<1, false><<<grid, kThreads, 0, st>>>(P);
