@@ -8,7 +8,9 @@
 // warp owns ONE gene for ALL (up to 32) replicas at once: lane l keeps channels (2l, 2l+1) of the 32 replicas in 64
 // accumulator registers; per CSR entry the warp loads the neighbour's table row ONCE (one coalesced 256-byte load) and the
 // neighbour's 32 replica values ONCE (one coalesced 128-byte load from the transposed node-value matrix xs_t [n][B]),
-// then broadcasts the replica values by shuffle: 32 SHFL + 32 FMUL + 64 FFMA per entry, four entries' loads in flight.
+// four entries' loads in flight.  The scalar pass then broadcasts the replica values by shuffle (32 SHFL + 64 FFMA per
+// entry); with all 32 replica slots live and C == 64 the packed pass below does the same arithmetic on replica pairs
+// (8 broadcast LDS.128 + 32 FFMA2 per entry).
 // The epilogue writes 32 coalesced 256-byte rows and (optionally) the 64 sign bits per (gene, replica) the backward kernel
 // uses instead of re-reading the activation.
 #include "common.cuh"

@@ -608,9 +608,14 @@ class SageLayer(torch.autograd.Function):
         out = act( [x | agg_x] @ [W1 | W2 @ W_r]^T + b ),   nn.0.weight = [W1 | W2], lin_r.weight = W_r
     i.e. the reference's  nn(cat(x, mean_j(w_ij x_j) @ W_r^T))  with the two chained Linears folded into
     one GEMM over the concatenated buffer (fp reassociation only).
-    Kernels: mlg_gather_sum writes agg_x and the copy of x straight into the two halves of the [N, 2Cin]
-    buffer (no torch.cat); the GEMMs are cuBLAS fp32; the weight/bias gradient is mlg_xty; the backward
-    aggregation reads the right half of d[x|agg_x] in place and adds the left half."""
+    Three evaluation orders of the same lines, chosen per layer:
+    * generic: mlg_gather_sum writes agg_x and the copy of x straight into the two halves of the [N, 2Cin] buffer (no
+      torch.cat), one mlg_gemm_tf32x3 update GEMM with bias + activation in its epilogue; backward: mlg_xty_tc / mlg_xty
+      weight gradient, mlg_gemm_tf32x3 dX, the backward aggregation reads the right half of d[x|agg_x] in place and adds
+      the left half;
+    * factored (MultilevelGNN's first layer, rank-1 input): per-gene tables + mlg_sage_rank1_fwd_rows / _bwd_rows;
+    * transform-first (out_channels < in_channels): [U | V] GEMM, then the aggregation on the narrower rows.
+    The last two take their weights from mlg_sage_fold_stacked_fwd (stacked weight, both 3xTF32 splits, bias: one launch)."""
 
     @staticmethod
     def forward(ctx, x, xs, lin_r_w, nn_w, nn_b, topo, relative, slope, in_slope=None, out_premasked=False):
