@@ -2,11 +2,14 @@
 ``dense_diff_pool`` semantics restated from SURVEY.md Appendix A).
 
 Same constructors, ``forward(x, adj, mask=None) -> (x, l_total, e_total)`` and state_dict keys
-(``diffpool_layers.{i}.gnn_pool.layers.0.lin_rel.weight`` ...).  The dense contractions
-(A.X, S^T.X, S^T.A.S, S.S^T) go through ``dense_ops.matmul``: cuBLAS fp32 at the reference's size
-(146 nodes -> 37 -> 10 clusters: launch-bound, tensor cores are irrelevant there) and the hand-written
-tcgen05/TMA bf16 GEMM (``mlg_gemm_bf16``) once the operands are large enough for the tensor pipe
-(``dense_ops.TENSOR_CORE_MIN``), e.g. the synthetic N=10k / K=2.5k / C=1024 shape of SURVEY section 8(d).
+(``diffpool_layers.{i}.gnn_pool.layers.0.lin_rel.weight`` ...).  Two paths behind ``DiffPool.forward``:
+* the reference's size (one shared 146-node adjacency, 146 -> 37 -> 10 clusters, hundreds of samples): the whole module
+  -- both DenseSAGE stacks, softmax, S^T.X, S^T.A.S, link and entropy terms -- is ONE kernel per direction
+  (``csrc/diffpool_fused.cu``, one persistent CTA per sample, shared-memory resident), see ``DiffPool._fused_plan``;
+* everything else goes layer by layer through ``dense_ops``: the contractions (A.X, S^T.X, S^T.A.S, S.S^T) and the
+  DenseSAGE projections on the hand-written tcgen05/TMA bf16 GEMM (``mlg_gemm_bf16``) once the operands are large
+  enough for the tensor pipe (``dense_ops.TENSOR_CORE_MIN``), e.g. the synthetic N=10k / K=2.5k / C=1024 shape of
+  SURVEY section 8(d); the library fp32 product only for small operands that fit neither path.
 """
 from math import ceil
 
