@@ -1,4 +1,5 @@
 #!/bin/bash
+# (historical: the environment switch this A/B used existed only in the commit it was run on; results: profiles/r02_ab_end_of_round.jsonl)
 # A/B of the C == 32 128-bit-lane pool kernels (MLG_POOL_C32_OFF=1 selects the previous kernels) + the tests that cover them
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out

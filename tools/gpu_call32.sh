@@ -1,4 +1,5 @@
 #!/bin/bash
+# (historical: the environment switch this A/B used existed only in the commit it was run on; results: profiles/r02_ab_end_of_round.jsonl)
 # programmatic dependent launch: the whole GPU suite with it on (default), then A/B of the gbm step and the DeeperGCN step
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out

@@ -1,4 +1,5 @@
 #!/bin/bash
+# (historical: the environment switch this A/B used existed only in the commit it was run on; results: profiles/r02_ab_end_of_round.jsonl)
 # packed-pair first-layer backward (MLG_R1B_PACKED_OFF=1 selects the scalar pass): tests + A/B
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
