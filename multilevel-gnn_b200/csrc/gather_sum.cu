@@ -968,6 +968,8 @@ extern "C" int mlg_gather_sum_act(const float* src, int64_t ld_src, const int32_
     const bool rank1 = rep_rows_src == 0;
     MLG_CHECK_ARG(rank1 || rep_rows_pre == 0, "mlg_gather_sum: per-replica pre is only supported with rep_rows_src == 0");
     const unsigned grid = (unsigned)(gx * gy);
+    // (the kernel uses no shared memory and wants the whole L1: with the carve-out forced to 100 % shared memory the gbm-shape
+    // aggregation ran 72 -> 86 us, with 0 % the same as the default)
 #define MLG_REP(L, V)                                                                        \
   if (rank1) gather_sum_rep_kernel<L, V, true><<<grid, kThreads, 0, st>>>(P, gy);            \
   else if (reduce_scale) gather_sum_rep_kernel<L, V, false, true><<<grid, kThreads, 0, st>>>(P, gy); \
