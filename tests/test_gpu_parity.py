@@ -502,6 +502,88 @@ def test_pool_linearity_and_oracle(mlg):
     assert_close(got_w.reshape(ref_w.shape), ref_w, what="pool wrap_negative")
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("P", [1, 2, 3, 5, 8])
+@pytest.mark.parametrize("bsz", [3, 8, 13])
+def test_pool_c32_lane_group_kernels(mlg, P, bsz):
+    """C == 32 pool kernels (8-lane groups on 128-bit lanes, mlg_pool_fwd / mlg_pool_bwd): forward and both gradients
+    against autograd of the oracle's gather / scatter formula (models/multilevel_gnn.py:212-239), with the value mask, for
+    every packed-butterfly width (P -> 1, 2, 4, 8 values per group) and replica counts that leave idle lane groups (3),
+    fill one warp exactly (8) and end in a partial chunk (13)."""
+    from multilevel_gnn_b200 import functional as Fn, graph, synth
+    genes, slots, C = 200, 1500, 32
+    b = synth.multilevel_batch(batch_size=bsz, genes=genes, slots=slots, intra_edges=100, seed=21)
+    n = 3 * genes
+    g = torch.Generator().manual_seed(5 + P)
+    x = torch.randn(bsz * n, C, generator=g)
+    vm = torch.randn(bsz * n, generator=g)
+    w = torch.randn(slots, P, generator=g)
+    mask = (torch.rand(slots, 1, generator=g) < 0.5).float()
+    gout = torch.randn(bsz, C, 438, P, generator=g)
+    lay = graph.pool_layout(b.gene_pca_match.to(DEV), b.raw_indice.to(DEV), n, 438)
+    assert lay.replicas == bsz      # one match / segment table for all graphs: the replicated kernels run
+    xd, wd = x.to(DEV).requires_grad_(True), w.to(DEV).requires_grad_(True)
+    out = Fn.PathwayPool.apply(xd, wd, vm.to(DEV), lay, None, mask.to(DEV))
+    out.backward(gout.to(DEV))
+    xr, wr = x.clone().requires_grad_(True), w.clone().requires_grad_(True)
+    ref = R.multilevel_pool(xr * vm[:, None], b.gene_pca_match, b.raw_indice, wr, mask, n, 438)
+    ref.backward(gout.reshape(ref.shape))
+    assert_close(out.reshape(ref.shape), ref, what="pool C=32 forward P=%d B=%d" % (P, bsz))
+    assert_close(xd.grad, xr.grad, what="pool C=32 dX P=%d B=%d" % (P, bsz))
+    assert_close(wd.grad, wr.grad, what="pool C=32 dW P=%d B=%d" % (P, bsz))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cout,cin,r,bias", [(64, 64, 64, True), (32, 64, 64, True), (32, 64, 48, False)])
+def test_sage_fold_stacked(mlg, cout, cin, r, bias):
+    """mlg_sage_fold_stacked_fwd / _bwd (torch_vertex.py:279-291 with lin_r commuted past the mean): Wst = [W1 ; W2 W_r], the
+    3xTF32 splits (hi keeps the top 19 bits, hi + lo == w exactly), the split of Wst^T, the bias [b | 0]; backward against
+    autograd of the same expression, with the gradient given as one tensor and as the sum of two strided blocks."""
+    from multilevel_gnn_b200 import _cabi
+    L = _cabi.lib()
+    g = torch.Generator().manual_seed(cout + r)
+    nn_w = torch.randn(cout, cin + r, generator=g).to(DEV)
+    w_r = torch.randn(r, cin, generator=g).to(DEV)
+    nn_b = torch.randn(cout, generator=g).to(DEV) if bias else None
+    bufs = [torch.empty(2 * cout, cin, device=DEV) for _ in range(3)] + [torch.empty(cin, 2 * cout, device=DEV) for _ in range(2)]
+    bias2 = torch.full((2 * cout,), 7.0, device=DEV)
+    with torch.cuda.device(DEV):
+        _cabi.check(L.mlg_sage_fold_stacked_fwd(_cabi.fptr(nn_w), _cabi.fptr(w_r), None if nn_b is None else _cabi.fptr(nn_b),
+                                                cout, cin, r, *[_cabi.fptr(t) for t in bufs], _cabi.fptr(bias2),
+                                                _cabi.stream_ptr()), "fold_stacked_fwd")
+    wst, hi, lo, t_hi, t_lo = bufs
+    nn_ref, wr_ref = nn_w.double().cpu().requires_grad_(True), w_r.double().cpu().requires_grad_(True)
+    ref = torch.cat([nn_ref[:, :cin], nn_ref[:, cin:] @ wr_ref], 0)
+    assert_close(wst, ref.detach().float(), rtol=1e-5, atol=1e-6, what="Wst")
+    assert torch.equal(hi + lo, wst) and torch.equal(hi.view(torch.int32) & 0x1FFF, torch.zeros_like(hi, dtype=torch.int32))
+    assert torch.equal(t_hi, hi.t().contiguous()) and torch.equal(t_lo, lo.t().contiguous())
+    want_b = torch.cat([nn_b if bias else torch.zeros(cout, device=DEV), torch.zeros(cout, device=DEV)])
+    assert torch.equal(bias2, want_b)
+    gw = torch.randn(2 * cout, cin, generator=g)
+    ref.backward(gw.double())
+    for split in (False, True):
+        g_nn, g_wr = torch.empty_like(nn_w), torch.empty_like(w_r)
+        if split:     # the gradient as the sum of two blocks of a wider buffer (leading dimension 2 * cin)
+            wide = torch.randn(4 * cout, 2 * cin, generator=g).to(DEV)
+            part = torch.randn(2 * cout, cin, generator=g).to(DEV)
+            wide[:2 * cout, :cin] = part
+            wide[2 * cout:, cin:] = gw.to(DEV) - part
+            a, bptr, ld = _cabi.fptr(wide), ctypes_ptr(wide[2 * cout:, cin:]), 2 * cin
+        else:
+            gd = gw.to(DEV)
+            a, bptr, ld = _cabi.fptr(gd), None, cin
+        with torch.cuda.device(DEV):
+            _cabi.check(L.mlg_sage_fold_stacked_bwd(a, bptr, ld, _cabi.fptr(nn_w), _cabi.fptr(w_r), cout, cin, r,
+                                                    _cabi.fptr(g_nn), _cabi.fptr(g_wr), _cabi.stream_ptr()), "fold_stacked_bwd")
+        assert_close(g_nn, nn_ref.grad.float(), rtol=2e-5, atol=2e-6, what="g_nn_w split=%s" % split)
+        assert_close(g_wr, wr_ref.grad.float(), rtol=2e-5, atol=2e-6, what="g_lin_r_w split=%s" % split)
+
+
+def ctypes_ptr(t):
+    import ctypes
+    return ctypes.c_void_p(t.data_ptr())
+
+
 def test_csr_build_matches_sort(mlg):
     from multilevel_gnn_b200 import graph
     n, e = 1000, 20000
