@@ -158,6 +158,13 @@ int mlg_gather_sum_act(const float* src, int64_t ld_src, const int32_t* rowptr, 
  * This is the gradient of MultilevelGNN's embed-scale prologue (x0 = x * node_embedding, multilevel_gnn.py:150-151)
  * folded into the first layer's backward aggregation: g_emb[n,:] = sum_b x[b,n] * g_x0[b,n,:]. */
 int64_t mlg_gather_sum_slices(int64_t n_rows, int64_t C, int64_t replicas);
+/* The replicated aggregation over a NODE-MAJOR source of 32-wide rows: src row of (replica b, node j) is j * replicas + b (the
+ * replica rows one CSR entry gathers are contiguous); out / self_out rows are graph-major (b * n_rows + i) like everywhere else.
+ * out_i(b) = sum_q val_q * pre[idx_q] * src[idx_q, b];  self_out_i(b) = src[i, b] (NULL ok); val / pre / order NULL ok.
+ * Backward aggregation of a transform-first SAGE layer on the gradient written by mlg_pool_bwd_layout(gx_node_major = 1). */
+int mlg_gather_sum_nm(const float* src, const int32_t* rowptr, const int32_t* idx, const float* val, const float* pre,
+                      const int32_t* order, int64_t n_rows, int64_t replicas, float* out, int64_t ld_out, float* self_out,
+                      int64_t ld_self, void* stream);
 
 /* Fully factored first SAGE layer of MultilevelGNN (models/multilevel_gnn.py:150-151 feeding SAGEConv,
  * gcn_lib/sparse/torch_vertex.py:269-294).  The layer input x0[b,n,:] = x[b,n] * node_embedding[n,:] is rank-1 per node,
@@ -459,6 +466,15 @@ int mlg_pool_bwd(const float* g_out_cl, const float* x, const float* vm, const f
                  const int32_t* node_slot, const int32_t* seg_of_slot, int64_t B, int64_t N, int64_t C, int64_t G,
                  int64_t S, int64_t P, int64_t replicas, float* g_x, float* g_w, float* workspace, int mask_input,
                  float mask_slope, const float* w_mask, void* stream);
+/* mlg_pool_bwd with a choice of layout for g_x.  gx_node_major != 0 (C == 32, replicas == B > 1, see
+ * mlg_pool_bwd_node_major_supported): the row of (graph b, node i) is i * B + b -- the B replica rows of a node are one
+ * contiguous 128 * B-byte block, which is what the by-source aggregation consuming this gradient (mlg_gather_sum_nm)
+ * gathers per CSR entry -- instead of b * N + i. */
+int mlg_pool_bwd_node_major_supported(int64_t C, int64_t replicas);
+int mlg_pool_bwd_layout(const float* g_out_cl, const float* x, const float* vm, const float* w, const int32_t* node_rowptr,
+                        const int32_t* node_slot, const int32_t* seg_of_slot, int64_t B, int64_t N, int64_t C, int64_t G,
+                        int64_t S, int64_t P, int64_t replicas, float* g_x, float* g_w, float* workspace, int mask_input,
+                        float mask_slope, const float* w_mask, int gx_node_major, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Dilated kNN graph (models/gcn_lib/sparse/torch_edge.py:53-104, dense/torch_edge.py:32-58):

@@ -125,6 +125,11 @@ _SIGNATURES = {
                                 _c_i64, _c_int, _c_i64, _c_vp, _c_vp]),
     "mlg_pool_bwd": (_c_int, [_c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_i64, _c_i64, _c_i64, _c_i64, _c_i64, _c_i64,
                               _c_i64, _c_vp, _c_vp, _c_vp, _c_int, _c_f32, _c_vp, _c_vp]),
+    "mlg_pool_bwd_node_major_supported": (_c_int, [_c_i64, _c_i64]),
+    "mlg_pool_bwd_layout": (_c_int, [_c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_i64, _c_i64, _c_i64, _c_i64, _c_i64,
+                                     _c_i64, _c_i64, _c_vp, _c_vp, _c_vp, _c_int, _c_f32, _c_vp, _c_int, _c_vp]),
+    "mlg_gather_sum_nm": (_c_int, [_c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_i64, _c_i64, _c_vp, _c_i64, _c_vp, _c_i64,
+                                   _c_vp]),
     "mlg_cast_bf16": (_c_int, [_c_vp, _c_i64, _c_i64, _c_i64, _c_i64, _c_int, _c_vp, _c_i64, _c_vp]),
     "mlg_gemm_bf16": (_c_int, [_c_vp, _c_i64, _c_i64, _c_vp, _c_i64, _c_i64, _c_vp, _c_i64, _c_i64, _c_i64, _c_i64,
                                _c_i64, _c_i64, _c_f32, _c_vp]),
@@ -187,7 +192,7 @@ def last_error():
 
 
 # kernels launched per C call (own kernels only; CUB's sort passes inside mlg_csr_build are not counted)
-_LAUNCHES_PER_CALL = {"mlg_csr_build": 2, "mlg_knn_graph": 2, "mlg_xty": 2, "mlg_xty_tc": 2, "mlg_skinny_linear": 2, "mlg_wcolsum": 2, "mlg_gen_aggr_bwd_affine": 3, "mlg_gen_aggr_bwd_affine_src": 3, "mlg_layernorm_bwd": 2, "mlg_layernorm_relu_bwd": 2, "mlg_pool_bwd": 2, "mlg_adam_step": 2,
+_LAUNCHES_PER_CALL = {"mlg_csr_build": 2, "mlg_knn_graph": 2, "mlg_xty": 2, "mlg_xty_tc": 2, "mlg_skinny_linear": 2, "mlg_wcolsum": 2, "mlg_gen_aggr_bwd_affine": 3, "mlg_gen_aggr_bwd_affine_src": 3, "mlg_layernorm_bwd": 2, "mlg_layernorm_relu_bwd": 2, "mlg_pool_bwd": 2, "mlg_pool_bwd_layout": 2, "mlg_adam_step": 2,
                       "mlg_head_conv_pool_bwd": 2, "mlg_head_mlp_fwd": 2, "mlg_diffpool_bwd": 2, "mlg_pca_indep_loss": 2}
 LAUNCH_COUNT = 0
 TIMER = None        # a KernelTimer while bench.py measures per-kernel device time

@@ -837,6 +837,84 @@ __global__ void __launch_bounds__(kThreads, MLG_R1B_MINB) sage_rank1_bwd_rows_ke
 // 4-4.5 TB/s on this part, below what plain LDG.128 gathers served from L2 reach (6.5-8.6 TB/s).  What did help was
 // getting ptxas to issue all RB row loads before the first FMA (see MLG_GS_MINB).
 
+// ---------------------------------------------------------------------------------------------
+// Replicated aggregation over a NODE-MAJOR source (C == 32): src row of (replica b, node j) is j * B + b, so the B replica
+// rows a CSR entry gathers are ONE contiguous 128 * B-byte block instead of B rows 128 * n * ld bytes apart.  A warp owns one
+// output row for 16 replicas: lane (q, sl) = (lane / 8, lane % 8) covers bytes 16 * sl of replica 4 j + q, so every load
+// instruction of the warp reads 512 contiguous bytes and an entry's four loads 2 KB (gather_sum_rep_kernel<8, 4>: four
+// 128-byte rows of four unrelated nodes per instruction; the same bytes through L2, at a coarser request granularity).
+// out / self_out stay graph-major (row b * n + i): they feed the row-wise GEMMs next to the activations of the forward pass.
+// Used for the backward aggregation of the transform-first SAGE layer, whose source -- the gradient the pool backward
+// writes (mlg_pool_bwd_layout) -- has no other reader.
+// ---------------------------------------------------------------------------------------------
+constexpr int NM_JU = 2;   // CSR entries in flight per lane (8 row loads)
+__global__ void __launch_bounds__(kThreads, 3)
+gather_nm_kernel(const float* __restrict__ src, const int* __restrict__ rowptr, const int* __restrict__ idx,
+                 const float* __restrict__ val, const float* __restrict__ pre, const int* __restrict__ order, int n, int B,
+                 float* __restrict__ out, unsigned ld_out, float* __restrict__ self_out, unsigned ld_self) {
+  const int lane = threadIdx.x & 31;
+  const int q = lane >> 3, sl = lane & 7;
+  const int halves = (B + 15) / 16;
+  const long long wid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long slot = wid / halves;
+  if (slot >= n) return;
+  const int b_base = (int)(wid % halves) * 16;
+  const unsigned row = order ? (unsigned)__ldg(order + slot) : (unsigned)slot;
+  const int beg = __ldg(rowptr + row), end = __ldg(rowptr + row + 1);
+  int bq[4];          // this lane's replica per load, clamped for the loads (stores test the unclamped value)
+#pragma unroll
+  for (int j = 0; j < 4; ++j) bq[j] = min(b_base + 4 * j + q, B - 1);
+  float acc[4][4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) acc[j][k] = 0.f;
+  const float* sc = src + sl * 4;
+  for (int base = beg; base < end; base += 32) {
+    const int p = min(base + lane, end - 1);
+    const unsigned my_idx = (unsigned)__ldg(idx + p);
+    float my_w = val ? __ldg(val + p) : 1.f;
+    if (pre) my_w *= __ldg(pre + my_idx);
+    const int cnt = min(32, end - base);
+    for (int e = 0; e < cnt; e += NM_JU) {
+      float4 v[NM_JU][4];
+      float w[NM_JU];
+#pragma unroll
+      for (int u = 0; u < NM_JU; ++u) {
+        const int ee = min(e + u, cnt - 1);
+        const unsigned s = __shfl_sync(0xffffffffu, my_idx, ee);
+        w[u] = (e + u < cnt) ? __shfl_sync(0xffffffffu, my_w, ee) : 0.f;
+        const float* ps = sc + (size_t)s * B * 32;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[u][j] = ld_gather4(ps + (size_t)bq[j] * 32);
+      }
+#pragma unroll
+      for (int u = 0; u < NM_JU; ++u)      // entries in CSR order: one fixed sequence of FMAs per output element
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          acc[j][0] = fmaf(w[u], v[u][j].x, acc[j][0]);
+          acc[j][1] = fmaf(w[u], v[u][j].y, acc[j][1]);
+          acc[j][2] = fmaf(w[u], v[u][j].z, acc[j][2]);
+          acc[j][3] = fmaf(w[u], v[u][j].w, acc[j][3]);
+        }
+    }
+  }
+  float4 t[4];
+  if (self_out) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) t[j] = ld_gather4(sc + ((size_t)row * B + bq[j]) * 32);
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int b = b_base + 4 * j + q;
+    if (b < B) {
+      const size_t orow = (size_t)b * n + row;
+      if (self_out) st4(self_out + orow * ld_self + sl * 4, t[j]);
+      st4(out + orow * ld_out + sl * 4, make_float4(acc[j][0], acc[j][1], acc[j][2], acc[j][3]));
+    }
+  }
+}
+
 __global__ void edge_values_kernel(const float* __restrict__ ea, const int* __restrict__ eid,
                                    const int* __restrict__ rowptr, int n_rows, long long cap, float fill,
                                    float* __restrict__ val) {
@@ -1127,5 +1205,24 @@ extern "C" int mlg_embed_scale_bwd(const float* xs, const float* g_out, int64_t 
       xs, reinterpret_cast<const float4*>(g_out), (int)B, (int)N, (int)(C / 4),
       reinterpret_cast<float4*>(g_emb));
   MLG_CHECK_LAUNCH("mlg_embed_scale_bwd");
+  return MLG_OK;
+}
+
+// out[b*n + i, :32] = sum_q val_q * pre[idx_q] * src[idx_q * B + b, :32]  (src node-major, see gather_nm_kernel);
+// self_out[b*n + i, :32] = src[i * B + b, :32] (NULL ok).  The backward aggregation of a transform-first SAGE layer
+// (SAGEConv.message + mean, torch_vertex.py:279-286, on the by-source CSR) reading the gradient mlg_pool_bwd_layout wrote.
+extern "C" int mlg_gather_sum_nm(const float* src, const int32_t* rowptr, const int32_t* idx, const float* val,
+                                 const float* pre, const int32_t* order, int64_t n_rows, int64_t replicas, float* out,
+                                 int64_t ld_out, float* self_out, int64_t ld_self, void* stream) {
+  MLG_CHECK_ARG(src && rowptr && idx && out, "mlg_gather_sum_nm: null pointer");
+  MLG_CHECK_ARG(n_rows >= 0 && replicas >= 1 && replicas * n_rows < (1ll << 31), "mlg_gather_sum_nm: bad sizes");
+  MLG_CHECK_ARG(ld_out >= 32 && ld_out % 4 == 0 && (!self_out || (ld_self >= 32 && ld_self % 4 == 0)) &&
+                    ((uintptr_t)src | (uintptr_t)out | (uintptr_t)self_out) % 16 == 0,
+                "mlg_gather_sum_nm: 32-wide rows, 16-byte aligned, leading dimensions multiples of 4");
+  if (n_rows == 0) return MLG_OK;
+  const long long warps = n_rows * ((replicas + 15) / 16);
+  gather_nm_kernel<<<(unsigned)mlg_ceil_div(warps, kThreads / 32), kThreads, 0, (cudaStream_t)stream>>>(
+      src, rowptr, idx, val, pre, order, (int)n_rows, (int)replicas, out, (unsigned)ld_out, self_out, (unsigned)ld_self);
+  MLG_CHECK_LAUNCH("mlg_gather_sum_nm");
   return MLG_OK;
 }

@@ -632,7 +632,7 @@ __global__ void __launch_bounds__(kThreads, 4)
 pool_bwd_c32_kernel(const float* __restrict__ g_cl, const float* __restrict__ x, const float* __restrict__ vm,
                     const float* __restrict__ w, const int* __restrict__ rowptr, const int* __restrict__ slots,
                     const int* __restrict__ seg_of_slot, int n_rows, int replicas, int S, int G,
-                    float* __restrict__ g_x, float* __restrict__ part, int mask_input, float mask_slope) {
+                    float* __restrict__ g_x, float* __restrict__ part, int mask_input, float mask_slope, int gx_node_major) {
   constexpr int C = 32;
   constexpr int P2 = P_ <= 1 ? 1 : (P_ <= 2 ? 2 : (P_ <= 4 ? 4 : 8));
   constexpr int KSHIFT = P2 == 1 ? 3 : (P2 == 2 ? 2 : (P2 == 4 ? 1 : 0));
@@ -652,11 +652,14 @@ pool_bwd_c32_kernel(const float* __restrict__ g_cl, const float* __restrict__ x,
   const size_t rep_g = (size_t)S * P_ * C;
   const size_t rep_x = (size_t)n_rows * C;
   const unsigned c = sl * 4;
-  float* gx0 = g_x + ((size_t)b0 * n_rows + row) * C + c;
+  // gx_node_major: g_x row of (replica b, node i) is i * replicas + b (the replica rows of a node contiguous: what the
+  // by-source aggregation that consumes this gradient gathers per CSR entry) instead of b * n_rows + i
+  const size_t gx_step = gx_node_major ? (size_t)C : rep_x;
+  float* gx0 = g_x + (gx_node_major ? ((size_t)row * replicas + b0) : ((size_t)b0 * n_rows + row)) * C + c;
   if (beg == end) {   // node without a gene slot: zero gradient, nothing to read
 #pragma unroll
     for (int r = 0; r < RBS; ++r)
-      if (r < nb) st4(gx0 + (size_t)r * rep_x, make_float4(0.f, 0.f, 0.f, 0.f));
+      if (r < nb) st4(gx0 + (size_t)r * gx_step, make_float4(0.f, 0.f, 0.f, 0.f));
     return;
   }
   float4 xr[RBS];
@@ -724,7 +727,7 @@ pool_bwd_c32_kernel(const float* __restrict__ g_cl, const float* __restrict__ x,
       const float xs[4] = {xr[r].x, xr[r].y, xr[r].z, xr[r].w};
 #pragma unroll
       for (int k = 0; k < 4; ++k) accx[r][k] *= (mask_input && !(xs[k] > 0.f)) ? scale[r] * mask_slope : scale[r];
-      st4(gx0 + (size_t)r * rep_x, make_float4(accx[r][0], accx[r][1], accx[r][2], accx[r][3]));
+      st4(gx0 + (size_t)r * gx_step, make_float4(accx[r][0], accx[r][1], accx[r][2], accx[r][3]));
     }
   }
 }
@@ -826,13 +829,27 @@ extern "C" int mlg_pool_bwd_w(const float* g_out_cl, const float* x, const float
   return MLG_OK;
 }
 
+extern "C" int mlg_pool_bwd_node_major_supported(int64_t C, int64_t replicas) { return C == 32 && replicas > 1; }
+
 extern "C" int mlg_pool_bwd(const float* g_out_cl, const float* x, const float* vm, const float* w,
                             const int32_t* node_rowptr, const int32_t* node_slot, const int32_t* seg_of_slot,
                             int64_t B, int64_t N, int64_t C, int64_t G, int64_t S, int64_t P, int64_t replicas,
                             float* g_x, float* g_w, float* workspace, int mask_input, float mask_slope, const float* w_mask,
                             void* stream) {
+  return mlg_pool_bwd_layout(g_out_cl, x, vm, w, node_rowptr, node_slot, seg_of_slot, B, N, C, G, S, P, replicas, g_x, g_w,
+                             workspace, mask_input, mask_slope, w_mask, 0, stream);
+}
+
+extern "C" int mlg_pool_bwd_layout(const float* g_out_cl, const float* x, const float* vm, const float* w,
+                                   const int32_t* node_rowptr, const int32_t* node_slot, const int32_t* seg_of_slot,
+                                   int64_t B, int64_t N, int64_t C, int64_t G, int64_t S, int64_t P, int64_t replicas,
+                                   float* g_x, float* g_w, float* workspace, int mask_input, float mask_slope,
+                                   const float* w_mask, int gx_node_major, void* stream) {
   MLG_CHECK_ARG(g_out_cl && x && w && node_rowptr && node_slot && seg_of_slot && g_x && g_w && workspace,
                 "mlg_pool_bwd: null pointer");
+  MLG_CHECK_ARG(!gx_node_major || (mlg_pool_bwd_node_major_supported(C, replicas) && (uintptr_t)g_out_cl % 16 == 0 &&
+                                   (uintptr_t)x % 16 == 0 && (uintptr_t)g_x % 16 == 0),
+                "mlg_pool_bwd_layout: the node-major gradient layout needs C == 32, a replicated layout and 16-byte alignment");
   int rc = check_dims("mlg_pool_bwd", B, N, C, G, S, P);
   if (rc) return rc;
   MLG_CHECK_ARG(replicas == 1 || replicas == B, "mlg_pool_bwd: replicas must be 1 or B");
@@ -856,7 +873,7 @@ extern "C" int mlg_pool_bwd(const float* g_out_cl, const float* x, const float* 
       MLG_CUDA(cudaMemsetAsync(workspace, 0, (size_t)chunks * G * P * sizeof(float), st));   // slots without a node stay zero
       MLG_P_SWITCH(P, (pool_bwd_c32_kernel<P_, 2><<<grid3, kThreads, 0, st>>>(
                           g_out_cl, x, vm, w, node_rowptr, node_slot, seg_of_slot, (int)n_rows, (int)replicas, (int)S,
-                          (int)G, g_x, workspace, mask_input, mask_slope)));
+                          (int)G, g_x, workspace, mask_input, mask_slope, gx_node_major)));
       MLG_CHECK_LAUNCH("mlg_pool_bwd(c32)");
       pool_wgrad_reduce_kernel<<<mlg_ceil_div(G * P, 256), 256, 0, st>>>(workspace, (int)chunks, G * P, (int)P, w_mask, g_w);
       MLG_CHECK_LAUNCH("mlg_pool_bwd(reduce)");

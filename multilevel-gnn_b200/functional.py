@@ -531,6 +531,7 @@ def _flag(name, default):
 FACTORED_RANK1 = True
 # SAGE layers with out_channels < in_channels evaluated transform-first (gather on the narrower rows); False: [x | agg] + GEMM
 TRANSFORM_FIRST = True
+GZ_NODE_MAJOR = True     # the pool writes the last layer's output gradient node-major for the transform-first backward aggregation
 # The factored first layer applies LeakyReLU'(y) to its output gradient INSIDE mlg_sage_rank1_bwd_rows, from 64 sign bits per
 # (gene, replica) its forward kernel wrote (B200: 66 us vs 61 us unmasked; re-reading the 126 MB activation instead costs
 # 175 us, profiles/r02_rank1_bwd_probe.jsonl).  Widths without sign words (!= 64): one library leaky_relu_backward pass.
@@ -618,7 +619,7 @@ class SageLayer(torch.autograd.Function):
     The last two take their weights from mlg_sage_fold_stacked_fwd (stacked weight, both 3xTF32 splits, bias: one launch)."""
 
     @staticmethod
-    def forward(ctx, x, xs, lin_r_w, nn_w, nn_b, topo, relative, slope, in_slope=None, out_premasked=False):
+    def forward(ctx, x, xs, lin_r_w, nn_w, nn_b, topo, relative, slope, in_slope=None, out_premasked=False, link=None):
         """x [B*N, Cin] node features -- or, with ``xs`` [B*N] given, x = node_embedding [N, Cin] and the layer
         input is the rank-1 product xs[b,n] * x[n,:] (MultilevelGNN's first layer, never materialised).
         Activation-backward fusion across layers (set by the model, which knows the layer chain):
@@ -725,6 +726,12 @@ class SageLayer(torch.autograd.Function):
             ctx.topo, ctx.relative, ctx.slope, ctx.cin, ctx.has_bias = topo, False, float(slope), cin, nn_b is not None
             ctx.rank1, ctx.transform_first, ctx.emb_param, ctx.in_slope = False, True, None, None
             ctx.out_premasked = bool(out_premasked)
+            # ``link``: shared with the PathwayPool that consumes y and pre-masks its gradient (out_premasked).  gy then IS dL/dz
+            # and its only reader is this layer's backward aggregation, so the pool may write it NODE-MAJOR (row i * B + b: the B
+            # replica rows a CSR entry gathers are one contiguous block) -- requested here, confirmed by the pool's backward.
+            ctx.link = link if (GZ_NODE_MAJOR and link is not None and out_premasked and cout == 32 and topo.replicas > 1) else None
+            if ctx.link is not None:
+                ctx.link["gz_node_major"] = True
             return y
         wsplit = (wbuf[1].view(cout, 2 * cin), wbuf[2].view(cout, 2 * cin))
         xcat = torch.empty(n, 2 * cin, dtype=torch.float32, device=xd.device)
@@ -820,7 +827,7 @@ class SageLayer(torch.autograd.Function):
             fk.hold(g_wst, g_wnn, g_wr)
         slot = grad_slot(ctx.emb_param, (n1, cin)) if ctx.emb_param is not None else None
         g_emb = tall_matmul(g12, wst.t(), tag="sage_rank1_demb", w_split=ctx.wst_t_split, out=slot)     # g12 @ Wst
-        return g_emb, None, g_wr, g_wnn, g_b, None, None, None, None, None
+        return g_emb, None, g_wr, g_wnn, g_b, None, None, None, None, None, None
 
     @staticmethod
     def _backward_transform_first(ctx, gy):
@@ -838,9 +845,19 @@ class SageLayer(torch.autograd.Function):
         bw = topo.bwd
         # G = [g_U | g_V] = [gz | A^T gz]: the by-source aggregation runs on the cout-wide gz rows and copies them alongside
         g_uv = torch.empty(n, 2 * cout, dtype=torch.float32, device=gz.device)
-        gather_sum(gz, bw.rowptr, bw.col, topo.n_single, val=topo.bwd_val, pre=topo.inv_cnt, out=g_uv[:, cout:],
-                   self_out=g_uv[:, :cout], replicas=topo.replicas, order=topo.bwd_order,
-                   tag="sage_aggr_bwd")
+        link = getattr(ctx, "link", None)
+        if link is not None and link.pop("gz_written_node_major", False):
+            # the pool wrote gz node-major: every load instruction of the aggregation reads 512 contiguous bytes
+            with torch.cuda.device(gz.device), _cabi.span("sage_aggr_bwd", 4 * cout * n * 2 + 8 * bw.col.numel()):
+                _cabi.check(L.mlg_gather_sum_nm(_cabi.fptr(gz), _cabi.iptr(bw.rowptr), _cabi.iptr(bw.col),
+                                                _cabi.fptr(topo.bwd_val, True), _cabi.fptr(topo.inv_cnt, True),
+                                                _cabi.iptr(topo.bwd_order, True), topo.n_single, topo.replicas,
+                                                _vptr(g_uv[:, cout:]), 2 * cout, _vptr(g_uv), 2 * cout, _cabi.stream_ptr()),
+                            "mlg_gather_sum_nm")
+        else:
+            gather_sum(gz, bw.rowptr, bw.col, topo.n_single, val=topo.bwd_val, pre=topo.inv_cnt, out=g_uv[:, cout:],
+                       self_out=g_uv[:, :cout], replicas=topo.replicas, order=topo.bwd_order,
+                       tag="sage_aggr_bwd")
         needs = ctx.needs_input_grad
         gx = g_wr = g_wnn = g_b = None
         # the weight gradient (tensor-core x^T G over the row pairs + fold) on a forked stream next to the input-gradient GEMM
@@ -868,7 +885,7 @@ class SageLayer(torch.autograd.Function):
                 fk.hold(o2, g_wnn, g_wr, g_b)
         if needs[0]:
             gx = tall_matmul(g_uv, wst.t(), tag="sage_dgrad_gemm", w_split=ctx.wst_t_split)     # dL/dx (the producer masks it itself)
-        return gx, None, g_wr, g_wnn, (g_b if ctx.has_bias else None), None, None, None, None, None
+        return gx, None, g_wr, g_wnn, (g_b if ctx.has_bias else None), None, None, None, None, None, None
 
     @staticmethod
     def backward(ctx, gy):
@@ -911,7 +928,7 @@ class SageLayer(torch.autograd.Function):
                     g_emb = torch.sum(part.view(-1, n1, cin), 0, out=slot) if slot is not None else part.view(-1, n1, cin).sum(0)
                 else:
                     g_emb = part
-                return g_emb, None, g_wr, g_wnn, (g_b if ctx.has_bias else None), None, None, None, None, None
+                return g_emb, None, g_wr, g_wnn, (g_b if ctx.has_bias else None), None, None, None, None, None, None
             gx = gather_sum(gxcat[:, cin:], bw.rowptr, bw.col, topo.n_single, val=topo.bwd_val, pre=topo.inv_cnt,
                             addend=gxcat[:, :cin], replicas=topo.replicas, order=topo.bwd_order, tag="sage_aggr_bwd",
                             mask=None if ctx.in_slope is None else xcat[:, :cin],
@@ -927,7 +944,7 @@ class SageLayer(torch.autograd.Function):
                     _cabi.check(L.mlg_embed_scale_bwd(_cabi.fptr(xs_d), _cabi.fptr(gx), topo.replicas, n1, cin,
                                                       _cabi.fptr(g_emb), _cabi.stream_ptr()), "mlg_embed_scale_bwd")
                 gx = g_emb
-        return gx, None, g_wr, g_wnn, (g_b if ctx.has_bias else None), None, None, None, None, None
+        return gx, None, g_wr, g_wnn, (g_b if ctx.has_bias else None), None, None, None, None, None, None
 
 
 class RankOne:
@@ -1085,7 +1102,7 @@ class PathwayPool(torch.autograd.Function):
     permute(0,3,1,2) VIEW of the channel-last buffer [B,S,P,C] the kernel writes."""
 
     @staticmethod
-    def forward(ctx, x, w, vm, layout, in_slope=None, w_mask=None):
+    def forward(ctx, x, w, vm, layout, in_slope=None, w_mask=None, link=None):
         """``in_slope``: x is the output of a (Leaky)ReLU with that slope whose producer expects dL/dz (see SageLayer).
         ``w_mask`` [G, 1] or [G]: the projection weights are w * w_mask (learnable_pca_params * info_mask,
         multilevel_gnn.py:222); the product and its backward are folded in (the gradient returned for ``w`` is dL/dw)."""
@@ -1109,6 +1126,7 @@ class PathwayPool(torch.autograd.Function):
         ctx.save_for_backward(xd, wd)
         ctx.vm, ctx.layout = vm, layout
         ctx.in_slope = None if in_slope is None else float(in_slope)
+        ctx.link = link       # shared with the SageLayer that produced x (see its forward): layout of the gradient handed back
         return out_cl.permute(0, 3, 1, 2)
 
     @staticmethod
@@ -1125,13 +1143,19 @@ class PathwayPool(torch.autograd.Function):
             gx, gw = torch.empty_like(xd), (slot if slot is not None else torch.empty_like(wd))
             node = lay.node_csr
             ws = torch.empty(B * G * P, dtype=torch.float32, device=xd.device)
+            link = getattr(ctx, "link", None)
+            node_major = bool(link is not None and link.get("gz_node_major") and ctx.in_slope is not None
+                              and L.mlg_pool_bwd_node_major_supported(C, lay.replicas))
             with torch.cuda.device(xd.device), _cabi.span("pool_bwd", 2 * (4 * C * B * N) + 4 * B * C * S * P):
-                _cabi.check(L.mlg_pool_bwd(_cabi.fptr(g_cl), _cabi.fptr(xd), _cabi.fptr(vm, True), _cabi.fptr(wd),
-                                           _cabi.iptr(node.rowptr), _cabi.iptr(node.col), _cabi.iptr(lay.seg_of_slot),
-                                           B, N, C, G, S, P, lay.replicas, _cabi.fptr(gx), _cabi.fptr(gw), _cabi.fptr(ws),
-                                           0 if ctx.in_slope is None else 1, 0.0 if ctx.in_slope is None else ctx.in_slope,
-                                           _cabi.fptr(ctx.w_mask, True), _cabi.stream_ptr()), "mlg_pool_bwd")
-            return gx, gw, None, None, None, None
+                _cabi.check(L.mlg_pool_bwd_layout(_cabi.fptr(g_cl), _cabi.fptr(xd), _cabi.fptr(vm, True), _cabi.fptr(wd),
+                                                  _cabi.iptr(node.rowptr), _cabi.iptr(node.col), _cabi.iptr(lay.seg_of_slot),
+                                                  B, N, C, G, S, P, lay.replicas, _cabi.fptr(gx), _cabi.fptr(gw), _cabi.fptr(ws),
+                                                  0 if ctx.in_slope is None else 1, 0.0 if ctx.in_slope is None else ctx.in_slope,
+                                                  _cabi.fptr(ctx.w_mask, True), 1 if node_major else 0, _cabi.stream_ptr()),
+                            "mlg_pool_bwd_layout")
+            if link is not None:
+                link["gz_written_node_major"] = node_major      # read (and cleared) by the producer layer's backward
+            return gx, gw, None, None, None, None, None
         with torch.cuda.device(xd.device):
             if ctx.needs_input_grad[0]:
                 gx = torch.empty_like(xd)
@@ -1152,7 +1176,9 @@ class PathwayPool(torch.autograd.Function):
             gx = torch.where(xd > 0, gx, gx * ctx.in_slope)
         if gw is not None and ctx.w_mask is not None:
             gw = gw * ctx.w_mask.reshape(-1, 1)
-        return gx, gw, None, None, None, None
+        if getattr(ctx, "link", None) is not None:
+            ctx.link["gz_written_node_major"] = False
+        return gx, gw, None, None, None, None, None
 
 
 def _drop_bits(n, device):

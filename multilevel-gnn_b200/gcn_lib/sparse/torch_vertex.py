@@ -171,7 +171,9 @@ class SAGEConv(nn.Module):
             raise NotImplementedError("vector edge weights: only [E] / [E,1] edge_attr is used by the reference")
         slope = self._fused_slope()
         # cross-layer activation-backward fusion requested by the model for THIS call (see Fn.SageLayer.forward)
-        in_slope, out_premasked = getattr(self, "_mlg_fuse", (None, False))
+        fuse = getattr(self, "_mlg_fuse", (None, False))
+        in_slope, out_premasked = fuse[0], fuse[1]
+        link = fuse[2] if len(fuse) > 2 else None      # dict shared with the pool that consumes this layer's output
         self._mlg_fuse = (None, False)
         n_total = x.shape[0]
         topo = graph.topology(edge_index, n_total, self_loops=True, edge_weight=edge_attr)
@@ -186,7 +188,7 @@ class SAGEConv(nn.Module):
         if slope is not None:
             lin = self.nn[0]
             return Fn.SageLayer.apply(x, None, self.lin_r.weight, lin.weight, lin.bias, topo, self.relative, slope,
-                                      in_slope, out_premasked)
+                                      in_slope, out_premasked, link)
         agg_x = Fn.SageAggregate.apply(x, topo, self.relative)
         agg = F.linear(agg_x, self.lin_r.weight)
         return self.update(agg, x)

@@ -160,13 +160,17 @@ class MultilevelGNN(nn.Module):
             and not args.repeat_mask and torch.is_grad_enabled()
         slopes = [getattr(l, "grad_fusion_slope", lambda: None)() if plain else None for l in self.gnn_model]
         pool_masks = plain and slopes[-1] is not None and (not (args.value_att_mask and value_mask) or args.merge_mode == 'mult')
+        pool_link = {}
         for i, layer in enumerate(self.gnn_model):
             if plain and slopes[i] is not None:
                 masks = lambda l: getattr(l, "masks_input_grad", lambda: not getattr(l, "relative", True))()
                 consumer_masks = pool_masks if i + 1 == n_layers else \
                     (slopes[i + 1] is not None and masks(self.gnn_model[i + 1]))
                 producer_masked = i > 0 and slopes[i - 1] is not None and masks(layer)
-                layer._mlg_fuse = (slopes[i - 1] if producer_masked else None, bool(consumer_masks))
+                # last layer + pool: a dict both Functions see, through which they agree on the layout of the gradient the
+                # pool's backward hands to the layer's backward (Fn.SageLayer / Fn.PathwayPool, ``gz_node_major``)
+                link = pool_link if (i + 1 == n_layers and consumer_masks) else None
+                layer._mlg_fuse = (slopes[i - 1] if producer_masked else None, bool(consumer_masks), link)
             y = layer(x, edge_index, edge_attr)
             if args.dense_gnn:
                 x = y
@@ -194,7 +198,7 @@ class MultilevelGNN(nn.Module):
         # w = learnable_pca_params * info_mask [G, P] (multilevel_gnn.py:222): the mask product and its backward are folded
         # into the pool Function (the projection gradient lands in the parameter's bucket slot)
         x = Fn.PathwayPool.apply(x, self.learnable_pca_params, vm, layout, slopes[-1] if pool_masks else None,
-                                 self.info_mask)                                      # [B, C, 438, P]
+                                 self.info_mask, pool_link if pool_masks else None)   # [B, C, 438, P]
         return x
 
     def forward(self, input_batch, x=None, gene_pca_match=None, raw_indice=None, age=None, require_grad=True,

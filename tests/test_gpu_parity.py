@@ -584,6 +584,51 @@ def ctypes_ptr(t):
     return ctypes.c_void_p(t.data_ptr())
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("bsz", [3, 16, 40])
+def test_node_major_gradient_between_pool_and_aggregation(mlg, bsz):
+    """mlg_pool_bwd_layout(gx_node_major=1) writes the same gradient as mlg_pool_bwd, at row i * B + b instead of b * N + i,
+    and mlg_gather_sum_nm on it equals mlg_gather_sum on the graph-major tensor (backward aggregation of the transform-first
+    layer, torch_vertex.py:279-286 on the by-source CSR; self rows copied alongside): bit-identical, the FMA order is the same."""
+    from multilevel_gnn_b200 import _cabi, functional as Fn, graph, synth
+    L = _cabi.lib()
+    genes, slots, C, P = 150, 1200, 32, 2
+    b = synth.multilevel_batch(batch_size=bsz, genes=genes, slots=slots, intra_edges=900, seed=31)
+    n = 3 * genes
+    g = torch.Generator().manual_seed(7)
+    x = torch.randn(bsz * n, C, generator=g).to(DEV)
+    w = torch.randn(slots, P, generator=g).to(DEV)
+    gout = torch.randn(bsz, 438, P, C, generator=g).to(DEV)
+    lay = graph.pool_layout(b.gene_pca_match.to(DEV), b.raw_indice.to(DEV), n, 438)
+    node = lay.node_csr
+    outs = []
+    for nm in (0, 1):
+        gx, gw = torch.empty_like(x), torch.empty_like(w)
+        ws = torch.empty(bsz * slots * P, device=DEV)
+        with torch.cuda.device(DEV):
+            _cabi.check(L.mlg_pool_bwd_layout(_cabi.fptr(gout), _cabi.fptr(x), None, _cabi.fptr(w), _cabi.iptr(node.rowptr),
+                                              _cabi.iptr(node.col), _cabi.iptr(lay.seg_of_slot), bsz, n, C, slots, 438, P,
+                                              lay.replicas, _cabi.fptr(gx), _cabi.fptr(gw), _cabi.fptr(ws), 1, 0.2, None, nm,
+                                              _cabi.stream_ptr()), "mlg_pool_bwd_layout")
+        outs.append((gx, gw))
+    gx_gm, gx_nm = outs[0][0], outs[1][0]
+    assert torch.equal(gx_nm.view(n, bsz, C).transpose(0, 1).reshape(bsz * n, C), gx_gm)
+    assert torch.equal(outs[0][1], outs[1][1])
+    topo = graph.topology(b.edge_index.to(DEV), bsz * n, self_loops=True, edge_weight=b.edge_attr.to(DEV), period=n)
+    assert topo.replicas == bsz
+    bw = topo.bwd
+    ref = torch.empty(bsz * n, 2 * C, device=DEV)
+    Fn.gather_sum(gx_gm, bw.rowptr, bw.col, topo.n_single, val=topo.bwd_val, pre=topo.inv_cnt, out=ref[:, C:],
+                  self_out=ref[:, :C], replicas=topo.replicas, order=topo.bwd_order)
+    got = torch.empty(bsz * n, 2 * C, device=DEV)
+    with torch.cuda.device(DEV):
+        _cabi.check(L.mlg_gather_sum_nm(_cabi.fptr(gx_nm), _cabi.iptr(bw.rowptr), _cabi.iptr(bw.col), _cabi.fptr(topo.bwd_val, True),
+                                        _cabi.fptr(topo.inv_cnt, True), _cabi.iptr(topo.bwd_order, True), topo.n_single, bsz,
+                                        ctypes_ptr(got[:, C:]), 2 * C, _cabi.fptr(got), 2 * C, _cabi.stream_ptr()),
+                    "mlg_gather_sum_nm")
+    assert torch.equal(got, ref)
+
+
 def test_csr_build_matches_sort(mlg):
     from multilevel_gnn_b200 import graph
     n, e = 1000, 20000
