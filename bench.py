@@ -172,15 +172,16 @@ def ncu_traffic(kernel):
 
 # per timer tag: the ncu kernel names behind it (profiles/ncu_traffic.json) and the ALGORITHMIC bytes of one launch
 KERNEL_INFO = {
-    "gather_sum_rep_kernel (SAGE mean aggregation fwd+bwd)": {
-        "ncu": ["gather_sum_rep_kernel<8, 4, 0, 0, 0>", "gather_sum_rep_kernel<8, 4, 0, 0, 0>#2"],
+    "SAGE mean aggregation fwd+bwd (gather_sum_rep_kernel forward, gather_nm_kernel backward)": {
+        "ncu": ["gather_sum_rep_kernel<8, 4, 0, 0, 0>", "gather_nm_kernel"],
         "alg": "8*C*B*N + 8*nnz per launch counted by the timer (rows read once + written once + idx/val per entry), C = 32: the "
                "second SAGE layer (64 -> 32) runs transform-first, so its forward and backward aggregations gather 32-wide rows "
                "(with the addend row U / the copied self row: 12*C*B*N = 190 MB); bounded by L2 -> SM row gathers (441 MB re-read "
-               "per launch: every source row once per CSR entry), not by DRAM"},
-    "sage_rank1_fwd": {"ncu": ["sage_rank1_fwd_rows_kernel<2>"],
+               "per launch: every source row once per CSR entry), not by DRAM.  The backward launch reads a node-major gradient "
+               "(one contiguous block per CSR entry, written that way by the pool backward)"},
+    "sage_rank1_fwd": {"ncu": ["sage_rank1_fwd_rows_kernel<2, 1>"],
                        "alg": "4*C*B*N (output) + 4*B*N + 8*nnz + 8*C*N (tables), C = 64: 137 MB, write bound"},
-    "pool_bwd": {"ncu": ["pool_bwd_fused2_kernel<2, 1, 4>", "pool_bwd_fused2_kernel<2, 1, 8>"], "alg": "2 * 4*C*B*N + 4*B*C*S*P: x read, g_x written, pooled gradient read"},
+    "pool_bwd": {"ncu": ["pool_bwd_c32_kernel<2, 2>"], "alg": "2 * 4*C*B*N + 4*B*C*S*P: x read, g_x written, pooled gradient read"},
 }
 
 
@@ -614,10 +615,10 @@ def run_b200(a):
     # the kernels of the step, by what bounds them
     bound_of = {"sage_aggr_fwd": "hbm", "sage_aggr_bwd": "hbm", "pool_fwd": "hbm", "pool_bwd_x": "hbm",
                 "pool_bwd_w": "hbm", "pool_bwd": "hbm", "sage_update_gemm": "hbm (tensor 3xTF32)", "sage_dgrad_gemm": "hbm (tensor 3xTF32)", "sage_bias_act": "hbm", "embed_scale_bwd": "hbm", "sage_wgrad": "fp32-fma"}
-    # sage_aggr_fwd / sage_aggr_bwd are the same kernel (gather_sum_rep_kernel) on the CSR / its transpose
+    # sage_aggr_fwd / sage_aggr_bwd: the layer-2 aggregation on the CSR / its transpose, reported together
     merged = {}
     for tag, d in ksum.items():
-        key = "gather_sum_rep_kernel (SAGE mean aggregation fwd+bwd)" if tag.startswith("sage_aggr") else tag
+        key = "SAGE mean aggregation fwd+bwd (gather_sum_rep_kernel forward, gather_nm_kernel backward)" if tag.startswith("sage_aggr") else tag
         m = merged.setdefault(key, {"launches": 0, "ms": 0.0, "bytes": 0, "bound": bound_of.get(tag, "hbm")})
         for f in ("launches", "ms", "bytes"):
             m[f] += d[f]
