@@ -172,8 +172,8 @@ def ncu_traffic(kernel):
 
 # per timer tag: the ncu kernel names behind it (profiles/ncu_traffic.json) and the ALGORITHMIC bytes of one launch
 KERNEL_INFO = {
-    "SAGE mean aggregation fwd+bwd (gather_sum_rep_kernel forward, gather_nm_kernel backward)": {
-        "ncu": ["gather_sum_rep_kernel<8, 4, 0, 0, 0>", "gather_nm_kernel"],
+    "SAGE mean aggregation fwd+bwd (gather_nm_kernel on node-major rows)": {
+        "ncu": ["gather_nm_kernel", "gather_nm_kernel#2"],
         "alg": "8*C*B*N + 8*nnz per launch counted by the timer (rows read once + written once + idx/val per entry), C = 32: the "
                "second SAGE layer (64 -> 32) runs transform-first, so its forward and backward aggregations gather 32-wide rows "
                "(with the addend row U / the copied self row: 12*C*B*N = 190 MB); bounded by L2 -> SM row gathers (441 MB re-read "
@@ -308,19 +308,33 @@ def dominant_kernel_alone(batch, hbm_peak, reps=20):
     uv = torch.randn(n, 2 * C, device=batch.x.device)
     out = torch.empty(n, C, device=batch.x.device)
     csr = topo.fwd
-    run = lambda: Fn.gather_sum(uv[:, C:], csr.rowptr, csr.col, topo.n_single, val=topo.fwd_val, post_mode=1, out=out,
-                                addend=uv[:, :C], replicas=topo.replicas, order=topo.fwd_order, tag="sage_aggr_alone",
-                                act_slope=0.2)
-    for _ in range(3):
-        run()
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(reps):
-        run()
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / reps
+    from multilevel_gnn_b200 import _cabi
+    L = _cabi.lib()
+
+    def run_graph_major():       # rows of (graph b, node i) at b * N + i: gather_sum_rep_kernel
+        Fn.gather_sum(uv[:, C:], csr.rowptr, csr.col, topo.n_single, val=topo.fwd_val, post_mode=1, out=out,
+                      addend=uv[:, :C], replicas=topo.replicas, order=topo.fwd_order, tag="sage_aggr_alone", act_slope=0.2)
+
+    def run_node_major():        # [U | V] rows at i * B + b (what the step's forward launches): gather_nm_kernel
+        _cabi.check(L.mlg_gather_sum_nm_ex(Fn._vptr(uv[:, C:]), 2 * C, _cabi.iptr(csr.rowptr), _cabi.iptr(csr.col),
+                                           _cabi.fptr(topo.fwd_val, True), None, _cabi.iptr(topo.fwd_order, True), topo.n_single,
+                                           topo.replicas, 1, _cabi.fptr(uv), 2 * C, 1, 0.2, _cabi.fptr(out), C, None, 0, 0,
+                                           _cabi.stream_ptr()), "mlg_gather_sum_nm_ex")
+
+    def timed(run):
+        for _ in range(3):
+            run()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            run()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    ms_gm = timed(run_graph_major)
+    ms = timed(run_node_major)
     nnz = int(csr.col.numel())
     alg = 12 * C * n + 8 * nnz                                   # U and V read once, output written once, idx + val
     gathered = 4 * C * nnz * topo.replicas + 8 * C * n           # V rows re-read per entry + U rows read + rows written
@@ -328,10 +342,11 @@ def dominant_kernel_alone(batch, hbm_peak, reps=20):
     l2_cap = 6300.0 * sm_mhz / 1e3                               # GB/s
     return {"ms": round(ms, 4), "achieved": round(alg / ms / 1e6, 1), "frac": round(alg / ms / 1e6 / hbm_peak, 4),
             "l2_bytes": gathered, "l2_GBps": round(gathered / ms / 1e6, 1), "l2_cap_GBps": round(l2_cap, 0),
-            "l2_frac": round(gathered / ms / 1e6 / l2_cap, 4),
-            "note": "%d launches back to back, [U | V] [%d,%d] fp32 (126 MB) -> out [%d,%d], nnz=%d per graph x %d replicas; "
-                    "l2_cap = 6300 B/clk x 1965 MHz (guide-measured full-chip LTS cap)"
-                    % (reps, n, 2 * C, n, C, nnz, topo.replicas)}
+            "l2_frac": round(gathered / ms / 1e6 / l2_cap, 4), "graph_major_layout_ms": round(ms_gm, 4),
+            "note": "%d launches back to back of the forward aggregation on node-major rows (gather_nm_kernel, what the step "
+                    "launches; graph_major_layout_ms: gather_sum_rep_kernel on the reference's row order), [U | V] [%d,%d] fp32 "
+                    "(126 MB) -> out [%d,%d], nnz=%d per graph x %d replicas; l2_cap = 6300 B/clk x 1965 MHz (guide-measured "
+                    "full-chip LTS cap)" % (reps, n, 2 * C, n, C, nnz, topo.replicas)}
 
 
 def diffpool_legs(dev):
@@ -618,7 +633,7 @@ def run_b200(a):
     # sage_aggr_fwd / sage_aggr_bwd: the layer-2 aggregation on the CSR / its transpose, reported together
     merged = {}
     for tag, d in ksum.items():
-        key = "SAGE mean aggregation fwd+bwd (gather_sum_rep_kernel forward, gather_nm_kernel backward)" if tag.startswith("sage_aggr") else tag
+        key = "SAGE mean aggregation fwd+bwd (gather_nm_kernel on node-major rows)" if tag.startswith("sage_aggr") else tag
         m = merged.setdefault(key, {"launches": 0, "ms": 0.0, "bytes": 0, "bound": bound_of.get(tag, "hbm")})
         for f in ("launches", "ms", "bytes"):
             m[f] += d[f]

@@ -165,6 +165,24 @@ int64_t mlg_gather_sum_slices(int64_t n_rows, int64_t C, int64_t replicas);
 int mlg_gather_sum_nm(const float* src, const int32_t* rowptr, const int32_t* idx, const float* val, const float* pre,
                       const int32_t* order, int64_t n_rows, int64_t replicas, float* out, int64_t ld_out, float* self_out,
                       int64_t ld_self, void* stream);
+/* The general form: src / addend node-major with leading dimensions (e.g. the V / U halves of a [rows, 64] GEMM output),
+ * out_i(b) = act( addend_i(b) + post_i * sum ), post_i = 1 / row length when mean != 0, LeakyReLU(act_slope) when act != 0,
+ * out / self_out node-major too when out_node_major != 0.  Forward of the transform-first SAGE layer whose input came
+ * node-major from mlg_sage_rank1_fwd_rows_nm, and its backward aggregation writing [g_U | g_V] in the same row order. */
+int mlg_gather_sum_nm_ex(const float* src, int64_t ld_src, const int32_t* rowptr, const int32_t* idx, const float* val,
+                         const float* pre, const int32_t* order, int64_t n_rows, int64_t replicas, int mean, const float* addend,
+                         int64_t ld_add, int act, float act_slope, float* out, int64_t ld_out, float* self_out, int64_t ld_self,
+                         int out_node_major, void* stream);
+/* mlg_sage_rank1_fwd_rows / mlg_sage_rank1_bwd_rows with NODE-MAJOR activation / gradient rows ((replica b, node i) at
+ * i * replicas + b: a gene's replica rows are one contiguous block); arguments as the graph-major entries. */
+int mlg_sage_rank1_fwd_rows_nm(const float* xs_t, const float* e_self, int64_t ld_self, const float* e_nbr, int64_t ld_nbr,
+                               const int32_t* rowptr, const int32_t* idx, const float* val, const int32_t* order, int64_t n_rows,
+                               int64_t C, int64_t replicas, const float* bias, float slope, float* out, int64_t ld_out,
+                               uint64_t* mask_bits, void* stream);
+int mlg_sage_rank1_bwd_rows_nm(const float* gz, int64_t ld_g, const float* y, const uint64_t* mask_bits, float slope, const float* xs,
+                               int xs_transposed, const int32_t* rowptr, const int32_t* idx, const float* val,
+                               const int32_t* order, int64_t n_rows, int64_t C, int64_t replicas, float* h, float* g_self,
+                               int64_t ld_self, float* g_bias_rows, void* stream);
 
 /* Fully factored first SAGE layer of MultilevelGNN (models/multilevel_gnn.py:150-151 feeding SAGEConv,
  * gcn_lib/sparse/torch_vertex.py:269-294).  The layer input x0[b,n,:] = x[b,n] * node_embedding[n,:] is rank-1 per node,

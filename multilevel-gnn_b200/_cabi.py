@@ -49,6 +49,12 @@ _SIGNATURES = {
     # (gz, ld_g, y, mask_bits, slope, xs, rowptr, idx, val, order, n_rows, C, replicas, h, g_self, ld_self, g_bias_rows, stream)
     "mlg_sage_rank1_bwd_rows": (_c_int, [_c_vp, _c_i64, _c_vp, _c_vp, _c_f32, _c_vp, _c_int, _c_vp, _c_vp, _c_vp, _c_vp, _c_i64, _c_i64, _c_i64,
                                          _c_vp, _c_vp, _c_i64, _c_vp, _c_vp]),
+    "mlg_sage_rank1_bwd_rows_nm": (_c_int, [_c_vp, _c_i64, _c_vp, _c_vp, _c_f32, _c_vp, _c_int, _c_vp, _c_vp, _c_vp, _c_vp, _c_i64, _c_i64,
+                                            _c_i64, _c_vp, _c_vp, _c_i64, _c_vp, _c_vp]),
+    "mlg_sage_rank1_fwd_rows_nm": (_c_int, [_c_vp, _c_vp, _c_i64, _c_vp, _c_i64, _c_vp, _c_vp, _c_vp, _c_vp, _c_i64, _c_i64, _c_i64,
+                                            _c_vp, _c_f32, _c_vp, _c_i64, _c_vp, _c_vp]),
+    "mlg_gather_sum_nm_ex": (_c_int, [_c_vp, _c_i64, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_i64, _c_i64, _c_int, _c_vp, _c_i64,
+                                      _c_int, _c_f32, _c_vp, _c_i64, _c_vp, _c_i64, _c_int, _c_vp]),
     "mlg_transpose_bn": (_c_int, [_c_vp, _c_i64, _c_i64, _c_vp, _c_vp]),
     "mlg_sage_rank1_fwd_rows_supported": (_c_int, [_c_i64]),
     "mlg_sage_rank1_fwd_rows": (_c_int, [_c_vp, _c_vp, _c_i64, _c_vp, _c_i64, _c_vp, _c_vp, _c_vp, _c_vp, _c_i64, _c_i64, _c_i64,

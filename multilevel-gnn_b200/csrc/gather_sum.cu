@@ -644,6 +644,7 @@ struct R1B {
   unsigned ld_g, ld_self;
   int n, B;
   int xs_t;            // xs is the transposed node-value matrix [n][B] (one coalesced load per entry) instead of [B][n]
+  int gz_nm;           // gz (and y) rows node-major: (replica b, node i) at i * B + b instead of b * n + i
 };
 
 #ifndef MLG_R1B_MINB
@@ -673,11 +674,13 @@ __global__ void __launch_bounds__(kThreads, MLG_R1B_MINB) sage_rank1_bwd_rows_ke
     const int nb = min(32, P.B - rb0);
     const bool first = rb0 == 0;
     float g[CPL][32];
-    const float* gp = P.gz + ((size_t)rb0 * P.n + row) * P.ld_g + lane;
+    const size_t rstride = P.gz_nm ? (size_t)P.ld_g : (size_t)P.n * P.ld_g;      // replica to replica
+    const size_t rbase = (P.gz_nm ? (size_t)row * P.B + rb0 : (size_t)rb0 * P.n + row) * P.ld_g + lane;
+    const float* gp = P.gz + rbase;
 #pragma unroll
     for (int b = 0; b < 32; ++b)
 #pragma unroll
-      for (int k = 0; k < CPL; ++k) g[k][b] = b < nb ? __ldg(gp + (size_t)b * P.n * P.ld_g + 32 * k) : 0.f;
+      for (int k = 0; k < CPL; ++k) g[k][b] = b < nb ? __ldg(gp + (size_t)b * rstride + 32 * k) : 0.f;
     if (P.mbits) {   // gz arrived as dL/dy: LeakyReLU'(y) from the forward kernel's sign bits (one 8-byte word per replica)
       const unsigned long long wd = lane < nb ? __ldg(P.mbits + (size_t)row * P.B + rb0 + lane) : ~0ull;
       const unsigned lo = (unsigned)wd, hi = (unsigned)(wd >> 32);
@@ -690,14 +693,14 @@ __global__ void __launch_bounds__(kThreads, MLG_R1B_MINB) sage_rank1_bwd_rows_ke
         if (CPL == 2) g[CPL - 1][b] *= ((w >> (pos + 8)) & 1ull) ? 1.f : P.slope;
       }
     } else if (P.y) {   // gz arrived as dL/dy: multiply by LeakyReLU'(y) (y has the layout of gz); 8 replicas' y values at a time
-      const float* yp = P.y + ((size_t)rb0 * P.n + row) * P.ld_g + lane;
+      const float* yp = P.y + rbase;
 #pragma unroll
       for (int b8 = 0; b8 < 32; b8 += MLG_R1B_YB) {
         float yv[CPL][MLG_R1B_YB];
 #pragma unroll
         for (int b = 0; b < MLG_R1B_YB; ++b)
 #pragma unroll
-          for (int k = 0; k < CPL; ++k) yv[k][b] = b8 + b < nb ? __ldg(yp + (size_t)(b8 + b) * P.n * P.ld_g + 32 * k) : 1.f;
+          for (int k = 0; k < CPL; ++k) yv[k][b] = b8 + b < nb ? __ldg(yp + (size_t)(b8 + b) * rstride + 32 * k) : 1.f;
 #pragma unroll
         for (int b = 0; b < MLG_R1B_YB; ++b)
 #pragma unroll
@@ -848,19 +851,34 @@ __global__ void __launch_bounds__(kThreads, MLG_R1B_MINB) sage_rank1_bwd_rows_ke
 // writes (mlg_pool_bwd_layout) -- has no other reader.
 // ---------------------------------------------------------------------------------------------
 constexpr int NM_JU = 2;   // CSR entries in flight per lane (8 row loads)
-__global__ void __launch_bounds__(kThreads, 3)
-gather_nm_kernel(const float* __restrict__ src, const int* __restrict__ rowptr, const int* __restrict__ idx,
-                 const float* __restrict__ val, const float* __restrict__ pre, const int* __restrict__ order, int n, int B,
-                 float* __restrict__ out, unsigned ld_out, float* __restrict__ self_out, unsigned ld_self) {
+struct NmP {
+  const float* src;      // node-major rows of 32 floats, leading dimension ld_src
+  const int* rowptr;
+  const int* idx;
+  const float* val;
+  const float* pre;      // optional [n]: weight *= pre[idx]
+  const int* order;
+  const float* addend;   // optional node-major rows (leading dimension ld_add): out = addend + post * sum
+  float* out;
+  float* self_out;       // optional: the row's own src rows copied alongside
+  unsigned ld_src, ld_add, ld_out, ld_self;
+  int n, B;
+  int mean;              // post = 1 / row length (0 for an empty row) instead of 1
+  int act;               // LeakyReLU(act_slope) on the result
+  float act_slope;
+  int out_nm;            // out / self_out rows node-major as well (else graph-major: b * n + i)
+};
+__global__ void __launch_bounds__(kThreads, 3) gather_nm_kernel(const NmP P) {
   const int lane = threadIdx.x & 31;
   const int q = lane >> 3, sl = lane & 7;
+  const int B = P.B, n = P.n;
   const int halves = (B + 15) / 16;
   const long long wid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long long slot = wid / halves;
   if (slot >= n) return;
   const int b_base = (int)(wid % halves) * 16;
-  const unsigned row = order ? (unsigned)__ldg(order + slot) : (unsigned)slot;
-  const int beg = __ldg(rowptr + row), end = __ldg(rowptr + row + 1);
+  const unsigned row = P.order ? (unsigned)__ldg(P.order + slot) : (unsigned)slot;
+  const int beg = __ldg(P.rowptr + row), end = __ldg(P.rowptr + row + 1);
   int bq[4];          // this lane's replica per load, clamped for the loads (stores test the unclamped value)
 #pragma unroll
   for (int j = 0; j < 4; ++j) bq[j] = min(b_base + 4 * j + q, B - 1);
@@ -869,12 +887,12 @@ gather_nm_kernel(const float* __restrict__ src, const int* __restrict__ rowptr, 
   for (int j = 0; j < 4; ++j)
 #pragma unroll
     for (int k = 0; k < 4; ++k) acc[j][k] = 0.f;
-  const float* sc = src + sl * 4;
+  const float* sc = P.src + sl * 4;
   for (int base = beg; base < end; base += 32) {
     const int p = min(base + lane, end - 1);
-    const unsigned my_idx = (unsigned)__ldg(idx + p);
-    float my_w = val ? __ldg(val + p) : 1.f;
-    if (pre) my_w *= __ldg(pre + my_idx);
+    const unsigned my_idx = (unsigned)__ldg(P.idx + p);
+    float my_w = P.val ? __ldg(P.val + p) : 1.f;
+    if (P.pre) my_w *= __ldg(P.pre + my_idx);
     const int cnt = min(32, end - base);
     for (int e = 0; e < cnt; e += NM_JU) {
       float4 v[NM_JU][4];
@@ -884,33 +902,58 @@ gather_nm_kernel(const float* __restrict__ src, const int* __restrict__ rowptr, 
         const int ee = min(e + u, cnt - 1);
         const unsigned s = __shfl_sync(0xffffffffu, my_idx, ee);
         w[u] = (e + u < cnt) ? __shfl_sync(0xffffffffu, my_w, ee) : 0.f;
-        const float* ps = sc + (size_t)s * B * 32;
+        const float* ps = sc + (size_t)s * B * P.ld_src;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) v[u][j] = ld_gather4(ps + (size_t)bq[j] * 32);
+        for (int j = 0; j < 4; ++j) v[u][j] = ld_gather4(ps + (size_t)bq[j] * P.ld_src);
       }
 #pragma unroll
       for (int u = 0; u < NM_JU; ++u)      // entries in CSR order: one fixed sequence of FMAs per output element
+        if (u == 0 || e + u < cnt) {       // (a padded entry is not added: -0.0 / NaN safe, and the sequence gather_sum_rep runs)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          acc[j][0] = fmaf(w[u], v[u][j].x, acc[j][0]);
-          acc[j][1] = fmaf(w[u], v[u][j].y, acc[j][1]);
-          acc[j][2] = fmaf(w[u], v[u][j].z, acc[j][2]);
-          acc[j][3] = fmaf(w[u], v[u][j].w, acc[j][3]);
+          for (int j = 0; j < 4; ++j) {
+            acc[j][0] = fmaf(w[u], v[u][j].x, acc[j][0]);
+            acc[j][1] = fmaf(w[u], v[u][j].y, acc[j][1]);
+            acc[j][2] = fmaf(w[u], v[u][j].z, acc[j][2]);
+            acc[j][3] = fmaf(w[u], v[u][j].w, acc[j][3]);
+          }
         }
     }
   }
+  const float postf = P.mean ? (end > beg ? 1.f / (float)(end - beg) : 0.f) : 1.f;
   float4 t[4];
-  if (self_out) {
+  if (P.addend) {
 #pragma unroll
-    for (int j = 0; j < 4; ++j) t[j] = ld_gather4(sc + ((size_t)row * B + bq[j]) * 32);
+    for (int j = 0; j < 4; ++j) t[j] = ld_gather4(P.addend + ((size_t)row * B + bq[j]) * P.ld_add + sl * 4);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      acc[j][0] = fmaf(acc[j][0], postf, t[j].x);
+      acc[j][1] = fmaf(acc[j][1], postf, t[j].y);
+      acc[j][2] = fmaf(acc[j][2], postf, t[j].z);
+      acc[j][3] = fmaf(acc[j][3], postf, t[j].w);
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) acc[j][k] *= postf;
+  }
+  if (P.act) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) acc[j][k] = acc[j][k] > 0.f ? acc[j][k] : acc[j][k] * P.act_slope;
+  }
+  if (P.self_out) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) t[j] = ld_gather4(sc + ((size_t)row * B + bq[j]) * P.ld_src);
   }
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     const int b = b_base + 4 * j + q;
     if (b < B) {
-      const size_t orow = (size_t)b * n + row;
-      if (self_out) st4(self_out + orow * ld_self + sl * 4, t[j]);
-      st4(out + orow * ld_out + sl * 4, make_float4(acc[j][0], acc[j][1], acc[j][2], acc[j][3]));
+      const size_t orow = P.out_nm ? (size_t)row * B + b : (size_t)b * n + row;
+      if (P.self_out) st4(P.self_out + orow * P.ld_self + sl * 4, t[j]);
+      st4(P.out + orow * P.ld_out + sl * 4, make_float4(acc[j][0], acc[j][1], acc[j][2], acc[j][3]));
     }
   }
 }
@@ -1148,10 +1191,10 @@ extern "C" int mlg_sage_rank1_bwd(const float* gz, int64_t ld_g, const float* xs
 
 extern "C" int mlg_sage_rank1_bwd_rows_supported(int64_t C) { return C == 32 || C == 64; }
 
-extern "C" int mlg_sage_rank1_bwd_rows(const float* gz, int64_t ld_g, const float* y, const uint64_t* mask_bits, float slope, const float* xs, int xs_transposed, const int32_t* rowptr,
-                                       const int32_t* idx, const float* val, const int32_t* order, int64_t n_rows,
-                                       int64_t C, int64_t replicas, float* h, float* g_self, int64_t ld_self,
-                                       float* g_bias_rows, void* stream) {
+static int rank1_bwd_rows_impl(const float* gz, int64_t ld_g, const float* y, const uint64_t* mask_bits, float slope, const float* xs, int xs_transposed, const int32_t* rowptr,
+                               const int32_t* idx, const float* val, const int32_t* order, int64_t n_rows,
+                               int64_t C, int64_t replicas, float* h, float* g_self, int64_t ld_self,
+                               float* g_bias_rows, int gz_node_major, void* stream) {
   MLG_CHECK_ARG(gz && xs && rowptr && idx && h && g_self && g_bias_rows, "mlg_sage_rank1_bwd_rows: null pointer");
   MLG_CHECK_ARG(mlg_sage_rank1_bwd_rows_supported(C), "mlg_sage_rank1_bwd_rows: C=%lld (needs 32 or 64)", (long long)C);
   MLG_CHECK_ARG(n_rows >= 0 && replicas >= 1 && replicas * n_rows < (1ll << 31) && ld_g >= C && ld_self >= C,
@@ -1162,7 +1205,7 @@ extern "C" int mlg_sage_rank1_bwd_rows(const float* gz, int64_t ld_g, const floa
   P.mbits = reinterpret_cast<const unsigned long long*>(mask_bits);
   P.gz = gz; P.y = y; P.slope = slope; P.xs = xs; P.rowptr = rowptr; P.idx = idx; P.val = val; P.order = order; P.h = h; P.g_self = g_self;
   P.g_bias_rows = g_bias_rows; P.ld_g = (unsigned)ld_g; P.ld_self = (unsigned)ld_self; P.n = (int)n_rows; P.B = (int)replicas;
-  P.xs_t = xs_transposed;
+  P.xs_t = xs_transposed; P.gz_nm = gz_node_major;
   const unsigned grid = (unsigned)mlg_ceil_div(n_rows, kThreads / 32);
   cudaStream_t st = (cudaStream_t)stream;
   if (C == 64 && P.xs_t && P.B % 32 == 0) sage_rank1_bwd_rows_kernel<2, true><<<grid, kThreads, 0, st>>>(P);
@@ -1170,6 +1213,22 @@ extern "C" int mlg_sage_rank1_bwd_rows(const float* gz, int64_t ld_g, const floa
   else sage_rank1_bwd_rows_kernel<1, false><<<grid, kThreads, 0, st>>>(P);
   MLG_CHECK_LAUNCH("mlg_sage_rank1_bwd_rows");
   return MLG_OK;
+}
+
+extern "C" int mlg_sage_rank1_bwd_rows(const float* gz, int64_t ld_g, const float* y, const uint64_t* mask_bits, float slope, const float* xs, int xs_transposed, const int32_t* rowptr,
+                                       const int32_t* idx, const float* val, const int32_t* order, int64_t n_rows,
+                                       int64_t C, int64_t replicas, float* h, float* g_self, int64_t ld_self,
+                                       float* g_bias_rows, void* stream) {
+  return rank1_bwd_rows_impl(gz, ld_g, y, mask_bits, slope, xs, xs_transposed, rowptr, idx, val, order, n_rows, C, replicas, h, g_self,
+                             ld_self, g_bias_rows, 0, stream);
+}
+// gz (and y) with NODE-MAJOR rows, the layout mlg_sage_rank1_fwd_rows_nm writes
+extern "C" int mlg_sage_rank1_bwd_rows_nm(const float* gz, int64_t ld_g, const float* y, const uint64_t* mask_bits, float slope, const float* xs, int xs_transposed, const int32_t* rowptr,
+                                          const int32_t* idx, const float* val, const int32_t* order, int64_t n_rows,
+                                          int64_t C, int64_t replicas, float* h, float* g_self, int64_t ld_self,
+                                          float* g_bias_rows, void* stream) {
+  return rank1_bwd_rows_impl(gz, ld_g, y, mask_bits, slope, xs, xs_transposed, rowptr, idx, val, order, n_rows, C, replicas, h, g_self,
+                             ld_self, g_bias_rows, 1, stream);
 }
 
 extern "C" int mlg_edge_values(const float* edge_attr, const int32_t* eid, const int32_t* rowptr,
@@ -1208,21 +1267,37 @@ extern "C" int mlg_embed_scale_bwd(const float* xs, const float* g_out, int64_t 
   return MLG_OK;
 }
 
-// out[b*n + i, :32] = sum_q val_q * pre[idx_q] * src[idx_q * B + b, :32]  (src node-major, see gather_nm_kernel);
-// self_out[b*n + i, :32] = src[i * B + b, :32] (NULL ok).  The backward aggregation of a transform-first SAGE layer
-// (SAGEConv.message + mean, torch_vertex.py:279-286, on the by-source CSR) reading the gradient mlg_pool_bwd_layout wrote.
+// Replicated aggregation over node-major 32-wide rows (gather_nm_kernel):
+//   out_i(b) = act( addend_i(b) + post_i * sum_q val_q * pre[idx_q] * src[idx_q, b] ),  self_out_i(b) = src[i, b]
+// src / addend rows node-major (row of (replica b, node j) = j * replicas + b, leading dimensions ld_src / ld_add);
+// out / self_out graph-major (b * n_rows + i) or, with out_node_major, node-major too.  post_i = 1 / row length when
+// `mean`.  Forward of the transform-first SAGE layer on a node-major [U | V] (SAGEConv.message + mean + update,
+// torch_vertex.py:279-291) and its backward aggregation on the by-source CSR.
+extern "C" int mlg_gather_sum_nm_ex(const float* src, int64_t ld_src, const int32_t* rowptr, const int32_t* idx, const float* val,
+                                    const float* pre, const int32_t* order, int64_t n_rows, int64_t replicas, int mean,
+                                    const float* addend, int64_t ld_add, int act, float act_slope, float* out, int64_t ld_out,
+                                    float* self_out, int64_t ld_self, int out_node_major, void* stream) {
+  MLG_CHECK_ARG(src && rowptr && idx && out, "mlg_gather_sum_nm: null pointer");
+  MLG_CHECK_ARG(n_rows >= 0 && replicas >= 1 && replicas * n_rows < (1ll << 31), "mlg_gather_sum_nm: bad sizes");
+  MLG_CHECK_ARG(ld_src >= 32 && ld_src % 4 == 0 && ld_out >= 32 && ld_out % 4 == 0 && (!self_out || (ld_self >= 32 && ld_self % 4 == 0)) &&
+                    (!addend || (ld_add >= 32 && ld_add % 4 == 0)) &&
+                    ((uintptr_t)src | (uintptr_t)out | (uintptr_t)self_out | (uintptr_t)addend) % 16 == 0,
+                "mlg_gather_sum_nm: 32-wide rows, 16-byte aligned, leading dimensions multiples of 4");
+  if (n_rows == 0) return MLG_OK;
+  NmP P;
+  P.src = src; P.rowptr = rowptr; P.idx = idx; P.val = val; P.pre = pre; P.order = order; P.addend = addend; P.out = out;
+  P.self_out = self_out; P.ld_src = (unsigned)ld_src; P.ld_add = (unsigned)ld_add; P.ld_out = (unsigned)ld_out;
+  P.ld_self = (unsigned)ld_self; P.n = (int)n_rows; P.B = (int)replicas; P.mean = mean; P.act = act; P.act_slope = act_slope;
+  P.out_nm = out_node_major;
+  const long long warps = n_rows * ((replicas + 15) / 16);
+  gather_nm_kernel<<<(unsigned)mlg_ceil_div(warps, kThreads / 32), kThreads, 0, (cudaStream_t)stream>>>(P);
+  MLG_CHECK_LAUNCH("mlg_gather_sum_nm");
+  return MLG_OK;
+}
+
 extern "C" int mlg_gather_sum_nm(const float* src, const int32_t* rowptr, const int32_t* idx, const float* val,
                                  const float* pre, const int32_t* order, int64_t n_rows, int64_t replicas, float* out,
                                  int64_t ld_out, float* self_out, int64_t ld_self, void* stream) {
-  MLG_CHECK_ARG(src && rowptr && idx && out, "mlg_gather_sum_nm: null pointer");
-  MLG_CHECK_ARG(n_rows >= 0 && replicas >= 1 && replicas * n_rows < (1ll << 31), "mlg_gather_sum_nm: bad sizes");
-  MLG_CHECK_ARG(ld_out >= 32 && ld_out % 4 == 0 && (!self_out || (ld_self >= 32 && ld_self % 4 == 0)) &&
-                    ((uintptr_t)src | (uintptr_t)out | (uintptr_t)self_out) % 16 == 0,
-                "mlg_gather_sum_nm: 32-wide rows, 16-byte aligned, leading dimensions multiples of 4");
-  if (n_rows == 0) return MLG_OK;
-  const long long warps = n_rows * ((replicas + 15) / 16);
-  gather_nm_kernel<<<(unsigned)mlg_ceil_div(warps, kThreads / 32), kThreads, 0, (cudaStream_t)stream>>>(
-      src, rowptr, idx, val, pre, order, (int)n_rows, (int)replicas, out, (unsigned)ld_out, self_out, (unsigned)ld_self);
-  MLG_CHECK_LAUNCH("mlg_gather_sum_nm");
-  return MLG_OK;
+  return mlg_gather_sum_nm_ex(src, 32, rowptr, idx, val, pre, order, n_rows, replicas, 0, nullptr, 0, 0, 0.f, out, ld_out, self_out,
+                              ld_self, 0, stream);
 }

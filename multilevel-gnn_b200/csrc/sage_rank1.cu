@@ -35,6 +35,7 @@ struct R1F {
   unsigned ld_self, ld_nbr, ld_out;
   float slope;
   int n, B;
+  int nm;              // output rows node-major: (replica b, node i) at i * B + b instead of b * n + i
 };
 
 template <int CPL>
@@ -98,7 +99,7 @@ __device__ __forceinline__ void rank1_rows_pass(const R1F& P, unsigned row, int 
       const float z = fmaf(es[k], xb, fmaf(acc[b][k], inv, bs[k]));
       y[k] = z > 0.f ? z : z * P.slope;
     }
-    float* dst = P.out + ((size_t)(rb0 + b) * P.n + row) * P.ld_out + CPL * lane;
+    float* dst = P.out + (P.nm ? (size_t)row * P.B + rb0 + b : (size_t)(rb0 + b) * P.n + row) * P.ld_out + CPL * lane;
     if (CPL == 2) *reinterpret_cast<float2*>(dst) = make_float2(y[0], y[CPL - 1]);
     else dst[0] = y[0];
     if (CPL == 2 && P.mbits) {
@@ -193,7 +194,7 @@ __device__ __forceinline__ void rank1_rows_pass_packed(const R1F& P, unsigned ro
         const int b = 2 * j + r;
         const float y0 = z[r][0] > 0.f ? z[r][0] : z[r][0] * P.slope;
         const float y1 = z[r][1] > 0.f ? z[r][1] : z[r][1] * P.slope;
-        float* dst = P.out + ((size_t)(rb0 + b) * P.n + row) * P.ld_out + 2 * lane;
+        float* dst = P.out + (P.nm ? (size_t)row * P.B + rb0 + b : (size_t)(rb0 + b) * P.n + row) * P.ld_out + 2 * lane;
         *reinterpret_cast<float2*>(dst) = make_float2(y0, y1);
         if (P.mbits) {   // same bit layout as the scalar pass
           const unsigned b0 = __ballot_sync(0xffffffffu, y0 > 0.f), b1 = __ballot_sync(0xffffffffu, y1 > 0.f);
@@ -271,10 +272,10 @@ extern "C" int mlg_transpose_bn(const float* xs, int64_t B, int64_t n, float* xs
 
 extern "C" int mlg_sage_rank1_fwd_rows_supported(int64_t C) { return C == 32 || C == 64; }
 
-extern "C" int mlg_sage_rank1_fwd_rows(const float* xs_t, const float* e_self, int64_t ld_self, const float* e_nbr, int64_t ld_nbr,
-                                       const int32_t* rowptr, const int32_t* idx, const float* val, const int32_t* order,
-                                       int64_t n_rows, int64_t C, int64_t replicas, const float* bias, float slope, float* out,
-                                       int64_t ld_out, uint64_t* mask_bits, void* stream) {
+static int rank1_fwd_rows_impl(const float* xs_t, const float* e_self, int64_t ld_self, const float* e_nbr, int64_t ld_nbr,
+                               const int32_t* rowptr, const int32_t* idx, const float* val, const int32_t* order,
+                               int64_t n_rows, int64_t C, int64_t replicas, const float* bias, float slope, float* out,
+                               int64_t ld_out, uint64_t* mask_bits, int out_node_major, void* stream) {
   MLG_CHECK_ARG(xs_t && e_self && e_nbr && rowptr && idx && out, "mlg_sage_rank1_fwd_rows: null pointer");
   MLG_CHECK_ARG(mlg_sage_rank1_fwd_rows_supported(C), "mlg_sage_rank1_fwd_rows: C=%lld (needs 32 or 64)", (long long)C);
   MLG_CHECK_ARG(n_rows >= 0 && replicas >= 1 && replicas * n_rows < (1ll << 31) && ld_self >= C && ld_nbr >= C && ld_out >= C,
@@ -288,7 +289,7 @@ extern "C" int mlg_sage_rank1_fwd_rows(const float* xs_t, const float* e_self, i
   P.xs_t = xs_t; P.e_self = e_self; P.e_nbr = e_nbr; P.rowptr = rowptr; P.idx = idx; P.val = val; P.order = order;
   P.bias = bias; P.out = out; P.mbits = reinterpret_cast<unsigned long long*>(mask_bits);
   P.ld_self = (unsigned)ld_self; P.ld_nbr = (unsigned)ld_nbr; P.ld_out = (unsigned)ld_out; P.slope = slope;
-  P.n = (int)n_rows; P.B = (int)replicas;
+  P.n = (int)n_rows; P.B = (int)replicas; P.nm = out_node_major;
   const unsigned grid = (unsigned)mlg_ceil_div(n_rows, kThreads / 32);
   cudaStream_t st = (cudaStream_t)stream;
   // the packed-pair pass needs 16-byte aligned rows of the transposed node values (B % 4 == 0, cudaMalloc'ed xs_t)
@@ -298,4 +299,22 @@ extern "C" int mlg_sage_rank1_fwd_rows(const float* xs_t, const float* e_self, i
   else sage_rank1_fwd_rows_kernel<1, false><<<grid, kThreads, 0, st>>>(P);
   MLG_CHECK_LAUNCH("mlg_sage_rank1_fwd_rows");
   return MLG_OK;
+}
+
+extern "C" int mlg_sage_rank1_fwd_rows(const float* xs_t, const float* e_self, int64_t ld_self, const float* e_nbr, int64_t ld_nbr,
+                                       const int32_t* rowptr, const int32_t* idx, const float* val, const int32_t* order,
+                                       int64_t n_rows, int64_t C, int64_t replicas, const float* bias, float slope, float* out,
+                                       int64_t ld_out, uint64_t* mask_bits, void* stream) {
+  return rank1_fwd_rows_impl(xs_t, e_self, ld_self, e_nbr, ld_nbr, rowptr, idx, val, order, n_rows, C, replicas, bias, slope, out,
+                             ld_out, mask_bits, 0, stream);
+}
+
+// the same layer with NODE-MAJOR output rows ((replica b, node i) at i * replicas + b: a gene's replica rows are one contiguous
+// block, what the next layer's aggregation gathers per CSR entry)
+extern "C" int mlg_sage_rank1_fwd_rows_nm(const float* xs_t, const float* e_self, int64_t ld_self, const float* e_nbr,
+                                          int64_t ld_nbr, const int32_t* rowptr, const int32_t* idx, const float* val,
+                                          const int32_t* order, int64_t n_rows, int64_t C, int64_t replicas, const float* bias,
+                                          float slope, float* out, int64_t ld_out, uint64_t* mask_bits, void* stream) {
+  return rank1_fwd_rows_impl(xs_t, e_self, ld_self, e_nbr, ld_nbr, rowptr, idx, val, order, n_rows, C, replicas, bias, slope, out,
+                             ld_out, mask_bits, 1, stream);
 }

@@ -531,6 +531,7 @@ def _flag(name, default):
 FACTORED_RANK1 = True
 # SAGE layers with out_channels < in_channels evaluated transform-first (gather on the narrower rows); False: [x | agg] + GEMM
 TRANSFORM_FIRST = True
+H1_NODE_MAJOR = True     # the factored first layer writes its output node-major for a transform-first consumer (and takes its gradient so)
 GZ_NODE_MAJOR = True     # the pool writes the last layer's output gradient node-major for the transform-first backward aggregation
 # The factored first layer applies LeakyReLU'(y) to its output gradient INSIDE mlg_sage_rank1_bwd_rows, from 64 sign bits per
 # (gene, replica) its forward kernel wrote (B200: 66 us vs 61 us unmasked; re-reading the 126 MB activation instead costs
@@ -619,7 +620,8 @@ class SageLayer(torch.autograd.Function):
     The last two take their weights from mlg_sage_fold_stacked_fwd (stacked weight, both 3xTF32 splits, bias: one launch)."""
 
     @staticmethod
-    def forward(ctx, x, xs, lin_r_w, nn_w, nn_b, topo, relative, slope, in_slope=None, out_premasked=False, link=None):
+    def forward(ctx, x, xs, lin_r_w, nn_w, nn_b, topo, relative, slope, in_slope=None, out_premasked=False, link=None,
+                prod_link=None):
         """x [B*N, Cin] node features -- or, with ``xs`` [B*N] given, x = node_embedding [N, Cin] and the layer
         input is the rank-1 product xs[b,n] * x[n,:] (MultilevelGNN's first layer, never materialised).
         Activation-backward fusion across layers (set by the model, which knows the layer chain):
@@ -641,6 +643,13 @@ class SageLayer(torch.autograd.Function):
         tfirst_ok = (not factored_ok and TRANSFORM_FIRST and not rank1 and not relative and in_slope is None
                      and topo.replicas > 1 and cout < cin and cout % 4 == 0 and cin % 4 == 0
                      and n == topo.n_single * topo.replicas)
+        # layout hand-shakes (dicts the model shares between neighbouring Functions; rows node-major = (replica b, node i) at
+        # i * B + b): ``prod_link["h1_nm"]`` -- the producer wrote x node-major; ``link["want_h1_nm"]`` -- the consumer of this
+        # layer's output can take it node-major (set by the model from the consumer's static configuration)
+        x_nm = bool(prod_link is not None and prod_link.get("h1_nm"))
+        if x_nm and not (tfirst_ok and cout == 32):
+            raise RuntimeError("SageLayer: node-major input rows reached a layer call that does not run transform-first on 32-wide "
+                               "rows (model-level layout hand-shake out of sync)")
         if factored_ok or tfirst_ok:
             # Wst = [W1 ; W2 . W_r] [2cout, cin], its tf32 hi / lo split, the split of Wst^T and the bias [b | 0]: one launch
             sb = torch.empty(5 * 2 * cout * cin + 2 * cout, dtype=torch.float32, device=xd.device)
@@ -682,6 +691,9 @@ class SageLayer(torch.autograd.Function):
                 mbits = torch.empty(n1 * topo.replicas, dtype=torch.int64, device=xd.device)
             rows_ok = RANK1_FWD_ROWS and bool(L.mlg_sage_rank1_fwd_rows_supported(cout))
             xs_t = None
+            h1_nm = bool(H1_NODE_MAJOR and rows_ok and link is not None and link.get("want_h1_nm")
+                         and bool(L.mlg_sage_rank1_bwd_rows_supported(cout)) and FACTORED_RANK1 != "gather")
+            fwd_rows = L.mlg_sage_rank1_fwd_rows_nm if h1_nm else L.mlg_sage_rank1_fwd_rows
             with torch.cuda.device(xd.device):
                 if rows_ok:
                     # node values transposed to [n1, B]: one coalesced load per CSR entry in the forward AND the backward kernel
@@ -690,7 +702,7 @@ class SageLayer(torch.autograd.Function):
                                 "mlg_transpose_bn")
                 with _cabi.span("sage_rank1_fwd", nbytes):
                     if rows_ok:
-                        _cabi.check(L.mlg_sage_rank1_fwd_rows(
+                        _cabi.check(fwd_rows(
                             _cabi.fptr(xs_t), _vptr(e12), 2 * cout, _vptr(e12[:, cout:]), 2 * cout, _cabi.iptr(csr.rowptr),
                             _cabi.iptr(csr.col), _cabi.fptr(topo.fwd_val, True),
                             _cabi.iptr(topo.fwd_order, True), n1, cout, topo.replicas,
@@ -705,6 +717,9 @@ class SageLayer(torch.autograd.Function):
                             _cabi.stream_ptr()), "mlg_sage_rank1_fwd")
             ctx.xs_t = xs_t
             ctx.mbits = mbits
+            ctx.h1_nm = h1_nm
+            if h1_nm:
+                link["h1_nm"] = True          # y (and the gradient this layer gets back) is node-major
             ctx.save_for_backward(xd, y, wst, w_r, w_nn, xs_d)
             ctx.topo, ctx.relative, ctx.slope, ctx.cin, ctx.has_bias = topo, False, float(slope), cin, nn_b is not None
             ctx.rank1, ctx.factored, ctx.transform_first = True, True, False
@@ -719,9 +734,19 @@ class SageLayer(torch.autograd.Function):
             # cin-wide ones, forward and backward, and no [x | agg] buffer is written.
             uv = tall_matmul(xd, wst, bias2, tag="sage_update_gemm", w_split=wst_split)     # [n, 2cout] = [U | V]
             csr = topo.fwd
-            y = gather_sum(uv[:, cout:], csr.rowptr, csr.col, topo.n_single, val=topo.fwd_val, post_mode=1,
-                           addend=uv[:, :cout], replicas=topo.replicas, order=topo.fwd_order,
-                           tag="sage_aggr_fwd", act_slope=slope)
+            if x_nm:
+                # x came node-major, so [U | V] is: one contiguous block of V rows per CSR entry; y goes out graph-major
+                y = torch.empty(n, cout, dtype=torch.float32, device=xd.device)
+                with torch.cuda.device(xd.device), _cabi.span("sage_aggr_fwd", 4 * cout * n * 2 + 8 * csr.col.numel()):
+                    _cabi.check(_cabi.lib().mlg_gather_sum_nm_ex(
+                        _vptr(uv[:, cout:]), 2 * cout, _cabi.iptr(csr.rowptr), _cabi.iptr(csr.col), _cabi.fptr(topo.fwd_val, True),
+                        None, _cabi.iptr(topo.fwd_order, True), topo.n_single, topo.replicas, 1, _cabi.fptr(uv), 2 * cout, 1,
+                        float(slope), _cabi.fptr(y), cout, None, 0, 0, _cabi.stream_ptr()), "mlg_gather_sum_nm_ex")
+            else:
+                y = gather_sum(uv[:, cout:], csr.rowptr, csr.col, topo.n_single, val=topo.fwd_val, post_mode=1,
+                               addend=uv[:, :cout], replicas=topo.replicas, order=topo.fwd_order,
+                               tag="sage_aggr_fwd", act_slope=slope)
+            ctx.x_nm = x_nm
             ctx.save_for_backward(xd, y, wst, w_r, w_nn, None)
             ctx.topo, ctx.relative, ctx.slope, ctx.cin, ctx.has_bias = topo, False, float(slope), cin, nn_b is not None
             ctx.rank1, ctx.transform_first, ctx.emb_param, ctx.in_slope = False, True, None, None
@@ -780,7 +805,8 @@ class SageLayer(torch.autograd.Function):
             nbytes = 4 * cout * gz.shape[0] + 4 * gz.shape[0] + 8 * fw.col.numel() + 4 * (h.numel() + 2 * gbr.numel())
             with torch.cuda.device(gz.device), _cabi.span("sage_rank1_bwd", nbytes):
                 xs_t = getattr(ctx, "xs_t", None)
-                _cabi.check(L.mlg_sage_rank1_bwd_rows(
+                bwd_rows = L.mlg_sage_rank1_bwd_rows_nm if getattr(ctx, "h1_nm", False) else L.mlg_sage_rank1_bwd_rows
+                _cabi.check(bwd_rows(
                     _cabi.fptr(gz), cout, _cabi.fptr(y_mask, True),
                     _cabi.lptr(bits, True), float(ctx.slope),
                     _cabi.fptr(xs_d if xs_t is None else xs_t), 0 if xs_t is None else 1, _cabi.iptr(fw.rowptr),
@@ -827,7 +853,7 @@ class SageLayer(torch.autograd.Function):
             fk.hold(g_wst, g_wnn, g_wr)
         slot = grad_slot(ctx.emb_param, (n1, cin)) if ctx.emb_param is not None else None
         g_emb = tall_matmul(g12, wst.t(), tag="sage_rank1_demb", w_split=ctx.wst_t_split, out=slot)     # g12 @ Wst
-        return g_emb, None, g_wr, g_wnn, g_b, None, None, None, None, None, None
+        return g_emb, None, g_wr, g_wnn, g_b, None, None, None, None, None, None, None
 
     @staticmethod
     def _backward_transform_first(ctx, gy):
@@ -846,14 +872,20 @@ class SageLayer(torch.autograd.Function):
         # G = [g_U | g_V] = [gz | A^T gz]: the by-source aggregation runs on the cout-wide gz rows and copies them alongside
         g_uv = torch.empty(n, 2 * cout, dtype=torch.float32, device=gz.device)
         link = getattr(ctx, "link", None)
-        if link is not None and link.pop("gz_written_node_major", False):
-            # the pool wrote gz node-major: every load instruction of the aggregation reads 512 contiguous bytes
+        gz_nm = bool(link is not None and link.pop("gz_written_node_major", False))
+        x_nm = bool(getattr(ctx, "x_nm", False))
+        if x_nm and not gz_nm:      # x (and so g_uv) node-major but the gradient arrived graph-major: one transposing copy
+            gz = gz.view(topo.replicas, topo.n_single, cout).transpose(0, 1).contiguous().view(n, cout)
+            gz_nm = True
+        if gz_nm:
+            # gz node-major (written so by the pool): every load instruction of the aggregation reads 512 contiguous bytes;
+            # g_uv in the row order of x
             with torch.cuda.device(gz.device), _cabi.span("sage_aggr_bwd", 4 * cout * n * 2 + 8 * bw.col.numel()):
-                _cabi.check(L.mlg_gather_sum_nm(_cabi.fptr(gz), _cabi.iptr(bw.rowptr), _cabi.iptr(bw.col),
-                                                _cabi.fptr(topo.bwd_val, True), _cabi.fptr(topo.inv_cnt, True),
-                                                _cabi.iptr(topo.bwd_order, True), topo.n_single, topo.replicas,
-                                                _vptr(g_uv[:, cout:]), 2 * cout, _vptr(g_uv), 2 * cout, _cabi.stream_ptr()),
-                            "mlg_gather_sum_nm")
+                _cabi.check(L.mlg_gather_sum_nm_ex(_cabi.fptr(gz), cout, _cabi.iptr(bw.rowptr), _cabi.iptr(bw.col),
+                                                   _cabi.fptr(topo.bwd_val, True), _cabi.fptr(topo.inv_cnt, True),
+                                                   _cabi.iptr(topo.bwd_order, True), topo.n_single, topo.replicas, 0, None, 0, 0,
+                                                   0.0, _vptr(g_uv[:, cout:]), 2 * cout, _vptr(g_uv), 2 * cout,
+                                                   1 if x_nm else 0, _cabi.stream_ptr()), "mlg_gather_sum_nm_ex")
         else:
             gather_sum(gz, bw.rowptr, bw.col, topo.n_single, val=topo.bwd_val, pre=topo.inv_cnt, out=g_uv[:, cout:],
                        self_out=g_uv[:, :cout], replicas=topo.replicas, order=topo.bwd_order,
@@ -885,7 +917,7 @@ class SageLayer(torch.autograd.Function):
                 fk.hold(o2, g_wnn, g_wr, g_b)
         if needs[0]:
             gx = tall_matmul(g_uv, wst.t(), tag="sage_dgrad_gemm", w_split=ctx.wst_t_split)     # dL/dx (the producer masks it itself)
-        return gx, None, g_wr, g_wnn, (g_b if ctx.has_bias else None), None, None, None, None, None, None
+        return gx, None, g_wr, g_wnn, (g_b if ctx.has_bias else None), None, None, None, None, None, None, None
 
     @staticmethod
     def backward(ctx, gy):
@@ -928,7 +960,7 @@ class SageLayer(torch.autograd.Function):
                     g_emb = torch.sum(part.view(-1, n1, cin), 0, out=slot) if slot is not None else part.view(-1, n1, cin).sum(0)
                 else:
                     g_emb = part
-                return g_emb, None, g_wr, g_wnn, (g_b if ctx.has_bias else None), None, None, None, None, None, None
+                return g_emb, None, g_wr, g_wnn, (g_b if ctx.has_bias else None), None, None, None, None, None, None, None
             gx = gather_sum(gxcat[:, cin:], bw.rowptr, bw.col, topo.n_single, val=topo.bwd_val, pre=topo.inv_cnt,
                             addend=gxcat[:, :cin], replicas=topo.replicas, order=topo.bwd_order, tag="sage_aggr_bwd",
                             mask=None if ctx.in_slope is None else xcat[:, :cin],
@@ -944,7 +976,7 @@ class SageLayer(torch.autograd.Function):
                     _cabi.check(L.mlg_embed_scale_bwd(_cabi.fptr(xs_d), _cabi.fptr(gx), topo.replicas, n1, cin,
                                                       _cabi.fptr(g_emb), _cabi.stream_ptr()), "mlg_embed_scale_bwd")
                 gx = g_emb
-        return gx, None, g_wr, g_wnn, (g_b if ctx.has_bias else None), None, None, None, None, None, None
+        return gx, None, g_wr, g_wnn, (g_b if ctx.has_bias else None), None, None, None, None, None, None, None
 
 
 class RankOne:

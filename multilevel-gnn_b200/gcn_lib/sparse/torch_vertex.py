@@ -173,7 +173,8 @@ class SAGEConv(nn.Module):
         # cross-layer activation-backward fusion requested by the model for THIS call (see Fn.SageLayer.forward)
         fuse = getattr(self, "_mlg_fuse", (None, False))
         in_slope, out_premasked = fuse[0], fuse[1]
-        link = fuse[2] if len(fuse) > 2 else None      # dict shared with the pool that consumes this layer's output
+        link = fuse[2] if len(fuse) > 2 else None      # dict shared with the consumer of this layer's output (next layer / pool)
+        prod_link = fuse[3] if len(fuse) > 3 else None # dict shared with the producer of this layer's input
         self._mlg_fuse = (None, False)
         n_total = x.shape[0]
         topo = graph.topology(edge_index, n_total, self_loops=True, edge_weight=edge_attr)
@@ -182,13 +183,17 @@ class SAGEConv(nn.Module):
             if slope is not None and topo.replicas > 1 and topo.n_single == x.emb.shape[0]:
                 lin = self.nn[0]
                 return Fn.SageLayer.apply(x.emb, x.xs, self.lin_r.weight, lin.weight, lin.bias, topo, self.relative, slope,
-                                          None, out_premasked)
+                                          None, out_premasked, link, None)
             x = x.materialize()
         x = x.unsqueeze(-1) if x.dim() == 1 else x
+        if prod_link is not None and prod_link.get("h1_nm") and slope is None:
+            # the producer wrote its rows node-major for a fused consumer, and this call is not fused: back to graph-major
+            x = x.view(topo.n_single, -1, x.shape[-1]).transpose(0, 1).reshape(n_total, x.shape[-1])
+            prod_link["h1_nm"] = False
         if slope is not None:
             lin = self.nn[0]
             return Fn.SageLayer.apply(x, None, self.lin_r.weight, lin.weight, lin.bias, topo, self.relative, slope,
-                                      in_slope, out_premasked, link)
+                                      in_slope, out_premasked, link, prod_link)
         agg_x = Fn.SageAggregate.apply(x, topo, self.relative)
         agg = F.linear(agg_x, self.lin_r.weight)
         return self.update(agg, x)

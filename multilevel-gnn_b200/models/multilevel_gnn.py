@@ -160,7 +160,7 @@ class MultilevelGNN(nn.Module):
             and not args.repeat_mask and torch.is_grad_enabled()
         slopes = [getattr(l, "grad_fusion_slope", lambda: None)() if plain else None for l in self.gnn_model]
         pool_masks = plain and slopes[-1] is not None and (not (args.value_att_mask and value_mask) or args.merge_mode == 'mult')
-        pool_link = {}
+        pool_link, layer_links = {}, {}
         for i, layer in enumerate(self.gnn_model):
             if plain and slopes[i] is not None:
                 masks = lambda l: getattr(l, "masks_input_grad", lambda: not getattr(l, "relative", True))()
@@ -170,7 +170,12 @@ class MultilevelGNN(nn.Module):
                 # last layer + pool: a dict both Functions see, through which they agree on the layout of the gradient the
                 # pool's backward hands to the layer's backward (Fn.SageLayer / Fn.PathwayPool, ``gz_node_major``)
                 link = pool_link if (i + 1 == n_layers and consumer_masks) else None
-                layer._mlg_fuse = (slopes[i - 1] if producer_masked else None, bool(consumer_masks), link)
+                if (i + 1 != n_layers and self._takes_node_major(self.gnn_model[i + 1], slopes[i + 1])
+                        and not self._hooked(layer) and not self._hooked(self.gnn_model[i + 1])):
+                    # layer -> layer: the next layer runs transform-first on 32-wide rows; this one may hand it NODE-MAJOR rows
+                    link = layer_links[i] = {"want_h1_nm": True}
+                layer._mlg_fuse = (slopes[i - 1] if producer_masked else None, bool(consumer_masks), link,
+                                   layer_links.get(i - 1))
             y = layer(x, edge_index, edge_attr)
             if args.dense_gnn:
                 x = y
@@ -200,6 +205,21 @@ class MultilevelGNN(nn.Module):
         x = Fn.PathwayPool.apply(x, self.learnable_pca_params, vm, layout, slopes[-1] if pool_masks else None,
                                  self.info_mask, pool_link if pool_masks else None)   # [B, C, 438, P]
         return x
+
+    @staticmethod
+    def _hooked(layer):
+        """A forward (pre-)hook sees the layer's input / output rows: they must then be in the reference's graph-major order."""
+        mods = [layer, getattr(layer, "gconv", layer)]
+        return any(m._forward_hooks or m._forward_pre_hooks for m in mods)
+
+    @staticmethod
+    def _takes_node_major(layer, slope):
+        """Static part of the layer-to-layer layout hand-shake (Fn.SageLayer): the consumer is a fused, non-relative SAGE layer
+        that will run transform-first with 32 output channels (the node-major aggregation kernel's row width)."""
+        conv = getattr(layer, "gconv", layer)
+        return (slope is not None and Fn.TRANSFORM_FIRST and Fn.H1_NODE_MAJOR and getattr(conv, "relative", True) is False
+                and getattr(conv, "out_channels", 0) == 32 and getattr(conv, "in_channels", 0) > 32
+                and getattr(conv, "in_channels", 0) % 4 == 0)
 
     def forward(self, input_batch, x=None, gene_pca_match=None, raw_indice=None, age=None, require_grad=True,
                 _loss_args=None):

@@ -849,6 +849,66 @@ def test_factored_first_layer_is_equivalent(mlg):
                                    rtol=1e-4, atol=2e-6, l2=1e-4, outliers=1e-4)
 
 
+def test_node_major_activation_is_equivalent(mlg):
+    """Layer-to-layer layout hand-shake (Fn.H1_NODE_MAJOR): the factored first layer writes its activation node-major
+    (mlg_sage_rank1_fwd_rows_nm), the transform-first second layer aggregates contiguous blocks (mlg_gather_sum_nm_ex) and
+    hands a node-major gradient back (mlg_sage_rank1_bwd_rows_nm).  Prediction, pooled features and every parameter
+    gradient against the graph-major path, at 5 and at 40 graphs (two replica passes in the first-layer kernels); with a
+    forward hook on a layer the hand-shake must stay off (the hook sees the reference's row order)."""
+    from multilevel_gnn_b200 import _cabi, configs, functional as Fn, synth
+    for cfg, bsz in (("gbm", 5), ("kirc", 5), ("gbm", 40)):
+        args = configs.make_args(cfg)
+        torch.manual_seed(3)
+        model = mlg.MultilevelGNN(args)
+        synth.multilevel_params(model)
+        model.to(DEV).train()
+        model.pathway_indexs = model.pathway_indexs.to(DEV)
+        b = synth.multilevel_batch(batch_size=bsz, seed=6).to(DEV)
+        params = [p for n, p in model.named_parameters() if p.requires_grad and not n.endswith("lin_l.weight")]
+        names = [n for n, p in model.named_parameters() if p.requires_grad and not n.endswith("lin_l.weight")]
+
+        def run(nm):
+            default = Fn.H1_NODE_MAJOR
+            Fn.H1_NODE_MAJOR = nm
+            torch.manual_seed(11)                     # same dropout masks
+            try:
+                pred, feat = model(b)
+                loss = (pred * torch.arange(pred.numel(), device=DEV).reshape(pred.shape)).sum() + feat.square().mean()
+                g = torch.autograd.grad(loss, params, allow_unused=True)
+                torch.cuda.synchronize()
+            finally:
+                Fn.H1_NODE_MAJOR = default
+            return pred.detach(), feat.detach(), g
+
+        p0, f0, g0 = run(False)
+        p1, f1, g1 = run(True)
+        assert_close(p1, p0, rtol=1e-5, atol=1e-6, what="node-major vs graph-major pred")
+        assert_close(f1, f0, rtol=1e-4, atol=1e-6, what="node-major vs graph-major pooled features")
+        for n, a, c in zip(names, g1, g0):
+            if a is None or c is None:
+                assert a is None and c is None
+                continue
+            sc = float(c.abs().max().clamp_min(1e-30))
+            # atol: the layer-2 weight gradient is a 3xTF32 sum over B*N rows taken in ANOTHER row order (accurate to ~4e-6 of
+            # sum |g||x|, DESIGN section 2): 1e-5 of the largest entry at 616 k rows
+            assert_close_flips(a / sc, c / sc, "node-major vs graph-major grad %s (%s, B=%d)" % (n, cfg, bsz),
+                               rtol=1e-4, atol=2e-5, l2=1e-4, outliers=1e-4)
+        # a hooked layer keeps the reference's row order
+        rows = []
+        h = model.gnn_model[0].register_forward_hook(lambda m, i, o: rows.append(o.detach().clone()))
+        try:
+            Fn.H1_NODE_MAJOR = True
+            torch.manual_seed(11)
+            model(b)
+            Fn.H1_NODE_MAJOR = False
+            torch.manual_seed(11)
+            model(b)
+        finally:
+            Fn.H1_NODE_MAJOR = True
+            h.remove()
+        assert torch.equal(rows[0], rows[1])
+
+
 def test_maxpool_channel_last_matches_torch(mlg):
     """mlg_maxpool_cl_fwd/bwd vs nn.MaxPool2d on the head's shape and on ragged ones (floor mode drops the tail rows /
     columns); ties (quantised values) must route the gradient to the first maximum like ATen."""

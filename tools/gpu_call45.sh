@@ -17,6 +17,6 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 1600 --csv --log-fi
     python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-diffpool --no-genconv --no-strong > gpurun_out/r02_ncu_launches8.log 2>&1
 echo "launch list rc=$?"
 ncu --set full --clock-control none --import-source on \
-    -k regex:'gather_sum_rep|gather_nm|pool_bwd_c32' \
-    -s 6 -c 6 -o /tmp/r02_step_nm python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-diffpool --no-genconv --no-strong > gpurun_out/r02_ncu_full_nm.log 2>&1
+    -k regex:'gather_nm|sage_rank1_fwd_rows|sage_rank1_bwd_rows' \
+    -s 8 -c 8 -o /tmp/r02_step_nm python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-diffpool --no-genconv --no-strong > gpurun_out/r02_ncu_full_nm.log 2>&1
 echo "ncu full rc=$?"; export_rep /tmp/r02_step_nm r02_step_nm
