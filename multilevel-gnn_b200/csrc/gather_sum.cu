@@ -846,9 +846,10 @@ __global__ void __launch_bounds__(kThreads, MLG_R1B_MINB) sage_rank1_bwd_rows_ke
 // output row for 16 replicas: lane (q, sl) = (lane / 8, lane % 8) covers bytes 16 * sl of replica 4 j + q, so every load
 // instruction of the warp reads 512 contiguous bytes and an entry's four loads 2 KB (gather_sum_rep_kernel<8, 4>: four
 // 128-byte rows of four unrelated nodes per instruction; the same bytes through L2, at a coarser request granularity).
-// out / self_out stay graph-major (row b * n + i): they feed the row-wise GEMMs next to the activations of the forward pass.
-// Used for the backward aggregation of the transform-first SAGE layer, whose source -- the gradient the pool backward
-// writes (mlg_pool_bwd_layout) -- has no other reader.
+// Both aggregations of the transform-first SAGE layer run here when the model hands it node-major rows: forward on the V half
+// of the node-major [U | V] GEMM output (addend U, mean, LeakyReLU; its OUTPUT graph-major for the pool and the caller),
+// backward on the gradient the pool backward writes node-major (mlg_pool_bwd_layout), out / self_out = [g_U | g_V] in the row
+// order of the layer's input.
 // ---------------------------------------------------------------------------------------------
 constexpr int NM_JU = 2;   // CSR entries in flight per lane (8 row loads)
 struct NmP {
